@@ -1,0 +1,173 @@
+"""The oracle (oracle/*.py, numpy restatement) against fixtures produced by executing the reference
+files themselves (oracle/gen_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+from conftest import assert_close, golden, load
+from oracle import gwd as ogwd
+from oracle import representations as orep
+
+
+def ids(cases):
+    return [c[0] for c in cases]
+
+
+ERGO = golden("ergo12_n*")
+
+
+@pytest.mark.parametrize("name,path", ERGO, ids=ids(ERGO))
+def test_ergo12(name, path):
+    g = load(path)
+    with np.errstate(all="ignore"):
+        out = orep.ergo12(g["x"], g["y"], g["t"], g["p"], int(g["H"]), int(g["W"]))
+    assert_close(out, g["out"], rtol=1e-12, atol=1e-15, what=name)
+
+
+def test_ergo12_gen1_50k():
+    g = load(golden("ergo12_gen1_50k")[0][1])
+    out = orep.ergo12(g["x"], g["y"], g["t"], g["p"], 240, 304)
+    assert_close(out.astype(np.float32), g["out"], rtol=1e-6, atol=1e-12, what="gen1")
+    # integer-valued channels are bit exact: polarity sum (3), count sum (5), count means (2,4,7,11)
+    for c in (2, 3, 4, 5, 7, 11):
+        assert np.array_equal(out[:, :, c].astype(np.float32), g["out"][:, :, c])
+
+
+def test_ergo12_f8_seconds():
+    """n_imagenet structured f8 input with t in seconds: .astype(int64) truncation."""
+    g = load(golden("ergo12_f8_seconds")[0][1])
+    with np.errstate(all="ignore"):
+        out = orep.ergo12(g["x"], g["y"], g["t_seconds"].astype(np.int64), g["p"], 30, 40)
+    assert_close(out, g["out"], rtol=1e-12, atol=1e-15)
+
+
+MDES = golden("mdes_*")
+
+
+@pytest.mark.parametrize("name,path", MDES, ids=ids(MDES))
+def test_mixed_density_generic(name, path):
+    g = load(path)
+    with np.errstate(all="ignore"):
+        out = orep.mixed_density_event_stack(g["x"], g["y"], g["t"], g["p"], int(g["H"]), int(g["W"]),
+                                             g["win"].tolist(), g["func"].tolist(), g["agg"].tolist(), str(g["stacking"]))
+    assert_close(out, g["out"], rtol=1e-12, atol=1e-15, what=name)
+
+
+ES = golden("eventstack_*")
+
+
+@pytest.mark.parametrize("name,path", ES, ids=ids(ES))
+def test_event_stack(name, path):
+    g = load(path)
+    out = orep.event_stack(g["x"], g["y"], g["t"], (g["p"].astype(np.int32) + 1) // 2, int(g["H"]), int(g["W"]), 12)
+    assert out.dtype == g["out"].dtype == np.float32
+    assert np.array_equal(out, g["out"]), name  # integer valued: bit exact
+
+
+TS = golden("timesurface_*")
+
+
+@pytest.mark.parametrize("name,path", TS, ids=ids(TS))
+def test_time_surface(name, path):
+    g = load(path)
+    p01 = ((g["p"].astype(np.int32) + 1) / 2).astype(np.int8)
+    with np.errstate(all="ignore"):
+        idx = orep.time_surface_indices(g["t"].astype(np.int32), 6)
+    assert np.array_equal(idx, g["indices"])
+    out = orep.time_surface(g["x"], g["y"], g["t"], p01, idx, int(g["H"]), int(g["W"]), tau=50000)
+    assert_close(out, g["out"], rtol=1e-13, atol=0, what=name)
+
+
+TG = golden("tore_gen1_*")
+
+
+@pytest.mark.parametrize("name,path", TG, ids=ids(TG))
+def test_tore_gen1(name, path):
+    g = load(path)
+    out = orep.tore_gen1(g["x"].astype(np.int32), g["y"].astype(np.int32), g["t"].astype(np.int32), g["p"].astype(np.int32), 6)
+    assert out.dtype == np.float32 and out.shape == g["out"].shape
+    assert_close(out, g["out"], rtol=3e-7, atol=0, what=name)
+
+
+TF = golden("tore_fixed_*")
+
+
+@pytest.mark.parametrize("name,path", TF, ids=ids(TF))
+def test_tore_fixed(name, path):
+    g = load(path)
+    t = g["t"].astype(np.int32)
+    out = orep.tore(g["x"].astype(np.int32) + 1, g["y"].astype(np.int32) + 1, t, g["p"].astype(np.int32), t[-1], int(g["k"]),
+                    (int(g["H"]), int(g["W"])))
+    assert_close(out, g["out"], rtol=3e-7, atol=0, what=name)
+
+
+VT = golden("voxel_tonic_*")
+
+
+@pytest.mark.parametrize("name,path", VT, ids=ids(VT))
+def test_voxel_tonic(name, path):
+    g = load(path)
+    with np.errstate(all="ignore"):
+        out = orep.voxel_tonic(g["x"], g["y"], g["t"].astype(np.int32), g["p"].astype(np.int32), int(g["H"]), int(g["W"]), 12)
+    assert_close(out[:, None], g["out"], rtol=1e-12, atol=1e-15, what=name)
+
+
+VE = golden("voxel_evlicious_*")
+
+
+@pytest.mark.parametrize("name,path", VE, ids=ids(VE))
+def test_voxel_evlicious(name, path):
+    g = load(path)
+    out = orep.voxel_evlicious(g["x"], g["y"], g["t"], g["p"], int(g["H"]), int(g["W"]), int(g["bins"]), bool(g["normalize"]))
+    assert out.dtype == np.float32
+    if not bool(g["normalize"]):
+        assert np.array_equal(out, g["out"])
+    else:
+        assert_close(out, g["out"], rtol=1e-6, atol=1e-7, what=name)
+
+
+def test_voxel_gwd():
+    g = load(golden("voxel_gwd_small")[0][1])
+    out = orep.voxel_gwd(g["x"].astype(int), g["y"].astype(int), g["t01"], g["p"].astype(float), 40, 30, 5)
+    assert_close(out, g["out"], rtol=1e-12, atol=1e-15)
+
+
+def test_dispatch_branches():
+    """get_item_transform (gen1_transforms.py:12-89) outputs, including the x255."""
+    G = {n[len("dispatch_"):]: load(p) for n, p in golden("dispatch_*")}
+    g = G["MixedDensityEventStack"]
+    x, y, t, p, H, W = g["x"], g["y"], g["t"], g["p"], int(g["H"]), int(g["W"])
+    assert_close(orep.ergo12(x, y, t, p, H, W) * 255, g["out"], rtol=1e-12, atol=1e-12)
+    assert np.array_equal(orep.event_stack(x, y, t, (p.astype(int) + 1) // 2, H, W) * 255, G["EventStack"]["out"])
+    assert_close(orep.time_surface_gen1(x, y, t.astype(np.int32), p, H, W) * 255, G["ToTimesurface"]["out"], rtol=1e-13)
+    assert_close(orep.tore_gen1(x.astype(np.int32), y.astype(np.int32), t.astype(np.int32), p.astype(np.int32)) * 255,
+                 G["tore"]["out"], rtol=3e-7)
+    vt = orep.voxel_tonic(x, y, t.astype(np.int32), p.astype(np.int32), H, W, 12).transpose(1, 2, 0) * 255
+    assert_close(vt, G["ToVoxelGrid"]["out"], rtol=1e-12, atol=1e-12)
+    img = orep.to_image(x, y, (p.astype(np.int32) + 1) // 2, H, W).transpose(1, 2, 0)
+    img *= 255
+    assert np.array_equal(img, G["ToImage"]["out"])
+
+
+GA = golden("gwd_a_pair_*")
+
+
+@pytest.mark.parametrize("name,path", GA, ids=ids(GA))
+def test_gwd_a_pair(name, path):
+    g = load(path)
+    assert_close(ogwd.gwd_a_cost(g["Xs"], g["Xt"], float(g["h"])), g["out"], rtol=1e-9, what=name)
+
+
+def test_otmi():
+    g = load(golden("otmi_small")[0][1])
+    ev = np.stack([g["x"], g["y"], g["t"], g["p"]], 1).astype(np.int32)
+    c = ogwd.otmi(ev, g["rep"].astype(np.float64), int(g["H"]), int(g["W"]), int(g["rep_size"]))
+    assert_close(c, g["out"], rtol=1e-6, what="otmi")
+
+
+def test_window_bounds():
+    for n in [0, 1, 2, 3, 7, 8, 9, 1000, 50000, 999999]:
+        b = orep.sbn_window_bounds(n)
+        assert b[0] == (0, n) and b[3][1] == 3 * (n // 3)
+        assert b[4][0] == n // 2 and b[5][0] == n // 2 + n // 4 and b[6][0] == n // 2 + n // 4 + n // 8
+        s = orep.event_stack_starts(n, 12)
+        assert s[0] == 0 and all(s[i] <= s[i + 1] <= n for i in range(11))
