@@ -1,0 +1,259 @@
+"""Batched engine API: many event windows -> dense tensors in one call per representation.
+
+This is the call the B200 engine is built around: the caller collates raw events of B
+windows into CSR-packed SoA arrays (`EventBatch`), already on the GPU or uploaded once, and each function
+below enqueues the kernels of libevrep.so on the current CUDA stream and returns a CUDA tensor in the
+layout the reference produces for one window, with a leading batch axis.  The per-window classes in
+`event_representation_study_b200.representations` are thin wrappers over these functions.
+
+Nothing here computes on the CPU; without a CUDA device or without the built library every call raises.
+"""
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import AGGS, FUNCS, STACKING, check, lib
+
+ERGO12_V2 = (
+    [0, 3, 2, 6, 5, 6, 2, 5, 1, 0, 4, 1],
+    ["polarity", "timestamp_neg", "count_neg", "polarity", "count_pos", "count", "timestamp_pos", "count_neg",
+     "timestamp_neg", "timestamp_pos", "timestamp", "count"],
+    ["variance", "variance", "mean", "sum", "mean", "sum", "mean", "mean", "max", "max", "max", "mean"],
+)  # representations/optimized_representation.py:86-115
+ERGO12_V1 = (
+    [0, 2, 2, 3, 5, 0, 0, 4, 2, 6, 1, 1],
+    ["timestamp", "timestamp_pos", "timestamp_neg", "count_neg", "count_pos", "polarity", "timestamp", "count",
+     "timestamp_pos", "count", "timestamp_pos", "timestamp_neg"],
+    ["max", "sum", "mean", "sum", "mean", "variance", "variance", "sum", "mean", "sum", "sum", "sum"],
+)  # representations/optimized_representation.py:16-66 (commented-out first version)
+
+
+@dataclass
+class EventBatch:
+    """CSR-packed SoA events of B windows.  x, y: uint16 values (torch.uint16 or int16 storage); t: int32 or
+    int64 microseconds; p: int8 in {-1, 0, +1}; all CUDA, contiguous, same length.  offsets: host int64
+    numpy array of B+1 entries; window b is [offsets[b], offsets[b+1]).  Events of a window are in stream
+    order (time sorted), as every loader of the reference delivers them."""
+    x: torch.Tensor
+    y: torch.Tensor
+    t: torch.Tensor
+    p: torch.Tensor
+    offsets: np.ndarray
+
+    def __post_init__(self):
+        self.offsets = np.ascontiguousarray(np.asarray(self.offsets, dtype=np.int64))
+        n = int(self.offsets[-1]) if len(self.offsets) else 0
+        for name, ok in (("x", (torch.uint16, torch.int16)), ("y", (torch.uint16, torch.int16)),
+                         ("t", (torch.int32, torch.int64)), ("p", (torch.int8,))):
+            v = getattr(self, name)
+            if not v.is_cuda:
+                raise ValueError(f"EventBatch.{name} must be a CUDA tensor (there is no CPU path)")
+            if v.dtype not in ok:
+                raise TypeError(f"EventBatch.{name} has dtype {v.dtype}, expected one of {ok}")
+            if not v.is_contiguous() or v.dim() != 1:
+                raise ValueError(f"EventBatch.{name} must be 1-D contiguous")
+            if v.numel() < n:
+                raise ValueError(f"EventBatch.{name} has {v.numel()} elements, offsets need {n}")
+        if len(self.offsets) < 1 or np.any(np.diff(self.offsets) < 0) or (len(self.offsets) and self.offsets[0] < 0):
+            raise ValueError("offsets must be non-decreasing and non-negative")
+
+    @property
+    def B(self):
+        return len(self.offsets) - 1
+
+    @property
+    def device(self):
+        return self.x.device
+
+    @property
+    def total(self):
+        return int(self.offsets[-1])
+
+
+def pack_events(windows, device="cuda", t_dtype=np.int32, pin=False):
+    """List of windows -> EventBatch on `device` (one host->device copy per field).
+    A window is a dict / structured array with fields x, y, t, p (any integer dtypes)."""
+    offs = np.zeros(len(windows) + 1, np.int64)
+    offs[1:] = np.cumsum([len(w["x"]) for w in windows])
+
+    def cat(k, dt):
+        if not windows:
+            return np.zeros(0, dt)
+        return np.concatenate([np.asarray(w[k]).astype(dt, copy=False) for w in windows])
+
+    def up(a):
+        h = torch.from_numpy(a)
+        if pin:
+            h = h.pin_memory()
+        return h.to(device, non_blocking=pin)
+
+    return EventBatch(up(cat("x", np.uint16).view(np.int16)), up(cat("y", np.uint16).view(np.int16)), up(cat("t", t_dtype)),
+                      up(cat("p", np.int8)), offs)
+
+
+_workspaces = {}
+
+
+def _workspace(device, stream_ptr, nbytes):
+    key = (device.index if device.index is not None else torch.cuda.current_device(), stream_ptr)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _prep(ev, op, H, W, C):
+    if not torch.cuda.is_available():
+        raise RuntimeError("event_representation_study_b200 needs a CUDA device; there is no CPU fallback")
+    stream = torch.cuda.current_stream(ev.device).cuda_stream
+    nbytes = lib.evrep_workspace_bytes(op, ev.B, ev.total, H, W, C)
+    if nbytes == 0:
+        raise ValueError(f"invalid geometry B={ev.B} total={ev.total} H={H} W={W}")
+    ws = _workspace(ev.device, stream, nbytes)
+    head = (ev.x.data_ptr(), ev.y.data_ptr(), ev.t.data_ptr(), ev.t.element_size(), ev.p.data_ptr(), ev.offsets.ctypes.data,
+            ev.B, H, W)
+    return head, ws, stream
+
+
+def _out(ev, shape, out):
+    if out is None:
+        return torch.empty(shape, dtype=torch.float32, device=ev.device)
+    if out.dtype != torch.float32 or not out.is_contiguous() or tuple(out.shape) != tuple(shape) or out.device != ev.device:
+        raise ValueError(f"out must be a contiguous float32 tensor of shape {tuple(shape)} on {ev.device}")
+    return out
+
+
+def window_flags(ev):
+    """EVREP_WF_* status word of every window for the last op run on the current stream (synchronises)."""
+    stream = torch.cuda.current_stream(ev.device).cuda_stream
+    key = (ev.device.index if ev.device.index is not None else torch.cuda.current_device(), stream)
+    ws = _workspaces[key]
+    flags = np.zeros(ev.B, np.uint32)
+    check(lib.evrep_window_flags(ws.data_ptr(), ev.B, flags.ctypes.data, stream))
+    return flags
+
+
+def _codes(windows, functions, aggregations):
+    C = len(windows)
+    if not (len(functions) == len(aggregations) == C):
+        raise ValueError("windows, functions and aggregations must have the same length")
+    win = np.array([int(w) if -128 <= int(w) <= 127 else 127 for w in windows], np.int8)
+    func = np.array([FUNCS.get(f, -1) if isinstance(f, str) else int(f) for f in functions], np.int8)
+    agg = np.array([AGGS.get(a, -1) if isinstance(a, str) else int(a) for a in aggregations], np.int8)
+    return win, func, agg, C
+
+
+def mixed_density(ev, H, W, windows, functions, aggregations, stacking="SBN", out=None):
+    """MixedDensityEventStack.stack for every window -> (B, H, W, C) float32.
+    (representations/representation_search/mixed_density_event_stack.py:25-46)"""
+    win, func, agg, C = _codes(windows, functions, aggregations)
+    if stacking not in STACKING:
+        # create_windows builds only window 0 for an unknown stacking type; every other index raises -> zero channel
+        win = np.where((win == 0) | (win == -1), 0, 127).astype(np.int8)
+        st = STACKING["SBN"]
+    else:
+        st = STACKING[stacking]
+    head, ws, stream = _prep(ev, _lib.OP_MIXED_DENSITY, H, W, C)
+    out = _out(ev, (ev.B, H, W, C), out)
+    check(lib.evrep_mixed_density_batched(*head, win.ctypes.data, func.ctypes.data, agg.ctypes.data, C, st, out.data_ptr(),
+                                          ws.data_ptr(), ws.numel(), stream))
+    return out
+
+
+def ergo12(ev, H, W, version=2, out=None):
+    """ERGO-12 (get_optimized_representation, representations/optimized_representation.py:86-134)
+    for every window -> (B, H, W, 12) float32."""
+    head, ws, stream = _prep(ev, _lib.OP_MIXED_DENSITY, H, W, 12)
+    out = _out(ev, (ev.B, H, W, 12), out)
+    check(lib.evrep_ergo12_batched(*head, int(version), out.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+    return out
+
+
+def event_stack(ev, H, W, stack_size=12, out=None):
+    """EventStack pre_stack + post_stack (representations/event_stack.py:15-63) -> (B, H, W, stack_size) in {-1,0,1}."""
+    head, ws, stream = _prep(ev, _lib.OP_EVENT_STACK, H, W, stack_size)
+    out = _out(ev, (ev.B, H, W, stack_size), out)
+    check(lib.evrep_event_stack_batched(*head, int(stack_size), out.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+    return out
+
+
+def time_surface(ev, H, W, n_surfaces=6, tau=50000.0, indices=None, out=None):
+    """ToTimesurface (representations/time_surface.py:25-74) -> (B, S, 2, H, W) float32.
+    indices: None for the gen1_transforms.py:78-80 rule, else an int64 array (B, S) of snapshot event indices."""
+    S = int(n_surfaces)
+    idx_ptr = None
+    if indices is not None:
+        indices = np.ascontiguousarray(np.asarray(indices, np.int64).reshape(ev.B, S))
+        idx_ptr = indices.ctypes.data
+    head, ws, stream = _prep(ev, _lib.OP_TIME_SURFACE, H, W, 2 * S)
+    out = _out(ev, (ev.B, S, 2, H, W), out)
+    check(lib.evrep_time_surface_batched(*head, idx_ptr, S, float(tau), out.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+    return out
+
+
+def tore(ev, H, W, k=6, out=None):
+    """events2ToreFeature (representations/tore.py:6-83) with sampleTimes = last timestamp of each window and
+    0-based pixel coordinates -> (B, H, W, 2k) float32."""
+    head, ws, stream = _prep(ev, _lib.OP_TORE, H, W, 2 * k)
+    out = _out(ev, (ev.B, H, W, 2 * k), out)
+    check(lib.evrep_tore_batched(*head, int(k), out.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+    return out
+
+
+def voxel_grid(ev, H, W, n_bins, flavour="tonic", normalize=True, t0_us=None, t1_us=None, out=None):
+    """flavour 'tonic' -> (B, n_bins, H, W); 'evlicious' -> (B, n_bins, H, W); 'gwd' -> (B, H, W, n_bins)."""
+    fl = {"tonic": _lib.VOXEL_TONIC, "evlicious": _lib.VOXEL_EVLICIOUS, "gwd": _lib.VOXEL_GWD}[flavour]
+    t01 = None
+    if (t0_us is not None or t1_us is not None) and fl == _lib.VOXEL_EVLICIOUS:
+        if t0_us is None or t1_us is None:
+            raise ValueError("give both t0_us and t1_us or neither (the batched call cannot read single timestamps back)")
+        t01 = np.array([int(t0_us), int(t1_us)], np.int64)
+    head, ws, stream = _prep(ev, _lib.OP_VOXEL, H, W, n_bins)
+    shape = (ev.B, H, W, n_bins) if fl == _lib.VOXEL_GWD else (ev.B, n_bins, H, W)
+    out = _out(ev, shape, out)
+    check(lib.evrep_voxel_batched(*head, fl, int(n_bins), int(bool(normalize)), None if t01 is None else t01.ctypes.data,
+                                  out.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+    return out
+
+
+def histogram(ev, H, W, out=None):
+    """tonic ToImage counts (gen1_transforms.py:44-49) -> (B, 2, H, W) float32, plane 1 = p > 0."""
+    head, ws, stream = _prep(ev, _lib.OP_HISTOGRAM, H, W, 2)
+    out = _out(ev, (ev.B, 2, H, W), out)
+    check(lib.evrep_histogram_batched(*head, out.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+    return out
+
+
+def gwd_kernel_l1(Xs_list, Xt_list, h=0.7, device="cuda"):
+    """GWD-A cost of every (Xs, Xt) pair (compute_otmi.py:50-93 in closed form) -> float64 CUDA tensor (n_pairs,).
+    Xs_list / Xt_list: lists of (n_i, ds) / (m_i, dt) arrays or tensors (any float dtype)."""
+    if len(Xs_list) != len(Xt_list):
+        raise ValueError("need as many Xs as Xt")
+    n_pairs = len(Xs_list)
+    dev = torch.device(device)
+    if n_pairs == 0:
+        return torch.zeros(0, dtype=torch.float64, device=dev)
+
+    def pack(lst):
+        ts = [torch.as_tensor(a).to(device=dev, dtype=torch.float64).reshape(len(a), -1) for a in lst]
+        d = ts[0].shape[1]
+        if any(t.shape[1] != d for t in ts):
+            raise ValueError("all pairs must share the feature width")
+        offs = np.zeros(n_pairs + 1, np.int64)
+        offs[1:] = np.cumsum([t.shape[0] for t in ts])
+        return torch.cat(ts, 0).contiguous(), offs, d
+
+    Xs, so, ds = pack(Xs_list)
+    Xt, to, dt = pack(Xt_list)
+    nbytes = lib.evrep_gwd_workspace_bytes(so.ctypes.data, to.ctypes.data, n_pairs)
+    if nbytes == 0:
+        raise ValueError("invalid pair sizes")
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    ws = _workspace(dev, stream, nbytes)
+    out = torch.empty(n_pairs, dtype=torch.float64, device=dev)
+    check(lib.evrep_gwd_kernel_l1(Xs.data_ptr(), so.ctypes.data, ds, Xt.data_ptr(), to.ctypes.data, dt, n_pairs, float(h),
+                                  out.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+    return out

@@ -1,0 +1,304 @@
+// The C ABI of libevrep (include/evrep.h): argument validation, tile geometry, workspace carving and
+// kernel sequencing.  No exceptions leave this file; every entry point returns an EVREP_* code.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+
+#include "evrep_common.cuh"
+
+namespace evrep {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int build_md_plan(const int8_t* win, const int8_t* func, const int8_t* agg, int C, int stacking, int64_t n_max, MdPlan* out);
+size_t gwd_workspace_bytes(const int64_t* so, const int64_t* to, int n_pairs);
+int launch_gwd(const double* Xs, const int64_t* so, int ds, const double* Xt, const int64_t* to, int dt, int n_pairs, double h,
+               double* out, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+constexpr size_t TILE_SMEM_TARGET = 100 * 1024;  // two tile CTAs per SM
+constexpr size_t TILE_SMEM_MAX = 220 * 1024;
+
+// tile_px = largest power of two (<= 4096) whose accumulators fit the target; T = tiles per window
+static int choose_tile(int H, int W, size_t bytes_per_px, Geom* g) {
+  if (H < 1 || W < 1 || H > 65535 || W > 65535 || (int64_t)H * W > ((int64_t)1 << 28)) {
+    set_error("sensor size %d x %d unsupported", W, H);
+    return EVREP_EINVAL;
+  }
+  g->H = H;
+  g->W = W;
+  g->HW = H * W;
+  int shift = 12;
+  while (shift > 8 && ((size_t)1 << shift) * bytes_per_px > TILE_SMEM_TARGET) --shift;
+  // a very large sensor needs bigger tiles than the target allows: trade occupancy for reach
+  while (((g->HW + (1 << shift) - 1) >> shift) > MAX_TILES && shift < 16) ++shift;
+  if (((size_t)1 << shift) * bytes_per_px > TILE_SMEM_MAX || ((g->HW + (1 << shift) - 1) >> shift) > MAX_TILES) {
+    set_error("%d x %d pixels with %zu accumulator bytes per pixel does not fit the tile pipeline", W, H, bytes_per_px);
+    return EVREP_EUNSUPPORTED;
+  }
+  g->tile_shift = shift;
+  g->tile_px = 1 << shift;
+  g->T = (g->HW + g->tile_px - 1) >> shift;
+  return EVREP_OK;
+}
+
+static int check_events(const uint16_t* x, const uint16_t* y, const void* t, int t_bytes, const int8_t* p, const int64_t* win_offsets,
+                        int B, const void* out, Events* ev, int64_t* total, int64_t* n_max) {
+  if (B < 0 || !win_offsets) { set_error("B must be >= 0 and win_offsets non-null"); return EVREP_EINVAL; }
+  if (t_bytes != 4 && t_bytes != 8) { set_error("t_bytes must be 4 (int32) or 8 (int64), got %d", t_bytes); return EVREP_EINVAL; }
+  *total = win_offsets[B];
+  *n_max = 0;
+  for (int b = 0; b < B; ++b) *n_max = std::max<int64_t>(*n_max, win_offsets[b + 1] - win_offsets[b]);
+  if (*total > 0 && (!x || !y || !t || !p)) { set_error("null event array"); return EVREP_EINVAL; }
+  if (B > 0 && !out) { set_error("null output"); return EVREP_EINVAL; }
+  ev->x = x; ev->y = y; ev->t = t; ev->t_bytes = t_bytes; ev->p = p;
+  return EVREP_OK;
+}
+
+static int carve_checked(void* workspace, size_t workspace_bytes, int B, int64_t total, int T, Workspace* ws) {
+  *ws = carve(workspace, B, total, T);
+  if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) {
+    set_error("workspace must be non-null and 256-byte aligned");
+    return EVREP_EWORKSPACE;
+  }
+  if (ws->bytes > workspace_bytes) {
+    set_error("workspace too small: need %zu bytes, got %zu", ws->bytes, workspace_bytes);
+    return EVREP_EWORKSPACE;
+  }
+  return EVREP_OK;
+}
+
+}  // namespace evrep
+
+using namespace evrep;
+
+#define EVREP_TRY(expr)            \
+  do {                             \
+    int _rc = (expr);              \
+    if (_rc != EVREP_OK) return _rc; \
+  } while (0)
+
+#define EVREP_GUARD_BEGIN try {
+#define EVREP_GUARD_END                                   \
+  }                                                       \
+  catch (const std::bad_alloc&) {                         \
+    set_error("host allocation failed");                  \
+    return EVREP_EINVAL;                                  \
+  }                                                       \
+  catch (...) {                                           \
+    set_error("unexpected C++ exception");                \
+    return EVREP_EINVAL;                                  \
+  }
+
+extern "C" {
+
+int evrep_version(void) { return EVREP_VERSION; }
+
+const char* evrep_last_error(void) { return g_err; }
+
+size_t evrep_workspace_bytes(int op, int B, int64_t total_events, int H, int W, int C) {
+  (void)C;
+  if (op < EVREP_OP_MIXED_DENSITY || op > EVREP_OP_HISTOGRAM || B < 0 || total_events < 0 || H < 1 || W < 1) return 0;
+  const int64_t hw = (int64_t)H * W;
+  int64_t T = (hw + MIN_TILE_PX - 1) / MIN_TILE_PX;
+  if (T > MAX_TILES) T = MAX_TILES;
+  const bool tiles = op != EVREP_OP_VOXEL && op != EVREP_OP_HISTOGRAM;
+  return carve(nullptr, B > 0 ? B : 1, tiles ? total_events : 0, tiles ? (int)T : 1).bytes;
+}
+
+int evrep_window_flags(const void* workspace, int B, uint32_t* flags_host, evrep_stream_t stream) {
+  if (!workspace || !flags_host || B < 0) { set_error("bad argument"); return EVREP_EINVAL; }
+  if (B == 0) return EVREP_OK;
+  const WinParams* wp = (const WinParams*)workspace;
+  EVREP_CUDA_OK(cudaMemcpy2DAsync(flags_host, sizeof(uint32_t), &wp[0].flags, sizeof(WinParams), sizeof(uint32_t), (size_t)B,
+                                  cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  EVREP_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+  return EVREP_OK;
+}
+
+int evrep_mixed_density_plan_info(int H, int W, const int8_t* win, const int8_t* func, const int8_t* agg, int C, int stacking,
+                                  int64_t max_events_per_window, int* info) {
+  EVREP_GUARD_BEGIN
+  if (!win || !func || !agg || !info) { set_error("null argument"); return EVREP_EINVAL; }
+  MdPlan plan;
+  EVREP_TRY(build_md_plan(win, func, agg, C, stacking, max_events_per_window, &plan));
+  Geom g;
+  memset(&g, 0, sizeof(g));
+  EVREP_TRY(choose_tile(H, W, (size_t)plan.words * 4, &g));
+  info[0] = plan.words * 4;
+  info[1] = g.tile_px;
+  info[2] = g.T;
+  info[3] = plan.words;
+  info[4] = (int)md_tile_smem_bytes(plan, g.tile_px);
+  return EVREP_OK;
+  EVREP_GUARD_END
+}
+
+int evrep_mixed_density_batched(const uint16_t* x, const uint16_t* y, const void* t, int t_bytes, const int8_t* p,
+                                const int64_t* win_offsets, int B, int H, int W, const int8_t* win, const int8_t* func,
+                                const int8_t* agg, int C, int stacking, float* out, void* workspace, size_t workspace_bytes,
+                                evrep_stream_t stream) {
+  EVREP_GUARD_BEGIN
+  Events ev;
+  int64_t total = 0, n_max = 0;
+  EVREP_TRY(check_events(x, y, t, t_bytes, p, win_offsets, B, out, &ev, &total, &n_max));
+  if (!win || !func || !agg) { set_error("null channel description"); return EVREP_EINVAL; }
+  if (B == 0) return EVREP_OK;
+  MdPlan plan;
+  EVREP_TRY(build_md_plan(win, func, agg, C, stacking, n_max, &plan));
+  Geom g;
+  memset(&g, 0, sizeof(g));
+  EVREP_TRY(choose_tile(H, W, (size_t)plan.words * 4, &g));
+  g.B = B;
+  g.total = total;
+  Workspace ws;
+  EVREP_TRY(carve_checked(workspace, workspace_bytes, B, total, g.T, &ws));
+  EVREP_TRY(run_binning(ev, win_offsets, g, ws, REC_T_WMASK, 0, nullptr, (cudaStream_t)stream));
+  return launch_md_tile(g, ws, plan, ev, out, (cudaStream_t)stream);
+  EVREP_GUARD_END
+}
+
+int evrep_ergo12_batched(const uint16_t* x, const uint16_t* y, const void* t, int t_bytes, const int8_t* p, const int64_t* win_offsets,
+                         int B, int H, int W, int version, float* out, void* workspace, size_t workspace_bytes, evrep_stream_t stream) {
+  // representations/optimized_representation.py:86-115 (v2, active) and :16-66 (v1, commented out)
+  enum { T_ = EVREP_FUNC_TIMESTAMP, P_ = EVREP_FUNC_POLARITY, C_ = EVREP_FUNC_COUNT, TP = EVREP_FUNC_TIMESTAMP_POS,
+         TN = EVREP_FUNC_TIMESTAMP_NEG, CP = EVREP_FUNC_COUNT_POS, CN = EVREP_FUNC_COUNT_NEG };
+  enum { SUM = EVREP_AGG_SUM, MEAN = EVREP_AGG_MEAN, MAX = EVREP_AGG_MAX, VAR = EVREP_AGG_VARIANCE };
+  static const int8_t w2[12] = {0, 3, 2, 6, 5, 6, 2, 5, 1, 0, 4, 1};
+  static const int8_t f2[12] = {P_, TN, CN, P_, CP, C_, TP, CN, TN, TP, T_, C_};
+  static const int8_t a2[12] = {VAR, VAR, MEAN, SUM, MEAN, SUM, MEAN, MEAN, MAX, MAX, MAX, MEAN};
+  static const int8_t w1[12] = {0, 2, 2, 3, 5, 0, 0, 4, 2, 6, 1, 1};
+  static const int8_t f1[12] = {T_, TP, TN, CN, CP, P_, T_, C_, TP, C_, TP, TN};
+  static const int8_t a1[12] = {MAX, SUM, MEAN, SUM, MEAN, VAR, VAR, SUM, MEAN, SUM, SUM, SUM};
+  if (version != 1 && version != 2) { set_error("ERGO-12 version must be 1 or 2"); return EVREP_EINVAL; }
+  return evrep_mixed_density_batched(x, y, t, t_bytes, p, win_offsets, B, H, W, version == 2 ? w2 : w1, version == 2 ? f2 : f1,
+                                     version == 2 ? a2 : a1, 12, EVREP_STACK_SBN, out, workspace, workspace_bytes, stream);
+}
+
+int evrep_event_stack_batched(const uint16_t* x, const uint16_t* y, const void* t, int t_bytes, const int8_t* p,
+                              const int64_t* win_offsets, int B, int H, int W, int stack_size, float* out, void* workspace,
+                              size_t workspace_bytes, evrep_stream_t stream) {
+  EVREP_GUARD_BEGIN
+  Events ev;
+  int64_t total = 0, n_max = 0;
+  EVREP_TRY(check_events(x, y, t, t_bytes, p, win_offsets, B, out, &ev, &total, &n_max));
+  if (stack_size < 1 || stack_size > EVREP_MAX_CHANNELS) { set_error("stack_size outside 1..%d", EVREP_MAX_CHANNELS); return EVREP_EINVAL; }
+  if (B == 0) return EVREP_OK;
+  Geom g;
+  memset(&g, 0, sizeof(g));
+  EVREP_TRY(choose_tile(H, W, 4, &g));
+  g.B = B;
+  g.total = total;
+  Workspace ws;
+  EVREP_TRY(carve_checked(workspace, workspace_bytes, B, total, g.T, &ws));
+  EVREP_TRY(run_binning(ev, win_offsets, g, ws, REC_IDX, 0, nullptr, (cudaStream_t)stream));
+  return launch_event_stack_tile(g, ws, stack_size, out, (cudaStream_t)stream);
+  EVREP_GUARD_END
+}
+
+int evrep_time_surface_batched(const uint16_t* x, const uint16_t* y, const void* t, int t_bytes, const int8_t* p,
+                               const int64_t* win_offsets, int B, int H, int W, const int64_t* indices, int S, double tau, float* out,
+                               void* workspace, size_t workspace_bytes, evrep_stream_t stream) {
+  EVREP_GUARD_BEGIN
+  Events ev;
+  int64_t total = 0, n_max = 0;
+  EVREP_TRY(check_events(x, y, t, t_bytes, p, win_offsets, B, out, &ev, &total, &n_max));
+  if (S < 1 || S > MAX_SNAP) { set_error("S outside 1..%d", MAX_SNAP); return EVREP_EINVAL; }
+  if (!(tau > 0.0)) { set_error("tau must be positive"); return EVREP_EINVAL; }
+  if (B == 0) return EVREP_OK;
+  Geom g;
+  memset(&g, 0, sizeof(g));
+  EVREP_TRY(choose_tile(H, W, (size_t)8 * S, &g));
+  g.B = B;
+  g.total = total;
+  Workspace ws;
+  EVREP_TRY(carve_checked(workspace, workspace_bytes, B, total, g.T, &ws));
+  EVREP_TRY(run_binning(ev, win_offsets, g, ws, REC_T_SNAP, S, indices, (cudaStream_t)stream));
+  return launch_time_surface_tile(g, ws, S, tau, out, (cudaStream_t)stream);
+  EVREP_GUARD_END
+}
+
+int evrep_tore_batched(const uint16_t* x, const uint16_t* y, const void* t, int t_bytes, const int8_t* p, const int64_t* win_offsets,
+                       int B, int H, int W, int k, float* out, void* workspace, size_t workspace_bytes, evrep_stream_t stream) {
+  EVREP_GUARD_BEGIN
+  Events ev;
+  int64_t total = 0, n_max = 0;
+  EVREP_TRY(check_events(x, y, t, t_bytes, p, win_offsets, B, out, &ev, &total, &n_max));
+  if (k < 1 || 2 * k > EVREP_MAX_CHANNELS) { set_error("k outside 1..%d", EVREP_MAX_CHANNELS / 2); return EVREP_EINVAL; }
+  if (B == 0) return EVREP_OK;
+  Geom g;
+  memset(&g, 0, sizeof(g));
+  EVREP_TRY(choose_tile(H, W, (size_t)8 * k, &g));
+  g.B = B;
+  g.total = total;
+  Workspace ws;
+  EVREP_TRY(carve_checked(workspace, workspace_bytes, B, total, g.T, &ws));
+  EVREP_TRY(run_binning(ev, win_offsets, g, ws, REC_T_TORE, 0, nullptr, (cudaStream_t)stream));
+  return launch_tore_tile(g, ws, k, out, (cudaStream_t)stream);
+  EVREP_GUARD_END
+}
+
+int evrep_voxel_batched(const uint16_t* x, const uint16_t* y, const void* t, int t_bytes, const int8_t* p, const int64_t* win_offsets,
+                        int B, int H, int W, int flavour, int n_bins, int normalize, const int64_t* t0_t1_us, float* out,
+                        void* workspace, size_t workspace_bytes, evrep_stream_t stream) {
+  EVREP_GUARD_BEGIN
+  Events ev;
+  int64_t total = 0, n_max = 0;
+  EVREP_TRY(check_events(x, y, t, t_bytes, p, win_offsets, B, out, &ev, &total, &n_max));
+  if (flavour < EVREP_VOXEL_TONIC || flavour > EVREP_VOXEL_GWD) { set_error("unknown voxel flavour %d", flavour); return EVREP_EINVAL; }
+  if (n_bins < 1 || n_bins > 1024) { set_error("n_bins outside 1..1024"); return EVREP_EINVAL; }
+  if (B == 0) return EVREP_OK;
+  Geom g;
+  memset(&g, 0, sizeof(g));
+  EVREP_TRY(choose_tile(H, W, 4, &g));
+  g.B = B;
+  g.total = total;
+  Workspace ws;
+  EVREP_TRY(carve_checked(workspace, workspace_bytes, B, 0, 1, &ws));
+  return launch_voxel(ev, win_offsets, g, ws, flavour, n_bins, normalize, t0_t1_us, out, (cudaStream_t)stream);
+  EVREP_GUARD_END
+}
+
+int evrep_histogram_batched(const uint16_t* x, const uint16_t* y, const void* t, int t_bytes, const int8_t* p, const int64_t* win_offsets,
+                            int B, int H, int W, float* out, void* workspace, size_t workspace_bytes, evrep_stream_t stream) {
+  EVREP_GUARD_BEGIN
+  Events ev;
+  int64_t total = 0, n_max = 0;
+  EVREP_TRY(check_events(x, y, t, t_bytes, p, win_offsets, B, out, &ev, &total, &n_max));
+  if (B == 0) return EVREP_OK;
+  Geom g;
+  memset(&g, 0, sizeof(g));
+  EVREP_TRY(choose_tile(H, W, 4, &g));
+  g.B = B;
+  g.total = total;
+  Workspace ws;
+  EVREP_TRY(carve_checked(workspace, workspace_bytes, B, 0, 1, &ws));
+  return launch_histogram(ev, win_offsets, g, ws, out, (cudaStream_t)stream);
+  EVREP_GUARD_END
+}
+
+size_t evrep_gwd_workspace_bytes(const int64_t* s_offsets, const int64_t* t_offsets, int n_pairs) {
+  if (!s_offsets || !t_offsets) return 0;
+  return gwd_workspace_bytes(s_offsets, t_offsets, n_pairs);
+}
+
+int evrep_gwd_kernel_l1(const double* Xs, const int64_t* s_offsets, int ds, const double* Xt, const int64_t* t_offsets, int dt,
+                        int n_pairs, double h, double* out, void* workspace, size_t workspace_bytes, evrep_stream_t stream) {
+  EVREP_GUARD_BEGIN
+  if (n_pairs < 0 || !s_offsets || !t_offsets) { set_error("bad pair description"); return EVREP_EINVAL; }
+  if (n_pairs == 0) return EVREP_OK;
+  if (!Xs || !Xt || !out) { set_error("null array"); return EVREP_EINVAL; }
+  if (!(h > 0.0)) { set_error("h must be positive"); return EVREP_EINVAL; }
+  return launch_gwd(Xs, s_offsets, ds, Xt, t_offsets, dt, n_pairs, h, out, workspace, workspace_bytes, (cudaStream_t)stream);
+  EVREP_GUARD_END
+}
+
+}  // extern "C"

@@ -1,0 +1,488 @@
+// Spatial pre-bucketing of event windows: count -> scan -> scatter.
+//
+// Every tile-based representation starts here.  A window's pixels are cut into tiles of tile_px
+// consecutive linear pixel indices (y*W + x); the events of each window are regrouped so that all
+// events of one (window, tile) bucket are contiguous 8-byte records.  The per-tile kernels then
+// reduce a bucket entirely in shared memory and write their slice of the output exactly once.
+//
+// Replaces the per-channel boolean masking / np.concatenate / torch_scatter passes of the reference
+// (representations/representation_search/mixed_density_event_stack.py:111-151, operations.py:39-89)
+// and the np.put passes of event_stack.py:118-131.
+#include <limits.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "evrep_common.cuh"
+
+namespace evrep {
+
+// ---------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int find_window(const int32_t* __restrict__ chunk_prefix, int B, int chunk) {
+  int lo = 0, hi = B;  // largest b with chunk_prefix[b] <= chunk
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(chunk_prefix + mid) <= chunk) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ void load8_u16(const uint16_t* __restrict__ p, int64_t g0, int64_t total, bool vec, uint32_t (&v)[EPT]) {
+  if (vec && g0 + EPT <= total) {
+    uint4 q = __ldg(reinterpret_cast<const uint4*>(p + g0));
+    v[0] = q.x & 0xffffu; v[1] = q.x >> 16; v[2] = q.y & 0xffffu; v[3] = q.y >> 16;
+    v[4] = q.z & 0xffffu; v[5] = q.z >> 16; v[6] = q.w & 0xffffu; v[7] = q.w >> 16;
+  } else {
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) v[e] = (g0 + e < total) ? (uint32_t)__ldg(p + g0 + e) : 0u;
+  }
+}
+
+__device__ __forceinline__ void load8_i8(const int8_t* __restrict__ p, int64_t g0, int64_t total, bool vec, int (&v)[EPT]) {
+  if (vec && g0 + EPT <= total) {
+    uint2 q = __ldg(reinterpret_cast<const uint2*>(p + g0));
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      v[e] = (int)(int8_t)((q.x >> (8 * e)) & 0xff);
+      v[4 + e] = (int)(int8_t)((q.y >> (8 * e)) & 0xff);
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) v[e] = (g0 + e < total) ? (int)__ldg(p + g0 + e) : 0;
+  }
+}
+
+template <typename TT>
+__device__ __forceinline__ void load8_t(const TT* __restrict__ p, int64_t g0, int64_t total, bool vec, int64_t (&v)[EPT]);
+
+template <>
+__device__ __forceinline__ void load8_t<int32_t>(const int32_t* __restrict__ p, int64_t g0, int64_t total, bool vec, int64_t (&v)[EPT]) {
+  if (vec && g0 + EPT <= total) {
+    int4 a = __ldg(reinterpret_cast<const int4*>(p + g0));
+    int4 b = __ldg(reinterpret_cast<const int4*>(p + g0) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) v[e] = (g0 + e < total) ? (int64_t)__ldg(p + g0 + e) : 0;
+  }
+}
+template <>
+__device__ __forceinline__ void load8_t<int64_t>(const int64_t* __restrict__ p, int64_t g0, int64_t total, bool vec, int64_t (&v)[EPT]) {
+  if (vec && g0 + EPT <= total) {
+    const longlong2* q = reinterpret_cast<const longlong2*>(p + g0);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      longlong2 a = __ldg(q + e);
+      v[2 * e] = a.x; v[2 * e + 1] = a.y;
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) v[e] = (g0 + e < total) ? (int64_t)__ldg(p + g0 + e) : 0;
+  }
+}
+
+// In-place exclusive scan of a[0..n) in shared memory by a BIN_THREADS-thread CTA (n <= MAX_TILES).
+// `warp_tot` is BIN_THREADS/32 words of scratch.  Returns the total.  Ends with a __syncthreads().
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t* a, int n, uint32_t* warp_tot) {
+  constexpr int ITEMS = MAX_TILES / BIN_THREADS;  // 8
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = (n + BIN_THREADS - 1) / BIN_THREADS;  // <= ITEMS
+  const int i0 = tid * per;
+  uint32_t loc[ITEMS];
+  uint32_t sum = 0;
+#pragma unroll
+  for (int k = 0; k < ITEMS; ++k) {
+    uint32_t v = (k < per && i0 + k < n) ? a[i0 + k] : 0u;
+    loc[k] = sum;
+    sum += v;
+  }
+  uint32_t inc = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31) warp_tot[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = (lane < BIN_THREADS / 32) ? warp_tot[lane] : 0u;
+    uint32_t winc = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t o = __shfl_up_sync(0xffffffffu, winc, d);
+      if (lane >= d) winc += o;
+    }
+    if (lane < BIN_THREADS / 32) warp_tot[lane] = winc - w;  // exclusive
+    if (lane == BIN_THREADS / 32 - 1) warp_tot[BIN_THREADS / 32] = winc;
+  }
+  __syncthreads();
+  const uint32_t basev = warp_tot[warp] + (inc - sum);
+#pragma unroll
+  for (int k = 0; k < ITEMS; ++k)
+    if (k < per && i0 + k < n) a[i0 + k] = basev + loc[k];
+  const uint32_t total = warp_tot[BIN_THREADS / 32];
+  __syncthreads();
+  return total;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-window initialisation
+// ---------------------------------------------------------------------------------------------
+template <typename TT>
+__global__ void k_init(const TT* __restrict__ t, const int64_t* __restrict__ offsets, int B, WinParams* __restrict__ wp) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  WinParams w;
+  w.start = offsets[b];
+  w.n = offsets[b + 1] - offsets[b];
+  w.flags = 0;
+  w.has_m1 = 0;
+  w.pad = 0;
+  w.tmin_rel = INT_MAX;
+  w.tmax_rel = INT_MIN;
+  w.t_base = 0;
+  w.tlast_rel = 0;
+  if (w.n > 0) {
+    w.t_base = (int64_t)t[w.start];
+    int64_t d = (int64_t)t[w.start + w.n - 1] - w.t_base;
+    if (d >= T_REL_LIMIT || d <= -T_REL_LIMIT) {
+      w.flags |= EVREP_WF_T_RANGE;
+      d = d > 0 ? T_REL_LIMIT - 1 : -(T_REL_LIMIT - 1);
+    }
+    w.tlast_rel = (int32_t)d;
+  }
+  wp[b] = w;
+}
+
+// Time-surface snapshot indices.  Either the caller's (B*S int64, already on the device) or the rule of
+// representations/gen1_transforms.py:78-80: searchsorted((t - t0)/(tN - t0)*S, [1..S]) (left).
+// Surface s is emitted only while the indices are strictly increasing and in range
+// (time_surface.py:66-74: the `i == indices[s]` test can never fire again after a duplicate).
+template <typename TT>
+__global__ void k_snap_init(const TT* __restrict__ t, const WinParams* __restrict__ wp, const int64_t* __restrict__ user_idx,
+                            int S, SnapParams* __restrict__ snap) {
+  const int b = blockIdx.x;
+  __shared__ int64_t idx[MAX_SNAP];
+  const WinParams w = wp[b];
+  const int s = threadIdx.x;
+  if (s < S) {
+    if (user_idx) {
+      idx[s] = user_idx[(size_t)b * S + s];
+    } else if (w.n > 0) {
+      const double t0 = (double)((int64_t)t[w.start] - w.t_base);
+      const double den = (double)((int64_t)t[w.start + w.n - 1] - w.t_base) - t0;
+      const double target = (double)(s + 1);
+      int64_t lo = 0, hi = w.n;
+      while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        double tn = ((double)((int64_t)t[w.start + mid] - w.t_base) - t0) / den * (double)S;
+        if (tn < target) lo = mid + 1; else hi = mid;  // NaN compares false -> behaves as +inf, like numpy's sort order
+      }
+      idx[s] = lo;
+    } else {
+      idx[s] = 0;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    SnapParams sp;
+    for (int k = 0; k < MAX_SNAP; ++k) { sp.idx[k] = 0; sp.t_rel[k] = 0; }
+    sp.pad[0] = sp.pad[1] = sp.pad[2] = 0;
+    int nv = 0;
+    int64_t prev = -1;
+    for (int k = 0; k < S; ++k) {
+      int64_t i = idx[k];
+      if (i <= prev || i >= w.n) break;
+      sp.idx[k] = (int32_t)i;
+      int64_t d = (int64_t)t[w.start + i] - w.t_base;
+      d = d >= T_REL_LIMIT ? T_REL_LIMIT - 1 : (d <= -T_REL_LIMIT ? -(T_REL_LIMIT - 1) : d);
+      sp.t_rel[k] = (int32_t)d;
+      prev = i;
+      ++nv;
+    }
+    sp.n_valid = nv;
+    snap[b] = sp;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 1: bucket sizes
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BIN_THREADS) k_hist(const uint16_t* __restrict__ x, const uint16_t* __restrict__ y,
+                                                      const WinParams* __restrict__ wp, const int32_t* __restrict__ chunk_prefix,
+                                                      Geom g, bool vec, uint32_t* __restrict__ hist) {
+  extern __shared__ uint32_t sh_hist[];
+  const int b = find_window(chunk_prefix, g.B, blockIdx.x);
+  const int chunk = blockIdx.x - __ldg(chunk_prefix + b);
+  const int64_t start = wp[b].start, end = start + wp[b].n;
+  for (int i = threadIdx.x; i < g.T; i += BIN_THREADS) sh_hist[i] = 0;
+  __syncthreads();
+  const int64_t g0 = (start & ~(int64_t)(EPT - 1)) + (int64_t)chunk * CHUNK + (int64_t)threadIdx.x * EPT;
+  if (g0 < end) {
+    uint32_t xs[EPT], ys[EPT];
+    load8_u16(x, g0, g.total, vec, xs);
+    load8_u16(y, g0, g.total, vec, ys);
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+      const int64_t a = g0 + e;
+      if (a >= start && a < end && xs[e] < (uint32_t)g.W && ys[e] < (uint32_t)g.H)
+        atomicAdd(&sh_hist[(ys[e] * (uint32_t)g.W + xs[e]) >> g.tile_shift], 1u);
+    }
+  }
+  __syncthreads();
+  uint32_t* dst = hist + (size_t)b * g.T;
+  for (int i = threadIdx.x; i < g.T; i += BIN_THREADS) {
+    uint32_t v = sh_hist[i];
+    if (v) atomicAdd(dst + i, v);
+  }
+}
+
+// bucket starts: one CTA per window, exclusive scan over its T buckets
+__global__ void __launch_bounds__(BIN_THREADS) k_scan(const uint32_t* __restrict__ hist, uint32_t* __restrict__ base, int T) {
+  __shared__ uint32_t a[MAX_TILES];
+  __shared__ uint32_t warp_tot[BIN_THREADS / 32 + 1];
+  const size_t o = (size_t)blockIdx.x * T;
+  for (int i = threadIdx.x; i < T; i += BIN_THREADS) a[i] = hist[o + i];
+  __syncthreads();
+  block_exclusive_scan(a, T, warp_tot);
+  for (int i = threadIdx.x; i < T; i += BIN_THREADS) base[o + i] = a[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 2: scatter the events into their buckets as 8-byte records
+// ---------------------------------------------------------------------------------------------
+template <typename TT>
+__global__ void __launch_bounds__(BIN_THREADS) k_bin(const uint16_t* __restrict__ x, const uint16_t* __restrict__ y,
+                                                     const TT* __restrict__ t, const int8_t* __restrict__ p,
+                                                     WinParams* __restrict__ wp, const SnapParams* __restrict__ snap,
+                                                     const int32_t* __restrict__ chunk_prefix, Geom g, bool vec, int mode,
+                                                     const uint32_t* __restrict__ base, uint32_t* __restrict__ cursor,
+                                                     uint2* __restrict__ records) {
+  extern __shared__ __align__(16) unsigned char sh_raw[];
+  uint2* stage = reinterpret_cast<uint2*>(sh_raw);                            // CHUNK records
+  uint16_t* stile = reinterpret_cast<uint16_t*>(stage + CHUNK);               // CHUNK tile ids
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(stile + CHUNK);                 // T
+  uint32_t* loff = cnt + g.T;                                                 // T
+  uint32_t* gbase = loff + g.T;                                               // T
+  __shared__ uint32_t warp_tot[BIN_THREADS / 32 + 1];
+  __shared__ int sh_tmin, sh_tmax;
+  __shared__ uint32_t sh_flags, sh_m1;
+  __shared__ int32_t sh_snap_idx[MAX_SNAP];
+  __shared__ int sh_nsnap;
+
+  const int tid = threadIdx.x;
+  const int b = find_window(chunk_prefix, g.B, blockIdx.x);
+  const int chunk = blockIdx.x - __ldg(chunk_prefix + b);
+  const int64_t start = wp[b].start, n = wp[b].n, end = start + n;
+  const int64_t t_base = wp[b].t_base;
+  const int32_t tlast_rel = wp[b].tlast_rel;
+
+  for (int i = tid; i < g.T; i += BIN_THREADS) cnt[i] = 0;
+  if (tid == 0) { sh_tmin = INT_MAX; sh_tmax = INT_MIN; sh_flags = 0; sh_m1 = 0; sh_nsnap = 0; }
+  if (mode == REC_T_SNAP) {
+    if (tid < MAX_SNAP) sh_snap_idx[tid] = snap[b].idx[tid];
+    if (tid == 0) sh_nsnap = snap[b].n_valid;
+  }
+  __syncthreads();
+
+  // index boundaries of the SBN windows (mixed_density_event_stack.py:55-74)
+  const int64_t n3 = n / 3, s4 = n / 2, s5 = s4 + n / 4, s6 = s5 + n / 8;
+
+  const int64_t g0 = (start & ~(int64_t)(EPT - 1)) + (int64_t)chunk * CHUNK + (int64_t)tid * EPT;
+  uint32_t key[EPT], meta[EPT], tile_rank[EPT];  // tile_rank = tile << 16 | rank-in-CTA... ranks < CHUNK = 2^12
+  int my_tmin = INT_MAX, my_tmax = INT_MIN;
+  uint32_t my_flags = 0, my_m1 = 0;
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) tile_rank[e] = 0xffffffffu;
+
+  if (g0 < end) {
+    uint32_t xs[EPT], ys[EPT];
+    int ps[EPT];
+    int64_t ts[EPT];
+    load8_u16(x, g0, g.total, vec, xs);
+    load8_u16(y, g0, g.total, vec, ys);
+    load8_i8(p, g0, g.total, vec, ps);
+    load8_t<TT>(t, g0, g.total, vec, ts);
+    int64_t t_prev = (g0 - 1 >= start) ? (int64_t)__ldg(t + g0 - 1) : LLONG_MIN;
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+      const int64_t a = g0 + e;
+      if (a < start || a >= end) continue;
+      if (ts[e] < t_prev) my_flags |= EVREP_WF_UNSORTED;
+      t_prev = ts[e];
+      if (xs[e] >= (uint32_t)g.W || ys[e] >= (uint32_t)g.H) { my_flags |= EVREP_WF_OUT_OF_RANGE; continue; }
+      const int64_t d = ts[e] - t_base;
+      if (d >= T_REL_LIMIT || d <= -T_REL_LIMIT) { my_flags |= EVREP_WF_T_RANGE; continue; }
+      const int32_t t_rel = (int32_t)d;
+      int pv = ps[e];
+      if (pv > 1 || pv < -1) { my_flags |= EVREP_WF_BAD_POLARITY; pv = pv > 0 ? 1 : -1; }
+      const int64_t idx = a - start;
+      uint32_t aux = 0, k = (uint32_t)t_rel;
+      if (mode == REC_T_WMASK) {
+        aux = 1u;
+        aux |= idx < n3 ? 2u : (idx < 2 * n3 ? 4u : (idx < 3 * n3 ? 8u : 0u));
+        aux |= (idx >= s4 ? 16u : 0u) | (idx >= s5 ? 32u : 0u) | (idx >= s6 ? 64u : 0u);
+        if (pv == -1) my_m1 |= aux;
+      } else if (mode == REC_IDX) {
+        k = (uint32_t)idx;
+      } else if (mode == REC_T_SNAP) {
+        const int ns = sh_nsnap;
+        int s = 0;
+        while (s < ns && idx > (int64_t)sh_snap_idx[s]) ++s;
+        if (s >= ns) continue;  // after the last emitted surface: feeds nothing
+        aux = (uint32_t)s;
+      } else {  // REC_T_TORE: strict `<` against the sample time = last timestamp (tore.py:17)
+        if (t_rel >= tlast_rel) continue;
+      }
+      my_tmin = min(my_tmin, t_rel);
+      my_tmax = max(my_tmax, t_rel);
+      const uint32_t lin = ys[e] * (uint32_t)g.W + xs[e];
+      const uint32_t tile = lin >> g.tile_shift;
+      const uint32_t r = atomicAdd(&cnt[tile], 1u);
+      tile_rank[e] = (tile << 16) | r;
+      key[e] = k;
+      meta[e] = rec_meta(lin & (uint32_t)(g.tile_px - 1), aux, (uint32_t)pv & 3u);
+    }
+  }
+  // CTA-wide reductions of the per-window scalars
+  my_tmin = __reduce_min_sync(0xffffffffu, my_tmin);
+  my_tmax = __reduce_max_sync(0xffffffffu, my_tmax);
+  my_flags = __reduce_or_sync(0xffffffffu, my_flags);
+  my_m1 = __reduce_or_sync(0xffffffffu, my_m1);
+  if ((tid & 31) == 0) {
+    if (my_tmin != INT_MAX) { atomicMin(&sh_tmin, my_tmin); atomicMax(&sh_tmax, my_tmax); }
+    if (my_flags) atomicOr(&sh_flags, my_flags);
+    if (my_m1) atomicOr(&sh_m1, my_m1);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (sh_tmin != INT_MAX) { atomicMin(&wp[b].tmin_rel, sh_tmin); atomicMax(&wp[b].tmax_rel, sh_tmax); }
+    if (sh_flags) atomicOr(&wp[b].flags, sh_flags);
+    if (sh_m1) atomicOr(&wp[b].has_m1, sh_m1);
+  }
+  // reserve global space per bucket, then local offsets
+  const size_t bo = (size_t)b * g.T;
+  for (int i = tid; i < g.T; i += BIN_THREADS) {
+    const uint32_t c = cnt[i];
+    loff[i] = c;
+    if (c) gbase[i] = __ldg(base + bo + i) + atomicAdd(cursor + bo + i, c);
+  }
+  __syncthreads();
+  const uint32_t total = block_exclusive_scan(loff, g.T, warp_tot);
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) {
+    if (tile_rank[e] != 0xffffffffu) {
+      const uint32_t tile = tile_rank[e] >> 16, r = tile_rank[e] & 0xffffu;
+      const uint32_t s = loff[tile] + r;
+      stage[s] = make_uint2(key[e], meta[e]);
+      stile[s] = (uint16_t)tile;
+    }
+  }
+  __syncthreads();
+  uint2* dst = records + start;
+  for (uint32_t i = tid; i < total; i += BIN_THREADS) {
+    const uint32_t tile = stile[i];
+    dst[gbase[tile] + (i - loff[tile])] = stage[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int build_chunk_prefix(const int64_t* win_offsets_host, int B, std::vector<int32_t>& prefix) {
+  prefix.assign((size_t)B + 1, 0);
+  int64_t acc = 0;
+  for (int b = 0; b < B; ++b) {
+    const int64_t s = win_offsets_host[b], e = win_offsets_host[b + 1];
+    if (e < s || s < 0) {
+      set_error("win_offsets must be non-decreasing and non-negative (window %d: %lld..%lld)", b, (long long)s, (long long)e);
+      return EVREP_EINVAL;
+    }
+    if (e - s >= (int64_t)INT_MAX - 8) {
+      set_error("window %d holds %lld events; the limit is 2^31 - 9", b, (long long)(e - s));
+      return EVREP_EUNSUPPORTED;
+    }
+    const int64_t a = s & ~(int64_t)(EPT - 1);
+    acc += (e > s) ? (e - a + CHUNK - 1) / CHUNK : 0;
+    if (acc > INT_MAX) {
+      set_error("batch too large: more than 2^31 chunks");
+      return EVREP_EUNSUPPORTED;
+    }
+    prefix[(size_t)b + 1] = (int32_t)acc;
+  }
+  return EVREP_OK;
+}
+
+// uploads offsets + chunk prefix, initialises the per-window parameters.  Shared by the tile pipeline
+// and the direct-scatter ops.  Returns the number of chunks through *n_chunks.
+int prepare_windows(const Events& ev, const int64_t* win_offsets_host, const Geom& g, const Workspace& ws, int* n_chunks,
+                    cudaStream_t stream) {
+  std::vector<int32_t> prefix;
+  int rc = build_chunk_prefix(win_offsets_host, g.B, prefix);
+  if (rc) return rc;
+  if (win_offsets_host[g.B] > g.total) {
+    set_error("win_offsets[B] = %lld exceeds total_events = %lld", (long long)win_offsets_host[g.B], (long long)g.total);
+    return EVREP_EINVAL;
+  }
+  *n_chunks = prefix[(size_t)g.B];
+  // pageable-source async copies are staged before the call returns, so the host vectors may die here
+  EVREP_CUDA_OK(cudaMemcpyAsync(ws.offsets, win_offsets_host, sizeof(int64_t) * (size_t)(g.B + 1), cudaMemcpyHostToDevice, stream));
+  EVREP_CUDA_OK(cudaMemcpyAsync(ws.chunk_prefix, prefix.data(), sizeof(int32_t) * (size_t)(g.B + 1), cudaMemcpyHostToDevice, stream));
+  const int thr = 128, blocks = (g.B + thr - 1) / thr;
+  if (ev.t_bytes == 4)
+    k_init<int32_t><<<blocks, thr, 0, stream>>>((const int32_t*)ev.t, ws.offsets, g.B, ws.wp);
+  else
+    k_init<int64_t><<<blocks, thr, 0, stream>>>((const int64_t*)ev.t, ws.offsets, g.B, ws.wp);
+  EVREP_CUDA_OK(cudaGetLastError());
+  return EVREP_OK;
+}
+
+bool events_vectorisable(const Events& ev) { return aligned16(ev.x) && aligned16(ev.y) && aligned16(ev.t) && aligned16(ev.p); }
+
+int run_binning(const Events& ev, const int64_t* win_offsets_host, const Geom& g, const Workspace& ws, int rec_mode, int n_snap,
+                const int64_t* snap_indices_host, cudaStream_t stream) {
+  int n_chunks = 0;
+  int rc = prepare_windows(ev, win_offsets_host, g, ws, &n_chunks, stream);
+  if (rc) return rc;
+  EVREP_CUDA_OK(cudaMemsetAsync(ws.hist, 0, sizeof(uint32_t) * (size_t)g.B * g.T * 2, stream));  // hist + cursor
+  const bool vec = events_vectorisable(ev);
+
+  if (rec_mode == REC_T_SNAP) {
+    const int64_t* user = nullptr;
+    if (snap_indices_host) {
+      EVREP_CUDA_OK(cudaMemcpyAsync(ws.snap_in, snap_indices_host, sizeof(int64_t) * (size_t)g.B * n_snap, cudaMemcpyHostToDevice, stream));
+      user = ws.snap_in;
+    }
+    if (ev.t_bytes == 4)
+      k_snap_init<int32_t><<<g.B, 32, 0, stream>>>((const int32_t*)ev.t, ws.wp, user, n_snap, ws.snap);
+    else
+      k_snap_init<int64_t><<<g.B, 32, 0, stream>>>((const int64_t*)ev.t, ws.wp, user, n_snap, ws.snap);
+    EVREP_CUDA_OK(cudaGetLastError());
+  }
+  if (n_chunks > 0) {
+    k_hist<<<n_chunks, BIN_THREADS, sizeof(uint32_t) * (size_t)g.T, stream>>>(ev.x, ev.y, ws.wp, ws.chunk_prefix, g, vec, ws.hist);
+    EVREP_CUDA_OK(cudaGetLastError());
+  }
+  k_scan<<<g.B, BIN_THREADS, 0, stream>>>(ws.hist, ws.base, g.T);
+  EVREP_CUDA_OK(cudaGetLastError());
+  if (n_chunks > 0) {
+    const size_t smem = (size_t)CHUNK * (sizeof(uint2) + sizeof(uint16_t)) + 3 * sizeof(uint32_t) * (size_t)g.T;
+    if (ev.t_bytes == 4) {
+      EVREP_CUDA_OK(cudaFuncSetAttribute(k_bin<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_bin<int32_t><<<n_chunks, BIN_THREADS, smem, stream>>>(ev.x, ev.y, (const int32_t*)ev.t, ev.p, ws.wp, ws.snap, ws.chunk_prefix, g,
+                                                               vec, rec_mode, ws.base, ws.cursor, ws.records);
+    } else {
+      EVREP_CUDA_OK(cudaFuncSetAttribute(k_bin<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_bin<int64_t><<<n_chunks, BIN_THREADS, smem, stream>>>(ev.x, ev.y, (const int64_t*)ev.t, ev.p, ws.wp, ws.snap, ws.chunk_prefix, g,
+                                                               vec, rec_mode, ws.base, ws.cursor, ws.records);
+    }
+    EVREP_CUDA_OK(cudaGetLastError());
+  }
+  return EVREP_OK;
+}
+
+}  // namespace evrep

@@ -1,0 +1,166 @@
+// libevrep internals shared by every translation unit.  Nothing in here is part of the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/evrep.h"
+
+namespace evrep {
+
+// ------------------------------------------------------------------------------------------------
+// Binning geometry: the events of one window are cut into chunks of CHUNK events; one CTA bins one
+// chunk.  Chunks start at an absolute event index that is a multiple of EPT so every thread's EPT
+// consecutive events can be fetched with aligned 16-byte loads.
+// ------------------------------------------------------------------------------------------------
+constexpr int BIN_THREADS = 512;
+constexpr int EPT = 8;
+constexpr int CHUNK = BIN_THREADS * EPT;  // 4096 events per CTA
+constexpr int MAX_TILES = 4096;           // tiles per window (shared-memory histogram size bound)
+constexpr int MIN_TILE_PX = 256;
+constexpr int MAX_SNAP = 16;              // time-surface snapshots per window
+constexpr int TILE_THREADS = 512;
+constexpr int T_REL_LIMIT = 1 << 30;      // |t - t_first| must stay below this (microseconds)
+
+// record payload written by the binning pass
+enum RecMode : int {
+  REC_T_WMASK = 0,  // key = t_rel, aux = SBN window mask           (mixed density)
+  REC_IDX = 1,      // key = index inside window, aux = 0            (event stack)
+  REC_T_SNAP = 2,   // key = t_rel, aux = first snapshot it feeds    (time surface)
+  REC_T_TORE = 3,   // key = t_rel, events with t >= t_last dropped  (TORE)
+};
+// meta word: [15:0] pixel inside tile, [23:16] aux, [25:24] polarity code (p & 3: 0 -> 0, 1 -> +1, 3 -> -1)
+__host__ __device__ inline uint32_t rec_meta(uint32_t pix, uint32_t aux, uint32_t pc) { return pix | (aux << 16) | (pc << 24); }
+
+struct WinParams {  // one per window, lives at the start of the workspace
+  int64_t start;    // absolute index of the first event
+  int64_t n;        // number of events
+  int64_t t_base;   // timestamp of the first event (t_rel = t - t_base)
+  int32_t tmin_rel, tmax_rel;  // over accepted events
+  int32_t tlast_rel;           // timestamp of the last event, relative
+  uint32_t flags;              // EVREP_WF_*
+  uint32_t has_m1;             // bit w set: window w of the mixed-density split holds an event with p == -1
+  uint32_t pad;
+};
+
+struct SnapParams {  // time surface, one per window
+  int32_t idx[MAX_SNAP];    // snapshot event indices (valid prefix only)
+  int32_t t_rel[MAX_SNAP];  // timestamps at those indices
+  int32_t n_valid;          // surfaces that the reference actually emits
+  int32_t pad[3];
+};
+
+struct Geom {
+  int B, H, W, HW;
+  int tile_shift, tile_px, T;  // tile = contiguous range of tile_px linear pixel indices; T tiles per window
+  int64_t total;               // total events in the batch
+};
+
+struct Workspace {  // device pointers carved out of the caller's buffer
+  WinParams* wp;
+  int64_t* offsets;
+  int32_t* chunk_prefix;
+  uint32_t* hist;    // B*T   bucket sizes (upper bound, from the counting pass)
+  uint32_t* cursor;  // B*T   records actually written
+  uint32_t* base;    // B*T   bucket start, relative to the window's first record
+  SnapParams* snap;  // B
+  int64_t* snap_in;  // B*MAX_SNAP caller-supplied snapshot indices
+  double* stats;     // B*4   voxel normalisation sums
+  uint2* records;    // total events
+  size_t bytes;
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Carves the workspace; with base == nullptr only computes the size.
+inline Workspace carve(void* basep, int B, int64_t total, int T) {
+  Workspace w;
+  size_t off = 0;
+  char* base = (char*)basep;
+  auto take = [&](size_t bytes) {
+    char* p = base ? base + off : nullptr;
+    off += align_up(bytes, 256);
+    return p;
+  };
+  w.wp = (WinParams*)take(sizeof(WinParams) * (size_t)B);
+  w.offsets = (int64_t*)take(sizeof(int64_t) * (size_t)(B + 1));
+  w.chunk_prefix = (int32_t*)take(sizeof(int32_t) * (size_t)(B + 1));
+  w.hist = (uint32_t*)take(sizeof(uint32_t) * (size_t)B * T * 2);
+  w.cursor = w.hist ? w.hist + (size_t)B * T : nullptr;
+  w.base = (uint32_t*)take(sizeof(uint32_t) * (size_t)B * T);
+  w.snap = (SnapParams*)take(sizeof(SnapParams) * (size_t)B);
+  w.snap_in = (int64_t*)take(sizeof(int64_t) * (size_t)B * MAX_SNAP);
+  w.stats = (double*)take(sizeof(double) * 4 * (size_t)B);
+  w.records = (uint2*)take(sizeof(uint2) * (size_t)(total > 0 ? total : 1));
+  w.bytes = off;
+  return w;
+}
+
+// thread-local error text (api.cu)
+void set_error(const char* fmt, ...);
+
+#define EVREP_CUDA_OK(expr)                                                                  \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      evrep::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return EVREP_ECUDA;                                                                    \
+    }                                                                                        \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// Mixed-density accumulator plan (built on the host from the (window, function, aggregation) tuple)
+// ------------------------------------------------------------------------------------------------
+enum { G_CNT = 1, G_PRES = 2, G_MAX = 4, G_ST = 8, G_ST2 = 16 };
+constexpr int MD_MAX_GROUPS = 24;
+
+struct MdGroup {   // one (window, polarity class) pair that some channel reads
+  uint8_t bit;     // membership bit: class * 8 + window, class 0 = all, 1 = p == 1, 2 = "negative"
+  uint8_t flags;   // G_*
+  uint8_t w_cnt, w_max, w_st, w_st2;  // accumulator word indices
+  uint8_t pres_bit;
+  uint8_t pad;
+};
+struct MdChan {
+  uint8_t func, agg, win, valid;
+  int8_t g_main, g_all, g_pos, g_neg;
+};
+struct MdPlan {
+  int32_t C, G, words, nl1, nl2, lw, w_pres, stacking;
+  MdGroup grp[MD_MAX_GROUPS];
+  MdChan ch[EVREP_MAX_CHANNELS];
+};
+
+// ------------------------------------------------------------------------------------------------
+// Launchers (each returns an EVREP_* code and enqueues on `stream`)
+// ------------------------------------------------------------------------------------------------
+struct Events {
+  const uint16_t* x;
+  const uint16_t* y;
+  const void* t;
+  int t_bytes;
+  const int8_t* p;
+};
+
+// memset + offsets upload + per-window init + count + scan + bin.  After it returns (stream order)
+// ws.records holds the tile-bucketed records, ws.cursor the bucket sizes, ws.base the bucket starts.
+int run_binning(const Events& ev, const int64_t* win_offsets_host, const Geom& g, const Workspace& ws, int rec_mode,
+                int n_snap, const int64_t* snap_indices_host, cudaStream_t stream);
+
+int prepare_windows(const Events& ev, const int64_t* win_offsets_host, const Geom& g, const Workspace& ws, int* n_chunks,
+                    cudaStream_t stream);
+bool events_vectorisable(const Events& ev);
+
+int launch_md_tile(const Geom& g, const Workspace& ws, const MdPlan& plan, const Events& ev, float* out, cudaStream_t stream);
+int launch_event_stack_tile(const Geom& g, const Workspace& ws, int stack_size, float* out, cudaStream_t stream);
+int launch_time_surface_tile(const Geom& g, const Workspace& ws, int S, double tau, float* out, cudaStream_t stream);
+int launch_tore_tile(const Geom& g, const Workspace& ws, int k, float* out, cudaStream_t stream);
+
+int launch_voxel(const Events& ev, const int64_t* win_offsets_host, const Geom& g, const Workspace& ws, int flavour,
+                 int n_bins, int normalize, const int64_t* t0_t1_host, float* out, cudaStream_t stream);
+int launch_histogram(const Events& ev, const int64_t* win_offsets_host, const Geom& g, const Workspace& ws, float* out,
+                     cudaStream_t stream);
+
+size_t md_tile_smem_bytes(const MdPlan& plan, int tile_px);
+
+}  // namespace evrep

@@ -1,0 +1,297 @@
+// MixedDensityEventStack / ERGO-12: per-tile shared-memory reduction + fused finalise.
+//
+// One CTA owns one (window, tile) bucket produced by binning.cu.  It keeps, for every pixel of the tile,
+// the integer accumulators the requested channels need (event counts, presence bits, latest timestamp,
+// and exact multi-limb sums of t and t^2), updates them with native 32-bit shared-memory atomics, and
+// then turns them into the C float32 channels of its output slice, written once, coalesced.
+//
+// Reference semantics: representations/representation_search/operations.py:15-89 (what each
+// (function, aggregation) pair computes), mixed_density_event_stack.py:25-151 (windows, t normalisation,
+// swallow-and-zero), optimized_representation.py:86-134 (the ERGO-12 tuple).
+#include <string.h>
+
+#include "evrep_common.cuh"
+
+namespace evrep {
+
+size_t md_tile_smem_bytes(const MdPlan& plan, int tile_px) { return (size_t)plan.words * (size_t)tile_px * sizeof(uint32_t); }
+
+// ---------------------------------------------------------------------------------------------
+// host: (window, function, aggregation) tuple -> accumulator plan
+// ---------------------------------------------------------------------------------------------
+int build_md_plan(const int8_t* win, const int8_t* func, const int8_t* agg, int C, int stacking, int64_t n_max, MdPlan* out) {
+  MdPlan& P = *out;
+  memset(&P, 0, sizeof(P));
+  if (C < 1 || C > EVREP_MAX_CHANNELS) {
+    set_error("C = %d outside 1..%d", C, EVREP_MAX_CHANNELS);
+    return EVREP_EINVAL;
+  }
+  if (stacking != EVREP_STACK_SBN && stacking != EVREP_STACK_SBT) {
+    set_error("stacking must be EVREP_STACK_SBN or EVREP_STACK_SBT");
+    return EVREP_EINVAL;
+  }
+  P.C = C;
+  P.stacking = stacking;
+  // limb width: a limb sum over at most n_max events must fit 32 bits
+  int nbits = 0;
+  while (nbits < 31 && ((int64_t)1 << nbits) <= n_max) ++nbits;  // n_max < 2^nbits
+  P.lw = 32 - nbits;
+  if (P.lw > 31) P.lw = 31;
+  if (P.lw < 1) P.lw = 1;
+  P.nl1 = (31 + P.lw - 1) / P.lw;
+  P.nl2 = (62 + P.lw - 1) / P.lw;
+
+  const int n_win = stacking == EVREP_STACK_SBN ? 7 : 8;
+  auto group = [&](int w, int cls, int need) -> int {
+    const int bit = cls * 8 + w;
+    for (int g = 0; g < P.G; ++g)
+      if (P.grp[g].bit == bit) { P.grp[g].flags |= (uint8_t)need; return g; }
+    P.grp[P.G].bit = (uint8_t)bit;
+    P.grp[P.G].flags = (uint8_t)need;
+    return P.G++;
+  };
+  for (int c = 0; c < C; ++c) {
+    MdChan& ch = P.ch[c];
+    int wi = win[c];
+    if (wi < 0 && wi >= -n_win) wi += n_win;  // the reference indexes a Python list: negative indices wrap
+    ch.func = (uint8_t)func[c];
+    ch.agg = (uint8_t)agg[c];
+    ch.win = (uint8_t)wi;
+    ch.g_main = ch.g_all = ch.g_pos = ch.g_neg = -1;
+    // an unknown window / function / aggregation raises inside the reference's make_stack and is
+    // swallowed into an all-zero channel (mixed_density_event_stack.py:120-127)
+    if (wi < 0 || wi >= n_win || func[c] < 0 || func[c] > EVREP_FUNC_COUNT_NEG || agg[c] < 0 || agg[c] > EVREP_AGG_VARIANCE) {
+      ch.valid = 0;
+      continue;
+    }
+    ch.valid = 1;
+    const int f = func[c], a = agg[c], w = wi;
+    if (f == EVREP_FUNC_POLARITY) {
+      ch.g_pos = (int8_t)group(w, 1, G_CNT);
+      ch.g_neg = (int8_t)group(w, 2, G_CNT);
+      if (a != EVREP_AGG_SUM) ch.g_all = (int8_t)group(w, 0, G_CNT);
+      continue;
+    }
+    const bool is_count = (f == EVREP_FUNC_COUNT || f == EVREP_FUNC_COUNT_POS || f == EVREP_FUNC_COUNT_NEG);
+    const int cls = (f == EVREP_FUNC_COUNT || f == EVREP_FUNC_TIMESTAMP) ? 0
+                    : (f == EVREP_FUNC_COUNT_POS || f == EVREP_FUNC_TIMESTAMP_POS) ? 1 : 2;
+    int need = 0;
+    if (is_count) {
+      need = a == EVREP_AGG_SUM ? G_CNT : (a == EVREP_AGG_VARIANCE ? 0 : G_PRES);
+      if (need == 0) { ch.g_main = -1; continue; }  // variance of a constant: 0 everywhere
+    } else {
+      need = a == EVREP_AGG_SUM ? (G_ST | G_PRES) : a == EVREP_AGG_MEAN ? (G_ST | G_CNT) : a == EVREP_AGG_MAX ? G_MAX : (G_ST | G_ST2 | G_CNT);
+    }
+    ch.g_main = (int8_t)group(w, cls, need);
+  }
+  // word assignment
+  int words = 0, pres_bits = 0;
+  bool any_pres = false;
+  for (int g = 0; g < P.G; ++g) {
+    MdGroup& G = P.grp[g];
+    if (G.flags & G_CNT) G.flags &= (uint8_t)~G_PRES;  // a count subsumes the presence bit
+    if ((G.flags & G_PRES) && (G.flags & G_MAX)) G.flags &= (uint8_t)~G_PRES;  // so does a latest-timestamp word
+    if (G.flags & G_PRES) any_pres = true;
+  }
+  if (any_pres) P.w_pres = words++;
+  for (int g = 0; g < P.G; ++g) {
+    MdGroup& G = P.grp[g];
+    if (G.flags & G_PRES) G.pres_bit = (uint8_t)pres_bits++;
+    if (G.flags & G_CNT) G.w_cnt = (uint8_t)words++;
+    if (G.flags & G_MAX) G.w_max = (uint8_t)words++;
+    if (G.flags & G_ST) { G.w_st = (uint8_t)words; words += P.nl1; }
+    if (G.flags & G_ST2) { G.w_st2 = (uint8_t)words; words += P.nl2; }
+    if (words > 250) {
+      set_error("mixed-density plan needs more than 250 accumulator words per pixel");
+      return EVREP_EUNSUPPORTED;
+    }
+  }
+  if (words == 0) words = 1;
+  P.words = words;
+  return EVREP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t md_touched(const MdPlan& P, const MdGroup& G, const uint32_t* acc, int TP, int pix) {
+  if (G.flags & G_CNT) return acc[G.w_cnt * TP + pix];
+  if (G.flags & G_MAX) return acc[G.w_max * TP + pix] != 0u;
+  if (G.flags & G_PRES) return (acc[P.w_pres * TP + pix] >> G.pres_bit) & 1u;
+  return 0u;
+}
+
+__device__ __forceinline__ double md_limb_sum(const uint32_t* acc, int TP, int pix, int w0, int nl, int lw) {
+  double s = 0.0, scale = 1.0;
+  const double step = (double)(1u << lw);
+  for (int l = 0; l < nl; ++l) {
+    s += (double)acc[(w0 + l) * TP + pix] * scale;
+    scale *= step;
+  }
+  return s;
+}
+
+__device__ float md_value(const MdPlan& P, const MdChan& ch, const uint32_t* acc, int TP, int pix, double delta, uint32_t has_m1) {
+  if (!ch.valid) return 0.f;
+  if (ch.func == EVREP_FUNC_POLARITY) {
+    const double c1 = (double)acc[P.grp[ch.g_pos].w_cnt * TP + pix];
+    const double cm = ((has_m1 >> ch.win) & 1u) ? (double)acc[P.grp[ch.g_neg].w_cnt * TP + pix] : 0.0;
+    if (ch.agg == EVREP_AGG_SUM) return (float)(c1 - cm);
+    const double call = (double)acc[P.grp[ch.g_all].w_cnt * TP + pix];
+    if (call == 0.0) return 0.f;
+    if (ch.agg == EVREP_AGG_MEAN) return (float)((c1 - cm) / call);
+    if (ch.agg == EVREP_AGG_VARIANCE) {
+      const double m = (c1 - cm) / call, m2 = (c1 + cm) / call;
+      return (float)(m2 - m * m);
+    }
+    return c1 > 0.0 ? 1.f : (call - c1 - cm > 0.0 ? 0.f : -1.f);  // max of the raw polarities
+  }
+  if (ch.g_main < 0) return 0.f;
+  const MdGroup& G = P.grp[ch.g_main];
+  const uint32_t c = md_touched(P, G, acc, TP, pix);
+  if (c == 0u) return 0.f;  // torch_scatter leaves untouched pixels at 0
+  const bool is_count = (ch.func == EVREP_FUNC_COUNT || ch.func == EVREP_FUNC_COUNT_POS || ch.func == EVREP_FUNC_COUNT_NEG);
+  if (is_count) return ch.agg == EVREP_AGG_SUM ? (float)c : 1.f;
+  // timestamps: t_s = (t - t_min) / (t_max - t_min); delta == 0 gives NaN exactly like the reference
+  if (ch.agg == EVREP_AGG_MAX) return (float)((double)(acc[G.w_max * TP + pix] - 1u) / delta);
+  const double st = md_limb_sum(acc, TP, pix, G.w_st, P.nl1, P.lw);
+  if (ch.agg == EVREP_AGG_SUM) return (float)(st / delta);
+  const double m = st / delta / (double)c;
+  if (ch.agg == EVREP_AGG_MEAN) return (float)m;
+  const double st2 = md_limb_sum(acc, TP, pix, G.w_st2, P.nl2, P.lw);
+  const double m2 = st2 / delta / delta / (double)c;
+  return (float)(m2 - m * m);
+}
+
+__global__ void __launch_bounds__(TILE_THREADS) k_md_tile(const uint2* __restrict__ records, const uint32_t* __restrict__ base,
+                                                          const uint32_t* __restrict__ cursor, const WinParams* __restrict__ wp,
+                                                          const __grid_constant__ MdPlan P, const Geom g, float* __restrict__ out) {
+  extern __shared__ __align__(16) uint32_t acc[];
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x / g.T, tile = blockIdx.x - b * g.T;
+  const int TP = g.tile_px;
+  const int pix0 = tile << g.tile_shift;
+  const int npix = min(TP, g.HW - pix0);
+
+  {  // zero the accumulators
+    uint4* a4 = reinterpret_cast<uint4*>(acc);
+    const int n4 = P.words * TP / 4;
+    for (int i = tid; i < n4; i += TILE_THREADS) a4[i] = make_uint4(0, 0, 0, 0);
+  }
+  const WinParams w = wp[b];
+  const uint32_t count = cursor[blockIdx.x];
+  const uint2* rec = records + w.start + base[blockIdx.x];
+  const int32_t tmin = w.tmin_rel;
+  const uint32_t delta_u = (w.tmax_rel >= w.tmin_rel) ? (uint32_t)(w.tmax_rel - w.tmin_rel) : 0u;
+  const double delta = (double)delta_u;
+  const uint32_t limb_mask = (P.lw >= 32) ? 0xffffffffu : ((1u << P.lw) - 1u);
+  __syncthreads();
+
+  for (uint32_t i = tid; i < count; i += TILE_THREADS) {
+    const uint2 r = __ldg(rec + i);
+    const uint32_t pix = r.y & 0xffffu;
+    const uint32_t pc = (r.y >> 24) & 3u;
+    const uint32_t tt = (uint32_t)((int32_t)r.x - tmin);  // t - t_min, < 2^31
+    uint32_t wmask;
+    if (P.stacking == EVREP_STACK_SBN) {
+      wmask = (r.y >> 16) & 0xffu;
+    } else {
+      // SBT windows (mixed_density_event_stack.py:76-107): float64 comparisons on t_s
+      const double ts = (double)tt / delta;
+      const double f = 1.0 / 3.0;
+      wmask = 1u;
+      if (ts <= 1.0 * f && ts >= 0.0 * f) wmask |= 2u;
+      if (ts <= 2.0 * f && ts >= 1.0 * f) wmask |= 4u;
+      if (ts <= 3.0 * f && ts >= 2.0 * f) wmask |= 8u;
+      if (ts <= 0.5) wmask |= 16u;
+      if (ts <= 0.25) wmask |= 32u;
+      if (ts <= 0.125) wmask |= 64u;
+      if (ts <= 0.0625) wmask |= 128u;
+    }
+    // "negative" events of a window: p == -1, or p == 0 when the window holds no -1 (operations.py:59-61,78-80)
+    const uint32_t posm = (pc == 1u) ? wmask : 0u;
+    const uint32_t negm = (pc == 3u) ? wmask : (pc == 0u ? (wmask & ~w.has_m1) : 0u);
+    const uint32_t M = wmask | (posm << 8) | (negm << 16);
+    uint32_t pres = 0;
+    for (int gi = 0; gi < P.G; ++gi) {
+      const MdGroup G = P.grp[gi];
+      if (!((M >> G.bit) & 1u)) continue;
+      if (G.flags & G_CNT) atomicAdd(&acc[G.w_cnt * TP + pix], 1u);
+      if (G.flags & G_PRES) pres |= 1u << G.pres_bit;
+      if (G.flags & G_MAX) atomicMax(&acc[G.w_max * TP + pix], tt + 1u);
+      if (G.flags & G_ST) {
+        uint32_t v = tt;
+        for (int l = 0; l < P.nl1 && v; ++l, v = (P.lw >= 32 ? 0u : v >> P.lw)) {
+          const uint32_t limb = v & limb_mask;
+          if (limb) atomicAdd(&acc[(G.w_st + l) * TP + pix], limb);
+        }
+      }
+      if (G.flags & G_ST2) {
+        unsigned long long v = (unsigned long long)tt * (unsigned long long)tt;
+        for (int l = 0; l < P.nl2 && v; ++l, v >>= P.lw) {
+          const uint32_t limb = (uint32_t)v & limb_mask;
+          if (limb) atomicAdd(&acc[(G.w_st2 + l) * TP + pix], limb);
+        }
+      }
+    }
+    if (pres) {
+      uint32_t* pw = &acc[P.w_pres * TP + pix];
+      if ((*(volatile uint32_t*)pw & pres) != pres) atomicOr(pw, pres);
+    }
+  }
+  __syncthreads();
+
+  // finalise: thread e -> (pixel e / C, channel e % C); consecutive threads write consecutive floats
+  const int C = P.C;
+  float* dst = out + ((size_t)b * g.HW + pix0) * C;
+  const int n_el = npix * C;
+  for (int e = tid; e < n_el; e += TILE_THREADS) {
+    const int pix = e / C, c = e - pix * C;
+    dst[e] = md_value(P, P.ch[c], acc, TP, pix, delta, w.has_m1);
+  }
+}
+
+// SBT only: which time windows hold a p == -1 event (needed before the tile pass can decide what
+// "negative" means in each window).  Runs after the binning pass, which produced t_min / t_max.
+template <typename TT>
+__global__ void k_sbt_negsel(const TT* __restrict__ t, const int8_t* __restrict__ p, WinParams* __restrict__ wp) {
+  const int b = blockIdx.y;
+  const WinParams w = wp[b];
+  const double delta = (w.tmax_rel >= w.tmin_rel) ? (double)(uint32_t)(w.tmax_rel - w.tmin_rel) : 0.0;
+  uint32_t m = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < w.n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (p[w.start + i] != -1) continue;
+    const int64_t d = (int64_t)t[w.start + i] - w.t_base;
+    if (d >= T_REL_LIMIT || d <= -T_REL_LIMIT) continue;
+    const double ts = (double)(uint32_t)((int32_t)d - w.tmin_rel) / delta;
+    const double f = 1.0 / 3.0;
+    m |= 1u;
+    if (ts <= 1.0 * f && ts >= 0.0 * f) m |= 2u;
+    if (ts <= 2.0 * f && ts >= 1.0 * f) m |= 4u;
+    if (ts <= 3.0 * f && ts >= 2.0 * f) m |= 8u;
+    if (ts <= 0.5) m |= 16u;
+    if (ts <= 0.25) m |= 32u;
+    if (ts <= 0.125) m |= 64u;
+    if (ts <= 0.0625) m |= 128u;
+  }
+  m = __reduce_or_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0 && m) atomicOr(&wp[b].has_m1, m);
+}
+
+int launch_md_tile(const Geom& g, const Workspace& ws, const MdPlan& plan, const Events& ev, float* out, cudaStream_t stream) {
+  if (plan.stacking == EVREP_STACK_SBT) {
+    dim3 grid(64, g.B);
+    if (ev.t_bytes == 4)
+      k_sbt_negsel<int32_t><<<grid, 256, 0, stream>>>((const int32_t*)ev.t, ev.p, ws.wp);
+    else
+      k_sbt_negsel<int64_t><<<grid, 256, 0, stream>>>((const int64_t*)ev.t, ev.p, ws.wp);
+    EVREP_CUDA_OK(cudaGetLastError());
+  }
+  const size_t smem = md_tile_smem_bytes(plan, g.tile_px);
+  EVREP_CUDA_OK(cudaFuncSetAttribute(k_md_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_md_tile<<<g.B * g.T, TILE_THREADS, smem, stream>>>(ws.records, ws.base, ws.cursor, ws.wp, plan, g, out);
+  EVREP_CUDA_OK(cudaGetLastError());
+  return EVREP_OK;
+}
+
+}  // namespace evrep

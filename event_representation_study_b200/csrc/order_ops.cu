@@ -1,0 +1,193 @@
+// The three "latest event wins" representations on top of the tile buckets of binning.cu:
+//   EventStack   representations/event_stack.py:15-131 as called at gen1_transforms.py:33-42
+//   TimeSurface  representations/time_surface.py:25-74 as called at gen1_transforms.py:69-87
+//   TORE         representations/tore.py:6-83 as called at gen1_transforms.py:51-67
+// The order-dependent stores of the reference (np.put, timestamp_memory[...] = t, the per-pixel FIFO)
+// become order-independent integer atomicMax operations on keys that grow with stream order, so the
+// result does not depend on which thread gets there first.
+#include <math.h>
+
+#include "evrep_common.cuh"
+
+namespace evrep {
+
+__device__ __forceinline__ void zero_smem(uint32_t* acc, int n_words) {
+  uint4* a4 = reinterpret_cast<uint4*>(acc);
+  for (int i = threadIdx.x; i < n_words / 4; i += TILE_THREADS) a4[i] = make_uint4(0, 0, 0, 0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// EventStack: out[y, x, k] = polarity sign of the latest event at the pixel if its index >= s_k else 0,
+// s_k = start of the k-th nested suffix window (event_stack.py:70-82: c //= 2; x = x[c:]).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TILE_THREADS) k_event_stack_tile(const uint2* __restrict__ records, const uint32_t* __restrict__ base,
+                                                                   const uint32_t* __restrict__ cursor, const WinParams* __restrict__ wp,
+                                                                   const Geom g, int K, float* __restrict__ out) {
+  extern __shared__ __align__(16) uint32_t acc[];
+  __shared__ uint32_t s_start[EVREP_MAX_CHANNELS];
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x / g.T, tile = blockIdx.x - b * g.T;
+  const int TP = g.tile_px, pix0 = tile << g.tile_shift, npix = min(TP, g.HW - pix0);
+  zero_smem(acc, TP);
+  const WinParams w = wp[b];
+  if (tid == 0) {
+    int64_t c = w.n, s = 0;
+    for (int k = 0; k < K; ++k) {
+      s_start[k] = (uint32_t)min(s, w.n);
+      c /= 2;
+      s += c;
+    }
+  }
+  const uint32_t count = cursor[blockIdx.x];
+  const uint2* rec = records + w.start + base[blockIdx.x];
+  __syncthreads();
+  for (uint32_t i = tid; i < count; i += TILE_THREADS) {
+    const uint2 r = __ldg(rec + i);
+    const uint32_t pol = (((r.y >> 24) & 3u) == 1u) ? 1u : 0u;  // p > 0
+    atomicMax(&acc[r.y & 0xffffu], ((r.x + 1u) << 1) | pol);
+  }
+  __syncthreads();
+  float* dst = out + ((size_t)b * g.HW + pix0) * K;
+  const int n_el = npix * K;
+  for (int e = tid; e < n_el; e += TILE_THREADS) {
+    const int pix = e / K, k = e - pix * K;
+    const uint32_t v = acc[pix];
+    float o = 0.f;
+    if (v && ((v >> 1) - 1u) >= s_start[k]) o = (v & 1u) ? 1.f : -1.f;
+    dst[e] = o;
+  }
+}
+
+int launch_event_stack_tile(const Geom& g, const Workspace& ws, int stack_size, float* out, cudaStream_t stream) {
+  const size_t smem = sizeof(uint32_t) * (size_t)g.tile_px;
+  EVREP_CUDA_OK(cudaFuncSetAttribute(k_event_stack_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_event_stack_tile<<<g.B * g.T, TILE_THREADS, smem, stream>>>(ws.records, ws.base, ws.cursor, ws.wp, g, stack_size, out);
+  EVREP_CUDA_OK(cudaGetLastError());
+  return EVREP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// TimeSurface: surface s = exp((mem - t_s) / tau), mem = timestamp of the latest event at
+// (polarity, y, x) with index <= indices[s], or -(3 tau + 1) where there is none.
+// Shared memory holds, per (first snapshot fed, polarity, pixel), the latest timestamp; a running
+// maximum over the snapshot axis reproduces the sequential memory of time_surface.py:66-74.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TILE_THREADS) k_time_surface_tile(const uint2* __restrict__ records, const uint32_t* __restrict__ base,
+                                                                    const uint32_t* __restrict__ cursor, const WinParams* __restrict__ wp,
+                                                                    const SnapParams* __restrict__ snap, const Geom g, int S, double tau,
+                                                                    float* __restrict__ out) {
+  extern __shared__ __align__(16) uint32_t acc[];  // [S][2][TP]
+  __shared__ int32_t s_trel[MAX_SNAP];
+  __shared__ float s_empty[MAX_SNAP];
+  __shared__ int s_nvalid;
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x / g.T, tile = blockIdx.x - b * g.T;
+  const int TP = g.tile_px, pix0 = tile << g.tile_shift, npix = min(TP, g.HW - pix0);
+  zero_smem(acc, S * 2 * TP);
+  const WinParams w = wp[b];
+  if (tid < MAX_SNAP) {
+    const int32_t tr = snap[b].t_rel[tid];
+    s_trel[tid] = tr;
+    // untouched pixels: exp((-(3 tau + 1) - t_snapshot) / tau) with the ABSOLUTE snapshot timestamp
+    s_empty[tid] = (float)exp((-(tau * 3.0 + 1.0) - (double)(w.t_base + (int64_t)tr)) / tau);
+  }
+  if (tid == 0) s_nvalid = snap[b].n_valid;
+  const uint32_t count = cursor[blockIdx.x];
+  const uint2* rec = records + w.start + base[blockIdx.x];
+  const int32_t tmin = w.tmin_rel;
+  __syncthreads();
+  for (uint32_t i = tid; i < count; i += TILE_THREADS) {
+    const uint2 r = __ldg(rec + i);
+    const uint32_t s = (r.y >> 16) & 0xffu;
+    const uint32_t plane = (((r.y >> 24) & 3u) == 1u) ? 1u : 0u;
+    atomicMax(&acc[(s * 2u + plane) * TP + (r.y & 0xffffu)], (uint32_t)((int32_t)r.x - tmin) + 1u);
+  }
+  __syncthreads();
+  const double inv_tau = 1.0 / tau;
+  const int nvalid = s_nvalid;
+  for (int e = tid; e < 2 * npix; e += TILE_THREADS) {
+    const int plane = e / npix, pix = e - plane * npix;
+    uint32_t m = 0;
+    for (int s = 0; s < S; ++s) {
+      m = max(m, acc[(s * 2 + plane) * TP + pix]);
+      float o = 0.f;
+      if (s < nvalid) {
+        if (m) {
+          const int64_t mem_rel = (int64_t)(m - 1u) + (int64_t)tmin;
+          o = expf((float)((double)(mem_rel - (int64_t)s_trel[s]) * inv_tau));
+        } else {
+          o = s_empty[s];
+        }
+      }
+      out[(((size_t)b * S + s) * 2 + plane) * g.HW + pix0 + pix] = o;
+    }
+  }
+}
+
+int launch_time_surface_tile(const Geom& g, const Workspace& ws, int S, double tau, float* out, cudaStream_t stream) {
+  const size_t smem = sizeof(uint32_t) * (size_t)g.tile_px * 2 * S;
+  EVREP_CUDA_OK(cudaFuncSetAttribute(k_time_surface_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_time_surface_tile<<<g.B * g.T, TILE_THREADS, smem, stream>>>(ws.records, ws.base, ws.cursor, ws.wp, ws.snap, g, S, tau, out);
+  EVREP_CUDA_OK(cudaGetLastError());
+  return EVREP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// TORE: per pixel and polarity class the k most recent ages T - t among events with t < T
+// (T = timestamp of the window's last event), ascending, then the float32 log compression of
+// tore.py:69-79.  The FIFO of the reference becomes a cascade of atomicMax: slot j receives what
+// slot j-1 displaced, which leaves the k largest timestamps sorted whatever the arrival order,
+// duplicates included.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TILE_THREADS) k_tore_tile(const uint2* __restrict__ records, const uint32_t* __restrict__ base,
+                                                            const uint32_t* __restrict__ cursor, const WinParams* __restrict__ wp,
+                                                            const Geom g, int K, float* __restrict__ out) {
+  extern __shared__ __align__(16) uint32_t acc[];  // [2][K][TP]
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x / g.T, tile = blockIdx.x - b * g.T;
+  const int TP = g.tile_px, pix0 = tile << g.tile_shift, npix = min(TP, g.HW - pix0);
+  zero_smem(acc, 2 * K * TP);
+  const WinParams w = wp[b];
+  const uint32_t count = cursor[blockIdx.x];
+  const uint2* rec = records + w.start + base[blockIdx.x];
+  const int32_t tmin = w.tmin_rel;
+  __syncthreads();
+  for (uint32_t i = tid; i < count; i += TILE_THREADS) {
+    const uint2 r = __ldg(rec + i);
+    const uint32_t plane = (((r.y >> 24) & 3u) == 1u) ? 0u : 1u;  // positive first (tore.py:63-65)
+    uint32_t v = (uint32_t)((int32_t)r.x - tmin) + 1u;
+    uint32_t* slot = &acc[plane * K * TP + (r.y & 0xffffu)];
+    for (int j = 0; j < K && v; ++j) {
+      const uint32_t old = atomicMax(slot + j * TP, v);
+      v = min(old, v);
+    }
+  }
+  __syncthreads();
+  const float max_time = 500e6f;
+  const float log151 = (float)log(151.0);
+  const float empty = fmaxf(logf(max_time + 1.f) - log151, 0.f);
+  float* dst = out + ((size_t)b * g.HW + pix0) * (2 * K);
+  const int n_el = npix * 2 * K;
+  for (int e = tid; e < n_el; e += TILE_THREADS) {
+    const int pix = e / (2 * K), c = e - pix * 2 * K;
+    const uint32_t v = acc[c * TP + pix];
+    float o = empty;
+    if (v) {
+      const int64_t t_rel = (int64_t)(v - 1u) + (int64_t)tmin;
+      float age = (float)((int64_t)w.tlast_rel - t_rel);
+      age = fminf(age, max_time);
+      o = fmaxf(logf(age + 1.f) - log151, 0.f);
+    }
+    dst[e] = o;
+  }
+}
+
+int launch_tore_tile(const Geom& g, const Workspace& ws, int k, float* out, cudaStream_t stream) {
+  const size_t smem = sizeof(uint32_t) * (size_t)g.tile_px * 2 * k;
+  EVREP_CUDA_OK(cudaFuncSetAttribute(k_tore_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_tore_tile<<<g.B * g.T, TILE_THREADS, smem, stream>>>(ws.records, ws.base, ws.cursor, ws.wp, g, k, out);
+  EVREP_CUDA_OK(cudaGetLastError());
+  return EVREP_OK;
+}
+
+}  // namespace evrep

@@ -1,0 +1,165 @@
+/*
+ * libevrep - B200-native event-representation engine: C ABI.
+ *
+ * This header is the drop-in boundary.  Every entry point takes plain pointers
+ * and sizes (no C++ / torch types), enqueues all device work on the caller's stream, allocates nothing
+ * persistent (scratch comes from the caller's workspace, sized by evrep_workspace_bytes), overwrites
+ * its output completely and returns 0 or a negative EVREP_E* code; evrep_last_error() gives the
+ * thread-local message.  Nothing here throws or calls exit().
+ *
+ * Event batches are SoA + CSR: x,y (uint16), t (int32 or int64 microseconds, see t_bytes), p (int8 in
+ * {-1,0,+1}) are DEVICE pointers to `total_events` elements; window b owns
+ * [win_offsets[b], win_offsets[b+1]).  `win_offsets` is a HOST pointer to B+1 int64 (the collate step
+ * that builds a batch knows the window sizes on the host; the library copies them to the device).
+ * Events inside one window must be in stream order (the order the reference's loaders deliver them);
+ * representations that are order dependent say so below.
+ *
+ * Outputs are DEVICE float32, batch-major, in the layout the reference produces for one window.
+ *
+ * Reference interfaces replaced (paths relative to the reference repository root):
+ *   evrep_mixed_density_batched  representations/representation_search/mixed_density_event_stack.py:25-46
+ *                                (+ operations.py:15-89), one call per window there
+ *   evrep_ergo12_batched         representations/optimized_representation.py:86-134
+ *   evrep_event_stack_batched    representations/event_stack.py:15-63 as called at gen1_transforms.py:33-42
+ *   evrep_time_surface_batched   representations/time_surface.py:25-74 as called at gen1_transforms.py:69-87
+ *   evrep_tore_batched           representations/tore.py:6-83 as called at gen1_transforms.py:51-67
+ *   evrep_voxel_batched          tonic ToVoxelGrid (gen1_transforms.py:21-25);
+ *                                ev-licious/src/evlicious/tools/utils.py:51-85 (events_to_voxel_grid);
+ *                                representation_search/gromov_wasserstein.py:72-82 (compute_repr)
+ *   evrep_histogram_batched      tonic ToImage (gen1_transforms.py:44-49)
+ *   evrep_gwd_kernel_l1          representation_search/compute_otmi.py:50-93 (OTMI.__init__ + solve, GWD-A)
+ */
+#ifndef EVREP_H
+#define EVREP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EVREP_VERSION 100 /* 0.1.0 */
+
+/* return codes */
+#define EVREP_OK 0
+#define EVREP_EINVAL (-1)       /* bad argument */
+#define EVREP_EWORKSPACE (-2)   /* workspace too small / misaligned */
+#define EVREP_ECUDA (-3)        /* a CUDA runtime call failed */
+#define EVREP_EUNSUPPORTED (-4) /* valid request outside the implemented envelope */
+
+/* ops, for evrep_workspace_bytes */
+#define EVREP_OP_MIXED_DENSITY 1
+#define EVREP_OP_EVENT_STACK 2
+#define EVREP_OP_TIME_SURFACE 3
+#define EVREP_OP_TORE 4
+#define EVREP_OP_VOXEL 5
+#define EVREP_OP_HISTOGRAM 6
+
+/* MixedDensityEventStack vocabulary (operations.py:39-89; mixed_density_event_stack.py:48-109) */
+#define EVREP_FUNC_TIMESTAMP 0
+#define EVREP_FUNC_POLARITY 1
+#define EVREP_FUNC_COUNT 2
+#define EVREP_FUNC_TIMESTAMP_POS 3
+#define EVREP_FUNC_TIMESTAMP_NEG 4
+#define EVREP_FUNC_COUNT_POS 5
+#define EVREP_FUNC_COUNT_NEG 6
+#define EVREP_AGG_SUM 0
+#define EVREP_AGG_MEAN 1
+#define EVREP_AGG_MAX 2
+#define EVREP_AGG_VARIANCE 3
+#define EVREP_STACK_SBN 0 /* windows by number of events (the one ERGO-12 uses) */
+#define EVREP_STACK_SBT 1 /* windows by time */
+#define EVREP_MAX_CHANNELS 32
+
+/* voxel-grid flavours */
+#define EVREP_VOXEL_TONIC 0     /* (B, n_bins, H, W): bilinear in time over [t_first, t_last], p==0 -> -1 */
+#define EVREP_VOXEL_EVLICIOUS 1 /* (B, n_bins, H, W): floor-bin polarity histogram (+ optional normalisation) */
+#define EVREP_VOXEL_GWD 2       /* (B, H, W, n_bins): compute_repr, bilinear over t in [0,1] = (t - t_first)/(t_last - t_first) */
+
+/* per-window status bits written by every batched op (read back with evrep_window_flags) */
+#define EVREP_WF_OUT_OF_RANGE 0x100u /* an event had x >= W or y >= H; it was dropped */
+#define EVREP_WF_UNSORTED 0x200u     /* timestamps decrease somewhere inside the window */
+#define EVREP_WF_T_RANGE 0x400u      /* |t - t_first| does not fit 31 bits; the event was dropped */
+#define EVREP_WF_BAD_POLARITY 0x800u /* p outside {-1,0,1}; treated as sign(p) */
+
+typedef void* evrep_stream_t; /* a cudaStream_t */
+
+int evrep_version(void);
+const char* evrep_last_error(void);
+
+/* Upper bound of the scratch an op needs for a batch of B windows with total_events events on an
+ * H x W sensor producing C channels.  0 on invalid arguments. */
+size_t evrep_workspace_bytes(int op, int B, int64_t total_events, int H, int W, int C);
+
+/* Copies the B per-window status words (EVREP_WF_*) of the last op that used `workspace` to the host
+ * and synchronises `stream`. */
+int evrep_window_flags(const void* workspace, int B, uint32_t* flags_host, evrep_stream_t stream);
+
+/* Host-only: the shared-memory plan the mixed-density tile kernel would use.  Writes
+ * info[0]=bytes of accumulator per pixel, info[1]=pixels per tile, info[2]=tiles per window,
+ * info[3]=number of accumulator words, info[4]=dynamic shared memory bytes per CTA. */
+int evrep_mixed_density_plan_info(int H, int W, const int8_t* win, const int8_t* func, const int8_t* agg, int C,
+                                  int stacking, int64_t max_events_per_window, int* info);
+
+/* out: (B, H, W, C) float32.  win/func/agg: HOST arrays of C entries.  Window indices 0..6 (SBN) or
+ * 0..7 (SBT); an index outside that range yields an all-zero channel like the reference's
+ * swallow-and-zero.  A window with zero events yields zeros. */
+int evrep_mixed_density_batched(const uint16_t* x, const uint16_t* y, const void* t, int t_bytes, const int8_t* p,
+                                const int64_t* win_offsets, int B, int H, int W, const int8_t* win, const int8_t* func,
+                                const int8_t* agg, int C, int stacking, float* out, void* workspace,
+                                size_t workspace_bytes, evrep_stream_t stream);
+
+/* ERGO-12: version 2 = the active tuple (optimized_representation.py:86-115), 1 = the commented one (:16-66). */
+int evrep_ergo12_batched(const uint16_t* x, const uint16_t* y, const void* t, int t_bytes, const int8_t* p,
+                         const int64_t* win_offsets, int B, int H, int W, int version, float* out, void* workspace,
+                         size_t workspace_bytes, evrep_stream_t stream);
+
+/* out: (B, H, W, stack_size) float32 in {-1,0,1}: polarity sign (p > 0 -> +1 else -1) of the latest
+ * event of the pixel if its index is inside nested suffix window k, else 0. */
+int evrep_event_stack_batched(const uint16_t* x, const uint16_t* y, const void* t, int t_bytes, const int8_t* p,
+                              const int64_t* win_offsets, int B, int H, int W, int stack_size, float* out,
+                              void* workspace, size_t workspace_bytes, evrep_stream_t stream);
+
+/* out: (B, S, 2, H, W) float32.  indices: HOST int64 (B*S) snapshot event indices, or NULL for the
+ * gen1_transforms.py:78-80 rule (searchsorted of S equal time steps).  Polarity plane = p > 0.
+ * Requires time-sorted windows (EVREP_WF_UNSORTED is raised otherwise). */
+int evrep_time_surface_batched(const uint16_t* x, const uint16_t* y, const void* t, int t_bytes, const int8_t* p,
+                               const int64_t* win_offsets, int B, int H, int W, const int64_t* indices, int S,
+                               double tau, float* out, void* workspace, size_t workspace_bytes,
+                               evrep_stream_t stream);
+
+/* out: (B, H, W, 2k) float32.  Sample time = timestamp of the last event of each window; events with
+ * t >= sample time are ignored; channels [0,k) = k most recent ages of p > 0 events ascending, [k,2k)
+ * the same for p <= 0; log compression of tore.py:69-79.  Pixels are the 0-based x,y. */
+int evrep_tore_batched(const uint16_t* x, const uint16_t* y, const void* t, int t_bytes, const int8_t* p,
+                       const int64_t* win_offsets, int B, int H, int W, int k, float* out, void* workspace,
+                       size_t workspace_bytes, evrep_stream_t stream);
+
+/* flavour = EVREP_VOXEL_*.  normalize and t0_t1_us (HOST, 2 entries: the t0_us / t1_us arguments of
+ * events_to_voxel_grid, or NULL for first / last timestamp of each window) apply to the ev-licious flavour
+ * only.  A window with fewer than 2 events gives zeros in the ev-licious flavour (utils.py:52-53). */
+int evrep_voxel_batched(const uint16_t* x, const uint16_t* y, const void* t, int t_bytes, const int8_t* p,
+                        const int64_t* win_offsets, int B, int H, int W, int flavour, int n_bins, int normalize,
+                        const int64_t* t0_t1_us, float* out, void* workspace, size_t workspace_bytes,
+                        evrep_stream_t stream);
+
+/* out: (B, 2, H, W) float32 event counts, plane 0 = p <= 0, plane 1 = p > 0. */
+int evrep_histogram_batched(const uint16_t* x, const uint16_t* y, const void* t, int t_bytes, const int8_t* p,
+                            const int64_t* win_offsets, int B, int H, int W, float* out, void* workspace,
+                            size_t workspace_bytes, evrep_stream_t stream);
+
+/* GWD-A for n_pairs independent (Xs, Xt) pairs: out[i] = mean |pad(Ks) - pad(Kt)| with Gaussian
+ * kernels of bandwidth h * std (compute_otmi.py:6-32, 61-93).  Xs: DEVICE float64 rows packed back to
+ * back, pair i = rows [s_offsets[i], s_offsets[i+1]) of width ds; same for Xt with dt.  s_offsets /
+ * t_offsets: HOST int64 (n_pairs+1).  out: DEVICE float64 (n_pairs).  workspace >=
+ * evrep_gwd_workspace_bytes(s_offsets, t_offsets, n_pairs), 256-byte aligned.  ds, dt <= 64. */
+size_t evrep_gwd_workspace_bytes(const int64_t* s_offsets, const int64_t* t_offsets, int n_pairs);
+int evrep_gwd_kernel_l1(const double* Xs, const int64_t* s_offsets, int ds, const double* Xt, const int64_t* t_offsets,
+                        int dt, int n_pairs, double h, double* out, void* workspace, size_t workspace_bytes,
+                        evrep_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVREP_H */

@@ -1,0 +1,383 @@
+"""Parity of the CUDA path (through the C ABI of libevrep.so) against
+  (1) the golden fixtures produced by executing the reference files (tests/golden, oracle/gen_golden.py),
+  (2) the numpy oracle on seeded streams at sizes the oracle finishes in seconds,
+  (3) size-independent properties at the BASELINE.json sizes.
+Bars: bit-exact for integer-valued outputs; <= 1e-5 relative for float outputs (BASELINE.json north_star),
+with a small absolute floor where the reference itself subtracts nearly equal numbers (variance channels).
+"""
+import numpy as np
+import pytest
+
+from conftest import assert_close, golden, load
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5  # the float tolerance BASELINE.json states
+VAR_ATOL = 2e-7  # variance = E[x^2] - E[x]^2 on values in [0,1]: float32 output resolution of the operands
+
+
+@pytest.fixture(scope="module")
+def E(cuda_device):
+    import event_representation_study_b200.batched as eb
+    return eb
+
+
+def ids(cases):
+    return [c[0] for c in cases]
+
+
+def batch_of(E, gs, t_dtype=np.int32, key_t="t"):
+    wins = [{"x": g["x"], "y": g["y"], "t": np.asarray(g[key_t]).astype(np.int64), "p": g["p"]} for g in gs]
+    return E.pack_events(wins, "cuda", t_dtype=t_dtype)
+
+
+def np_(t):
+    return t.detach().cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------------
+# golden fixtures (reference outputs)
+# ------------------------------------------------------------------------------------------------
+ERGO = golden("ergo12_n*")
+
+
+@pytest.mark.parametrize("name,path", ERGO, ids=ids(ERGO))
+@pytest.mark.parametrize("t_dtype", [np.int32, np.int64])
+def test_ergo12_golden(E, name, path, t_dtype):
+    g = load(path)
+    out = np_(E.ergo12(batch_of(E, [g], t_dtype), int(g["H"]), int(g["W"])))[0]
+    assert_close(out, g["out"], rtol=RTOL, atol=VAR_ATOL, what=name)
+    for c in (2, 3, 4, 5, 7, 11):  # integer-valued channels: bit exact
+        assert np.array_equal(out[:, :, c], g["out"][:, :, c].astype(np.float32)), (name, c)
+
+
+def test_ergo12_golden_ragged_batch(E):
+    """All small fixtures as ONE ragged batch (window starts at arbitrary, unaligned offsets)."""
+    gs = [load(p) for n, p in ERGO if "dups" not in n]
+    H, W = int(gs[0]["H"]), int(gs[0]["W"])
+    out = np_(E.ergo12(batch_of(E, gs), H, W))
+    for i, g in enumerate(gs):
+        assert_close(out[i], g["out"], rtol=RTOL, atol=VAR_ATOL, what=f"window {i}")
+
+
+def test_ergo12_gen1_50k(E):
+    g = load(golden("ergo12_gen1_50k")[0][1])
+    out = np_(E.ergo12(batch_of(E, [g]), 240, 304))[0]
+    assert_close(out, g["out"], rtol=RTOL, atol=VAR_ATOL, what="gen1 50k")
+    for c in (2, 3, 4, 5, 7, 11):
+        assert np.array_equal(out[:, :, c], g["out"][:, :, c])
+
+
+def test_ergo12_f8_seconds(E):
+    g = load(golden("ergo12_f8_seconds")[0][1])
+    g["t"] = g["t_seconds"].astype(np.int64)  # the reference's own .astype(np.int64) truncation
+    out = np_(E.ergo12(batch_of(E, [g]), 30, 40))[0]
+    assert_close(out, g["out"], rtol=RTOL, atol=VAR_ATOL)
+
+
+MDES = golden("mdes_*")
+
+
+@pytest.mark.parametrize("name,path", MDES, ids=ids(MDES))
+def test_mixed_density_golden(E, name, path):
+    g = load(path)
+    out = np_(E.mixed_density(batch_of(E, [g]), int(g["H"]), int(g["W"]), g["win"].tolist(), g["func"].tolist(),
+                              g["agg"].tolist(), str(g["stacking"])))[0]
+    assert_close(out, g["out"], rtol=RTOL, atol=VAR_ATOL, what=name)
+
+
+ES = golden("eventstack_*")
+
+
+@pytest.mark.parametrize("name,path", ES, ids=ids(ES))
+def test_event_stack_golden(E, name, path):
+    g = load(path)
+    out = np_(E.event_stack(batch_of(E, [g]), int(g["H"]), int(g["W"]), 12))[0]
+    assert np.array_equal(out, g["out"]), name  # integer valued: bit exact
+
+
+TS = golden("timesurface_*")
+
+
+@pytest.mark.parametrize("name,path", TS, ids=ids(TS))
+def test_time_surface_golden(E, name, path):
+    g = load(path)
+    H, W = int(g["H"]), int(g["W"])
+    ev = batch_of(E, [g], np.int64)
+    out = np_(E.time_surface(ev, H, W, 6, 50000.0))[0]  # internal searchsorted rule
+    assert_close(out, g["out"], rtol=RTOL, atol=1e-30, what=name)
+    out2 = np_(E.time_surface(ev, H, W, 6, 50000.0, indices=g["indices"][None]))[0]  # caller-supplied indices
+    assert np.array_equal(out, out2)
+
+
+TF = golden("tore_fixed_*")
+
+
+@pytest.mark.parametrize("name,path", TF, ids=ids(TF))
+def test_tore_golden(E, name, path):
+    g = load(path)
+    out = np_(E.tore(batch_of(E, [g]), int(g["H"]), int(g["W"]), int(g["k"])))[0]
+    assert_close(out, g["out"], rtol=RTOL, atol=0, what=name)
+
+
+VT = [c for c in golden("voxel_tonic_*") if "tconst" not in c[0]]  # t[-1]==t[0]: numpy NaN->int cast is undefined there
+
+
+@pytest.mark.parametrize("name,path", VT, ids=ids(VT))
+def test_voxel_tonic_golden(E, name, path):
+    g = load(path)
+    out = np_(E.voxel_grid(batch_of(E, [g]), int(g["H"]), int(g["W"]), 12, "tonic"))[0]
+    assert_close(out, g["out"][:, 0], rtol=RTOL, atol=2e-6, what=name)  # sums of signed weights: absolute floor
+
+
+VE = golden("voxel_evlicious_*")
+
+
+@pytest.mark.parametrize("name,path", VE, ids=ids(VE))
+def test_voxel_evlicious_golden(E, name, path):
+    g = load(path)
+    out = np_(E.voxel_grid(batch_of(E, [g], np.int64), int(g["H"]), int(g["W"]), int(g["bins"]), "evlicious",
+                           normalize=bool(g["normalize"])))[0]
+    if not bool(g["normalize"]):
+        assert np.array_equal(out, g["out"])  # polarity histogram: bit exact
+    else:
+        assert_close(out, g["out"], rtol=RTOL, atol=1e-6, what=name)
+
+
+def test_voxel_gwd_golden(E):
+    g = load(golden("voxel_gwd_small")[0][1])
+    # compute_repr receives t already normalised as (t - t[0]) / (t[-1] - t[0]); rebuild integer microseconds
+    wins = [{"x": g["x"], "y": g["y"], "t": np.rint(g["t01"] * 1e6).astype(np.int64), "p": g["p"]}]
+    ev = E.pack_events(wins, "cuda")
+    out = np_(E.voxel_grid(ev, 30, 40, 5, "gwd"))[0]
+    from oracle import representations as orep
+    t = wins[0]["t"]
+    want = orep.voxel_gwd(g["x"].astype(int), g["y"].astype(int), (t - t[0]) / (t[-1] - t[0]), g["p"].astype(float), 40, 30, 5)
+    assert_close(out, want, rtol=RTOL, atol=2e-6)
+    assert_close(out, g["out"], rtol=1e-3, atol=1e-4)  # vs the fixture itself (timestamps re-quantised to 1 us)
+
+
+def test_histogram_golden(E):
+    g = load(golden("dispatch_ToImage")[0][1])
+    out = np_(E.histogram(batch_of(E, [g]), int(g["H"]), int(g["W"])))[0]
+    want = (g["out"].astype(np.int32) // 255).transpose(2, 0, 1)  # fixture holds int16 counts * 255, no overflow at this size
+    assert np.array_equal(out, want.astype(np.float32))
+
+
+GA = golden("gwd_a_pair_*")
+
+
+def test_gwd_a_golden(E):
+    gs = [load(p) for _, p in GA]
+    same = [g for g in gs if g["Xt"].shape[1] == 14]  # one call needs one feature width
+    out = np_(E.gwd_kernel_l1([g["Xs"] for g in same], [g["Xt"] for g in same], 0.7))
+    for o, g in zip(out, same):
+        assert_close(o, g["out"], rtol=RTOL, what="gwd-a")
+    for g in gs:  # widths differ between fixtures -> separate calls too
+        o = np_(E.gwd_kernel_l1([g["Xs"]], [g["Xt"]], float(g["h"])))[0]
+        assert_close(o, g["out"], rtol=RTOL, what="gwd-a single")
+
+
+# ------------------------------------------------------------------------------------------------
+# oracle on seeded streams (sizes the oracle finishes in seconds)
+# ------------------------------------------------------------------------------------------------
+def streams(H, W, sizes, seed0=0, **kw):
+    from event_representation_study_b200.synth import poisson_window
+    return [poisson_window(seed0 + i, n, H, W, **kw) for i, n in enumerate(sizes)]
+
+
+@pytest.mark.parametrize("H,W,sizes,kw", [
+    (240, 304, [200_000, 50_000, 0, 123_457], {}),
+    (240, 304, [60_000, 60_001], {"clustered": True}),
+    (720, 1280, [300_000, 7], {}),
+    (720, 1280, [150_000], {"polarity": "01"}),
+], ids=["gen1", "gen1-clustered", "1mpx", "1mpx-p01"])
+def test_ergo12_vs_oracle(E, H, W, sizes, kw):
+    from oracle import representations as orep
+    wins = streams(H, W, sizes, 11, **kw)
+    ev = E.pack_events(wins, "cuda")
+    out = np_(E.ergo12(ev, H, W))
+    assert (E.window_flags(ev) == 0).all()
+    for i, w in enumerate(wins):
+        if len(w["x"]) == 0:
+            assert not out[i].any()  # C ABI contract: empty window -> zeros (the reference raises)
+            continue
+        with np.errstate(all="ignore"):
+            want = orep.ergo12(w["x"], w["y"], w["t"], w["p"], H, W)
+        assert_close(out[i], want, rtol=RTOL, atol=VAR_ATOL, what=f"window {i}")
+        for c in (2, 3, 4, 5, 7, 11):
+            assert np.array_equal(out[i][:, :, c], want[:, :, c].astype(np.float32))
+
+
+def test_ergo12_v1_vs_oracle(E):
+    from oracle import representations as orep
+    H, W = 120, 160
+    wins = streams(H, W, [40_000, 999], 21)
+    out = np_(E.ergo12(E.pack_events(wins, "cuda"), H, W, version=1))
+    for i, w in enumerate(wins):
+        with np.errstate(all="ignore"):
+            want = orep.ergo12(w["x"], w["y"], w["t"], w["p"], H, W, version=1)
+        assert_close(out[i], want, rtol=RTOL, atol=VAR_ATOL, what=f"v1 window {i}")
+
+
+def test_mixed_density_all_pairs_vs_oracle(E):
+    """Every (function, aggregation) pair on every SBN window, mixed {-1,0,+1} polarities."""
+    from oracle import representations as orep
+    H, W = 48, 64
+    w = streams(H, W, [30_000], 31)[0]
+    rng = np.random.default_rng(5)
+    w["p"] = rng.integers(-1, 2, len(w["p"])).astype(np.int8)
+    w["p"][: len(w["p"]) // 3] = np.abs(w["p"][: len(w["p"]) // 3])  # first third holds no -1: the p == 0 fallback
+    ev = E.pack_events([w], "cuda")
+    for st, nwin in (("SBN", 7), ("SBT", 8)):
+        for win in range(nwin):
+            spec = [(win, f, a) for f in orep.FUNCTIONS for a in orep.AGGREGATIONS]
+            wi, fu, ag = [s[0] for s in spec], [s[1] for s in spec], [s[2] for s in spec]
+            out = np_(E.mixed_density(ev, H, W, wi, fu, ag, st))[0]
+            with np.errstate(all="ignore"):
+                want = orep.mixed_density_event_stack(w["x"], w["y"], w["t"], w["p"], H, W, wi, fu, ag, st)
+            assert_close(out, want, rtol=RTOL, atol=VAR_ATOL, what=f"{st} window {win}")
+
+
+def test_mixed_density_bad_spec_is_zero_channel(E):
+    H, W = 30, 40
+    w = streams(H, W, [2000], 41)[0]
+    ev = E.pack_events([w], "cuda")
+    out = np_(E.mixed_density(ev, H, W, [0, 9, 0, 0, -1], ["count", "count", "nope", "count", "count"],
+                              ["sum", "sum", "sum", "median", "sum"], "SBN"))[0]
+    assert out[:, :, 0].sum() == 2000 and not out[:, :, 1:4].any()
+    assert out[:, :, 4].sum() == 2000 - (1000 + 500 + 250)  # windows[-1] is the last nested suffix
+
+
+@pytest.mark.parametrize("H,W,sizes", [(240, 304, [50_000, 1, 33_333]), (720, 1280, [500_000])], ids=["gen1", "1mpx"])
+def test_order_ops_vs_oracle(E, H, W, sizes):
+    from oracle import representations as orep
+    wins = streams(H, W, sizes, 51)
+    ev = E.pack_events(wins, "cuda")
+    es = np_(E.event_stack(ev, H, W, 12))
+    ts = np_(E.time_surface(ev, H, W, 6, 50000.0))
+    tr = np_(E.tore(ev, H, W, 6))
+    for i, w in enumerate(wins):
+        p01 = (w["p"].astype(np.int32) + 1) // 2
+        assert np.array_equal(es[i], orep.event_stack(w["x"], w["y"], w["t"], p01, H, W, 12)), "event stack"
+        if len(w["x"]) >= 2:
+            with np.errstate(all="ignore"):
+                idx = orep.time_surface_indices(w["t"].astype(np.int32), 6)
+            assert_close(ts[i], orep.time_surface(w["x"], w["y"], w["t"], p01, idx, H, W, 50000.0), rtol=RTOL, atol=1e-30,
+                         what="time surface")
+        t = w["t"].astype(np.int32)
+        want = orep.tore(w["x"].astype(np.int32) + 1, w["y"].astype(np.int32) + 1, t, w["p"].astype(np.int32), t[-1], 6, (H, W))
+        assert_close(tr[i], want, rtol=RTOL, atol=0, what="tore")
+
+
+def test_voxels_vs_oracle(E):
+    from oracle import representations as orep
+    H, W = 240, 304
+    wins = streams(H, W, [50_000, 20_000], 61)
+    ev = E.pack_events(wins, "cuda", t_dtype=np.int64)
+    vt = np_(E.voxel_grid(ev, H, W, 12, "tonic"))
+    ve = np_(E.voxel_grid(ev, H, W, 5, "evlicious", normalize=False))
+    vn = np_(E.voxel_grid(ev, H, W, 5, "evlicious", normalize=True))
+    hi = np_(E.histogram(ev, H, W))
+    for i, w in enumerate(wins):
+        assert_close(vt[i], orep.voxel_tonic(w["x"], w["y"], w["t"], w["p"].astype(np.int32), H, W, 12), rtol=RTOL, atol=2e-6)
+        assert np.array_equal(ve[i], orep.voxel_evlicious(w["x"], w["y"], w["t"], w["p"], H, W, 5, normalize=False))
+        assert_close(vn[i], orep.voxel_evlicious(w["x"], w["y"], w["t"], w["p"], H, W, 5, normalize=True), rtol=RTOL, atol=1e-6)
+        assert np.array_equal(hi[i], orep.to_image(w["x"], w["y"], (w["p"].astype(int) + 1) // 2, H, W).astype(np.float32))
+
+
+def test_gwd_a_vs_oracle(E):
+    from oracle import gwd as ogwd
+    rng = np.random.default_rng(7)
+    Xs = [rng.random((n, 4)) for n in (700, 65, 1)]
+    Xt = [np.concatenate([rng.random((m, 12)) * 255, rng.random((m, 2))], 1) for m in (500, 900, 130)]
+    out = np_(E.gwd_kernel_l1(Xs, Xt, 0.7))
+    for o, a, b in zip(out, Xs, Xt):
+        with np.errstate(all="ignore"):
+            want = ogwd.gwd_a_cost(a, b, 0.7)
+        assert_close(o, want, rtol=RTOL, what="gwd-a")
+
+
+# ------------------------------------------------------------------------------------------------
+# flags, edge cases, properties at BASELINE sizes
+# ------------------------------------------------------------------------------------------------
+def test_flags_and_dropped_events(E):
+    from event_representation_study_b200 import _lib
+    H, W = 30, 40
+    w = streams(H, W, [1000, 1000], 71)
+    w[0]["x"][10] = 40  # out of range -> dropped, flagged
+    w[1]["t"][500] = 0  # time goes backwards -> flagged
+    ev = E.pack_events(w, "cuda")
+    out = np_(E.mixed_density(ev, H, W, [0], ["count"], ["sum"]))
+    f = E.window_flags(ev)
+    assert f[0] & _lib.WF_OUT_OF_RANGE and not f[0] & _lib.WF_UNSORTED
+    assert f[1] & _lib.WF_UNSORTED and not f[1] & _lib.WF_OUT_OF_RANGE
+    assert out[0].sum() == 999 and out[1].sum() == 1000
+
+
+def test_errors_are_reported_not_thrown(E):
+    import torch
+    from event_representation_study_b200 import _lib
+    w = streams(30, 40, [100], 81)
+    ev = E.pack_events(w, "cuda")
+    with pytest.raises(_lib.EvrepError):
+        E.ergo12(ev, 30, 40, version=3)
+    with pytest.raises(_lib.EvrepError):
+        E.time_surface(ev, 30, 40, 17)
+    out = torch.empty(1, 30, 40, 12, device="cuda")
+    rc = _lib.lib.evrep_ergo12_batched(ev.x.data_ptr(), ev.y.data_ptr(), ev.t.data_ptr(), 4, ev.p.data_ptr(), ev.offsets.ctypes.data, 1,
+                                       30, 40, 2, out.data_ptr(), out.data_ptr(), 16, None)
+    assert rc == _lib.EWORKSPACE and b"workspace" in _lib.lib.evrep_last_error()
+
+
+@pytest.mark.parametrize("cfg", ["config2", "config4-shard"])
+def test_ergo12_properties_at_baseline_size(E, cfg):
+    """BASELINE.json configs 2 and 4 (one rank's shard): checksums that do not need the oracle."""
+    import torch
+    from event_representation_study_b200.synth import device_batch
+    H, W, N, B = (240, 304, 200_000, 32) if cfg == "config2" else (720, 1280, 1_000_000, 8)
+    d = device_batch(B, N, H, W, "cuda", seed=3)
+    ev = E.EventBatch(d["x"], d["y"], d["t"], d["p"], d["offsets"].cpu().numpy())
+    out = E.ergo12(ev, H, W)
+    out2 = E.ergo12(ev, H, W)
+    assert torch.equal(out.view(torch.int32), out2.view(torch.int32)), "not bit-reproducible"
+    assert (E.window_flags(ev) == 0).all()
+    s6 = N // 2 + N // 4 + N // 8
+    p = d["p"].view(B, N).to(torch.float64)
+    assert torch.equal(out[..., 5].sum((1, 2), dtype=torch.float64), torch.full((B,), float(N - s6), device="cuda", dtype=torch.float64))
+    assert torch.equal(out[..., 3].sum((1, 2), dtype=torch.float64), p[:, s6:].sum(1))
+    # channel 11 = "pixel saw an event in the first third": number of distinct pixels
+    n3 = N // 3
+    lin = (d["y"].view(B, N).long() * W + d["x"].view(B, N).long())[:, :n3]
+    distinct = torch.tensor([torch.unique(lin[b]).numel() for b in range(B)], device="cuda", dtype=torch.float64)
+    assert torch.equal(out[..., 11].sum((1, 2), dtype=torch.float64), distinct)
+    # max-timestamp channels live in [0, 1] and channel 10 peaks at exactly 1 (the last event)
+    assert float(out[..., 8:11].min()) >= 0.0 and float(out[..., 10].max()) == 1.0
+    assert not torch.isnan(out).any()
+
+
+def test_config3_properties(E):
+    """BASELINE.json config 3 (TimeSurface + EventStack + TORE at 1 Mpx, 500k events): cross-representation checks."""
+    import torch
+    from event_representation_study_b200.synth import device_batch
+    H, W, N, B = 720, 1280, 500_000, 4
+    d = device_batch(B, N, H, W, "cuda", seed=4)
+    ev = E.EventBatch(d["x"], d["y"], d["t"], d["p"], d["offsets"].cpu().numpy())
+    es = E.event_stack(ev, H, W, 12)
+    ts = E.time_surface(ev, H, W, 6, 50000.0)
+    tr = E.tore(ev, H, W, 6)
+    lin = d["y"].view(B, N).long() * W + d["x"].view(B, N).long()
+    for b in range(B):
+        touched = torch.zeros(H * W, dtype=torch.bool, device="cuda")
+        touched[lin[b]] = True
+        assert torch.equal(es[b, :, :, 0].reshape(-1) != 0, touched)  # widest window: every touched pixel is +-1
+        # nested windows: a pixel set in window k+1 is set, with the same sign, in window k
+        for k in range(11):
+            nz = es[b, :, :, k + 1] != 0
+            assert torch.equal(es[b, :, :, k + 1][nz], es[b, :, :, k][nz])
+    assert float(ts.max()) <= 1.0 and float(ts.min()) >= 0.0
+    # the last surface is taken at the last event: its pixel holds exp(0) = 1
+    assert float(ts[:, 5].max()) == 1.0
+    # TORE: ages ascending inside each polarity's k slots; empty slots carry the constant 15.0128
+    assert bool((tr[..., 0:5] <= tr[..., 1:6]).all()) and bool((tr[..., 6:11] <= tr[..., 7:12]).all())
+    assert abs(float(tr.max()) - 15.0128) < 1e-3
