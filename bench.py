@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""Headline benchmark: Gevents/s into ERGO-12 at 1 Mpx (BASELINE.json configs[3], one rank's shard).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU algorithm on the host cores
+
+A step = one pass of the hot path (raw events of a batch of windows -> ERGO-12 tensors) over one synthetic
+batch: 32 windows x 1,000,000 events on a 1280x720 sensor per GPU (config 4 shards its 256 windows 32 per GPU,
+so per-GPU work is fixed: weak scaling, no data-path collective).  One JSON line is printed by rank 0.
+
+value     events of all ranks / max-over-ranks device time, inputs resident in HBM
+e2e       same through the public batched API with HOST (pinned) event arrays: per step the host->device copy
+          of the events, the kernels, and the device->host read of a per-window checksum of the output
+roofline  the kernel that writes the output (k_md_tile), timed with CUDA events inside the timed region
+cpu_baseline  the numpy oracle (a port of the reference algorithm) on the host cores, bounded sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+H, W, C = 720, 1280, 12
+BYTES_PER_EVENT = 9  # x u16 + y u16 + t i32 + p i8: SURVEY.md 8(d)
+METRIC = "Gevents/s into ERGO-12 @1Mpx 1280x720"
+
+
+def algorithmic_bytes(n_windows, n_events):
+    return n_windows * (n_events * BYTES_PER_EVENT + H * W * C * 4)
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_per_launch(workload):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(workload)
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, uuid):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", uuid, f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            f = [v.strip() for v in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm (oracle port of the reference algorithm)
+# ------------------------------------------------------------------------------------------------
+def _cpu_one(args):
+    seed, n = args
+    from oracle import representations as orep
+    from event_representation_study_b200.synth import poisson_window
+    w = poisson_window(seed, n, H, W)
+    t0 = time.perf_counter()
+    out = orep.ergo12(w["x"], w["y"], w["t"], w["p"], H, W)
+    return time.perf_counter() - t0, float(out[:, :, 5].sum())
+
+
+def cpu_baseline_scalar(n_events, budget_s=12.0, max_windows=24):
+    """Single-process oracle on a bounded sample of the same workload (windows of the bench's size)."""
+    done, spent = 0, 0.0
+    while done < max_windows and spent < budget_s:
+        dt, _ = _cpu_one((5000 + done, n_events))
+        spent += dt
+        done += 1
+    return {"value": done * n_events / spent / 1e9, "unit": "Gevents/s", "cores": 1, "kind": "port",
+            "sample": f"{done} windows of {n_events} events at {W}x{H}, numpy oracle (oracle/representations.py::ergo12), "
+                      f"generation excluded, {spent:.1f} s"}
+
+
+def run_reference_arm(a):
+    """The reference's CPU implementation of the path.  /root/reference is pure Python and absent on the GPU box,
+    and three of its imports (torch_scatter, tonic, POT) are not installable offline, so this arm times the numpy
+    port of its algorithm (oracle/), one window per worker process on every host core - the shape of the
+    reference's own 8-process TaskManager pool (ev-YOLOv6/yolov6/data/gen4/precompute_reps.py:444)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 64))
+    per_step = procs  # one window per worker per step
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs) as pool:
+        for s in range(a.warmup):
+            pool.map(_cpu_one, [(s * per_step + i, a.events) for i in range(per_step)])
+        t0 = time.perf_counter()
+        for s in range(a.steps):
+            pool.map(_cpu_one, [(10_000 + s * per_step + i, a.events) for i in range(per_step)])
+        dt = time.perf_counter() - t0
+    val = a.steps * per_step * a.events / dt / 1e9
+    sample = f"{per_step} windows of {a.events} events per step ({procs} worker processes, window generation included)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "Gevents/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": config_dict(a, per_step),
+        "cpu_baseline": {"value": val, "unit": "Gevents/s", "cores": procs, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "Gevents/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def config_dict(a, windows):
+    return {"workload": f"ERGO-12 v2, {W}x{H}, {a.events} ev/window, {windows} windows/GPU (BASELINE configs[3] shard: 256 windows over 8 GPUs)",
+            "windows_per_gpu": windows, "events_per_window": a.events, "stream": "poisson-uniform" + ("-clustered" if a.clustered else ""),
+            "l2": "inputs (288 MB) and outputs (1.4 GB) per step exceed the 126 MB L2; no explicit flush"}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu_arm(a):
+    import torch
+    import torch.distributed as dist
+    import event_representation_study_b200.batched as eb
+    from event_representation_study_b200 import _lib
+    from event_representation_study_b200.synth import device_batch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, N = a.windows, a.events
+    d = device_batch(B, N, H, W, dev, seed=1000 * 4 + rank, clustered=a.clustered)
+    ev = eb.EventBatch(d["x"], d["y"], d["t"], d["p"], d["offsets"].cpu().numpy())
+    out = torch.empty((B, H, W, C), dtype=torch.float32, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(max(a.warmup, 3)):
+        eb.ergo12(ev, H, W, out=out)
+    torch.cuda.synchronize()
+    flags = eb.window_flags(ev)
+    assert (flags == 0).all(), f"window flags {flags}"
+
+    # ---- device-resident throughput, with per-kernel events ------------------------------------
+    uuid = str(torch.cuda.get_device_properties(local).uuid)
+    uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+    sampler = ClockSampler(uuid) if rank == 0 else None
+    _lib.profile_enable(a.steps)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        eb.ergo12(ev, H, W, out=out)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    kern = {k: _lib.profile_read(k) for k in (_lib.K_COUNT, _lib.K_SCAN, _lib.K_BIN, _lib.K_TILE)}
+    _lib.profile_enable(0)
+    clocks = sampler.stop() if sampler else None
+    tmax = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_all = float(tmax.item())
+    value = world * B * N * a.steps / (ms_all * 1e-3) / 1e9
+
+    # ---- end to end: pinned host events -> H2D -> kernels -> per-window checksum -> D2H ----------
+    host = {k: d[k].cpu().pin_memory() for k in ("x", "y", "t", "p")}
+    dbuf = {k: torch.empty_like(d[k]) for k in ("x", "y", "t", "p")}
+    res_host = torch.empty(B, dtype=torch.float64).pin_memory()
+    offs = ev.offsets
+
+    def e2e_step():
+        for k in ("x", "y", "t", "p"):
+            dbuf[k].copy_(host[k], non_blocking=True)
+        o = eb.ergo12(eb.EventBatch(dbuf["x"], dbuf["y"], dbuf["t"], dbuf["p"], offs), H, W, out=out)
+        res_host.copy_(o.view(B, -1).sum(1, dtype=torch.float64), non_blocking=True)
+        torch.cuda.synchronize()  # the caller reads the result before the next step
+        return res_host
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    ms_e2e = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * N * a.steps / (float(ms_e2e.item()) * 1e-3) / 1e9
+    h2d = int(sum(host[k].numel() * host[k].element_size() for k in host))
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        tile_ms, tile_n = kern[_lib.K_TILE]
+        tile_avg_s = tile_ms / max(tile_n, 1) * 1e-3
+        alg = algorithmic_bytes(B, N)
+        achieved = alg / tile_avg_s / 1e9
+        step_s = ms_all / a.steps * 1e-3
+        line = {
+            "metric": METRIC, "value": value, "unit": "Gevents/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": ms_all / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32/f64->f32",
+            "data": "synthetic", "config": config_dict(a, B),
+            "e2e": {"value": e2e_value, "unit": "Gevents/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * 8,
+                    "note": "PCIe-bound: 9 B/event over the host link; the dense output stays on the GPU for the model"},
+            "gpu_launches": a.steps * 5,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_md_tile (per-tile reduction + finalise, writes the output)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic_per_launch("ergo12_1mpx_b32"),
+                         "algorithmic_bytes_per_launch": alg, "launch_ms": tile_avg_s * 1e3, "peak_source": peak_src,
+                         "whole_step": {"achieved": alg / step_s / 1e9, "frac": alg / step_s / 1e9 / peak,
+                                        "note": "same algorithmic bytes over the whole 5-kernel step"},
+                         "kernel_ms": {_lib.KERNEL_NAMES[k]: (v[0] / max(v[1], 1)) for k, v in kern.items()}},
+        }
+        if world == 1 and not a.no_cpu:
+            line["cpu_baseline"] = cpu_baseline_scalar(N)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--windows", type=int, default=32, help="windows per GPU")
+    ap.add_argument("--events", type=int, default=1_000_000, help="events per window")
+    ap.add_argument("--clustered", action="store_true", help="80%% of the events on 5%% of the pixels (contention stress; not the headline)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_gpu_arm(a)
+
+
+if __name__ == "__main__":
+    main()

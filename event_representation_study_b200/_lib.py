@@ -16,6 +16,8 @@ FUNCS = {"timestamp": 0, "polarity": 1, "count": 2, "timestamp_pos": 3, "timesta
 AGGS = {"sum": 0, "mean": 1, "max": 2, "variance": 3}
 STACKING = {"SBN": 0, "SBT": 1}
 VOXEL_TONIC, VOXEL_EVLICIOUS, VOXEL_GWD = 0, 1, 2
+K_COUNT, K_SCAN, K_BIN, K_TILE = 0, 1, 2, 3
+KERNEL_NAMES = {K_COUNT: "k_hist", K_SCAN: "k_scan", K_BIN: "k_bin", K_TILE: "tile kernel"}
 WF_OUT_OF_RANGE, WF_UNSORTED, WF_T_RANGE, WF_BAD_POLARITY = 0x100, 0x200, 0x400, 0x800
 
 _c = ctypes
@@ -26,6 +28,8 @@ _TAIL = [_vp, _vp, _sz, _vp]                      # out, workspace, workspace_by
 SIGNATURES = {
     "evrep_version": (_i, []),
     "evrep_last_error": (_c.c_char_p, []),
+    "evrep_profile_enable": (_i, [_i]),
+    "evrep_profile_read": (_i, [_i, _vp, _vp]),
     "evrep_workspace_bytes": (_sz, [_i, _i, _i64, _i, _i, _i]),
     "evrep_window_flags": (_i, [_vp, _i, _vp, _vp]),
     "evrep_mixed_density_plan_info": (_i, [_i, _i, _vp, _vp, _vp, _i, _i, _i64, _vp]),
@@ -68,3 +72,14 @@ lib = _load()
 def check(rc):
     if rc != OK:
         raise EvrepError(rc, lib.evrep_last_error().decode("utf-8", "replace"))
+
+
+def profile_enable(max_calls):
+    check(lib.evrep_profile_enable(int(max_calls)))
+
+
+def profile_read(kernel_id):
+    """-> (total milliseconds, launches timed) for one kernel of the tile pipeline since profile_enable."""
+    ms, n = ctypes.c_float(0), ctypes.c_int(0)
+    check(lib.evrep_profile_read(int(kernel_id), ctypes.byref(ms), ctypes.byref(n)))
+    return ms.value, n.value

@@ -19,6 +19,34 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// ---- optional kernel timing -------------------------------------------------------------------
+static struct Prof {
+  int max_calls = 0, call = -1;
+  cudaEvent_t* ev = nullptr;  // [max_calls][EVREP_K_N][2]
+  unsigned char* used = nullptr;
+} g_prof;
+
+static void prof_free() {
+  if (g_prof.ev) {
+    for (int i = 0; i < g_prof.max_calls * EVREP_K_N * 2; ++i) cudaEventDestroy(g_prof.ev[i]);
+    delete[] g_prof.ev;
+    delete[] g_prof.used;
+  }
+  g_prof = Prof();
+}
+void prof_next_call() {
+  if (g_prof.max_calls) ++g_prof.call;
+}
+void prof_begin(int k, cudaStream_t stream) {
+  if (!g_prof.max_calls || g_prof.call < 0 || g_prof.call >= g_prof.max_calls) return;
+  cudaEventRecord(g_prof.ev[(g_prof.call * EVREP_K_N + k) * 2], stream);
+}
+void prof_end(int k, cudaStream_t stream) {
+  if (!g_prof.max_calls || g_prof.call < 0 || g_prof.call >= g_prof.max_calls) return;
+  cudaEventRecord(g_prof.ev[(g_prof.call * EVREP_K_N + k) * 2 + 1], stream);
+  g_prof.used[g_prof.call * EVREP_K_N + k] = 1;
+}
+
 int build_md_plan(const int8_t* win, const int8_t* func, const int8_t* agg, int C, int stacking, int64_t n_max, MdPlan* out);
 size_t gwd_workspace_bytes(const int64_t* so, const int64_t* to, int n_pairs);
 int launch_gwd(const double* Xs, const int64_t* so, int ds, const double* Xt, const int64_t* to, int dt, int n_pairs, double h,
@@ -104,6 +132,35 @@ int evrep_version(void) { return EVREP_VERSION; }
 
 const char* evrep_last_error(void) { return g_err; }
 
+int evrep_profile_enable(int max_calls) {
+  prof_free();
+  if (max_calls <= 0) return EVREP_OK;
+  if (max_calls > 4096) { set_error("max_calls > 4096"); return EVREP_EINVAL; }
+  g_prof.ev = new (std::nothrow) cudaEvent_t[(size_t)max_calls * EVREP_K_N * 2];
+  g_prof.used = new (std::nothrow) unsigned char[(size_t)max_calls * EVREP_K_N]();
+  if (!g_prof.ev || !g_prof.used) { set_error("host allocation failed"); return EVREP_EINVAL; }
+  g_prof.max_calls = max_calls;
+  g_prof.call = -1;
+  for (int i = 0; i < max_calls * EVREP_K_N * 2; ++i) EVREP_CUDA_OK(cudaEventCreate(&g_prof.ev[i]));
+  return EVREP_OK;
+}
+
+int evrep_profile_read(int kernel_id, float* total_ms, int* launches) {
+  if (kernel_id < 0 || kernel_id >= EVREP_K_N || !total_ms || !launches) { set_error("bad argument"); return EVREP_EINVAL; }
+  *total_ms = 0.f;
+  *launches = 0;
+  for (int c = 0; c < g_prof.max_calls && c <= g_prof.call; ++c) {
+    if (!g_prof.used[c * EVREP_K_N + kernel_id]) continue;
+    cudaEvent_t a = g_prof.ev[(c * EVREP_K_N + kernel_id) * 2], b = g_prof.ev[(c * EVREP_K_N + kernel_id) * 2 + 1];
+    EVREP_CUDA_OK(cudaEventSynchronize(b));
+    float ms = 0.f;
+    EVREP_CUDA_OK(cudaEventElapsedTime(&ms, a, b));
+    *total_ms += ms;
+    ++*launches;
+  }
+  return EVREP_OK;
+}
+
 size_t evrep_workspace_bytes(int op, int B, int64_t total_events, int H, int W, int C) {
   (void)C;
   if (op < EVREP_OP_MIXED_DENSITY || op > EVREP_OP_HISTOGRAM || B < 0 || total_events < 0 || H < 1 || W < 1) return 0;
@@ -132,8 +189,8 @@ int evrep_mixed_density_plan_info(int H, int W, const int8_t* win, const int8_t*
   EVREP_TRY(build_md_plan(win, func, agg, C, stacking, max_events_per_window, &plan));
   Geom g;
   memset(&g, 0, sizeof(g));
-  EVREP_TRY(choose_tile(H, W, (size_t)plan.words * 4, &g));
-  info[0] = plan.words * 4;
+  EVREP_TRY(choose_tile(H, W, (size_t)plan.stride * 4, &g));
+  info[0] = plan.stride * 4;
   info[1] = g.tile_px;
   info[2] = g.T;
   info[3] = plan.words;
@@ -156,12 +213,12 @@ int evrep_mixed_density_batched(const uint16_t* x, const uint16_t* y, const void
   EVREP_TRY(build_md_plan(win, func, agg, C, stacking, n_max, &plan));
   Geom g;
   memset(&g, 0, sizeof(g));
-  EVREP_TRY(choose_tile(H, W, (size_t)plan.words * 4, &g));
+  EVREP_TRY(choose_tile(H, W, (size_t)plan.stride * 4, &g));
   g.B = B;
   g.total = total;
   Workspace ws;
   EVREP_TRY(carve_checked(workspace, workspace_bytes, B, total, g.T, &ws));
-  EVREP_TRY(run_binning(ev, win_offsets, g, ws, REC_T_WMASK, 0, nullptr, (cudaStream_t)stream));
+  EVREP_TRY(run_binning(ev, win_offsets, g, ws, stacking == EVREP_STACK_SBN ? REC_T_WMASK : REC_T_ONLY, 0, nullptr, (cudaStream_t)stream));
   return launch_md_tile(g, ws, plan, ev, out, (cudaStream_t)stream);
   EVREP_GUARD_END
 }

@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin(const uint16_t* __restrict_
         while (s < ns && idx > (int64_t)sh_snap_idx[s]) ++s;
         if (s >= ns) continue;  // after the last emitted surface: feeds nothing
         aux = (uint32_t)s;
-      } else {  // REC_T_TORE: strict `<` against the sample time = last timestamp (tore.py:17)
+      } else if (mode == REC_T_TORE) {  // strict `<` against the sample time = last timestamp (tore.py:17)
         if (t_rel >= tlast_rel) continue;
       }
       my_tmin = min(my_tmin, t_rel);
@@ -446,6 +446,7 @@ bool events_vectorisable(const Events& ev) { return aligned16(ev.x) && aligned16
 int run_binning(const Events& ev, const int64_t* win_offsets_host, const Geom& g, const Workspace& ws, int rec_mode, int n_snap,
                 const int64_t* snap_indices_host, cudaStream_t stream) {
   int n_chunks = 0;
+  prof_next_call();
   int rc = prepare_windows(ev, win_offsets_host, g, ws, &n_chunks, stream);
   if (rc) return rc;
   EVREP_CUDA_OK(cudaMemsetAsync(ws.hist, 0, sizeof(uint32_t) * (size_t)g.B * g.T * 2, stream));  // hist + cursor
@@ -464,12 +465,17 @@ int run_binning(const Events& ev, const int64_t* win_offsets_host, const Geom& g
     EVREP_CUDA_OK(cudaGetLastError());
   }
   if (n_chunks > 0) {
+    prof_begin(EVREP_K_COUNT, stream);
     k_hist<<<n_chunks, BIN_THREADS, sizeof(uint32_t) * (size_t)g.T, stream>>>(ev.x, ev.y, ws.wp, ws.chunk_prefix, g, vec, ws.hist);
+    prof_end(EVREP_K_COUNT, stream);
     EVREP_CUDA_OK(cudaGetLastError());
   }
+  prof_begin(EVREP_K_SCAN, stream);
   k_scan<<<g.B, BIN_THREADS, 0, stream>>>(ws.hist, ws.base, g.T);
+  prof_end(EVREP_K_SCAN, stream);
   EVREP_CUDA_OK(cudaGetLastError());
   if (n_chunks > 0) {
+    prof_begin(EVREP_K_BIN, stream);
     const size_t smem = (size_t)CHUNK * (sizeof(uint2) + sizeof(uint16_t)) + 3 * sizeof(uint32_t) * (size_t)g.T;
     if (ev.t_bytes == 4) {
       EVREP_CUDA_OK(cudaFuncSetAttribute(k_bin<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -480,6 +486,7 @@ int run_binning(const Events& ev, const int64_t* win_offsets_host, const Geom& g
       k_bin<int64_t><<<n_chunks, BIN_THREADS, smem, stream>>>(ev.x, ev.y, (const int64_t*)ev.t, ev.p, ws.wp, ws.snap, ws.chunk_prefix, g,
                                                                vec, rec_mode, ws.base, ws.cursor, ws.records);
     }
+    prof_end(EVREP_K_BIN, stream);
     EVREP_CUDA_OK(cudaGetLastError());
   }
   return EVREP_OK;

@@ -28,6 +28,7 @@ enum RecMode : int {
   REC_IDX = 1,      // key = index inside window, aux = 0            (event stack)
   REC_T_SNAP = 2,   // key = t_rel, aux = first snapshot it feeds    (time surface)
   REC_T_TORE = 3,   // key = t_rel, events with t >= t_last dropped  (TORE)
+  REC_T_ONLY = 4,   // key = t_rel, aux = 0: windows are derived from t later (mixed density, SBT)
 };
 // meta word: [15:0] pixel inside tile, [23:16] aux, [25:24] polarity code (p & 3: 0 -> 0, 1 -> +1, 3 -> -1)
 __host__ __device__ inline uint32_t rec_meta(uint32_t pix, uint32_t aux, uint32_t pc) { return pix | (aux << 16) | (pc << 24); }
@@ -99,6 +100,12 @@ inline Workspace carve(void* basep, int B, int64_t total, int T) {
 // thread-local error text (api.cu)
 void set_error(const char* fmt, ...);
 
+// Optional per-kernel timing with CUDA events on the caller's stream (api.cu; evrep_profile_* in evrep.h).
+// No-ops unless profiling was enabled; never synchronise.
+void prof_next_call();
+void prof_begin(int kernel_id, cudaStream_t stream);
+void prof_end(int kernel_id, cudaStream_t stream);
+
 #define EVREP_CUDA_OK(expr)                                                                  \
   do {                                                                                       \
     cudaError_t _e = (expr);                                                                 \
@@ -126,7 +133,7 @@ struct MdChan {
   int8_t g_main, g_all, g_pos, g_neg;
 };
 struct MdPlan {
-  int32_t C, G, words, nl1, nl2, lw, w_pres, stacking;
+  int32_t C, G, words, stride, nl1, nl2, lw, w_pres, stacking, pad;
   MdGroup grp[MD_MAX_GROUPS];
   MdChan ch[EVREP_MAX_CHANNELS];
 };

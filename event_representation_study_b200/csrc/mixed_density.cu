@@ -14,7 +14,7 @@
 
 namespace evrep {
 
-size_t md_tile_smem_bytes(const MdPlan& plan, int tile_px) { return (size_t)plan.words * (size_t)tile_px * sizeof(uint32_t); }
+size_t md_tile_smem_bytes(const MdPlan& plan, int tile_px) { return align_up((size_t)plan.stride * (size_t)tile_px * sizeof(uint32_t), 16); }
 
 // ---------------------------------------------------------------------------------------------
 // host: (window, function, aggregation) tuple -> accumulator plan
@@ -108,61 +108,69 @@ int build_md_plan(const int8_t* win, const int8_t* func, const int8_t* agg, int 
   }
   if (words == 0) words = 1;
   P.words = words;
+  P.stride = (words > C ? words : C) | 1;  // odd: bank-conflict-free, and room for the C outputs written in place
   return EVREP_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
 // device
+//
+// Shared-memory layout: array of structures, pixel p owns acc[p*stride .. p*stride+stride) with an ODD
+// stride >= max(words, C), so that (a) atomics of different pixels spread over all banks, (b) a thread can
+// finalise its pixel in place (outputs overwrite the pixel's own dead accumulators) and (c) the CTA then
+// streams the tile's output slice to global memory with fully coalesced 16-byte stores.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t md_touched(const MdPlan& P, const MdGroup& G, const uint32_t* acc, int TP, int pix) {
-  if (G.flags & G_CNT) return acc[G.w_cnt * TP + pix];
-  if (G.flags & G_MAX) return acc[G.w_max * TP + pix] != 0u;
-  if (G.flags & G_PRES) return (acc[P.w_pres * TP + pix] >> G.pres_bit) & 1u;
+__device__ __forceinline__ uint32_t md_touched(const MdPlan& P, const MdGroup& G, const uint32_t* a) {
+  if (G.flags & G_CNT) return a[G.w_cnt];
+  if (G.flags & G_MAX) return a[G.w_max] != 0u;
+  if (G.flags & G_PRES) return (a[P.w_pres] >> G.pres_bit) & 1u;
   return 0u;
 }
 
-__device__ __forceinline__ double md_limb_sum(const uint32_t* acc, int TP, int pix, int w0, int nl, int lw) {
-  double s = 0.0, scale = 1.0;
-  const double step = (double)(1u << lw);
-  for (int l = 0; l < nl; ++l) {
-    s += (double)acc[(w0 + l) * TP + pix] * scale;
-    scale *= step;
-  }
+// exact value of a multi-limb sum as a double (limbs are base-2^lw digits with 32-bit headroom)
+__device__ __forceinline__ double md_limb_sum(const uint32_t* a, int w0, int nl, int lw) {
+  // low three limbs and the rest are each combined exactly in 64-bit integers, then joined in fp64
+  unsigned long long lo = 0, hi = 0;
+  for (int l = 0; l < nl && l < 3; ++l) lo += (unsigned long long)a[w0 + l] << (l * lw);
+  for (int l = 3; l < nl; ++l) hi += (unsigned long long)a[w0 + l] << ((l - 3) * lw);
+  double s = (double)lo;
+  if (nl > 3) s = fma((double)hi, (double)(1ull << (3 * lw)), s);
   return s;
 }
 
-__device__ float md_value(const MdPlan& P, const MdChan& ch, const uint32_t* acc, int TP, int pix, double delta, uint32_t has_m1) {
+// One channel of one pixel.  All divisions are single fp32 divisions of exactly computed numerators and
+// denominators (no fp64 division, no cancellation after rounding), within 3e-7 relative of the reference's fp64.
+__device__ __forceinline__ float md_value(const MdPlan& P, const MdChan& ch, const uint32_t* a, float delta_f, double delta, uint32_t has_m1) {
   if (!ch.valid) return 0.f;
   if (ch.func == EVREP_FUNC_POLARITY) {
-    const double c1 = (double)acc[P.grp[ch.g_pos].w_cnt * TP + pix];
-    const double cm = ((has_m1 >> ch.win) & 1u) ? (double)acc[P.grp[ch.g_neg].w_cnt * TP + pix] : 0.0;
+    const long long c1 = a[P.grp[ch.g_pos].w_cnt];
+    const long long cm = ((has_m1 >> ch.win) & 1u) ? (long long)a[P.grp[ch.g_neg].w_cnt] : 0ll;
     if (ch.agg == EVREP_AGG_SUM) return (float)(c1 - cm);
-    const double call = (double)acc[P.grp[ch.g_all].w_cnt * TP + pix];
-    if (call == 0.0) return 0.f;
-    if (ch.agg == EVREP_AGG_MEAN) return (float)((c1 - cm) / call);
-    if (ch.agg == EVREP_AGG_VARIANCE) {
-      const double m = (c1 - cm) / call, m2 = (c1 + cm) / call;
-      return (float)(m2 - m * m);
-    }
-    return c1 > 0.0 ? 1.f : (call - c1 - cm > 0.0 ? 0.f : -1.f);  // max of the raw polarities
+    const long long call = a[P.grp[ch.g_all].w_cnt];
+    if (call == 0) return 0.f;
+    if (ch.agg == EVREP_AGG_MEAN) return (float)(c1 - cm) / (float)call;
+    if (ch.agg == EVREP_AGG_VARIANCE)  // mean(p^2) - mean(p)^2 = ((c1+cm) call - (c1-cm)^2) / call^2, numerator exact
+      return (float)((double)((c1 + cm) * call - (c1 - cm) * (c1 - cm))) / (float)((double)call * (double)call);
+    return c1 > 0 ? 1.f : (call - c1 - cm > 0 ? 0.f : -1.f);  // max of the raw polarities
   }
   if (ch.g_main < 0) return 0.f;
   const MdGroup& G = P.grp[ch.g_main];
-  const uint32_t c = md_touched(P, G, acc, TP, pix);
+  const uint32_t c = md_touched(P, G, a);
   if (c == 0u) return 0.f;  // torch_scatter leaves untouched pixels at 0
   const bool is_count = (ch.func == EVREP_FUNC_COUNT || ch.func == EVREP_FUNC_COUNT_POS || ch.func == EVREP_FUNC_COUNT_NEG);
   if (is_count) return ch.agg == EVREP_AGG_SUM ? (float)c : 1.f;
-  // timestamps: t_s = (t - t_min) / (t_max - t_min); delta == 0 gives NaN exactly like the reference
-  if (ch.agg == EVREP_AGG_MAX) return (float)((double)(acc[G.w_max * TP + pix] - 1u) / delta);
-  const double st = md_limb_sum(acc, TP, pix, G.w_st, P.nl1, P.lw);
-  if (ch.agg == EVREP_AGG_SUM) return (float)(st / delta);
-  const double m = st / delta / (double)c;
-  if (ch.agg == EVREP_AGG_MEAN) return (float)m;
-  const double st2 = md_limb_sum(acc, TP, pix, G.w_st2, P.nl2, P.lw);
-  const double m2 = st2 / delta / delta / (double)c;
-  return (float)(m2 - m * m);
+  // timestamps: t_s = (t - t_min) / (t_max - t_min); delta == 0 gives 0/0 = NaN exactly like the reference
+  if (ch.agg == EVREP_AGG_MAX) return (float)(a[G.w_max] - 1u) / delta_f;
+  const double st = md_limb_sum(a, G.w_st, P.nl1, P.lw);
+  if (ch.agg == EVREP_AGG_SUM) return (float)st / delta_f;
+  const double cd = (double)c * delta;
+  if (ch.agg == EVREP_AGG_MEAN) return (float)st / (float)cd;
+  const double st2 = md_limb_sum(a, G.w_st2, P.nl2, P.lw);
+  // mean(t_s^2) - mean(t_s)^2 = (c sum(t^2) - sum(t)^2) / (c delta)^2
+  return (float)fma((double)c, st2, -st * st) / (float)(cd * cd);
 }
 
+template <int CMAX>
 __global__ void __launch_bounds__(TILE_THREADS) k_md_tile(const uint2* __restrict__ records, const uint32_t* __restrict__ base,
                                                           const uint32_t* __restrict__ cursor, const WinParams* __restrict__ wp,
                                                           const __grid_constant__ MdPlan P, const Geom g, float* __restrict__ out) {
@@ -172,10 +180,11 @@ __global__ void __launch_bounds__(TILE_THREADS) k_md_tile(const uint2* __restric
   const int TP = g.tile_px;
   const int pix0 = tile << g.tile_shift;
   const int npix = min(TP, g.HW - pix0);
+  const int stride = P.stride;
 
   {  // zero the accumulators
     uint4* a4 = reinterpret_cast<uint4*>(acc);
-    const int n4 = P.words * TP / 4;
+    const int n4 = (stride * TP + 3) / 4;
     for (int i = tid; i < n4; i += TILE_THREADS) a4[i] = make_uint4(0, 0, 0, 0);
   }
   const WinParams w = wp[b];
@@ -184,12 +193,13 @@ __global__ void __launch_bounds__(TILE_THREADS) k_md_tile(const uint2* __restric
   const int32_t tmin = w.tmin_rel;
   const uint32_t delta_u = (w.tmax_rel >= w.tmin_rel) ? (uint32_t)(w.tmax_rel - w.tmin_rel) : 0u;
   const double delta = (double)delta_u;
-  const uint32_t limb_mask = (P.lw >= 32) ? 0xffffffffu : ((1u << P.lw) - 1u);
+  const float delta_f = (float)delta_u;
+  const uint32_t limb_mask = (1u << P.lw) - 1u;  // lw <= 31
   __syncthreads();
 
   for (uint32_t i = tid; i < count; i += TILE_THREADS) {
     const uint2 r = __ldg(rec + i);
-    const uint32_t pix = r.y & 0xffffu;
+    uint32_t* a = acc + (r.y & 0xffffu) * stride;
     const uint32_t pc = (r.y >> 24) & 3u;
     const uint32_t tt = (uint32_t)((int32_t)r.x - tmin);  // t - t_min, < 2^31
     uint32_t wmask;
@@ -216,38 +226,61 @@ __global__ void __launch_bounds__(TILE_THREADS) k_md_tile(const uint2* __restric
     for (int gi = 0; gi < P.G; ++gi) {
       const MdGroup G = P.grp[gi];
       if (!((M >> G.bit) & 1u)) continue;
-      if (G.flags & G_CNT) atomicAdd(&acc[G.w_cnt * TP + pix], 1u);
+      if (G.flags & G_CNT) atomicAdd(a + G.w_cnt, 1u);
       if (G.flags & G_PRES) pres |= 1u << G.pres_bit;
-      if (G.flags & G_MAX) atomicMax(&acc[G.w_max * TP + pix], tt + 1u);
+      if (G.flags & G_MAX) atomicMax(a + G.w_max, tt + 1u);
       if (G.flags & G_ST) {
         uint32_t v = tt;
-        for (int l = 0; l < P.nl1 && v; ++l, v = (P.lw >= 32 ? 0u : v >> P.lw)) {
+        for (int l = 0; l < P.nl1 && v; ++l, v >>= P.lw) {
           const uint32_t limb = v & limb_mask;
-          if (limb) atomicAdd(&acc[(G.w_st + l) * TP + pix], limb);
+          if (limb) atomicAdd(a + G.w_st + l, limb);
         }
       }
       if (G.flags & G_ST2) {
         unsigned long long v = (unsigned long long)tt * (unsigned long long)tt;
         for (int l = 0; l < P.nl2 && v; ++l, v >>= P.lw) {
           const uint32_t limb = (uint32_t)v & limb_mask;
-          if (limb) atomicAdd(&acc[(G.w_st2 + l) * TP + pix], limb);
+          if (limb) atomicAdd(a + G.w_st2 + l, limb);
         }
       }
     }
     if (pres) {
-      uint32_t* pw = &acc[P.w_pres * TP + pix];
+      uint32_t* pw = a + P.w_pres;
       if ((*(volatile uint32_t*)pw & pres) != pres) atomicOr(pw, pres);
     }
   }
   __syncthreads();
 
-  // finalise: thread e -> (pixel e / C, channel e % C); consecutive threads write consecutive floats
+  // finalise in place: thread -> pixel, channels in lock-step across the warp (no divergence between kinds)
   const int C = P.C;
+  for (int p = tid; p < npix; p += TILE_THREADS) {
+    uint32_t* a = acc + p * stride;
+    float o[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) o[c] = md_value(P, P.ch[c], a, delta_f, delta, w.has_m1);
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) a[c] = __float_as_uint(o[c]);
+  }
+  __syncthreads();
+
+  // stream the tile's slice of the (B, H, W, C) output: consecutive threads write consecutive 16 bytes
   float* dst = out + ((size_t)b * g.HW + pix0) * C;
-  const int n_el = npix * C;
-  for (int e = tid; e < n_el; e += TILE_THREADS) {
-    const int pix = e / C, c = e - pix * C;
-    dst[e] = md_value(P, P.ch[c], acc, TP, pix, delta, w.has_m1);
+  if ((C & 3) == 0) {
+    const int q_per_px = C >> 2, n_q = npix * q_per_px;
+    float4* dst4 = reinterpret_cast<float4*>(dst);  // (b*HW + pix0)*C*4 bytes: multiple of 16 because C % 4 == 0
+    for (int e = tid; e < n_q; e += TILE_THREADS) {
+      const int p = e / q_per_px, q = e - p * q_per_px;
+      const uint32_t* a = acc + p * stride + 4 * q;
+      __stcs(dst4 + e, make_float4(__uint_as_float(a[0]), __uint_as_float(a[1]), __uint_as_float(a[2]), __uint_as_float(a[3])));
+    }
+  } else {
+    const int n_el = npix * C;
+    for (int e = tid; e < n_el; e += TILE_THREADS) {
+      const int p = e / C, c = e - p * C;
+      __stcs(dst + e, __uint_as_float(acc[p * stride + c]));
+    }
   }
 }
 
@@ -288,8 +321,11 @@ int launch_md_tile(const Geom& g, const Workspace& ws, const MdPlan& plan, const
     EVREP_CUDA_OK(cudaGetLastError());
   }
   const size_t smem = md_tile_smem_bytes(plan, g.tile_px);
-  EVREP_CUDA_OK(cudaFuncSetAttribute(k_md_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_md_tile<<<g.B * g.T, TILE_THREADS, smem, stream>>>(ws.records, ws.base, ws.cursor, ws.wp, plan, g, out);
+  auto kern = plan.C <= 12 ? k_md_tile<12> : k_md_tile<EVREP_MAX_CHANNELS>;
+  EVREP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  prof_begin(EVREP_K_TILE, stream);
+  kern<<<g.B * g.T, TILE_THREADS, smem, stream>>>(ws.records, ws.base, ws.cursor, ws.wp, plan, g, out);
+  prof_end(EVREP_K_TILE, stream);
   EVREP_CUDA_OK(cudaGetLastError());
   return EVREP_OK;
 }

@@ -61,7 +61,9 @@ __global__ void __launch_bounds__(TILE_THREADS) k_event_stack_tile(const uint2* 
 int launch_event_stack_tile(const Geom& g, const Workspace& ws, int stack_size, float* out, cudaStream_t stream) {
   const size_t smem = sizeof(uint32_t) * (size_t)g.tile_px;
   EVREP_CUDA_OK(cudaFuncSetAttribute(k_event_stack_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  prof_begin(EVREP_K_TILE, stream);
   k_event_stack_tile<<<g.B * g.T, TILE_THREADS, smem, stream>>>(ws.records, ws.base, ws.cursor, ws.wp, g, stack_size, out);
+  prof_end(EVREP_K_TILE, stream);
   EVREP_CUDA_OK(cudaGetLastError());
   return EVREP_OK;
 }
@@ -127,7 +129,9 @@ __global__ void __launch_bounds__(TILE_THREADS) k_time_surface_tile(const uint2*
 int launch_time_surface_tile(const Geom& g, const Workspace& ws, int S, double tau, float* out, cudaStream_t stream) {
   const size_t smem = sizeof(uint32_t) * (size_t)g.tile_px * 2 * S;
   EVREP_CUDA_OK(cudaFuncSetAttribute(k_time_surface_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  prof_begin(EVREP_K_TILE, stream);
   k_time_surface_tile<<<g.B * g.T, TILE_THREADS, smem, stream>>>(ws.records, ws.base, ws.cursor, ws.wp, ws.snap, g, S, tau, out);
+  prof_end(EVREP_K_TILE, stream);
   EVREP_CUDA_OK(cudaGetLastError());
   return EVREP_OK;
 }
@@ -185,7 +189,9 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tore_tile(const uint2* __restr
 int launch_tore_tile(const Geom& g, const Workspace& ws, int k, float* out, cudaStream_t stream) {
   const size_t smem = sizeof(uint32_t) * (size_t)g.tile_px * 2 * k;
   EVREP_CUDA_OK(cudaFuncSetAttribute(k_tore_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  prof_begin(EVREP_K_TILE, stream);
   k_tore_tile<<<g.B * g.T, TILE_THREADS, smem, stream>>>(ws.records, ws.base, ws.cursor, ws.wp, g, k, out);
+  prof_end(EVREP_K_TILE, stream);
   EVREP_CUDA_OK(cudaGetLastError());
   return EVREP_OK;
 }

@@ -83,10 +83,25 @@ extern "C" {
 #define EVREP_WF_T_RANGE 0x400u      /* |t - t_first| does not fit 31 bits; the event was dropped */
 #define EVREP_WF_BAD_POLARITY 0x800u /* p outside {-1,0,1}; treated as sign(p) */
 
+/* kernels of the tile pipeline, for evrep_profile_read */
+#define EVREP_K_COUNT 0 /* bucket sizes (binning pass 1) */
+#define EVREP_K_SCAN 1  /* bucket starts */
+#define EVREP_K_BIN 2   /* scatter into tile buckets (binning pass 2) */
+#define EVREP_K_TILE 3  /* per-tile reduction + finalise: the kernel that writes the output */
+#define EVREP_K_N 4
+
 typedef void* evrep_stream_t; /* a cudaStream_t */
 
 int evrep_version(void);
 const char* evrep_last_error(void);
+
+/* Per-kernel device timing for benchmarks.  evrep_profile_enable(n) makes the next n batched calls record
+ * CUDA events around their kernels on the caller's stream (no synchronisation, a few microseconds of
+ * stream time per call); n = 0 switches it off and frees the events.  evrep_profile_read synchronises on
+ * the recorded events and returns, for one kernel, the summed milliseconds and the number of launches
+ * timed since the last enable.  Process-global, not thread safe: benchmark use only. */
+int evrep_profile_enable(int max_calls);
+int evrep_profile_read(int kernel_id, float* total_ms, int* launches);
 
 /* Upper bound of the scratch an op needs for a batch of B windows with total_events events on an
  * H x W sensor producing C channels.  0 on invalid arguments. */

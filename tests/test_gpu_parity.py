@@ -13,6 +13,10 @@ from conftest import assert_close, golden, load
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-5  # the float tolerance BASELINE.json states
+# TORE: the reference computes log(age + 1) - log(151) in float32 (tore.py:69-79); for ages near 150 us the two
+# logs (~5.0, ulp 4.8e-7) nearly cancel, so one ulp of difference between numpy's and CUDA's float32 log
+# shows up as ~5e-7 absolute on a value of ~1e-2.  The selection of the k ages itself is integer exact.
+TORE_ATOL = 1e-6
 VAR_ATOL = 2e-7  # variance = E[x^2] - E[x]^2 on values in [0,1]: float32 output resolution of the operands
 
 
@@ -117,7 +121,7 @@ TF = golden("tore_fixed_*")
 def test_tore_golden(E, name, path):
     g = load(path)
     out = np_(E.tore(batch_of(E, [g]), int(g["H"]), int(g["W"]), int(g["k"])))[0]
-    assert_close(out, g["out"], rtol=RTOL, atol=0, what=name)
+    assert_close(out, g["out"], rtol=RTOL, atol=TORE_ATOL, what=name)
 
 
 VT = [c for c in golden("voxel_tonic_*") if "tconst" not in c[0]]  # t[-1]==t[0]: numpy NaN->int cast is undefined there
@@ -267,7 +271,7 @@ def test_order_ops_vs_oracle(E, H, W, sizes):
                          what="time surface")
         t = w["t"].astype(np.int32)
         want = orep.tore(w["x"].astype(np.int32) + 1, w["y"].astype(np.int32) + 1, t, w["p"].astype(np.int32), t[-1], 6, (H, W))
-        assert_close(tr[i], want, rtol=RTOL, atol=0, what="tore")
+        assert_close(tr[i], want, rtol=RTOL, atol=TORE_ATOL, what="tore")
 
 
 def test_voxels_vs_oracle(E):
