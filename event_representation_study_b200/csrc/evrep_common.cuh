@@ -133,7 +133,8 @@ struct MdChan {
   int8_t g_main, g_all, g_pos, g_neg;
 };
 struct MdPlan {
-  int32_t C, G, words, stride, nl1, nl2, lw, w_pres, stacking, pad;
+  int32_t C, G, words, stride, nl1, nl2, lw, w_pres, stacking;
+  int32_t static_id;  // 0, or version * 100 + limb width of a compile-time specialised ERGO-12 kernel
   MdGroup grp[MD_MAX_GROUPS];
   MdChan ch[EVREP_MAX_CHANNELS];
 };

@@ -1,0 +1,122 @@
+// Accumulator plan of the mixed-density tile kernel, buildable at run time (any tuple) and at compile time
+// (the ERGO-12 tuples, so that their kernels are fully specialised).
+#pragma once
+#include "evrep_common.cuh"
+
+namespace evrep {
+
+// representations/optimized_representation.py:86-115 (v2, active) and :16-66 (v1, commented out)
+constexpr int8_t kErgoWin2[12] = {0, 3, 2, 6, 5, 6, 2, 5, 1, 0, 4, 1};
+constexpr int8_t kErgoFunc2[12] = {EVREP_FUNC_POLARITY, EVREP_FUNC_TIMESTAMP_NEG, EVREP_FUNC_COUNT_NEG, EVREP_FUNC_POLARITY,
+                                   EVREP_FUNC_COUNT_POS, EVREP_FUNC_COUNT, EVREP_FUNC_TIMESTAMP_POS, EVREP_FUNC_COUNT_NEG,
+                                   EVREP_FUNC_TIMESTAMP_NEG, EVREP_FUNC_TIMESTAMP_POS, EVREP_FUNC_TIMESTAMP, EVREP_FUNC_COUNT};
+constexpr int8_t kErgoAgg2[12] = {EVREP_AGG_VARIANCE, EVREP_AGG_VARIANCE, EVREP_AGG_MEAN, EVREP_AGG_SUM, EVREP_AGG_MEAN, EVREP_AGG_SUM,
+                                  EVREP_AGG_MEAN, EVREP_AGG_MEAN, EVREP_AGG_MAX, EVREP_AGG_MAX, EVREP_AGG_MAX, EVREP_AGG_MEAN};
+constexpr int8_t kErgoWin1[12] = {0, 2, 2, 3, 5, 0, 0, 4, 2, 6, 1, 1};
+constexpr int8_t kErgoFunc1[12] = {EVREP_FUNC_TIMESTAMP, EVREP_FUNC_TIMESTAMP_POS, EVREP_FUNC_TIMESTAMP_NEG, EVREP_FUNC_COUNT_NEG,
+                                   EVREP_FUNC_COUNT_POS, EVREP_FUNC_POLARITY, EVREP_FUNC_TIMESTAMP, EVREP_FUNC_COUNT,
+                                   EVREP_FUNC_TIMESTAMP_POS, EVREP_FUNC_COUNT, EVREP_FUNC_TIMESTAMP_POS, EVREP_FUNC_TIMESTAMP_NEG};
+constexpr int8_t kErgoAgg1[12] = {EVREP_AGG_MAX, EVREP_AGG_SUM, EVREP_AGG_MEAN, EVREP_AGG_SUM, EVREP_AGG_MEAN, EVREP_AGG_VARIANCE,
+                                  EVREP_AGG_VARIANCE, EVREP_AGG_SUM, EVREP_AGG_MEAN, EVREP_AGG_SUM, EVREP_AGG_SUM, EVREP_AGG_SUM};
+
+// limb width for windows of at most n_max events: a limb sum must fit 32 bits
+constexpr int md_limb_width(int64_t n_max) {
+  int nbits = 0;
+  while (nbits < 31 && ((int64_t)1 << nbits) <= n_max) ++nbits;  // n_max < 2^nbits
+  int lw = 32 - nbits;
+  return lw > 31 ? 31 : (lw < 1 ? 1 : lw);
+}
+
+// Returns 0, or 1 when the plan needs too many accumulator words.  C in 1..EVREP_MAX_CHANNELS, stacking valid.
+constexpr int md_plan_build(const int8_t* win, const int8_t* func, const int8_t* agg, int C, int stacking, int lw, MdPlan& P) {
+  P = MdPlan{};
+  P.C = C;
+  P.stacking = stacking;
+  P.lw = lw;
+  P.nl1 = (31 + lw - 1) / lw;
+  P.nl2 = (62 + lw - 1) / lw;
+  const int n_win = stacking == EVREP_STACK_SBN ? 7 : 8;
+  for (int c = 0; c < C; ++c) {
+    MdChan& ch = P.ch[c];
+    int wi = win[c];
+    if (wi < 0 && wi >= -n_win) wi += n_win;  // the reference indexes a Python list: negative indices wrap
+    ch.func = (uint8_t)func[c];
+    ch.agg = (uint8_t)agg[c];
+    ch.win = (uint8_t)wi;
+    ch.g_main = ch.g_all = ch.g_pos = ch.g_neg = -1;
+    // an unknown window / function / aggregation raises inside the reference's make_stack and is
+    // swallowed into an all-zero channel (mixed_density_event_stack.py:120-127)
+    if (wi < 0 || wi >= n_win || func[c] < 0 || func[c] > EVREP_FUNC_COUNT_NEG || agg[c] < 0 || agg[c] > EVREP_AGG_VARIANCE) {
+      ch.valid = 0;
+      continue;
+    }
+    ch.valid = 1;
+    const int f = func[c], a = agg[c];
+    // up to three (class, need) requests per channel
+    int req_cls[3] = {0, 0, 0}, req_need[3] = {0, 0, 0}, n_req = 0;
+    if (f == EVREP_FUNC_POLARITY) {
+      req_cls[0] = 1; req_need[0] = G_CNT;
+      req_cls[1] = 2; req_need[1] = G_CNT;
+      n_req = 2;
+      if (a != EVREP_AGG_SUM) { req_cls[2] = 0; req_need[2] = G_CNT; n_req = 3; }
+    } else {
+      const bool is_count = (f == EVREP_FUNC_COUNT || f == EVREP_FUNC_COUNT_POS || f == EVREP_FUNC_COUNT_NEG);
+      req_cls[0] = (f == EVREP_FUNC_COUNT || f == EVREP_FUNC_TIMESTAMP) ? 0 : (f == EVREP_FUNC_COUNT_POS || f == EVREP_FUNC_TIMESTAMP_POS) ? 1 : 2;
+      if (is_count)
+        req_need[0] = a == EVREP_AGG_SUM ? G_CNT : (a == EVREP_AGG_VARIANCE ? 0 : G_PRES);  // variance of a constant is 0
+      else
+        req_need[0] = a == EVREP_AGG_SUM ? (G_ST | G_PRES) : a == EVREP_AGG_MEAN ? (G_ST | G_CNT) : a == EVREP_AGG_MAX ? G_MAX : (G_ST | G_ST2 | G_CNT);
+      n_req = req_need[0] ? 1 : 0;
+    }
+    for (int r = 0; r < n_req; ++r) {
+      const int bit = req_cls[r] * 8 + wi;
+      int g = 0;
+      for (; g < P.G; ++g)
+        if (P.grp[g].bit == bit) break;
+      if (g == P.G) { P.grp[g].bit = (uint8_t)bit; P.grp[g].flags = 0; ++P.G; }
+      P.grp[g].flags |= (uint8_t)req_need[r];
+      if (f == EVREP_FUNC_POLARITY) {
+        if (r == 0) ch.g_pos = (int8_t)g; else if (r == 1) ch.g_neg = (int8_t)g; else ch.g_all = (int8_t)g;
+      } else {
+        ch.g_main = (int8_t)g;
+      }
+    }
+  }
+  int words = 0, pres_bits = 0;
+  bool any_pres = false;
+  for (int g = 0; g < P.G; ++g) {
+    MdGroup& G = P.grp[g];
+    if (G.flags & G_CNT) G.flags &= (uint8_t)~G_PRES;                          // a count subsumes the presence bit
+    if ((G.flags & G_PRES) && (G.flags & G_MAX)) G.flags &= (uint8_t)~G_PRES;  // so does a latest-timestamp word
+    if (G.flags & G_PRES) any_pres = true;
+  }
+  if (any_pres) P.w_pres = words++;
+  for (int g = 0; g < P.G; ++g) {
+    MdGroup& G = P.grp[g];
+    if (G.flags & G_PRES) G.pres_bit = (uint8_t)pres_bits++;
+    if (G.flags & G_CNT) G.w_cnt = (uint8_t)words++;
+    if (G.flags & G_MAX) G.w_max = (uint8_t)words++;
+    if (G.flags & G_ST) { G.w_st = (uint8_t)words; words += P.nl1; }
+    if (G.flags & G_ST2) { G.w_st2 = (uint8_t)words; words += P.nl2; }
+    if (words > 250) return 1;
+  }
+  if (words == 0) words = 1;
+  P.words = words;
+  P.stride = (words > C ? words : C) | 1;  // odd: bank-conflict-free, and room for the C outputs written in place
+  return 0;
+}
+
+// compile-time ERGO-12 plans for a menu of limb widths
+constexpr int kErgoLimbMenu[] = {16, 14, 12, 10, 8};  // windows below 2^16, 2^18, 2^20, 2^22, 2^24 events
+template <int VER, int LW>
+struct ErgoPlan {
+  static constexpr MdPlan make() {
+    MdPlan P{};
+    md_plan_build(VER == 2 ? kErgoWin2 : kErgoWin1, VER == 2 ? kErgoFunc2 : kErgoFunc1, VER == 2 ? kErgoAgg2 : kErgoAgg1, 12,
+                  EVREP_STACK_SBN, LW, P);
+    return P;
+  }
+  static constexpr MdPlan value = make();
+};
+
+}  // namespace evrep

@@ -10,18 +10,19 @@
 // swallow-and-zero), optimized_representation.py:86-134 (the ERGO-12 tuple).
 #include <string.h>
 
+#include <utility>
+
 #include "evrep_common.cuh"
+#include "md_plan.cuh"
 
 namespace evrep {
 
 size_t md_tile_smem_bytes(const MdPlan& plan, int tile_px) { return align_up((size_t)plan.stride * (size_t)tile_px * sizeof(uint32_t), 16); }
 
 // ---------------------------------------------------------------------------------------------
-// host: (window, function, aggregation) tuple -> accumulator plan
+// host: (window, function, aggregation) tuple -> accumulator plan (md_plan.cuh does the work)
 // ---------------------------------------------------------------------------------------------
 int build_md_plan(const int8_t* win, const int8_t* func, const int8_t* agg, int C, int stacking, int64_t n_max, MdPlan* out) {
-  MdPlan& P = *out;
-  memset(&P, 0, sizeof(P));
   if (C < 1 || C > EVREP_MAX_CHANNELS) {
     set_error("C = %d outside 1..%d", C, EVREP_MAX_CHANNELS);
     return EVREP_EINVAL;
@@ -30,85 +31,29 @@ int build_md_plan(const int8_t* win, const int8_t* func, const int8_t* agg, int 
     set_error("stacking must be EVREP_STACK_SBN or EVREP_STACK_SBT");
     return EVREP_EINVAL;
   }
-  P.C = C;
-  P.stacking = stacking;
-  // limb width: a limb sum over at most n_max events must fit 32 bits
-  int nbits = 0;
-  while (nbits < 31 && ((int64_t)1 << nbits) <= n_max) ++nbits;  // n_max < 2^nbits
-  P.lw = 32 - nbits;
-  if (P.lw > 31) P.lw = 31;
-  if (P.lw < 1) P.lw = 1;
-  P.nl1 = (31 + P.lw - 1) / P.lw;
-  P.nl2 = (62 + P.lw - 1) / P.lw;
-
-  const int n_win = stacking == EVREP_STACK_SBN ? 7 : 8;
-  auto group = [&](int w, int cls, int need) -> int {
-    const int bit = cls * 8 + w;
-    for (int g = 0; g < P.G; ++g)
-      if (P.grp[g].bit == bit) { P.grp[g].flags |= (uint8_t)need; return g; }
-    P.grp[P.G].bit = (uint8_t)bit;
-    P.grp[P.G].flags = (uint8_t)need;
-    return P.G++;
-  };
-  for (int c = 0; c < C; ++c) {
-    MdChan& ch = P.ch[c];
-    int wi = win[c];
-    if (wi < 0 && wi >= -n_win) wi += n_win;  // the reference indexes a Python list: negative indices wrap
-    ch.func = (uint8_t)func[c];
-    ch.agg = (uint8_t)agg[c];
-    ch.win = (uint8_t)wi;
-    ch.g_main = ch.g_all = ch.g_pos = ch.g_neg = -1;
-    // an unknown window / function / aggregation raises inside the reference's make_stack and is
-    // swallowed into an all-zero channel (mixed_density_event_stack.py:120-127)
-    if (wi < 0 || wi >= n_win || func[c] < 0 || func[c] > EVREP_FUNC_COUNT_NEG || agg[c] < 0 || agg[c] > EVREP_AGG_VARIANCE) {
-      ch.valid = 0;
-      continue;
-    }
-    ch.valid = 1;
-    const int f = func[c], a = agg[c], w = wi;
-    if (f == EVREP_FUNC_POLARITY) {
-      ch.g_pos = (int8_t)group(w, 1, G_CNT);
-      ch.g_neg = (int8_t)group(w, 2, G_CNT);
-      if (a != EVREP_AGG_SUM) ch.g_all = (int8_t)group(w, 0, G_CNT);
-      continue;
-    }
-    const bool is_count = (f == EVREP_FUNC_COUNT || f == EVREP_FUNC_COUNT_POS || f == EVREP_FUNC_COUNT_NEG);
-    const int cls = (f == EVREP_FUNC_COUNT || f == EVREP_FUNC_TIMESTAMP) ? 0
-                    : (f == EVREP_FUNC_COUNT_POS || f == EVREP_FUNC_TIMESTAMP_POS) ? 1 : 2;
-    int need = 0;
-    if (is_count) {
-      need = a == EVREP_AGG_SUM ? G_CNT : (a == EVREP_AGG_VARIANCE ? 0 : G_PRES);
-      if (need == 0) { ch.g_main = -1; continue; }  // variance of a constant: 0 everywhere
-    } else {
-      need = a == EVREP_AGG_SUM ? (G_ST | G_PRES) : a == EVREP_AGG_MEAN ? (G_ST | G_CNT) : a == EVREP_AGG_MAX ? G_MAX : (G_ST | G_ST2 | G_CNT);
-    }
-    ch.g_main = (int8_t)group(w, cls, need);
-  }
-  // word assignment
-  int words = 0, pres_bits = 0;
-  bool any_pres = false;
-  for (int g = 0; g < P.G; ++g) {
-    MdGroup& G = P.grp[g];
-    if (G.flags & G_CNT) G.flags &= (uint8_t)~G_PRES;  // a count subsumes the presence bit
-    if ((G.flags & G_PRES) && (G.flags & G_MAX)) G.flags &= (uint8_t)~G_PRES;  // so does a latest-timestamp word
-    if (G.flags & G_PRES) any_pres = true;
-  }
-  if (any_pres) P.w_pres = words++;
-  for (int g = 0; g < P.G; ++g) {
-    MdGroup& G = P.grp[g];
-    if (G.flags & G_PRES) G.pres_bit = (uint8_t)pres_bits++;
-    if (G.flags & G_CNT) G.w_cnt = (uint8_t)words++;
-    if (G.flags & G_MAX) G.w_max = (uint8_t)words++;
-    if (G.flags & G_ST) { G.w_st = (uint8_t)words; words += P.nl1; }
-    if (G.flags & G_ST2) { G.w_st2 = (uint8_t)words; words += P.nl2; }
-    if (words > 250) {
-      set_error("mixed-density plan needs more than 250 accumulator words per pixel");
-      return EVREP_EUNSUPPORTED;
+  int lw = md_limb_width(n_max);
+  // ERGO-12 has kernels specialised at compile time for a menu of limb widths: round down onto the menu
+  out->static_id = 0;
+  if (C == 12 && stacking == EVREP_STACK_SBN) {
+    int ver = 0;
+    if (!memcmp(win, kErgoWin2, 12) && !memcmp(func, kErgoFunc2, 12) && !memcmp(agg, kErgoAgg2, 12)) ver = 2;
+    if (!memcmp(win, kErgoWin1, 12) && !memcmp(func, kErgoFunc1, 12) && !memcmp(agg, kErgoAgg1, 12)) ver = 1;
+    if (ver) {
+      int pick = 0;
+      for (int m : kErgoLimbMenu)
+        if (m <= lw) { pick = m; break; }
+      if (pick) {
+        lw = pick;
+        if (md_plan_build(win, func, agg, C, stacking, lw, *out)) return EVREP_EUNSUPPORTED;
+        out->static_id = ver * 100 + lw;
+        return EVREP_OK;
+      }
     }
   }
-  if (words == 0) words = 1;
-  P.words = words;
-  P.stride = (words > C ? words : C) | 1;  // odd: bank-conflict-free, and room for the C outputs written in place
+  if (md_plan_build(win, func, agg, C, stacking, lw, *out)) {
+    set_error("mixed-density plan needs more than 250 accumulator words per pixel");
+    return EVREP_EUNSUPPORTED;
+  }
   return EVREP_OK;
 }
 
@@ -284,6 +229,119 @@ __global__ void __launch_bounds__(TILE_THREADS) k_md_tile(const uint2* __restric
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// compile-time specialised variant (ERGO-12): same algorithm, the plan is a constant expression, so every
+// group test, word index, limb count and channel formula is folded and the loops disappear.
+// ---------------------------------------------------------------------------------------------
+template <typename PS, int GI>
+__device__ __forceinline__ void md_acc_group(uint32_t* a, uint32_t M, uint32_t tt, uint32_t& pres) {
+  constexpr MdGroup G = PS::value.grp[GI];
+  constexpr int LW = PS::value.lw, NL1 = PS::value.nl1, NL2 = PS::value.nl2;
+  constexpr uint32_t MASK = (1u << LW) - 1u;
+  if (!((M >> G.bit) & 1u)) return;
+  if constexpr (G.flags & G_CNT) atomicAdd(a + G.w_cnt, 1u);
+  if constexpr (G.flags & G_PRES) pres |= 1u << G.pres_bit;
+  if constexpr (G.flags & G_MAX) atomicMax(a + G.w_max, tt + 1u);
+  if constexpr (G.flags & G_ST) {
+#pragma unroll
+    for (int l = 0; l < NL1; ++l) {
+      const uint32_t limb = (tt >> (l * LW)) & MASK;
+      if (limb) atomicAdd(a + G.w_st + l, limb);
+    }
+  }
+  if constexpr (G.flags & G_ST2) {
+    const unsigned long long v = (unsigned long long)tt * (unsigned long long)tt;
+#pragma unroll
+    for (int l = 0; l < NL2; ++l) {
+      const uint32_t limb = (uint32_t)(v >> (l * LW)) & MASK;
+      if (limb) atomicAdd(a + G.w_st2 + l, limb);
+    }
+  }
+}
+template <typename PS, int... GI>
+__device__ __forceinline__ void md_acc_all(uint32_t* a, uint32_t M, uint32_t tt, uint32_t& pres, std::integer_sequence<int, GI...>) {
+  (md_acc_group<PS, GI>(a, M, tt, pres), ...);
+}
+
+template <typename PS, int CI>
+__device__ __forceinline__ float md_value_static(const uint32_t* a, float delta_f, double delta, uint32_t has_m1) {
+  constexpr MdPlan P = PS::value;
+  constexpr MdChan ch = PS::value.ch[CI];
+  return md_value(P, ch, a, delta_f, delta, has_m1);
+}
+template <typename PS, int... CI>
+__device__ __forceinline__ void md_finalise_static(uint32_t* a, float delta_f, double delta, uint32_t has_m1, std::integer_sequence<int, CI...>) {
+  const float o[sizeof...(CI)] = {md_value_static<PS, CI>(a, delta_f, delta, has_m1)...};
+  ((a[CI] = __float_as_uint(o[CI])), ...);
+}
+
+template <typename PS>
+__global__ void __launch_bounds__(TILE_THREADS, 2) k_md_tile_static(const uint2* __restrict__ records, const uint32_t* __restrict__ base,
+                                                                    const uint32_t* __restrict__ cursor, const WinParams* __restrict__ wp,
+                                                                    const Geom g, float* __restrict__ out) {
+  extern __shared__ __align__(16) uint32_t acc[];
+  constexpr int STRIDE = PS::value.stride, C = PS::value.C, G = PS::value.G;
+  static_assert(PS::value.stacking == EVREP_STACK_SBN && (C & 3) == 0, "static path: SBN, C % 4 == 0");
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x / g.T, tile = blockIdx.x - b * g.T;
+  const int TP = g.tile_px;
+  const int pix0 = tile << g.tile_shift;
+  const int npix = min(TP, g.HW - pix0);
+  {
+    uint4* a4 = reinterpret_cast<uint4*>(acc);
+    const int n4 = (STRIDE * TP + 3) / 4;
+    for (int i = tid; i < n4; i += TILE_THREADS) a4[i] = make_uint4(0, 0, 0, 0);
+  }
+  const WinParams w = wp[b];
+  const uint32_t count = cursor[blockIdx.x];
+  const uint2* rec = records + w.start + base[blockIdx.x];
+  const int32_t tmin = w.tmin_rel;
+  const uint32_t delta_u = (w.tmax_rel >= w.tmin_rel) ? (uint32_t)(w.tmax_rel - w.tmin_rel) : 0u;
+  const double delta = (double)delta_u;
+  const float delta_f = (float)delta_u;
+  const uint32_t not_m1 = ~w.has_m1;
+  __syncthreads();
+
+  for (uint32_t i = tid; i < count; i += TILE_THREADS) {
+    const uint2 r = __ldg(rec + i);
+    uint32_t* a = acc + (r.y & 0xffffu) * STRIDE;
+    const uint32_t pc = (r.y >> 24) & 3u;
+    const uint32_t tt = (uint32_t)((int32_t)r.x - tmin);
+    const uint32_t wmask = (r.y >> 16) & 0xffu;
+    const uint32_t posm = (pc == 1u) ? wmask : 0u;
+    const uint32_t negm = (pc == 3u) ? wmask : (pc == 0u ? (wmask & not_m1) : 0u);
+    const uint32_t M = wmask | (posm << 8) | (negm << 16);
+    uint32_t pres = 0;
+    md_acc_all<PS>(a, M, tt, pres, std::make_integer_sequence<int, G>{});
+    if (pres) {
+      uint32_t* pw = a + PS::value.w_pres;
+      if ((*(volatile uint32_t*)pw & pres) != pres) atomicOr(pw, pres);
+    }
+  }
+  __syncthreads();
+  for (int p = tid; p < npix; p += TILE_THREADS)
+    md_finalise_static<PS>(acc + p * STRIDE, delta_f, delta, w.has_m1, std::make_integer_sequence<int, C>{});
+  __syncthreads();
+  constexpr int Q = C / 4;
+  float4* dst4 = reinterpret_cast<float4*>(out + ((size_t)b * g.HW + pix0) * C);
+  const int n_q = npix * Q;
+  for (int e = tid; e < n_q; e += TILE_THREADS) {
+    const int p = e / Q, q = e - p * Q;
+    const uint32_t* a = acc + p * STRIDE + 4 * q;
+    __stcs(dst4 + e, make_float4(__uint_as_float(a[0]), __uint_as_float(a[1]), __uint_as_float(a[2]), __uint_as_float(a[3])));
+  }
+}
+
+template <typename PS>
+static int launch_static(const Geom& g, const Workspace& ws, size_t smem, float* out, cudaStream_t stream) {
+  EVREP_CUDA_OK(cudaFuncSetAttribute(k_md_tile_static<PS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  prof_begin(EVREP_K_TILE, stream);
+  k_md_tile_static<PS><<<g.B * g.T, TILE_THREADS, smem, stream>>>(ws.records, ws.base, ws.cursor, ws.wp, g, out);
+  prof_end(EVREP_K_TILE, stream);
+  EVREP_CUDA_OK(cudaGetLastError());
+  return EVREP_OK;
+}
+
 // SBT only: which time windows hold a p == -1 event (needed before the tile pass can decide what
 // "negative" means in each window).  Runs after the binning pass, which produced t_min / t_max.
 template <typename TT>
@@ -321,6 +379,15 @@ int launch_md_tile(const Geom& g, const Workspace& ws, const MdPlan& plan, const
     EVREP_CUDA_OK(cudaGetLastError());
   }
   const size_t smem = md_tile_smem_bytes(plan, g.tile_px);
+  switch (plan.static_id) {
+#define EVREP_STATIC_CASE(VER, LW) \
+  case VER * 100 + LW:             \
+    return launch_static<ErgoPlan<VER, LW>>(g, ws, smem, out, stream);
+    EVREP_STATIC_CASE(2, 16) EVREP_STATIC_CASE(2, 14) EVREP_STATIC_CASE(2, 12) EVREP_STATIC_CASE(2, 10) EVREP_STATIC_CASE(2, 8)
+    EVREP_STATIC_CASE(1, 16) EVREP_STATIC_CASE(1, 14) EVREP_STATIC_CASE(1, 12) EVREP_STATIC_CASE(1, 10) EVREP_STATIC_CASE(1, 8)
+#undef EVREP_STATIC_CASE
+    default: break;
+  }
   auto kern = plan.C <= 12 ? k_md_tile<12> : k_md_tile<EVREP_MAX_CHANNELS>;
   EVREP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   prof_begin(EVREP_K_TILE, stream);
