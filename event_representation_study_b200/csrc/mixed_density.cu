@@ -119,7 +119,7 @@ template <int CMAX>
 __global__ void __launch_bounds__(TILE_THREADS) k_md_tile(const uint2* __restrict__ records, const uint32_t* __restrict__ base,
                                                           const uint32_t* __restrict__ cursor, const WinParams* __restrict__ wp,
                                                           const __grid_constant__ MdPlan P, const Geom g, float* __restrict__ out) {
-  extern __shared__ __align__(16) uint32_t acc[];
+  extern __shared__ __align__(128) uint32_t acc[];
   const int tid = threadIdx.x;
   const int b = blockIdx.x / g.T, tile = blockIdx.x - b * g.T;
   const int TP = g.tile_px;
@@ -270,31 +270,63 @@ __device__ __forceinline__ float md_value_static(const uint32_t* a, float delta_
   return md_value(P, ch, a, delta_f, delta, has_m1);
 }
 template <typename PS, int... CI>
-__device__ __forceinline__ void md_finalise_static(uint32_t* a, float delta_f, double delta, uint32_t has_m1, std::integer_sequence<int, CI...>) {
-  const float o[sizeof...(CI)] = {md_value_static<PS, CI>(a, delta_f, delta, has_m1)...};
-  ((a[CI] = __float_as_uint(o[CI])), ...);
+__device__ __forceinline__ void md_finalise_static(const uint32_t* a, float delta_f, double delta, uint32_t has_m1, float (&o)[sizeof...(CI)],
+                                                   std::integer_sequence<int, CI...>) {
+  ((o[CI] = md_value_static<PS, CI>(a, delta_f, delta, has_m1)), ...);
 }
 
 template <typename PS>
+__device__ __forceinline__ void md_accumulate_static(uint32_t* acc, const uint2 r, int32_t tmin, uint32_t not_m1) {
+  constexpr int STRIDE = PS::value.stride, G = PS::value.G;
+  uint32_t* a = acc + (r.y & 0xffffu) * STRIDE;
+  const uint32_t pc = (r.y >> 24) & 3u;
+  const uint32_t tt = (uint32_t)((int32_t)r.x - tmin);
+  const uint32_t wmask = (r.y >> 16) & 0xffu;
+  const uint32_t posm = (pc == 1u) ? wmask : 0u;
+  const uint32_t negm = (pc == 3u) ? wmask : (pc == 0u ? (wmask & not_m1) : 0u);
+  const uint32_t M = wmask | (posm << 8) | (negm << 16);
+  uint32_t pres = 0;
+  md_acc_all<PS>(a, M, tt, pres, std::make_integer_sequence<int, G>{});
+  if (pres) {
+    uint32_t* pw = a + PS::value.w_pres;
+    if ((*(volatile uint32_t*)pw & pres) != pres) atomicOr(pw, pres);
+  }
+}
+
+// TP = pixels per tile (compile time here), PPT = pixels per thread.
+// Timeline of one CTA: issue the first record loads -> zero the accumulators while they fly -> atomics ->
+// finalise every pixel into registers -> barrier -> repack the tile's output slice contiguously in shared
+// memory (it overwrites the dead accumulators) -> one thread per 12 KB hands it to the TMA engine
+// (cp.async.bulk shared -> global), which streams it out while the SM's other CTA computes.
+template <typename PS, int TP>
 __global__ void __launch_bounds__(TILE_THREADS, 2) k_md_tile_static(const uint2* __restrict__ records, const uint32_t* __restrict__ base,
                                                                     const uint32_t* __restrict__ cursor, const WinParams* __restrict__ wp,
                                                                     const Geom g, float* __restrict__ out) {
-  extern __shared__ __align__(16) uint32_t acc[];
-  constexpr int STRIDE = PS::value.stride, C = PS::value.C, G = PS::value.G;
-  static_assert(PS::value.stacking == EVREP_STACK_SBN && (C & 3) == 0, "static path: SBN, C % 4 == 0");
+  extern __shared__ __align__(128) uint32_t acc[];
+  constexpr int STRIDE = PS::value.stride, C = PS::value.C;
+  constexpr int PPT = TP / TILE_THREADS, PRE = 3;
+  static_assert(PS::value.stacking == EVREP_STACK_SBN && (C & 3) == 0 && TP % TILE_THREADS == 0, "static path: SBN, C % 4 == 0");
+  static_assert(C * 4 <= STRIDE * 4, "outputs must fit the accumulator footprint");
   const int tid = threadIdx.x;
   const int b = blockIdx.x / g.T, tile = blockIdx.x - b * g.T;
-  const int TP = g.tile_px;
-  const int pix0 = tile << g.tile_shift;
+  const int pix0 = tile * TP;
   const int npix = min(TP, g.HW - pix0);
-  {
-    uint4* a4 = reinterpret_cast<uint4*>(acc);
-    const int n4 = (STRIDE * TP + 3) / 4;
-    for (int i = tid; i < n4; i += TILE_THREADS) a4[i] = make_uint4(0, 0, 0, 0);
-  }
   const WinParams w = wp[b];
   const uint32_t count = cursor[blockIdx.x];
   const uint2* rec = records + w.start + base[blockIdx.x];
+
+  uint2 pre[PRE];
+#pragma unroll
+  for (int j = 0; j < PRE; ++j) {
+    const uint32_t i = tid + j * TILE_THREADS;
+    pre[j] = i < count ? __ldg(rec + i) : make_uint2(0u, 0u);  // meta 0: member of no window, touches nothing
+  }
+  {
+    uint4* a4 = reinterpret_cast<uint4*>(acc);
+    constexpr int N4 = (STRIDE * TP + 3) / 4;
+#pragma unroll 4
+    for (int i = tid; i < N4; i += TILE_THREADS) a4[i] = make_uint4(0, 0, 0, 0);
+  }
   const int32_t tmin = w.tmin_rel;
   const uint32_t delta_u = (w.tmax_rel >= w.tmin_rel) ? (uint32_t)(w.tmax_rel - w.tmin_rel) : 0u;
   const double delta = (double)delta_u;
@@ -302,41 +334,46 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_md_tile_static(const uint2*
   const uint32_t not_m1 = ~w.has_m1;
   __syncthreads();
 
-  for (uint32_t i = tid; i < count; i += TILE_THREADS) {
-    const uint2 r = __ldg(rec + i);
-    uint32_t* a = acc + (r.y & 0xffffu) * STRIDE;
-    const uint32_t pc = (r.y >> 24) & 3u;
-    const uint32_t tt = (uint32_t)((int32_t)r.x - tmin);
-    const uint32_t wmask = (r.y >> 16) & 0xffu;
-    const uint32_t posm = (pc == 1u) ? wmask : 0u;
-    const uint32_t negm = (pc == 3u) ? wmask : (pc == 0u ? (wmask & not_m1) : 0u);
-    const uint32_t M = wmask | (posm << 8) | (negm << 16);
-    uint32_t pres = 0;
-    md_acc_all<PS>(a, M, tt, pres, std::make_integer_sequence<int, G>{});
-    if (pres) {
-      uint32_t* pw = a + PS::value.w_pres;
-      if ((*(volatile uint32_t*)pw & pres) != pres) atomicOr(pw, pres);
+#pragma unroll
+  for (int j = 0; j < PRE; ++j)
+    if (pre[j].y) md_accumulate_static<PS>(acc, pre[j], tmin, not_m1);
+  for (uint32_t i = tid + PRE * TILE_THREADS; i < count; i += TILE_THREADS) md_accumulate_static<PS>(acc, __ldg(rec + i), tmin, not_m1);
+  __syncthreads();
+
+  float o[PPT][C];
+#pragma unroll
+  for (int k = 0; k < PPT; ++k)
+    md_finalise_static<PS>(acc + (tid + k * TILE_THREADS) * STRIDE, delta_f, delta, w.has_m1, o[k], std::make_integer_sequence<int, C>{});
+  __syncthreads();
+  float4* stage = reinterpret_cast<float4*>(acc);  // [TP][C] floats, contiguous = the global layout of the slice
+#pragma unroll
+  for (int k = 0; k < PPT; ++k)
+#pragma unroll
+    for (int q = 0; q < C / 4; ++q)
+      stage[(tid + k * TILE_THREADS) * (C / 4) + q] = make_float4(o[k][4 * q], o[k][4 * q + 1], o[k][4 * q + 2], o[k][4 * q + 3]);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  constexpr int SLICE_PX = TP / 4;  // four issuing threads, one per 1/4 of the tile
+  if ((tid & 31) == 0 && tid < 128) {
+    const int p0 = (tid >> 5) * SLICE_PX;
+    const int np = min(SLICE_PX, npix - p0);
+    if (np > 0) {
+      float* dst = out + ((size_t)b * g.HW + pix0 + p0) * C;
+      const uint32_t src = (uint32_t)__cvta_generic_to_shared(acc + p0 * C);
+      const uint32_t bytes = (uint32_t)np * C * 4u;
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must outlive the read
     }
-  }
-  __syncthreads();
-  for (int p = tid; p < npix; p += TILE_THREADS)
-    md_finalise_static<PS>(acc + p * STRIDE, delta_f, delta, w.has_m1, std::make_integer_sequence<int, C>{});
-  __syncthreads();
-  constexpr int Q = C / 4;
-  float4* dst4 = reinterpret_cast<float4*>(out + ((size_t)b * g.HW + pix0) * C);
-  const int n_q = npix * Q;
-  for (int e = tid; e < n_q; e += TILE_THREADS) {
-    const int p = e / Q, q = e - p * Q;
-    const uint32_t* a = acc + p * STRIDE + 4 * q;
-    __stcs(dst4 + e, make_float4(__uint_as_float(a[0]), __uint_as_float(a[1]), __uint_as_float(a[2]), __uint_as_float(a[3])));
   }
 }
 
 template <typename PS>
 static int launch_static(const Geom& g, const Workspace& ws, size_t smem, float* out, cudaStream_t stream) {
-  EVREP_CUDA_OK(cudaFuncSetAttribute(k_md_tile_static<PS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  constexpr int TP = 1024;  // what choose_tile picks for the ERGO-12 footprint on every sensor below 4 Mpx
+  EVREP_CUDA_OK(cudaFuncSetAttribute(k_md_tile_static<PS, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   prof_begin(EVREP_K_TILE, stream);
-  k_md_tile_static<PS><<<g.B * g.T, TILE_THREADS, smem, stream>>>(ws.records, ws.base, ws.cursor, ws.wp, g, out);
+  k_md_tile_static<PS, TP><<<g.B * g.T, TILE_THREADS, smem, stream>>>(ws.records, ws.base, ws.cursor, ws.wp, g, out);
   prof_end(EVREP_K_TILE, stream);
   EVREP_CUDA_OK(cudaGetLastError());
   return EVREP_OK;
@@ -379,7 +416,7 @@ int launch_md_tile(const Geom& g, const Workspace& ws, const MdPlan& plan, const
     EVREP_CUDA_OK(cudaGetLastError());
   }
   const size_t smem = md_tile_smem_bytes(plan, g.tile_px);
-  switch (plan.static_id) {
+  switch (g.tile_px == 1024 ? plan.static_id : 0) {
 #define EVREP_STATIC_CASE(VER, LW) \
   case VER * 100 + LW:             \
     return launch_static<ErgoPlan<VER, LW>>(g, ws, smem, out, stream);
