@@ -83,19 +83,23 @@ __device__ __forceinline__ double md_limb_sum(const uint32_t* a, int w0, int nl,
   return s;
 }
 
-// One channel of one pixel.  All divisions are single fp32 divisions of exactly computed numerators and
-// denominators (no fp64 division, no cancellation after rounding), within 3e-7 relative of the reference's fp64.
-__device__ __forceinline__ float md_value(const MdPlan& P, const MdChan& ch, const uint32_t* a, float delta_f, double delta, uint32_t has_m1) {
+// One channel of one pixel.  Numerators and denominators are computed exactly (integers / fp64), then divided
+// once in fp32 with the hardware reciprocal (<= 2 ulp): no fp64 division and no cancellation after rounding,
+// within 4e-7 relative of the reference's fp64 result.  0 * rcp(0) = NaN reproduces the reference's 0/0.
+__device__ __forceinline__ float md_value(const MdPlan& P, const MdChan& ch, const uint32_t* a, float inv_delta, double delta, uint32_t delta_u,
+                                          uint32_t has_m1) {
   if (!ch.valid) return 0.f;
   if (ch.func == EVREP_FUNC_POLARITY) {
-    const long long c1 = a[P.grp[ch.g_pos].w_cnt];
-    const long long cm = ((has_m1 >> ch.win) & 1u) ? (long long)a[P.grp[ch.g_neg].w_cnt] : 0ll;
+    const int c1 = (int)a[P.grp[ch.g_pos].w_cnt];
+    const int cm = ((has_m1 >> ch.win) & 1u) ? (int)a[P.grp[ch.g_neg].w_cnt] : 0;
     if (ch.agg == EVREP_AGG_SUM) return (float)(c1 - cm);
-    const long long call = a[P.grp[ch.g_all].w_cnt];
+    const int call = (int)a[P.grp[ch.g_all].w_cnt];
     if (call == 0) return 0.f;
-    if (ch.agg == EVREP_AGG_MEAN) return (float)(c1 - cm) / (float)call;
-    if (ch.agg == EVREP_AGG_VARIANCE)  // mean(p^2) - mean(p)^2 = ((c1+cm) call - (c1-cm)^2) / call^2, numerator exact
-      return (float)((double)((c1 + cm) * call - (c1 - cm) * (c1 - cm))) / (float)((double)call * (double)call);
+    if (ch.agg == EVREP_AGG_MEAN) return __fdividef((float)(c1 - cm), (float)call);
+    if (ch.agg == EVREP_AGG_VARIANCE) {  // mean(p^2) - mean(p)^2 = ((c1+cm) call - (c1-cm)^2) / call^2, numerator exact in fp64
+      const double dc = (double)call, dd = (double)(c1 - cm);
+      return __fdividef((float)fma((double)(c1 + cm), dc, -dd * dd), (float)(dc * dc));
+    }
     return c1 > 0 ? 1.f : (call - c1 - cm > 0 ? 0.f : -1.f);  // max of the raw polarities
   }
   if (ch.g_main < 0) return 0.f;
@@ -104,15 +108,18 @@ __device__ __forceinline__ float md_value(const MdPlan& P, const MdChan& ch, con
   if (c == 0u) return 0.f;  // torch_scatter leaves untouched pixels at 0
   const bool is_count = (ch.func == EVREP_FUNC_COUNT || ch.func == EVREP_FUNC_COUNT_POS || ch.func == EVREP_FUNC_COUNT_NEG);
   if (is_count) return ch.agg == EVREP_AGG_SUM ? (float)c : 1.f;
-  // timestamps: t_s = (t - t_min) / (t_max - t_min); delta == 0 gives 0/0 = NaN exactly like the reference
-  if (ch.agg == EVREP_AGG_MAX) return (float)(a[G.w_max] - 1u) / delta_f;
+  // timestamps: t_s = (t - t_min) / (t_max - t_min); delta == 0 gives NaN exactly like the reference
+  if (ch.agg == EVREP_AGG_MAX) {
+    const uint32_t v = a[G.w_max] - 1u;
+    return (v == delta_u && delta_u) ? 1.f : (float)v * inv_delta;  // the window's last event maps to exactly 1
+  }
   const double st = md_limb_sum(a, G.w_st, P.nl1, P.lw);
-  if (ch.agg == EVREP_AGG_SUM) return (float)st / delta_f;
+  if (ch.agg == EVREP_AGG_SUM) return (float)st * inv_delta;
   const double cd = (double)c * delta;
-  if (ch.agg == EVREP_AGG_MEAN) return (float)st / (float)cd;
+  if (ch.agg == EVREP_AGG_MEAN) return __fdividef((float)st, (float)cd);
   const double st2 = md_limb_sum(a, G.w_st2, P.nl2, P.lw);
   // mean(t_s^2) - mean(t_s)^2 = (c sum(t^2) - sum(t)^2) / (c delta)^2
-  return (float)fma((double)c, st2, -st * st) / (float)(cd * cd);
+  return __fdividef((float)fma((double)c, st2, -st * st), (float)(cd * cd));
 }
 
 template <int CMAX>
@@ -138,7 +145,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_md_tile(const uint2* __restric
   const int32_t tmin = w.tmin_rel;
   const uint32_t delta_u = (w.tmax_rel >= w.tmin_rel) ? (uint32_t)(w.tmax_rel - w.tmin_rel) : 0u;
   const double delta = (double)delta_u;
-  const float delta_f = (float)delta_u;
+  const float inv_delta = 1.f / (float)delta_u;
   const uint32_t limb_mask = (1u << P.lw) - 1u;  // lw <= 31
   __syncthreads();
 
@@ -203,7 +210,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_md_tile(const uint2* __restric
     float o[CMAX];
 #pragma unroll
     for (int c = 0; c < CMAX; ++c)
-      if (c < C) o[c] = md_value(P, P.ch[c], a, delta_f, delta, w.has_m1);
+      if (c < C) o[c] = md_value(P, P.ch[c], a, inv_delta, delta, delta_u, w.has_m1);
 #pragma unroll
     for (int c = 0; c < CMAX; ++c)
       if (c < C) a[c] = __float_as_uint(o[c]);
@@ -264,15 +271,15 @@ __device__ __forceinline__ void md_acc_all(uint32_t* a, uint32_t M, uint32_t tt,
 }
 
 template <typename PS, int CI>
-__device__ __forceinline__ float md_value_static(const uint32_t* a, float delta_f, double delta, uint32_t has_m1) {
+__device__ __forceinline__ float md_value_static(const uint32_t* a, float inv_delta, double delta, uint32_t delta_u, uint32_t has_m1) {
   constexpr MdPlan P = PS::value;
   constexpr MdChan ch = PS::value.ch[CI];
-  return md_value(P, ch, a, delta_f, delta, has_m1);
+  return md_value(P, ch, a, inv_delta, delta, delta_u, has_m1);
 }
 template <typename PS, int... CI>
-__device__ __forceinline__ void md_finalise_static(const uint32_t* a, float delta_f, double delta, uint32_t has_m1, float (&o)[sizeof...(CI)],
-                                                   std::integer_sequence<int, CI...>) {
-  ((o[CI] = md_value_static<PS, CI>(a, delta_f, delta, has_m1)), ...);
+__device__ __forceinline__ void md_finalise_static(const uint32_t* a, float inv_delta, double delta, uint32_t delta_u, uint32_t has_m1,
+                                                   float (&o)[sizeof...(CI)], std::integer_sequence<int, CI...>) {
+  ((o[CI] = md_value_static<PS, CI>(a, inv_delta, delta, delta_u, has_m1)), ...);
 }
 
 template <typename PS>
@@ -330,7 +337,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_md_tile_static(const uint2*
   const int32_t tmin = w.tmin_rel;
   const uint32_t delta_u = (w.tmax_rel >= w.tmin_rel) ? (uint32_t)(w.tmax_rel - w.tmin_rel) : 0u;
   const double delta = (double)delta_u;
-  const float delta_f = (float)delta_u;
+  const float inv_delta = 1.f / (float)delta_u;
   const uint32_t not_m1 = ~w.has_m1;
   __syncthreads();
 
@@ -343,7 +350,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_md_tile_static(const uint2*
   float o[PPT][C];
 #pragma unroll
   for (int k = 0; k < PPT; ++k)
-    md_finalise_static<PS>(acc + (tid + k * TILE_THREADS) * STRIDE, delta_f, delta, w.has_m1, o[k], std::make_integer_sequence<int, C>{});
+    md_finalise_static<PS>(acc + (tid + k * TILE_THREADS) * STRIDE, inv_delta, delta, delta_u, w.has_m1, o[k], std::make_integer_sequence<int, C>{});
   __syncthreads();
   float4* stage = reinterpret_cast<float4*>(acc);  // [TP][C] floats, contiguous = the global layout of the slice
 #pragma unroll
