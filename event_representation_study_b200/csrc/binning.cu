@@ -253,11 +253,11 @@ __global__ void __launch_bounds__(BIN_THREADS) k_scan(const uint32_t* __restrict
 // ---------------------------------------------------------------------------------------------
 // pass 2: scatter the events into their buckets as 8-byte records
 // ---------------------------------------------------------------------------------------------
-template <typename TT>
+template <typename TT, int MODE>
 __global__ void __launch_bounds__(BIN_THREADS) k_bin(const uint16_t* __restrict__ x, const uint16_t* __restrict__ y,
                                                      const TT* __restrict__ t, const int8_t* __restrict__ p,
                                                      WinParams* __restrict__ wp, const SnapParams* __restrict__ snap,
-                                                     const int32_t* __restrict__ chunk_prefix, Geom g, bool vec, int mode,
+                                                     const int32_t* __restrict__ chunk_prefix, Geom g, bool vec,
                                                      const uint32_t* __restrict__ base, uint32_t* __restrict__ cursor,
                                                      uint2* __restrict__ records) {
   extern __shared__ __align__(16) unsigned char sh_raw[];
@@ -275,29 +275,31 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin(const uint16_t* __restrict_
   const int tid = threadIdx.x;
   const int b = find_window(chunk_prefix, g.B, blockIdx.x);
   const int chunk = blockIdx.x - __ldg(chunk_prefix + b);
-  const int64_t start = wp[b].start, n = wp[b].n, end = start + n;
+  const int64_t start = wp[b].start;
+  const int n = (int)wp[b].n;  // < 2^31 - 8 (checked on the host)
   const int64_t t_base = wp[b].t_base;
   const int32_t tlast_rel = wp[b].tlast_rel;
 
   for (int i = tid; i < g.T; i += BIN_THREADS) cnt[i] = 0;
   if (tid == 0) { sh_tmin = INT_MAX; sh_tmax = INT_MIN; sh_flags = 0; sh_m1 = 0; sh_nsnap = 0; }
-  if (mode == REC_T_SNAP) {
+  if (MODE == REC_T_SNAP) {
     if (tid < MAX_SNAP) sh_snap_idx[tid] = snap[b].idx[tid];
     if (tid == 0) sh_nsnap = snap[b].n_valid;
   }
   __syncthreads();
 
   // index boundaries of the SBN windows (mixed_density_event_stack.py:55-74)
-  const int64_t n3 = n / 3, s4 = n / 2, s5 = s4 + n / 4, s6 = s5 + n / 8;
+  const int n3 = n / 3, s4 = n / 2, s5 = s4 + n / 4, s6 = s5 + n / 8;
 
   const int64_t g0 = (start & ~(int64_t)(EPT - 1)) + (int64_t)chunk * CHUNK + (int64_t)tid * EPT;
-  uint32_t key[EPT], meta[EPT], tile_rank[EPT];  // tile_rank = tile << 16 | rank-in-CTA... ranks < CHUNK = 2^12
+  const int idx0 = (int)(g0 - start);  // index of this thread's first event inside the window (may be < 0 at the head)
+  uint32_t key[EPT], meta[EPT], tile_rank[EPT];  // tile_rank = tile << 16 | rank inside the CTA's bucket (< CHUNK = 2^12)
   int my_tmin = INT_MAX, my_tmax = INT_MIN;
   uint32_t my_flags = 0, my_m1 = 0;
 #pragma unroll
   for (int e = 0; e < EPT; ++e) tile_rank[e] = 0xffffffffu;
 
-  if (g0 < end) {
+  if (idx0 < n) {
     uint32_t xs[EPT], ys[EPT];
     int ps[EPT];
     int64_t ts[EPT];
@@ -305,35 +307,34 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin(const uint16_t* __restrict_
     load8_u16(y, g0, g.total, vec, ys);
     load8_i8(p, g0, g.total, vec, ps);
     load8_t<TT>(t, g0, g.total, vec, ts);
-    int64_t t_prev = (g0 - 1 >= start) ? (int64_t)__ldg(t + g0 - 1) : LLONG_MIN;
+    int64_t t_prev = (idx0 >= 1) ? (int64_t)__ldg(t + g0 - 1) : LLONG_MIN;
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
-      const int64_t a = g0 + e;
-      if (a < start || a >= end) continue;
+      const int idx = idx0 + e;
+      if (idx < 0 || idx >= n) continue;
       if (ts[e] < t_prev) my_flags |= EVREP_WF_UNSORTED;
       t_prev = ts[e];
-      if (xs[e] >= (uint32_t)g.W || ys[e] >= (uint32_t)g.H) { my_flags |= EVREP_WF_OUT_OF_RANGE; continue; }
       const int64_t d = ts[e] - t_base;
-      if (d >= T_REL_LIMIT || d <= -T_REL_LIMIT) { my_flags |= EVREP_WF_T_RANGE; continue; }
+      const bool bad_xy = xs[e] >= (uint32_t)g.W || ys[e] >= (uint32_t)g.H;
+      const bool bad_t = d >= T_REL_LIMIT || d <= -T_REL_LIMIT;
+      if (bad_xy | bad_t) { my_flags |= (bad_xy ? EVREP_WF_OUT_OF_RANGE : 0u) | (bad_t ? EVREP_WF_T_RANGE : 0u); continue; }
       const int32_t t_rel = (int32_t)d;
       int pv = ps[e];
       if (pv > 1 || pv < -1) { my_flags |= EVREP_WF_BAD_POLARITY; pv = pv > 0 ? 1 : -1; }
-      const int64_t idx = a - start;
       uint32_t aux = 0, k = (uint32_t)t_rel;
-      if (mode == REC_T_WMASK) {
-        aux = 1u;
-        aux |= idx < n3 ? 2u : (idx < 2 * n3 ? 4u : (idx < 3 * n3 ? 8u : 0u));
-        aux |= (idx >= s4 ? 16u : 0u) | (idx >= s5 ? 32u : 0u) | (idx >= s6 ? 64u : 0u);
-        if (pv == -1) my_m1 |= aux;
-      } else if (mode == REC_IDX) {
+      if (MODE == REC_T_WMASK) {
+        aux = 1u | (idx < n3 ? 2u : (idx < 2 * n3 ? 4u : (idx < 3 * n3 ? 8u : 0u))) | (idx >= s4 ? 16u : 0u) | (idx >= s5 ? 32u : 0u) |
+              (idx >= s6 ? 64u : 0u);
+        my_m1 |= pv == -1 ? aux : 0u;
+      } else if (MODE == REC_IDX) {
         k = (uint32_t)idx;
-      } else if (mode == REC_T_SNAP) {
+      } else if (MODE == REC_T_SNAP) {
         const int ns = sh_nsnap;
         int s = 0;
-        while (s < ns && idx > (int64_t)sh_snap_idx[s]) ++s;
+        while (s < ns && idx > sh_snap_idx[s]) ++s;
         if (s >= ns) continue;  // after the last emitted surface: feeds nothing
         aux = (uint32_t)s;
-      } else if (mode == REC_T_TORE) {  // strict `<` against the sample time = last timestamp (tore.py:17)
+      } else if (MODE == REC_T_TORE) {  // strict `<` against the sample time = last timestamp (tore.py:17)
         if (t_rel >= tlast_rel) continue;
       }
       my_tmin = min(my_tmin, t_rel);
@@ -385,6 +386,25 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin(const uint16_t* __restrict_
   for (uint32_t i = tid; i < total; i += BIN_THREADS) {
     const uint32_t tile = stile[i];
     dst[gbase[tile] + (i - loff[tile])] = stage[i];
+  }
+}
+
+template <typename TT, int MODE>
+static int launch_bin(const Events& ev, const Geom& g, const Workspace& ws, int n_chunks, bool vec, size_t smem, cudaStream_t stream) {
+  EVREP_CUDA_OK(cudaFuncSetAttribute(k_bin<TT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_bin<TT, MODE><<<n_chunks, BIN_THREADS, smem, stream>>>(ev.x, ev.y, (const TT*)ev.t, ev.p, ws.wp, ws.snap, ws.chunk_prefix, g, vec, ws.base,
+                                                           ws.cursor, ws.records);
+  EVREP_CUDA_OK(cudaGetLastError());
+  return EVREP_OK;
+}
+template <typename TT>
+static int launch_bin_mode(int mode, const Events& ev, const Geom& g, const Workspace& ws, int n_chunks, bool vec, size_t smem, cudaStream_t stream) {
+  switch (mode) {
+    case REC_T_WMASK: return launch_bin<TT, REC_T_WMASK>(ev, g, ws, n_chunks, vec, smem, stream);
+    case REC_IDX: return launch_bin<TT, REC_IDX>(ev, g, ws, n_chunks, vec, smem, stream);
+    case REC_T_SNAP: return launch_bin<TT, REC_T_SNAP>(ev, g, ws, n_chunks, vec, smem, stream);
+    case REC_T_TORE: return launch_bin<TT, REC_T_TORE>(ev, g, ws, n_chunks, vec, smem, stream);
+    default: return launch_bin<TT, REC_T_ONLY>(ev, g, ws, n_chunks, vec, smem, stream);
   }
 }
 
@@ -449,7 +469,7 @@ int run_binning(const Events& ev, const int64_t* win_offsets_host, const Geom& g
   prof_next_call();
   int rc = prepare_windows(ev, win_offsets_host, g, ws, &n_chunks, stream);
   if (rc) return rc;
-  EVREP_CUDA_OK(cudaMemsetAsync(ws.hist, 0, sizeof(uint32_t) * (size_t)g.B * g.T * 2, stream));  // hist + cursor
+  EVREP_CUDA_OK(cudaMemsetAsync(ws.hist, 0, sizeof(uint32_t) * ((size_t)g.B * g.T * 2 + 64), stream));  // hist + cursor + tickets
   const bool vec = events_vectorisable(ev);
 
   if (rec_mode == REC_T_SNAP) {
@@ -477,15 +497,9 @@ int run_binning(const Events& ev, const int64_t* win_offsets_host, const Geom& g
   if (n_chunks > 0) {
     prof_begin(EVREP_K_BIN, stream);
     const size_t smem = (size_t)CHUNK * (sizeof(uint2) + sizeof(uint16_t)) + 3 * sizeof(uint32_t) * (size_t)g.T;
-    if (ev.t_bytes == 4) {
-      EVREP_CUDA_OK(cudaFuncSetAttribute(k_bin<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_bin<int32_t><<<n_chunks, BIN_THREADS, smem, stream>>>(ev.x, ev.y, (const int32_t*)ev.t, ev.p, ws.wp, ws.snap, ws.chunk_prefix, g,
-                                                               vec, rec_mode, ws.base, ws.cursor, ws.records);
-    } else {
-      EVREP_CUDA_OK(cudaFuncSetAttribute(k_bin<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_bin<int64_t><<<n_chunks, BIN_THREADS, smem, stream>>>(ev.x, ev.y, (const int64_t*)ev.t, ev.p, ws.wp, ws.snap, ws.chunk_prefix, g,
-                                                               vec, rec_mode, ws.base, ws.cursor, ws.records);
-    }
+    const int rc2 = ev.t_bytes == 4 ? launch_bin_mode<int32_t>(rec_mode, ev, g, ws, n_chunks, vec, smem, stream)
+                                    : launch_bin_mode<int64_t>(rec_mode, ev, g, ws, n_chunks, vec, smem, stream);
+    if (rc2) return rc2;
     prof_end(EVREP_K_BIN, stream);
     EVREP_CUDA_OK(cudaGetLastError());
   }

@@ -63,6 +63,7 @@ struct Workspace {  // device pointers carved out of the caller's buffer
   int32_t* chunk_prefix;
   uint32_t* hist;    // B*T   bucket sizes (upper bound, from the counting pass)
   uint32_t* cursor;  // B*T   records actually written
+  uint32_t* ticket;  // 64 words after cursor (zeroed with it): work counters of persistent kernels
   uint32_t* base;    // B*T   bucket start, relative to the window's first record
   SnapParams* snap;  // B
   int64_t* snap_in;  // B*MAX_SNAP caller-supplied snapshot indices
@@ -86,8 +87,9 @@ inline Workspace carve(void* basep, int B, int64_t total, int T) {
   w.wp = (WinParams*)take(sizeof(WinParams) * (size_t)B);
   w.offsets = (int64_t*)take(sizeof(int64_t) * (size_t)(B + 1));
   w.chunk_prefix = (int32_t*)take(sizeof(int32_t) * (size_t)(B + 1));
-  w.hist = (uint32_t*)take(sizeof(uint32_t) * (size_t)B * T * 2);
+  w.hist = (uint32_t*)take(sizeof(uint32_t) * ((size_t)B * T * 2 + 64));
   w.cursor = w.hist ? w.hist + (size_t)B * T : nullptr;
+  w.ticket = w.hist ? w.hist + (size_t)B * T * 2 : nullptr;
   w.base = (uint32_t*)take(sizeof(uint32_t) * (size_t)B * T);
   w.snap = (SnapParams*)take(sizeof(SnapParams) * (size_t)B);
   w.snap_in = (int64_t*)take(sizeof(int64_t) * (size_t)B * MAX_SNAP);

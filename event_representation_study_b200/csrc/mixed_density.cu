@@ -241,33 +241,33 @@ __global__ void __launch_bounds__(TILE_THREADS) k_md_tile(const uint2* __restric
 // group test, word index, limb count and channel formula is folded and the loops disappear.
 // ---------------------------------------------------------------------------------------------
 template <typename PS, int GI>
-__device__ __forceinline__ void md_acc_group(uint32_t* a, uint32_t M, uint32_t tt, uint32_t& pres) {
+__device__ __forceinline__ void md_acc_group(uint32_t* a, uint32_t M, uint32_t tt, unsigned long long tt2, uint32_t& pres) {
   constexpr MdGroup G = PS::value.grp[GI];
   constexpr int LW = PS::value.lw, NL1 = PS::value.nl1, NL2 = PS::value.nl2;
   constexpr uint32_t MASK = (1u << LW) - 1u;
-  if (!((M >> G.bit) & 1u)) return;
-  if constexpr (G.flags & G_CNT) atomicAdd(a + G.w_cnt, 1u);
-  if constexpr (G.flags & G_PRES) pres |= 1u << G.pres_bit;
-  if constexpr (G.flags & G_MAX) atomicMax(a + G.w_max, tt + 1u);
+  const bool m = (M >> G.bit) & 1u;  // one predicate per atomic instead of nested branches
+  if constexpr (G.flags & G_CNT) { if (m) atomicAdd(a + G.w_cnt, 1u); }
+  if constexpr (G.flags & G_PRES) pres |= m ? (1u << G.pres_bit) : 0u;
+  if constexpr (G.flags & G_MAX) { if (m) atomicMax(a + G.w_max, tt + 1u); }
   if constexpr (G.flags & G_ST) {
 #pragma unroll
     for (int l = 0; l < NL1; ++l) {
       const uint32_t limb = (tt >> (l * LW)) & MASK;
-      if (limb) atomicAdd(a + G.w_st + l, limb);
+      if (m && limb) atomicAdd(a + G.w_st + l, limb);
     }
   }
   if constexpr (G.flags & G_ST2) {
-    const unsigned long long v = (unsigned long long)tt * (unsigned long long)tt;
 #pragma unroll
     for (int l = 0; l < NL2; ++l) {
-      const uint32_t limb = (uint32_t)(v >> (l * LW)) & MASK;
-      if (limb) atomicAdd(a + G.w_st2 + l, limb);
+      const uint32_t limb = (uint32_t)(tt2 >> (l * LW)) & MASK;
+      if (m && limb) atomicAdd(a + G.w_st2 + l, limb);
     }
   }
 }
 template <typename PS, int... GI>
 __device__ __forceinline__ void md_acc_all(uint32_t* a, uint32_t M, uint32_t tt, uint32_t& pres, std::integer_sequence<int, GI...>) {
-  (md_acc_group<PS, GI>(a, M, tt, pres), ...);
+  const unsigned long long tt2 = (unsigned long long)tt * (unsigned long long)tt;
+  (md_acc_group<PS, GI>(a, M, tt, tt2, pres), ...);
 }
 
 template <typename PS, int CI>
@@ -301,86 +301,139 @@ __device__ __forceinline__ void md_accumulate_static(uint32_t* acc, const uint2 
 }
 
 // TP = pixels per tile (compile time here), PPT = pixels per thread.
-// Timeline of one CTA: issue the first record loads -> zero the accumulators while they fly -> atomics ->
-// finalise every pixel into registers -> barrier -> repack the tile's output slice contiguously in shared
-// memory (it overwrites the dead accumulators) -> one thread per 12 KB hands it to the TMA engine
-// (cp.async.bulk shared -> global), which streams it out while the SM's other CTA computes.
+// Persistent CTAs (two per SM) pull (window, tile) buckets from a ticket counter.  Timeline of one bucket:
+// zero the accumulators -> atomics over the bucket's records (already in registers: they were fetched while
+// the previous bucket was being finalised) -> finalise every pixel into registers -> repack the tile's
+// output slice contiguously in shared memory (over the dead accumulators) -> four threads hand 12 KB each to
+// the TMA engine (cp.async.bulk shared -> global).  Header and record loads of the next bucket are issued
+// early, so no global-load latency sits on the critical path after the first bucket.
+struct TileHdr {
+  int b, pix0;
+  uint32_t count, has_m1, delta_u;
+  int32_t tmin;
+  const uint2* rec;
+};
+
+__device__ __forceinline__ TileHdr md_load_hdr(int id, const Geom& g, int TP, const uint2* records, const uint32_t* base,
+                                               const uint32_t* cursor, const WinParams* wp) {
+  TileHdr h;
+  h.b = id / g.T;
+  h.pix0 = (id - h.b * g.T) * TP;
+  const WinParams* w = wp + h.b;
+  h.count = __ldg(cursor + id);
+  h.rec = records + w->start + __ldg(base + id);
+  h.tmin = w->tmin_rel;
+  const int32_t tmax = w->tmax_rel;
+  h.delta_u = tmax >= h.tmin ? (uint32_t)(tmax - h.tmin) : 0u;
+  h.has_m1 = w->has_m1;
+  return h;
+}
+
 template <typename PS, int TP>
 __global__ void __launch_bounds__(TILE_THREADS, 2) k_md_tile_static(const uint2* __restrict__ records, const uint32_t* __restrict__ base,
                                                                     const uint32_t* __restrict__ cursor, const WinParams* __restrict__ wp,
-                                                                    const Geom g, float* __restrict__ out) {
+                                                                    const Geom g, uint32_t* __restrict__ ticket, float* __restrict__ out) {
   extern __shared__ __align__(128) uint32_t acc[];
+  __shared__ int s_next;
   constexpr int STRIDE = PS::value.stride, C = PS::value.C;
   constexpr int PPT = TP / TILE_THREADS, PRE = 3;
   static_assert(PS::value.stacking == EVREP_STACK_SBN && (C & 3) == 0 && TP % TILE_THREADS == 0, "static path: SBN, C % 4 == 0");
-  static_assert(C * 4 <= STRIDE * 4, "outputs must fit the accumulator footprint");
+  static_assert(C <= STRIDE, "outputs must fit the accumulator footprint");
   const int tid = threadIdx.x;
-  const int b = blockIdx.x / g.T, tile = blockIdx.x - b * g.T;
-  const int pix0 = tile * TP;
-  const int npix = min(TP, g.HW - pix0);
-  const WinParams w = wp[b];
-  const uint32_t count = cursor[blockIdx.x];
-  const uint2* rec = records + w.start + base[blockIdx.x];
+  const int n_tiles = g.B * g.T;
+  // bucket order: blockIdx.x, blockIdx.x + gridDim.x, then tickets 2*gridDim.x + k; the ticket for the bucket
+  // after next is requested a whole iteration early so that its round trip never stalls the CTA
+  int cur = blockIdx.x, nxt = blockIdx.x + (int)gridDim.x;
+  if (cur >= n_tiles) return;
 
+  TileHdr h = md_load_hdr(cur, g, TP, records, base, cursor, wp);
   uint2 pre[PRE];
 #pragma unroll
   for (int j = 0; j < PRE; ++j) {
     const uint32_t i = tid + j * TILE_THREADS;
-    pre[j] = i < count ? __ldg(rec + i) : make_uint2(0u, 0u);  // meta 0: member of no window, touches nothing
+    pre[j] = i < h.count ? __ldg(h.rec + i) : make_uint2(0u, 0u);  // meta 0: member of no window, touches nothing
   }
-  {
-    uint4* a4 = reinterpret_cast<uint4*>(acc);
-    constexpr int N4 = (STRIDE * TP + 3) / 4;
+
+  while (true) {
+    int my_ticket = 0;
+    if (tid == 0) my_ticket = (int)atomicAdd(ticket, 1u);  // consumed after the atomics phase
+    {
+      uint4* a4 = reinterpret_cast<uint4*>(acc);
+      constexpr int N4 = (STRIDE * TP + 3) / 4;
 #pragma unroll 4
-    for (int i = tid; i < N4; i += TILE_THREADS) a4[i] = make_uint4(0, 0, 0, 0);
-  }
-  const int32_t tmin = w.tmin_rel;
-  const uint32_t delta_u = (w.tmax_rel >= w.tmin_rel) ? (uint32_t)(w.tmax_rel - w.tmin_rel) : 0u;
-  const double delta = (double)delta_u;
-  const float inv_delta = 1.f / (float)delta_u;
-  const uint32_t not_m1 = ~w.has_m1;
-  __syncthreads();
-
-#pragma unroll
-  for (int j = 0; j < PRE; ++j)
-    if (pre[j].y) md_accumulate_static<PS>(acc, pre[j], tmin, not_m1);
-  for (uint32_t i = tid + PRE * TILE_THREADS; i < count; i += TILE_THREADS) md_accumulate_static<PS>(acc, __ldg(rec + i), tmin, not_m1);
-  __syncthreads();
-
-  float o[PPT][C];
-#pragma unroll
-  for (int k = 0; k < PPT; ++k)
-    md_finalise_static<PS>(acc + (tid + k * TILE_THREADS) * STRIDE, inv_delta, delta, delta_u, w.has_m1, o[k], std::make_integer_sequence<int, C>{});
-  __syncthreads();
-  float4* stage = reinterpret_cast<float4*>(acc);  // [TP][C] floats, contiguous = the global layout of the slice
-#pragma unroll
-  for (int k = 0; k < PPT; ++k)
-#pragma unroll
-    for (int q = 0; q < C / 4; ++q)
-      stage[(tid + k * TILE_THREADS) * (C / 4) + q] = make_float4(o[k][4 * q], o[k][4 * q + 1], o[k][4 * q + 2], o[k][4 * q + 3]);
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  __syncthreads();
-  constexpr int SLICE_PX = TP / 4;  // four issuing threads, one per 1/4 of the tile
-  if ((tid & 31) == 0 && tid < 128) {
-    const int p0 = (tid >> 5) * SLICE_PX;
-    const int np = min(SLICE_PX, npix - p0);
-    if (np > 0) {
-      float* dst = out + ((size_t)b * g.HW + pix0 + p0) * C;
-      const uint32_t src = (uint32_t)__cvta_generic_to_shared(acc + p0 * C);
-      const uint32_t bytes = (uint32_t)np * C * 4u;
-      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must outlive the read
+      for (int i = tid; i < N4; i += TILE_THREADS) a4[i] = make_uint4(0, 0, 0, 0);
     }
+    const bool more = nxt < n_tiles;
+    TileHdr hn = h;
+    if (more) hn = md_load_hdr(nxt, g, TP, records, base, cursor, wp);  // in flight during the atomics below
+    __syncthreads();
+
+    const uint32_t not_m1 = ~h.has_m1;
+#pragma unroll
+    for (int j = 0; j < PRE; ++j)
+      if (pre[j].y) md_accumulate_static<PS>(acc, pre[j], h.tmin, not_m1);
+    for (uint32_t i = tid + PRE * TILE_THREADS; i < h.count; i += TILE_THREADS) md_accumulate_static<PS>(acc, __ldg(h.rec + i), h.tmin, not_m1);
+
+#pragma unroll
+    for (int j = 0; j < PRE; ++j) {  // next bucket's records: in flight during finalise + store
+      const uint32_t i = tid + j * TILE_THREADS;
+      pre[j] = (more && i < hn.count) ? __ldg(hn.rec + i) : make_uint2(0u, 0u);
+    }
+    if (tid == 0) s_next = my_ticket + 2 * (int)gridDim.x;
+    __syncthreads();
+    const int nn = s_next;
+
+    const double delta = (double)h.delta_u;
+    const float inv_delta = 1.f / (float)h.delta_u;
+    float o[PPT][C];
+#pragma unroll
+    for (int k = 0; k < PPT; ++k)
+      md_finalise_static<PS>(acc + (tid + k * TILE_THREADS) * STRIDE, inv_delta, delta, h.delta_u, h.has_m1, o[k], std::make_integer_sequence<int, C>{});
+    __syncthreads();
+    float4* stage = reinterpret_cast<float4*>(acc);  // [TP][C] floats, contiguous = the global layout of the slice
+#pragma unroll
+    for (int k = 0; k < PPT; ++k)
+#pragma unroll
+      for (int q = 0; q < C / 4; ++q)
+        stage[(tid + k * TILE_THREADS) * (C / 4) + q] = make_float4(o[k][4 * q], o[k][4 * q + 1], o[k][4 * q + 2], o[k][4 * q + 3]);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    constexpr int SLICE_PX = TP / 4;  // four issuing threads, one per quarter of the tile
+    if ((tid & 31) == 0 && tid < 128) {
+      const int npix = min(TP, g.HW - h.pix0);
+      const int p0 = (tid >> 5) * SLICE_PX;
+      const int np = min(SLICE_PX, npix - p0);
+      if (np > 0) {
+        float* dst = out + ((size_t)h.b * g.HW + h.pix0 + p0) * C;
+        const uint32_t src = (uint32_t)__cvta_generic_to_shared(acc + p0 * C);
+        const uint32_t bytes = (uint32_t)np * C * 4u;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the source may be overwritten once it has been read
+      }
+    }
+    if (!more) break;
+    __syncthreads();  // shared memory is free again
+    h = hn;
+    cur = nxt;
+    nxt = nn;
   }
 }
 
 template <typename PS>
 static int launch_static(const Geom& g, const Workspace& ws, size_t smem, float* out, cudaStream_t stream) {
   constexpr int TP = 1024;  // what choose_tile picks for the ERGO-12 footprint on every sensor below 4 Mpx
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    EVREP_CUDA_OK(cudaGetDevice(&dev));
+    EVREP_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
   EVREP_CUDA_OK(cudaFuncSetAttribute(k_md_tile_static<PS, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int n_tiles = g.B * g.T;
+  const int grid = n_tiles < 2 * n_sm ? n_tiles : 2 * n_sm;
   prof_begin(EVREP_K_TILE, stream);
-  k_md_tile_static<PS, TP><<<g.B * g.T, TILE_THREADS, smem, stream>>>(ws.records, ws.base, ws.cursor, ws.wp, g, out);
+  k_md_tile_static<PS, TP><<<grid, TILE_THREADS, smem, stream>>>(ws.records, ws.base, ws.cursor, ws.wp, g, ws.ticket, out);
   prof_end(EVREP_K_TILE, stream);
   EVREP_CUDA_OK(cudaGetLastError());
   return EVREP_OK;
