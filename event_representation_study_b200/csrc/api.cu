@@ -1,6 +1,7 @@
 // The C ABI of libevrep (include/evrep.h): argument validation, tile geometry, workspace carving and
 // kernel sequencing.  No exceptions leave this file; every entry point returns an EVREP_* code.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -64,8 +65,13 @@ static int choose_tile(int H, int W, size_t bytes_per_px, Geom* g) {
   g->H = H;
   g->W = W;
   g->HW = H * W;
+  size_t target = TILE_SMEM_TARGET;
+  if (const char* e = getenv("EVREP_TILE_SMEM_KB")) {  // tuning knob for experiments
+    const long kb = atol(e);
+    if (kb >= 8 && kb <= 220) target = (size_t)kb * 1024;
+  }
   int shift = 12;
-  while (shift > 8 && ((size_t)1 << shift) * bytes_per_px > TILE_SMEM_TARGET) --shift;
+  while (shift > 8 && ((size_t)1 << shift) * bytes_per_px > target) --shift;
   // a very large sensor needs bigger tiles than the target allows: trade occupancy for reach
   while (((g->HW + (1 << shift) - 1) >> shift) > MAX_TILES && shift < 16) ++shift;
   if (((size_t)1 << shift) * bytes_per_px > TILE_SMEM_MAX || ((g->HW + (1 << shift) - 1) >> shift) > MAX_TILES) {

@@ -245,22 +245,22 @@ __device__ __forceinline__ void md_acc_group(uint32_t* a, uint32_t M, uint32_t t
   constexpr MdGroup G = PS::value.grp[GI];
   constexpr int LW = PS::value.lw, NL1 = PS::value.nl1, NL2 = PS::value.nl2;
   constexpr uint32_t MASK = (1u << LW) - 1u;
-  const bool m = (M >> G.bit) & 1u;  // one predicate per atomic instead of nested branches
-  if constexpr (G.flags & G_CNT) { if (m) atomicAdd(a + G.w_cnt, 1u); }
-  if constexpr (G.flags & G_PRES) pres |= m ? (1u << G.pres_bit) : 0u;
-  if constexpr (G.flags & G_MAX) { if (m) atomicMax(a + G.w_max, tt + 1u); }
+  if (!((M >> G.bit) & 1u)) return;
+  if constexpr (G.flags & G_CNT) atomicAdd(a + G.w_cnt, 1u);
+  if constexpr (G.flags & G_PRES) pres |= 1u << G.pres_bit;
+  if constexpr (G.flags & G_MAX) atomicMax(a + G.w_max, tt + 1u);
   if constexpr (G.flags & G_ST) {
 #pragma unroll
     for (int l = 0; l < NL1; ++l) {
       const uint32_t limb = (tt >> (l * LW)) & MASK;
-      if (m && limb) atomicAdd(a + G.w_st + l, limb);
+      if (limb) atomicAdd(a + G.w_st + l, limb);
     }
   }
   if constexpr (G.flags & G_ST2) {
 #pragma unroll
     for (int l = 0; l < NL2; ++l) {
       const uint32_t limb = (uint32_t)(tt2 >> (l * LW)) & MASK;
-      if (m && limb) atomicAdd(a + G.w_st2 + l, limb);
+      if (limb) atomicAdd(a + G.w_st2 + l, limb);
     }
   }
 }
@@ -330,7 +330,7 @@ __device__ __forceinline__ TileHdr md_load_hdr(int id, const Geom& g, int TP, co
 }
 
 template <typename PS, int TP>
-__global__ void __launch_bounds__(TILE_THREADS, 2) k_md_tile_static(const uint2* __restrict__ records, const uint32_t* __restrict__ base,
+__global__ void __launch_bounds__(TILE_THREADS, TP == 1024 ? 2 : 3) k_md_tile_static(const uint2* __restrict__ records, const uint32_t* __restrict__ base,
                                                                     const uint32_t* __restrict__ cursor, const WinParams* __restrict__ wp,
                                                                     const Geom g, uint32_t* __restrict__ ticket, float* __restrict__ out) {
   extern __shared__ __align__(128) uint32_t acc[];
@@ -354,14 +354,22 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_md_tile_static(const uint2*
     pre[j] = i < h.count ? __ldg(h.rec + i) : make_uint2(0u, 0u);  // meta 0: member of no window, touches nothing
   }
 
+  bool first = true;
   while (true) {
     int my_ticket = 0;
     if (tid == 0) my_ticket = (int)atomicAdd(ticket, 1u);  // consumed after the atomics phase
     {
+      // the first TP*C words may still be read by the TMA store of the previous bucket: clear the rest first
       uint4* a4 = reinterpret_cast<uint4*>(acc);
-      constexpr int N4 = (STRIDE * TP + 3) / 4;
+      constexpr int N4 = (STRIDE * TP + 3) / 4, S4 = TP * C / 4;
 #pragma unroll 4
-      for (int i = tid; i < N4; i += TILE_THREADS) a4[i] = make_uint4(0, 0, 0, 0);
+      for (int i = S4 + tid; i < N4; i += TILE_THREADS) a4[i] = make_uint4(0, 0, 0, 0);
+      if (!first) {
+        if ((tid & 31) == 0 && tid < 128) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncthreads();
+      }
+#pragma unroll 4
+      for (int i = tid; i < S4; i += TILE_THREADS) a4[i] = make_uint4(0, 0, 0, 0);
     }
     const bool more = nxt < n_tiles;
     TileHdr hn = h;
@@ -409,20 +417,21 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_md_tile_static(const uint2*
         const uint32_t bytes = (uint32_t)np * C * 4u;
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the source may be overwritten once it has been read
       }
     }
-    if (!more) break;
-    __syncthreads();  // shared memory is free again
+    if (!more) {
+      if ((tid & 31) == 0 && tid < 128) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must outlive the read
+      break;
+    }
+    first = false;
     h = hn;
     cur = nxt;
     nxt = nn;
   }
 }
 
-template <typename PS>
-static int launch_static(const Geom& g, const Workspace& ws, size_t smem, float* out, cudaStream_t stream) {
-  constexpr int TP = 1024;  // what choose_tile picks for the ERGO-12 footprint on every sensor below 4 Mpx
+template <typename PS, int TP>
+static int launch_static_tp(const Geom& g, const Workspace& ws, size_t smem, float* out, cudaStream_t stream) {
   static int n_sm = 0;
   if (!n_sm) {
     int dev = 0;
@@ -430,13 +439,21 @@ static int launch_static(const Geom& g, const Workspace& ws, size_t smem, float*
     EVREP_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   }
   EVREP_CUDA_OK(cudaFuncSetAttribute(k_md_tile_static<PS, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;
+  EVREP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_md_tile_static<PS, TP>, TILE_THREADS, smem));
+  if (per_sm < 1) per_sm = 1;
   const int n_tiles = g.B * g.T;
-  const int grid = n_tiles < 2 * n_sm ? n_tiles : 2 * n_sm;
+  const int grid = n_tiles < per_sm * n_sm ? n_tiles : per_sm * n_sm;
   prof_begin(EVREP_K_TILE, stream);
   k_md_tile_static<PS, TP><<<grid, TILE_THREADS, smem, stream>>>(ws.records, ws.base, ws.cursor, ws.wp, g, ws.ticket, out);
   prof_end(EVREP_K_TILE, stream);
   EVREP_CUDA_OK(cudaGetLastError());
   return EVREP_OK;
+}
+template <typename PS>
+static int launch_static(const Geom& g, const Workspace& ws, size_t smem, float* out, cudaStream_t stream) {
+  if (g.tile_px == 1024) return launch_static_tp<PS, 1024>(g, ws, smem, out, stream);
+  return launch_static_tp<PS, 512>(g, ws, smem, out, stream);
 }
 
 // SBT only: which time windows hold a p == -1 event (needed before the tile pass can decide what
@@ -476,7 +493,7 @@ int launch_md_tile(const Geom& g, const Workspace& ws, const MdPlan& plan, const
     EVREP_CUDA_OK(cudaGetLastError());
   }
   const size_t smem = md_tile_smem_bytes(plan, g.tile_px);
-  switch (g.tile_px == 1024 ? plan.static_id : 0) {
+  switch ((g.tile_px == 1024 || g.tile_px == 512) ? plan.static_id : 0) {
 #define EVREP_STATIC_CASE(VER, LW) \
   case VER * 100 + LW:             \
     return launch_static<ErgoPlan<VER, LW>>(g, ws, smem, out, stream);
