@@ -1,0 +1,86 @@
+"""Mirror of representations/representation_search/mixed_density_event_stack.py (reference :8-151)."""
+import numpy as np
+
+from ... import batched as eb
+from ..._single import one_window
+from .operations import Operations
+
+
+class MixedDensityEventStack:
+    def __init__(self, stack_size, num_of_events, height, width, indexes_functions_aggregations, stacking_type):
+        self.stack_size = stack_size
+        self.num_of_events = num_of_events
+        self.height = height
+        self.width = width
+        self.indexes_functions_aggregations = indexes_functions_aggregations
+        self.stacking_type = stacking_type
+
+    def _spec(self):
+        w, f, a = self.indexes_functions_aggregations
+        n = self.stack_size
+        # make_stack indexes the three lists with range(stack_size): shorter lists raise -> zero channel (reference :116-127)
+        pad = lambda lst, fill: [lst[i] if i < len(lst) else fill for i in range(n)]
+        return pad(list(w), 127), pad(list(f), "<missing>"), pad(list(a), "<missing>")
+
+    def _run(self, x, y, p, t):
+        if len(t) == 0:
+            raise ValueError("zero-size array to reduction operation minimum which has no identity")  # t.min() (reference :33)
+        w, f, a = self._spec()
+        try:
+            ev = one_window(x, y, t, p, self.height, self.width)
+        except IndexError:
+            # an out-of-range pixel makes every torch_scatter call raise inside make_stack: all channels zero (reference :120-127)
+            return np.zeros((self.height, self.width, self.stack_size), np.float64)
+        return eb.mixed_density(ev, self.height, self.width, w, f, a, self.stacking_type)[0].double().cpu().numpy()
+
+    def stack(self, event_sequence):
+        x = event_sequence["x"].astype(np.int32)
+        y = event_sequence["y"].astype(np.int32)
+        p = event_sequence["p"].astype(np.int32)
+        t = event_sequence["t"].astype(np.int64)
+        assert len(x) == len(y) == len(p) == len(t)
+        return self._run(x, y, p, t)
+
+    def create_windows(self, x, y, p, t):
+        """The 7 (SBN) / 8 (SBT) event subsets, as host array views like the reference (reference :48-109).
+        Pure slicing - kept for API compatibility; `stack` never materialises them."""
+        windows = [(x, y, p, t)]
+        n3 = x.shape[0] // 3
+        if self.stacking_type == "SBN":
+            for i in range(3):
+                s = slice(i * n3, (i + 1) * n3)
+                windows.append((x[s], y[s], p[s], t[s]))
+            c = len(t)
+            for _ in range(3):
+                c = c // 2
+                x, y, p, t = x[c:], y[c:], p[c:], t[c:]
+                windows.append((x, y, p, t))
+        elif self.stacking_type == "SBT":
+            f = 1 / 3
+            for i in range(3):
+                m = np.logical_and(t <= (i + 1) * f, t >= i * f)
+                windows.append((x[m], y[m], p[m], t[m]))
+            factor = 1
+            for _ in range(4):
+                factor = factor / 2
+                m = t <= factor
+                x, y, p, t = x[m], y[m], p[m], t[m]
+                windows.append((x, y, p, t))
+        return windows
+
+    def make_stack(self, x, y, p, t):
+        """-> list of {name: (H, W) float64} like the reference (reference :111-130)."""
+        rep = self._run(x, y, p, t)
+        w, f, a = self._spec()
+        out = []
+        for i in range(self.stack_size):
+            valid = isinstance(f[i], str) and isinstance(a[i], str) and f[i] in eb.FUNCS and a[i] in eb.AGGS
+            name = "_".join([f[i].capitalize(), a[i].capitalize()]) if valid else ""
+            out.append({name: rep[:, :, i]})
+        return out
+
+    def stack_data(self, x, y, p, t_s, func, aggregation):
+        assert len(x) == len(y) == len(p) == len(t_s)
+        events = np.concatenate([x[..., np.newaxis], y[..., np.newaxis], t_s[..., np.newaxis], p[..., np.newaxis]], axis=1)
+        surface = Operations(func, aggregation, self.height, self.width)(events)
+        return {"_".join([func.capitalize(), aggregation.capitalize()]): surface}

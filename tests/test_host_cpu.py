@@ -1,0 +1,163 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/evrep.h declares, host-side logic
+(accumulator plans, workspace sizing, argument validation, window sharding) and the world_size-2 exchange over gloo.
+No kernel is launched here."""
+import ctypes
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def L():
+    from event_representation_study_b200 import _lib
+    return _lib
+
+
+def test_library_exports_every_declared_symbol(L):
+    hdr = open(os.path.join(ROOT, "include", "evrep.h")).read()
+    declared = set(re.findall(r"\b(evrep_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 16
+    raw = ctypes.CDLL(L.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(raw, name), f"libevrep.so does not export {name}"
+    assert declared == set(L.SIGNATURES), declared ^ set(L.SIGNATURES)
+    assert L.lib.evrep_version() == 100
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "event_representation_study_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(d, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports the oracle"
+
+
+def plan_info(L, H, W, win, func, agg, stacking, nmax):
+    w, f, a = (np.array(v, np.int8) for v in (win, func, agg))
+    info = np.zeros(5, np.int32)
+    rc = L.lib.evrep_mixed_density_plan_info(H, W, w.ctypes.data, f.ctypes.data, a.ctypes.data, len(w), stacking, nmax, info.ctypes.data)
+    return rc, info
+
+
+def test_ergo12_plan(L):
+    from event_representation_study_b200.batched import ERGO12_V2
+    win, func, agg = ERGO12_V2
+    f = [L.FUNCS[x] for x in func]
+    a = [L.AGGS[x] for x in agg]
+    rc, info = plan_info(L, 720, 1280, win, f, a, 0, 1_000_000)
+    assert rc == 0
+    bytes_px, tile_px, tiles, words, smem = info
+    assert words == 24 and bytes_px == 100 and tile_px == 1024 and tiles == 900 and smem == 102400
+    rc, info = plan_info(L, 240, 304, win, f, a, 0, 50_000)  # fewer events -> wider limbs -> fewer words
+    assert rc == 0 and info[3] < 24 and info[2] == -(-240 * 304 // info[1])
+
+
+def test_plan_rejects_bad_arguments(L):
+    rc, _ = plan_info(L, 720, 1280, [0] * 33, [0] * 33, [0] * 33, 0, 1000)
+    assert rc == L.EINVAL and b"outside" in L.lib.evrep_last_error()
+    rc, _ = plan_info(L, 720, 1280, [0], [0], [0], 7, 1000)
+    assert rc == L.EINVAL
+    rc, _ = plan_info(L, 0, 1280, [0], [0], [0], 0, 1000)
+    assert rc == L.EINVAL
+    rc, info = plan_info(L, 30, 40, [9, -1, 0], [2, 2, 99], [0, 0, 0], 0, 1000)  # bad window / function -> zero channels, not errors
+    assert rc == 0
+
+
+def test_workspace_bytes(L):
+    f = L.lib.evrep_workspace_bytes
+    small = f(L.OP_MIXED_DENSITY, 1, 1000, 240, 304, 12)
+    big = f(L.OP_MIXED_DENSITY, 32, 32_000_000, 720, 1280, 12)
+    assert 0 < small < big and big >= 32_000_000 * 8
+    assert f(L.OP_VOXEL, 32, 32_000_000, 720, 1280, 12) < 1 << 20  # direct-scatter ops need no record buffer
+    assert f(0, 1, 1, 1, 1, 1) == 0 and f(L.OP_TORE, -1, 1, 1, 1, 1) == 0
+
+
+def test_validation_happens_before_any_cuda_call(L):
+    offs = np.array([0, 10], np.int64)
+    rc = L.lib.evrep_ergo12_batched(None, None, None, 4, None, offs.ctypes.data, 1, 30, 40, 2, None, None, 0, None)
+    assert rc == L.EINVAL and b"null" in L.lib.evrep_last_error()
+    rc = L.lib.evrep_ergo12_batched(None, None, None, 3, None, offs.ctypes.data, 1, 30, 40, 2, None, None, 0, None)
+    assert rc == L.EINVAL and b"t_bytes" in L.lib.evrep_last_error()
+    rc = L.lib.evrep_event_stack_batched(None, None, None, 4, None, offs.ctypes.data, 0, 30, 40, 12, None, None, 0, None)
+    assert rc == L.OK  # B == 0: nothing to do
+    assert L.lib.evrep_gwd_workspace_bytes(None, None, 3) == 0
+
+
+def test_batched_api_refuses_cpu_tensors():
+    import torch
+    import event_representation_study_b200.batched as eb
+    z = torch.zeros(4, dtype=torch.int16)
+    with pytest.raises(ValueError, match="CUDA"):
+        eb.EventBatch(z, z, torch.zeros(4, dtype=torch.int32), torch.zeros(4, dtype=torch.int8), np.array([0, 4]))
+
+
+def test_shard_range_and_offsets():
+    from event_representation_study_b200.sharding import shard_offsets, shard_range
+    for n, w in [(256, 8), (10, 4), (3, 8), (0, 2)]:
+        blocks = [shard_range(n, w, r) for r in range(w)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+        sizes = [hi - lo for lo, hi in blocks]
+        assert max(sizes) - min(sizes) <= 1
+    assert shard_range(256, 8, 3) == (96, 128)  # BASELINE config 4: 32 windows per GPU
+    offs = np.array([0, 5, 5, 12, 20, 21])
+    (lo, hi), (e0, e1), local = shard_offsets(offs, 2, 1)
+    assert (lo, hi) == (3, 5) and (e0, e1) == (12, 21) and local.tolist() == [0, 8, 9]
+    with pytest.raises(ValueError):
+        shard_range(4, 2, 2)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gather_worker(rank, world, port, n_samples, q):
+    import torch
+    import torch.distributed as dist
+    from event_representation_study_b200.sharding import gather_cost_matrix, shard_range
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    R = 12
+    full = torch.arange(R * n_samples, dtype=torch.float64).reshape(R, n_samples)
+    lo, hi = shard_range(n_samples, world, rank)
+    out = gather_cost_matrix(full[:, lo:hi].contiguous())
+    q.put((rank, bool(torch.equal(out, full)), tuple(out.shape)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_samples", [10, 7])
+def test_gwd_matrix_all_gather_world_size_2(n_samples):
+    """The one collective of the design: R x S/G blocks gathered into the R x S matrix, ragged included."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, n_samples, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res) and all(shape == (12, n_samples) for _, _, shape in res)
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """bench.py --impl reference must work without a GPU (tiny sample here)."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--events", "20000"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0
