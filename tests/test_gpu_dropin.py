@@ -52,7 +52,10 @@ def test_get_item_transform_all_branches():
         if name == "ToVoxelGrid":  # tonic rewrites 0 -> -1 in place
             assert set(np.unique(data["p"])) <= {-1, 1}
         out4 = gen4_transforms.get_item_transform(ev_of(g), name if tr is None else str(tr), tr, H, W, len(data))
-        assert np.array_equal(out4, out, equal_nan=True)
+        if name == "ToVoxelGrid":  # float L2 reductions: order dependent in the last ulp (voxel grids)
+            assert_close(out4, out, rtol=1e-6, atol=1e-4)
+        else:
+            assert np.array_equal(out4, out, equal_nan=True)
 
 
 ES = golden("eventstack_*")
