@@ -1,0 +1,143 @@
+#!/usr/bin/env python
+"""Secondary measurements (not the driver's contract line): BASELINE.json configs 1, 2, 3 and 5 on one GPU.
+
+    python bench_extra.py [--steps K] [--only config2,config3,gwd,config1]
+
+One JSON line per workload: device-resident throughput (CUDA events, >= 3 warm-ups, inputs + outputs larger than L2 where
+the config allows), the algorithmic-byte roofline fraction of SURVEY.md 8(d) against MEASURED_PEAKS.json, and a bounded CPU
+baseline with the numpy oracle (1 core).  Results are summarised in profiles/README.md.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def timed(fn, steps, warm=3):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps * 1e-3
+
+
+def cpu_time(fn, budget=8.0, max_n=8):
+    n, spent = 0, 0.0
+    while n < max_n and spent < budget:
+        t0 = time.perf_counter()
+        fn(n)
+        spent += time.perf_counter() - t0
+        n += 1
+    return spent / n, n
+
+
+def rep_line(name, ev_per_step, sec, alg_bytes, cpu_ev_per_s, cpu_note, extra=None):
+    line = {"workload": name, "value": ev_per_step / sec / 1e9, "unit": "Gevents/s", "ms_per_step": sec * 1e3,
+            "roofline": {"bound": "hbm", "achieved": alg_bytes / sec / 1e9, "peak": peak(), "unit": "GB/s", "frac": alg_bytes / sec / 1e9 / peak(),
+                         "algorithmic_bytes_per_step": alg_bytes, "scope": "whole step (all kernels of the call)"},
+            "cpu_baseline": {"value": cpu_ev_per_s / 1e9, "unit": "Gevents/s", "cores": 1, "kind": "port", "sample": cpu_note}}
+    if extra:
+        line.update(extra)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--only", default="config1,config2,config3,gwd")
+    a = ap.parse_args()
+    import torch
+    import event_representation_study_b200.batched as eb
+    from event_representation_study_b200.synth import device_batch, poisson_window
+    from oracle import gwd as ogwd
+    from oracle import representations as orep
+    only = set(a.only.split(","))
+    dev = torch.device("cuda", 0)
+
+    def batch(B, N, H, W, seed):
+        d = device_batch(B, N, H, W, dev, seed=seed)
+        return eb.EventBatch(d["x"], d["y"], d["t"], d["p"], d["offsets"].cpu().numpy())
+
+    if "config1" in only:  # VoxelGrid 5-bin, Gen1, 50k events, batch 1 (the reference's CPU-runnable case)
+        H, W, N = 240, 304, 50_000
+        ev = batch(1, N, H, W, 1001)
+        for fl, nb in (("evlicious", 5), ("tonic", 12)):
+            out = torch.empty((1, nb, H, W), device=dev)
+            sec = timed(lambda: eb.voxel_grid(ev, H, W, nb, fl, normalize=True, out=out), a.steps)
+            w = poisson_window(1, N, H, W)
+            f = (lambda i: orep.voxel_evlicious(w["x"], w["y"], w["t"], w["p"], H, W, nb, True)) if fl == "evlicious" else \
+                (lambda i: orep.voxel_tonic(w["x"], w["y"], w["t"], w["p"].astype(np.int32), H, W, nb))
+            c, n = cpu_time(f, 3.0, 50)
+            rep_line(f"config1 VoxelGrid[{fl}] {nb}-bin Gen1 304x240 50k ev batch 1 (latency bound: one small window)", N, sec,
+                     N * 9 + H * W * nb * 4, N / c, f"{n} calls of oracle voxel_{fl}")
+
+    if "config2" in only:  # ERGO-12, Gen1, 200k ev/window, batch 32
+        H, W, N, B = 240, 304, 200_000, 32
+        ev = batch(B, N, H, W, 2000)
+        out = torch.empty((B, H, W, 12), device=dev)
+        sec = timed(lambda: eb.ergo12(ev, H, W, out=out), a.steps)
+        c, n = cpu_time(lambda i: orep.ergo12(*[poisson_window(2000 + i, N, H, W)[k] for k in "xytp"], H, W), 6.0, 16)
+        rep_line("config2 ERGO-12 Gen1 304x240 200k ev/window batch 32 (169.7 MB/step: partly L2 resident)", B * N, sec,
+                 B * (N * 9 + H * W * 12 * 4), N / c, f"{n} windows, oracle ergo12 incl. window generation")
+
+    if "config3" in only:  # TimeSurface + EventStack + TORE, 1 Mpx, 500k ev/window, batch 32
+        H, W, N, B = 720, 1280, 500_000, 32
+        ev = batch(B, N, H, W, 3000)
+        o1 = torch.empty((B, 6, 2, H, W), device=dev)
+        o2 = torch.empty((B, H, W, 12), device=dev)
+        o3 = torch.empty((B, H, W, 12), device=dev)
+        per = B * (N * 9 + H * W * 12 * 4)
+        w = poisson_window(3000, N, H, W)
+        p01 = (w["p"].astype(np.int32) + 1) // 2
+        idx = orep.time_surface_indices(w["t"].astype(np.int32), 6)
+        ws = poisson_window(3001, 50_000, H, W)
+        for name, fn, cpu_fn, cpu_n, note in [
+            ("TimeSurface", lambda: eb.time_surface(ev, H, W, 6, 50000.0, out=o1), lambda i: orep.time_surface(w["x"], w["y"], w["t"], p01, idx, H, W, 50000.0), N, "oracle time_surface, 500k events"),
+            ("EventStack", lambda: eb.event_stack(ev, H, W, 12, out=o2), lambda i: orep.event_stack(w["x"], w["y"], w["t"], p01, H, W, 12), N, "oracle event_stack, 500k events"),
+            ("TORE", lambda: eb.tore(ev, H, W, 6, out=o3), lambda i: orep.tore(w["x"].astype(np.int32) + 1, w["y"].astype(np.int32) + 1, w["t"].astype(np.int32), w["p"].astype(np.int32), int(w["t"][-1]), 6, (H, W)), N, "oracle tore (vectorised restatement, far faster than the reference's per-event Python loop), 500k events"),
+        ]:
+            sec = timed(fn, a.steps)
+            c, n = cpu_time(cpu_fn, 6.0, 6)
+            rep_line(f"config3 {name} 1Mpx 1280x720 500k ev/window batch 32", B * N, sec, per, cpu_n / c, f"{n} windows, {note}")
+        sec = timed(lambda: (eb.time_surface(ev, H, W, 6, 50000.0, out=o1), eb.event_stack(ev, H, W, 12, out=o2), eb.tore(ev, H, W, 6, out=o3)), a.steps)
+        rep_line("config3 all three (three calls; events counted once in the algorithmic bytes)", B * N, sec, B * (N * 9 + 3 * H * W * 12 * 4), float("nan"), "n/a")
+
+    if "gwd" in only:  # config 5, reading (ii): 12 representations x S samples, each pair subsampled to n = m = 1000 points
+        R, S, n = 12, 256, 1000
+        rng = np.random.default_rng(5)
+        Xs = [torch.as_tensor(rng.random((n, 4)), device=dev) for _ in range(S)]
+        Xt = [torch.as_tensor(np.concatenate([rng.random((n, 12)) * 255, rng.random((n, 2))], 1), device=dev) for _ in range(R * S)]
+        Xs_rep = [Xs[i % S] for i in range(R * S)]
+        sec = timed(lambda: eb.gwd_kernel_l1(Xs_rep, Xt, 0.7), max(3, a.steps // 4), warm=2)
+        a_np, b_np = Xs[0].cpu().numpy(), Xt[0].cpu().numpy()
+        c, k = cpu_time(lambda i: ogwd.gwd_a_cost(a_np, b_np, 0.7), 6.0, 40)
+        flop = R * S * (n * n) * (3 * (4 + 14) + 12)  # both kernels over the upper triangle + the mirrored half folded in
+        print(json.dumps({"workload": f"config5 GWD-A {R} representations x {S} samples, n = m = {n} points per pair (includes packing the pair list)",
+                          "value": R * S / sec, "unit": "pairs/s", "ms_per_step": sec * 1e3,
+                          "roofline": {"bound": "fp32 alu/sfu", "achieved": flop / sec / 1e12, "unit": "TFLOP/s (approx. flop model, 2 exp per cell counted as 12 flop)"},
+                          "cpu_baseline": {"value": 1.0 / c, "unit": "pairs/s", "cores": "numpy/BLAS threads", "kind": "port",
+                                           "sample": f"{k} pairs of the same size, oracle gwd_a_cost (closed form of POT's estimate; POT not installable offline)"},
+                          "speedup_vs_cpu_port": (R * S / sec) * c}), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -83,6 +83,15 @@ __device__ __forceinline__ void load8_t<int64_t>(const int64_t* __restrict__ p, 
   }
 }
 
+// Shared-memory atomics on a 32-bit shared-window address (the generic-pointer form makes the compiler rebuild the
+// window base around every atomic inside divergent code).
+__device__ __forceinline__ void smem_inc(uint32_t addr) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory"); }
+__device__ __forceinline__ uint32_t smem_fetch_inc(uint32_t addr) {
+  uint32_t old;
+  asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(addr) : "memory");
+  return old;
+}
+
 // In-place exclusive scan of a[0..n) in shared memory by a BIN_THREADS-thread CTA (n <= MAX_TILES).
 // `warp_tot` is BIN_THREADS/32 words of scratch.  Returns the total.  Ends with a __syncthreads().
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t* a, int n, uint32_t* warp_tot) {
@@ -219,16 +228,21 @@ __global__ void __launch_bounds__(BIN_THREADS) k_hist(const uint16_t* __restrict
   const int64_t start = wp[b].start, end = start + wp[b].n;
   for (int i = threadIdx.x; i < g.T; i += BIN_THREADS) sh_hist[i] = 0;
   __syncthreads();
-  const int64_t g0 = (start & ~(int64_t)(EPT - 1)) + (int64_t)chunk * CHUNK + (int64_t)threadIdx.x * EPT;
-  if (g0 < end) {
+  const int n = (int)wp[b].n;
+  const int64_t c0 = (start & ~(int64_t)(EPT - 1)) + (int64_t)chunk * CHUNK;  // first event of this CTA's chunk
+  const int64_t g0 = c0 + (int64_t)threadIdx.x * EPT;
+  const int idx0 = (int)(g0 - start);
+  const uint32_t hbase = (uint32_t)__cvta_generic_to_shared(sh_hist);
+  const uint32_t Wd = (uint32_t)g.W, Hd = (uint32_t)g.H;
+  if (idx0 < n) {
     uint32_t xs[EPT], ys[EPT];
     load8_u16(x, g0, g.total, vec, xs);
     load8_u16(y, g0, g.total, vec, ys);
+    const bool interior = c0 >= start && c0 + CHUNK <= end;  // CTA-uniform: no per-event window test needed
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
-      const int64_t a = g0 + e;
-      if (a >= start && a < end && xs[e] < (uint32_t)g.W && ys[e] < (uint32_t)g.H)
-        atomicAdd(&sh_hist[(ys[e] * (uint32_t)g.W + xs[e]) >> g.tile_shift], 1u);
+      const bool ok = (interior || (uint32_t)(idx0 + e) < (uint32_t)n) && xs[e] < Wd && ys[e] < Hd;
+      if (ok) smem_inc(hbase + (((ys[e] * Wd + xs[e]) >> g.tile_shift) << 2));
     }
   }
   __syncthreads();
@@ -291,8 +305,12 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin(const uint16_t* __restrict_
   // index boundaries of the SBN windows (mixed_density_event_stack.py:55-74)
   const int n3 = n / 3, s4 = n / 2, s5 = s4 + n / 4, s6 = s5 + n / 8;
 
-  const int64_t g0 = (start & ~(int64_t)(EPT - 1)) + (int64_t)chunk * CHUNK + (int64_t)tid * EPT;
+  const int64_t c0 = (start & ~(int64_t)(EPT - 1)) + (int64_t)chunk * CHUNK;
+  const int64_t g0 = c0 + (int64_t)tid * EPT;
   const int idx0 = (int)(g0 - start);  // index of this thread's first event inside the window (may be < 0 at the head)
+  const bool interior = c0 >= start && c0 + CHUNK <= start + n;  // CTA-uniform: every event of the chunk is inside the window
+  const uint32_t cnt_base = (uint32_t)__cvta_generic_to_shared(cnt);
+  const uint32_t Wd = (uint32_t)g.W, Hd = (uint32_t)g.H;
   uint32_t key[EPT], meta[EPT], tile_rank[EPT];  // tile_rank = tile << 16 | rank inside the CTA's bucket (< CHUNK = 2^12)
   int my_tmin = INT_MAX, my_tmax = INT_MIN;
   uint32_t my_flags = 0, my_m1 = 0;
@@ -311,11 +329,11 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin(const uint16_t* __restrict_
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
       const int idx = idx0 + e;
-      if (idx < 0 || idx >= n) continue;
+      if (!interior && (uint32_t)idx >= (uint32_t)n) continue;
       if (ts[e] < t_prev) my_flags |= EVREP_WF_UNSORTED;
       t_prev = ts[e];
       const int64_t d = ts[e] - t_base;
-      const bool bad_xy = xs[e] >= (uint32_t)g.W || ys[e] >= (uint32_t)g.H;
+      const bool bad_xy = (xs[e] >= Wd) | (ys[e] >= Hd);
       const bool bad_t = d >= T_REL_LIMIT || d <= -T_REL_LIMIT;
       if (bad_xy | bad_t) { my_flags |= (bad_xy ? EVREP_WF_OUT_OF_RANGE : 0u) | (bad_t ? EVREP_WF_T_RANGE : 0u); continue; }
       const int32_t t_rel = (int32_t)d;
@@ -339,9 +357,9 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin(const uint16_t* __restrict_
       }
       my_tmin = min(my_tmin, t_rel);
       my_tmax = max(my_tmax, t_rel);
-      const uint32_t lin = ys[e] * (uint32_t)g.W + xs[e];
+      const uint32_t lin = ys[e] * Wd + xs[e];
       const uint32_t tile = lin >> g.tile_shift;
-      const uint32_t r = atomicAdd(&cnt[tile], 1u);
+      const uint32_t r = smem_fetch_inc(cnt_base + (tile << 2));
       tile_rank[e] = (tile << 16) | r;
       key[e] = k;
       meta[e] = rec_meta(lin & (uint32_t)(g.tile_px - 1), aux, (uint32_t)pv & 3u);
