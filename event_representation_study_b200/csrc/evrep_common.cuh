@@ -121,25 +121,29 @@ void prof_end(int kernel_id, cudaStream_t stream);
 // Mixed-density accumulator plan (built on the host from the (window, function, aggregation) tuple)
 // ------------------------------------------------------------------------------------------------
 enum { G_CNT = 1, G_PRES = 2, G_MAX = 4, G_ST = 8, G_ST2 = 16 };
-constexpr int MD_MAX_GROUPS = 24;
+constexpr int MD_MAX_GROUPS = 32;
 
 struct MdGroup {   // one (window, polarity class) pair that some channel reads
-  uint8_t bit;     // membership bit: class * 8 + window, class 0 = all, 1 = p == 1, 2 = "negative"
+  uint8_t bit;     // membership bit: class * 8 + window; class 0 = all, 1 = p == 1, 2 = "negative", 3 = neither
   uint8_t flags;   // G_*
   uint8_t w_cnt, w_max, w_st, w_st2;  // accumulator word indices
   uint8_t pres_bit;
-  uint8_t pad;
+  uint8_t cnt_shift;  // packed plans keep two 16-bit counters per word: 0 or 16
 };
 struct MdChan {
   uint8_t func, agg, win, valid;
-  int8_t g_main, g_all, g_pos, g_neg;
+  int8_t g_main;               // group holding the sums / latest timestamp / presence bit / single-class count
+  int8_t g_pos, g_neg, g_oth;  // class counters; "all events" counts are their sum (an event bumps exactly one of them)
 };
 struct MdPlan {
   int32_t C, G, words, stride, nl1, nl2, lw, w_pres, stacking;
   int32_t static_id;  // 0, or version * 100 + limb width of a compile-time specialised ERGO-12 kernel
+  int32_t packed;     // 1: 16-bit counters and 16-bit limbs, valid for buckets of fewer than 65536 events
+  int32_t pad;
   MdGroup grp[MD_MAX_GROUPS];
   MdChan ch[EVREP_MAX_CHANNELS];
 };
+constexpr uint32_t MD_PACKED_LIMIT = 65536;  // a packed plan may only see buckets with fewer events than this
 
 // ------------------------------------------------------------------------------------------------
 // Launchers (each returns an EVREP_* code and enqueues on `stream`)

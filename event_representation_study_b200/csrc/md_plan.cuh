@@ -28,10 +28,13 @@ constexpr int md_limb_width(int64_t n_max) {
 }
 
 // Returns 0, or 1 when the plan needs too many accumulator words.  C in 1..EVREP_MAX_CHANNELS, stacking valid.
-constexpr int md_plan_build(const int8_t* win, const int8_t* func, const int8_t* agg, int C, int stacking, int lw, MdPlan& P) {
+// packed = true: 16-bit counters (two per word) and 16-bit limbs; exact as long as a bucket holds < 65536 events.
+constexpr int md_plan_build(const int8_t* win, const int8_t* func, const int8_t* agg, int C, int stacking, int lw, bool packed, MdPlan& P) {
   P = MdPlan{};
   P.C = C;
   P.stacking = stacking;
+  P.packed = packed ? 1 : 0;
+  if (packed) lw = 16;
   P.lw = lw;
   P.nl1 = (31 + lw - 1) / lw;
   P.nl2 = (62 + lw - 1) / lw;
@@ -43,7 +46,7 @@ constexpr int md_plan_build(const int8_t* win, const int8_t* func, const int8_t*
     ch.func = (uint8_t)func[c];
     ch.agg = (uint8_t)agg[c];
     ch.win = (uint8_t)wi;
-    ch.g_main = ch.g_all = ch.g_pos = ch.g_neg = -1;
+    ch.g_main = ch.g_pos = ch.g_neg = ch.g_oth = -1;
     // an unknown window / function / aggregation raises inside the reference's make_stack and is
     // swallowed into an all-zero channel (mixed_density_event_stack.py:120-127)
     if (wi < 0 || wi >= n_win || func[c] < 0 || func[c] > EVREP_FUNC_COUNT_NEG || agg[c] < 0 || agg[c] > EVREP_AGG_VARIANCE) {
@@ -52,37 +55,46 @@ constexpr int md_plan_build(const int8_t* win, const int8_t* func, const int8_t*
     }
     ch.valid = 1;
     const int f = func[c], a = agg[c];
-    // up to three (class, need) requests per channel
-    int req_cls[3] = {0, 0, 0}, req_need[3] = {0, 0, 0}, n_req = 0;
+    // requests: need[k] for class k (0 all, 1 pos, 2 neg, 3 neither); `main_cls` names the group md_value starts from
+    int need[4] = {0, 0, 0, 0};
+    int main_cls = -1;
+    bool all_counts = false;  // the channel needs the number of events of every class (= count over "all")
     if (f == EVREP_FUNC_POLARITY) {
-      req_cls[0] = 1; req_need[0] = G_CNT;
-      req_cls[1] = 2; req_need[1] = G_CNT;
-      n_req = 2;
-      if (a != EVREP_AGG_SUM) { req_cls[2] = 0; req_need[2] = G_CNT; n_req = 3; }
+      need[1] = need[2] = G_CNT;
+      if (a != EVREP_AGG_SUM) need[3] = G_CNT;
     } else {
       const bool is_count = (f == EVREP_FUNC_COUNT || f == EVREP_FUNC_COUNT_POS || f == EVREP_FUNC_COUNT_NEG);
-      req_cls[0] = (f == EVREP_FUNC_COUNT || f == EVREP_FUNC_TIMESTAMP) ? 0 : (f == EVREP_FUNC_COUNT_POS || f == EVREP_FUNC_TIMESTAMP_POS) ? 1 : 2;
-      if (is_count)
-        req_need[0] = a == EVREP_AGG_SUM ? G_CNT : (a == EVREP_AGG_VARIANCE ? 0 : G_PRES);  // variance of a constant is 0
-      else
-        req_need[0] = a == EVREP_AGG_SUM ? (G_ST | G_PRES) : a == EVREP_AGG_MEAN ? (G_ST | G_CNT) : a == EVREP_AGG_MAX ? G_MAX : (G_ST | G_ST2 | G_CNT);
-      n_req = req_need[0] ? 1 : 0;
+      const int cls = (f == EVREP_FUNC_COUNT || f == EVREP_FUNC_TIMESTAMP) ? 0 : (f == EVREP_FUNC_COUNT_POS || f == EVREP_FUNC_TIMESTAMP_POS) ? 1 : 2;
+      int main_need = 0;
+      bool count_needed = false;
+      if (is_count) {
+        if (a == EVREP_AGG_SUM) count_needed = true;
+        else if (a != EVREP_AGG_VARIANCE) main_need = G_PRES;  // mean / max of ones: "touched"; variance of a constant is 0
+      } else {
+        main_need = a == EVREP_AGG_SUM ? (G_ST | G_PRES) : a == EVREP_AGG_MEAN ? G_ST : a == EVREP_AGG_MAX ? G_MAX : (G_ST | G_ST2);
+        count_needed = (a == EVREP_AGG_MEAN || a == EVREP_AGG_VARIANCE);
+      }
+      if (count_needed) {
+        if (cls == 0) all_counts = true; else main_need |= G_CNT;
+      }
+      if (all_counts) need[1] = need[2] = need[3] = G_CNT;
+      if (main_need) { need[cls] |= main_need; main_cls = cls; }
     }
-    for (int r = 0; r < n_req; ++r) {
-      const int bit = req_cls[r] * 8 + wi;
+    for (int k = 0; k < 4; ++k) {
+      if (!need[k]) continue;
+      const int bit = k * 8 + wi;
       int g = 0;
       for (; g < P.G; ++g)
         if (P.grp[g].bit == bit) break;
       if (g == P.G) { P.grp[g].bit = (uint8_t)bit; P.grp[g].flags = 0; ++P.G; }
-      P.grp[g].flags |= (uint8_t)req_need[r];
-      if (f == EVREP_FUNC_POLARITY) {
-        if (r == 0) ch.g_pos = (int8_t)g; else if (r == 1) ch.g_neg = (int8_t)g; else ch.g_all = (int8_t)g;
-      } else {
-        ch.g_main = (int8_t)g;
+      P.grp[g].flags |= (uint8_t)need[k];
+      if (k == main_cls) ch.g_main = (int8_t)g;
+      if (f == EVREP_FUNC_POLARITY || all_counts) {
+        if (k == 1) ch.g_pos = (int8_t)g; else if (k == 2) ch.g_neg = (int8_t)g; else if (k == 3) ch.g_oth = (int8_t)g;
       }
     }
   }
-  int words = 0, pres_bits = 0;
+  int words = 0, pres_bits = 0, half = 0, cnt_word = 0;
   bool any_pres = false;
   for (int g = 0; g < P.G; ++g) {
     MdGroup& G = P.grp[g];
@@ -91,10 +103,21 @@ constexpr int md_plan_build(const int8_t* win, const int8_t* func, const int8_t*
     if (G.flags & G_PRES) any_pres = true;
   }
   if (any_pres) P.w_pres = words++;
+  for (int g = 0; g < P.G; ++g) {  // counters first: packed plans pair them up
+    MdGroup& G = P.grp[g];
+    if (!(G.flags & G_CNT)) continue;
+    if (packed) {
+      if (half == 0) cnt_word = words++;
+      G.w_cnt = (uint8_t)cnt_word;
+      G.cnt_shift = (uint8_t)(16 * half);
+      half ^= 1;
+    } else {
+      G.w_cnt = (uint8_t)words++;
+    }
+  }
   for (int g = 0; g < P.G; ++g) {
     MdGroup& G = P.grp[g];
     if (G.flags & G_PRES) G.pres_bit = (uint8_t)pres_bits++;
-    if (G.flags & G_CNT) G.w_cnt = (uint8_t)words++;
     if (G.flags & G_MAX) G.w_max = (uint8_t)words++;
     if (G.flags & G_ST) { G.w_st = (uint8_t)words; words += P.nl1; }
     if (G.flags & G_ST2) { G.w_st2 = (uint8_t)words; words += P.nl2; }
@@ -108,12 +131,12 @@ constexpr int md_plan_build(const int8_t* win, const int8_t* func, const int8_t*
 
 // compile-time ERGO-12 plans for a menu of limb widths
 constexpr int kErgoLimbMenu[] = {16, 14, 12, 10, 8};  // windows below 2^16, 2^18, 2^20, 2^22, 2^24 events
-template <int VER, int LW>
+template <int VER, int LW, bool PACKED = false>
 struct ErgoPlan {
   static constexpr MdPlan make() {
     MdPlan P{};
     md_plan_build(VER == 2 ? kErgoWin2 : kErgoWin1, VER == 2 ? kErgoFunc2 : kErgoFunc1, VER == 2 ? kErgoAgg2 : kErgoAgg1, 12,
-                  EVREP_STACK_SBN, LW, P);
+                  EVREP_STACK_SBN, LW, PACKED, P);
     return P;
   }
   static constexpr MdPlan value = make();

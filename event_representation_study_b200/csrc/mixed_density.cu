@@ -15,6 +15,12 @@
 #include "evrep_common.cuh"
 #include "md_plan.cuh"
 
+#define EVREP_TRY_RC(expr)       \
+  do {                          \
+    int _rc = (expr);           \
+    if (_rc != EVREP_OK) return _rc; \
+  } while (0)
+
 namespace evrep {
 
 size_t md_tile_smem_bytes(const MdPlan& plan, int tile_px) { return align_up((size_t)plan.stride * (size_t)tile_px * sizeof(uint32_t), 16); }
@@ -44,13 +50,13 @@ int build_md_plan(const int8_t* win, const int8_t* func, const int8_t* agg, int 
         if (m <= lw) { pick = m; break; }
       if (pick) {
         lw = pick;
-        if (md_plan_build(win, func, agg, C, stacking, lw, *out)) return EVREP_EUNSUPPORTED;
+        if (md_plan_build(win, func, agg, C, stacking, lw, false, *out)) return EVREP_EUNSUPPORTED;
         out->static_id = ver * 100 + lw;
         return EVREP_OK;
       }
     }
   }
-  if (md_plan_build(win, func, agg, C, stacking, lw, *out)) {
+  if (md_plan_build(win, func, agg, C, stacking, lw, false, *out)) {
     set_error("mixed-density plan needs more than 250 accumulator words per pixel");
     return EVREP_EUNSUPPORTED;
   }
@@ -65,8 +71,15 @@ int build_md_plan(const int8_t* win, const int8_t* func, const int8_t* agg, int 
 // finalise its pixel in place (outputs overwrite the pixel's own dead accumulators) and (c) the CTA then
 // streams the tile's output slice to global memory with fully coalesced 16-byte stores.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t md_touched(const MdPlan& P, const MdGroup& G, const uint32_t* a) {
-  if (G.flags & G_CNT) return a[G.w_cnt];
+__device__ __forceinline__ uint32_t md_cnt(const MdPlan& P, const MdGroup& G, const uint32_t* a) {
+  return P.packed ? ((a[G.w_cnt] >> G.cnt_shift) & 0xffffu) : a[G.w_cnt];
+}
+// number of events of the channel's class at this pixel (or just 0 / 1 when only "touched" is tracked)
+__device__ __forceinline__ uint32_t md_count(const MdPlan& P, const MdChan& ch, const uint32_t* a) {
+  if (ch.g_pos >= 0 && ch.g_neg >= 0 && ch.g_oth >= 0)  // "all events": every event bumped exactly one class counter
+    return md_cnt(P, P.grp[ch.g_pos], a) + md_cnt(P, P.grp[ch.g_neg], a) + md_cnt(P, P.grp[ch.g_oth], a);
+  const MdGroup& G = P.grp[ch.g_main];
+  if (G.flags & G_CNT) return md_cnt(P, G, a);
   if (G.flags & G_MAX) return a[G.w_max] != 0u;
   if (G.flags & G_PRES) return (a[P.w_pres] >> G.pres_bit) & 1u;
   return 0u;
@@ -90,10 +103,11 @@ __device__ __forceinline__ float md_value(const MdPlan& P, const MdChan& ch, con
                                           uint32_t has_m1) {
   if (!ch.valid) return 0.f;
   if (ch.func == EVREP_FUNC_POLARITY) {
-    const int c1 = (int)a[P.grp[ch.g_pos].w_cnt];
-    const int cm = ((has_m1 >> ch.win) & 1u) ? (int)a[P.grp[ch.g_neg].w_cnt] : 0;
+    const int c1 = (int)md_cnt(P, P.grp[ch.g_pos], a);
+    const int cn = (int)md_cnt(P, P.grp[ch.g_neg], a);
+    const int cm = ((has_m1 >> ch.win) & 1u) ? cn : 0;  // the "negative" class holds the p == 0 events when the window has no -1
     if (ch.agg == EVREP_AGG_SUM) return (float)(c1 - cm);
-    const int call = (int)a[P.grp[ch.g_all].w_cnt];
+    const int call = c1 + cn + (int)md_cnt(P, P.grp[ch.g_oth], a);
     if (call == 0) return 0.f;
     if (ch.agg == EVREP_AGG_MEAN) return __fdividef((float)(c1 - cm), (float)call);
     if (ch.agg == EVREP_AGG_VARIANCE) {  // mean(p^2) - mean(p)^2 = ((c1+cm) call - (c1-cm)^2) / call^2, numerator exact in fp64
@@ -102,13 +116,13 @@ __device__ __forceinline__ float md_value(const MdPlan& P, const MdChan& ch, con
     }
     return c1 > 0 ? 1.f : (call - c1 - cm > 0 ? 0.f : -1.f);  // max of the raw polarities
   }
-  if (ch.g_main < 0) return 0.f;
-  const MdGroup& G = P.grp[ch.g_main];
-  const uint32_t c = md_touched(P, G, a);
-  if (c == 0u) return 0.f;  // torch_scatter leaves untouched pixels at 0
   const bool is_count = (ch.func == EVREP_FUNC_COUNT || ch.func == EVREP_FUNC_COUNT_POS || ch.func == EVREP_FUNC_COUNT_NEG);
+  if (ch.g_main < 0 && ch.g_pos < 0) return 0.f;  // variance of a constant
+  const uint32_t c = md_count(P, ch, a);
+  if (c == 0u) return 0.f;  // torch_scatter leaves untouched pixels at 0
   if (is_count) return ch.agg == EVREP_AGG_SUM ? (float)c : 1.f;
   // timestamps: t_s = (t - t_min) / (t_max - t_min); delta == 0 gives NaN exactly like the reference
+  const MdGroup& G = P.grp[ch.g_main];
   if (ch.agg == EVREP_AGG_MAX) {
     const uint32_t v = a[G.w_max] - 1u;
     return (v == delta_u && delta_u) ? 1.f : (float)v * inv_delta;  // the window's last event maps to exactly 1
@@ -173,12 +187,12 @@ __global__ void __launch_bounds__(TILE_THREADS) k_md_tile(const uint2* __restric
     // "negative" events of a window: p == -1, or p == 0 when the window holds no -1 (operations.py:59-61,78-80)
     const uint32_t posm = (pc == 1u) ? wmask : 0u;
     const uint32_t negm = (pc == 3u) ? wmask : (pc == 0u ? (wmask & ~w.has_m1) : 0u);
-    const uint32_t M = wmask | (posm << 8) | (negm << 16);
+    const uint32_t M = wmask | (posm << 8) | (negm << 16) | ((wmask & ~(posm | negm)) << 24);
     uint32_t pres = 0;
     for (int gi = 0; gi < P.G; ++gi) {
       const MdGroup G = P.grp[gi];
       if (!((M >> G.bit) & 1u)) continue;
-      if (G.flags & G_CNT) atomicAdd(a + G.w_cnt, 1u);
+      if (G.flags & G_CNT) atomicAdd(a + G.w_cnt, 1u << G.cnt_shift);
       if (G.flags & G_PRES) pres |= 1u << G.pres_bit;
       if (G.flags & G_MAX) atomicMax(a + G.w_max, tt + 1u);
       if (G.flags & G_ST) {
@@ -246,7 +260,7 @@ __device__ __forceinline__ void md_acc_group(uint32_t* a, uint32_t M, uint32_t t
   constexpr int LW = PS::value.lw, NL1 = PS::value.nl1, NL2 = PS::value.nl2;
   constexpr uint32_t MASK = (1u << LW) - 1u;
   if (!((M >> G.bit) & 1u)) return;
-  if constexpr (G.flags & G_CNT) atomicAdd(a + G.w_cnt, 1u);
+  if constexpr (G.flags & G_CNT) atomicAdd(a + G.w_cnt, 1u << G.cnt_shift);
   if constexpr (G.flags & G_PRES) pres |= 1u << G.pres_bit;
   if constexpr (G.flags & G_MAX) atomicMax(a + G.w_max, tt + 1u);
   if constexpr (G.flags & G_ST) {
@@ -291,7 +305,7 @@ __device__ __forceinline__ void md_accumulate_static(uint32_t* acc, const uint2 
   const uint32_t wmask = (r.y >> 16) & 0xffu;
   const uint32_t posm = (pc == 1u) ? wmask : 0u;
   const uint32_t negm = (pc == 3u) ? wmask : (pc == 0u ? (wmask & not_m1) : 0u);
-  const uint32_t M = wmask | (posm << 8) | (negm << 16);
+  const uint32_t M = wmask | (posm << 8) | (negm << 16) | ((wmask & ~(posm | negm)) << 24);
   uint32_t pres = 0;
   md_acc_all<PS>(a, M, tt, pres, std::make_integer_sequence<int, G>{});
   if (pres) {
@@ -329,16 +343,57 @@ __device__ __forceinline__ TileHdr md_load_hdr(int id, const Geom& g, int TP, co
   return h;
 }
 
+// finalise + repack + TMA store of one tile (all threads of the CTA); leaves the bulk store in flight
 template <typename PS, int TP>
-__global__ void __launch_bounds__(TILE_THREADS, TP == 1024 ? 2 : 3) k_md_tile_static(const uint2* __restrict__ records, const uint32_t* __restrict__ base,
-                                                                    const uint32_t* __restrict__ cursor, const WinParams* __restrict__ wp,
-                                                                    const Geom g, uint32_t* __restrict__ ticket, float* __restrict__ out) {
+__device__ __forceinline__ void md_finalise_store(uint32_t* acc, const TileHdr& h, const Geom& g, float* __restrict__ out) {
+  constexpr int STRIDE = PS::value.stride, C = PS::value.C, PPT = TP / TILE_THREADS;
+  const int tid = threadIdx.x;
+  const double delta = (double)h.delta_u;
+  const float inv_delta = 1.f / (float)h.delta_u;
+  float o[PPT][C];
+#pragma unroll
+  for (int k = 0; k < PPT; ++k)
+    md_finalise_static<PS>(acc + (tid + k * TILE_THREADS) * STRIDE, inv_delta, delta, h.delta_u, h.has_m1, o[k], std::make_integer_sequence<int, C>{});
+  __syncthreads();
+  float4* stage = reinterpret_cast<float4*>(acc);  // [TP][C] floats, contiguous = the global layout of the slice
+#pragma unroll
+  for (int k = 0; k < PPT; ++k)
+#pragma unroll
+    for (int q = 0; q < C / 4; ++q)
+      stage[(tid + k * TILE_THREADS) * (C / 4) + q] = make_float4(o[k][4 * q], o[k][4 * q + 1], o[k][4 * q + 2], o[k][4 * q + 3]);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  constexpr int SLICE_PX = TP / 4;  // four issuing threads, one per quarter of the tile
+  if ((tid & 31) == 0 && tid < 128) {
+    const int npix = min(TP, g.HW - h.pix0);
+    const int p0 = (tid >> 5) * SLICE_PX;
+    const int np = min(SLICE_PX, npix - p0);
+    if (np > 0) {
+      float* dst = out + ((size_t)h.b * g.HW + h.pix0 + p0) * C;
+      const uint32_t src = (uint32_t)__cvta_generic_to_shared(acc + p0 * C);
+      const uint32_t bytes = (uint32_t)np * C * 4u;
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+}
+__device__ __forceinline__ void md_wait_store() {  // the four issuing threads: the TMA engine has read its source
+  if ((threadIdx.x & 31) == 0 && threadIdx.x < 128) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+// LIGHT_ONLY: the plan is a packed one (16-bit counters / limbs); buckets with >= 65536 events are left to
+// k_md_tile_heavy, which runs the wide plan on them afterwards.
+template <typename PS, int TP, bool LIGHT_ONLY>
+__global__ void __launch_bounds__(TILE_THREADS, (PS::value.stride * TP * 4 <= 74 * 1024) ? 3 : 2)
+    k_md_tile_static(const uint2* __restrict__ records, const uint32_t* __restrict__ base, const uint32_t* __restrict__ cursor,
+                     const WinParams* __restrict__ wp, const Geom g, uint32_t* __restrict__ ticket, float* __restrict__ out) {
   extern __shared__ __align__(128) uint32_t acc[];
   __shared__ int s_next;
   constexpr int STRIDE = PS::value.stride, C = PS::value.C;
-  constexpr int PPT = TP / TILE_THREADS, PRE = 3;
+  constexpr int PRE = 3;
   static_assert(PS::value.stacking == EVREP_STACK_SBN && (C & 3) == 0 && TP % TILE_THREADS == 0, "static path: SBN, C % 4 == 0");
   static_assert(C <= STRIDE, "outputs must fit the accumulator footprint");
+  static_assert(!LIGHT_ONLY || PS::value.packed, "only packed plans have an event limit");
   const int tid = threadIdx.x;
   const int n_tiles = g.B * g.T;
   // bucket order: blockIdx.x, blockIdx.x + gridDim.x, then tickets 2*gridDim.x + k; the ticket for the bucket
@@ -354,19 +409,21 @@ __global__ void __launch_bounds__(TILE_THREADS, TP == 1024 ? 2 : 3) k_md_tile_st
     pre[j] = i < h.count ? __ldg(h.rec + i) : make_uint2(0u, 0u);  // meta 0: member of no window, touches nothing
   }
 
-  bool first = true;
+  bool pending = false;  // a TMA store issued by this CTA may still be reading shared memory
   while (true) {
+    const bool skip = LIGHT_ONLY && h.count >= MD_PACKED_LIMIT;  // CTA-uniform
     int my_ticket = 0;
     if (tid == 0) my_ticket = (int)atomicAdd(ticket, 1u);  // consumed after the atomics phase
-    {
+    if (!skip) {
       // the first TP*C words may still be read by the TMA store of the previous bucket: clear the rest first
       uint4* a4 = reinterpret_cast<uint4*>(acc);
       constexpr int N4 = (STRIDE * TP + 3) / 4, S4 = TP * C / 4;
 #pragma unroll 4
       for (int i = S4 + tid; i < N4; i += TILE_THREADS) a4[i] = make_uint4(0, 0, 0, 0);
-      if (!first) {
-        if ((tid & 31) == 0 && tid < 128) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      if (pending) {
+        md_wait_store();
         __syncthreads();
+        pending = false;
       }
 #pragma unroll 4
       for (int i = tid; i < S4; i += TILE_THREADS) a4[i] = make_uint4(0, 0, 0, 0);
@@ -376,12 +433,13 @@ __global__ void __launch_bounds__(TILE_THREADS, TP == 1024 ? 2 : 3) k_md_tile_st
     if (more) hn = md_load_hdr(nxt, g, TP, records, base, cursor, wp);  // in flight during the atomics below
     __syncthreads();
 
-    const uint32_t not_m1 = ~h.has_m1;
+    if (!skip) {
+      const uint32_t not_m1 = ~h.has_m1;
 #pragma unroll
-    for (int j = 0; j < PRE; ++j)
-      if (pre[j].y) md_accumulate_static<PS>(acc, pre[j], h.tmin, not_m1);
-    for (uint32_t i = tid + PRE * TILE_THREADS; i < h.count; i += TILE_THREADS) md_accumulate_static<PS>(acc, __ldg(h.rec + i), h.tmin, not_m1);
-
+      for (int j = 0; j < PRE; ++j)
+        if (pre[j].y) md_accumulate_static<PS>(acc, pre[j], h.tmin, not_m1);
+      for (uint32_t i = tid + PRE * TILE_THREADS; i < h.count; i += TILE_THREADS) md_accumulate_static<PS>(acc, __ldg(h.rec + i), h.tmin, not_m1);
+    }
 #pragma unroll
     for (int j = 0; j < PRE; ++j) {  // next bucket's records: in flight during finalise + store
       const uint32_t i = tid + j * TILE_THREADS;
@@ -391,69 +449,96 @@ __global__ void __launch_bounds__(TILE_THREADS, TP == 1024 ? 2 : 3) k_md_tile_st
     __syncthreads();
     const int nn = s_next;
 
-    const double delta = (double)h.delta_u;
-    const float inv_delta = 1.f / (float)h.delta_u;
-    float o[PPT][C];
-#pragma unroll
-    for (int k = 0; k < PPT; ++k)
-      md_finalise_static<PS>(acc + (tid + k * TILE_THREADS) * STRIDE, inv_delta, delta, h.delta_u, h.has_m1, o[k], std::make_integer_sequence<int, C>{});
-    __syncthreads();
-    float4* stage = reinterpret_cast<float4*>(acc);  // [TP][C] floats, contiguous = the global layout of the slice
-#pragma unroll
-    for (int k = 0; k < PPT; ++k)
-#pragma unroll
-      for (int q = 0; q < C / 4; ++q)
-        stage[(tid + k * TILE_THREADS) * (C / 4) + q] = make_float4(o[k][4 * q], o[k][4 * q + 1], o[k][4 * q + 2], o[k][4 * q + 3]);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    constexpr int SLICE_PX = TP / 4;  // four issuing threads, one per quarter of the tile
-    if ((tid & 31) == 0 && tid < 128) {
-      const int npix = min(TP, g.HW - h.pix0);
-      const int p0 = (tid >> 5) * SLICE_PX;
-      const int np = min(SLICE_PX, npix - p0);
-      if (np > 0) {
-        float* dst = out + ((size_t)h.b * g.HW + h.pix0 + p0) * C;
-        const uint32_t src = (uint32_t)__cvta_generic_to_shared(acc + p0 * C);
-        const uint32_t bytes = (uint32_t)np * C * 4u;
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      }
+    if (!skip) {
+      md_finalise_store<PS, TP>(acc, h, g, out);
+      pending = true;
     }
     if (!more) {
-      if ((tid & 31) == 0 && tid < 128) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must outlive the read
+      if (pending) md_wait_store();  // shared memory must outlive the read
       break;
     }
-    first = false;
     h = hn;
     cur = nxt;
     nxt = nn;
   }
 }
 
+// The buckets a packed plan must not touch (>= 65536 events: one hot tile), with the wide plan, one at a time.
 template <typename PS, int TP>
-static int launch_static_tp(const Geom& g, const Workspace& ws, size_t smem, float* out, cudaStream_t stream) {
-  static int n_sm = 0;
-  if (!n_sm) {
+__global__ void __launch_bounds__(TILE_THREADS, 2) k_md_tile_heavy(const uint2* __restrict__ records, const uint32_t* __restrict__ base,
+                                                                   const uint32_t* __restrict__ cursor, const WinParams* __restrict__ wp,
+                                                                   const Geom g, float* __restrict__ out) {
+  extern __shared__ __align__(128) uint32_t acc[];
+  __shared__ uint32_t s_heavy[TILE_THREADS / 32];
+  constexpr int STRIDE = PS::value.stride;
+  const int tid = threadIdx.x;
+  const int n_tiles = g.B * g.T;
+  for (int base_id = blockIdx.x * TILE_THREADS; base_id < n_tiles; base_id += gridDim.x * TILE_THREADS) {
+    const int id = base_id + tid;
+    const bool heavy = id < n_tiles && __ldg(cursor + id) >= MD_PACKED_LIMIT;
+    const uint32_t m = __ballot_sync(0xffffffffu, heavy);
+    if ((tid & 31) == 0) s_heavy[tid >> 5] = m;
+    __syncthreads();
+    for (int wd = 0; wd < TILE_THREADS / 32; ++wd) {
+      uint32_t bits = s_heavy[wd];  // same value in every thread: uniform control flow
+      while (bits) {
+        const int tile_id = base_id + wd * 32 + (__ffs(bits) - 1);
+        bits &= bits - 1;
+        const TileHdr h = md_load_hdr(tile_id, g, TP, records, base, cursor, wp);
+        uint4* a4 = reinterpret_cast<uint4*>(acc);
+        for (int i = tid; i < (STRIDE * TP + 3) / 4; i += TILE_THREADS) a4[i] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+        const uint32_t not_m1 = ~h.has_m1;
+        for (uint32_t i = tid; i < h.count; i += TILE_THREADS) md_accumulate_static<PS>(acc, __ldg(h.rec + i), h.tmin, not_m1);
+        __syncthreads();
+        md_finalise_store<PS, TP>(acc, h, g, out);
+        md_wait_store();
+        __syncthreads();
+      }
+    }
+    __syncthreads();
+  }
+}
+
+static int sm_count(int* n_sm) {
+  static int cached = 0;
+  if (!cached) {
     int dev = 0;
     EVREP_CUDA_OK(cudaGetDevice(&dev));
-    EVREP_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    EVREP_CUDA_OK(cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev));
   }
-  EVREP_CUDA_OK(cudaFuncSetAttribute(k_md_tile_static<PS, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 1;
-  EVREP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_md_tile_static<PS, TP>, TILE_THREADS, smem));
-  if (per_sm < 1) per_sm = 1;
+  *n_sm = cached;
+  return EVREP_OK;
+}
+
+static_assert(ErgoPlan<2, 16, true>::value.words == 16 && ErgoPlan<2, 16, true>::value.stride == 17, "packed ERGO-12 v2 plan: 16 words per pixel");
+static_assert(ErgoPlan<2, 12, false>::value.words == 24, "wide ERGO-12 v2 plan at 2^20 events: 24 words per pixel");
+
+// ERGO-12 at the standard 1024-pixel tile: packed plan on every bucket below 65536 events, wide plan on the rest
+template <int VER, int LW>
+static int launch_static(const Geom& g, const Workspace& ws, float* out, cudaStream_t stream) {
+  constexpr int TP = 1024;
+  using Packed = ErgoPlan<VER, 16, true>;
+  using Wide = ErgoPlan<VER, LW, false>;
+  int n_sm = 0;
+  EVREP_TRY_RC(sm_count(&n_sm));
   const int n_tiles = g.B * g.T;
+  auto light = k_md_tile_static<Packed, TP, true>;
+  auto heavy = k_md_tile_heavy<Wide, TP>;
+  const size_t smem_l = align_up((size_t)Packed::value.stride * TP * 4, 128), smem_h = align_up((size_t)Wide::value.stride * TP * 4, 128);
+  EVREP_CUDA_OK(cudaFuncSetAttribute(light, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
+  EVREP_CUDA_OK(cudaFuncSetAttribute(heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
+  int per_sm = 1;
+  EVREP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, light, TILE_THREADS, smem_l));
+  if (per_sm < 1) per_sm = 1;
   const int grid = n_tiles < per_sm * n_sm ? n_tiles : per_sm * n_sm;
   prof_begin(EVREP_K_TILE, stream);
-  k_md_tile_static<PS, TP><<<grid, TILE_THREADS, smem, stream>>>(ws.records, ws.base, ws.cursor, ws.wp, g, ws.ticket, out);
+  light<<<grid, TILE_THREADS, smem_l, stream>>>(ws.records, ws.base, ws.cursor, ws.wp, g, ws.ticket, out);
+  heavy<<<(n_tiles + TILE_THREADS - 1) / TILE_THREADS < n_sm ? (n_tiles + TILE_THREADS - 1) / TILE_THREADS : n_sm, TILE_THREADS, smem_h, stream>>>(
+      ws.records, ws.base, ws.cursor, ws.wp, g, out);
   prof_end(EVREP_K_TILE, stream);
   EVREP_CUDA_OK(cudaGetLastError());
   return EVREP_OK;
-}
-template <typename PS>
-static int launch_static(const Geom& g, const Workspace& ws, size_t smem, float* out, cudaStream_t stream) {
-  if (g.tile_px == 1024) return launch_static_tp<PS, 1024>(g, ws, smem, out, stream);
-  return launch_static_tp<PS, 512>(g, ws, smem, out, stream);
 }
 
 // SBT only: which time windows hold a p == -1 event (needed before the tile pass can decide what
@@ -493,10 +578,10 @@ int launch_md_tile(const Geom& g, const Workspace& ws, const MdPlan& plan, const
     EVREP_CUDA_OK(cudaGetLastError());
   }
   const size_t smem = md_tile_smem_bytes(plan, g.tile_px);
-  switch ((g.tile_px == 1024 || g.tile_px == 512) ? plan.static_id : 0) {
+  switch (g.tile_px == 1024 ? plan.static_id : 0) {
 #define EVREP_STATIC_CASE(VER, LW) \
   case VER * 100 + LW:             \
-    return launch_static<ErgoPlan<VER, LW>>(g, ws, smem, out, stream);
+    return launch_static<VER, LW>(g, ws, out, stream);
     EVREP_STATIC_CASE(2, 16) EVREP_STATIC_CASE(2, 14) EVREP_STATIC_CASE(2, 12) EVREP_STATIC_CASE(2, 10) EVREP_STATIC_CASE(2, 8)
     EVREP_STATIC_CASE(1, 16) EVREP_STATIC_CASE(1, 14) EVREP_STATIC_CASE(1, 12) EVREP_STATIC_CASE(1, 10) EVREP_STATIC_CASE(1, 8)
 #undef EVREP_STATIC_CASE

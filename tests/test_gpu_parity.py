@@ -213,6 +213,24 @@ def test_ergo12_vs_oracle(E, H, W, sizes, kw):
             assert np.array_equal(out[i][:, :, c], want[:, :, c].astype(np.float32))
 
 
+def test_ergo12_hot_tile(E):
+    """More than 65535 events inside one 1024-pixel tile: the packed (16-bit) plan must hand the bucket to the wide plan."""
+    from oracle import representations as orep
+    from event_representation_study_b200.synth import poisson_window
+    H, W = 64, 64
+    w = poisson_window(77, 180_000, H, W)
+    w["x"] = (w["x"] % 8).astype(np.uint16)  # 150k+ events on 8 x 64 pixels of the first tiles, the rest nearly empty
+    hot = np.arange(len(w["x"])) % 3 == 0
+    w["x"][hot] = 3
+    w["y"][hot] = 5  # one pixel alone receives 60k events
+    out = np_(E.ergo12(E.pack_events([w, poisson_window(78, 5000, H, W)], "cuda"), H, W))
+    with np.errstate(all="ignore"):
+        want = orep.ergo12(w["x"], w["y"], w["t"], w["p"], H, W)
+    assert_close(out[0], want, rtol=RTOL, atol=VAR_ATOL, what="hot tile")
+    for c in (2, 3, 4, 5, 7, 11):
+        assert np.array_equal(out[0][:, :, c], want[:, :, c].astype(np.float32))
+
+
 def test_ergo12_v1_vs_oracle(E):
     from oracle import representations as orep
     H, W = 120, 160
