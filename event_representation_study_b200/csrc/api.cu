@@ -81,12 +81,14 @@ static int choose_tile(int H, int W, size_t bytes_per_px, Geom* g) {
   g->tile_shift = shift;
   g->tile_px = 1 << shift;
   g->T = (g->HW + g->tile_px - 1) >> shift;
+  g->t_magic = ((1ull << 44) + (unsigned long long)g->T - 1) / (unsigned long long)g->T;
   return EVREP_OK;
 }
 
 static int check_events(const uint16_t* x, const uint16_t* y, const void* t, int t_bytes, const int8_t* p, const int64_t* win_offsets,
                         int B, const void* out, Events* ev, int64_t* total, int64_t* n_max) {
   if (B < 0 || !win_offsets) { set_error("B must be >= 0 and win_offsets non-null"); return EVREP_EINVAL; }
+  if (B >= (1 << 20)) { set_error("at most 2^20 - 1 windows per call"); return EVREP_EUNSUPPORTED; }
   if (t_bytes != 4 && t_bytes != 8) { set_error("t_bytes must be 4 (int32) or 8 (int64), got %d", t_bytes); return EVREP_EINVAL; }
   *total = win_offsets[B];
   *n_max = 0;

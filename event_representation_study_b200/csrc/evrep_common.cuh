@@ -55,6 +55,7 @@ struct Geom {
   int B, H, W, HW;
   int tile_shift, tile_px, T;  // tile = contiguous range of tile_px linear pixel indices; T tiles per window
   int64_t total;               // total events in the batch
+  unsigned long long t_magic;  // ceil(2^44 / T): id / T == (id * t_magic) >> 44 for id < 2^32, T <= 4096
 };
 
 struct Workspace {  // device pointers carved out of the caller's buffer

@@ -85,14 +85,12 @@ __device__ __forceinline__ uint32_t md_count(const MdPlan& P, const MdChan& ch, 
   return 0u;
 }
 
-// exact value of a multi-limb sum as a double (limbs are base-2^lw digits with 32-bit headroom)
+// value of a multi-limb sum as a double (limbs are base-2^lw digits with 32-bit headroom): Horner in fp64, exact while the
+// sum stays below 2^53 and correctly rounded to ~1e-16 relative beyond
 __device__ __forceinline__ double md_limb_sum(const uint32_t* a, int w0, int nl, int lw) {
-  // low three limbs and the rest are each combined exactly in 64-bit integers, then joined in fp64
-  unsigned long long lo = 0, hi = 0;
-  for (int l = 0; l < nl && l < 3; ++l) lo += (unsigned long long)a[w0 + l] << (l * lw);
-  for (int l = 3; l < nl; ++l) hi += (unsigned long long)a[w0 + l] << ((l - 3) * lw);
-  double s = (double)lo;
-  if (nl > 3) s = fma((double)hi, (double)(1ull << (3 * lw)), s);
+  const double radix = (double)(1u << lw);
+  double s = (double)a[w0 + nl - 1];
+  for (int l = nl - 2; l >= 0; --l) s = fma(s, radix, (double)a[w0 + l]);
   return s;
 }
 
@@ -331,7 +329,7 @@ struct TileHdr {
 __device__ __forceinline__ TileHdr md_load_hdr(int id, const Geom& g, int TP, const uint2* records, const uint32_t* base,
                                                const uint32_t* cursor, const WinParams* wp) {
   TileHdr h;
-  h.b = id / g.T;
+  h.b = (int)(((unsigned long long)(uint32_t)id * g.t_magic) >> 44);  // id / T, exact for id < 2^32 and T <= 4096
   h.pix0 = (id - h.b * g.T) * TP;
   const WinParams* w = wp + h.b;
   h.count = __ldg(cursor + id);
