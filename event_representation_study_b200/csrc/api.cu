@@ -57,7 +57,7 @@ constexpr size_t TILE_SMEM_TARGET = 100 * 1024;  // two tile CTAs per SM
 constexpr size_t TILE_SMEM_MAX = 220 * 1024;
 
 // tile_px = largest power of two (<= 4096) whose accumulators fit the target; T = tiles per window
-static int choose_tile(int H, int W, size_t bytes_per_px, Geom* g) {
+static int choose_tile(int H, int W, size_t bytes_per_px, Geom* g, int split = 0) {
   if (H < 1 || W < 1 || H > 65535 || W > 65535 || (int64_t)H * W > ((int64_t)1 << 28)) {
     set_error("sensor size %d x %d unsupported", W, H);
     return EVREP_EINVAL;
@@ -73,14 +73,16 @@ static int choose_tile(int H, int W, size_t bytes_per_px, Geom* g) {
   int shift = 12;
   while (shift > 8 && ((size_t)1 << shift) * bytes_per_px > target) --shift;
   // a very large sensor needs bigger tiles than the target allows: trade occupancy for reach
-  while (((g->HW + (1 << shift) - 1) >> shift) > MAX_TILES && shift < 16) ++shift;
-  if (((size_t)1 << shift) * bytes_per_px > TILE_SMEM_MAX || ((g->HW + (1 << shift) - 1) >> shift) > MAX_TILES) {
+  while ((((g->HW + (1 << shift) - 1) >> shift) << split) > MAX_TILES && shift < 16) ++shift;
+  if (((size_t)1 << shift) * bytes_per_px > TILE_SMEM_MAX || (((g->HW + (1 << shift) - 1) >> shift) << split) > MAX_TILES) {
     set_error("%d x %d pixels with %zu accumulator bytes per pixel does not fit the tile pipeline", W, H, bytes_per_px);
     return EVREP_EUNSUPPORTED;
   }
   g->tile_shift = shift;
   g->tile_px = 1 << shift;
   g->T = (g->HW + g->tile_px - 1) >> shift;
+  g->split = split;
+  g->Tb = g->T << split;
   g->t_magic = ((1ull << 44) + (unsigned long long)g->T - 1) / (unsigned long long)g->T;
   return EVREP_OK;
 }
@@ -173,7 +175,7 @@ size_t evrep_workspace_bytes(int op, int B, int64_t total_events, int H, int W, 
   (void)C;
   if (op < EVREP_OP_MIXED_DENSITY || op > EVREP_OP_HISTOGRAM || B < 0 || total_events < 0 || H < 1 || W < 1) return 0;
   const int64_t hw = (int64_t)H * W;
-  int64_t T = (hw + MIN_TILE_PX - 1) / MIN_TILE_PX;
+  int64_t T = 2 * ((hw + MIN_TILE_PX - 1) / MIN_TILE_PX);  // buckets per window: at most two per tile
   if (T > MAX_TILES) T = MAX_TILES;
   const bool tiles = op != EVREP_OP_VOXEL && op != EVREP_OP_HISTOGRAM;
   return carve(nullptr, B > 0 ? B : 1, tiles ? total_events : 0, tiles ? (int)T : 1).bytes;
@@ -222,10 +224,13 @@ int evrep_mixed_density_batched(const uint16_t* x, const uint16_t* y, const void
   Geom g;
   memset(&g, 0, sizeof(g));
   EVREP_TRY(choose_tile(H, W, (size_t)plan.stride * 4, &g));
+  // the compile-time specialised ERGO-12 kernels (1024-pixel tiles) want every tile's events split by polarity
+  if (plan.static_id && g.tile_px == 1024 && 2 * g.T <= MAX_TILES) EVREP_TRY(choose_tile(H, W, (size_t)plan.stride * 4, &g, 1));
+  if (g.tile_px != 1024) g.split = 0, g.Tb = g.T;
   g.B = B;
   g.total = total;
   Workspace ws;
-  EVREP_TRY(carve_checked(workspace, workspace_bytes, B, total, g.T, &ws));
+  EVREP_TRY(carve_checked(workspace, workspace_bytes, B, total, g.Tb, &ws));
   EVREP_TRY(run_binning(ev, win_offsets, g, ws, stacking == EVREP_STACK_SBN ? REC_T_WMASK : REC_T_ONLY, 0, nullptr, (cudaStream_t)stream));
   return launch_md_tile(g, ws, plan, ev, out, (cudaStream_t)stream);
   EVREP_GUARD_END
@@ -263,7 +268,7 @@ int evrep_event_stack_batched(const uint16_t* x, const uint16_t* y, const void* 
   g.B = B;
   g.total = total;
   Workspace ws;
-  EVREP_TRY(carve_checked(workspace, workspace_bytes, B, total, g.T, &ws));
+  EVREP_TRY(carve_checked(workspace, workspace_bytes, B, total, g.Tb, &ws));
   EVREP_TRY(run_binning(ev, win_offsets, g, ws, REC_IDX, 0, nullptr, (cudaStream_t)stream));
   return launch_event_stack_tile(g, ws, stack_size, out, (cudaStream_t)stream);
   EVREP_GUARD_END
@@ -285,7 +290,7 @@ int evrep_time_surface_batched(const uint16_t* x, const uint16_t* y, const void*
   g.B = B;
   g.total = total;
   Workspace ws;
-  EVREP_TRY(carve_checked(workspace, workspace_bytes, B, total, g.T, &ws));
+  EVREP_TRY(carve_checked(workspace, workspace_bytes, B, total, g.Tb, &ws));
   EVREP_TRY(run_binning(ev, win_offsets, g, ws, REC_T_SNAP, S, indices, (cudaStream_t)stream));
   return launch_time_surface_tile(g, ws, S, tau, out, (cudaStream_t)stream);
   EVREP_GUARD_END
@@ -305,7 +310,7 @@ int evrep_tore_batched(const uint16_t* x, const uint16_t* y, const void* t, int 
   g.B = B;
   g.total = total;
   Workspace ws;
-  EVREP_TRY(carve_checked(workspace, workspace_bytes, B, total, g.T, &ws));
+  EVREP_TRY(carve_checked(workspace, workspace_bytes, B, total, g.Tb, &ws));
   EVREP_TRY(run_binning(ev, win_offsets, g, ws, REC_T_TORE, 0, nullptr, (cudaStream_t)stream));
   return launch_tore_tile(g, ws, k, out, (cudaStream_t)stream);
   EVREP_GUARD_END
@@ -327,6 +332,7 @@ int evrep_voxel_batched(const uint16_t* x, const uint16_t* y, const void* t, int
   g.B = B;
   g.total = total;
   Workspace ws;
+  g.Tb = 0;  // direct scatter: no buckets
   EVREP_TRY(carve_checked(workspace, workspace_bytes, B, 0, 1, &ws));
   return launch_voxel(ev, win_offsets, g, ws, flavour, n_bins, normalize, t0_t1_us, out, (cudaStream_t)stream);
   EVREP_GUARD_END
@@ -345,6 +351,7 @@ int evrep_histogram_batched(const uint16_t* x, const uint16_t* y, const void* t,
   g.B = B;
   g.total = total;
   Workspace ws;
+  g.Tb = 0;  // direct scatter: no buckets
   EVREP_TRY(carve_checked(workspace, workspace_bytes, B, 0, 1, &ws));
   return launch_histogram(ev, win_offsets, g, ws, out, (cudaStream_t)stream);
   EVREP_GUARD_END

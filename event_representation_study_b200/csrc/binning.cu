@@ -1,9 +1,17 @@
-// Spatial pre-bucketing of event windows: count -> scan -> scatter.
+// Spatial pre-bucketing of event windows: count -> column scan -> scan -> scatter.
 //
 // Every tile-based representation starts here.  A window's pixels are cut into tiles of tile_px
 // consecutive linear pixel indices (y*W + x); the events of each window are regrouped so that all
-// events of one (window, tile) bucket are contiguous 8-byte records.  The per-tile kernels then
-// reduce a bucket entirely in shared memory and write their slice of the output exactly once.
+// events of one (window, tile) bucket are contiguous 8-byte records (two buckets per tile, p > 0 first,
+// when the consumer asks for a polarity split).  The per-tile kernels then reduce a bucket entirely in
+// shared memory and write their slice of the output exactly once.
+//
+// The placement is deterministic and needs no global atomics: a CTA owns one super-chunk of SUPER = 16384
+// consecutive events.  k_hist writes that super-chunk's bucket counts as one row of `cc`; k_colscan turns each
+// column of `cc` into the exclusive prefix over the window's super-chunks (the column total is the bucket
+// size); k_scan turns bucket sizes into bucket starts; k_bin loads its row (bucket start + prefix) into
+// shared-memory cursors and each event takes the next slot of its bucket with one shared-memory atomic.
+// Records of different super-chunks therefore stay in stream order inside a bucket.
 //
 // Replaces the per-channel boolean masking / np.concatenate / torch_scatter passes of the reference
 // (representations/representation_search/mixed_density_event_stack.py:111-151, operations.py:39-89)
@@ -20,15 +28,6 @@ namespace evrep {
 // ---------------------------------------------------------------------------------------------
 // small device helpers
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int find_window(const int32_t* __restrict__ chunk_prefix, int B, int chunk) {
-  int lo = 0, hi = B;  // largest b with chunk_prefix[b] <= chunk
-  while (hi - lo > 1) {
-    int mid = (lo + hi) >> 1;
-    if (__ldg(chunk_prefix + mid) <= chunk) lo = mid; else hi = mid;
-  }
-  return lo;
-}
-
 __device__ __forceinline__ void load8_u16(const uint16_t* __restrict__ p, int64_t g0, int64_t total, bool vec, uint32_t (&v)[EPT]) {
   if (vec && g0 + EPT <= total) {
     uint4 q = __ldg(reinterpret_cast<const uint4*>(p + g0));
@@ -137,12 +136,15 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t* a, int n, uin
 }
 
 // ---------------------------------------------------------------------------------------------
-// per-window initialisation
+// per-window initialisation: one CTA per window; also labels the window's super-chunks
 // ---------------------------------------------------------------------------------------------
 template <typename TT>
-__global__ void k_init(const TT* __restrict__ t, const int64_t* __restrict__ offsets, int B, WinParams* __restrict__ wp) {
-  int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
+__global__ void k_init(const TT* __restrict__ t, const int64_t* __restrict__ offsets, const int32_t* __restrict__ sc_prefix,
+                       int32_t* __restrict__ sc_win, WinParams* __restrict__ wp) {
+  const int b = blockIdx.x;
+  if (sc_win)
+    for (int s = sc_prefix[b] + (int)threadIdx.x; s < sc_prefix[b + 1]; s += (int)blockDim.x) sc_win[s] = b;
+  if (threadIdx.x != 0) return;
   WinParams w;
   w.start = offsets[b];
   w.n = offsets[b + 1] - offsets[b];
@@ -217,43 +219,75 @@ __global__ void k_snap_init(const TT* __restrict__ t, const WinParams* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
-// pass 1: bucket sizes
+// pass 1: bucket counts of one super-chunk -> one row of cc.  Counts every event with a valid pixel.
+// HBM: reads x, y (+ p when the buckets are split by polarity).
 // ---------------------------------------------------------------------------------------------
+template <bool SPLIT>
 __global__ void __launch_bounds__(BIN_THREADS) k_hist(const uint16_t* __restrict__ x, const uint16_t* __restrict__ y,
-                                                      const WinParams* __restrict__ wp, const int32_t* __restrict__ chunk_prefix,
-                                                      Geom g, bool vec, uint32_t* __restrict__ hist) {
+                                                      const int8_t* __restrict__ p, const WinParams* __restrict__ wp,
+                                                      const int32_t* __restrict__ sc_prefix, const int32_t* __restrict__ sc_win,
+                                                      const Geom g, const bool vec, uint32_t* __restrict__ cc) {
   extern __shared__ uint32_t sh_hist[];
-  const int b = find_window(chunk_prefix, g.B, blockIdx.x);
-  const int chunk = blockIdx.x - __ldg(chunk_prefix + b);
-  const int64_t start = wp[b].start, end = start + wp[b].n;
-  for (int i = threadIdx.x; i < g.T; i += BIN_THREADS) sh_hist[i] = 0;
-  __syncthreads();
+  const int b = __ldg(sc_win + blockIdx.x);
+  const int scl = blockIdx.x - __ldg(sc_prefix + b);
+  const int64_t start = wp[b].start;
   const int n = (int)wp[b].n;
-  const int64_t c0 = (start & ~(int64_t)(EPT - 1)) + (int64_t)chunk * CHUNK;  // first event of this CTA's chunk
-  const int64_t g0 = c0 + (int64_t)threadIdx.x * EPT;
-  const int idx0 = (int)(g0 - start);
+  for (int i = threadIdx.x; i < g.Tb; i += BIN_THREADS) sh_hist[i] = 0;
+  __syncthreads();
+  const int64_t c0 = (start & ~(int64_t)(EPT - 1)) + (int64_t)scl * SUPER;  // first event of this CTA's super-chunk
   const uint32_t hbase = (uint32_t)__cvta_generic_to_shared(sh_hist);
   const uint32_t Wd = (uint32_t)g.W, Hd = (uint32_t)g.H;
-  if (idx0 < n) {
+#pragma unroll
+  for (int sub = 0; sub < SC_CHUNKS; ++sub) {
+    const int64_t g0 = c0 + (int64_t)sub * CHUNK + (int64_t)threadIdx.x * EPT;
+    const int idx0 = (int)(g0 - start);
+    if (idx0 >= n || idx0 + EPT <= 0) continue;
     uint32_t xs[EPT], ys[EPT];
+    int ps[EPT];
     load8_u16(x, g0, g.total, vec, xs);
     load8_u16(y, g0, g.total, vec, ys);
-    const bool interior = c0 >= start && c0 + CHUNK <= end;  // CTA-uniform: no per-event window test needed
+    if (SPLIT) load8_i8(p, g0, g.total, vec, ps);
+    const bool interior = idx0 >= 0 && idx0 + EPT <= n;
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
       const bool ok = (interior || (uint32_t)(idx0 + e) < (uint32_t)n) && xs[e] < Wd && ys[e] < Hd;
-      if (ok) smem_inc(hbase + (((ys[e] * Wd + xs[e]) >> g.tile_shift) << 2));
+      uint32_t bin = (ys[e] * Wd + xs[e]) >> g.tile_shift;
+      if (SPLIT) bin = (bin << 1) | (ps[e] > 0 ? 0u : 1u);
+      if (ok) smem_inc(hbase + (bin << 2));
     }
   }
   __syncthreads();
-  uint32_t* dst = hist + (size_t)b * g.T;
-  for (int i = threadIdx.x; i < g.T; i += BIN_THREADS) {
-    uint32_t v = sh_hist[i];
-    if (v) atomicAdd(dst + i, v);
-  }
+  uint32_t* dst = cc + (size_t)blockIdx.x * g.Tb;
+  for (int i = threadIdx.x; i < g.Tb; i += BIN_THREADS) dst[i] = sh_hist[i];
 }
 
-// bucket starts: one CTA per window, exclusive scan over its T buckets
+// pass 2: per bucket (column of cc), exclusive prefix over the window's super-chunks; the total is the bucket size
+__global__ void __launch_bounds__(128) k_colscan(uint32_t* __restrict__ cc, const int32_t* __restrict__ sc_prefix, int Tb,
+                                                 uint32_t* __restrict__ hist) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  if (c >= Tb) return;
+  const int s0 = sc_prefix[b], s1 = sc_prefix[b + 1];
+  uint32_t run = 0;
+  uint32_t* col = cc + (size_t)s0 * Tb + c;
+  int s = s0;
+  for (; s + 4 <= s1; s += 4, col += (size_t)4 * Tb) {  // four independent loads in flight
+    const uint32_t v0 = col[0], v1 = col[Tb], v2 = col[(size_t)2 * Tb], v3 = col[(size_t)3 * Tb];
+    col[0] = run;
+    col[Tb] = run + v0;
+    col[(size_t)2 * Tb] = run + v0 + v1;
+    col[(size_t)3 * Tb] = run + v0 + v1 + v2;
+    run += v0 + v1 + v2 + v3;
+  }
+  for (; s < s1; ++s, col += Tb) {
+    const uint32_t v = col[0];
+    col[0] = run;
+    run += v;
+  }
+  hist[(size_t)b * Tb + c] = run;
+}
+
+// bucket starts: one CTA per window, exclusive scan over its Tb buckets
 __global__ void __launch_bounds__(BIN_THREADS) k_scan(const uint32_t* __restrict__ hist, uint32_t* __restrict__ base, int T) {
   __shared__ uint32_t a[MAX_TILES];
   __shared__ uint32_t warp_tot[BIN_THREADS / 32 + 1];
@@ -265,36 +299,34 @@ __global__ void __launch_bounds__(BIN_THREADS) k_scan(const uint32_t* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------
-// pass 2: scatter the events into their buckets as 8-byte records
+// pass 3: scatter the events into their buckets as 8-byte records.  HBM: reads 9 B/event, writes 8 B/event.
 // ---------------------------------------------------------------------------------------------
-template <typename TT, int MODE>
+template <typename TT, int MODE, bool SPLIT>
 __global__ void __launch_bounds__(BIN_THREADS) k_bin(const uint16_t* __restrict__ x, const uint16_t* __restrict__ y,
                                                      const TT* __restrict__ t, const int8_t* __restrict__ p,
                                                      WinParams* __restrict__ wp, const SnapParams* __restrict__ snap,
-                                                     const int32_t* __restrict__ chunk_prefix, Geom g, bool vec,
-                                                     const uint32_t* __restrict__ base, uint32_t* __restrict__ cursor,
-                                                     uint2* __restrict__ records) {
-  extern __shared__ __align__(16) unsigned char sh_raw[];
-  uint2* stage = reinterpret_cast<uint2*>(sh_raw);                            // CHUNK records
-  uint16_t* stile = reinterpret_cast<uint16_t*>(stage + CHUNK);               // CHUNK tile ids
-  uint32_t* cnt = reinterpret_cast<uint32_t*>(stile + CHUNK);                 // T
-  uint32_t* loff = cnt + g.T;                                                 // T
-  uint32_t* gbase = loff + g.T;                                               // T
-  __shared__ uint32_t warp_tot[BIN_THREADS / 32 + 1];
+                                                     const int32_t* __restrict__ sc_prefix, const int32_t* __restrict__ sc_win,
+                                                     const Geom g, const bool vec, const uint32_t* __restrict__ base,
+                                                     const uint32_t* __restrict__ cc, uint2* __restrict__ records) {
+  extern __shared__ uint32_t cursor[];  // Tb: next free slot of every bucket, relative to the window's first record
   __shared__ int sh_tmin, sh_tmax;
   __shared__ uint32_t sh_flags, sh_m1;
   __shared__ int32_t sh_snap_idx[MAX_SNAP];
   __shared__ int sh_nsnap;
 
   const int tid = threadIdx.x;
-  const int b = find_window(chunk_prefix, g.B, blockIdx.x);
-  const int chunk = blockIdx.x - __ldg(chunk_prefix + b);
+  const int b = __ldg(sc_win + blockIdx.x);
+  const int scl = blockIdx.x - __ldg(sc_prefix + b);
   const int64_t start = wp[b].start;
   const int n = (int)wp[b].n;  // < 2^31 - 8 (checked on the host)
   const int64_t t_base = wp[b].t_base;
   const int32_t tlast_rel = wp[b].tlast_rel;
 
-  for (int i = tid; i < g.T; i += BIN_THREADS) cnt[i] = 0;
+  {
+    const uint32_t* brow = base + (size_t)b * g.Tb;
+    const uint32_t* crow = cc + (size_t)blockIdx.x * g.Tb;
+    for (int i = tid; i < g.Tb; i += BIN_THREADS) cursor[i] = __ldg(brow + i) + __ldg(crow + i);
+  }
   if (tid == 0) { sh_tmin = INT_MAX; sh_tmax = INT_MIN; sh_flags = 0; sh_m1 = 0; sh_nsnap = 0; }
   if (MODE == REC_T_SNAP) {
     if (tid < MAX_SNAP) sh_snap_idx[tid] = snap[b].idx[tid];
@@ -304,20 +336,19 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin(const uint16_t* __restrict_
 
   // index boundaries of the SBN windows (mixed_density_event_stack.py:55-74)
   const int n3 = n / 3, s4 = n / 2, s5 = s4 + n / 4, s6 = s5 + n / 8;
-
-  const int64_t c0 = (start & ~(int64_t)(EPT - 1)) + (int64_t)chunk * CHUNK;
-  const int64_t g0 = c0 + (int64_t)tid * EPT;
-  const int idx0 = (int)(g0 - start);  // index of this thread's first event inside the window (may be < 0 at the head)
-  const bool interior = c0 >= start && c0 + CHUNK <= start + n;  // CTA-uniform: every event of the chunk is inside the window
-  const uint32_t cnt_base = (uint32_t)__cvta_generic_to_shared(cnt);
+  const int64_t c0 = (start & ~(int64_t)(EPT - 1)) + (int64_t)scl * SUPER;
+  const uint32_t cur_base = (uint32_t)__cvta_generic_to_shared(cursor);
   const uint32_t Wd = (uint32_t)g.W, Hd = (uint32_t)g.H;
-  uint32_t key[EPT], meta[EPT], tile_rank[EPT];  // tile_rank = tile << 16 | rank inside the CTA's bucket (< CHUNK = 2^12)
+  uint2* dst = records + start;
   int my_tmin = INT_MAX, my_tmax = INT_MIN;
   uint32_t my_flags = 0, my_m1 = 0;
-#pragma unroll
-  for (int e = 0; e < EPT; ++e) tile_rank[e] = 0xffffffffu;
 
-  if (idx0 < n) {
+#pragma unroll 1
+  for (int sub = 0; sub < SC_CHUNKS; ++sub) {
+    const int64_t g0 = c0 + (int64_t)sub * CHUNK + (int64_t)tid * EPT;
+    const int idx0 = (int)(g0 - start);  // index of this thread's first event inside the window (may be < 0 at the head)
+    if (idx0 >= n) break;
+    if (idx0 + EPT <= 0) continue;
     uint32_t xs[EPT], ys[EPT];
     int ps[EPT];
     int64_t ts[EPT];
@@ -326,16 +357,22 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin(const uint16_t* __restrict_
     load8_i8(p, g0, g.total, vec, ps);
     load8_t<TT>(t, g0, g.total, vec, ts);
     int64_t t_prev = (idx0 >= 1) ? (int64_t)__ldg(t + g0 - 1) : LLONG_MIN;
+    const bool interior = idx0 >= 0 && idx0 + EPT <= n;
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
       const int idx = idx0 + e;
       if (!interior && (uint32_t)idx >= (uint32_t)n) continue;
       if (ts[e] < t_prev) my_flags |= EVREP_WF_UNSORTED;
       t_prev = ts[e];
+      if ((xs[e] >= Wd) | (ys[e] >= Hd)) { my_flags |= EVREP_WF_OUT_OF_RANGE; continue; }  // not counted by k_hist: no slot
+      const uint32_t lin = ys[e] * Wd + xs[e];
+      uint32_t bin = lin >> g.tile_shift;
+      if (SPLIT) bin = (bin << 1) | (ps[e] > 0 ? 0u : 1u);
+      const uint32_t slot = smem_fetch_inc(cur_base + (bin << 2));
       const int64_t d = ts[e] - t_base;
-      const bool bad_xy = (xs[e] >= Wd) | (ys[e] >= Hd);
-      const bool bad_t = d >= T_REL_LIMIT || d <= -T_REL_LIMIT;
-      if (bad_xy | bad_t) { my_flags |= (bad_xy ? EVREP_WF_OUT_OF_RANGE : 0u) | (bad_t ? EVREP_WF_T_RANGE : 0u); continue; }
+      uint2 rec = make_uint2(0u, REC_NULL_META);
+      bool keep = true;
+      if (d >= T_REL_LIMIT || d <= -T_REL_LIMIT) { my_flags |= EVREP_WF_T_RANGE; keep = false; }
       const int32_t t_rel = (int32_t)d;
       int pv = ps[e];
       if (pv > 1 || pv < -1) { my_flags |= EVREP_WF_BAD_POLARITY; pv = pv > 0 ? 1 : -1; }
@@ -343,26 +380,24 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin(const uint16_t* __restrict_
       if (MODE == REC_T_WMASK) {
         aux = 1u | (idx < n3 ? 2u : (idx < 2 * n3 ? 4u : (idx < 3 * n3 ? 8u : 0u))) | (idx >= s4 ? 16u : 0u) | (idx >= s5 ? 32u : 0u) |
               (idx >= s6 ? 64u : 0u);
-        my_m1 |= pv == -1 ? aux : 0u;
+        if (keep) my_m1 |= pv == -1 ? aux : 0u;
       } else if (MODE == REC_IDX) {
         k = (uint32_t)idx;
       } else if (MODE == REC_T_SNAP) {
         const int ns = sh_nsnap;
         int s = 0;
         while (s < ns && idx > sh_snap_idx[s]) ++s;
-        if (s >= ns) continue;  // after the last emitted surface: feeds nothing
+        if (s >= ns) keep = false;  // after the last emitted surface: feeds nothing
         aux = (uint32_t)s;
       } else if (MODE == REC_T_TORE) {  // strict `<` against the sample time = last timestamp (tore.py:17)
-        if (t_rel >= tlast_rel) continue;
+        if (t_rel >= tlast_rel) keep = false;
       }
-      my_tmin = min(my_tmin, t_rel);
-      my_tmax = max(my_tmax, t_rel);
-      const uint32_t lin = ys[e] * Wd + xs[e];
-      const uint32_t tile = lin >> g.tile_shift;
-      const uint32_t r = smem_fetch_inc(cnt_base + (tile << 2));
-      tile_rank[e] = (tile << 16) | r;
-      key[e] = k;
-      meta[e] = rec_meta(lin & (uint32_t)(g.tile_px - 1), aux, (uint32_t)pv & 3u);
+      if (keep) {
+        my_tmin = min(my_tmin, t_rel);
+        my_tmax = max(my_tmax, t_rel);
+        rec = make_uint2(k, rec_meta(lin & (uint32_t)(g.tile_px - 1), aux, (uint32_t)pv & 3u));
+      }
+      dst[slot] = rec;
     }
   }
   // CTA-wide reductions of the per-window scalars
@@ -381,48 +416,24 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin(const uint16_t* __restrict_
     if (sh_flags) atomicOr(&wp[b].flags, sh_flags);
     if (sh_m1) atomicOr(&wp[b].has_m1, sh_m1);
   }
-  // reserve global space per bucket, then local offsets
-  const size_t bo = (size_t)b * g.T;
-  for (int i = tid; i < g.T; i += BIN_THREADS) {
-    const uint32_t c = cnt[i];
-    loff[i] = c;
-    if (c) gbase[i] = __ldg(base + bo + i) + atomicAdd(cursor + bo + i, c);
-  }
-  __syncthreads();
-  const uint32_t total = block_exclusive_scan(loff, g.T, warp_tot);
-#pragma unroll
-  for (int e = 0; e < EPT; ++e) {
-    if (tile_rank[e] != 0xffffffffu) {
-      const uint32_t tile = tile_rank[e] >> 16, r = tile_rank[e] & 0xffffu;
-      const uint32_t s = loff[tile] + r;
-      stage[s] = make_uint2(key[e], meta[e]);
-      stile[s] = (uint16_t)tile;
-    }
-  }
-  __syncthreads();
-  uint2* dst = records + start;
-  for (uint32_t i = tid; i < total; i += BIN_THREADS) {
-    const uint32_t tile = stile[i];
-    dst[gbase[tile] + (i - loff[tile])] = stage[i];
-  }
 }
 
-template <typename TT, int MODE>
-static int launch_bin(const Events& ev, const Geom& g, const Workspace& ws, int n_chunks, bool vec, size_t smem, cudaStream_t stream) {
-  EVREP_CUDA_OK(cudaFuncSetAttribute(k_bin<TT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_bin<TT, MODE><<<n_chunks, BIN_THREADS, smem, stream>>>(ev.x, ev.y, (const TT*)ev.t, ev.p, ws.wp, ws.snap, ws.chunk_prefix, g, vec, ws.base,
-                                                           ws.cursor, ws.records);
+template <typename TT, int MODE, bool SPLIT>
+static int launch_bin(const Events& ev, const Geom& g, const Workspace& ws, int n_sc, bool vec, cudaStream_t stream) {
+  k_bin<TT, MODE, SPLIT><<<n_sc, BIN_THREADS, sizeof(uint32_t) * (size_t)g.Tb, stream>>>(
+      ev.x, ev.y, (const TT*)ev.t, ev.p, ws.wp, ws.snap, ws.sc_prefix, ws.sc_win, g, vec, ws.base, ws.cc, ws.records);
   EVREP_CUDA_OK(cudaGetLastError());
   return EVREP_OK;
 }
 template <typename TT>
-static int launch_bin_mode(int mode, const Events& ev, const Geom& g, const Workspace& ws, int n_chunks, bool vec, size_t smem, cudaStream_t stream) {
+static int launch_bin_mode(int mode, const Events& ev, const Geom& g, const Workspace& ws, int n_sc, bool vec, cudaStream_t stream) {
   switch (mode) {
-    case REC_T_WMASK: return launch_bin<TT, REC_T_WMASK>(ev, g, ws, n_chunks, vec, smem, stream);
-    case REC_IDX: return launch_bin<TT, REC_IDX>(ev, g, ws, n_chunks, vec, smem, stream);
-    case REC_T_SNAP: return launch_bin<TT, REC_T_SNAP>(ev, g, ws, n_chunks, vec, smem, stream);
-    case REC_T_TORE: return launch_bin<TT, REC_T_TORE>(ev, g, ws, n_chunks, vec, smem, stream);
-    default: return launch_bin<TT, REC_T_ONLY>(ev, g, ws, n_chunks, vec, smem, stream);
+    case REC_T_WMASK:
+      return g.split ? launch_bin<TT, REC_T_WMASK, true>(ev, g, ws, n_sc, vec, stream) : launch_bin<TT, REC_T_WMASK, false>(ev, g, ws, n_sc, vec, stream);
+    case REC_IDX: return launch_bin<TT, REC_IDX, false>(ev, g, ws, n_sc, vec, stream);
+    case REC_T_SNAP: return launch_bin<TT, REC_T_SNAP, false>(ev, g, ws, n_sc, vec, stream);
+    case REC_T_TORE: return launch_bin<TT, REC_T_TORE, false>(ev, g, ws, n_sc, vec, stream);
+    default: return launch_bin<TT, REC_T_ONLY, false>(ev, g, ws, n_sc, vec, stream);
   }
 }
 
@@ -431,7 +442,7 @@ static int launch_bin_mode(int mode, const Events& ev, const Geom& g, const Work
 // ---------------------------------------------------------------------------------------------
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-int build_chunk_prefix(const int64_t* win_offsets_host, int B, std::vector<int32_t>& prefix) {
+int build_sc_prefix(const int64_t* win_offsets_host, int B, std::vector<int32_t>& prefix) {
   prefix.assign((size_t)B + 1, 0);
   int64_t acc = 0;
   for (int b = 0; b < B; ++b) {
@@ -445,9 +456,9 @@ int build_chunk_prefix(const int64_t* win_offsets_host, int B, std::vector<int32
       return EVREP_EUNSUPPORTED;
     }
     const int64_t a = s & ~(int64_t)(EPT - 1);
-    acc += (e > s) ? (e - a + CHUNK - 1) / CHUNK : 0;
+    acc += (e > s) ? (e - a + SUPER - 1) / SUPER : 0;
     if (acc > INT_MAX) {
-      set_error("batch too large: more than 2^31 chunks");
+      set_error("batch too large: more than 2^31 super-chunks");
       return EVREP_EUNSUPPORTED;
     }
     prefix[(size_t)b + 1] = (int32_t)acc;
@@ -455,26 +466,30 @@ int build_chunk_prefix(const int64_t* win_offsets_host, int B, std::vector<int32
   return EVREP_OK;
 }
 
-// uploads offsets + chunk prefix, initialises the per-window parameters.  Shared by the tile pipeline
-// and the direct-scatter ops.  Returns the number of chunks through *n_chunks.
-int prepare_windows(const Events& ev, const int64_t* win_offsets_host, const Geom& g, const Workspace& ws, int* n_chunks,
+// uploads offsets + super-chunk prefix, initialises the per-window parameters.  Shared by the tile pipeline
+// and the direct-scatter ops (which pass g.Tb == 0: no super-chunk table).  Returns the number of super-chunks.
+int prepare_windows(const Events& ev, const int64_t* win_offsets_host, const Geom& g, const Workspace& ws, int* n_super_chunks,
                     cudaStream_t stream) {
   std::vector<int32_t> prefix;
-  int rc = build_chunk_prefix(win_offsets_host, g.B, prefix);
+  int rc = build_sc_prefix(win_offsets_host, g.B, prefix);
   if (rc) return rc;
   if (win_offsets_host[g.B] > g.total) {
     set_error("win_offsets[B] = %lld exceeds total_events = %lld", (long long)win_offsets_host[g.B], (long long)g.total);
     return EVREP_EINVAL;
   }
-  *n_chunks = prefix[(size_t)g.B];
+  *n_super_chunks = prefix[(size_t)g.B];
+  if ((int64_t)*n_super_chunks > max_super_chunks(g.B, g.total)) {  // cannot happen: ceil((n + 7) / SUPER) <= n / SUPER + 2
+    set_error("internal: super-chunk bound exceeded");
+    return EVREP_EINVAL;
+  }
   // pageable-source async copies are staged before the call returns, so the host vectors may die here
   EVREP_CUDA_OK(cudaMemcpyAsync(ws.offsets, win_offsets_host, sizeof(int64_t) * (size_t)(g.B + 1), cudaMemcpyHostToDevice, stream));
-  EVREP_CUDA_OK(cudaMemcpyAsync(ws.chunk_prefix, prefix.data(), sizeof(int32_t) * (size_t)(g.B + 1), cudaMemcpyHostToDevice, stream));
-  const int thr = 128, blocks = (g.B + thr - 1) / thr;
+  EVREP_CUDA_OK(cudaMemcpyAsync(ws.sc_prefix, prefix.data(), sizeof(int32_t) * (size_t)(g.B + 1), cudaMemcpyHostToDevice, stream));
+  int32_t* sc_win = g.Tb > 0 ? ws.sc_win : nullptr;
   if (ev.t_bytes == 4)
-    k_init<int32_t><<<blocks, thr, 0, stream>>>((const int32_t*)ev.t, ws.offsets, g.B, ws.wp);
+    k_init<int32_t><<<g.B, 64, 0, stream>>>((const int32_t*)ev.t, ws.offsets, ws.sc_prefix, sc_win, ws.wp);
   else
-    k_init<int64_t><<<blocks, thr, 0, stream>>>((const int64_t*)ev.t, ws.offsets, g.B, ws.wp);
+    k_init<int64_t><<<g.B, 64, 0, stream>>>((const int64_t*)ev.t, ws.offsets, ws.sc_prefix, sc_win, ws.wp);
   EVREP_CUDA_OK(cudaGetLastError());
   return EVREP_OK;
 }
@@ -483,11 +498,15 @@ bool events_vectorisable(const Events& ev) { return aligned16(ev.x) && aligned16
 
 int run_binning(const Events& ev, const int64_t* win_offsets_host, const Geom& g, const Workspace& ws, int rec_mode, int n_snap,
                 const int64_t* snap_indices_host, cudaStream_t stream) {
-  int n_chunks = 0;
+  int n_sc = 0;
   prof_next_call();
-  int rc = prepare_windows(ev, win_offsets_host, g, ws, &n_chunks, stream);
+  if (g.Tb < 1 || g.Tb > MAX_TILES) {
+    set_error("internal: %d buckets per window", g.Tb);
+    return EVREP_EINVAL;
+  }
+  int rc = prepare_windows(ev, win_offsets_host, g, ws, &n_sc, stream);
   if (rc) return rc;
-  EVREP_CUDA_OK(cudaMemsetAsync(ws.hist, 0, sizeof(uint32_t) * ((size_t)g.B * g.T * 2 + 64), stream));  // hist + cursor + tickets
+  EVREP_CUDA_OK(cudaMemsetAsync(ws.ticket, 0, sizeof(uint32_t) * 64, stream));
   const bool vec = events_vectorisable(ev);
 
   if (rec_mode == REC_T_SNAP) {
@@ -502,21 +521,28 @@ int run_binning(const Events& ev, const int64_t* win_offsets_host, const Geom& g
       k_snap_init<int64_t><<<g.B, 32, 0, stream>>>((const int64_t*)ev.t, ws.wp, user, n_snap, ws.snap);
     EVREP_CUDA_OK(cudaGetLastError());
   }
-  if (n_chunks > 0) {
+  if (n_sc > 0) {
     prof_begin(EVREP_K_COUNT, stream);
-    k_hist<<<n_chunks, BIN_THREADS, sizeof(uint32_t) * (size_t)g.T, stream>>>(ev.x, ev.y, ws.wp, ws.chunk_prefix, g, vec, ws.hist);
+    if (g.split)
+      k_hist<true><<<n_sc, BIN_THREADS, sizeof(uint32_t) * (size_t)g.Tb, stream>>>(ev.x, ev.y, ev.p, ws.wp, ws.sc_prefix, ws.sc_win, g, vec, ws.cc);
+    else
+      k_hist<false><<<n_sc, BIN_THREADS, sizeof(uint32_t) * (size_t)g.Tb, stream>>>(ev.x, ev.y, ev.p, ws.wp, ws.sc_prefix, ws.sc_win, g, vec, ws.cc);
     prof_end(EVREP_K_COUNT, stream);
     EVREP_CUDA_OK(cudaGetLastError());
   }
   prof_begin(EVREP_K_SCAN, stream);
-  k_scan<<<g.B, BIN_THREADS, 0, stream>>>(ws.hist, ws.base, g.T);
+  // bucket sizes (also for windows without events: an empty column range gives 0), then bucket starts
+  for (int b0 = 0; b0 < g.B; b0 += 65535) {
+    const int nb = std::min(65535, g.B - b0);
+    k_colscan<<<dim3((unsigned)((g.Tb + 127) / 128), (unsigned)nb), 128, 0, stream>>>(ws.cc, ws.sc_prefix + b0, g.Tb, ws.hist + (size_t)b0 * g.Tb);
+  }
+  k_scan<<<g.B, BIN_THREADS, 0, stream>>>(ws.hist, ws.base, g.Tb);
   prof_end(EVREP_K_SCAN, stream);
   EVREP_CUDA_OK(cudaGetLastError());
-  if (n_chunks > 0) {
+  if (n_sc > 0) {
     prof_begin(EVREP_K_BIN, stream);
-    const size_t smem = (size_t)CHUNK * (sizeof(uint2) + sizeof(uint16_t)) + 3 * sizeof(uint32_t) * (size_t)g.T;
-    const int rc2 = ev.t_bytes == 4 ? launch_bin_mode<int32_t>(rec_mode, ev, g, ws, n_chunks, vec, smem, stream)
-                                    : launch_bin_mode<int64_t>(rec_mode, ev, g, ws, n_chunks, vec, smem, stream);
+    const int rc2 = ev.t_bytes == 4 ? launch_bin_mode<int32_t>(rec_mode, ev, g, ws, n_sc, vec, stream)
+                                    : launch_bin_mode<int64_t>(rec_mode, ev, g, ws, n_sc, vec, stream);
     if (rc2) return rc2;
     prof_end(EVREP_K_BIN, stream);
     EVREP_CUDA_OK(cudaGetLastError());

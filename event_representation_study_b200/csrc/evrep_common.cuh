@@ -15,8 +15,10 @@ namespace evrep {
 // ------------------------------------------------------------------------------------------------
 constexpr int BIN_THREADS = 512;
 constexpr int EPT = 8;
-constexpr int CHUNK = BIN_THREADS * EPT;  // 4096 events per CTA
-constexpr int MAX_TILES = 4096;           // tiles per window (shared-memory histogram size bound)
+constexpr int CHUNK = BIN_THREADS * EPT;  // 4096 events per CTA iteration
+constexpr int SC_CHUNKS = 4;
+constexpr int SUPER = CHUNK * SC_CHUNKS;  // 16384 events per CTA ("super-chunk"): the unit of the counting / scatter passes
+constexpr int MAX_TILES = 4096;           // buckets per window (shared-memory histogram size bound)
 constexpr int MIN_TILE_PX = 256;
 constexpr int MAX_SNAP = 16;              // time-surface snapshots per window
 constexpr int TILE_THREADS = 512;
@@ -30,8 +32,12 @@ enum RecMode : int {
   REC_T_TORE = 3,   // key = t_rel, events with t >= t_last dropped  (TORE)
   REC_T_ONLY = 4,   // key = t_rel, aux = 0: windows are derived from t later (mixed density, SBT)
 };
-// meta word: [15:0] pixel inside tile, [23:16] aux, [25:24] polarity code (p & 3: 0 -> 0, 1 -> +1, 3 -> -1)
+// meta word: [15:0] pixel inside tile, [23:16] aux, [25:24] polarity code (p & 3: 0 -> 0, 1 -> +1, 3 -> -1; 2 = null record)
 __host__ __device__ inline uint32_t rec_meta(uint32_t pix, uint32_t aux, uint32_t pc) { return pix | (aux << 16) | (pc << 24); }
+// A null record fills the slot of an event that was counted (valid x, y) but then dropped (timestamp out of range, after
+// the last time-surface snapshot, at the TORE sample time): polarity code 2, member of no window.  Tile kernels skip it.
+constexpr uint32_t REC_NULL_META = 2u << 24;
+__host__ __device__ inline bool rec_is_null(uint32_t meta) { return ((meta >> 24) & 3u) == 2u; }
 
 struct WinParams {  // one per window, lives at the start of the workspace
   int64_t start;    // absolute index of the first event
@@ -54,6 +60,8 @@ struct SnapParams {  // time surface, one per window
 struct Geom {
   int B, H, W, HW;
   int tile_shift, tile_px, T;  // tile = contiguous range of tile_px linear pixel indices; T tiles per window
+  int split;                   // 1: every tile has two buckets, p > 0 first, then the rest (mixed-density static kernels)
+  int Tb;                      // buckets per window = T << split
   int64_t total;               // total events in the batch
   unsigned long long t_magic;  // ceil(2^44 / T): id / T == (id * t_magic) >> 44 for id < 2^32, T <= 4096
 };
@@ -61,12 +69,13 @@ struct Geom {
 struct Workspace {  // device pointers carved out of the caller's buffer
   WinParams* wp;
   int64_t* offsets;
-  int32_t* chunk_prefix;
-  uint32_t* hist;    // B*T   bucket sizes (upper bound, from the counting pass)
-  uint32_t* cursor;  // B*T   records actually written
-  uint32_t* ticket;  // 64 words after cursor (zeroed with it): work counters of persistent kernels
-  uint32_t* base;    // B*T   bucket start, relative to the window's first record
-  SnapParams* snap;  // B
+  int32_t* sc_prefix;  // B+1   first super-chunk of each window
+  int32_t* sc_win;     // n_sc  window of each super-chunk
+  uint32_t* ticket;    // 64 words: work counters of persistent kernels
+  uint32_t* hist;      // B*Tb  bucket sizes (events with valid x, y; dropped ones keep a null record)
+  uint32_t* base;      // B*Tb  bucket start, relative to the window's first record
+  uint32_t* cc;        // n_sc*Tb  per super-chunk bucket counts, then (k_colscan) their exclusive prefix inside the bucket
+  SnapParams* snap;    // B
   int64_t* snap_in;  // B*MAX_SNAP caller-supplied snapshot indices
   double* stats;     // B*4   voxel normalisation sums
   uint2* records;    // total events
@@ -76,6 +85,7 @@ struct Workspace {  // device pointers carved out of the caller's buffer
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // Carves the workspace; with base == nullptr only computes the size.
+inline int64_t max_super_chunks(int B, int64_t total) { return total / SUPER + 2 * (int64_t)B + 1; }
 inline Workspace carve(void* basep, int B, int64_t total, int T) {
   Workspace w;
   size_t off = 0;
@@ -87,11 +97,13 @@ inline Workspace carve(void* basep, int B, int64_t total, int T) {
   };
   w.wp = (WinParams*)take(sizeof(WinParams) * (size_t)B);
   w.offsets = (int64_t*)take(sizeof(int64_t) * (size_t)(B + 1));
-  w.chunk_prefix = (int32_t*)take(sizeof(int32_t) * (size_t)(B + 1));
-  w.hist = (uint32_t*)take(sizeof(uint32_t) * ((size_t)B * T * 2 + 64));
-  w.cursor = w.hist ? w.hist + (size_t)B * T : nullptr;
-  w.ticket = w.hist ? w.hist + (size_t)B * T * 2 : nullptr;
+  const size_t n_sc = total > 0 ? (size_t)max_super_chunks(B, total) : 1;
+  w.sc_prefix = (int32_t*)take(sizeof(int32_t) * (size_t)(B + 1));
+  w.sc_win = (int32_t*)take(sizeof(int32_t) * n_sc);
+  w.ticket = (uint32_t*)take(sizeof(uint32_t) * 64);
+  w.hist = (uint32_t*)take(sizeof(uint32_t) * (size_t)B * T);
   w.base = (uint32_t*)take(sizeof(uint32_t) * (size_t)B * T);
+  w.cc = (uint32_t*)take(sizeof(uint32_t) * n_sc * (size_t)T);
   w.snap = (SnapParams*)take(sizeof(SnapParams) * (size_t)B);
   w.snap_in = (int64_t*)take(sizeof(int64_t) * (size_t)B * MAX_SNAP);
   w.stats = (double*)take(sizeof(double) * 4 * (size_t)B);
@@ -162,7 +174,7 @@ struct Events {
 int run_binning(const Events& ev, const int64_t* win_offsets_host, const Geom& g, const Workspace& ws, int rec_mode,
                 int n_snap, const int64_t* snap_indices_host, cudaStream_t stream);
 
-int prepare_windows(const Events& ev, const int64_t* win_offsets_host, const Geom& g, const Workspace& ws, int* n_chunks,
+int prepare_windows(const Events& ev, const int64_t* win_offsets_host, const Geom& g, const Workspace& ws, int* n_super_chunks,
                     cudaStream_t stream);
 bool events_vectorisable(const Events& ev);
 

@@ -108,9 +108,10 @@ __device__ __forceinline__ float md_value(const MdPlan& P, const MdChan& ch, con
     const int call = c1 + cn + (int)md_cnt(P, P.grp[ch.g_oth], a);
     if (call == 0) return 0.f;
     if (ch.agg == EVREP_AGG_MEAN) return __fdividef((float)(c1 - cm), (float)call);
-    if (ch.agg == EVREP_AGG_VARIANCE) {  // mean(p^2) - mean(p)^2 = ((c1+cm) call - (c1-cm)^2) / call^2, numerator exact in fp64
-      const double dc = (double)call, dd = (double)(c1 - cm);
-      return __fdividef((float)fma((double)(c1 + cm), dc, -dd * dd), (float)(dc * dc));
+    if (ch.agg == EVREP_AGG_VARIANCE) {  // mean(p^2) - mean(p)^2 = ((c1+cm) call - (c1-cm)^2) / call^2, exact in 64-bit integers
+      const long long dd = (long long)(c1 - cm);
+      const unsigned long long num = (unsigned long long)(uint32_t)(c1 + cm) * (uint32_t)call - (unsigned long long)(dd * dd);
+      return __fdividef(__ull2float_rn(num), __ull2float_rn((unsigned long long)(uint32_t)call * (uint32_t)call));
     }
     return c1 > 0 ? 1.f : (call - c1 - cm > 0 ? 0.f : -1.f);  // max of the raw polarities
   }
@@ -125,10 +126,14 @@ __device__ __forceinline__ float md_value(const MdPlan& P, const MdChan& ch, con
     const uint32_t v = a[G.w_max] - 1u;
     return (v == delta_u && delta_u) ? 1.f : (float)v * inv_delta;  // the window's last event maps to exactly 1
   }
-  const double st = md_limb_sum(a, G.w_st, P.nl1, P.lw);
-  if (ch.agg == EVREP_AGG_SUM) return (float)st * inv_delta;
+  // sum of t: below 2^63 (fewer than 2^32 events of t < 2^31), exact in 64-bit integers
+  unsigned long long sti = a[G.w_st + P.nl1 - 1];
+  for (int l = P.nl1 - 2; l >= 0; --l) sti = (sti << P.lw) + a[G.w_st + l];
+  if (ch.agg == EVREP_AGG_SUM) return __ull2float_rn(sti) * inv_delta;
+  if (ch.agg == EVREP_AGG_MEAN) return __fdividef(__ull2float_rn(sti), __ull2float_rn((unsigned long long)c * delta_u));
+  if (c == 1u) return 0.f;  // a single event: t_s^2 - t_s^2, exactly 0 in the reference too
+  const double st = (double)sti;
   const double cd = (double)c * delta;
-  if (ch.agg == EVREP_AGG_MEAN) return __fdividef((float)st, (float)cd);
   const double st2 = md_limb_sum(a, G.w_st2, P.nl2, P.lw);
   // mean(t_s^2) - mean(t_s)^2 = (c sum(t^2) - sum(t)^2) / (c delta)^2
   return __fdividef((float)fma((double)c, st2, -st * st), (float)(cd * cd));
@@ -136,7 +141,7 @@ __device__ __forceinline__ float md_value(const MdPlan& P, const MdChan& ch, con
 
 template <int CMAX>
 __global__ void __launch_bounds__(TILE_THREADS) k_md_tile(const uint2* __restrict__ records, const uint32_t* __restrict__ base,
-                                                          const uint32_t* __restrict__ cursor, const WinParams* __restrict__ wp,
+                                                          const uint32_t* __restrict__ hist, const WinParams* __restrict__ wp,
                                                           const __grid_constant__ MdPlan P, const Geom g, float* __restrict__ out) {
   extern __shared__ __align__(128) uint32_t acc[];
   const int tid = threadIdx.x;
@@ -152,7 +157,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_md_tile(const uint2* __restric
     for (int i = tid; i < n4; i += TILE_THREADS) a4[i] = make_uint4(0, 0, 0, 0);
   }
   const WinParams w = wp[b];
-  const uint32_t count = cursor[blockIdx.x];
+  const uint32_t count = hist[blockIdx.x];
   const uint2* rec = records + w.start + base[blockIdx.x];
   const int32_t tmin = w.tmin_rel;
   const uint32_t delta_u = (w.tmax_rel >= w.tmin_rel) ? (uint32_t)(w.tmax_rel - w.tmin_rel) : 0u;
@@ -163,6 +168,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_md_tile(const uint2* __restric
 
   for (uint32_t i = tid; i < count; i += TILE_THREADS) {
     const uint2 r = __ldg(rec + i);
+    if (rec_is_null(r.y)) continue;
     uint32_t* a = acc + (r.y & 0xffffu) * stride;
     const uint32_t pc = (r.y >> 24) & 3u;
     const uint32_t tt = (uint32_t)((int32_t)r.x - tmin);  // t - t_min, < 2^31
@@ -252,34 +258,39 @@ __global__ void __launch_bounds__(TILE_THREADS) k_md_tile(const uint2* __restric
 // compile-time specialised variant (ERGO-12): same algorithm, the plan is a constant expression, so every
 // group test, word index, limb count and channel formula is folded and the loops disappear.
 // ---------------------------------------------------------------------------------------------
-template <typename PS, int GI>
+// CLS selects the groups an event can belong to: 0 = any (buckets not split by polarity), 1 = the event has p > 0
+// (groups of class "all" and "positive"), 2 = it has not (classes "all", "negative", "neither").
+template <typename PS, int GI, int CLS>
 __device__ __forceinline__ void md_acc_group(uint32_t* a, uint32_t M, uint32_t tt, unsigned long long tt2, uint32_t& pres) {
   constexpr MdGroup G = PS::value.grp[GI];
   constexpr int LW = PS::value.lw, NL1 = PS::value.nl1, NL2 = PS::value.nl2;
   constexpr uint32_t MASK = (1u << LW) - 1u;
+  constexpr int gcls = G.bit >> 3;
+  if constexpr ((CLS == 1 && gcls >= 2) || (CLS == 2 && gcls == 1)) return;
+  if constexpr (G.flags == G_PRES) {  // presence only: no branch
+    pres |= ((M >> G.bit) & 1u) << G.pres_bit;
+    return;
+  }
   if (!((M >> G.bit) & 1u)) return;
   if constexpr (G.flags & G_CNT) atomicAdd(a + G.w_cnt, 1u << G.cnt_shift);
   if constexpr (G.flags & G_PRES) pres |= 1u << G.pres_bit;
   if constexpr (G.flags & G_MAX) atomicMax(a + G.w_max, tt + 1u);
   if constexpr (G.flags & G_ST) {
 #pragma unroll
-    for (int l = 0; l < NL1; ++l) {
-      const uint32_t limb = (tt >> (l * LW)) & MASK;
-      if (limb) atomicAdd(a + G.w_st + l, limb);
-    }
+    for (int l = 0; l < NL1; ++l) atomicAdd(a + G.w_st + l, (tt >> (l * LW)) & MASK);  // adding a zero limb is harmless
   }
   if constexpr (G.flags & G_ST2) {
 #pragma unroll
     for (int l = 0; l < NL2; ++l) {
       const uint32_t limb = (uint32_t)(tt2 >> (l * LW)) & MASK;
-      if (limb) atomicAdd(a + G.w_st2 + l, limb);
+      if (l < 2 || limb) atomicAdd(a + G.w_st2 + l, limb);  // the high limbs of t^2 are zero for most events
     }
   }
 }
-template <typename PS, int... GI>
+template <typename PS, int CLS, int... GI>
 __device__ __forceinline__ void md_acc_all(uint32_t* a, uint32_t M, uint32_t tt, uint32_t& pres, std::integer_sequence<int, GI...>) {
   const unsigned long long tt2 = (unsigned long long)tt * (unsigned long long)tt;
-  (md_acc_group<PS, GI>(a, M, tt, tt2, pres), ...);
+  (md_acc_group<PS, GI, CLS>(a, M, tt, tt2, pres), ...);
 }
 
 template <typename PS, int CI>
@@ -294,21 +305,37 @@ __device__ __forceinline__ void md_finalise_static(const uint32_t* a, float inv_
   ((o[CI] = md_value_static<PS, CI>(a, inv_delta, delta, delta_u, has_m1)), ...);
 }
 
-template <typename PS>
+template <typename PS, int CLS>
 __device__ __forceinline__ void md_accumulate_static(uint32_t* acc, const uint2 r, int32_t tmin, uint32_t not_m1) {
   constexpr int STRIDE = PS::value.stride, G = PS::value.G;
   uint32_t* a = acc + (r.y & 0xffffu) * STRIDE;
   const uint32_t pc = (r.y >> 24) & 3u;
   const uint32_t tt = (uint32_t)((int32_t)r.x - tmin);
-  const uint32_t wmask = (r.y >> 16) & 0xffu;
-  const uint32_t posm = (pc == 1u) ? wmask : 0u;
-  const uint32_t negm = (pc == 3u) ? wmask : (pc == 0u ? (wmask & not_m1) : 0u);
-  const uint32_t M = wmask | (posm << 8) | (negm << 16) | ((wmask & ~(posm | negm)) << 24);
+  const uint32_t wmask = (r.y >> 16) & 0xffu;  // 0 for null and padding records: member of no window
+  uint32_t M;
+  if constexpr (CLS == 1) {
+    M = wmask | (wmask << 8);
+  } else {
+    // "negative" events of a window: p == -1, or p == 0 when the window holds no -1 (operations.py:59-61,78-80)
+    const uint32_t posm = (CLS == 0 && pc == 1u) ? wmask : 0u;
+    const uint32_t negm = (pc == 3u) ? wmask : (pc == 0u ? (wmask & not_m1) : 0u);
+    M = wmask | (posm << 8) | (negm << 16) | ((wmask & ~(posm | negm)) << 24);
+  }
   uint32_t pres = 0;
-  md_acc_all<PS>(a, M, tt, pres, std::make_integer_sequence<int, G>{});
+  md_acc_all<PS, CLS>(a, M, tt, pres, std::make_integer_sequence<int, G>{});
   if (pres) {
     uint32_t* pw = a + PS::value.w_pres;
     if ((*(volatile uint32_t*)pw & pres) != pres) atomicOr(pw, pres);
+  }
+}
+// record i of a bucket pair whose first n_pos records are the p > 0 events (n_pos = 0xffffffff: not split, any class)
+template <typename PS, bool SPLIT>
+__device__ __forceinline__ void md_accumulate_at(uint32_t* acc, const uint2 r, uint32_t i, uint32_t n_pos, int32_t tmin, uint32_t not_m1) {
+  if constexpr (SPLIT) {
+    if (i < n_pos) md_accumulate_static<PS, 1>(acc, r, tmin, not_m1);
+    else md_accumulate_static<PS, 2>(acc, r, tmin, not_m1);
+  } else {
+    md_accumulate_static<PS, 0>(acc, r, tmin, not_m1);
   }
 }
 
@@ -321,19 +348,28 @@ __device__ __forceinline__ void md_accumulate_static(uint32_t* acc, const uint2 
 // early, so no global-load latency sits on the critical path after the first bucket.
 struct TileHdr {
   int b, pix0;
-  uint32_t count, has_m1, delta_u;
+  uint32_t count, n_pos, has_m1, delta_u;
   int32_t tmin;
   const uint2* rec;
 };
 
+template <bool SPLIT>
 __device__ __forceinline__ TileHdr md_load_hdr(int id, const Geom& g, int TP, const uint2* records, const uint32_t* base,
-                                               const uint32_t* cursor, const WinParams* wp) {
+                                               const uint32_t* hist, const WinParams* wp) {
   TileHdr h;
   h.b = (int)(((unsigned long long)(uint32_t)id * g.t_magic) >> 44);  // id / T, exact for id < 2^32 and T <= 4096
   h.pix0 = (id - h.b * g.T) * TP;
   const WinParams* w = wp + h.b;
-  h.count = __ldg(cursor + id);
-  h.rec = records + w->start + __ldg(base + id);
+  if constexpr (SPLIT) {  // two buckets per tile, p > 0 first, contiguous
+    const uint2 c2 = __ldg(reinterpret_cast<const uint2*>(hist) + id);
+    h.n_pos = c2.x;
+    h.count = c2.x + c2.y;
+    h.rec = records + w->start + __ldg(base + 2 * id);
+  } else {
+    h.n_pos = 0xffffffffu;
+    h.count = __ldg(hist + id);
+    h.rec = records + w->start + __ldg(base + id);
+  }
   h.tmin = w->tmin_rel;
   const int32_t tmax = w->tmax_rel;
   h.delta_u = tmax >= h.tmin ? (uint32_t)(tmax - h.tmin) : 0u;
@@ -381,9 +417,9 @@ __device__ __forceinline__ void md_wait_store() {  // the four issuing threads: 
 
 // LIGHT_ONLY: the plan is a packed one (16-bit counters / limbs); buckets with >= 65536 events are left to
 // k_md_tile_heavy, which runs the wide plan on them afterwards.
-template <typename PS, int TP, bool LIGHT_ONLY>
+template <typename PS, int TP, bool LIGHT_ONLY, bool SPLIT>
 __global__ void __launch_bounds__(TILE_THREADS, (PS::value.stride * TP * 4 <= 74 * 1024) ? 3 : 2)
-    k_md_tile_static(const uint2* __restrict__ records, const uint32_t* __restrict__ base, const uint32_t* __restrict__ cursor,
+    k_md_tile_static(const uint2* __restrict__ records, const uint32_t* __restrict__ base, const uint32_t* __restrict__ hist,
                      const WinParams* __restrict__ wp, const Geom g, uint32_t* __restrict__ ticket, float* __restrict__ out) {
   extern __shared__ __align__(128) uint32_t acc[];
   __shared__ int s_next;
@@ -399,7 +435,7 @@ __global__ void __launch_bounds__(TILE_THREADS, (PS::value.stride * TP * 4 <= 74
   int cur = blockIdx.x, nxt = blockIdx.x + (int)gridDim.x;
   if (cur >= n_tiles) return;
 
-  TileHdr h = md_load_hdr(cur, g, TP, records, base, cursor, wp);
+  TileHdr h = md_load_hdr<SPLIT>(cur, g, TP, records, base, hist, wp);
   uint2 pre[PRE];
 #pragma unroll
   for (int j = 0; j < PRE; ++j) {
@@ -428,15 +464,16 @@ __global__ void __launch_bounds__(TILE_THREADS, (PS::value.stride * TP * 4 <= 74
     }
     const bool more = nxt < n_tiles;
     TileHdr hn = h;
-    if (more) hn = md_load_hdr(nxt, g, TP, records, base, cursor, wp);  // in flight during the atomics below
+    if (more) hn = md_load_hdr<SPLIT>(nxt, g, TP, records, base, hist, wp);  // in flight during the atomics below
     __syncthreads();
 
     if (!skip) {
       const uint32_t not_m1 = ~h.has_m1;
 #pragma unroll
       for (int j = 0; j < PRE; ++j)
-        if (pre[j].y) md_accumulate_static<PS>(acc, pre[j], h.tmin, not_m1);
-      for (uint32_t i = tid + PRE * TILE_THREADS; i < h.count; i += TILE_THREADS) md_accumulate_static<PS>(acc, __ldg(h.rec + i), h.tmin, not_m1);
+        if (pre[j].y) md_accumulate_at<PS, SPLIT>(acc, pre[j], tid + j * TILE_THREADS, h.n_pos, h.tmin, not_m1);
+      for (uint32_t i = tid + PRE * TILE_THREADS; i < h.count; i += TILE_THREADS)
+        md_accumulate_at<PS, SPLIT>(acc, __ldg(h.rec + i), i, h.n_pos, h.tmin, not_m1);
     }
 #pragma unroll
     for (int j = 0; j < PRE; ++j) {  // next bucket's records: in flight during finalise + store
@@ -462,9 +499,9 @@ __global__ void __launch_bounds__(TILE_THREADS, (PS::value.stride * TP * 4 <= 74
 }
 
 // The buckets a packed plan must not touch (>= 65536 events: one hot tile), with the wide plan, one at a time.
-template <typename PS, int TP>
+template <typename PS, int TP, bool SPLIT>
 __global__ void __launch_bounds__(TILE_THREADS, 2) k_md_tile_heavy(const uint2* __restrict__ records, const uint32_t* __restrict__ base,
-                                                                   const uint32_t* __restrict__ cursor, const WinParams* __restrict__ wp,
+                                                                   const uint32_t* __restrict__ hist, const WinParams* __restrict__ wp,
                                                                    const Geom g, float* __restrict__ out) {
   extern __shared__ __align__(128) uint32_t acc[];
   __shared__ uint32_t s_heavy[TILE_THREADS / 32];
@@ -473,7 +510,8 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_md_tile_heavy(const uint2* 
   const int n_tiles = g.B * g.T;
   for (int base_id = blockIdx.x * TILE_THREADS; base_id < n_tiles; base_id += gridDim.x * TILE_THREADS) {
     const int id = base_id + tid;
-    const bool heavy = id < n_tiles && __ldg(cursor + id) >= MD_PACKED_LIMIT;
+    bool heavy = false;
+    if (id < n_tiles) heavy = (SPLIT ? __ldg(hist + 2 * id) + __ldg(hist + 2 * id + 1) : __ldg(hist + id)) >= MD_PACKED_LIMIT;
     const uint32_t m = __ballot_sync(0xffffffffu, heavy);
     if ((tid & 31) == 0) s_heavy[tid >> 5] = m;
     __syncthreads();
@@ -482,12 +520,12 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_md_tile_heavy(const uint2* 
       while (bits) {
         const int tile_id = base_id + wd * 32 + (__ffs(bits) - 1);
         bits &= bits - 1;
-        const TileHdr h = md_load_hdr(tile_id, g, TP, records, base, cursor, wp);
+        const TileHdr h = md_load_hdr<SPLIT>(tile_id, g, TP, records, base, hist, wp);
         uint4* a4 = reinterpret_cast<uint4*>(acc);
         for (int i = tid; i < (STRIDE * TP + 3) / 4; i += TILE_THREADS) a4[i] = make_uint4(0, 0, 0, 0);
         __syncthreads();
         const uint32_t not_m1 = ~h.has_m1;
-        for (uint32_t i = tid; i < h.count; i += TILE_THREADS) md_accumulate_static<PS>(acc, __ldg(h.rec + i), h.tmin, not_m1);
+        for (uint32_t i = tid; i < h.count; i += TILE_THREADS) md_accumulate_at<PS, SPLIT>(acc, __ldg(h.rec + i), i, h.n_pos, h.tmin, not_m1);
         __syncthreads();
         md_finalise_store<PS, TP>(acc, h, g, out);
         md_wait_store();
@@ -513,7 +551,7 @@ static_assert(ErgoPlan<2, 16, true>::value.words == 16 && ErgoPlan<2, 16, true>:
 static_assert(ErgoPlan<2, 12, false>::value.words == 24, "wide ERGO-12 v2 plan at 2^20 events: 24 words per pixel");
 
 // ERGO-12 at the standard 1024-pixel tile: packed plan on every bucket below 65536 events, wide plan on the rest
-template <int VER, int LW>
+template <int VER, int LW, bool SPLIT>
 static int launch_static(const Geom& g, const Workspace& ws, float* out, cudaStream_t stream) {
   constexpr int TP = 1024;
   using Packed = ErgoPlan<VER, 16, true>;
@@ -521,8 +559,8 @@ static int launch_static(const Geom& g, const Workspace& ws, float* out, cudaStr
   int n_sm = 0;
   EVREP_TRY_RC(sm_count(&n_sm));
   const int n_tiles = g.B * g.T;
-  auto light = k_md_tile_static<Packed, TP, true>;
-  auto heavy = k_md_tile_heavy<Wide, TP>;
+  auto light = k_md_tile_static<Packed, TP, true, SPLIT>;
+  auto heavy = k_md_tile_heavy<Wide, TP, SPLIT>;
   const size_t smem_l = align_up((size_t)Packed::value.stride * TP * 4, 128), smem_h = align_up((size_t)Wide::value.stride * TP * 4, 128);
   EVREP_CUDA_OK(cudaFuncSetAttribute(light, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
   EVREP_CUDA_OK(cudaFuncSetAttribute(heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
@@ -531,9 +569,9 @@ static int launch_static(const Geom& g, const Workspace& ws, float* out, cudaStr
   if (per_sm < 1) per_sm = 1;
   const int grid = n_tiles < per_sm * n_sm ? n_tiles : per_sm * n_sm;
   prof_begin(EVREP_K_TILE, stream);
-  light<<<grid, TILE_THREADS, smem_l, stream>>>(ws.records, ws.base, ws.cursor, ws.wp, g, ws.ticket, out);
+  light<<<grid, TILE_THREADS, smem_l, stream>>>(ws.records, ws.base, ws.hist, ws.wp, g, ws.ticket, out);
   heavy<<<(n_tiles + TILE_THREADS - 1) / TILE_THREADS < n_sm ? (n_tiles + TILE_THREADS - 1) / TILE_THREADS : n_sm, TILE_THREADS, smem_h, stream>>>(
-      ws.records, ws.base, ws.cursor, ws.wp, g, out);
+      ws.records, ws.base, ws.hist, ws.wp, g, out);
   prof_end(EVREP_K_TILE, stream);
   EVREP_CUDA_OK(cudaGetLastError());
   return EVREP_OK;
@@ -579,7 +617,7 @@ int launch_md_tile(const Geom& g, const Workspace& ws, const MdPlan& plan, const
   switch (g.tile_px == 1024 ? plan.static_id : 0) {
 #define EVREP_STATIC_CASE(VER, LW) \
   case VER * 100 + LW:             \
-    return launch_static<VER, LW>(g, ws, out, stream);
+    return g.split ? launch_static<VER, LW, true>(g, ws, out, stream) : launch_static<VER, LW, false>(g, ws, out, stream);
     EVREP_STATIC_CASE(2, 16) EVREP_STATIC_CASE(2, 14) EVREP_STATIC_CASE(2, 12) EVREP_STATIC_CASE(2, 10) EVREP_STATIC_CASE(2, 8)
     EVREP_STATIC_CASE(1, 16) EVREP_STATIC_CASE(1, 14) EVREP_STATIC_CASE(1, 12) EVREP_STATIC_CASE(1, 10) EVREP_STATIC_CASE(1, 8)
 #undef EVREP_STATIC_CASE
@@ -588,7 +626,7 @@ int launch_md_tile(const Geom& g, const Workspace& ws, const MdPlan& plan, const
   auto kern = plan.C <= 12 ? k_md_tile<12> : k_md_tile<EVREP_MAX_CHANNELS>;
   EVREP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   prof_begin(EVREP_K_TILE, stream);
-  kern<<<g.B * g.T, TILE_THREADS, smem, stream>>>(ws.records, ws.base, ws.cursor, ws.wp, plan, g, out);
+  kern<<<g.B * g.T, TILE_THREADS, smem, stream>>>(ws.records, ws.base, ws.hist, ws.wp, plan, g, out);
   prof_end(EVREP_K_TILE, stream);
   EVREP_CUDA_OK(cudaGetLastError());
   return EVREP_OK;

@@ -21,7 +21,7 @@ __device__ __forceinline__ void zero_smem(uint32_t* acc, int n_words) {
 // s_k = start of the k-th nested suffix window (event_stack.py:70-82: c //= 2; x = x[c:]).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TILE_THREADS) k_event_stack_tile(const uint2* __restrict__ records, const uint32_t* __restrict__ base,
-                                                                   const uint32_t* __restrict__ cursor, const WinParams* __restrict__ wp,
+                                                                   const uint32_t* __restrict__ hist, const WinParams* __restrict__ wp,
                                                                    const Geom g, int K, float* __restrict__ out) {
   extern __shared__ __align__(16) uint32_t acc[];
   __shared__ uint32_t s_start[EVREP_MAX_CHANNELS];
@@ -38,11 +38,12 @@ __global__ void __launch_bounds__(TILE_THREADS) k_event_stack_tile(const uint2* 
       s += c;
     }
   }
-  const uint32_t count = cursor[blockIdx.x];
+  const uint32_t count = hist[blockIdx.x];
   const uint2* rec = records + w.start + base[blockIdx.x];
   __syncthreads();
   for (uint32_t i = tid; i < count; i += TILE_THREADS) {
     const uint2 r = __ldg(rec + i);
+    if (rec_is_null(r.y)) continue;
     const uint32_t pol = (((r.y >> 24) & 3u) == 1u) ? 1u : 0u;  // p > 0
     atomicMax(&acc[r.y & 0xffffu], ((r.x + 1u) << 1) | pol);
   }
@@ -62,7 +63,7 @@ int launch_event_stack_tile(const Geom& g, const Workspace& ws, int stack_size, 
   const size_t smem = sizeof(uint32_t) * (size_t)g.tile_px;
   EVREP_CUDA_OK(cudaFuncSetAttribute(k_event_stack_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   prof_begin(EVREP_K_TILE, stream);
-  k_event_stack_tile<<<g.B * g.T, TILE_THREADS, smem, stream>>>(ws.records, ws.base, ws.cursor, ws.wp, g, stack_size, out);
+  k_event_stack_tile<<<g.B * g.T, TILE_THREADS, smem, stream>>>(ws.records, ws.base, ws.hist, ws.wp, g, stack_size, out);
   prof_end(EVREP_K_TILE, stream);
   EVREP_CUDA_OK(cudaGetLastError());
   return EVREP_OK;
@@ -75,7 +76,7 @@ int launch_event_stack_tile(const Geom& g, const Workspace& ws, int stack_size, 
 // maximum over the snapshot axis reproduces the sequential memory of time_surface.py:66-74.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TILE_THREADS) k_time_surface_tile(const uint2* __restrict__ records, const uint32_t* __restrict__ base,
-                                                                    const uint32_t* __restrict__ cursor, const WinParams* __restrict__ wp,
+                                                                    const uint32_t* __restrict__ hist, const WinParams* __restrict__ wp,
                                                                     const SnapParams* __restrict__ snap, const Geom g, int S, double tau,
                                                                     float* __restrict__ out) {
   extern __shared__ __align__(16) uint32_t acc[];  // [S][2][TP]
@@ -94,12 +95,13 @@ __global__ void __launch_bounds__(TILE_THREADS) k_time_surface_tile(const uint2*
     s_empty[tid] = (float)exp((-(tau * 3.0 + 1.0) - (double)(w.t_base + (int64_t)tr)) / tau);
   }
   if (tid == 0) s_nvalid = snap[b].n_valid;
-  const uint32_t count = cursor[blockIdx.x];
+  const uint32_t count = hist[blockIdx.x];
   const uint2* rec = records + w.start + base[blockIdx.x];
   const int32_t tmin = w.tmin_rel;
   __syncthreads();
   for (uint32_t i = tid; i < count; i += TILE_THREADS) {
     const uint2 r = __ldg(rec + i);
+    if (rec_is_null(r.y)) continue;
     const uint32_t s = (r.y >> 16) & 0xffu;
     const uint32_t plane = (((r.y >> 24) & 3u) == 1u) ? 1u : 0u;
     atomicMax(&acc[(s * 2u + plane) * TP + (r.y & 0xffffu)], (uint32_t)((int32_t)r.x - tmin) + 1u);
@@ -130,7 +132,7 @@ int launch_time_surface_tile(const Geom& g, const Workspace& ws, int S, double t
   const size_t smem = sizeof(uint32_t) * (size_t)g.tile_px * 2 * S;
   EVREP_CUDA_OK(cudaFuncSetAttribute(k_time_surface_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   prof_begin(EVREP_K_TILE, stream);
-  k_time_surface_tile<<<g.B * g.T, TILE_THREADS, smem, stream>>>(ws.records, ws.base, ws.cursor, ws.wp, ws.snap, g, S, tau, out);
+  k_time_surface_tile<<<g.B * g.T, TILE_THREADS, smem, stream>>>(ws.records, ws.base, ws.hist, ws.wp, ws.snap, g, S, tau, out);
   prof_end(EVREP_K_TILE, stream);
   EVREP_CUDA_OK(cudaGetLastError());
   return EVREP_OK;
@@ -144,7 +146,7 @@ int launch_time_surface_tile(const Geom& g, const Workspace& ws, int S, double t
 // duplicates included.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TILE_THREADS) k_tore_tile(const uint2* __restrict__ records, const uint32_t* __restrict__ base,
-                                                            const uint32_t* __restrict__ cursor, const WinParams* __restrict__ wp,
+                                                            const uint32_t* __restrict__ hist, const WinParams* __restrict__ wp,
                                                             const Geom g, int K, float* __restrict__ out) {
   extern __shared__ __align__(16) uint32_t acc[];  // [2][K][TP]
   const int tid = threadIdx.x;
@@ -152,12 +154,13 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tore_tile(const uint2* __restr
   const int TP = g.tile_px, pix0 = tile << g.tile_shift, npix = min(TP, g.HW - pix0);
   zero_smem(acc, 2 * K * TP);
   const WinParams w = wp[b];
-  const uint32_t count = cursor[blockIdx.x];
+  const uint32_t count = hist[blockIdx.x];
   const uint2* rec = records + w.start + base[blockIdx.x];
   const int32_t tmin = w.tmin_rel;
   __syncthreads();
   for (uint32_t i = tid; i < count; i += TILE_THREADS) {
     const uint2 r = __ldg(rec + i);
+    if (rec_is_null(r.y)) continue;
     const uint32_t plane = (((r.y >> 24) & 3u) == 1u) ? 0u : 1u;  // positive first (tore.py:63-65)
     uint32_t v = (uint32_t)((int32_t)r.x - tmin) + 1u;
     uint32_t* slot = &acc[plane * K * TP + (r.y & 0xffffu)];
@@ -190,7 +193,7 @@ int launch_tore_tile(const Geom& g, const Workspace& ws, int k, float* out, cuda
   const size_t smem = sizeof(uint32_t) * (size_t)g.tile_px * 2 * k;
   EVREP_CUDA_OK(cudaFuncSetAttribute(k_tore_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   prof_begin(EVREP_K_TILE, stream);
-  k_tore_tile<<<g.B * g.T, TILE_THREADS, smem, stream>>>(ws.records, ws.base, ws.cursor, ws.wp, g, k, out);
+  k_tore_tile<<<g.B * g.T, TILE_THREADS, smem, stream>>>(ws.records, ws.base, ws.hist, ws.wp, g, k, out);
   prof_end(EVREP_K_TILE, stream);
   EVREP_CUDA_OK(cudaGetLastError());
   return EVREP_OK;
