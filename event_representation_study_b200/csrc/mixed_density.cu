@@ -131,7 +131,7 @@ __device__ __forceinline__ float md_value(const MdPlan& P, const MdChan& ch, con
   for (int l = P.nl1 - 2; l >= 0; --l) sti = (sti << P.lw) + a[G.w_st + l];
   if (ch.agg == EVREP_AGG_SUM) return __ull2float_rn(sti) * inv_delta;
   if (ch.agg == EVREP_AGG_MEAN) return __fdividef(__ull2float_rn(sti), __ull2float_rn((unsigned long long)c * delta_u));
-  if (c == 1u) return 0.f;  // a single event: t_s^2 - t_s^2, exactly 0 in the reference too
+  if (c == 1u && delta_u) return 0.f;  // a single event: t_s^2 - t_s^2, exactly 0 in the reference too (NaN when delta == 0)
   const double st = (double)sti;
   const double cd = (double)c * delta;
   const double st2 = md_limb_sum(a, G.w_st2, P.nl2, P.lw);
