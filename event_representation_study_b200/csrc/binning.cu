@@ -6,12 +6,15 @@
 // when the consumer asks for a polarity split).  The per-tile kernels then reduce a bucket entirely in
 // shared memory and write their slice of the output exactly once.
 //
-// The placement is deterministic and needs no global atomics: a CTA owns one super-chunk of SUPER = 16384
-// consecutive events.  k_hist writes that super-chunk's bucket counts as one row of `cc`; k_colscan turns each
-// column of `cc` into the exclusive prefix over the window's super-chunks (the column total is the bucket
-// size); k_scan turns bucket sizes into bucket starts; k_bin loads its row (bucket start + prefix) into
-// shared-memory cursors and each event takes the next slot of its bucket with one shared-memory atomic.
-// Records of different super-chunks therefore stay in stream order inside a bucket.
+// The placement is deterministic and needs no global atomics: a CTA owns one super-chunk of SUPER = 8192
+// consecutive events.  k_hist writes that super-chunk's bucket counts as one row of `cc`; k_colscan writes, per
+// column of `cc`, the exclusive prefix over the window's super-chunks into `cp` (the column total is the bucket
+// size); k_scan turns bucket sizes into bucket starts; k_bin ranks its events inside its own counts with one
+// shared-memory atomic each, stages the super-chunk sorted by bucket in shared memory and copies it out as
+// runs (bucket start + prefix gives the run's place).  Records of different super-chunks therefore stay in
+// stream order inside a bucket, and adjacent runs are written by CTAs that run at about the same time, so
+// partially written sectors complete in L2 (scattering single records straight from registers was measured:
+// 32 M sector writes, sectors evicted half full, 486 MB read + 387 MB written for 288 + 256 MB of payload).
 //
 // Replaces the per-channel boolean masking / np.concatenate / torch_scatter passes of the reference
 // (representations/representation_search/mixed_density_event_stack.py:111-151, operations.py:39-89)
@@ -81,6 +84,67 @@ __device__ __forceinline__ void load8_t<int64_t>(const int64_t* __restrict__ p, 
     for (int e = 0; e < EPT; ++e) v[e] = (g0 + e < total) ? (int64_t)__ldg(p + g0 + e) : 0;
   }
 }
+
+// Packed forms of the same loads: the k_bin prefetch keeps a chunk's events in 18 (int32 t) / 26 (int64 t) registers
+// while the bucket tables are being built, and unpacks them afterwards.
+__device__ __forceinline__ uint4 load8_u16_raw(const uint16_t* __restrict__ p, int64_t g0, int64_t total, bool vec) {
+  if (vec && g0 + EPT <= total) return __ldg(reinterpret_cast<const uint4*>(p + g0));
+  uint32_t v[EPT];
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) v[e] = (g0 + e < total) ? (uint32_t)__ldg(p + g0 + e) : 0u;
+  return make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
+}
+__device__ __forceinline__ uint2 load8_i8_raw(const int8_t* __restrict__ p, int64_t g0, int64_t total, bool vec) {
+  if (vec && g0 + EPT <= total) return __ldg(reinterpret_cast<const uint2*>(p + g0));
+  uint32_t v[EPT];
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) v[e] = (g0 + e < total) ? ((uint32_t)(int)__ldg(p + g0 + e) & 0xffu) : 0u;
+  return make_uint2(v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24), v[4] | (v[5] << 8) | (v[6] << 16) | (v[7] << 24));
+}
+__device__ __forceinline__ uint32_t raw_u16(const uint4& q, int e) {
+  const uint32_t w = (e >> 1) == 0 ? q.x : (e >> 1) == 1 ? q.y : (e >> 1) == 2 ? q.z : q.w;
+  return (e & 1) ? (w >> 16) : (w & 0xffffu);
+}
+__device__ __forceinline__ int raw_i8(const uint2& q, int e) { return (int)(int8_t)(((e < 4 ? q.x : q.y) >> (8 * (e & 3))) & 0xffu); }
+
+template <typename TT>
+struct RawT;
+template <>
+struct RawT<int32_t> {
+  int4 a, b;
+  __device__ __forceinline__ void load(const int32_t* __restrict__ p, int64_t g0, int64_t total, bool vec) {
+    if (vec && g0 + EPT <= total) {
+      a = __ldg(reinterpret_cast<const int4*>(p + g0));
+      b = __ldg(reinterpret_cast<const int4*>(p + g0) + 1);
+    } else {
+      int v[EPT];
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) v[e] = (g0 + e < total) ? __ldg(p + g0 + e) : 0;
+      a = make_int4(v[0], v[1], v[2], v[3]);
+      b = make_int4(v[4], v[5], v[6], v[7]);
+    }
+  }
+  __device__ __forceinline__ int64_t get(int e) const {
+    return (int64_t)(e == 0 ? a.x : e == 1 ? a.y : e == 2 ? a.z : e == 3 ? a.w : e == 4 ? b.x : e == 5 ? b.y : e == 6 ? b.z : b.w);
+  }
+};
+template <>
+struct RawT<int64_t> {
+  longlong2 q[4];
+  __device__ __forceinline__ void load(const int64_t* __restrict__ p, int64_t g0, int64_t total, bool vec) {
+    if (vec && g0 + EPT <= total) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) q[e] = __ldg(reinterpret_cast<const longlong2*>(p + g0) + e);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        q[e].x = (g0 + 2 * e < total) ? __ldg(p + g0 + 2 * e) : 0;
+        q[e].y = (g0 + 2 * e + 1 < total) ? __ldg(p + g0 + 2 * e + 1) : 0;
+      }
+    }
+  }
+  __device__ __forceinline__ int64_t get(int e) const { return (e & 1) ? q[e >> 1].y : q[e >> 1].x; }
+};
 
 // Shared-memory atomics on a 32-bit shared-window address (the generic-pointer form makes the compiler rebuild the
 // window base around every atomic inside divergent code).
@@ -226,7 +290,7 @@ template <bool SPLIT>
 __global__ void __launch_bounds__(BIN_THREADS) k_hist(const uint16_t* __restrict__ x, const uint16_t* __restrict__ y,
                                                       const int8_t* __restrict__ p, const WinParams* __restrict__ wp,
                                                       const int32_t* __restrict__ sc_prefix, const int32_t* __restrict__ sc_win,
-                                                      const Geom g, const bool vec, uint32_t* __restrict__ cc) {
+                                                      const Geom g, const bool vec, uint16_t* __restrict__ cc) {
   extern __shared__ uint32_t sh_hist[];
   const int b = __ldg(sc_win + blockIdx.x);
   const int scl = blockIdx.x - __ldg(sc_prefix + b);
@@ -257,32 +321,28 @@ __global__ void __launch_bounds__(BIN_THREADS) k_hist(const uint16_t* __restrict
     }
   }
   __syncthreads();
-  uint32_t* dst = cc + (size_t)blockIdx.x * g.Tb;
-  for (int i = threadIdx.x; i < g.Tb; i += BIN_THREADS) dst[i] = sh_hist[i];
+  uint16_t* dst = cc + (size_t)blockIdx.x * g.Tb;
+  for (int i = threadIdx.x; i < g.Tb; i += BIN_THREADS) dst[i] = (uint16_t)sh_hist[i];  // <= SUPER = 8192
 }
 
 // pass 2: per bucket (column of cc), exclusive prefix over the window's super-chunks; the total is the bucket size
-__global__ void __launch_bounds__(128) k_colscan(uint32_t* __restrict__ cc, const int32_t* __restrict__ sc_prefix, int Tb,
-                                                 uint32_t* __restrict__ hist) {
+__global__ void __launch_bounds__(128) k_colscan(const uint16_t* __restrict__ cc, const int32_t* __restrict__ sc_prefix, int Tb,
+                                                 uint32_t* __restrict__ cp, uint32_t* __restrict__ hist) {
+  constexpr int U = 16;  // loads in flight per thread
   const int b = blockIdx.y;
   const int c = blockIdx.x * 128 + threadIdx.x;
   if (c >= Tb) return;
   const int s0 = sc_prefix[b], s1 = sc_prefix[b + 1];
   uint32_t run = 0;
-  uint32_t* col = cc + (size_t)s0 * Tb + c;
-  int s = s0;
-  for (; s + 4 <= s1; s += 4, col += (size_t)4 * Tb) {  // four independent loads in flight
-    const uint32_t v0 = col[0], v1 = col[Tb], v2 = col[(size_t)2 * Tb], v3 = col[(size_t)3 * Tb];
-    col[0] = run;
-    col[Tb] = run + v0;
-    col[(size_t)2 * Tb] = run + v0 + v1;
-    col[(size_t)3 * Tb] = run + v0 + v1 + v2;
-    run += v0 + v1 + v2 + v3;
-  }
-  for (; s < s1; ++s, col += Tb) {
-    const uint32_t v = col[0];
-    col[0] = run;
-    run += v;
+  for (int s = s0; s < s1; s += U) {
+    uint32_t v[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) v[k] = (s + k < s1) ? (uint32_t)cc[(size_t)(s + k) * Tb + c] : 0u;
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      if (s + k < s1) cp[(size_t)(s + k) * Tb + c] = run;
+      run += v[k];
+    }
   }
   hist[(size_t)b * Tb + c] = run;
 }
@@ -302,13 +362,19 @@ __global__ void __launch_bounds__(BIN_THREADS) k_scan(const uint32_t* __restrict
 // pass 3: scatter the events into their buckets as 8-byte records.  HBM: reads 9 B/event, writes 8 B/event.
 // ---------------------------------------------------------------------------------------------
 template <typename TT, int MODE, bool SPLIT>
-__global__ void __launch_bounds__(BIN_THREADS) k_bin(const uint16_t* __restrict__ x, const uint16_t* __restrict__ y,
+__global__ void __launch_bounds__(BIN_THREADS, 2) k_bin(const uint16_t* __restrict__ x, const uint16_t* __restrict__ y,
                                                      const TT* __restrict__ t, const int8_t* __restrict__ p,
                                                      WinParams* __restrict__ wp, const SnapParams* __restrict__ snap,
                                                      const int32_t* __restrict__ sc_prefix, const int32_t* __restrict__ sc_win,
                                                      const Geom g, const bool vec, const uint32_t* __restrict__ base,
-                                                     const uint32_t* __restrict__ cc, uint2* __restrict__ records) {
-  extern __shared__ uint32_t cursor[];  // Tb: next free slot of every bucket, relative to the window's first record
+                                                     const uint16_t* __restrict__ cc, const uint32_t* __restrict__ cp,
+                                                     uint2* __restrict__ records) {
+  extern __shared__ __align__(16) unsigned char sh_raw[];
+  uint2* stage = reinterpret_cast<uint2*>(sh_raw);                    // SUPER records, sorted by bucket
+  uint32_t* sdest = reinterpret_cast<uint32_t*>(stage + SUPER);       // SUPER destinations (relative to the window's first record)
+  uint32_t* lcur = sdest + SUPER;                                     // Tb: next free staged slot of every bucket
+  uint32_t* delta = lcur + g.Tb;                                      // Tb: destination minus staged slot
+  __shared__ uint32_t warp_tot[BIN_THREADS / 32 + 1];
   __shared__ int sh_tmin, sh_tmax;
   __shared__ uint32_t sh_flags, sh_m1;
   __shared__ int32_t sh_snap_idx[MAX_SNAP];
@@ -321,60 +387,76 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin(const uint16_t* __restrict_
   const int n = (int)wp[b].n;  // < 2^31 - 8 (checked on the host)
   const int64_t t_base = wp[b].t_base;
   const int32_t tlast_rel = wp[b].tlast_rel;
+  const int64_t c0 = (start & ~(int64_t)(EPT - 1)) + (int64_t)scl * SUPER;
 
-  {
-    const uint32_t* brow = base + (size_t)b * g.Tb;
-    const uint32_t* crow = cc + (size_t)blockIdx.x * g.Tb;
-    for (int i = tid; i < g.Tb; i += BIN_THREADS) cursor[i] = __ldg(brow + i) + __ldg(crow + i);
-  }
+  // the first chunk's events are requested (packed, 18-26 registers) before the bucket tables are built
+  uint4 qx = make_uint4(0, 0, 0, 0), qy = qx;
+  uint2 qp = make_uint2(0, 0);
+  RawT<TT> qt;
+  TT t_before = 0;
+  auto fetch = [&](int sub) {
+    const int64_t g0 = c0 + (int64_t)sub * CHUNK + (int64_t)tid * EPT;
+    const int idx0 = (int)(g0 - start);
+    if (idx0 < n && idx0 + EPT > 0) {
+      qx = load8_u16_raw(x, g0, g.total, vec);
+      qy = load8_u16_raw(y, g0, g.total, vec);
+      qp = load8_i8_raw(p, g0, g.total, vec);
+      qt.load(t, g0, g.total, vec);
+      if (idx0 >= 1) t_before = __ldg(t + g0 - 1);
+    }
+  };
+  fetch(0);
+
+  const uint16_t* crow = cc + (size_t)blockIdx.x * g.Tb;
+  for (int i = tid; i < g.Tb; i += BIN_THREADS) lcur[i] = (uint32_t)__ldg(crow + i);
   if (tid == 0) { sh_tmin = INT_MAX; sh_tmax = INT_MIN; sh_flags = 0; sh_m1 = 0; sh_nsnap = 0; }
   if (MODE == REC_T_SNAP) {
     if (tid < MAX_SNAP) sh_snap_idx[tid] = snap[b].idx[tid];
     if (tid == 0) sh_nsnap = snap[b].n_valid;
   }
   __syncthreads();
+  const uint32_t total = block_exclusive_scan(lcur, g.Tb, warp_tot);  // lcur[i] = first staged slot of bucket i
+  {
+    const uint32_t* brow = base + (size_t)b * g.Tb;
+    const uint32_t* prow = cp + (size_t)blockIdx.x * g.Tb;
+    for (int i = tid; i < g.Tb; i += BIN_THREADS) delta[i] = __ldg(brow + i) + __ldg(prow + i) - lcur[i];
+  }
+  __syncthreads();
 
   // index boundaries of the SBN windows (mixed_density_event_stack.py:55-74)
   const int n3 = n / 3, s4 = n / 2, s5 = s4 + n / 4, s6 = s5 + n / 8;
-  const int64_t c0 = (start & ~(int64_t)(EPT - 1)) + (int64_t)scl * SUPER;
-  const uint32_t cur_base = (uint32_t)__cvta_generic_to_shared(cursor);
+  const uint32_t cur_base = (uint32_t)__cvta_generic_to_shared(lcur);
   const uint32_t Wd = (uint32_t)g.W, Hd = (uint32_t)g.H;
-  uint2* dst = records + start;
   int my_tmin = INT_MAX, my_tmax = INT_MIN;
   uint32_t my_flags = 0, my_m1 = 0;
 
 #pragma unroll 1
   for (int sub = 0; sub < SC_CHUNKS; ++sub) {
-    const int64_t g0 = c0 + (int64_t)sub * CHUNK + (int64_t)tid * EPT;
-    const int idx0 = (int)(g0 - start);  // index of this thread's first event inside the window (may be < 0 at the head)
-    if (idx0 >= n) break;
-    if (idx0 + EPT <= 0) continue;
-    uint32_t xs[EPT], ys[EPT];
-    int ps[EPT];
-    int64_t ts[EPT];
-    load8_u16(x, g0, g.total, vec, xs);
-    load8_u16(y, g0, g.total, vec, ys);
-    load8_i8(p, g0, g.total, vec, ps);
-    load8_t<TT>(t, g0, g.total, vec, ts);
-    int64_t t_prev = (idx0 >= 1) ? (int64_t)__ldg(t + g0 - 1) : LLONG_MIN;
+    if (sub) fetch(sub);
+    const int idx0 = (int)(c0 + (int64_t)sub * CHUNK + (int64_t)tid * EPT - start);  // may be < 0 at the head of the window
+    if (idx0 >= n || idx0 + EPT <= 0) continue;
     const bool interior = idx0 >= 0 && idx0 + EPT <= n;
+    int64_t t_prev = (idx0 >= 1) ? (int64_t)t_before : LLONG_MIN;
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
       const int idx = idx0 + e;
       if (!interior && (uint32_t)idx >= (uint32_t)n) continue;
-      if (ts[e] < t_prev) my_flags |= EVREP_WF_UNSORTED;
-      t_prev = ts[e];
-      if ((xs[e] >= Wd) | (ys[e] >= Hd)) { my_flags |= EVREP_WF_OUT_OF_RANGE; continue; }  // not counted by k_hist: no slot
-      const uint32_t lin = ys[e] * Wd + xs[e];
+      const int64_t te = qt.get(e);
+      const uint32_t xe = raw_u16(qx, e), ye = raw_u16(qy, e);
+      const int pe = raw_i8(qp, e);
+      if (te < t_prev) my_flags |= EVREP_WF_UNSORTED;
+      t_prev = te;
+      if ((xe >= Wd) | (ye >= Hd)) { my_flags |= EVREP_WF_OUT_OF_RANGE; continue; }  // not counted by k_hist: no slot
+      const uint32_t lin = ye * Wd + xe;
       uint32_t bin = lin >> g.tile_shift;
-      if (SPLIT) bin = (bin << 1) | (ps[e] > 0 ? 0u : 1u);
+      if (SPLIT) bin = (bin << 1) | (pe > 0 ? 0u : 1u);
       const uint32_t slot = smem_fetch_inc(cur_base + (bin << 2));
-      const int64_t d = ts[e] - t_base;
+      const int64_t d = te - t_base;
       uint2 rec = make_uint2(0u, REC_NULL_META);
       bool keep = true;
       if (d >= T_REL_LIMIT || d <= -T_REL_LIMIT) { my_flags |= EVREP_WF_T_RANGE; keep = false; }
       const int32_t t_rel = (int32_t)d;
-      int pv = ps[e];
+      int pv = pe;
       if (pv > 1 || pv < -1) { my_flags |= EVREP_WF_BAD_POLARITY; pv = pv > 0 ? 1 : -1; }
       uint32_t aux = 0, k = (uint32_t)t_rel;
       if (MODE == REC_T_WMASK) {
@@ -397,7 +479,8 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin(const uint16_t* __restrict_
         my_tmax = max(my_tmax, t_rel);
         rec = make_uint2(k, rec_meta(lin & (uint32_t)(g.tile_px - 1), aux, (uint32_t)pv & 3u));
       }
-      dst[slot] = rec;
+      stage[slot] = rec;
+      sdest[slot] = slot + delta[bin];
     }
   }
   // CTA-wide reductions of the per-window scalars
@@ -416,12 +499,17 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin(const uint16_t* __restrict_
     if (sh_flags) atomicOr(&wp[b].flags, sh_flags);
     if (sh_m1) atomicOr(&wp[b].has_m1, sh_m1);
   }
+  // copy out: consecutive threads hold consecutive records of a run
+  uint2* dst = records + start;
+  for (uint32_t i = tid; i < total; i += BIN_THREADS) dst[sdest[i]] = stage[i];
 }
 
 template <typename TT, int MODE, bool SPLIT>
 static int launch_bin(const Events& ev, const Geom& g, const Workspace& ws, int n_sc, bool vec, cudaStream_t stream) {
-  k_bin<TT, MODE, SPLIT><<<n_sc, BIN_THREADS, sizeof(uint32_t) * (size_t)g.Tb, stream>>>(
-      ev.x, ev.y, (const TT*)ev.t, ev.p, ws.wp, ws.snap, ws.sc_prefix, ws.sc_win, g, vec, ws.base, ws.cc, ws.records);
+  const size_t smem = (size_t)SUPER * (sizeof(uint2) + sizeof(uint32_t)) + 2 * sizeof(uint32_t) * (size_t)g.Tb;
+  EVREP_CUDA_OK(cudaFuncSetAttribute(k_bin<TT, MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_bin<TT, MODE, SPLIT><<<n_sc, BIN_THREADS, smem, stream>>>(ev.x, ev.y, (const TT*)ev.t, ev.p, ws.wp, ws.snap, ws.sc_prefix, ws.sc_win, g, vec,
+                                                              ws.base, ws.cc, ws.cp, ws.records);
   EVREP_CUDA_OK(cudaGetLastError());
   return EVREP_OK;
 }
@@ -534,7 +622,7 @@ int run_binning(const Events& ev, const int64_t* win_offsets_host, const Geom& g
   // bucket sizes (also for windows without events: an empty column range gives 0), then bucket starts
   for (int b0 = 0; b0 < g.B; b0 += 65535) {
     const int nb = std::min(65535, g.B - b0);
-    k_colscan<<<dim3((unsigned)((g.Tb + 127) / 128), (unsigned)nb), 128, 0, stream>>>(ws.cc, ws.sc_prefix + b0, g.Tb, ws.hist + (size_t)b0 * g.Tb);
+    k_colscan<<<dim3((unsigned)((g.Tb + 127) / 128), (unsigned)nb), 128, 0, stream>>>(ws.cc, ws.sc_prefix + b0, g.Tb, ws.cp, ws.hist + (size_t)b0 * g.Tb);
   }
   k_scan<<<g.B, BIN_THREADS, 0, stream>>>(ws.hist, ws.base, g.Tb);
   prof_end(EVREP_K_SCAN, stream);

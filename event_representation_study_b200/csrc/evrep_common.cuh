@@ -16,8 +16,8 @@ namespace evrep {
 constexpr int BIN_THREADS = 512;
 constexpr int EPT = 8;
 constexpr int CHUNK = BIN_THREADS * EPT;  // 4096 events per CTA iteration
-constexpr int SC_CHUNKS = 4;
-constexpr int SUPER = CHUNK * SC_CHUNKS;  // 16384 events per CTA ("super-chunk"): the unit of the counting / scatter passes
+constexpr int SC_CHUNKS = 2;
+constexpr int SUPER = CHUNK * SC_CHUNKS;  // 8192 events per CTA ("super-chunk"): the unit of the counting / scatter passes
 constexpr int MAX_TILES = 4096;           // buckets per window (shared-memory histogram size bound)
 constexpr int MIN_TILE_PX = 256;
 constexpr int MAX_SNAP = 16;              // time-surface snapshots per window
@@ -74,7 +74,8 @@ struct Workspace {  // device pointers carved out of the caller's buffer
   uint32_t* ticket;    // 64 words: work counters of persistent kernels
   uint32_t* hist;      // B*Tb  bucket sizes (events with valid x, y; dropped ones keep a null record)
   uint32_t* base;      // B*Tb  bucket start, relative to the window's first record
-  uint32_t* cc;        // n_sc*Tb  per super-chunk bucket counts, then (k_colscan) their exclusive prefix inside the bucket
+  uint16_t* cc;        // n_sc*Tb  per super-chunk bucket counts (<= SUPER)
+  uint32_t* cp;        // n_sc*Tb  exclusive prefix of cc over the window's super-chunks: where the super-chunk's run starts inside the bucket
   SnapParams* snap;    // B
   int64_t* snap_in;  // B*MAX_SNAP caller-supplied snapshot indices
   double* stats;     // B*4   voxel normalisation sums
@@ -103,7 +104,8 @@ inline Workspace carve(void* basep, int B, int64_t total, int T) {
   w.ticket = (uint32_t*)take(sizeof(uint32_t) * 64);
   w.hist = (uint32_t*)take(sizeof(uint32_t) * (size_t)B * T);
   w.base = (uint32_t*)take(sizeof(uint32_t) * (size_t)B * T);
-  w.cc = (uint32_t*)take(sizeof(uint32_t) * n_sc * (size_t)T);
+  w.cc = (uint16_t*)take(sizeof(uint16_t) * n_sc * (size_t)T);
+  w.cp = (uint32_t*)take(sizeof(uint32_t) * n_sc * (size_t)T);
   w.snap = (SnapParams*)take(sizeof(SnapParams) * (size_t)B);
   w.snap_in = (int64_t*)take(sizeof(int64_t) * (size_t)B * MAX_SNAP);
   w.stats = (double*)take(sizeof(double) * 4 * (size_t)B);
