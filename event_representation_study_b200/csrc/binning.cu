@@ -124,8 +124,8 @@ struct RawT<int32_t> {
       b = make_int4(v[4], v[5], v[6], v[7]);
     }
   }
-  __device__ __forceinline__ int64_t get(int e) const {
-    return (int64_t)(e == 0 ? a.x : e == 1 ? a.y : e == 2 ? a.z : e == 3 ? a.w : e == 4 ? b.x : e == 5 ? b.y : e == 6 ? b.z : b.w);
+  __device__ __forceinline__ int32_t get(int e) const {
+    return e == 0 ? a.x : e == 1 ? a.y : e == 2 ? a.z : e == 3 ? a.w : e == 4 ? b.x : e == 5 ? b.y : e == 6 ? b.z : b.w;
   }
 };
 template <>
@@ -157,8 +157,8 @@ __device__ __forceinline__ uint32_t smem_fetch_inc(uint32_t addr) {
 
 // In-place exclusive scan of a[0..n) in shared memory by a BIN_THREADS-thread CTA (n <= MAX_TILES).
 // `warp_tot` is BIN_THREADS/32 words of scratch.  Returns the total.  Ends with a __syncthreads().
-__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t* a, int n, uint32_t* warp_tot) {
-  constexpr int ITEMS = MAX_TILES / BIN_THREADS;  // 8
+template <int ITEMS>
+__device__ __forceinline__ uint32_t block_exclusive_scan_n(uint32_t* a, int n, uint32_t* warp_tot) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int per = (n + BIN_THREADS - 1) / BIN_THREADS;  // <= ITEMS
   const int i0 = tid * per;
@@ -197,6 +197,12 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t* a, int n, uin
   const uint32_t total = warp_tot[BIN_THREADS / 32];
   __syncthreads();
   return total;
+}
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t* a, int n, uint32_t* warp_tot) {
+  static_assert(MAX_TILES / BIN_THREADS == 8, "items per thread");
+  if (n <= 2 * BIN_THREADS) return block_exclusive_scan_n<2>(a, n, warp_tot);  // CTA-uniform choice
+  if (n <= 4 * BIN_THREADS) return block_exclusive_scan_n<4>(a, n, warp_tot);
+  return block_exclusive_scan_n<8>(a, n, warp_tot);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -321,30 +327,66 @@ __global__ void __launch_bounds__(BIN_THREADS) k_hist(const uint16_t* __restrict
     }
   }
   __syncthreads();
-  uint16_t* dst = cc + (size_t)blockIdx.x * g.Tb;
+  // the row holds the exclusive scan of the counts (where each bucket's records start when the super-chunk is sorted
+  // by bucket) followed by the total: k_bin needs exactly that, k_colscan recovers a count as a difference
+  __shared__ uint32_t warp_tot[BIN_THREADS / 32 + 1];
+  const uint32_t total = block_exclusive_scan(sh_hist, g.Tb, warp_tot);
+  uint16_t* dst = cc + (size_t)blockIdx.x * (g.Tb + 1);
   for (int i = threadIdx.x; i < g.Tb; i += BIN_THREADS) dst[i] = (uint16_t)sh_hist[i];  // <= SUPER = 8192
+  if (threadIdx.x == 0) dst[g.Tb] = (uint16_t)total;
 }
 
-// pass 2: per bucket (column of cc), exclusive prefix over the window's super-chunks; the total is the bucket size
-__global__ void __launch_bounds__(128) k_colscan(const uint16_t* __restrict__ cc, const int32_t* __restrict__ sc_prefix, int Tb,
+// pass 2: per bucket (column of cc), exclusive prefix over the window's super-chunks; the total is the bucket size.
+// A CTA owns 32 columns of one window; its 8 warps split the window's rows, so that a window of hundreds of
+// super-chunks costs two short rounds of independent loads (row segment totals, then the prefix) instead of one long
+// dependent walk.  A count is the difference of two neighbouring row entries: one load per lane plus a shuffle.
+__global__ void __launch_bounds__(256) k_colscan(const uint16_t* __restrict__ cc, const int32_t* __restrict__ sc_prefix, int Tb,
                                                  uint32_t* __restrict__ cp, uint32_t* __restrict__ hist) {
-  constexpr int U = 16;  // loads in flight per thread
+  constexpr int U = 8;
+  __shared__ uint32_t tot[8][32];
   const int b = blockIdx.y;
-  const int c = blockIdx.x * 128 + threadIdx.x;
-  if (c >= Tb) return;
+  const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 32, c = c0 + lane;
   const int s0 = sc_prefix[b], s1 = sc_prefix[b + 1];
-  uint32_t run = 0;
-  for (int s = s0; s < s1; s += U) {
+  const int per = (s1 - s0 + 7) / 8;
+  const int r0 = min(s0 + seg * per, s1), r1 = min(r0 + per, s1);
+  const bool ok = c < Tb;
+  // count of (row r, column c): lanes hold row[c0 + lane]; lane 31 (or the last valid column) also needs row[c + 1]
+  auto count_at = [&](int r) -> uint32_t {
+    const uint16_t* row = cc + (size_t)r * (Tb + 1);
+    const uint32_t lo = ok ? (uint32_t)row[c] : 0u;
+    uint32_t hi = __shfl_down_sync(0xffffffffu, lo, 1);
+    if (ok && (lane == 31 || c + 1 == Tb)) hi = (uint32_t)row[c + 1];
+    return ok ? hi - lo : 0u;
+  };
+  uint32_t sum = 0;
+  for (int r = r0; r < r1; r += U) {
     uint32_t v[U];
 #pragma unroll
-    for (int k = 0; k < U; ++k) v[k] = (s + k < s1) ? (uint32_t)cc[(size_t)(s + k) * Tb + c] : 0u;
+    for (int k = 0; k < U; ++k) v[k] = (r + k < r1) ? count_at(r + k) : 0u;  // r1 is warp-uniform: shuffles stay converged
+#pragma unroll
+    for (int k = 0; k < U; ++k) sum += v[k];
+  }
+  tot[seg][lane] = sum;
+  __syncthreads();
+  uint32_t run = 0, total = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const uint32_t tk = tot[k][lane];
+    if (k < seg) run += tk;
+    total += tk;
+  }
+  for (int r = r0; r < r1; r += U) {
+    uint32_t v[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) v[k] = (r + k < r1) ? count_at(r + k) : 0u;
 #pragma unroll
     for (int k = 0; k < U; ++k) {
-      if (s + k < s1) cp[(size_t)(s + k) * Tb + c] = run;
+      if (ok && r + k < r1) cp[(size_t)(r + k) * Tb + c] = run;
       run += v[k];
     }
   }
-  hist[(size_t)b * Tb + c] = run;
+  if (ok && seg == 0) hist[(size_t)b * Tb + c] = total;
 }
 
 // bucket starts: one CTA per window, exclusive scan over its Tb buckets
@@ -374,7 +416,6 @@ __global__ void __launch_bounds__(BIN_THREADS, 2) k_bin(const uint16_t* __restri
   uint32_t* sdest = reinterpret_cast<uint32_t*>(stage + SUPER);       // SUPER destinations (relative to the window's first record)
   uint32_t* lcur = sdest + SUPER;                                     // Tb: next free staged slot of every bucket
   uint32_t* delta = lcur + g.Tb;                                      // Tb: destination minus staged slot
-  __shared__ uint32_t warp_tot[BIN_THREADS / 32 + 1];
   __shared__ int sh_tmin, sh_tmax;
   __shared__ uint32_t sh_flags, sh_m1;
   __shared__ int32_t sh_snap_idx[MAX_SNAP];
@@ -407,19 +448,19 @@ __global__ void __launch_bounds__(BIN_THREADS, 2) k_bin(const uint16_t* __restri
   };
   fetch(0);
 
-  const uint16_t* crow = cc + (size_t)blockIdx.x * g.Tb;
-  for (int i = tid; i < g.Tb; i += BIN_THREADS) lcur[i] = (uint32_t)__ldg(crow + i);
+  const uint16_t* crow = cc + (size_t)blockIdx.x * (g.Tb + 1);  // first staged slot of every bucket (k_hist), then the total
+  const uint32_t* brow = base + (size_t)b * g.Tb;
+  const uint32_t* prow = cp + (size_t)blockIdx.x * g.Tb;
+  for (int i = tid; i < g.Tb; i += BIN_THREADS) {
+    const uint32_t lo = (uint32_t)__ldg(crow + i);
+    lcur[i] = lo;
+    delta[i] = __ldg(brow + i) + __ldg(prow + i) - lo;
+  }
+  const uint32_t total = (uint32_t)__ldg(crow + g.Tb);
   if (tid == 0) { sh_tmin = INT_MAX; sh_tmax = INT_MIN; sh_flags = 0; sh_m1 = 0; sh_nsnap = 0; }
   if (MODE == REC_T_SNAP) {
     if (tid < MAX_SNAP) sh_snap_idx[tid] = snap[b].idx[tid];
     if (tid == 0) sh_nsnap = snap[b].n_valid;
-  }
-  __syncthreads();
-  const uint32_t total = block_exclusive_scan(lcur, g.Tb, warp_tot);  // lcur[i] = first staged slot of bucket i
-  {
-    const uint32_t* brow = base + (size_t)b * g.Tb;
-    const uint32_t* prow = cp + (size_t)blockIdx.x * g.Tb;
-    for (int i = tid; i < g.Tb; i += BIN_THREADS) delta[i] = __ldg(brow + i) + __ldg(prow + i) - lcur[i];
   }
   __syncthreads();
 
@@ -436,32 +477,52 @@ __global__ void __launch_bounds__(BIN_THREADS, 2) k_bin(const uint16_t* __restri
     const int idx0 = (int)(c0 + (int64_t)sub * CHUNK + (int64_t)tid * EPT - start);  // may be < 0 at the head of the window
     if (idx0 >= n || idx0 + EPT <= 0) continue;
     const bool interior = idx0 >= 0 && idx0 + EPT <= n;
-    int64_t t_prev = (idx0 >= 1) ? (int64_t)t_before : LLONG_MIN;
+    TT t_prev = t_before;
+    bool have_prev = idx0 >= 1;
+    // SBN window mask of an index; a thread's EPT consecutive events nearly always share it
+    auto sbn_mask = [&](int idx) {
+      return 1u | (idx < n3 ? 2u : (idx < 2 * n3 ? 4u : (idx < 3 * n3 ? 8u : 0u))) | (idx >= s4 ? 16u : 0u) | (idx >= s5 ? 32u : 0u) |
+             (idx >= s6 ? 64u : 0u);
+    };
+    uint32_t aux_first = 0;
+    bool aux_uniform = false;
+    if (MODE == REC_T_WMASK) {
+      aux_first = sbn_mask(idx0);
+      aux_uniform = aux_first == sbn_mask(idx0 + EPT - 1);  // the mask changes monotonically with the index
+    }
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
       const int idx = idx0 + e;
       if (!interior && (uint32_t)idx >= (uint32_t)n) continue;
-      const int64_t te = qt.get(e);
+      const TT te = qt.get(e);
       const uint32_t xe = raw_u16(qx, e), ye = raw_u16(qy, e);
       const int pe = raw_i8(qp, e);
-      if (te < t_prev) my_flags |= EVREP_WF_UNSORTED;
+      if (have_prev && te < t_prev) my_flags |= EVREP_WF_UNSORTED;
       t_prev = te;
+      have_prev = true;
       if ((xe >= Wd) | (ye >= Hd)) { my_flags |= EVREP_WF_OUT_OF_RANGE; continue; }  // not counted by k_hist: no slot
       const uint32_t lin = ye * Wd + xe;
       uint32_t bin = lin >> g.tile_shift;
       if (SPLIT) bin = (bin << 1) | (pe > 0 ? 0u : 1u);
       const uint32_t slot = smem_fetch_inc(cur_base + (bin << 2));
-      const int64_t d = te - t_base;
       uint2 rec = make_uint2(0u, REC_NULL_META);
       bool keep = true;
-      if (d >= T_REL_LIMIT || d <= -T_REL_LIMIT) { my_flags |= EVREP_WF_T_RANGE; keep = false; }
-      const int32_t t_rel = (int32_t)d;
+      int32_t t_rel;
+      if constexpr (sizeof(TT) == 4) {  // 32-bit timestamps: the difference in wrapping arithmetic plus an overflow test
+        const int32_t tb = (int32_t)t_base;
+        t_rel = (int32_t)((uint32_t)te - (uint32_t)tb);
+        const bool ovf = (((int32_t)te ^ tb) & ((int32_t)te ^ t_rel)) < 0;
+        if (ovf || (uint32_t)t_rel + (uint32_t)(T_REL_LIMIT - 1) >= 2u * (uint32_t)T_REL_LIMIT - 1u) { my_flags |= EVREP_WF_T_RANGE; keep = false; }
+      } else {
+        const int64_t d = (int64_t)te - t_base;
+        if (d >= T_REL_LIMIT || d <= -T_REL_LIMIT) { my_flags |= EVREP_WF_T_RANGE; keep = false; }
+        t_rel = (int32_t)d;
+      }
       int pv = pe;
       if (pv > 1 || pv < -1) { my_flags |= EVREP_WF_BAD_POLARITY; pv = pv > 0 ? 1 : -1; }
       uint32_t aux = 0, k = (uint32_t)t_rel;
       if (MODE == REC_T_WMASK) {
-        aux = 1u | (idx < n3 ? 2u : (idx < 2 * n3 ? 4u : (idx < 3 * n3 ? 8u : 0u))) | (idx >= s4 ? 16u : 0u) | (idx >= s5 ? 32u : 0u) |
-              (idx >= s6 ? 64u : 0u);
+        aux = aux_uniform ? aux_first : sbn_mask(idx);
         if (keep) my_m1 |= pv == -1 ? aux : 0u;
       } else if (MODE == REC_IDX) {
         k = (uint32_t)idx;
@@ -622,7 +683,7 @@ int run_binning(const Events& ev, const int64_t* win_offsets_host, const Geom& g
   // bucket sizes (also for windows without events: an empty column range gives 0), then bucket starts
   for (int b0 = 0; b0 < g.B; b0 += 65535) {
     const int nb = std::min(65535, g.B - b0);
-    k_colscan<<<dim3((unsigned)((g.Tb + 127) / 128), (unsigned)nb), 128, 0, stream>>>(ws.cc, ws.sc_prefix + b0, g.Tb, ws.cp, ws.hist + (size_t)b0 * g.Tb);
+    k_colscan<<<dim3((unsigned)((g.Tb + 31) / 32), (unsigned)nb), 256, 0, stream>>>(ws.cc, ws.sc_prefix + b0, g.Tb, ws.cp + 0, ws.hist + (size_t)b0 * g.Tb);
   }
   k_scan<<<g.B, BIN_THREADS, 0, stream>>>(ws.hist, ws.base, g.Tb);
   prof_end(EVREP_K_SCAN, stream);
