@@ -351,19 +351,28 @@ __global__ void __launch_bounds__(256) k_colscan(const uint16_t* __restrict__ cc
   const int per = (s1 - s0 + 7) / 8;
   const int r0 = min(s0 + seg * per, s1), r1 = min(r0 + per, s1);
   const bool ok = c < Tb;
-  // count of (row r, column c): lanes hold row[c0 + lane]; lane 31 (or the last valid column) also needs row[c + 1]
-  auto count_at = [&](int r) -> uint32_t {
-    const uint16_t* row = cc + (size_t)r * (Tb + 1);
-    const uint32_t lo = ok ? (uint32_t)row[c] : 0u;
-    uint32_t hi = __shfl_down_sync(0xffffffffu, lo, 1);
-    if (ok && (lane == 31 || c + 1 == Tb)) hi = (uint32_t)row[c + 1];
-    return ok ? hi - lo : 0u;
+  // counts of U rows at column c: every lane loads row[c] (the last lane / last column also row[c + 1]) for all U rows
+  // first, so the loads are in flight together; the neighbour's value then comes from a shuffle
+  const bool edge = ok && (lane == 31 || c + 1 == Tb);
+  auto counts = [&](int r, uint32_t (&v)[U]) {
+    uint32_t lo[U], ex[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const uint16_t* row = cc + (size_t)(r + k) * (Tb + 1);
+      const bool live = ok && r + k < r1;
+      lo[k] = live ? (uint32_t)row[c] : 0u;
+      ex[k] = (live && edge) ? (uint32_t)row[c + 1] : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const uint32_t hi = __shfl_down_sync(0xffffffffu, lo[k], 1);
+      v[k] = (edge ? ex[k] : hi) - lo[k];  // dead lanes / rows: 0 - 0
+    }
   };
   uint32_t sum = 0;
   for (int r = r0; r < r1; r += U) {
     uint32_t v[U];
-#pragma unroll
-    for (int k = 0; k < U; ++k) v[k] = (r + k < r1) ? count_at(r + k) : 0u;  // r1 is warp-uniform: shuffles stay converged
+    counts(r, v);
 #pragma unroll
     for (int k = 0; k < U; ++k) sum += v[k];
   }
@@ -378,8 +387,7 @@ __global__ void __launch_bounds__(256) k_colscan(const uint16_t* __restrict__ cc
   }
   for (int r = r0; r < r1; r += U) {
     uint32_t v[U];
-#pragma unroll
-    for (int k = 0; k < U; ++k) v[k] = (r + k < r1) ? count_at(r + k) : 0u;
+    counts(r, v);
 #pragma unroll
     for (int k = 0; k < U; ++k) {
       if (ok && r + k < r1) cp[(size_t)(r + k) * Tb + c] = run;
