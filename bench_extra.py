@@ -63,7 +63,7 @@ def rep_line(name, ev_per_step, sec, alg_bytes, cpu_ev_per_s, cpu_note, extra=No
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--only", default="config1,config2,config3,gwd")
+    ap.add_argument("--only", default="config1,config2,config3,gwd,gwdb")
     a = ap.parse_args()
     import torch
     import event_representation_study_b200.batched as eb
@@ -137,6 +137,40 @@ def main():
                           "cpu_baseline": {"value": 1.0 / c, "unit": "pairs/s", "cores": "numpy/BLAS threads", "kind": "port",
                                            "sample": f"{k} pairs of the same size, oracle gwd_a_cost (closed form of POT's estimate; POT not installable offline)"},
                           "speedup_vs_cpu_port": (R * S / sec) * c}), flush=True)
+
+    if "gwdb" in only:  # config 5, GWD-B: conditional-gradient GW with the KL loss, n = m = 1000 points per pair
+        n = 1000
+        rng = np.random.default_rng(55)
+        Xs = rng.random((n, 4))
+        Xt = np.concatenate([Xs[rng.permutation(n)][:, :3] + 0.05 * rng.standard_normal((n, 3)), rng.random((n, 11)) * 0.2], 1)
+        eb.gw_kl(Xs, Xt, 0.7, max_iter=2)  # warm-up (module load, shared-memory attribute)
+        t0 = time.perf_counter()
+        dist, iters = eb.gw_kl(Xs, Xt, 0.7)
+        sec = time.perf_counter() - t0
+        # the contraction alone, device timed: one n x n x n GEMM per iteration
+        A = torch.rand((n, n), device=dev)
+        Bm = torch.rand((n, n), device=dev)
+        out = torch.empty((n, n), device=dev)
+        gsec = timed(lambda: eb.gemm_nt_3xtf32(A, Bm, out=out), 50)
+        A8 = torch.rand((8192, 8192), device=dev)
+        o8 = torch.empty((8192, 8192), device=dev)
+        g8 = timed(lambda: eb.gemm_nt_3xtf32(A8, A8, out=o8), 5)
+        t0 = time.perf_counter()
+        want = ogwd.gwd_b_cost(Xs, Xt, 0.7)
+        csec = time.perf_counter() - t0
+        tf32_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"]) / 2 if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 795.0
+        print(json.dumps({"workload": f"config5 GWD-B (CG Gromov-Wasserstein, KL loss) one pair, n = m = {n}", "value": 1.0 / sec, "unit": "pairs/s",
+                          "ms_per_pair": sec * 1e3, "iterations": iters, "gw_dist": dist,
+                          "note": "wall clock of the synchronous call: kernels + one host assignment solve (LMO) and two small D2H copies per iteration",
+                          "contraction": {"kernel": "k_gemm_nt_3xtf32 (tcgen05, 3 TF32 UMMAs per product)", "n1000_us": gsec * 1e6,
+                                          "n1000_useful_tflops": 2 * n ** 3 / gsec / 1e12, "n8192_ms": g8 * 1e3,
+                                          "n8192_useful_tflops": 2 * 8192 ** 3 / g8 / 1e12, "n8192_issued_tf32_tflops": 3 * 2 * 8192 ** 3 / g8 / 1e12,
+                                          "roofline": {"bound": "tensor", "peak_tf32_tflops_assumed": tf32_peak,
+                                                       "frac_issued": 3 * 2 * 8192 ** 3 / g8 / 1e12 / tf32_peak,
+                                                       "peak_source": "half of MEASURED_PEAKS.json bf16_tflops (TF32 runs at half the bf16 rate)"}},
+                          "cpu_baseline": {"value": 1.0 / csec, "unit": "pairs/s", "cores": "numpy/BLAS threads", "kind": "port", "gw_dist": want,
+                                           "sample": "the same pair, oracle gw_kl_cg (float64 GEMMs + scipy linear_sum_assignment); POT not installable offline"},
+                          "speedup_vs_cpu_port": csec / sec}), flush=True)
 
 
 if __name__ == "__main__":

@@ -42,6 +42,9 @@ SIGNATURES = {
     "evrep_histogram_batched": (_i, _EV + _TAIL),
     "evrep_gwd_workspace_bytes": (_sz, [_vp, _vp, _i]),
     "evrep_gwd_kernel_l1": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _d, _vp, _vp, _sz, _vp]),
+    "evrep_gw_kl_workspace_bytes": (_sz, [_i, _i]),
+    "evrep_gw_kl": (_i, [_vp, _i, _i, _vp, _i, _i, _d, _i, _d, _d, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "evrep_gemm_nt_3xtf32": (_i, [_vp, _vp, _vp, _i, _i, _i, _c.c_float, _vp, _vp, _vp]),
 }
 
 

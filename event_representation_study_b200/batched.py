@@ -257,3 +257,48 @@ def gwd_kernel_l1(Xs_list, Xt_list, h=0.7, device="cuda"):
     check(lib.evrep_gwd_kernel_l1(Xs.data_ptr(), so.ctypes.data, ds, Xt.data_ptr(), to.ctypes.data, dt, n_pairs, float(h),
                                   out.data_ptr(), ws.data_ptr(), ws.numel(), stream))
     return out
+
+
+def gemm_nt_3xtf32(A, B, alpha=1.0, row_vec=None, col_vec=None, out=None):
+    """alpha * A @ B.T + row_vec[:, None] + col_vec[None, :] on the tcgen05 tensor cores with fp32-class accuracy
+    (3 x TF32 split).  A (M, K), B (N, K): float32 CUDA tensors.  This is the contraction of GWD-B's tensor product."""
+    if not (A.is_cuda and B.is_cuda):
+        raise ValueError("gemm_nt_3xtf32 needs CUDA tensors (there is no CPU path)")
+    A = A.contiguous().float()
+    B = B.contiguous().float()
+    M, K = A.shape
+    N, K2 = B.shape
+    if K != K2:
+        raise ValueError("A and B must share the contraction length")
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    rv = row_vec.contiguous().float() if row_vec is not None else None
+    cv = col_vec.contiguous().float() if col_vec is not None else None
+    stream = torch.cuda.current_stream(A.device).cuda_stream
+    check(lib.evrep_gemm_nt_3xtf32(A.data_ptr(), B.data_ptr(), out.data_ptr(), M, N, K, float(alpha),
+                                   rv.data_ptr() if rv is not None else None, cv.data_ptr() if cv is not None else None, stream))
+    return out
+
+
+def gw_kl(Xs, Xt, h=0.7, max_iter=10000, tol_rel=1e-9, tol_abs=1e-9, return_plan=False, device="cuda"):
+    """GWD-B (gromov_wasserstein.py:39-69): Gaussian kernels of Xs (n, ds) and Xt (m, dt), then conditional-gradient
+    Gromov-Wasserstein with the KL loss.  -> (gw_dist, iterations[, plan (n, m) float32 CUDA tensor]).  n == m only."""
+    import ctypes
+    dev = torch.device(device)
+    Xs = torch.as_tensor(Xs).to(device=dev, dtype=torch.float64).contiguous()
+    Xt = torch.as_tensor(Xt).to(device=dev, dtype=torch.float64).contiguous()
+    Xs = Xs.reshape(len(Xs), -1)
+    Xt = Xt.reshape(len(Xt), -1)
+    n, ds = Xs.shape
+    m, dt = Xt.shape
+    nbytes = lib.evrep_gw_kl_workspace_bytes(n, m)
+    if nbytes == 0:
+        raise ValueError("invalid sizes")
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    ws = _workspace(dev, stream, nbytes)
+    plan = torch.empty((n, m), dtype=torch.float32, device=dev) if return_plan else None
+    dist, iters = ctypes.c_double(0.0), ctypes.c_int(0)
+    check(lib.evrep_gw_kl(Xs.data_ptr(), n, ds, Xt.data_ptr(), m, dt, float(h), int(max_iter), float(tol_rel), float(tol_abs),
+                          ctypes.byref(dist), plan.data_ptr() if plan is not None else None, ctypes.byref(iters), ws.data_ptr(), ws.numel(),
+                          stream))
+    return (dist.value, iters.value, plan) if return_plan else (dist.value, iters.value)

@@ -4,14 +4,14 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = ["api.cu", "binning.cu", "mixed_density.cu", "order_ops.cu", "voxel.cu", "gwd.cu"]
+SRC = ["api.cu", "binning.cu", "mixed_density.cu", "order_ops.cu", "voxel.cu", "gwd.cu", "gw_kl.cu"]
 OUT = os.path.join(HERE, "lib", "libevrep.so")
 
 
 def needs_build():
     if not os.path.exists(OUT):
         return True
-    newest = max(os.path.getmtime(os.path.join(HERE, "csrc", f)) for f in SRC + ["evrep_common.cuh"])
+    newest = max(os.path.getmtime(os.path.join(HERE, "csrc", f)) for f in SRC + ["evrep_common.cuh", "md_plan.cuh"])
     newest = max(newest, os.path.getmtime(os.path.join(HERE, "..", "include", "evrep.h")))
     return newest > os.path.getmtime(OUT)
 

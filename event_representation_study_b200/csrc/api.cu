@@ -53,6 +53,12 @@ size_t gwd_workspace_bytes(const int64_t* so, const int64_t* to, int n_pairs);
 int launch_gwd(const double* Xs, const int64_t* so, int ds, const double* Xt, const int64_t* to, int dt, int n_pairs, double h,
                double* out, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
+size_t gw_kl_workspace_bytes(int n, int m);
+int run_gw_kl(const double* Xs, int n, int ds, const double* Xt, int m, int dt, double h, int max_iter, double tol_rel, double tol_abs,
+              double* gw_dist_host, float* T_out, int* iters_host, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int launch_gemm_nt_3xtf32(const float* A, const float* B, float* C, int M, int N, int K, float alpha, const float* rv, const float* cv,
+                          cudaStream_t stream);
+
 constexpr size_t TILE_SMEM_TARGET = 100 * 1024;  // two tile CTAs per SM
 constexpr size_t TILE_SMEM_MAX = 220 * 1024;
 
@@ -370,6 +376,26 @@ int evrep_gwd_kernel_l1(const double* Xs, const int64_t* s_offsets, int ds, cons
   if (!Xs || !Xt || !out) { set_error("null array"); return EVREP_EINVAL; }
   if (!(h > 0.0)) { set_error("h must be positive"); return EVREP_EINVAL; }
   return launch_gwd(Xs, s_offsets, ds, Xt, t_offsets, dt, n_pairs, h, out, workspace, workspace_bytes, (cudaStream_t)stream);
+  EVREP_GUARD_END
+}
+
+size_t evrep_gw_kl_workspace_bytes(int n, int m) { return gw_kl_workspace_bytes(n, m); }
+
+int evrep_gw_kl(const double* Xs, int n, int ds, const double* Xt, int m, int dt, double h, int max_iter, double tol_rel, double tol_abs,
+                double* gw_dist, float* T_out, int* iters, void* workspace, size_t workspace_bytes, evrep_stream_t stream) {
+  EVREP_GUARD_BEGIN
+  if (!Xs || !Xt || !gw_dist) { set_error("null array"); return EVREP_EINVAL; }
+  if (!(h > 0.0)) { set_error("h must be positive"); return EVREP_EINVAL; }
+  if (max_iter < 0) { set_error("max_iter must be >= 0"); return EVREP_EINVAL; }
+  return run_gw_kl(Xs, n, ds, Xt, m, dt, h, max_iter, tol_rel, tol_abs, gw_dist, T_out, iters, workspace, workspace_bytes, (cudaStream_t)stream);
+  EVREP_GUARD_END
+}
+
+int evrep_gemm_nt_3xtf32(const float* A, const float* B, float* C, int M, int N, int K, float alpha, const float* rv, const float* cv,
+                         evrep_stream_t stream) {
+  EVREP_GUARD_BEGIN
+  if (!A || !B || !C) { set_error("null matrix"); return EVREP_EINVAL; }
+  return launch_gemm_nt_3xtf32(A, B, C, M, N, K, alpha, rv, cv, (cudaStream_t)stream);
   EVREP_GUARD_END
 }
 

@@ -1,0 +1,625 @@
+// GWD-B: conditional-gradient Gromov-Wasserstein with the KL loss between the Gaussian kernels of two point clouds
+// (representations/representation_search/gromov_wasserstein.py:39-69: OTMI.__init__ + OTMI.solve, which calls
+// POT's ot.gromov.gromov_wasserstein(Ks, Kt, p, q, "kl_loss")).
+//
+//   constC = f1(Ks) p 1^T + 1 q^T f2(Kt)^T,  f1(a) = a log(a + 1e-15) - a,  f2(b) = b
+//   tens(T) = constC - hC1 T hC2^T,           hC1 = Ks,  hC2 = log(Kt + 1e-15)       <- the dense contraction
+//   loop:  LMO  Gc = argmin_{G in U(p,q)} <tens(T), G>;  exact line search on the quadratic;  T += alpha (Gc - T)
+//
+// The contraction is the only GEMM-shaped work of the whole library and the only place tensor cores are used:
+// k_gemm_nt_3xtf32 is a hand-written tcgen05 kernel (TF32 UMMA, accumulators in TMEM) that splits every fp32
+// operand into two TF32 terms on the fly while staging it into the 128-byte-swizzled shared-memory tiles and
+// issues hi*hi + lo*hi + hi*lo, i.e. fp32-class accuracy (about 2^-22 relative) at a third of the TF32 rate.
+// For uniform marginals with n == m every vertex of U(p, q) is a permutation matrix / n, so the LMO is a linear
+// assignment problem (solved on the host, like POT's network simplex) and hC1 Gc hC2^T is ONE gather + ONE GEMM.
+#include <float.h>
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "evrep_common.cuh"
+
+namespace evrep {
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers (sm_100a)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem] * B[smem]^T, one 128 x N x 8 TF32 UMMA issued by one thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// the mbarrier receives one arrival when every MMA issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// K-major operand tile in the canonical SWIZZLE_128B layout: rows of 128 bytes, 8-row groups of 1024 bytes
+// (cute/arch/mma_sm100_desc.hpp SmemDescriptor: start >> 4, LBO = 1, SBO = 1024 >> 4, version 1, layout 2)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// C[M x N] = alpha * A[M x K] * B[N x K]^T + rv[i] + cv[j]      (all fp32, row-major, K contiguous in A and B)
+// ---------------------------------------------------------------------------------------------
+constexpr int GB_M = 128, GB_N = 128, GB_K = 32;  // CTA tile; GB_K floats = one 128-byte swizzle row
+constexpr int GB_STAGES = 3;
+constexpr int GB_TILE_BYTES = GB_M * GB_K * 4;    // 16 KB per operand term
+constexpr int GB_STAGE_BYTES = 4 * GB_TILE_BYTES; // A_hi, A_lo, B_hi, B_lo
+constexpr int GB_THREADS = 288;                   // warps 0-3 producers, 4-7 accumulators + epilogue, 8 TMEM owner + MMA issuer
+constexpr size_t GB_SMEM = (size_t)GB_STAGES * GB_STAGE_BYTES + 1024 /* alignment slack */ + 128 /* barriers */;
+// instruction descriptor (InstrDescriptor in mma_sm100_desc.hpp): F32 accumulate, TF32 x TF32, both K-major, M = 128, N = 128
+constexpr uint32_t GB_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(GB_N >> 3) << 17) | ((uint32_t)(GB_M >> 4) << 24);
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+
+// stages one 128 x 32 fp32 tile (rows r0.., columns k0..) as its two TF32 terms; rows / columns outside the matrix are zero
+__device__ __forceinline__ void gb_stage_tile(const float* __restrict__ X, int rows, int K, int r0, int k0, bool vec, unsigned char* hi,
+                                              unsigned char* lo, int t) {
+  const int c4 = t & 7, rsub = t >> 3;  // 8 threads per row (one 16-byte chunk each), 16 rows per pass
+#pragma unroll
+  for (int pass = 0; pass < GB_M / 16; ++pass) {
+    const int r = pass * 16 + rsub;
+    const int gr = r0 + r, gk = k0 + 4 * c4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gr < rows) {
+      const float* src = X + (size_t)gr * K + gk;
+      if (vec && gk + 4 <= K) {
+        v = __ldg(reinterpret_cast<const float4*>(src));
+      } else {
+        if (gk + 0 < K) v.x = __ldg(src + 0);
+        if (gk + 1 < K) v.y = __ldg(src + 1);
+        if (gk + 2 < K) v.z = __ldg(src + 2);
+        if (gk + 3 < K) v.w = __ldg(src + 3);
+      }
+    }
+    // hi = x rounded to the nearest TF32 (an exact TF32 number, so the tensor core's own conversion cannot change it);
+    // lo = the exact remainder x - hi, rounded to TF32 again.  |x - hi - lo| <= 2^-23 |x| and the errors are unbiased.
+    uint4 h, l;
+    h.x = to_tf32(v.x); l.x = to_tf32(v.x - __uint_as_float(h.x));
+    h.y = to_tf32(v.y); l.y = to_tf32(v.y - __uint_as_float(h.y));
+    h.z = to_tf32(v.z); l.z = to_tf32(v.z - __uint_as_float(h.z));
+    h.w = to_tf32(v.w); l.w = to_tf32(v.w - __uint_as_float(h.w));
+    const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c4 ^ (r & 7)) << 4);  // Swizzle<3,4,3>: chunk ^= row mod 8
+    *reinterpret_cast<uint4*>(hi + off) = h;
+    *reinterpret_cast<uint4*>(lo + off) = l;
+  }
+}
+
+// TMEM -> registers: 32 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+      "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+        "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Warp roles: 0-3 producers (global fp32 -> hi / lo TF32 tiles), 4-7 accumulators (drain TMEM after every k-block),
+// 8 TMEM owner + MMA issuer.
+//
+// Why the accumulators do not simply stay in TMEM for the whole K loop: the tensor core adds into its fp32
+// accumulator with truncation, not round-to-nearest.  For the GW operands (hC1 > 0, hC2 < 0: every term has the same
+// sign) K / 8 truncating additions into a growing sum leave a one-sided error of about K / 16 ulp (measured 6e-6
+// relative at K = 300), and the GW loss is a 30:1 cancellation of this product against constC.  Each k-block of 32
+// therefore gets a FRESH accumulator (two TMEM buffers, ping-pong) which four warps add into registers with
+// round-to-nearest while the tensor core works on the next k-block: fp32 blocked summation, error ~ sqrt(K / 32) ulp.
+__global__ void __launch_bounds__(GB_THREADS, 1) k_gemm_nt_3xtf32(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
+                                                                  int M, int N, int K, float alpha, const float* __restrict__ rv,
+                                                                  const float* __restrict__ cv, int vecA, int vecB, int vecC) {
+  extern __shared__ unsigned char gb_raw[];
+  unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gb_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + (size_t)GB_STAGES * GB_STAGE_BYTES);  // full[S], empty[S], tfull[2], tempty[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * GB_STAGES + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * GB_M, n0 = blockIdx.x * GB_N;
+  const int nkb = (K + GB_K - 1) / GB_K;
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * (uint32_t)s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (uint32_t)(GB_STAGES + s); };
+  auto tfull_bar = [&](int q) { return bar0 + 8u * (uint32_t)(2 * GB_STAGES + q); };
+  auto tempty_bar = [&](int q) { return bar0 + 8u * (uint32_t)(2 * GB_STAGES + 2 + q); };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < GB_STAGES; ++s) {
+      mbar_init(full_bar(s), 128);  // every producer thread arrives
+      mbar_init(empty_bar(s), 1);   // one tcgen05.commit
+    }
+    for (int q = 0; q < 2; ++q) {
+      mbar_init(tfull_bar(q), 1);     // one tcgen05.commit
+      mbar_init(tempty_bar(q), 128);  // every accumulator thread arrives
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {  // TMEM: 128 lanes x 2 x 128 fp32 columns (two accumulator buffers)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(2 * GB_N) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (warp < 4) {
+    // ---- producers ----
+    const int t = threadIdx.x;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % GB_STAGES;
+      const uint32_t round = (uint32_t)(kb / GB_STAGES);
+      mbar_wait(empty_bar(s), (round & 1u) ^ 1u);  // a fresh barrier passes the wait on parity 1
+      unsigned char* st = tiles + (size_t)s * GB_STAGE_BYTES;
+      gb_stage_tile(A, M, K, m0, kb * GB_K, vecA != 0, st, st + GB_TILE_BYTES, t);
+      gb_stage_tile(B, N, K, n0, kb * GB_K, vecB != 0, st + 2 * GB_TILE_BYTES, st + 3 * GB_TILE_BYTES, t);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core's async proxy
+      mbar_arrive(full_bar(s));
+    }
+  } else if (warp < 8) {
+    // ---- accumulators: TMEM -> registers after every k-block, then the epilogue ----
+    const int wq = warp - 4;                // == warp % 4: this warp may touch TMEM lanes 32 wq .. 32 wq + 31
+    const int row = m0 + wq * 32 + lane;
+    float acc[GB_N];
+#pragma unroll
+    for (int j = 0; j < GB_N; ++j) acc[j] = 0.f;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int q = kb & 1;
+      mbar_wait(tfull_bar(q), (uint32_t)(kb >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < GB_N; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_d + ((uint32_t)(wq * 32) << 16) + (uint32_t)(q * GB_N + c0), r);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(q));  // this buffer may be overwritten
+    }
+    if (row < M) {
+      const float rvv = rv ? rv[row] : 0.f;
+      float* dst = C + (size_t)row * N + n0;
+#pragma unroll
+      for (int j = 0; j < GB_N; j += 4) {
+        const int col = n0 + j;
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = alpha * acc[j + e] + rvv + ((cv && col + e < N) ? __ldg(cv + col + e) : 0.f);
+        if (vecC && col + 4 <= N) {
+          *reinterpret_cast<float4*>(dst + j) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (col + e < N) dst[j + e] = o[e];
+        }
+      }
+    }
+  } else if (lane == 0) {
+    // ---- MMA issuer: one thread ----
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % GB_STAGES, q = kb & 1;
+      mbar_wait(tempty_bar(q), ((uint32_t)(kb >> 1) & 1u) ^ 1u);  // accumulator buffer drained (passes at once the first time)
+      mbar_wait(full_bar(s), (uint32_t)(kb / GB_STAGES) & 1u);
+      tc_fence_after();
+      const uint32_t st = smem_u32(tiles + (size_t)s * GB_STAGE_BYTES);
+      const uint32_t td = tmem_d + (uint32_t)(q * GB_N);
+      const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + GB_TILE_BYTES);
+      const uint64_t b_hi = umma_desc_sw128(st + 2 * GB_TILE_BYTES), b_lo = umma_desc_sw128(st + 3 * GB_TILE_BYTES);
+#pragma unroll
+      for (int k = 0; k < GB_K / 8; ++k) {  // UMMA K = 8 TF32 = 32 bytes: advance the start address inside the swizzle row
+        const uint64_t adv = (uint64_t)((k * 32) >> 4);
+        // small terms first: they are added into a small accumulator
+        umma_tf32(td, a_lo + adv, b_hi + adv, GB_IDESC, k != 0 ? 1u : 0u);
+        umma_tf32(td, a_hi + adv, b_lo + adv, GB_IDESC, 1u);
+      }
+#pragma unroll
+      for (int k = 0; k < GB_K / 8; ++k) {
+        const uint64_t adv = (uint64_t)((k * 32) >> 4);
+        umma_tf32(td, a_hi + adv, b_hi + adv, GB_IDESC, 1u);
+      }
+      umma_commit(empty_bar(s));  // the stage may be refilled once these MMAs have read it
+      umma_commit(tfull_bar(q));  // this k-block's partial product is complete
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 8) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(2 * GB_N) : "memory");
+  }
+}
+
+static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int launch_gemm_nt_3xtf32(const float* A, const float* B, float* C, int M, int N, int K, float alpha, const float* rv, const float* cv,
+                          cudaStream_t stream) {
+  if (M < 1 || N < 1 || K < 1) {
+    set_error("gemm: empty problem");
+    return EVREP_EINVAL;
+  }
+  static bool configured = false;
+  if (!configured) {
+    EVREP_CUDA_OK(cudaFuncSetAttribute(k_gemm_nt_3xtf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GB_SMEM));
+    configured = true;
+  }
+  dim3 grid((unsigned)((N + GB_N - 1) / GB_N), (unsigned)((M + GB_M - 1) / GB_M));
+  k_gemm_nt_3xtf32<<<grid, GB_THREADS, GB_SMEM, stream>>>(A, B, C, M, N, K, alpha, rv, cv, (al16(A) && K % 4 == 0) ? 1 : 0,
+                                                          (al16(B) && K % 4 == 0) ? 1 : 0, (al16(C) && N % 4 == 0) ? 1 : 0);
+  EVREP_CUDA_OK(cudaGetLastError());
+  return EVREP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gaussian kernels and the small dense helpers of the conditional-gradient loop
+// ---------------------------------------------------------------------------------------------
+constexpr int GK_THREADS = 256;
+constexpr int GK_MAX_D = 64;
+
+// mu[k] and mean_ij |xi - xj|^2 = 2/n sum_i |xi - mu|^2 (compute_kernel needs sqrt(mean(C^2) / 2)); one CTA
+__global__ void __launch_bounds__(GK_THREADS) k_gwb_moments(const double* __restrict__ X, int n, int d, double* __restrict__ out /* [0] = mean D^2 */) {
+  __shared__ double mu[GK_MAX_D];
+  __shared__ double red[GK_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int k = 0; k < d; ++k) {
+    double s = 0.0;
+    for (int i = tid; i < n; i += GK_THREADS) s += X[(size_t)i * d + k];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    if (tid == 0) {
+      double a = 0.0;
+      for (int q = 0; q < GK_THREADS / 32; ++q) a += red[q];
+      mu[k] = a / n;
+    }
+    __syncthreads();
+  }
+  double s = 0.0;
+  for (int i = tid; i < n; i += GK_THREADS)
+    for (int k = 0; k < d; ++k) {
+      const double v = X[(size_t)i * d + k] - mu[k];
+      s += v * v;
+    }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  if (tid == 0) {
+    double a = 0.0;
+    for (int q = 0; q < GK_THREADS / 32; ++q) a += red[q];
+    out[0] = 2.0 * a / n;
+  }
+}
+
+// One row of the kernel per CTA: K[i, j] = exp(-|xi - xj|^2 / (2 h^2 std^2)) in fp64, stored as fp32 (`Kf`, or its
+// log(K + 1e-15) when want_log), plus the fp64 row sums the KL decomposition needs:
+//   rs_a[i] = sum_j (K log(K + 1e-15) - K)   (f1, source side)     or   sum_j K         (f2, target side, want_log)
+//   rs_h[i] = sum_j hC[i, j]  (K on the source side, log(K + 1e-15) on the target side): A(p q^T) is rank one
+__global__ void __launch_bounds__(GK_THREADS) k_gwb_kernel_rows(const double* __restrict__ X, int n, int d, double h, const double* __restrict__ msq,
+                                                                int want_log, float* __restrict__ Kf, double* __restrict__ rs_a,
+                                                                double* __restrict__ rs_h) {
+  __shared__ double xi[GK_MAX_D];
+  __shared__ double red[2][GK_THREADS / 32];
+  const int i = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < d) xi[tid] = X[(size_t)i * d + tid];
+  __syncthreads();
+  const double std2 = msq[0] / 2.0;           // std^2 = mean(C^2) / 2
+  const double coef = -0.5 / (h * h * std2);  // K = exp(coef * D^2)
+  double sa = 0.0, sh = 0.0;
+  for (int j = tid; j < n; j += GK_THREADS) {
+    double d2 = 0.0;
+    for (int k = 0; k < d; ++k) {
+      const double v = xi[k] - X[(size_t)j * d + k];
+      d2 += v * v;
+    }
+    const double kv = exp(coef * d2);
+    const double lg = log(kv + 1e-15);
+    if (want_log) {
+      Kf[(size_t)i * n + j] = (float)lg;
+      sa += kv;
+      sh += lg;
+    } else {
+      Kf[(size_t)i * n + j] = (float)kv;
+      sa += kv * lg - kv;
+      sh += kv;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    sa += __shfl_xor_sync(0xffffffffu, sa, o);
+    sh += __shfl_xor_sync(0xffffffffu, sh, o);
+  }
+  if (lane == 0) { red[0][warp] = sa; red[1][warp] = sh; }
+  __syncthreads();
+  if (tid == 0) {
+    double a = 0.0, b = 0.0;
+    for (int q = 0; q < GK_THREADS / 32; ++q) { a += red[0][q]; b += red[1][q]; }
+    rs_a[i] = a;
+    rs_h[i] = b;
+  }
+}
+
+// cr[i] = rs_a1[i] / n (f1(Ks) p), cc[j] = rs_a2[j] / m (f2(Kt) q); AG = (rs_h1[i] / n) (rs_h2[j] / m) = hC1 (p q^T) hC2^T; G = 1 / (n m)
+__global__ void k_gwb_init(int n, int m, const double* __restrict__ rs_a1, const double* __restrict__ rs_a2, const double* __restrict__ rs_h1,
+                           const double* __restrict__ rs_h2, float* __restrict__ cr, float* __restrict__ cc, float* __restrict__ G,
+                           float* __restrict__ AG) {
+  const size_t total = (size_t)n * m;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / m), j = (int)(e - (size_t)i * m);
+    G[e] = (float)(1.0 / ((double)n * (double)m));
+    AG[e] = (float)((rs_h1[i] / n) * (rs_h2[j] / m));
+    if (j == 0) cr[i] = (float)(rs_a1[i] / n);
+    if (i == 0) cc[j] = (float)(rs_a2[j] / m);
+  }
+}
+
+// Bp[j, k] = hC2[j, sigma[k]]: the gather that turns hC1 Gc hC2^T (Gc = permutation / n) into one GEMM
+__global__ void k_gwb_gather(const float* __restrict__ hC2, const int* __restrict__ sigma, int m, int n, float* __restrict__ Bp) {
+  const size_t total = (size_t)m * n;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(e / n), k = (int)(e - (size_t)j * n);
+    Bp[e] = hC2[(size_t)j * m + sigma[k]];
+  }
+}
+
+// Mi = constC - AG (the gradient up to the factor 2 and a constant shift, neither changes the LMO), and
+// red[0] += sum Mi * G  (= the GW loss at G)
+__global__ void __launch_bounds__(256) k_gwb_grad(int n, int m, const float* __restrict__ cr, const float* __restrict__ cc, const float* __restrict__ AG,
+                                                  const float* __restrict__ G, float* __restrict__ Mi, double* __restrict__ red) {
+  const size_t total = (size_t)n * m;
+  double s = 0.0;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / m), j = (int)(e - (size_t)i * m);
+    const float v = cr[i] + cc[j] - AG[e];
+    Mi[e] = v;
+    s += (double)v * (double)G[e];
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(red, s);
+}
+
+// line-search sums with Gc = permutation / n given as sigma, dG = Gc - G, AdG = AGc - AG:
+//   red[0] = sum AdG * dG,  red[1] = sum constC * dG,  red[2] = sum AG * dG,  red[3] = sum AdG * G
+__global__ void __launch_bounds__(256) k_gwb_linesearch(int n, int m, const float* __restrict__ cr, const float* __restrict__ cc,
+                                                        const float* __restrict__ AG, const float* __restrict__ AGc, const float* __restrict__ G,
+                                                        const int* __restrict__ sigma, double* __restrict__ red) {
+  const size_t total = (size_t)n * m;
+  const double inv_n = 1.0 / (double)n;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / m), j = (int)(e - (size_t)i * m);
+    const double g = (double)G[e];
+    const double dg = ((sigma[i] == j) ? inv_n : 0.0) - g;
+    const double ag = (double)AG[e];
+    const double adg = (double)AGc[e] - ag;
+    s0 += adg * dg;
+    s1 += ((double)cr[i] + (double)cc[j]) * dg;
+    s2 += ag * dg;
+    s3 += adg * g;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(red + 0, s0);
+    atomicAdd(red + 1, s1);
+    atomicAdd(red + 2, s2);
+    atomicAdd(red + 3, s3);
+  }
+}
+
+// G += alpha (Gc - G),  AG += alpha (AGc - AG)
+__global__ void k_gwb_step(int n, int m, float alpha, const int* __restrict__ sigma, const float* __restrict__ AGc, float* __restrict__ G,
+                           float* __restrict__ AG) {
+  const size_t total = (size_t)n * m;
+  const float inv_n = 1.f / (float)n;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / m), j = (int)(e - (size_t)i * m);
+    const float g = G[e], ag = AG[e];
+    G[e] = g + alpha * (((sigma[i] == j) ? inv_n : 0.f) - g);
+    AG[e] = ag + alpha * (AGc[e] - ag);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host: linear assignment (shortest augmenting paths with potentials, O(n^3)), the exact LMO for n == m
+// ---------------------------------------------------------------------------------------------
+static void lap_solve(const float* cost, int n, std::vector<int>& row_to_col) {
+  const double INF = DBL_MAX;
+  std::vector<double> u(n + 1, 0.0), v(n + 1, 0.0), minv(n + 1);
+  std::vector<int> p(n + 1, 0), way(n + 1, 0);
+  std::vector<char> used(n + 1);
+  for (int i = 1; i <= n; ++i) {
+    p[0] = i;
+    int j0 = 0;
+    std::fill(minv.begin(), minv.end(), INF);
+    std::fill(used.begin(), used.end(), 0);
+    do {
+      used[j0] = 1;
+      const int i0 = p[j0];
+      const float* crow = cost + (size_t)(i0 - 1) * n;
+      double delta = INF;
+      int j1 = 0;
+      for (int j = 1; j <= n; ++j) {
+        if (used[j]) continue;
+        const double cur = (double)crow[j - 1] - u[i0] - v[j];
+        if (cur < minv[j]) { minv[j] = cur; way[j] = j0; }
+        if (minv[j] < delta) { delta = minv[j]; j1 = j; }
+      }
+      for (int j = 0; j <= n; ++j) {
+        if (used[j]) { u[p[j]] += delta; v[j] -= delta; }
+        else minv[j] -= delta;
+      }
+      j0 = j1;
+    } while (p[j0] != 0);
+    do {
+      const int j1 = way[j0];
+      p[j0] = p[j1];
+      j0 = j1;
+    } while (j0);
+  }
+  row_to_col.assign(n, 0);
+  for (int j = 1; j <= n; ++j) row_to_col[p[j] - 1] = j - 1;
+}
+
+struct GwbWs {
+  float *hC1, *hC2, *G, *AG, *AGc, *Mi, *Bp, *cr, *cc;
+  double *rs_a1, *rs_a2, *rs_h1, *rs_h2, *red, *msq;
+  int* sigma;
+  size_t bytes;
+};
+static GwbWs gwb_carve(void* basep, int n, int m) {
+  GwbWs w;
+  size_t off = 0;
+  char* base = (char*)basep;
+  auto take = [&](size_t bytes) {
+    char* p = base ? base + off : nullptr;
+    off += align_up(bytes, 256);
+    return p;
+  };
+  const size_t nm = (size_t)n * m;
+  w.hC1 = (float*)take(sizeof(float) * (size_t)n * n);
+  w.hC2 = (float*)take(sizeof(float) * (size_t)m * m);
+  w.G = (float*)take(sizeof(float) * nm);
+  w.AG = (float*)take(sizeof(float) * nm);
+  w.AGc = (float*)take(sizeof(float) * nm);
+  w.Mi = (float*)take(sizeof(float) * nm);
+  w.Bp = (float*)take(sizeof(float) * nm);
+  w.cr = (float*)take(sizeof(float) * (size_t)n);
+  w.cc = (float*)take(sizeof(float) * (size_t)m);
+  w.rs_a1 = (double*)take(sizeof(double) * (size_t)n);
+  w.rs_h1 = (double*)take(sizeof(double) * (size_t)n);
+  w.rs_a2 = (double*)take(sizeof(double) * (size_t)m);
+  w.rs_h2 = (double*)take(sizeof(double) * (size_t)m);
+  w.red = (double*)take(sizeof(double) * 8);
+  w.msq = (double*)take(sizeof(double) * 2);
+  w.sigma = (int*)take(sizeof(int) * (size_t)n);
+  w.bytes = off;
+  return w;
+}
+size_t gw_kl_workspace_bytes(int n, int m) { return (n < 1 || m < 1) ? 0 : gwb_carve(nullptr, n, m).bytes; }
+
+// Synchronous (the LMO runs on the host between device steps).  Returns the GW loss at the last iterate.
+int run_gw_kl(const double* Xs, int n, int ds, const double* Xt, int m, int dt, double h, int max_iter, double tol_rel, double tol_abs,
+              double* gw_dist_host, float* T_out, int* iters_host, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (n != m) {
+    set_error("gw_kl: only n == m (uniform marginals => the LMO is an assignment problem) is implemented; got n = %d, m = %d", n, m);
+    return EVREP_EUNSUPPORTED;
+  }
+  if (n < 1 || ds < 1 || dt < 1 || ds > GK_MAX_D || dt > GK_MAX_D) {
+    set_error("gw_kl: need n >= 1 and 1 <= ds, dt <= %d", GK_MAX_D);
+    return EVREP_EINVAL;
+  }
+  if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) {
+    set_error("workspace must be non-null and 256-byte aligned");
+    return EVREP_EWORKSPACE;
+  }
+  const GwbWs w = gwb_carve(workspace, n, m);
+  if (w.bytes > workspace_bytes) {
+    set_error("workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
+    return EVREP_EWORKSPACE;
+  }
+  const size_t nm = (size_t)n * m;
+  const int eb = (int)std::min<size_t>((nm + 255) / 256, 148 * 8);
+  // kernels: OTMI.__init__ (gromov_wasserstein.py:52-60)
+  k_gwb_moments<<<1, GK_THREADS, 0, stream>>>(Xs, n, ds, w.msq);
+  k_gwb_moments<<<1, GK_THREADS, 0, stream>>>(Xt, m, dt, w.msq + 1);
+  k_gwb_kernel_rows<<<n, GK_THREADS, 0, stream>>>(Xs, n, ds, h, w.msq, 0, w.hC1, w.rs_a1, w.rs_h1);
+  k_gwb_kernel_rows<<<m, GK_THREADS, 0, stream>>>(Xt, m, dt, h, w.msq + 1, 1, w.hC2, w.rs_a2, w.rs_h2);
+  k_gwb_init<<<eb, 256, 0, stream>>>(n, m, w.rs_a1, w.rs_a2, w.rs_h1, w.rs_h2, w.cr, w.cc, w.G, w.AG);
+  EVREP_CUDA_OK(cudaGetLastError());
+
+  std::vector<float> Mi_host(nm);
+  std::vector<int> sigma;
+  double red_host[4];
+  double f_val = 0.0;
+  int it = 0;
+  for (; it < max_iter; ++it) {
+    EVREP_CUDA_OK(cudaMemsetAsync(w.red, 0, sizeof(double) * 8, stream));
+    k_gwb_grad<<<eb, 256, 0, stream>>>(n, m, w.cr, w.cc, w.AG, w.G, w.Mi, w.red);
+    EVREP_CUDA_OK(cudaMemcpyAsync(Mi_host.data(), w.Mi, sizeof(float) * nm, cudaMemcpyDeviceToHost, stream));
+    EVREP_CUDA_OK(cudaMemcpyAsync(red_host, w.red, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    EVREP_CUDA_OK(cudaStreamSynchronize(stream));
+    if (it == 0) f_val = red_host[0];
+    lap_solve(Mi_host.data(), n, sigma);  // LMO: the vertex of U(p, q) minimising <Mi, G>
+    EVREP_CUDA_OK(cudaMemcpyAsync(w.sigma, sigma.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, stream));
+    // hC1 Gc hC2^T = (1 / n) hC1 (hC2[:, sigma])^T : gather, then the tensor-core contraction
+    k_gwb_gather<<<eb, 256, 0, stream>>>(w.hC2, w.sigma, m, n, w.Bp);
+    const int rc = launch_gemm_nt_3xtf32(w.hC1, w.Bp, w.AGc, n, m, n, 1.f / (float)n, nullptr, nullptr, stream);
+    if (rc) return rc;
+    EVREP_CUDA_OK(cudaMemsetAsync(w.red, 0, sizeof(double) * 8, stream));
+    k_gwb_linesearch<<<eb, 256, 0, stream>>>(n, m, w.cr, w.cc, w.AG, w.AGc, w.G, w.sigma, w.red);
+    EVREP_CUDA_OK(cudaMemcpyAsync(red_host, w.red, sizeof(double) * 4, cudaMemcpyDeviceToHost, stream));
+    EVREP_CUDA_OK(cudaStreamSynchronize(stream));
+    // f(G + alpha dG) = f(G) + b alpha + a alpha^2 with
+    const double a = -red_host[0];
+    const double b = red_host[1] - red_host[2] - red_host[3];
+    double alpha;
+    if (a > 0) alpha = std::min(1.0, std::max(0.0, -b / (2 * a)));
+    else alpha = (a + b < 0) ? 1.0 : 0.0;
+    const double old = f_val;
+    f_val = old + a * alpha * alpha + b * alpha;
+    if (alpha != 0.0) k_gwb_step<<<eb, 256, 0, stream>>>(n, m, (float)alpha, w.sigma, w.AGc, w.G, w.AG);
+    EVREP_CUDA_OK(cudaGetLastError());
+    const double dlt = fabs(f_val - old);
+    if (dlt < tol_abs || dlt / std::max(fabs(f_val), 1e-300) < tol_rel) { ++it; break; }
+  }
+  // the loss at the final plan, from a fresh contraction (two GEMMs: X^T = hC2 G^T, then hC1 X)
+  {
+    int rc = launch_gemm_nt_3xtf32(w.hC2, w.G, w.Bp, m, n, m, 1.f, nullptr, nullptr, stream);  // Bp[j, i] = sum_l hC2[j, l] G[i, l]
+    if (rc) return rc;
+    rc = launch_gemm_nt_3xtf32(w.hC1, w.Bp, w.AG, n, m, n, 1.f, nullptr, nullptr, stream);     // AG[i, j] = sum_k hC1[i, k] Bp[j, k]
+    if (rc) return rc;
+    EVREP_CUDA_OK(cudaMemsetAsync(w.red, 0, sizeof(double) * 8, stream));
+    k_gwb_grad<<<eb, 256, 0, stream>>>(n, m, w.cr, w.cc, w.AG, w.G, w.Mi, w.red);
+    EVREP_CUDA_OK(cudaMemcpyAsync(red_host, w.red, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    if (T_out) EVREP_CUDA_OK(cudaMemcpyAsync(T_out, w.G, sizeof(float) * nm, cudaMemcpyDeviceToDevice, stream));
+    EVREP_CUDA_OK(cudaStreamSynchronize(stream));
+  }
+  if (gw_dist_host) *gw_dist_host = red_host[0];
+  if (iters_host) *iters_host = it;
+  return EVREP_OK;
+}
+
+}  // namespace evrep

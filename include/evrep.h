@@ -28,6 +28,9 @@
  *                                representation_search/gromov_wasserstein.py:72-82 (compute_repr)
  *   evrep_histogram_batched      tonic ToImage (gen1_transforms.py:44-49)
  *   evrep_gwd_kernel_l1          representation_search/compute_otmi.py:50-93 (OTMI.__init__ + solve, GWD-A)
+ *   evrep_gw_kl                  representation_search/gromov_wasserstein.py:39-69 (OTMI.__init__ + solve, GWD-B:
+ *                                POT ot.gromov.gromov_wasserstein(Ks, Kt, p, q, "kl_loss"))
+ *   evrep_gemm_nt_3xtf32         the tensor product constC - hC1 T hC2^T inside that solve (POT ot/gromov tensor_product)
  */
 #ifndef EVREP_H
 #define EVREP_H
@@ -173,6 +176,25 @@ size_t evrep_gwd_workspace_bytes(const int64_t* s_offsets, const int64_t* t_offs
 int evrep_gwd_kernel_l1(const double* Xs, const int64_t* s_offsets, int ds, const double* Xt, const int64_t* t_offsets,
                         int dt, int n_pairs, double h, double* out, void* workspace, size_t workspace_bytes,
                         evrep_stream_t stream);
+
+/* GWD-B for ONE pair: builds the Gaussian kernels Ks (n x n) and Kt (m x m) of Xs (n x ds) and Xt (m x dt) (DEVICE
+ * float64, row major, bandwidth h * std as in compute_kernel), then runs conditional-gradient Gromov-Wasserstein with
+ * the KL loss from T = p q^T (uniform p, q) until the loss changes by less than tol_abs or tol_rel (POT: 1e-9, 1e-9)
+ * or max_iter (POT: 10000) steps.  Writes the loss at the final plan to *gw_dist (HOST), the iteration count to *iters
+ * (HOST, may be NULL) and the plan to T_out (DEVICE float32 n x m, may be NULL).  The dense contraction of every step
+ * runs on the tensor cores (evrep_gemm_nt_3xtf32); the linear minimisation oracle is an exact assignment solve on
+ * the host, so the call SYNCHRONISES the stream every iteration.  Implemented for n == m only (uniform marginals make
+ * every vertex a permutation); EVREP_EUNSUPPORTED otherwise.  ds, dt <= 64. */
+size_t evrep_gw_kl_workspace_bytes(int n, int m);
+int evrep_gw_kl(const double* Xs, int n, int ds, const double* Xt, int m, int dt, double h, int max_iter, double tol_rel,
+                double tol_abs, double* gw_dist, float* T_out, int* iters, void* workspace, size_t workspace_bytes,
+                evrep_stream_t stream);
+
+/* C[M x N] = alpha * A[M x K] * B[N x K]^T + rv[i] + cv[j] on the tcgen05 tensor cores: every fp32 operand is split
+ * into two TF32 terms while it is staged and hi*hi + lo*hi + hi*lo is accumulated in fp32 (error about 2^-21 relative
+ * to |A| |B|).  All pointers DEVICE float32, row major, K contiguous in A and B; rv (M) and cv (N) may be NULL. */
+int evrep_gemm_nt_3xtf32(const float* A, const float* B, float* C, int M, int N, int K, float alpha, const float* rv,
+                         const float* cv, evrep_stream_t stream);
 
 #ifdef __cplusplus
 }
