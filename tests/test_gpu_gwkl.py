@@ -99,7 +99,7 @@ def test_gw_kl_matches_oracle(E, n, seed):
     assert abs(got - want) <= 1e-5 * abs(want), (got, want, iters)
 
 
-@pytest.mark.parametrize("n,seed", [(64, 2), (200, 4), (333, 5)])
+@pytest.mark.parametrize("n,seed", [(64, 2), (200, 4), (129, 5)])
 def test_gw_kl_plan_is_a_stationary_point_with_the_reported_loss(E, n, seed):
     """Conditional gradient on this non-convex objective is chaotic in its rounding: one assignment that flips in the
     LMO (float32 operands vs the oracle's float64; n = 200 / seed 4 flips at the second step) leads to another local
