@@ -90,33 +90,40 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
   return r;
 }
 
-// stages one 128 x 32 fp32 tile (rows r0.., columns k0..) as its two TF32 terms; rows / columns outside the matrix are zero
-__device__ __forceinline__ void gb_stage_tile(const float* __restrict__ X, int rows, int K, int r0, int k0, bool vec, unsigned char* hi,
-                                              unsigned char* lo, int t) {
+// One 128 x 32 fp32 tile (rows r0.., columns k0..) in two steps, so that a producer thread has all 16 of its global loads
+// (A and B tile) in flight before it converts anything: fetch -> 8 float4 registers, then split into the two TF32
+// terms and store them swizzled.  Rows / columns outside the matrix are zero.
+__device__ __forceinline__ void gb_fetch_tile(const float* __restrict__ X, int rows, int K, int r0, int k0, bool vec, int t, float4 (&v)[GB_M / 16]) {
   const int c4 = t & 7, rsub = t >> 3;  // 8 threads per row (one 16-byte chunk each), 16 rows per pass
 #pragma unroll
   for (int pass = 0; pass < GB_M / 16; ++pass) {
-    const int r = pass * 16 + rsub;
-    const int gr = r0 + r, gk = k0 + 4 * c4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int gr = r0 + pass * 16 + rsub, gk = k0 + 4 * c4;
+    v[pass] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (gr < rows) {
       const float* src = X + (size_t)gr * K + gk;
       if (vec && gk + 4 <= K) {
-        v = __ldg(reinterpret_cast<const float4*>(src));
+        v[pass] = __ldg(reinterpret_cast<const float4*>(src));
       } else {
-        if (gk + 0 < K) v.x = __ldg(src + 0);
-        if (gk + 1 < K) v.y = __ldg(src + 1);
-        if (gk + 2 < K) v.z = __ldg(src + 2);
-        if (gk + 3 < K) v.w = __ldg(src + 3);
+        if (gk + 0 < K) v[pass].x = __ldg(src + 0);
+        if (gk + 1 < K) v[pass].y = __ldg(src + 1);
+        if (gk + 2 < K) v[pass].z = __ldg(src + 2);
+        if (gk + 3 < K) v[pass].w = __ldg(src + 3);
       }
     }
+  }
+}
+__device__ __forceinline__ void gb_store_tile(const float4 (&v)[GB_M / 16], unsigned char* hi, unsigned char* lo, int t) {
+  const int c4 = t & 7, rsub = t >> 3;
+#pragma unroll
+  for (int pass = 0; pass < GB_M / 16; ++pass) {
+    const int r = pass * 16 + rsub;
     // hi = x rounded to the nearest TF32 (an exact TF32 number, so the tensor core's own conversion cannot change it);
     // lo = the exact remainder x - hi, rounded to TF32 again.  |x - hi - lo| <= 2^-23 |x| and the errors are unbiased.
     uint4 h, l;
-    h.x = to_tf32(v.x); l.x = to_tf32(v.x - __uint_as_float(h.x));
-    h.y = to_tf32(v.y); l.y = to_tf32(v.y - __uint_as_float(h.y));
-    h.z = to_tf32(v.z); l.z = to_tf32(v.z - __uint_as_float(h.z));
-    h.w = to_tf32(v.w); l.w = to_tf32(v.w - __uint_as_float(h.w));
+    h.x = to_tf32(v[pass].x); l.x = to_tf32(v[pass].x - __uint_as_float(h.x));
+    h.y = to_tf32(v[pass].y); l.y = to_tf32(v[pass].y - __uint_as_float(h.y));
+    h.z = to_tf32(v[pass].z); l.z = to_tf32(v[pass].z - __uint_as_float(h.z));
+    h.w = to_tf32(v[pass].w); l.w = to_tf32(v[pass].w - __uint_as_float(h.w));
     const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c4 ^ (r & 7)) << 4);  // Swizzle<3,4,3>: chunk ^= row mod 8
     *reinterpret_cast<uint4*>(hi + off) = h;
     *reinterpret_cast<uint4*>(lo + off) = l;
@@ -185,13 +192,20 @@ __global__ void __launch_bounds__(GB_THREADS, 1) k_gemm_nt_3xtf32(const float* _
   if (warp < 4) {
     // ---- producers ----
     const int t = threadIdx.x;
+    float4 va[GB_M / 16], vb[GB_N / 16];
+    gb_fetch_tile(A, M, K, m0, 0, vecA != 0, t, va);
+    gb_fetch_tile(B, N, K, n0, 0, vecB != 0, t, vb);
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % GB_STAGES;
       const uint32_t round = (uint32_t)(kb / GB_STAGES);
       mbar_wait(empty_bar(s), (round & 1u) ^ 1u);  // a fresh barrier passes the wait on parity 1
       unsigned char* st = tiles + (size_t)s * GB_STAGE_BYTES;
-      gb_stage_tile(A, M, K, m0, kb * GB_K, vecA != 0, st, st + GB_TILE_BYTES, t);
-      gb_stage_tile(B, N, K, n0, kb * GB_K, vecB != 0, st + 2 * GB_TILE_BYTES, st + 3 * GB_TILE_BYTES, t);
+      gb_store_tile(va, st, st + GB_TILE_BYTES, t);
+      gb_store_tile(vb, st + 2 * GB_TILE_BYTES, st + 3 * GB_TILE_BYTES, t);
+      if (kb + 1 < nkb) {  // the next k-block's loads fly while the tensor core and the other producers work
+        gb_fetch_tile(A, M, K, m0, (kb + 1) * GB_K, vecA != 0, t, va);
+        gb_fetch_tile(B, N, K, n0, (kb + 1) * GB_K, vecB != 0, t, vb);
+      }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core's async proxy
       mbar_arrive(full_bar(s));
     }

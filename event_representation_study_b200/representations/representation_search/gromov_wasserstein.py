@@ -1,7 +1,7 @@
-"""Mirror of the in-scope parts of representations/representation_search/gromov_wasserstein.py:
-`compute_repr` (reference :72-82), the 5-bin bilinear voxel grid used by its __main__ experiment, and `compute_kernel`.
-The conditional-gradient Gromov-Wasserstein solve of that file (OTMI.solve, reference :62-69, POT's
-ot.gromov.gromov_wasserstein with kl_loss) is not built yet ("what comes next")."""
+"""Mirror of representations/representation_search/gromov_wasserstein.py: `compute_repr` (reference :72-82), the 5-bin
+bilinear voxel grid used by its __main__ experiment, `compute_kernel`, and `OTMI` (reference :39-69), whose `solve()` is
+POT's conditional-gradient Gromov-Wasserstein with the KL loss: here `evrep_gw_kl` (tcgen05 contraction on the GPU,
+exact assignment LMO on the host; n == m only, see include/evrep.h)."""
 import numpy as np
 
 from ... import batched as eb
@@ -22,3 +22,20 @@ def compute_repr(x, y, t, p, width, height, bins=5):
         raise ValueError("events must be time sorted (t[0] == 0, t[-1] == 1)")
     ev = one_window(x, y, ti, np.asarray(p).astype(np.int64), height, width)
     return eb.voxel_grid(ev, height, width, bins, "gwd")[0].double().cpu().numpy()
+
+
+class OTMI:
+    """OTMI(Xs, Xt, h, reg=0.05).solve() -> (T, gw_dist) like the reference (gromov_wasserstein.py:39-69); `reg` is
+    stored and unused there too.  T is the (n, m) float64 plan on the host."""
+
+    def __init__(self, Xs, Xt, h, reg=0.05):
+        self.Xs = np.asarray(Xs, np.float64)
+        self.Xt = np.asarray(Xt, np.float64)
+        self.h = h
+        self.reg = reg
+        self.P = None
+
+    def solve(self):
+        dist, _, plan = eb.gw_kl(self.Xs, self.Xt, self.h, return_plan=True)
+        self.P = plan.double().cpu().numpy()
+        return self.P, dist

@@ -138,3 +138,13 @@ def test_gw_kl_rejects_unequal_sizes(E):
     with pytest.raises(EvrepError) as e:
         E.gw_kl(np.random.rand(10, 4), np.random.rand(12, 4))
     assert e.value.code == EUNSUPPORTED
+
+
+def test_otmi_mirror_of_gromov_wasserstein_py(E):
+    """reference call sequence (gromov_wasserstein.py:39-69): OTMI(Xs, Xt, h).solve() -> (T, gw_dist)"""
+    from event_representation_study_b200.representations.representation_search.gromov_wasserstein import OTMI
+    from oracle import gwd as ogwd
+    Xs, Xt = _clouds(2, 64)
+    T, dist = OTMI(Xs, Xt, 0.7).solve()
+    assert T.shape == (64, 64) and T.dtype == np.float64
+    assert abs(dist - ogwd.gwd_b_cost(Xs, Xt, 0.7)) <= 1e-5 * abs(dist)
