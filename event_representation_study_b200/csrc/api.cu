@@ -312,7 +312,9 @@ int evrep_tore_batched(const uint16_t* x, const uint16_t* y, const void* t, int 
   if (B == 0) return EVREP_OK;
   Geom g;
   memset(&g, 0, sizeof(g));
-  EVREP_TRY(choose_tile(H, W, (size_t)8 * k, &g));
+  // 8 k bytes of accumulators per pixel; the k = 6 kernel also stages 24 KB of output, which would leave one 2048-pixel
+  // CTA per SM: ask for 1024-pixel tiles there (72 KB, three CTAs per SM)
+  EVREP_TRY(choose_tile(H, W, (size_t)8 * k + (k == 6 ? 12 : 0), &g));
   g.B = B;
   g.total = total;
   Workspace ws;

@@ -59,7 +59,75 @@ __global__ void __launch_bounds__(TILE_THREADS) k_event_stack_tile(const uint2* 
   }
 }
 
+// Compile-time K (the reference's stack_size = 12): one thread per pixel computes all K channels, the K floats of 512
+// pixels are staged in shared memory ([pixel][K], 16-byte stores at a 48-byte stride are conflict free) and leave as
+// consecutive float4: no integer division, no per-element address arithmetic (ncu r01: the generic kernel spent 38
+// instructions per output element and was issue bound at 42 % of the DRAM peak).
+template <int K>
+__global__ void __launch_bounds__(TILE_THREADS) k_event_stack_tile_k(const uint2* __restrict__ records, const uint32_t* __restrict__ base,
+                                                                     const uint32_t* __restrict__ hist, const WinParams* __restrict__ wp,
+                                                                     const Geom g, float* __restrict__ out) {
+  static_assert(K % 4 == 0, "float4 staging");
+  extern __shared__ __align__(16) uint32_t acc[];  // TP accumulators, then TILE_THREADS * K staged floats
+  __shared__ uint32_t s_start[K];
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x / g.T, tile = blockIdx.x - b * g.T;
+  const int TP = g.tile_px, pix0 = tile << g.tile_shift, npix = min(TP, g.HW - pix0);
+  float4* stage = reinterpret_cast<float4*>(acc + TP);
+  zero_smem(acc, TP);
+  const WinParams w = wp[b];
+  if (tid == 0) {
+    int64_t c = w.n, st = 0;
+    for (int k = 0; k < K; ++k) {
+      s_start[k] = (uint32_t)min(st, w.n);
+      c /= 2;
+      st += c;
+    }
+  }
+  const uint32_t count = hist[blockIdx.x];
+  const uint2* rec = records + w.start + base[blockIdx.x];
+  __syncthreads();
+  for (uint32_t i = tid; i < count; i += TILE_THREADS) {
+    const uint2 r = __ldg(rec + i);
+    if (rec_is_null(r.y)) continue;
+    const uint32_t pol = (((r.y >> 24) & 3u) == 1u) ? 1u : 0u;  // p > 0
+    atomicMax(&acc[r.y & 0xffffu], ((r.x + 1u) << 1) | pol);
+  }
+  __syncthreads();
+  uint32_t start[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) start[k] = s_start[k];
+  float4* dst4 = reinterpret_cast<float4*>(out + ((size_t)b * g.HW + pix0) * K);
+  for (int p0 = 0; p0 < npix; p0 += TILE_THREADS) {
+    const uint32_t v = (p0 + tid < npix) ? acc[p0 + tid] : 0u;
+    const float sgn = (v & 1u) ? 1.f : -1.f;
+    const uint32_t idx = (v >> 1) - 1u;  // v == 0: 0xffffffff, masked by the v test
+    float o[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) o[k] = (v && idx >= start[k]) ? sgn : 0.f;
+#pragma unroll
+    for (int q = 0; q < K / 4; ++q) stage[tid * (K / 4) + q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+    __syncthreads();
+    const int n4 = min(TILE_THREADS, npix - p0) * (K / 4);
+#pragma unroll
+    for (int q = 0; q < K / 4; ++q) {
+      const int e = q * TILE_THREADS + tid;
+      if (e < n4) __stcs(dst4 + (size_t)p0 * (K / 4) + e, stage[e]);
+    }
+    __syncthreads();
+  }
+}
+
 int launch_event_stack_tile(const Geom& g, const Workspace& ws, int stack_size, float* out, cudaStream_t stream) {
+  if (stack_size == 12 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
+    const size_t smem12 = sizeof(uint32_t) * (size_t)g.tile_px + sizeof(float) * 12 * TILE_THREADS;
+    EVREP_CUDA_OK(cudaFuncSetAttribute(k_event_stack_tile_k<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem12));
+    prof_begin(EVREP_K_TILE, stream);
+    k_event_stack_tile_k<12><<<g.B * g.T, TILE_THREADS, smem12, stream>>>(ws.records, ws.base, ws.hist, ws.wp, g, out);
+    prof_end(EVREP_K_TILE, stream);
+    EVREP_CUDA_OK(cudaGetLastError());
+    return EVREP_OK;
+  }
   const size_t smem = sizeof(uint32_t) * (size_t)g.tile_px;
   EVREP_CUDA_OK(cudaFuncSetAttribute(k_event_stack_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   prof_begin(EVREP_K_TILE, stream);
@@ -128,7 +196,78 @@ __global__ void __launch_bounds__(TILE_THREADS) k_time_surface_tile(const uint2*
   }
 }
 
+// Compile-time S (the reference's 6 snapshots): the snapshot loop is unrolled, the running maximum lives in a register
+// and the S stores of a thread go to one base pointer plus constant strides (the generic kernel: 62 instructions per
+// output element, issue bound at 23 % of the DRAM peak).
+template <int S>
+__global__ void __launch_bounds__(TILE_THREADS) k_time_surface_tile_s(const uint2* __restrict__ records, const uint32_t* __restrict__ base,
+                                                                      const uint32_t* __restrict__ hist, const WinParams* __restrict__ wp,
+                                                                      const SnapParams* __restrict__ snap, const Geom g, double tau,
+                                                                      float* __restrict__ out) {
+  extern __shared__ __align__(16) uint32_t acc[];  // [S][2][TP]
+  __shared__ int32_t s_trel[S];
+  __shared__ float s_empty[S];
+  __shared__ int s_nvalid;
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x / g.T, tile = blockIdx.x - b * g.T;
+  const int TP = g.tile_px, pix0 = tile << g.tile_shift, npix = min(TP, g.HW - pix0);
+  zero_smem(acc, S * 2 * TP);
+  const WinParams w = wp[b];
+  if (tid < S) {
+    const int32_t tr = snap[b].t_rel[tid];
+    s_trel[tid] = tr;
+    // untouched pixels: exp((-(3 tau + 1) - t_snapshot) / tau) with the ABSOLUTE snapshot timestamp
+    s_empty[tid] = (float)exp((-(tau * 3.0 + 1.0) - (double)(w.t_base + (int64_t)tr)) / tau);
+  }
+  if (tid == 0) s_nvalid = snap[b].n_valid;
+  const uint32_t count = hist[blockIdx.x];
+  const uint2* rec = records + w.start + base[blockIdx.x];
+  const int32_t tmin = w.tmin_rel;
+  __syncthreads();
+  for (uint32_t i = tid; i < count; i += TILE_THREADS) {
+    const uint2 r = __ldg(rec + i);
+    if (rec_is_null(r.y)) continue;
+    const uint32_t sn = (r.y >> 16) & 0xffu;
+    const uint32_t plane = (((r.y >> 24) & 3u) == 1u) ? 1u : 0u;
+    atomicMax(&acc[(sn * 2u + plane) * TP + (r.y & 0xffffu)], (uint32_t)((int32_t)r.x - tmin) + 1u);
+  }
+  __syncthreads();
+  const double inv_tau = 1.0 / tau;
+  const int nvalid = s_nvalid;
+  int32_t trel[S];
+  float empty[S];
+#pragma unroll
+  for (int k = 0; k < S; ++k) {
+    trel[k] = s_trel[k] - tmin + 1;  // compare against the stored key (t - tmin + 1)
+    empty[k] = k < nvalid ? s_empty[k] : 0.f;
+  }
+  const size_t plane_stride = (size_t)g.HW, snap_stride = 2 * (size_t)g.HW;
+  for (int plane = 0; plane < 2; ++plane) {
+    float* dst = out + ((size_t)b * S * 2 + plane) * plane_stride + pix0;
+    for (int pix = tid; pix < npix; pix += TILE_THREADS) {
+      uint32_t m = 0;
+#pragma unroll
+      for (int k = 0; k < S; ++k) {
+        m = max(m, acc[(k * 2 + plane) * TP + pix]);
+        float o = empty[k];
+        // (mem - t_snapshot) / tau with mem = key - 1 + tmin, t_snapshot = trel - 1 + tmin: the difference of the keys
+        if (m && k < nvalid) o = expf((float)((double)((int32_t)m - trel[k]) * inv_tau));
+        __stcs(dst + k * snap_stride + pix, o);
+      }
+    }
+  }
+}
+
 int launch_time_surface_tile(const Geom& g, const Workspace& ws, int S, double tau, float* out, cudaStream_t stream) {
+  if (S == 6) {
+    const size_t smem6 = sizeof(uint32_t) * (size_t)g.tile_px * 2 * 6;
+    EVREP_CUDA_OK(cudaFuncSetAttribute(k_time_surface_tile_s<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));
+    prof_begin(EVREP_K_TILE, stream);
+    k_time_surface_tile_s<6><<<g.B * g.T, TILE_THREADS, smem6, stream>>>(ws.records, ws.base, ws.hist, ws.wp, ws.snap, g, tau, out);
+    prof_end(EVREP_K_TILE, stream);
+    EVREP_CUDA_OK(cudaGetLastError());
+    return EVREP_OK;
+  }
   const size_t smem = sizeof(uint32_t) * (size_t)g.tile_px * 2 * S;
   EVREP_CUDA_OK(cudaFuncSetAttribute(k_time_surface_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   prof_begin(EVREP_K_TILE, stream);
@@ -189,7 +328,82 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tore_tile(const uint2* __restr
   }
 }
 
+// Compile-time K (the reference's k = 6): one thread per pixel, 2K outputs staged as [pixel][2K] and copied out as
+// consecutive float4; logf only runs for warps that hold a filled slot (slots beyond the first are nearly always empty).
+template <int K>
+__global__ void __launch_bounds__(TILE_THREADS) k_tore_tile_k(const uint2* __restrict__ records, const uint32_t* __restrict__ base,
+                                                              const uint32_t* __restrict__ hist, const WinParams* __restrict__ wp,
+                                                              const Geom g, float* __restrict__ out) {
+  constexpr int C = 2 * K;
+  static_assert(C % 4 == 0, "float4 staging");
+  extern __shared__ __align__(16) uint32_t acc[];  // [2][K][TP], then TILE_THREADS * C staged floats
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x / g.T, tile = blockIdx.x - b * g.T;
+  const int TP = g.tile_px, pix0 = tile << g.tile_shift, npix = min(TP, g.HW - pix0);
+  float4* stage = reinterpret_cast<float4*>(acc + C * TP);
+  zero_smem(acc, C * TP);
+  const WinParams w = wp[b];
+  const uint32_t count = hist[blockIdx.x];
+  const uint2* rec = records + w.start + base[blockIdx.x];
+  const int32_t tmin = w.tmin_rel;
+  __syncthreads();
+  for (uint32_t i = tid; i < count; i += TILE_THREADS) {
+    const uint2 r = __ldg(rec + i);
+    if (rec_is_null(r.y)) continue;
+    const uint32_t plane = (((r.y >> 24) & 3u) == 1u) ? 0u : 1u;  // positive first (tore.py:63-65)
+    uint32_t v = (uint32_t)((int32_t)r.x - tmin) + 1u;
+    uint32_t* slot = &acc[plane * K * TP + (r.y & 0xffffu)];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      if (!v) break;
+      const uint32_t old = atomicMax(slot + j * TP, v);
+      v = min(old, v);
+    }
+  }
+  __syncthreads();
+  const float max_time = 500e6f;
+  const float log151 = (float)log(151.0);
+  const float empty = fmaxf(logf(max_time + 1.f) - log151, 0.f);
+  const int32_t age0 = w.tlast_rel - tmin + 1;  // age = tlast_rel - (key - 1 + tmin)
+  float4* dst4 = reinterpret_cast<float4*>(out + ((size_t)b * g.HW + pix0) * C);
+  for (int p0 = 0; p0 < npix; p0 += TILE_THREADS) {
+    const bool live = p0 + tid < npix;
+    float o[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const uint32_t v = live ? acc[c * TP + p0 + tid] : 0u;
+      o[c] = empty;
+      if (__any_sync(0xffffffffu, v != 0u)) {
+        if (v) {
+          float age = (float)(age0 - (int32_t)v);
+          age = fminf(age, max_time);
+          o[c] = fmaxf(logf(age + 1.f) - log151, 0.f);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < C / 4; ++q) stage[tid * (C / 4) + q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+    __syncthreads();
+    const int n4 = min(TILE_THREADS, npix - p0) * (C / 4);
+#pragma unroll
+    for (int q = 0; q < C / 4; ++q) {
+      const int e = q * TILE_THREADS + tid;
+      if (e < n4) __stcs(dst4 + (size_t)p0 * (C / 4) + e, stage[e]);
+    }
+    __syncthreads();
+  }
+}
+
 int launch_tore_tile(const Geom& g, const Workspace& ws, int k, float* out, cudaStream_t stream) {
+  if (k == 6 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
+    const size_t smem6 = sizeof(uint32_t) * (size_t)g.tile_px * 12 + sizeof(float) * 12 * TILE_THREADS;
+    EVREP_CUDA_OK(cudaFuncSetAttribute(k_tore_tile_k<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));
+    prof_begin(EVREP_K_TILE, stream);
+    k_tore_tile_k<6><<<g.B * g.T, TILE_THREADS, smem6, stream>>>(ws.records, ws.base, ws.hist, ws.wp, g, out);
+    prof_end(EVREP_K_TILE, stream);
+    EVREP_CUDA_OK(cudaGetLastError());
+    return EVREP_OK;
+  }
   const size_t smem = sizeof(uint32_t) * (size_t)g.tile_px * 2 * k;
   EVREP_CUDA_OK(cudaFuncSetAttribute(k_tore_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   prof_begin(EVREP_K_TILE, stream);
