@@ -63,7 +63,7 @@ def rep_line(name, ev_per_step, sec, alg_bytes, cpu_ev_per_s, cpu_note, extra=No
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--only", default="config1,config2,config3,gwd,gwdb")
+    ap.add_argument("--only", default="config1,config2,config3,gwd,gwdb,img")
     a = ap.parse_args()
     import torch
     import event_representation_study_b200.batched as eb
@@ -137,6 +137,23 @@ def main():
                           "cpu_baseline": {"value": 1.0 / c, "unit": "pairs/s", "cores": "numpy/BLAS threads", "kind": "port",
                                            "sample": f"{k} pairs of the same size, oracle gwd_a_cost (closed form of POT's estimate; POT not installable offline)"},
                           "speedup_vs_cpu_port": (R * S / sec) * c}), flush=True)
+
+    if "img" in only:  # representation -> detector input, fused (x255, cv2.resize, letterbox, CHW reversed, /255)
+        from oracle import image_pipeline as oimg
+        for (H, W, B, S, mode, what) in [(720, 1280, 32, 640, "letterbox", "1 Mpx -> 640 INTER_AREA 2x2 + letterbox (gen4_2yolo_raw)"),
+                                         (720, 1280, 32, 640, "squash", "1 Mpx -> 640x640 general INTER_AREA (precompute_reps)"),
+                                         (240, 304, 256, 640, "letterbox", "Gen1 -> 640 INTER_LINEAR + letterbox (gen1_2yolo)")]:
+            rep = torch.rand((B, H, W, 12), device=dev) * (torch.rand((B, H, W, 12), device=dev) < 0.3)
+            out = torch.empty((B, 12, S, S), device=dev)
+            sec = timed(lambda: eb.detector_input(rep, S, mode=mode, out=out), a.steps)
+            one = rep[0].cpu().numpy()
+            c, n = cpu_time(lambda i: oimg.detector_input(one, S, mode), 4.0, 20)
+            alg = B * (H * W * 12 * 4 + 12 * S * S * 4)
+            print(json.dumps({"workload": f"image pipeline {what}, batch {B}, 12 channels", "value": B / sec, "unit": "windows/s", "ms_per_step": sec * 1e3,
+                              "roofline": {"bound": "hbm", "achieved": alg / sec / 1e9, "peak": peak(), "unit": "GB/s", "frac": alg / sec / 1e9 / peak(),
+                                           "algorithmic_bytes_per_step": alg},
+                              "cpu_baseline": {"value": 1.0 / c, "unit": "windows/s", "cores": 1, "kind": "reference",
+                                               "sample": f"{n} windows, cv2 {what.split()[3] if False else ''}resize + letterbox + transpose per window (oracle/image_pipeline.py around cv2)"}}), flush=True)
 
     if "gwdb" in only:  # config 5, GWD-B: conditional-gradient GW with the KL loss.  The exact assignment LMO (host, like
         # POT's network simplex) costs ~1 s per iteration at n = 1000 on these structured costs for scipy and for our solver

@@ -302,3 +302,25 @@ def gw_kl(Xs, Xt, h=0.7, max_iter=10000, tol_rel=1e-9, tol_abs=1e-9, return_plan
                           ctypes.byref(dist), plan.data_ptr() if plan is not None else None, ctypes.byref(iters), ws.data_ptr(), ws.numel(),
                           stream))
     return (dist.value, iters.value, plan) if return_plan else (dist.value, iters.value)
+
+
+IMG_MODES = {"letterbox": 0, "squash": 1}
+INTERP = {"auto": 0, "linear": 1, "area": 2}
+
+
+def detector_input(rep, img_size=640, mode="letterbox", interp="auto", scale_in=255.0, scale_out=1.0 / 255.0, pad_value=114.0,
+                   reverse_channels=True, out=None):
+    """The reference's per-sample image pipeline for a whole batch, fused on the GPU: (B, H, W, C) representation ->
+    x255 -> cv2.resize per channel -> letterbox(114) (or squash) -> CHW with reversed channel order -> /255, i.e. what
+    Gen1H5.__getitem__ (gen1_2yolo.py:230-265, 321-341, 397) plus Trainer.prepro_data (engine.py:629-635) hand to the
+    detector.  Returns a float32 CUDA tensor (B, C, img_size, img_size)."""
+    if not rep.is_cuda:
+        raise ValueError("detector_input needs a CUDA tensor (there is no CPU path)")
+    rep = rep.contiguous().float()
+    B, H, W, C = rep.shape
+    if out is None:
+        out = torch.empty((B, C, img_size, img_size), dtype=torch.float32, device=rep.device)
+    stream = torch.cuda.current_stream(rep.device).cuda_stream
+    check(lib.evrep_image_pipeline_batched(rep.data_ptr(), B, H, W, C, int(img_size), IMG_MODES[mode], INTERP[interp], float(scale_in),
+                                           float(scale_out), float(pad_value), 1 if reverse_channels else 0, out.data_ptr(), stream))
+    return out

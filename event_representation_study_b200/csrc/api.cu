@@ -59,6 +59,9 @@ int run_gw_kl(const double* Xs, int n, int ds, const double* Xt, int m, int dt, 
 int launch_gemm_nt_3xtf32(const float* A, const float* B, float* C, int M, int N, int K, float alpha, const float* rv, const float* cv,
                           cudaStream_t stream);
 
+int launch_image_pipeline(const float* rep, int B, int H, int W, int C, int img_size, int mode, int interp, float scale_in, float scale_out,
+                          float pad, int reverse, float* out, cudaStream_t stream);
+
 constexpr size_t TILE_SMEM_TARGET = 100 * 1024;  // two tile CTAs per SM
 constexpr size_t TILE_SMEM_MAX = 220 * 1024;
 
@@ -398,6 +401,19 @@ int evrep_gemm_nt_3xtf32(const float* A, const float* B, float* C, int M, int N,
   EVREP_GUARD_BEGIN
   if (!A || !B || !C) { set_error("null matrix"); return EVREP_EINVAL; }
   return launch_gemm_nt_3xtf32(A, B, C, M, N, K, alpha, rv, cv, (cudaStream_t)stream);
+  EVREP_GUARD_END
+}
+
+int evrep_image_pipeline_batched(const float* rep, int B, int H, int W, int C, int img_size, int mode, int interp, float scale_in,
+                                 float scale_out, float pad_value, int reverse_channels, float* out, evrep_stream_t stream) {
+  EVREP_GUARD_BEGIN
+  if (B < 0 || H < 1 || W < 1 || C < 1 || C > 4096 || img_size < 1 || img_size > 65535) { set_error("bad image geometry"); return EVREP_EINVAL; }
+  if (B > 65535) { set_error("at most 65535 windows per call"); return EVREP_EUNSUPPORTED; }
+  if (mode != EVREP_IMG_LETTERBOX && mode != EVREP_IMG_SQUASH) { set_error("unknown mode %d", mode); return EVREP_EINVAL; }
+  if (interp < EVREP_INTERP_AUTO || interp > EVREP_INTERP_AREA) { set_error("unknown interpolation %d", interp); return EVREP_EINVAL; }
+  if (B == 0) return EVREP_OK;
+  if (!rep || !out) { set_error("null image"); return EVREP_EINVAL; }
+  return launch_image_pipeline(rep, B, H, W, C, img_size, mode, interp, scale_in, scale_out, pad_value, reverse_channels, out, (cudaStream_t)stream);
   EVREP_GUARD_END
 }
 

@@ -1,0 +1,185 @@
+// The step that follows every representation in the reference's detector pipelines, fused into one pass on the GPU
+// (SURVEY.md 8f, rank 1):
+//
+//   rep (H, W, C)  --x255-->  per-channel cv2.resize  -->  letterbox (pad 114)  -->  HWC -> CHW, channel order reversed
+//                  -->  / 255 (Trainer.prepro_data)
+//
+// Reference: ev-YOLOv6/yolov6/data/gen1_2yolo.py:230-265 (resize_image: keep the aspect ratio, INTER_AREA when shrinking
+// without augmentation, else INTER_LINEAR), :321-341 + data_augment.py:31-83 (letterbox, pad value 114), :397
+// (transpose + [::-1]); gen4/precompute_reps.py:216-251 (resize_image_process: squash to img_size x img_size);
+// yolov6/core/engine.py:629-635 (/ 255).
+//
+// One thread per output pixel, all C channels: the taps of a pixel are C contiguous floats in the HWC input (read as
+// float4) and its C results go to C planes, each written coalesced along x.  HBM bound: reads H W C 4 bytes, writes
+// C S S 4 bytes per window.  The OpenCV arithmetic is followed tap for tap (float32 weights computed from the double
+// scale exactly as cv::resize does: half-pixel centres and border clamping for INTER_LINEAR, the cell-overlap table of
+// computeResizeAreaTab for INTER_AREA).
+#include "evrep_common.cuh"
+
+namespace evrep {
+
+struct ImgArgs {
+  int B, H, W, C;            // input windows (B, H, W, C)
+  int rw, rh;                // resized width / height
+  int left, top;             // where the resized image sits in the canvas
+  int out_w, out_h;          // canvas
+  int interp;                // 1 linear, 2 area
+  int reverse;               // 1: output channel c holds input channel C - 1 - c
+  float scale_in, scale_out, pad;
+  double sx, sy;             // source pixels per destination pixel (cv::resize: 1 / (dsize / ssize))
+};
+
+constexpr int IMG_MAX_TAPS = 6;  // INTER_AREA: floor(scale) + 2 taps per axis -> scale < 5 (1280 -> 320 is scale 4)
+
+// cv::resize INTER_LINEAR coordinate: fx = (float)((d + 0.5) * scale - 0.5); s = floor(fx); fx -= s; clamped at the borders
+__device__ __forceinline__ void linear_taps(int d, double scale, int ssize, int* idx, float* wgt, int* n) {
+  float fx = (float)(((double)d + 0.5) * scale - 0.5);
+  int s = (int)floorf(fx);
+  fx -= (float)s;
+  if (s < 0) { s = 0; fx = 0.f; }
+  if (s >= ssize - 1) { s = ssize - 1; fx = 0.f; }
+  idx[0] = s;
+  idx[1] = min(s + 1, ssize - 1);
+  wgt[0] = 1.f - fx;
+  wgt[1] = fx;
+  *n = 2;
+}
+
+// cv::resize INTER_AREA (general path), computeResizeAreaTab for one destination index
+__device__ __forceinline__ void area_taps(int d, double scale, int ssize, int* idx, float* wgt, int* n) {
+  const double fsx1 = d * scale, fsx2 = fsx1 + scale;
+  const double cell = fmin(scale, (double)ssize - fsx1);
+  int sx1 = (int)ceil(fsx1), sx2 = (int)floor(fsx2);
+  sx2 = min(sx2, ssize - 1);
+  sx1 = min(sx1, sx2);
+  int k = 0;
+  if (sx1 - fsx1 > 1e-3 && k < IMG_MAX_TAPS) {
+    idx[k] = sx1 - 1;
+    wgt[k++] = (float)((sx1 - fsx1) / cell);
+  }
+  for (int s = sx1; s < sx2 && k < IMG_MAX_TAPS; ++s) {
+    idx[k] = s;
+    wgt[k++] = (float)(1.0 / cell);
+  }
+  if (fsx2 - sx2 > 1e-3 && k < IMG_MAX_TAPS) {
+    idx[k] = sx2;
+    wgt[k++] = (float)(fmin(fmin(fsx2 - sx2, 1.0), cell) / cell);
+  }
+  *n = k;
+}
+
+template <int CT>  // CT = compile-time channel count (multiple of 4), or 0 for the generic path
+__global__ void __launch_bounds__(256) k_image_pipeline(const float* __restrict__ rep, const ImgArgs a, float* __restrict__ out) {
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  const int oy = blockIdx.y;
+  const int b = blockIdx.z;
+  if (ox >= a.out_w) return;
+  const int C = CT ? CT : a.C;
+  const size_t plane = (size_t)a.out_w * a.out_h;
+  float* dst = out + (size_t)b * C * plane + (size_t)oy * a.out_w + ox;
+  const int rx = ox - a.left, ry = oy - a.top;
+  if (rx < 0 || rx >= a.rw || ry < 0 || ry >= a.rh) {  // letterbox border
+    const float v = a.pad * a.scale_out;
+    for (int c = 0; c < C; ++c) __stcs(dst + (size_t)c * plane, v);
+    return;
+  }
+  int xi[IMG_MAX_TAPS], yi[IMG_MAX_TAPS], nx, ny;
+  float xw[IMG_MAX_TAPS], yw[IMG_MAX_TAPS];
+  if (a.interp == 1) {
+    linear_taps(rx, a.sx, a.W, xi, xw, &nx);
+    linear_taps(ry, a.sy, a.H, yi, yw, &ny);
+  } else {
+    area_taps(rx, a.sx, a.W, xi, xw, &nx);
+    area_taps(ry, a.sy, a.H, yi, yw, &ny);
+  }
+  const float* src = rep + (size_t)b * a.H * a.W * C;
+  if (CT) {
+    float acc[CT ? CT : 4];
+#pragma unroll
+    for (int c = 0; c < CT; ++c) acc[c] = 0.f;
+    for (int j = 0; j < ny; ++j) {
+      float row[CT ? CT : 4];
+#pragma unroll
+      for (int c = 0; c < CT; ++c) row[c] = 0.f;
+      const float* srow = src + (size_t)yi[j] * a.W * CT;
+      for (int i = 0; i < nx; ++i) {  // horizontal pass first, like cv::resize
+        const float4* px = reinterpret_cast<const float4*>(srow + (size_t)xi[i] * CT);
+        const float w = xw[i];
+#pragma unroll
+        for (int q = 0; q < CT / 4; ++q) {
+          const float4 v = __ldg(px + q);
+          row[4 * q + 0] += (v.x * a.scale_in) * w;
+          row[4 * q + 1] += (v.y * a.scale_in) * w;
+          row[4 * q + 2] += (v.z * a.scale_in) * w;
+          row[4 * q + 3] += (v.w * a.scale_in) * w;
+        }
+      }
+      const float wy = yw[j];
+#pragma unroll
+      for (int c = 0; c < CT; ++c) acc[c] += row[c] * wy;
+    }
+#pragma unroll
+    for (int c = 0; c < CT; ++c) __stcs(dst + (size_t)(a.reverse ? CT - 1 - c : c) * plane, acc[c] * a.scale_out);
+  } else {
+    for (int c = 0; c < C; ++c) {
+      float acc = 0.f;
+      for (int j = 0; j < ny; ++j) {
+        float row = 0.f;
+        const float* srow = src + ((size_t)yi[j] * a.W) * C + c;
+        for (int i = 0; i < nx; ++i) row += (__ldg(srow + (size_t)xi[i] * C) * a.scale_in) * xw[i];
+        acc += row * yw[j];
+      }
+      __stcs(dst + (size_t)(a.reverse ? C - 1 - c : c) * plane, acc * a.scale_out);
+    }
+  }
+}
+
+// mode 0: gen1_2yolo.py (keep aspect ratio, then letterbox to img_size x img_size); mode 1: precompute_reps.py (squash)
+int launch_image_pipeline(const float* rep, int B, int H, int W, int C, int img_size, int mode, int interp, float scale_in, float scale_out,
+                          float pad, int reverse, float* out, cudaStream_t stream) {
+  ImgArgs a;
+  a.B = B; a.H = H; a.W = W; a.C = C;
+  a.out_w = a.out_h = img_size;
+  a.scale_in = scale_in; a.scale_out = scale_out; a.pad = pad; a.reverse = reverse;
+  const double r = (double)img_size / (double)(H > W ? H : W);  // resize_image: r = img_size / max(h0, w0)
+  if (mode == 0) {
+    a.rw = (int)((double)W * r);  // int(w0 * r)
+    a.rh = (int)((double)H * r);
+    if (r == 1.0) { a.rw = W; a.rh = H; }
+    // letterbox(auto=False, scaleup=False) on the resized image: it already fits, so only the border is added
+    const double dw = (double)(img_size - a.rw) / 2.0, dh = (double)(img_size - a.rh) / 2.0;
+    a.left = (int)lround(dw - 0.1);
+    a.top = (int)lround(dh - 0.1);
+  } else {
+    a.rw = a.rh = img_size;
+    a.left = a.top = 0;
+  }
+  if (a.rw < 1 || a.rh < 1) {
+    set_error("image pipeline: resized image would be empty");
+    return EVREP_EINVAL;
+  }
+  if (interp == 0) interp = (r < 1.0) ? 2 : 1;  // INTER_AREA if r < 1 and not augment else INTER_LINEAR
+  a.interp = interp;
+  a.sx = 1.0 / ((double)a.rw / (double)W);  // cv::resize: inv_scale = dsize / ssize, scale = 1 / inv_scale
+  a.sy = 1.0 / ((double)a.rh / (double)H);
+  if (interp == 2) {
+    if (a.sx < 1.0 || a.sy < 1.0) {  // cv::resize turns INTER_AREA on an enlarging axis into a linear variant: not mirrored here
+      set_error("image pipeline: INTER_AREA needs both axes to shrink (got scale %.4f x %.4f)", a.sx, a.sy);
+      return EVREP_EUNSUPPORTED;
+    }
+    if (a.sx > IMG_MAX_TAPS - 2 || a.sy > IMG_MAX_TAPS - 2) {
+      set_error("image pipeline: INTER_AREA scale above %d is not supported", IMG_MAX_TAPS - 2);
+      return EVREP_EUNSUPPORTED;
+    }
+  }
+  dim3 grid((unsigned)((img_size + 255) / 256), (unsigned)img_size, (unsigned)B);
+  const bool vec = (reinterpret_cast<uintptr_t>(rep) & 15u) == 0;
+  if (C == 12 && vec)
+    k_image_pipeline<12><<<grid, 256, 0, stream>>>(rep, a, out);
+  else
+    k_image_pipeline<0><<<grid, 256, 0, stream>>>(rep, a, out);
+  EVREP_CUDA_OK(cudaGetLastError());
+  return EVREP_OK;
+}
+
+}  // namespace evrep

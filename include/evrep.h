@@ -31,6 +31,8 @@
  *   evrep_gw_kl                  representation_search/gromov_wasserstein.py:39-69 (OTMI.__init__ + solve, GWD-B:
  *                                POT ot.gromov.gromov_wasserstein(Ks, Kt, p, q, "kl_loss"))
  *   evrep_gemm_nt_3xtf32         the tensor product constC - hC1 T hC2^T inside that solve (POT ot/gromov tensor_product)
+ *   evrep_image_pipeline_batched ev-YOLOv6/yolov6/data/gen1_2yolo.py:230-265,321-341,397 (resize_image, letterbox, CHW + reversal),
+ *                                gen4/precompute_reps.py:216-251 (resize_image_process), yolov6/core/engine.py:629-635 (/ 255)
  */
 #ifndef EVREP_H
 #define EVREP_H
@@ -195,6 +197,22 @@ int evrep_gw_kl(const double* Xs, int n, int ds, const double* Xt, int m, int dt
  * to |A| |B|).  All pointers DEVICE float32, row major, K contiguous in A and B; rv (M) and cv (N) may be NULL. */
 int evrep_gemm_nt_3xtf32(const float* A, const float* B, float* C, int M, int N, int K, float alpha, const float* rv,
                          const float* cv, evrep_stream_t stream);
+
+/* The image pipeline that follows a representation in the detector's datasets, fused: out = letterbox(resize(rep *
+ * scale_in)) * scale_out, HWC -> CHW, optionally with the channel order reversed (`img.transpose(2, 0, 1)[::-1]`).
+ * rep: DEVICE float32 (B, H, W, C); out: DEVICE float32 (B, C, img_size, img_size).
+ * mode EVREP_IMG_LETTERBOX: gen1_2yolo.py - resize to (int(W r), int(H r)), r = img_size / max(H, W), then pad to the
+ * square with pad_value (114) like letterbox(auto=False, scaleup=False); mode EVREP_IMG_SQUASH: precompute_reps.py -
+ * resize straight to img_size x img_size.  interp EVREP_INTERP_AUTO follows the reference (INTER_AREA when r < 1, the
+ * non-augmented branch, else INTER_LINEAR); the arithmetic follows cv::resize on float images tap for tap.
+ * INTER_AREA is implemented for shrinking axes with scale <= 4 (EVREP_EUNSUPPORTED otherwise). */
+#define EVREP_IMG_LETTERBOX 0
+#define EVREP_IMG_SQUASH 1
+#define EVREP_INTERP_AUTO 0
+#define EVREP_INTERP_LINEAR 1
+#define EVREP_INTERP_AREA 2
+int evrep_image_pipeline_batched(const float* rep, int B, int H, int W, int C, int img_size, int mode, int interp, float scale_in,
+                                 float scale_out, float pad_value, int reverse_channels, float* out, evrep_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,80 @@
+"""The fused image pipeline (rep -> x255 -> cv2.resize -> letterbox -> CHW reversed -> /255) on the GPU against the
+fixtures produced with the reference's own letterbox + cv2 (tests/golden/img_*.npz) and against the cv2 oracle at the
+BASELINE sizes.  Bar: 1e-5 relative (north_star) with an absolute floor of 2e-6: the reference resizes a float64 image
+with float32 weights, the kernel a float32 image, and outputs near zero are sums of cancelling positive and negative taps
+(values are O(1) after the / 255)."""
+import numpy as np
+import pytest
+
+from conftest import assert_close, golden, load
+
+pytestmark = pytest.mark.gpu
+ATOL = 2e-6
+
+
+@pytest.fixture(scope="module")
+def E(cuda_device):
+    import event_representation_study_b200.batched as eb
+    return eb
+
+
+@pytest.mark.parametrize("name,path", golden("img_*"), ids=[n for n, _ in golden("img_*")])
+def test_image_pipeline_matches_reference_fixtures(E, name, path):
+    import torch
+    g = load(path)
+    rep = torch.as_tensor(g["rep"].astype(np.float32)).cuda()[None]
+    got = E.detector_input(rep, int(g["img_size"]), mode=str(g["mode"]))[0].cpu().numpy()
+    assert_close(got, g["out"], rtol=1e-5, atol=ATOL, what=name)
+
+
+@pytest.mark.parametrize("H,W,S,mode", [(240, 304, 640, "letterbox"), (720, 1280, 640, "letterbox"), (720, 1280, 640, "squash"),
+                                       (240, 304, 224, "letterbox")])
+def test_image_pipeline_baseline_sizes_vs_cv2_oracle(E, H, W, S, mode):
+    import torch
+    from oracle import image_pipeline as oimg
+    rng = np.random.default_rng(H + S)
+    reps = (rng.random((3, H, W, 12)) * (rng.random((3, H, W, 12)) < 0.3)).astype(np.float32)
+    reps[..., 3] -= 0.5 * (rng.random((3, H, W)) < 0.2)
+    got = E.detector_input(torch.as_tensor(reps).cuda(), S, mode=mode).cpu().numpy()
+    assert got.shape == (3, 12, S, S)
+    for b in range(3):
+        assert_close(got[b], oimg.detector_input(reps[b], S, mode), rtol=1e-5, atol=ATOL, what=f"window {b}")
+
+
+def test_image_pipeline_generic_channels_and_options(E):
+    import torch
+    from oracle import image_pipeline as oimg
+    rng = np.random.default_rng(3)
+    rep = rng.random((2, 60, 80, 5)).astype(np.float32)
+    t = torch.as_tensor(rep).cuda()
+    got = E.detector_input(t, 96, mode="letterbox").cpu().numpy()
+    for b in range(2):
+        assert_close(got[b], oimg.detector_input(rep[b], 96, "letterbox"), rtol=1e-5, atol=ATOL)
+    # no reversal, no scaling, another pad value: the raw resize + letterbox
+    raw = E.detector_input(t, 96, scale_in=1.0, scale_out=1.0, pad_value=0.5, reverse_channels=False).cpu().numpy()
+    want = oimg.letterbox(oimg.resize_image(rep[0].astype(np.float64), 96), 96, color=0.5).transpose(2, 0, 1)
+    assert_close(raw[0], want, rtol=1e-5, atol=ATOL)
+
+
+def test_image_pipeline_feeds_from_the_representation(E):
+    """end to end on the device: events -> ERGO-12 -> detector input, against oracle representation + cv2 pipeline"""
+    from event_representation_study_b200.synth import poisson_window
+    from oracle import image_pipeline as oimg
+    from oracle import representations as orep
+    H, W = 240, 304
+    w = poisson_window(77, 30000, H, W)
+    ev = E.pack_events([w], "cuda")
+    img = E.detector_input(E.ergo12(ev, H, W), 640).cpu().numpy()[0]
+    want = oimg.detector_input(np.nan_to_num(orep.ergo12(w["x"], w["y"], w["t"], w["p"], H, W)), 640)
+    assert_close(np.nan_to_num(img), want, rtol=1e-5, atol=5e-6)
+
+
+def test_image_pipeline_rejects_what_it_does_not_mirror(E):
+    import torch
+    from event_representation_study_b200._lib import EvrepError, EUNSUPPORTED
+    t = torch.zeros((1, 64, 2000, 12), device="cuda")
+    with pytest.raises(EvrepError) as e:  # scale 2000 / 64 > 4
+        E.detector_input(t, 64, mode="letterbox")
+    assert e.value.code == EUNSUPPORTED
+    with pytest.raises(ValueError):
+        E.detector_input(torch.zeros((1, 8, 8, 12)), 16)

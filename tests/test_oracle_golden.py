@@ -171,3 +171,12 @@ def test_window_bounds():
         assert b[4][0] == n // 2 and b[5][0] == n // 2 + n // 4 and b[6][0] == n // 2 + n // 4 + n // 8
         s = orep.event_stack_starts(n, 12)
         assert s[0] == 0 and all(s[i] <= s[i + 1] <= n for i in range(11))
+
+
+# ---- post-representation image pipeline: oracle vs fixtures made with the reference's letterbox ----
+@pytest.mark.parametrize("name,path", golden("img_*"), ids=[n for n, _ in golden("img_*")])
+def test_image_pipeline_oracle_matches_reference_fixtures(name, path):
+    from oracle import image_pipeline as oimg
+    g = load(path)
+    got = oimg.detector_input(g["rep"], int(g["img_size"]), str(g["mode"]))
+    assert got.dtype == np.float32 and np.array_equal(got, g["out"])
