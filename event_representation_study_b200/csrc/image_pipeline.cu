@@ -12,7 +12,7 @@
 // One thread per output pixel, all C channels: the taps of a pixel are C contiguous floats in the HWC input (read as
 // float4) and its C results go to C planes, each written coalesced along x.  HBM bound: reads H W C 4 bytes, writes
 // C S S 4 bytes per window.  The OpenCV arithmetic is followed tap for tap (float32 weights computed from the double
-// scale exactly as cv::resize does: half-pixel centres and border clamping for INTER_LINEAR, the cell-overlap table of
+// scale as cv::resize does: half-pixel centres and border clamping for INTER_LINEAR, the cell-overlap table of
 // computeResizeAreaTab for INTER_AREA).
 #include "evrep_common.cuh"
 
@@ -31,17 +31,20 @@ struct ImgArgs {
 
 constexpr int IMG_MAX_TAPS = 6;  // INTER_AREA: floor(scale) + 2 taps per axis -> scale < 5 (1280 -> 320 is scale 4)
 
-// cv::resize INTER_LINEAR coordinate: fx = (float)((d + 0.5) * scale - 0.5); s = floor(fx); fx -= s; clamped at the borders
+// cv::resize INTER_LINEAR coordinate: f = (d + 0.5) * scale - 0.5, s = floor(f), weight = f - s, clamped at the borders.
+// OpenCV 4.13 (the reference's cv2 here) carries the coordinate in double for CV_64F images - which is what the
+// reference resizes (float64 representations x 255) - and its CV_32F path (IPP) agrees to 1e-7; casting the coordinate
+// to float first, as older generic code did, costs 1.5e-5 in the weight at x ~ 600 (checked against cv2 with numpy).
 __device__ __forceinline__ void linear_taps(int d, double scale, int ssize, int* idx, float* wgt, int* n) {
-  float fx = (float)(((double)d + 0.5) * scale - 0.5);
-  int s = (int)floorf(fx);
-  fx -= (float)s;
-  if (s < 0) { s = 0; fx = 0.f; }
-  if (s >= ssize - 1) { s = ssize - 1; fx = 0.f; }
+  double fx = ((double)d + 0.5) * scale - 0.5;
+  int s = (int)floor(fx);
+  fx -= (double)s;
+  if (s < 0) { s = 0; fx = 0.0; }
+  if (s >= ssize - 1) { s = ssize - 1; fx = 0.0; }
   idx[0] = s;
   idx[1] = min(s + 1, ssize - 1);
-  wgt[0] = 1.f - fx;
-  wgt[1] = fx;
+  wgt[0] = (float)(1.0 - fx);
+  wgt[1] = (float)fx;
   *n = 2;
 }
 
