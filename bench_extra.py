@@ -155,17 +155,29 @@ def main():
                               "cpu_baseline": {"value": 1.0 / c, "unit": "windows/s", "cores": 1, "kind": "reference",
                                                "sample": f"{n} windows, cv2 {what.split()[3] if False else ''}resize + letterbox + transpose per window (oracle/image_pipeline.py around cv2)"}}), flush=True)
 
-    if "gwdb" in only:  # config 5, GWD-B: conditional-gradient GW with the KL loss.  The exact assignment LMO (host, like
-        # POT's network simplex) costs ~1 s per iteration at n = 1000 on these structured costs for scipy and for our solver
-        # alike, so the whole-pair line uses n = m = 300; the contraction kernel is timed alone at n = 1000 and 8192
-        n = 300
+    if "gwdb" in only:  # config 5, GWD-B: conditional-gradient GW with the KL loss, LMO = auction on the GPU.  An exact CPU
+        # assignment solve costs ~1 s per iteration at n = 1000 on these structured costs (scipy and our host solver alike),
+        # so the CPU leg runs the same pair at n = m = 500; the contraction kernel is also timed alone at n = 1000 and 8192
+        n = 500
         rng = np.random.default_rng(55)
         Xs = rng.random((n, 4))
         Xt = np.concatenate([Xs[rng.permutation(n)][:, :3] + 0.05 * rng.standard_normal((n, 3)), rng.random((n, 11)) * 0.2], 1)
         eb.gw_kl(Xs, Xt, 0.7, max_iter=2)  # warm-up (module load, shared-memory attribute)
+        st = {}
         t0 = time.perf_counter()
-        dist, iters = eb.gw_kl(Xs, Xt, 0.7)
+        dist, iters = eb.gw_kl(Xs, Xt, 0.7, stats=st)
         sec = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        dist_h, iters_h = eb.gw_kl(Xs, Xt, 0.7, lmo="host")
+        sec_h = time.perf_counter() - t0
+        n2 = 1000
+        rng2 = np.random.default_rng(56)
+        Xs2 = rng2.random((n2, 4))
+        Xt2 = np.concatenate([Xs2[rng2.permutation(n2)][:, :3] + 0.05 * rng2.standard_normal((n2, 3)), rng2.random((n2, 11)) * 0.2], 1)
+        st2 = {}
+        t0 = time.perf_counter()
+        dist2, iters2 = eb.gw_kl(Xs2, Xt2, 0.7, stats=st2)
+        sec2 = time.perf_counter() - t0
         # the contraction alone, device timed: one n x n x n GEMM per iteration
         A = torch.rand((1000, 1000), device=dev)
         Bm = torch.rand((1000, 1000), device=dev)
@@ -179,8 +191,10 @@ def main():
         csec = time.perf_counter() - t0
         tf32_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"]) / 2 if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 795.0
         print(json.dumps({"workload": f"config5 GWD-B (CG Gromov-Wasserstein, KL loss) one pair, n = m = {n}", "value": 1.0 / sec, "unit": "pairs/s",
-                          "ms_per_pair": sec * 1e3, "iterations": iters, "gw_dist": dist,
-                          "note": "wall clock of the synchronous call: kernels + one host assignment solve (LMO) and two small D2H copies per iteration",
+                          "ms_per_pair": sec * 1e3, "iterations": iters, "gw_dist": dist, "lmo": "auction (GPU)", "lmo_stats": st,
+                          "host_lmo": {"ms_per_pair": sec_h * 1e3, "iterations": iters_h, "gw_dist": dist_h},
+                          "n1000": {"ms_per_pair": sec2 * 1e3, "iterations": iters2, "gw_dist": dist2, "lmo_stats": st2},
+                          "note": "wall clock of the synchronous call: kernels + a few scalars copied back per iteration",
                           "contraction": {"kernel": "k_gemm_nt_3xtf32 (tcgen05, 3 TF32 UMMAs per product)", "n1000_us": gsec * 1e6,
                                           "n1000_useful_tflops": 2 * 1000 ** 3 / gsec / 1e12, "n8192_ms": g8 * 1e3,
                                           "n8192_useful_tflops": 2 * 8192 ** 3 / g8 / 1e12, "n8192_issued_tf32_tflops": 3 * 2 * 8192 ** 3 / g8 / 1e12,

@@ -280,9 +280,14 @@ def gemm_nt_3xtf32(A, B, alpha=1.0, row_vec=None, col_vec=None, out=None):
     return out
 
 
-def gw_kl(Xs, Xt, h=0.7, max_iter=10000, tol_rel=1e-9, tol_abs=1e-9, return_plan=False, device="cuda"):
+LMO = {"auction": 0, "host": 1}
+
+
+def gw_kl(Xs, Xt, h=0.7, max_iter=10000, tol_rel=1e-9, tol_abs=1e-9, return_plan=False, device="cuda", lmo="auction", stats=None):
     """GWD-B (gromov_wasserstein.py:39-69): Gaussian kernels of Xs (n, ds) and Xt (m, dt), then conditional-gradient
-    Gromov-Wasserstein with the KL loss.  -> (gw_dist, iterations[, plan (n, m) float32 CUDA tensor]).  n == m only."""
+    Gromov-Wasserstein with the KL loss.  -> (gw_dist, iterations[, plan (n, m) float32 CUDA tensor]).  n == m only.
+    lmo: "auction" (assignment solved on the GPU) or "host" (exact solver on the CPU); `stats`, if a dict, receives the
+    auction's round / bid counts and the number of steps that fell back to the host solver."""
     import ctypes
     dev = torch.device(device)
     Xs = torch.as_tensor(Xs).to(device=dev, dtype=torch.float64).contiguous()
@@ -298,9 +303,12 @@ def gw_kl(Xs, Xt, h=0.7, max_iter=10000, tol_rel=1e-9, tol_abs=1e-9, return_plan
     ws = _workspace(dev, stream, nbytes)
     plan = torch.empty((n, m), dtype=torch.float32, device=dev) if return_plan else None
     dist, iters = ctypes.c_double(0.0), ctypes.c_int(0)
-    check(lib.evrep_gw_kl(Xs.data_ptr(), n, ds, Xt.data_ptr(), m, dt, float(h), int(max_iter), float(tol_rel), float(tol_abs),
-                          ctypes.byref(dist), plan.data_ptr() if plan is not None else None, ctypes.byref(iters), ws.data_ptr(), ws.numel(),
-                          stream))
+    lst = (ctypes.c_int * 3)()
+    check(lib.evrep_gw_kl(Xs.data_ptr(), n, ds, Xt.data_ptr(), m, dt, float(h), int(max_iter), float(tol_rel), float(tol_abs), LMO[lmo],
+                          ctypes.byref(dist), plan.data_ptr() if plan is not None else None, ctypes.byref(iters), lst, ws.data_ptr(),
+                          ws.numel(), stream))
+    if stats is not None:
+        stats.update(auction_rounds=lst[0], auction_bids=lst[1], host_fallbacks=lst[2])
     return (dist.value, iters.value, plan) if return_plan else (dist.value, iters.value)
 
 
@@ -324,3 +332,20 @@ def detector_input(rep, img_size=640, mode="letterbox", interp="auto", scale_in=
     check(lib.evrep_image_pipeline_batched(rep.data_ptr(), B, H, W, C, int(img_size), IMG_MODES[mode], INTERP[interp], float(scale_in),
                                            float(scale_out), float(pad_value), 1 if reverse_channels else 0, out.data_ptr(), stream))
     return out
+
+
+def assignment_auction(cost, eps_rel=1e-9):
+    """Min-cost assignment of a square float32 CUDA matrix on the GPU (the LMO of gw_kl) -> (sigma int32 CUDA tensor,
+    stats dict).  Optimal up to n * eps_rel * (cost range)."""
+    if not cost.is_cuda:
+        raise ValueError("assignment_auction needs a CUDA tensor (there is no CPU path)")
+    cost = cost.contiguous().float()
+    n = cost.shape[0]
+    if cost.shape != (n, n):
+        raise ValueError("cost must be square")
+    sigma = torch.empty(n, dtype=torch.int32, device=cost.device)
+    st = torch.zeros(3, dtype=torch.int32, device=cost.device)
+    check(lib.evrep_assignment_auction(cost.data_ptr(), n, float(eps_rel), sigma.data_ptr(), st.data_ptr(),
+                                       torch.cuda.current_stream(cost.device).cuda_stream))
+    r, b, status = (int(v) for v in st.cpu())
+    return sigma, {"rounds": r, "bids": b, "status": status}

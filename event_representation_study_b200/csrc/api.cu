@@ -55,10 +55,12 @@ int launch_gwd(const double* Xs, const int64_t* so, int ds, const double* Xt, co
 
 size_t gw_kl_workspace_bytes(int n, int m);
 int run_gw_kl(const double* Xs, int n, int ds, const double* Xt, int m, int dt, double h, int max_iter, double tol_rel, double tol_abs,
-              double* gw_dist_host, float* T_out, int* iters_host, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+              int lmo, double* gw_dist_host, float* T_out, int* iters_host, int* lmo_stats_host, void* workspace, size_t workspace_bytes,
+              cudaStream_t stream);
 int launch_gemm_nt_3xtf32(const float* A, const float* B, float* C, int M, int N, int K, float alpha, const float* rv, const float* cv,
                           cudaStream_t stream);
 
+int launch_auction(const float* cost, int n, double eps_rel, int* sigma, int* stats, cudaStream_t stream);
 int launch_image_pipeline(const float* rep, int B, int H, int W, int C, int img_size, int mode, int interp, float scale_in, float scale_out,
                           float pad, int reverse, float* out, cudaStream_t stream);
 
@@ -387,12 +389,22 @@ int evrep_gwd_kernel_l1(const double* Xs, const int64_t* s_offsets, int ds, cons
 size_t evrep_gw_kl_workspace_bytes(int n, int m) { return gw_kl_workspace_bytes(n, m); }
 
 int evrep_gw_kl(const double* Xs, int n, int ds, const double* Xt, int m, int dt, double h, int max_iter, double tol_rel, double tol_abs,
-                double* gw_dist, float* T_out, int* iters, void* workspace, size_t workspace_bytes, evrep_stream_t stream) {
+                int lmo, double* gw_dist, float* T_out, int* iters, int* lmo_stats, void* workspace, size_t workspace_bytes,
+                evrep_stream_t stream) {
   EVREP_GUARD_BEGIN
   if (!Xs || !Xt || !gw_dist) { set_error("null array"); return EVREP_EINVAL; }
   if (!(h > 0.0)) { set_error("h must be positive"); return EVREP_EINVAL; }
   if (max_iter < 0) { set_error("max_iter must be >= 0"); return EVREP_EINVAL; }
-  return run_gw_kl(Xs, n, ds, Xt, m, dt, h, max_iter, tol_rel, tol_abs, gw_dist, T_out, iters, workspace, workspace_bytes, (cudaStream_t)stream);
+  if (lmo != EVREP_LMO_AUCTION && lmo != EVREP_LMO_HOST) { set_error("unknown lmo %d", lmo); return EVREP_EINVAL; }
+  return run_gw_kl(Xs, n, ds, Xt, m, dt, h, max_iter, tol_rel, tol_abs, lmo, gw_dist, T_out, iters, lmo_stats, workspace, workspace_bytes,
+                   (cudaStream_t)stream);
+  EVREP_GUARD_END
+}
+
+int evrep_assignment_auction(const float* cost, int n, double eps_rel, int* sigma, int* stats, evrep_stream_t stream) {
+  EVREP_GUARD_BEGIN
+  if (!cost || !sigma || !stats) { set_error("null argument"); return EVREP_EINVAL; }
+  return launch_auction(cost, n, eps_rel, sigma, stats, (cudaStream_t)stream);
   EVREP_GUARD_END
 }
 

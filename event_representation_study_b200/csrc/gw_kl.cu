@@ -11,12 +11,15 @@
 // operand into two TF32 terms on the fly while staging it into the 128-byte-swizzled shared-memory tiles and
 // issues hi*hi + lo*hi + hi*lo, i.e. fp32-class accuracy (about 2^-22 relative) at a third of the TF32 rate.
 // For uniform marginals with n == m every vertex of U(p, q) is a permutation matrix / n, so the LMO is a linear
-// assignment problem (solved on the host, like POT's network simplex) and hC1 Gc hC2^T is ONE gather + ONE GEMM.
+// assignment problem (k_auction on the GPU; an exact host solver is kept as the selectable alternative and as the
+// fallback) and hC1 Gc hC2^T is ONE gather + ONE GEMM.
 #include <float.h>
+#include <limits.h>
 #include <math.h>
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
 #include <vector>
 
 #include "evrep_common.cuh"
@@ -477,6 +480,142 @@ __global__ void k_gwb_step(int n, int m, float alpha, const int* __restrict__ si
 }
 
 // ---------------------------------------------------------------------------------------------
+// Device LMO: the assignment problem by Bertsekas' forward auction with epsilon scaling, Jacobi rounds, one CTA.
+//
+// Persons = rows, objects = columns, benefit a_ij = -cost_ij.  In a round every unassigned person i finds its best
+// object j1 (value v1 = a_ij1 - price_j1) and the second best value v2 and bids price_j1 + (v1 - v2) + eps; every
+// object takes its highest bid, raises its price to it and swaps owners.  When nobody is unassigned the assignment is
+// within n eps of optimal; eps starts at C / 4 (C = cost range) and shrinks by theta per phase (prices kept,
+// assignment reset) down to eps_rel C, so the final plan is optimal up to n eps_rel C - on the GW cost matrices
+// (numpy prototype, n = 300 and 1000) that is the exact optimum of scipy's solver at eps_rel = 1e-9.
+// One warp per bidder scans its cost row (coalesced, L2 resident); prices, owners and the bid table live in shared
+// memory (doubles, and benefits are taken relative to the smallest cost so that their magnitude is C: an increment of
+// 1e-9 C must stay visible in a_ij - price_j, or two bidders fight over one object for gap / eps rounds - seen with the
+// nearly constant cost matrix of an n = 2 problem before the shift); rounds are separated by __syncthreads only.  A round with few
+// bidders costs one row scan (~3 us), which is what most of the thousands of rounds are.
+// ---------------------------------------------------------------------------------------------
+constexpr int AUC_THREADS = 1024;
+constexpr int AUC_MAX_N = 4096;
+static size_t auction_smem_bytes(int n) { return (size_t)n * (3 * sizeof(double) + 5 * sizeof(int)) + 16; }
+
+__global__ void __launch_bounds__(AUC_THREADS, 1) k_auction(const float* __restrict__ cost, int n, double eps_rel, double theta, int max_rounds,
+                                                            int* __restrict__ sigma, int* __restrict__ stats /* rounds, bids, status */) {
+  extern __shared__ __align__(16) unsigned char auc_raw[];
+  double* price = reinterpret_cast<double*>(auc_raw);                             // n
+  unsigned long long* objbid = reinterpret_cast<unsigned long long*>(price + n);  // n: highest bid of the round (bits of a positive double), 0 = none
+  double* mybid = reinterpret_cast<double*>(objbid + n);                          // n: bid of person i in this round
+  int* owner = reinterpret_cast<int*>(mybid + n);                                 // n: person owning object j, or -1
+  int* assigned = owner + n;                                                      // n: object of person i, or -1
+  int* queue = assigned + n;                                                      // n: unassigned persons of this round
+  int* mybid_obj = queue + n;                                                     // n: object person i bid for
+  int* winner = mybid_obj + n;                                                    // n: lowest person index among the highest bidders, INT_MAX = none
+  __shared__ int s_count, s_rounds, s_bids, s_bad;
+  __shared__ double s_red[2][AUC_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // cost range
+  double lo = DBL_MAX, hi = -DBL_MAX;
+  for (size_t e = tid; e < (size_t)n * n; e += AUC_THREADS) {
+    const double c = (double)__ldg(cost + e);
+    lo = fmin(lo, c);
+    hi = fmax(hi, c);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if (lane == 0) { s_red[0][warp] = lo; s_red[1][warp] = hi; }
+  for (int j = tid; j < n; j += AUC_THREADS) { price[j] = 0.0; objbid[j] = 0ull; winner[j] = INT_MAX; }
+  if (tid == 0) { s_rounds = 0; s_bids = 0; s_bad = 0; }
+  __syncthreads();
+  lo = s_red[0][0]; hi = s_red[1][0];
+  for (int w = 1; w < AUC_THREADS / 32; ++w) { lo = fmin(lo, s_red[0][w]); hi = fmax(hi, s_red[1][w]); }
+  const double C = fmax(hi - lo, 1e-300);
+  const double eps_final = C * eps_rel;
+  double eps = fmax(C / 4.0, eps_final);
+  int status = 0;
+
+  while (true) {  // epsilon phases: prices are kept, the assignment starts over
+    for (int j = tid; j < n; j += AUC_THREADS) { owner[j] = -1; assigned[j] = -1; }
+    __syncthreads();
+    while (true) {  // rounds
+      if (tid == 0) s_count = 0;
+      __syncthreads();
+      for (int i = tid; i < n; i += AUC_THREADS)
+        if (assigned[i] < 0) queue[atomicAdd(&s_count, 1)] = i;
+      __syncthreads();
+      const int nb = s_count;
+      if (nb == 0) break;
+      if (s_rounds >= max_rounds) { status = 1; break; }  // uniform: every thread reads the same shared values
+      // 1. bids: one warp per unassigned person
+      for (int q = warp; q < nb; q += AUC_THREADS / 32) {
+        const int i = queue[q];
+        const float* row = cost + (size_t)i * n;
+        double v1 = -DBL_MAX, v2 = -DBL_MAX;
+        int j1 = INT_MAX;
+        for (int j = lane; j < n; j += 32) {
+          const double v = (lo - (double)__ldg(row + j)) - price[j];  // benefit relative to the smallest cost: magnitudes ~ C
+          if (v > v1) { v2 = v1; v1 = v; j1 = j; }
+          else if (v > v2) v2 = v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {  // merge (v1, j1, v2); equal values go to the lower object index
+          const double ov1 = __shfl_xor_sync(0xffffffffu, v1, o), ov2 = __shfl_xor_sync(0xffffffffu, v2, o);
+          const int oj1 = __shfl_xor_sync(0xffffffffu, j1, o);
+          if (ov1 > v1 || (ov1 == v1 && oj1 < j1)) {
+            v2 = fmax(v1, ov2);
+            v1 = ov1;
+            j1 = oj1;
+          } else {
+            v2 = fmax(v2, ov1);
+          }
+        }
+        if (lane == 0) {
+          if (n == 1) v2 = v1;
+          if (j1 == INT_MAX || !(v1 - v2 >= 0.0) || !isfinite(v1 - v2)) {  // NaN / infinite costs: no meaningful bid
+            s_bad = 1;
+            j1 = 0;
+            v2 = v1 = 0.0;
+          }
+          const double bid = price[j1] + (v1 - v2) + eps;  // > price >= 0, so its bit pattern orders like its value
+          mybid_obj[i] = j1;
+          mybid[i] = bid;
+          atomicMax(&objbid[j1], (unsigned long long)__double_as_longlong(bid));
+        }
+      }
+      __syncthreads();
+      if (s_bad) { status = 2; break; }
+      // 2. among the highest bidders of an object, the lowest person index wins (deterministic)
+      for (int q = tid; q < nb; q += AUC_THREADS) {
+        const int i = queue[q], j = mybid_obj[i];
+        if ((unsigned long long)__double_as_longlong(mybid[i]) == objbid[j]) atomicMin(&winner[j], i);
+      }
+      __syncthreads();
+      // 3. the winner takes the object at its bid; the previous owner becomes unassigned
+      for (int q = tid; q < nb; q += AUC_THREADS) {
+        const int i = queue[q], j = mybid_obj[i];
+        if (winner[j] == i) {
+          const int prev = owner[j];
+          if (prev >= 0) assigned[prev] = -1;
+          owner[j] = i;
+          assigned[i] = j;
+          price[j] = mybid[i];
+          objbid[j] = 0ull;
+          winner[j] = INT_MAX;
+        }
+      }
+      if (tid == 0) { s_rounds += 1; s_bids += nb; }
+      __syncthreads();
+    }
+    if (status || eps <= eps_final) break;
+    eps = fmax(eps / theta, eps_final);
+    __syncthreads();
+  }
+  for (int i = tid; i < n; i += AUC_THREADS) sigma[i] = assigned[i];
+  if (tid == 0) { stats[0] = s_rounds; stats[1] = s_bids; stats[2] = status; }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Host: linear assignment (shortest augmenting paths with potentials, O(n^3)), the exact LMO for n == m
 // ---------------------------------------------------------------------------------------------
 static void lap_solve(const float* cost, int n, std::vector<int>& row_to_col) {
@@ -501,6 +640,11 @@ static void lap_solve(const float* cost, int n, std::vector<int>& row_to_col) {
         if (cur < minv[j]) { minv[j] = cur; way[j] = j0; }
         if (minv[j] < delta) { delta = minv[j]; j1 = j; }
       }
+      if (j1 == 0) {  // no finite reduced cost left (NaN / infinite input): give up with the identity
+        row_to_col.resize(n);
+        for (int k = 0; k < n; ++k) row_to_col[k] = k;
+        return;
+      }
       for (int j = 0; j <= n; ++j) {
         if (used[j]) { u[p[j]] += delta; v[j] -= delta; }
         else minv[j] -= delta;
@@ -517,10 +661,26 @@ static void lap_solve(const float* cost, int n, std::vector<int>& row_to_col) {
   for (int j = 1; j <= n; ++j) row_to_col[p[j] - 1] = j - 1;
 }
 
+// the LMO on its own (tests, and callers with their own assignment problems): sigma and stats are DEVICE pointers
+int launch_auction(const float* cost, int n, double eps_rel, int* sigma, int* stats, cudaStream_t stream) {
+  if (n < 1 || n > AUC_MAX_N) {
+    set_error("auction: n = %d outside 1..%d", n, AUC_MAX_N);
+    return EVREP_EUNSUPPORTED;
+  }
+  if (!(eps_rel > 0.0)) {
+    set_error("auction: eps_rel must be positive");
+    return EVREP_EINVAL;
+  }
+  EVREP_CUDA_OK(cudaFuncSetAttribute(k_auction, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)auction_smem_bytes(n)));
+  k_auction<<<1, AUC_THREADS, auction_smem_bytes(n), stream>>>(cost, n, eps_rel, 6.0, 4000000, sigma, stats);
+  EVREP_CUDA_OK(cudaGetLastError());
+  return EVREP_OK;
+}
+
 struct GwbWs {
   float *hC1, *hC2, *G, *AG, *AGc, *Mi, *Bp, *cr, *cc;
   double *rs_a1, *rs_a2, *rs_h1, *rs_h2, *red, *msq;
-  int* sigma;
+  int *sigma, *stats;
   size_t bytes;
 };
 static GwbWs gwb_carve(void* basep, int n, int m) {
@@ -549,14 +709,17 @@ static GwbWs gwb_carve(void* basep, int n, int m) {
   w.red = (double*)take(sizeof(double) * 8);
   w.msq = (double*)take(sizeof(double) * 2);
   w.sigma = (int*)take(sizeof(int) * (size_t)n);
+  w.stats = (int*)take(sizeof(int) * 4);
   w.bytes = off;
   return w;
 }
 size_t gw_kl_workspace_bytes(int n, int m) { return (n < 1 || m < 1) ? 0 : gwb_carve(nullptr, n, m).bytes; }
 
 // Synchronous (the LMO runs on the host between device steps).  Returns the GW loss at the last iterate.
+// lmo: 0 = auction on the GPU (falls back to the host solver for one step if it hits its round limit), 1 = host solver
 int run_gw_kl(const double* Xs, int n, int ds, const double* Xt, int m, int dt, double h, int max_iter, double tol_rel, double tol_abs,
-              double* gw_dist_host, float* T_out, int* iters_host, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+              int lmo, double* gw_dist_host, float* T_out, int* iters_host, int* lmo_stats_host, void* workspace, size_t workspace_bytes,
+              cudaStream_t stream) {
   if (n != m) {
     set_error("gw_kl: only n == m (uniform marginals => the LMO is an assignment problem) is implemented; got n = %d, m = %d", n, m);
     return EVREP_EUNSUPPORTED;
@@ -584,20 +747,54 @@ int run_gw_kl(const double* Xs, int n, int ds, const double* Xt, int m, int dt, 
   k_gwb_init<<<eb, 256, 0, stream>>>(n, m, w.rs_a1, w.rs_a2, w.rs_h1, w.rs_h2, w.cr, w.cc, w.G, w.AG);
   EVREP_CUDA_OK(cudaGetLastError());
 
-  std::vector<float> Mi_host(nm);
+  const bool device_lmo = lmo == 0 && n <= AUC_MAX_N;
+  if (device_lmo) EVREP_CUDA_OK(cudaFuncSetAttribute(k_auction, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)auction_smem_bytes(n)));
+  std::vector<float> Mi_host;
   std::vector<int> sigma;
   double red_host[4];
   double f_val = 0.0;
   int it = 0;
+  long long lmo_rounds = 0, lmo_bids = 0, lmo_fallbacks = 0;
+  {  // the loss of the starting plan; degenerate inputs (a single point, coincident points: std = 0) give NaN kernels
+     // in the reference too - report NaN without iterating
+    EVREP_CUDA_OK(cudaMemsetAsync(w.red, 0, sizeof(double) * 8, stream));
+    k_gwb_grad<<<eb, 256, 0, stream>>>(n, m, w.cr, w.cc, w.AG, w.G, w.Mi, w.red);
+    EVREP_CUDA_OK(cudaMemcpyAsync(red_host, w.red, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    EVREP_CUDA_OK(cudaStreamSynchronize(stream));
+    if (!std::isfinite(red_host[0])) {
+      if (gw_dist_host) *gw_dist_host = red_host[0];
+      if (iters_host) *iters_host = 0;
+      if (lmo_stats_host) lmo_stats_host[0] = lmo_stats_host[1] = lmo_stats_host[2] = 0;
+      if (T_out) EVREP_CUDA_OK(cudaMemcpyAsync(T_out, w.G, sizeof(float) * nm, cudaMemcpyDeviceToDevice, stream));
+      EVREP_CUDA_OK(cudaStreamSynchronize(stream));
+      return EVREP_OK;
+    }
+  }
   for (; it < max_iter; ++it) {
     EVREP_CUDA_OK(cudaMemsetAsync(w.red, 0, sizeof(double) * 8, stream));
     k_gwb_grad<<<eb, 256, 0, stream>>>(n, m, w.cr, w.cc, w.AG, w.G, w.Mi, w.red);
-    EVREP_CUDA_OK(cudaMemcpyAsync(Mi_host.data(), w.Mi, sizeof(float) * nm, cudaMemcpyDeviceToHost, stream));
-    EVREP_CUDA_OK(cudaMemcpyAsync(red_host, w.red, sizeof(double), cudaMemcpyDeviceToHost, stream));
-    EVREP_CUDA_OK(cudaStreamSynchronize(stream));
+    // LMO: the vertex of U(p, q) minimising <Mi, G>
+    bool solved = false;
+    if (device_lmo) {
+      int st_host[3];
+      k_auction<<<1, AUC_THREADS, auction_smem_bytes(n), stream>>>(w.Mi, n, 1e-9, 6.0, 4000000, w.sigma, w.stats);
+      EVREP_CUDA_OK(cudaMemcpyAsync(st_host, w.stats, sizeof(int) * 3, cudaMemcpyDeviceToHost, stream));
+      EVREP_CUDA_OK(cudaMemcpyAsync(red_host, w.red, sizeof(double), cudaMemcpyDeviceToHost, stream));
+      EVREP_CUDA_OK(cudaStreamSynchronize(stream));
+      lmo_rounds += st_host[0];
+      lmo_bids += st_host[1];
+      solved = st_host[2] == 0;
+      if (!solved) ++lmo_fallbacks;
+    }
+    if (!solved) {
+      Mi_host.resize(nm);
+      EVREP_CUDA_OK(cudaMemcpyAsync(Mi_host.data(), w.Mi, sizeof(float) * nm, cudaMemcpyDeviceToHost, stream));
+      EVREP_CUDA_OK(cudaMemcpyAsync(red_host, w.red, sizeof(double), cudaMemcpyDeviceToHost, stream));
+      EVREP_CUDA_OK(cudaStreamSynchronize(stream));
+      lap_solve(Mi_host.data(), n, sigma);
+      EVREP_CUDA_OK(cudaMemcpyAsync(w.sigma, sigma.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, stream));
+    }
     if (it == 0) f_val = red_host[0];
-    lap_solve(Mi_host.data(), n, sigma);  // LMO: the vertex of U(p, q) minimising <Mi, G>
-    EVREP_CUDA_OK(cudaMemcpyAsync(w.sigma, sigma.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, stream));
     // hC1 Gc hC2^T = (1 / n) hC1 (hC2[:, sigma])^T : gather, then the tensor-core contraction
     k_gwb_gather<<<eb, 256, 0, stream>>>(w.hC2, w.sigma, m, n, w.Bp);
     const int rc = launch_gemm_nt_3xtf32(w.hC1, w.Bp, w.AGc, n, m, n, 1.f / (float)n, nullptr, nullptr, stream);
@@ -609,6 +806,7 @@ int run_gw_kl(const double* Xs, int n, int ds, const double* Xt, int m, int dt, 
     // f(G + alpha dG) = f(G) + b alpha + a alpha^2 with
     const double a = -red_host[0];
     const double b = red_host[1] - red_host[2] - red_host[3];
+    if (!std::isfinite(a) || !std::isfinite(b)) break;
     double alpha;
     if (a > 0) alpha = std::min(1.0, std::max(0.0, -b / (2 * a)));
     else alpha = (a + b < 0) ? 1.0 : 0.0;
@@ -633,6 +831,11 @@ int run_gw_kl(const double* Xs, int n, int ds, const double* Xt, int m, int dt, 
   }
   if (gw_dist_host) *gw_dist_host = red_host[0];
   if (iters_host) *iters_host = it;
+  if (lmo_stats_host) {
+    lmo_stats_host[0] = (int)std::min<long long>(lmo_rounds, INT_MAX);
+    lmo_stats_host[1] = (int)std::min<long long>(lmo_bids, INT_MAX);
+    lmo_stats_host[2] = (int)lmo_fallbacks;
+  }
   return EVREP_OK;
 }
 

@@ -184,13 +184,24 @@ int evrep_gwd_kernel_l1(const double* Xs, const int64_t* s_offsets, int ds, cons
  * the KL loss from T = p q^T (uniform p, q) until the loss changes by less than tol_abs or tol_rel (POT: 1e-9, 1e-9)
  * or max_iter (POT: 10000) steps.  Writes the loss at the final plan to *gw_dist (HOST), the iteration count to *iters
  * (HOST, may be NULL) and the plan to T_out (DEVICE float32 n x m, may be NULL).  The dense contraction of every step
- * runs on the tensor cores (evrep_gemm_nt_3xtf32); the linear minimisation oracle is an exact assignment solve on
- * the host, so the call SYNCHRONISES the stream every iteration.  Implemented for n == m only (uniform marginals make
- * every vertex a permutation); EVREP_EUNSUPPORTED otherwise.  ds, dt <= 64. */
+ * runs on the tensor cores (evrep_gemm_nt_3xtf32).  The linear minimisation oracle (an assignment problem) is, with lmo =
+ * EVREP_LMO_AUCTION, Bertsekas' forward auction with epsilon scaling on the GPU (optimal up to n * 1e-9 * cost range; n <=
+ * 4096; a step that hits the round limit is redone by the host solver) or, with EVREP_LMO_HOST, an exact shortest-
+ * augmenting-path solve on the host.  Either way a few scalars come back every iteration, so the call SYNCHRONISES the
+ * stream.  lmo_stats (HOST, 3 ints, may be NULL): auction rounds, auction bids, steps redone on the host.  Implemented for
+ * n == m only (uniform marginals make every vertex a permutation); EVREP_EUNSUPPORTED otherwise.  ds, dt <= 64. */
+#define EVREP_LMO_AUCTION 0
+#define EVREP_LMO_HOST 1
 size_t evrep_gw_kl_workspace_bytes(int n, int m);
 int evrep_gw_kl(const double* Xs, int n, int ds, const double* Xt, int m, int dt, double h, int max_iter, double tol_rel,
-                double tol_abs, double* gw_dist, float* T_out, int* iters, void* workspace, size_t workspace_bytes,
-                evrep_stream_t stream);
+                double tol_abs, int lmo, double* gw_dist, float* T_out, int* iters, int* lmo_stats, void* workspace,
+                size_t workspace_bytes, evrep_stream_t stream);
+
+/* The LMO of evrep_gw_kl on its own: min-cost assignment of the n x n DEVICE float32 matrix `cost` (row major) by a
+ * forward auction with epsilon scaling.  sigma (DEVICE, n ints): column assigned to every row; the total cost is within
+ * n * eps_rel * (max cost - min cost) of the optimum.  stats (DEVICE, 3 ints): rounds, bids, status (0 ok, 1 round limit,
+ * 2 non-finite costs; sigma is not a permutation unless status is 0).  n <= 4096.  Enqueued on `stream`, no sync. */
+int evrep_assignment_auction(const float* cost, int n, double eps_rel, int* sigma, int* stats, evrep_stream_t stream);
 
 /* C[M x N] = alpha * A[M x K] * B[N x K]^T + rv[i] + cv[j] on the tcgen05 tensor cores: every fp32 operand is split
  * into two TF32 terms while it is staged and hi*hi + lo*hi + hi*lo is accumulated in fp32 (error about 2^-21 relative

@@ -85,13 +85,14 @@ def _loss64(Xs, Xt, P, h=0.7):
     return float(np.sum(tens * P)), float(2 * np.sum(tens * (P - Gc)))
 
 
+@pytest.mark.parametrize("lmo", ["auction", "host"])
 @pytest.mark.parametrize("n,seed", [(32, 1), (64, 2), (100, 3)])
-def test_gw_kl_matches_oracle(E, n, seed):
+def test_gw_kl_matches_oracle(E, n, seed, lmo):
     """problems on which the float32-operand solve takes the same vertex sequence as the float64 oracle"""
     from oracle import gwd as ogwd
     Xs, Xt = _clouds(seed, n)
     want = ogwd.gwd_b_cost(Xs, Xt, 0.7)
-    got, iters, plan = E.gw_kl(Xs, Xt, 0.7, return_plan=True)
+    got, iters, plan = E.gw_kl(Xs, Xt, 0.7, return_plan=True, lmo=lmo)
     assert iters >= 1
     P = plan.double().cpu().numpy()
     assert np.abs(P.sum(1) - 1.0 / n).max() < 1e-6 and np.abs(P.sum(0) - 1.0 / n).max() < 1e-6
@@ -148,3 +149,53 @@ def test_otmi_mirror_of_gromov_wasserstein_py(E):
     T, dist = OTMI(Xs, Xt, 0.7).solve()
     assert T.shape == (64, 64) and T.dtype == np.float64
     assert abs(dist - ogwd.gwd_b_cost(Xs, Xt, 0.7)) <= 1e-5 * abs(dist)
+
+
+def test_gw_kl_degenerate_input_is_nan_not_a_hang(E):
+    """one point: std = 0, the reference's kernels are NaN (0 / 0); the solve must come back with NaN at once"""
+    d, it = E.gw_kl(np.array([[0.1, 0.2, 0.3, 0.4]]), np.array([[0.5, 0.6]]), 0.7)
+    assert np.isnan(d) and it == 0
+
+
+@pytest.mark.parametrize("n,seed", [(2, 1), (7, 2), (64, 2), (129, 5)])
+def test_auction_lmo_agrees_with_the_exact_host_lmo(E, n, seed):
+    """same loss with the GPU auction as with the exact host assignment solver (on problems without a near-tie in
+    the LMO; see the stationary-point test for why a flipped vertex is not an error), and no fallback to the host"""
+    Xs, Xt = _clouds(seed, n, dt=6) if n >= 4 else (np.random.default_rng(seed).random((n, 4)), np.random.default_rng(seed + 1).random((n, 6)))
+    st = {}
+    da, ia = E.gw_kl(Xs, Xt, 0.7, lmo="auction", stats=st, max_iter=50)
+    dh, ih = E.gw_kl(Xs, Xt, 0.7, lmo="host", max_iter=50)
+    assert st["host_fallbacks"] == 0 and st["auction_rounds"] > 0
+    assert abs(da - dh) <= 1e-6 * max(abs(dh), 1e-12), (da, dh, ia, ih, st)
+
+
+@pytest.mark.parametrize("kind,n", [("random", 1), ("random", 2), ("random", 33), ("random", 500), ("random", 1500), ("gw", 300), ("gw", 1000),
+                                    ("ties", 64), ("constant", 50)])
+def test_assignment_auction_is_optimal(E, kind, n):
+    """the device LMO against scipy's exact solver: a permutation whose cost is within n * eps_rel * range of the optimum"""
+    import torch
+    from scipy.optimize import linear_sum_assignment
+    rng = np.random.default_rng(n)
+    if kind == "random":
+        cost = rng.random((n, n)).astype(np.float32) * 10 - 3
+    elif kind == "ties":
+        cost = rng.integers(0, 4, (n, n)).astype(np.float32)  # massive ties
+    elif kind == "constant":
+        cost = np.full((n, n), 2.5, np.float32)
+    else:  # the structured matrix of a GW step: constC - hC1 G hC2^T at a mixed plan
+        from oracle import gwd as ogwd
+        Xs, Xt = _clouds(55, n, dt=14)
+        Ks, Kt = ogwd.compute_kernel(ogwd.pairwise_euclidean(Xs), ogwd.pairwise_euclidean(Xt), 0.7)
+        p = np.ones(n) / n
+        constC, hC1, hC2 = ogwd.gw_kl_init(Ks, Kt, p, p)
+        G = 0.5 * np.outer(p, p) + 0.5 * np.eye(n)[rng.permutation(n)] / n
+        cost = (constC - hC1 @ G @ hC2.T).astype(np.float32)
+    sigma, st = E.assignment_auction(torch.as_tensor(cost).cuda())
+    sg = sigma.cpu().numpy()
+    assert st["status"] == 0
+    assert sorted(sg.tolist()) == list(range(n))
+    r, c = linear_sum_assignment(cost.astype(np.float64))
+    opt = cost.astype(np.float64)[r, c].sum()
+    got = cost.astype(np.float64)[np.arange(n), sg].sum()
+    rng_c = float(cost.max() - cost.min())
+    assert got <= opt + n * 1e-9 * rng_c + 1e-12 * abs(opt), (got, opt, st)
