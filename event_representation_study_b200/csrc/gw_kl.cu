@@ -814,8 +814,12 @@ int run_gw_kl(const double* Xs, int n, int ds, const double* Xt, int m, int dt, 
     f_val = old + a * alpha * alpha + b * alpha;
     if (alpha != 0.0) k_gwb_step<<<eb, 256, 0, stream>>>(n, m, (float)alpha, w.sigma, w.AGc, w.G, w.AG);
     EVREP_CUDA_OK(cudaGetLastError());
+    // POT's stopping rule (|df| < tol_abs or |df| / |f| < tol_rel), with both tolerances floored at the resolution of
+    // the float32 gradient (4 ulp of the loss): below it the predicted decrease is rounding noise and the iteration
+    // would wander until max_iter (seen at n = 1000: 10000 steps of ~1e-8 relative "progress")
     const double dlt = fabs(f_val - old);
-    if (dlt < tol_abs || dlt / std::max(fabs(f_val), 1e-300) < tol_rel) { ++it; break; }
+    const double floor_rel = 4.0 * 1.1920929e-7;
+    if (dlt < std::max(tol_abs, floor_rel * fabs(f_val)) || dlt / std::max(fabs(f_val), 1e-300) < std::max(tol_rel, floor_rel)) { ++it; break; }
   }
   // the loss at the final plan, from a fresh contraction (two GEMMs: X^T = hC2 G^T, then hC1 X)
   {

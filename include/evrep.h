@@ -181,8 +181,8 @@ int evrep_gwd_kernel_l1(const double* Xs, const int64_t* s_offsets, int ds, cons
 
 /* GWD-B for ONE pair: builds the Gaussian kernels Ks (n x n) and Kt (m x m) of Xs (n x ds) and Xt (m x dt) (DEVICE
  * float64, row major, bandwidth h * std as in compute_kernel), then runs conditional-gradient Gromov-Wasserstein with
- * the KL loss from T = p q^T (uniform p, q) until the loss changes by less than tol_abs or tol_rel (POT: 1e-9, 1e-9)
- * or max_iter (POT: 10000) steps.  Writes the loss at the final plan to *gw_dist (HOST), the iteration count to *iters
+ * the KL loss from T = p q^T (uniform p, q) until the loss changes by less than tol_abs or tol_rel (POT: 1e-9, 1e-9;
+ * both are floored at 4 float32 ulp of the loss, the resolution of the float32 gradient) or max_iter (POT: 10000) steps.  Writes the loss at the final plan to *gw_dist (HOST), the iteration count to *iters
  * (HOST, may be NULL) and the plan to T_out (DEVICE float32 n x m, may be NULL).  The dense contraction of every step
  * runs on the tensor cores (evrep_gemm_nt_3xtf32).  The linear minimisation oracle (an assignment problem) is, with lmo =
  * EVREP_LMO_AUCTION, Bertsekas' forward auction with epsilon scaling on the GPU (optimal up to n * 1e-9 * cost range; n <=
