@@ -601,10 +601,15 @@ __global__ void __launch_bounds__(AUC_THREADS, 1) k_auction(const float* __restr
           assigned[i] = j;
           price[j] = mybid[i];
           objbid[j] = 0ull;
-          winner[j] = INT_MAX;
         }
       }
       if (tid == 0) { s_rounds += 1; s_bids += nb; }
+      __syncthreads();
+      // 4. clear the winner slots (after the barrier: the losers of an object were still reading them in step 3)
+      for (int q = tid; q < nb; q += AUC_THREADS) {
+        const int i = queue[q], j = mybid_obj[i];
+        if (owner[j] == i) winner[j] = INT_MAX;
+      }
       __syncthreads();
     }
     if (status || eps <= eps_final) break;

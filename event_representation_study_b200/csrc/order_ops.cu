@@ -370,14 +370,23 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tore_tile_k(const uint2* __res
     const bool live = p0 + tid < npix;
     float o[C];
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const uint32_t v = live ? acc[c * TP + p0 + tid] : 0u;
-      o[c] = empty;
-      if (__any_sync(0xffffffffu, v != 0u)) {
-        if (v) {
-          float age = (float)(age0 - (int32_t)v);
-          age = fminf(age, max_time);
-          o[c] = fmaxf(logf(age + 1.f) - log151, 0.f);
+    for (int plane = 0; plane < 2; ++plane) {
+      // the cascade keeps the k most recent timestamps sorted: slot j is filled only if slot j - 1 is, so a warp stops
+      // loading a polarity's slots at the first one that is empty in all of its 32 pixels (slots past the second nearly
+      // always are)
+      bool alive = true;
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        const int c = plane * K + j;
+        o[c] = empty;
+        if (alive) {
+          const uint32_t v = live ? acc[c * TP + p0 + tid] : 0u;
+          alive = __any_sync(0xffffffffu, v != 0u);
+          if (v) {
+            float age = (float)(age0 - (int32_t)v);
+            age = fminf(age, max_time);
+            o[c] = fmaxf(logf(age + 1.f) - log151, 0.f);
+          }
         }
       }
     }
