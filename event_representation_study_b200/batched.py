@@ -313,7 +313,7 @@ def gw_kl(Xs, Xt, h=0.7, max_iter=10000, tol_rel=1e-9, tol_abs=1e-9, return_plan
 
 
 IMG_MODES = {"letterbox": 0, "squash": 1}
-INTERP = {"auto": 0, "linear": 1, "area": 2}
+INTERP = {"auto": 0, "linear": 1, "area": 2, "linear_torch": 3}
 
 
 def detector_input(rep, img_size=640, mode="letterbox", interp="auto", scale_in=255.0, scale_out=1.0 / 255.0, pad_value=114.0,

@@ -60,6 +60,10 @@ int run_gw_kl(const double* Xs, int n, int ds, const double* Xt, int m, int dt, 
 int launch_gemm_nt_3xtf32(const float* A, const float* B, float* C, int M, int N, int K, float alpha, const float* rv, const float* cv,
                           cudaStream_t stream);
 
+size_t est_workspace_bytes(int B);
+int launch_est(const uint16_t* x, const uint16_t* y, const float* t, const int8_t* p, const int64_t* win_offsets_host, int B, int H, int W, int C,
+               const double* breaks, const double* slope, const double* icpt, int K, float* out, void* workspace, size_t workspace_bytes,
+               cudaStream_t stream);
 int launch_auction(const float* cost, int n, double eps_rel, int* sigma, int* stats, cudaStream_t stream);
 int launch_image_pipeline(const float* rep, int B, int H, int W, int C, int img_size, int mode, int interp, float scale_in, float scale_out,
                           float pad, int reverse, float* out, cudaStream_t stream);
@@ -401,6 +405,23 @@ int evrep_gw_kl(const double* Xs, int n, int ds, const double* Xt, int m, int dt
   EVREP_GUARD_END
 }
 
+size_t evrep_est_workspace_bytes(int B) { return B < 0 ? 0 : est_workspace_bytes(B > 0 ? B : 1); }
+
+int evrep_est_quantize_batched(const uint16_t* x, const uint16_t* y, const float* t, const int8_t* p, const int64_t* win_offsets, int B, int H,
+                               int W, int C, const double* breaks, const double* slope, const double* icpt, int K, float* out, void* workspace,
+                               size_t workspace_bytes, evrep_stream_t stream) {
+  EVREP_GUARD_BEGIN
+  if (B < 0 || !win_offsets) { set_error("B must be >= 0 and win_offsets non-null"); return EVREP_EINVAL; }
+  if (B > 65535) { set_error("at most 65535 windows per call"); return EVREP_EUNSUPPORTED; }
+  if (H < 1 || W < 1 || H > 65535 || W > 65535) { set_error("sensor size %d x %d unsupported", W, H); return EVREP_EINVAL; }
+  if (C < 2 || C > 64) { set_error("EST needs 2 <= C <= 64 temporal bins (the reference divides by C - 1)"); return EVREP_EINVAL; }
+  if (K < 0 || !slope || !icpt || (K > 0 && !breaks)) { set_error("bad piecewise-linear table"); return EVREP_EINVAL; }
+  if (B == 0) return EVREP_OK;
+  if (!out || (win_offsets[B] > 0 && (!x || !y || !t || !p))) { set_error("null array"); return EVREP_EINVAL; }
+  return launch_est(x, y, t, p, win_offsets, B, H, W, C, breaks, slope, icpt, K, out, workspace, workspace_bytes, (cudaStream_t)stream);
+  EVREP_GUARD_END
+}
+
 int evrep_assignment_auction(const float* cost, int n, double eps_rel, int* sigma, int* stats, evrep_stream_t stream) {
   EVREP_GUARD_BEGIN
   if (!cost || !sigma || !stats) { set_error("null argument"); return EVREP_EINVAL; }
@@ -422,7 +443,7 @@ int evrep_image_pipeline_batched(const float* rep, int B, int H, int W, int C, i
   if (B < 0 || H < 1 || W < 1 || C < 1 || C > 4096 || img_size < 1 || img_size > 65535) { set_error("bad image geometry"); return EVREP_EINVAL; }
   if (B > 65535) { set_error("at most 65535 windows per call"); return EVREP_EUNSUPPORTED; }
   if (mode != EVREP_IMG_LETTERBOX && mode != EVREP_IMG_SQUASH) { set_error("unknown mode %d", mode); return EVREP_EINVAL; }
-  if (interp < EVREP_INTERP_AUTO || interp > EVREP_INTERP_AREA) { set_error("unknown interpolation %d", interp); return EVREP_EINVAL; }
+  if (interp < EVREP_INTERP_AUTO || interp > EVREP_INTERP_LINEAR_TORCH) { set_error("unknown interpolation %d", interp); return EVREP_EINVAL; }
   if (B == 0) return EVREP_OK;
   if (!rep || !out) { set_error("null image"); return EVREP_EINVAL; }
   return launch_image_pipeline(rep, B, H, W, C, img_size, mode, interp, scale_in, scale_out, pad_value, reverse_channels, out, (cudaStream_t)stream);

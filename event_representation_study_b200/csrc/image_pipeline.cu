@@ -23,7 +23,7 @@ struct ImgArgs {
   int rw, rh;                // resized width / height
   int left, top;             // where the resized image sits in the canvas
   int out_w, out_h;          // canvas
-  int interp;                // 1 linear, 2 area
+  int interp;                // 1 linear (cv2), 2 area (cv2), 3 linear with float32 coordinates (torch interpolate)
   int reverse;               // 1: output channel c holds input channel C - 1 - c
   float scale_in, scale_out, pad;
   double sx, sy;             // source pixels per destination pixel (cv::resize: 1 / (dsize / ssize))
@@ -45,6 +45,22 @@ __device__ __forceinline__ void linear_taps(int d, double scale, int ssize, int*
   idx[1] = min(s + 1, ssize - 1);
   wgt[0] = (float)(1.0 - fx);
   wgt[1] = (float)fx;
+  *n = 2;
+}
+
+// torch.nn.functional.interpolate(mode="bilinear", align_corners=False) on float32 tensors (what the reference's learned
+// representation uses, learned_repr.py:113-115): the same taps, but scale and source coordinate are float32
+// (area_pixel_compute_source_index: scale * (d + 0.5f) - 0.5f, clamped at 0)
+__device__ __forceinline__ void linear_taps_f32(int d, float scale, int ssize, int* idx, float* wgt, int* n) {
+  float fx = scale * ((float)d + 0.5f) - 0.5f;
+  if (fx < 0.f) fx = 0.f;
+  int s = (int)fx;
+  if (s > ssize - 1) s = ssize - 1;
+  const float l1 = fx - (float)s;
+  idx[0] = s;
+  idx[1] = s + (s < ssize - 1 ? 1 : 0);
+  wgt[0] = 1.f - l1;
+  wgt[1] = l1;
   *n = 2;
 }
 
@@ -91,6 +107,9 @@ __global__ void __launch_bounds__(256) k_image_pipeline(const float* __restrict_
   if (a.interp == 1) {
     linear_taps(rx, a.sx, a.W, xi, xw, &nx);
     linear_taps(ry, a.sy, a.H, yi, yw, &ny);
+  } else if (a.interp == 3) {
+    linear_taps_f32(rx, (float)a.W / (float)a.rw, a.W, xi, xw, &nx);
+    linear_taps_f32(ry, (float)a.H / (float)a.rh, a.H, yi, yw, &ny);
   } else {
     area_taps(rx, a.sx, a.W, xi, xw, &nx);
     area_taps(ry, a.sy, a.H, yi, yw, &ny);
@@ -153,6 +172,10 @@ int launch_image_pipeline(const float* rep, int B, int H, int W, int C, int img_
     const double dw = (double)(img_size - a.rw) / 2.0, dh = (double)(img_size - a.rh) / 2.0;
     a.left = (int)lround(dw - 0.1);
     a.top = (int)lround(dh - 0.1);
+    if (interp == 3) {  // letterbox_image_batch (learned_repr.py:130-131): floor division
+      a.left = (img_size - a.rw) / 2;
+      a.top = (img_size - a.rh) / 2;
+    }
   } else {
     a.rw = a.rh = img_size;
     a.left = a.top = 0;

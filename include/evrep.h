@@ -31,6 +31,7 @@
  *   evrep_gw_kl                  representation_search/gromov_wasserstein.py:39-69 (OTMI.__init__ + solve, GWD-B:
  *                                POT ot.gromov.gromov_wasserstein(Ks, Kt, p, q, "kl_loss"))
  *   evrep_gemm_nt_3xtf32         the tensor product constC - hC1 T hC2^T inside that solve (POT ot/gromov tensor_product)
+ *   evrep_est_quantize_batched   ev-YOLOv6/yolov6/models/learned_repr.py:143-172 (QuantizationLayer.forward, inference only)
  *   evrep_image_pipeline_batched ev-YOLOv6/yolov6/data/gen1_2yolo.py:230-265,321-341,397 (resize_image, letterbox, CHW + reversal),
  *                                gen4/precompute_reps.py:216-251 (resize_image_process), yolov6/core/engine.py:629-635 (/ 255)
  */
@@ -222,8 +223,22 @@ int evrep_gemm_nt_3xtf32(const float* A, const float* B, float* C, int M, int N,
 #define EVREP_INTERP_AUTO 0
 #define EVREP_INTERP_LINEAR 1
 #define EVREP_INTERP_AREA 2
+#define EVREP_INTERP_LINEAR_TORCH 3 /* torch interpolate(bilinear, align_corners=False) arithmetic + letterbox_image_batch placement (learned_repr.py:94-141) */
 int evrep_image_pipeline_batched(const float* rep, int B, int H, int W, int C, int img_size, int mode, int interp, float scale_in,
                                  float scale_out, float pad_value, int reverse_channels, float* out, evrep_stream_t stream);
+
+/* EST, the reference's learned quantisation layer, forward only (ev-YOLOv6/yolov6/models/learned_repr.py:143-172):
+ * out[b, y, x, p * C + i] = sum over the events of window b at (x, y, p) of tn * f(tn - i / (C - 1)), tn = t / max(t of the
+ * window) in float32, f = the ValueLayer MLP given as the piecewise-linear function it is: `breaks` (K sorted float64
+ * breakpoints), `slope` and `icpt` (K + 1 float64 each; segment j covers breaks[j-1] <= u < breaks[j]) - compile them from
+ * the weights with event_representation_study_b200/est.py::compile_value_layer.  All three are DEVICE pointers.
+ * x, y, p as everywhere; t: DEVICE float32 (the reference's event tensor is float).  out: DEVICE float32 (B, H, W, 2C),
+ * i.e. torch.cat([vox[:, 0], vox[:, 1]], 1) in HWC.  p > 0 selects the second half.  C >= 2.  Accumulation uses float
+ * atomics like the reference's put_(accumulate=True): reproducible to rounding only. */
+size_t evrep_est_workspace_bytes(int B);
+int evrep_est_quantize_batched(const uint16_t* x, const uint16_t* y, const float* t, const int8_t* p, const int64_t* win_offsets, int B,
+                               int H, int W, int C, const double* breaks, const double* slope, const double* icpt, int K, float* out,
+                               void* workspace, size_t workspace_bytes, evrep_stream_t stream);
 
 #ifdef __cplusplus
 }

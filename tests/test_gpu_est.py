@@ -1,0 +1,81 @@
+"""EST (learned quantisation layer, forward) on the GPU against fixtures produced by the reference's own ValueLayer /
+QuantizationLayer (tests/golden/est_*.npz) and against the torch-CPU oracle on larger seeded inputs.  Bar: 1e-5 relative
+with an absolute floor of 2e-5 - the reference evaluates its MLP in float32 (7e-7 absolute per evaluation against the
+exact piecewise-linear function, measured) and both sides add a few to a few dozen such values per voxel with float
+atomics in arbitrary order."""
+import numpy as np
+import pytest
+
+from conftest import assert_close, golden, load
+
+pytestmark = pytest.mark.gpu
+ATOL = 2e-5
+
+
+@pytest.fixture(scope="module")
+def M(cuda_device):
+    import event_representation_study_b200.batched as eb
+    import event_representation_study_b200.est as est
+    return eb, est
+
+
+def _batch(eb, events, B):
+    wins = []
+    for b in range(B):
+        e = events[events[:, 4] == b]
+        wins.append({"x": e[:, 0].astype(np.uint16), "y": e[:, 1].astype(np.uint16), "t": e[:, 2].astype(np.int64), "p": e[:, 3].astype(np.int8)})
+    return eb.pack_events(wins, "cuda")
+
+
+def _tables(est, ws, bs):
+    import torch
+    br, sl, ic = est.compile_value_layer(ws, bs, 0.1)
+    return tuple(torch.as_tensor(v, dtype=torch.float64, device="cuda") for v in (br, sl, ic))
+
+
+@pytest.mark.parametrize("name,path", golden("est_*"), ids=[n for n, _ in golden("est_*")])
+def test_est_matches_reference_fixtures(M, name, path):
+    eb, est = M
+    g = load(path)
+    C, H, W = (int(v) for v in g["dim"])
+    B = g["out"].shape[0]
+    ev = _batch(eb, g["events"], B)
+    tables = _tables(est, [g[f"w{i}"] for i in range(3)], [g[f"b{i}"] for i in range(3)])
+    vox = est.quantize(ev, H, W, C, tables).permute(0, 3, 1, 2).cpu().numpy()
+    assert_close(vox, g["vox"], rtol=1e-5, atol=ATOL, what=name + " vox")
+    out = est.forward(ev, H, W, C, tables, image_size=int(g["image_size"])).cpu().numpy()
+    assert_close(out, g["out"], rtol=1e-5, atol=ATOL, what=name + " letterboxed")
+
+
+def test_est_gen1_size_vs_oracle(M):
+    """the reference's configuration: dim = (6, 240, 304), image_size 640 (yolo.py:56-61), two windows of 50 k events"""
+    import torch
+    from oracle import est as oest
+    eb, est = M
+    g = load(golden("est_small")[0][1])
+    ws, bs = [g[f"w{i}"] for i in range(3)], [g[f"b{i}"] for i in range(3)]
+    C, H, W, S = 6, 240, 304, 640
+    rng = np.random.default_rng(12)
+    rows = []
+    for b, n in enumerate((50000, 31000)):
+        t = np.sort(rng.integers(0, 100000, n)).astype(np.float32)
+        rows.append(np.stack([rng.integers(0, W, n), rng.integers(0, H, n), t, rng.integers(0, 2, n), np.full(n, b)], 1))
+    events = np.concatenate(rows).astype(np.float32)
+    with torch.no_grad():
+        vox_w, out_w = oest.est_forward(torch.tensor(events), ws, bs, (C, H, W), S)
+    ev = _batch(eb, events, 2)
+    tables = _tables(est, ws, bs)
+    assert_close(est.quantize(ev, H, W, C, tables).permute(0, 3, 1, 2).cpu().numpy(), vox_w.numpy(), rtol=1e-5, atol=ATOL, what="vox")
+    assert_close(est.forward(ev, H, W, C, tables, image_size=S).cpu().numpy(), out_w.numpy(), rtol=1e-5, atol=ATOL, what="out")
+
+
+def test_est_argument_checks(M):
+    import torch
+    from event_representation_study_b200._lib import EvrepError
+    eb, est = M
+    ev = _batch(eb, np.array([[1, 1, 5, 1, 0], [2, 2, 9, 0, 0]], np.float32), 1)
+    tab = tuple(torch.zeros(k, dtype=torch.float64, device="cuda") for k in (0, 1, 1))
+    with pytest.raises(EvrepError):
+        est.quantize(ev, 8, 8, 1, tab)  # C - 1 == 0: the reference divides by zero
+    out = est.quantize(ev, 8, 8, 2, tab)  # f == 0 everywhere
+    assert float(out.abs().max()) == 0.0

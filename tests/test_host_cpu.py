@@ -161,3 +161,25 @@ def test_bench_reference_arm_runs_on_cpu():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_value_layer_compiles_to_the_same_piecewise_linear_function():
+    """host logic of the EST path: the LeakyReLU MLP of one scalar, compiled to breakpoints / slopes / intercepts, is the
+    same function as the MLP (float64, 1e-12) - on the reference-trained weights of the fixture and on random ones"""
+    from event_representation_study_b200.est import compile_value_layer
+    z = np.load(os.path.join(ROOT, "tests", "golden", "est_small.npz"))
+    rng = np.random.default_rng(0)
+    cases = [([z[f"w{i}"] for i in range(3)], [z[f"b{i}"] for i in range(3)]),
+             ([rng.standard_normal((40, 1)), rng.standard_normal((30, 40)), rng.standard_normal((20, 30)), rng.standard_normal((1, 20))],
+              [rng.standard_normal(40), rng.standard_normal(30), rng.standard_normal(20), rng.standard_normal(1)])]
+    u = np.linspace(-1.5, 1.5, 30001)
+    for ws, bs in cases:
+        br, sl, ic = compile_value_layer(ws, bs, 0.1)
+        assert np.all(np.diff(br) > 0) and len(sl) == len(br) + 1 == len(ic)
+        h = u[:, None]
+        for w, b in zip(ws[:-1], bs[:-1]):
+            h = h @ np.asarray(w, np.float64).T + np.asarray(b, np.float64)
+            h = np.where(h > 0, h, 0.1 * h)
+        want = (h @ np.asarray(ws[-1], np.float64).T + np.asarray(bs[-1], np.float64))[:, 0]
+        j = np.searchsorted(br, u, side="right")
+        assert np.abs(sl[j] * u + ic[j] - want).max() <= 1e-12 * max(1.0, np.abs(want).max())

@@ -180,3 +180,16 @@ def test_image_pipeline_oracle_matches_reference_fixtures(name, path):
     g = load(path)
     got = oimg.detector_input(g["rep"], int(g["img_size"]), str(g["mode"]))
     assert got.dtype == np.float32 and np.array_equal(got, g["out"])
+
+
+# ---- EST learned quantisation layer: oracle vs fixtures made with the reference's classes ----
+@pytest.mark.parametrize("name,path", golden("est_*"), ids=[n for n, _ in golden("est_*")])
+def test_est_oracle_matches_reference_fixtures(name, path):
+    import torch
+    from oracle import est as oest
+    g = load(path)
+    ws = [g[f"w{i}"] for i in range(3)]
+    bs = [g[f"b{i}"] for i in range(3)]
+    with torch.no_grad():
+        vox, lb = oest.est_forward(torch.tensor(g["events"]), ws, bs, tuple(int(v) for v in g["dim"]), int(g["image_size"]))
+    assert np.allclose(lb.numpy(), g["out"], rtol=1e-6, atol=1e-6) and np.allclose(vox.numpy(), g["vox"], rtol=1e-6, atol=1e-6)
