@@ -63,7 +63,7 @@ def rep_line(name, ev_per_step, sec, alg_bytes, cpu_ev_per_s, cpu_note, extra=No
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--only", default="config1,config2,config3,gwd,gwdb,img")
+    ap.add_argument("--only", default="config1,config2,config3,gwd,gwdb,img,est")
     a = ap.parse_args()
     import torch
     import event_representation_study_b200.batched as eb
@@ -154,6 +154,32 @@ def main():
                                            "algorithmic_bytes_per_step": alg},
                               "cpu_baseline": {"value": 1.0 / c, "unit": "windows/s", "cores": 1, "kind": "reference",
                                                "sample": f"{n} windows, cv2 {what.split()[3] if False else ''}resize + letterbox + transpose per window (oracle/image_pipeline.py around cv2)"}}), flush=True)
+
+    if "est" in only:  # the learned EST quantisation layer, forward (dim = (6, 240, 304), image 640: yolo.py:56-61)
+        import event_representation_study_b200.est as est
+        from oracle import est as oest
+        g = np.load(os.path.join(ROOT, "tests", "golden", "est_small.npz"))
+        ws, bs = [g[f"w{i}"] for i in range(3)], [g[f"b{i}"] for i in range(3)]
+        t0 = time.perf_counter()
+        br, sl, ic = est.compile_value_layer(ws, bs, 0.1)
+        compile_s = time.perf_counter() - t0
+        tables = tuple(torch.as_tensor(v, dtype=torch.float64, device=dev) for v in (br, sl, ic))
+        C, H, W, S, B, N = 6, 240, 304, 640, 32, 50_000
+        ev = batch(B, N, H, W, 8000)
+        tf = ev.t.float()
+        sec_q = timed(lambda: est.quantize(ev, H, W, C, tables, t_float=tf), a.steps)
+        sec_f = timed(lambda: est.forward(ev, H, W, C, tables, image_size=S, t_float=tf), a.steps)
+        rng = np.random.default_rng(1)
+        one = torch.tensor(np.stack([rng.integers(0, W, N), rng.integers(0, H, N), np.sort(rng.integers(0, 100000, N)), rng.integers(0, 2, N),
+                                     np.zeros(N)], 1), dtype=torch.float32)
+        with torch.no_grad():
+            c, n = cpu_time(lambda i: oest.est_forward(one, ws, bs, (C, H, W), S), 6.0, 10)
+        print(json.dumps({"workload": f"EST learned quantisation forward, dim (6, 240, 304) -> 12 x 640 x 640, {N} ev/window, batch {B}",
+                          "value": B * N / sec_f / 1e9, "unit": "Gevents/s", "ms_per_step": sec_f * 1e3, "quantize_only_ms": sec_q * 1e3,
+                          "pwl_segments": int(len(sl)), "compile_ms_host_once": compile_s * 1e3,
+                          "cpu_baseline": {"value": N / c / 1e9, "unit": "Gevents/s", "cores": "torch CPU threads", "kind": "port",
+                                           "sample": f"{n} windows, oracle/est.py (the reference's forward restated on CPU tensors: MLP evaluated {C} times per event)"},
+                          "speedup_vs_cpu_port": (B * N / sec_f) / (N / c)}), flush=True)
 
     if "gwdb" in only:  # config 5, GWD-B: conditional-gradient GW with the KL loss, LMO = auction on the GPU.  An exact CPU
         # assignment solve costs ~1 s per iteration at n = 1000 on these structured costs (scipy and our host solver alike),
