@@ -412,7 +412,10 @@ __global__ void __launch_bounds__(BIN_THREADS) k_scan(const uint32_t* __restrict
 // pass 3: scatter the events into their buckets as 8-byte records.  HBM: reads 9 B/event, writes 8 B/event.
 // ---------------------------------------------------------------------------------------------
 template <typename TT, int MODE, bool SPLIT>
-__global__ void __launch_bounds__(BIN_THREADS, 2) k_bin(const uint16_t* __restrict__ x, const uint16_t* __restrict__ y,
+#ifndef EVREP_BIN_CTAS
+#define EVREP_BIN_CTAS 2
+#endif
+__global__ void __launch_bounds__(BIN_THREADS, EVREP_BIN_CTAS) k_bin(const uint16_t* __restrict__ x, const uint16_t* __restrict__ y,
                                                      const TT* __restrict__ t, const int8_t* __restrict__ p,
                                                      WinParams* __restrict__ wp, const SnapParams* __restrict__ snap,
                                                      const int32_t* __restrict__ sc_prefix, const int32_t* __restrict__ sc_win,

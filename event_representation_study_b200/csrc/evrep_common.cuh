@@ -16,7 +16,10 @@ namespace evrep {
 constexpr int BIN_THREADS = 512;
 constexpr int EPT = 8;
 constexpr int CHUNK = BIN_THREADS * EPT;  // 4096 events per CTA iteration
-constexpr int SC_CHUNKS = 2;
+#ifndef EVREP_SC_CHUNKS
+#define EVREP_SC_CHUNKS 2
+#endif
+constexpr int SC_CHUNKS = EVREP_SC_CHUNKS;
 constexpr int SUPER = CHUNK * SC_CHUNKS;  // 8192 events per CTA ("super-chunk"): the unit of the counting / scatter passes
 constexpr int MAX_TILES = 4096;           // buckets per window (shared-memory histogram size bound)
 constexpr int MIN_TILE_PX = 256;

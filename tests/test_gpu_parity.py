@@ -403,3 +403,36 @@ def test_config3_properties(E):
     # TORE: ages ascending inside each polarity's k slots; empty slots carry the constant 15.0128
     assert bool((tr[..., 0:5] <= tr[..., 1:6]).all()) and bool((tr[..., 6:11] <= tr[..., 7:12]).all())
     assert abs(float(tr.max()) - 15.0128) < 1e-3
+
+
+# ---- the super-chunk binning: window sizes around the 8192-event super-chunk and 4096-event chunk boundaries, windows
+# that start at unaligned event offsets, many tiny windows, and bit-identical results whatever the batch composition ----
+@pytest.mark.parametrize("sizes", [
+    [8191, 8192, 8193, 1, 16383, 16384, 16385, 4095, 4096, 4097, 3, 24577],
+    [5] * 40 + [8200] + [1] * 25 + [12289],
+    [100_003],
+], ids=["boundaries", "many-tiny", "one"])
+def test_binning_boundaries_all_tile_ops(E, sizes):
+    from oracle import representations as orep
+    H, W = 96, 128
+    wins = streams(H, W, sizes, 700)
+    ev = E.pack_events(wins, "cuda")
+    er = np_(E.ergo12(ev, H, W))
+    es = np_(E.event_stack(ev, H, W, 12))
+    tr = np_(E.tore(ev, H, W, 6))
+    assert (E.window_flags(ev) == 0).all()
+    for i, w in enumerate(wins):
+        with np.errstate(all="ignore"):
+            want = orep.ergo12(w["x"], w["y"], w["t"], w["p"], H, W)
+        assert_close(er[i], want, rtol=RTOL, atol=VAR_ATOL, what=f"ergo window {i} ({sizes[i]} events)")
+        p01 = (w["p"].astype(np.int32) + 1) // 2
+        assert np.array_equal(es[i], orep.event_stack(w["x"], w["y"], w["t"], p01, H, W, 12)), f"event stack window {i}"
+        t = w["t"].astype(np.int32)
+        want_t = orep.tore(w["x"].astype(np.int32) + 1, w["y"].astype(np.int32) + 1, t, w["p"].astype(np.int32), t[-1], 6, (H, W))
+        assert_close(tr[i], want_t, rtol=RTOL, atol=TORE_ATOL, what=f"tore window {i}")
+    # a window computed alone equals the same window inside the batch, bit for bit (deterministic placement, integer sums)
+    k = int(np.argmax(sizes))
+    alone = np_(E.ergo12(E.pack_events([wins[k]], "cuda"), H, W))[0]
+    assert np.array_equal(np.nan_to_num(alone), np.nan_to_num(er[k]))
+    again = np_(E.ergo12(ev, H, W))
+    assert np.array_equal(np.nan_to_num(again), np.nan_to_num(er))
