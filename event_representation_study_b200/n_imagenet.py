@@ -1,0 +1,124 @@
+"""Drop-in mirrors of the N-ImageNet loader wrappers around the hot path (caller ii):
+n_imagenet/real_cnn_model/data/imagenet.py:1002-1134 - fix_events_training and reshape_then_{voxel_grid, optimized,
+event_stack, to_image, tore, time_surface}.  Same names, arguments (`event_tensor`: (N, 4) torch tensor [x, y, t, p],
+p in {-1, +1}; `augment`; `height` / `width` keywords) and return layout (float32 torch CPU tensors, channels first
+except to_image, which the reference leaves channels last); each one calls the same representation entry point as the
+reference, here the CUDA-backed mirror.
+
+Two reference lines cannot run on current numpy / at all and are mirrored by intent, not by exception:
+  * reshape_then_to_image ends with `rep.float()` on a numpy array (AttributeError in the reference, imagenet.py:1077);
+    here the array is converted to a float32 tensor like every other wrapper does.
+  * reshape_then_time_surface uses `np.int`, removed in numpy 1.24 (imagenet.py:1125-1126); plain `int` is used.
+"""
+import numpy as np
+import numpy.lib.recfunctions as rfn
+import torch
+
+from . import tonic_compat as tonic_transforms
+from .representations.event_stack import EventStack
+from .representations.optimized_representation import get_optimized_representation
+from .representations.time_surface import ToTimesurface
+from .representations.tore import events2ToreFeature
+
+IMAGE_H = 224
+IMAGE_W = 224
+
+
+def fix_events_training(events):
+    """imagenet.py:1002-1006: (N, 4) float64 array -> structured array with f8 fields x, y, t, p"""
+    events = rfn.unstructured_to_structured(events)
+    events.dtype = [("x", "<f8"), ("y", "<f8"), ("t", "<f8"), ("p", "<f8")]
+    return events
+
+
+def reshape_then_voxel_grid(event_tensor, augment=None, **kwargs):
+    """imagenet.py:1009-1022"""
+    if augment is not None:
+        event_tensor = augment(event_tensor)
+    H = kwargs.get("height", IMAGE_H)
+    W = kwargs.get("width", IMAGE_W)
+    transformation = tonic_transforms.ToVoxelGrid((W, H, 2), n_time_bins=12)
+    reshaped_return_data = fix_events_training(event_tensor.numpy())
+    rep = transformation(reshaped_return_data)
+    rep = torch.tensor(rep.transpose(0, 2, 3, 1)[..., 0])
+    return rep.float()
+
+
+def reshape_then_optimized(event_tensor, augment=None, **kwargs):
+    """imagenet.py:1025-1039"""
+    if augment is not None:
+        event_tensor = augment(event_tensor)
+    H = kwargs.get("height", IMAGE_H)
+    W = kwargs.get("width", IMAGE_W)
+    reshaped_return_data = fix_events_training(event_tensor.numpy())
+    rep = get_optimized_representation(reshaped_return_data, reshaped_return_data.shape[0], H, W)
+    rep = torch.tensor(rep.transpose(2, 0, 1))
+    return rep.float()
+
+
+def reshape_then_event_stack(event_tensor, augment=None, **kwargs):
+    """imagenet.py:1042-1060"""
+    if augment is not None:
+        event_tensor = augment(event_tensor)
+    H = kwargs.get("height", IMAGE_H)
+    W = kwargs.get("width", IMAGE_W)
+    reshaped_return_data = fix_events_training(event_tensor.numpy())
+    reshaped_return_data["p"] = (reshaped_return_data["p"] + 1) // 2
+    stack_size = 12
+    transformation = EventStack(stack_size, reshaped_return_data.shape[0], H, W)
+    pre_stack = transformation.pre_stack(reshaped_return_data, reshaped_return_data[-1]["t"])
+    post_stack = transformation.post_stack(pre_stack)
+    rep = torch.tensor(post_stack.transpose(3, 0, 1, 2)[..., 0])
+    return rep.float()
+
+
+def reshape_then_to_image(event_tensor, augment=None, **kwargs):
+    """imagenet.py:1063-1077 (see the module docstring for the last line)"""
+    if augment is not None:
+        event_tensor = augment(event_tensor)
+    H = kwargs.get("height", IMAGE_H)
+    W = kwargs.get("width", IMAGE_W)
+    reshaped_return_data = fix_events_training(event_tensor.numpy())
+    transformation = tonic_transforms.ToImage((W, H, 2))
+    reshaped_return_data["p"] = (reshaped_return_data["p"] + 1) // 2
+    rep = transformation(reshaped_return_data)
+    rep = rep.transpose(1, 2, 0)
+    return torch.tensor(np.ascontiguousarray(rep)).float()
+
+
+def reshape_then_tore(event_tensor, augment=None, **kwargs):
+    """imagenet.py:1080-1107"""
+    if augment is not None:
+        event_tensor = augment(event_tensor)
+    H = kwargs.get("height", IMAGE_H)
+    W = kwargs.get("width", IMAGE_W)
+    k = 6
+    reshaped_return_data = fix_events_training(event_tensor.numpy())
+    x, y, ts, pol = (reshaped_return_data["x"], reshaped_return_data["y"], reshaped_return_data["t"], reshaped_return_data["p"])
+    x = x - min(x) + 1
+    y = y - min(y) + 1
+    sampleTimes = ts[-1]
+    frameSize = (H, W)
+    rep = events2ToreFeature(x, y, ts, pol, sampleTimes, k, frameSize)
+    rep = torch.tensor(rep.transpose(2, 0, 1))
+    return rep.float()
+
+
+def reshape_then_time_surface(event_tensor, augment=None, **kwargs):
+    """imagenet.py:1110-1134"""
+    if augment is not None:
+        event_tensor = augment(event_tensor)
+    H = kwargs.get("height", IMAGE_H)
+    W = kwargs.get("width", IMAGE_W)
+    reshaped_return_data = fix_events_training(event_tensor.numpy())
+    reshaped_return_data["p"] = ((reshaped_return_data["p"] + 1) / 2).astype(np.int8)
+    transform = ToTimesurface(sensor_size=(W, H, 2), surface_dimensions=None, tau=50000, decay="exp")
+    t = reshaped_return_data["t"]
+    t_norm = (t - t[0]) / (t[-1] - t[0]) * 6
+    idx = np.searchsorted(t_norm, np.arange(6) + 1)
+    reshaped_return_data["x"] = reshaped_return_data["x"].astype(int)
+    reshaped_return_data["y"] = reshaped_return_data["y"].astype(int)
+    rep = transform(reshaped_return_data, idx)
+    rep = rep.reshape((-1, rep.shape[-2], rep.shape[-1]))
+    rep = torch.tensor(rep.transpose(1, 2, 0)) if not torch.is_tensor(rep) else rep.permute(1, 2, 0)
+    return rep.float()

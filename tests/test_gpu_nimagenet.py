@@ -1,0 +1,57 @@
+"""The N-ImageNet loader wrappers (n_imagenet/real_cnn_model/data/imagenet.py:1002-1134, SURVEY.md 8b caller ii) through
+the drop-in module, against outputs of the reference's own wrappers (tests/golden/nimg_wrappers.npz, made by
+oracle/gen_golden_nimagenet.py; the time-surface wrapper of the reference cannot run - see that script - and is pinned
+through the reference's ToTimesurface with the casts the wrapper intends)."""
+import numpy as np
+import pytest
+
+from conftest import assert_close, golden, load
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def N(cuda_device):
+    import event_representation_study_b200.n_imagenet as n
+    return n
+
+
+@pytest.fixture(scope="module")
+def G():
+    return load(golden("nimg_wrappers")[0][1])
+
+
+def test_fix_events_training(N, G):
+    s = N.fix_events_training(G["events_s"].copy())
+    assert s.dtype.names == ("x", "y", "t", "p") and all(s.dtype[k] == np.dtype("<f8") for k in s.dtype.names)
+    assert np.array_equal(s["t"], G["events_s"][:, 2])
+
+
+@pytest.mark.parametrize("name,src,rtol,atol", [
+    ("voxel_grid", "events_s", 1e-5, 2e-6),
+    ("optimized", "events_us", 1e-5, 2e-7),
+    ("event_stack", "events_s", 0, 0),
+    ("tore", "events_us", 1e-5, 1e-6),
+    ("time_surface", "events_us", 1e-5, 1e-30),
+    ("to_image", "events_s", 0, 0),
+])
+def test_reshape_then_wrappers_match_the_reference(N, G, name, src, rtol, atol):
+    import torch
+    H, W = int(G["H"]), int(G["W"])
+    rep = getattr(N, "reshape_then_" + name)(torch.tensor(G[src].copy()), height=H, width=W)
+    assert torch.is_tensor(rep) and rep.dtype == torch.float32 and not rep.is_cuda
+    want = G[name]
+    assert tuple(rep.shape) == want.shape
+    if rtol == 0:
+        assert np.array_equal(rep.numpy(), want)
+    else:
+        assert_close(rep.numpy(), want, rtol=rtol, atol=atol, what=name)
+
+
+def test_augment_hook_is_applied_first(N, G):
+    import torch
+    H, W = int(G["H"]), int(G["W"])
+    flip = lambda e: torch.stack([W - 1 - e[:, 0], e[:, 1], e[:, 2], e[:, 3]], 1)  # noqa: E731
+    a = N.reshape_then_to_image(torch.tensor(G["events_s"].copy()), augment=flip, height=H, width=W)
+    b = N.reshape_then_to_image(torch.tensor(G["events_s"].copy()), height=H, width=W)
+    assert np.array_equal(a.numpy(), b.numpy()[:, ::-1])
