@@ -20,7 +20,15 @@ class ToVoxelGrid:
             raise IndexError("ToVoxelGrid needs at least two events")  # t[-1] - t[0] on a shorter stream fails in tonic
         p = events["p"]
         p[p == 0] = -1  # tonic rewrites the caller's polarity field in place
-        ev = one_window(events["x"], events["y"], events["t"], p, H, W)
+        t = np.asarray(events["t"])
+        if t.dtype.kind == "f" and not np.array_equal(t, np.floor(t)):
+            # fractional timestamps (N-ImageNet hands seconds as float64, imagenet.py:1002-1020): tonic only uses
+            # (t - t[0]) / (t[-1] - t[0]), so put that on a 2^30 integer grid (error < 1e-9 of the window)
+            span = float(t[-1] - t[0])
+            if not (span > 0 and np.all(t >= t[0]) and np.all(t <= t[-1])):
+                raise ValueError("ToVoxelGrid on the GPU needs t[0] <= t <= t[-1] with t[-1] > t[0] for fractional timestamps")
+            t = np.rint((t - t[0]) / span * float(2**30 - 2)).astype(np.int64)
+        ev = one_window(events["x"], events["y"], t, p, H, W)
         out = eb.voxel_grid(ev, H, W, self.n_time_bins, "tonic")[0]
         return out.double().cpu().numpy()[:, None]  # (n_bins, 1, H, W) float64
 
