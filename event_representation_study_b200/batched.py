@@ -349,3 +349,35 @@ def assignment_auction(cost, eps_rel=1e-9):
                                        torch.cuda.current_stream(cost.device).cuda_stream))
     r, b, status = (int(v) for v in st.cpu())
     return sigma, {"rounds": r, "bids": b, "status": status}
+
+
+FILTERS = {"refractory": 0, "contrast": 1, "resize": 2}
+_FILTER_STATE_DTYPE = {"refractory": torch.float64, "contrast": torch.int32, "resize": torch.float32}
+
+
+def filter_state(kind, B, H, W, device="cuda"):
+    """Fresh state for `filter_events`: -inf last timestamps (refractory), zero activity (contrast) / change map (resize)."""
+    fill = float("-inf") if kind == "refractory" else 0
+    return torch.full((B, H, W), fill, dtype=_FILTER_STATE_DTYPE[kind], device=device)
+
+
+def filter_events(ev, H, W, kind, param=0.0, state=None, fx=1, fy=1):
+    """ev-licious' per-pixel stateful filters over a batch of streams (utils.py:143-158, 184-200) -> (mask, state):
+    mask is a uint8 CUDA tensor with one entry per event (1 = the event passes), state the (B, H, W) per-pixel state,
+    updated in place, to pass to the next call of the same streams.  kind: "refractory" (param = period), "contrast"
+    (param = factor) or "resize" (H, W = the change-map size, fx, fy = cell size)."""
+    B = len(ev.offsets) - 1
+    dev = ev.x.device
+    if state is None:
+        state = filter_state(kind, B, H, W, dev)
+    if state.dtype != _FILTER_STATE_DTYPE[kind] or tuple(state.shape) != (B, H, W) or not state.is_cuda or not state.is_contiguous():
+        raise ValueError(f"state must be a contiguous CUDA {_FILTER_STATE_DTYPE[kind]} tensor of shape {(B, H, W)}")
+    total = int(ev.offsets[-1])
+    mask = torch.empty(max(total, 1), dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    ws = _workspace(dev, stream, lib.evrep_workspace_bytes(7, B, total, H, W, 1))
+    offs = np.ascontiguousarray(ev.offsets, np.int64)
+    check(lib.evrep_filter_batched(ev.x.data_ptr(), ev.y.data_ptr(), ev.t.data_ptr(), ev.t.element_size(), ev.p.data_ptr(), offs.ctypes.data,
+                                   B, H, W, FILTERS[kind], float(param), int(fx), int(fy), state.data_ptr(), mask.data_ptr(), ws.data_ptr(),
+                                   ws.numel(), stream))
+    return mask[:total], state

@@ -4,7 +4,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = ["api.cu", "binning.cu", "mixed_density.cu", "order_ops.cu", "voxel.cu", "gwd.cu", "gw_kl.cu", "image_pipeline.cu", "est.cu"]
+SRC = ["api.cu", "binning.cu", "mixed_density.cu", "order_ops.cu", "voxel.cu", "gwd.cu", "gw_kl.cu", "image_pipeline.cu", "est.cu", "filters.cu"]
 OUT = os.path.join(HERE, "lib", "libevrep.so")
 
 

@@ -97,6 +97,7 @@ static int choose_tile(int H, int W, size_t bytes_per_px, Geom* g, int split = 0
   g->tile_px = 1 << shift;
   g->T = (g->HW + g->tile_px - 1) >> shift;
   g->split = split;
+  g->div_x = g->div_y = 1;
   g->Tb = g->T << split;
   g->t_magic = ((1ull << 44) + (unsigned long long)g->T - 1) / (unsigned long long)g->T;
   return EVREP_OK;
@@ -188,7 +189,7 @@ int evrep_profile_read(int kernel_id, float* total_ms, int* launches) {
 
 size_t evrep_workspace_bytes(int op, int B, int64_t total_events, int H, int W, int C) {
   (void)C;
-  if (op < EVREP_OP_MIXED_DENSITY || op > EVREP_OP_HISTOGRAM || B < 0 || total_events < 0 || H < 1 || W < 1) return 0;
+  if (op < EVREP_OP_MIXED_DENSITY || op > EVREP_OP_FILTER || B < 0 || total_events < 0 || H < 1 || W < 1) return 0;
   const int64_t hw = (int64_t)H * W;
   int64_t T = 2 * ((hw + MIN_TILE_PX - 1) / MIN_TILE_PX);  // buckets per window: at most two per tile
   if (T > MAX_TILES) T = MAX_TILES;
@@ -402,6 +403,34 @@ int evrep_gw_kl(const double* Xs, int n, int ds, const double* Xt, int m, int dt
   if (lmo != EVREP_LMO_AUCTION && lmo != EVREP_LMO_HOST) { set_error("unknown lmo %d", lmo); return EVREP_EINVAL; }
   return run_gw_kl(Xs, n, ds, Xt, m, dt, h, max_iter, tol_rel, tol_abs, lmo, gw_dist, T_out, iters, lmo_stats, workspace, workspace_bytes,
                    (cudaStream_t)stream);
+  EVREP_GUARD_END
+}
+
+int evrep_filter_batched(const uint16_t* x, const uint16_t* y, const void* t, int t_bytes, const int8_t* p, const int64_t* win_offsets, int B,
+                         int H, int W, int filter, double param, int fx, int fy, void* state, unsigned char* mask, void* workspace,
+                         size_t workspace_bytes, evrep_stream_t stream) {
+  EVREP_GUARD_BEGIN
+  Events ev;
+  int64_t total = 0, n_max = 0;
+  EVREP_TRY(check_events(x, y, t, t_bytes, p, win_offsets, B, mask, &ev, &total, &n_max));
+  if (filter < EVREP_FILTER_REFRACTORY || filter > EVREP_FILTER_RESIZE) { set_error("unknown filter %d", filter); return EVREP_EINVAL; }
+  if (B == 0) return EVREP_OK;
+  if (!state) { set_error("null state"); return EVREP_EINVAL; }
+  if (filter != EVREP_FILTER_RESIZE) fx = fy = 1;
+  if (fx < 1 || fy < 1) { set_error("fx, fy must be >= 1"); return EVREP_EINVAL; }
+  if (n_max > (int64_t)4096 * SUPER - 16) { set_error("filters: at most %lld events per window", (long long)4096 * SUPER - 16); return EVREP_EUNSUPPORTED; }
+  Geom g;
+  memset(&g, 0, sizeof(g));
+  EVREP_TRY(choose_tile(H, W, 96, &g));  // 1024-pixel tiles: the sort scratch is what fills shared memory
+  g.B = B;
+  g.total = total;
+  g.div_x = fx;
+  g.div_y = fy;
+  Workspace ws;
+  EVREP_TRY(carve_checked(workspace, workspace_bytes, B, total, g.Tb, &ws));
+  EVREP_CUDA_OK(cudaMemsetAsync(mask, 0, (size_t)total, (cudaStream_t)stream));
+  EVREP_TRY(run_binning(ev, win_offsets, g, ws, REC_IDX, 0, nullptr, (cudaStream_t)stream));
+  return launch_filter_tile(g, ws, ev, filter, param, state, mask, (cudaStream_t)stream);
   EVREP_GUARD_END
 }
 

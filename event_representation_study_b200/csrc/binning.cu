@@ -320,6 +320,8 @@ __global__ void __launch_bounds__(BIN_THREADS) k_hist(const uint16_t* __restrict
     const bool interior = idx0 >= 0 && idx0 + EPT <= n;
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
+      if (g.div_x > 1) xs[e] /= (uint32_t)g.div_x;
+      if (g.div_y > 1) ys[e] /= (uint32_t)g.div_y;
       const bool ok = (interior || (uint32_t)(idx0 + e) < (uint32_t)n) && xs[e] < Wd && ys[e] < Hd;
       uint32_t bin = (ys[e] * Wd + xs[e]) >> g.tile_shift;
       if (SPLIT) bin = (bin << 1) | (ps[e] > 0 ? 0u : 1u);
@@ -506,7 +508,9 @@ __global__ void __launch_bounds__(BIN_THREADS, EVREP_BIN_CTAS) k_bin(const uint1
       const int idx = idx0 + e;
       if (!interior && (uint32_t)idx >= (uint32_t)n) continue;
       const TT te = qt.get(e);
-      const uint32_t xe = raw_u16(qx, e), ye = raw_u16(qy, e);
+      uint32_t xe = raw_u16(qx, e), ye = raw_u16(qy, e);
+      if (g.div_x > 1) xe /= (uint32_t)g.div_x;
+      if (g.div_y > 1) ye /= (uint32_t)g.div_y;
       const int pe = raw_i8(qp, e);
       if (have_prev && te < t_prev) my_flags |= EVREP_WF_UNSORTED;
       t_prev = te;

@@ -63,6 +63,7 @@ struct SnapParams {  // time surface, one per window
 struct Geom {
   int B, H, W, HW;
   int tile_shift, tile_px, T;  // tile = contiguous range of tile_px linear pixel indices; T tiles per window
+  int div_x, div_y;            // > 1: pixels are cells of div_x x div_y sensor pixels (x / div_x, y / div_y); W, H count cells
   int split;                   // 1: every tile has two buckets, p > 0 first, then the rest (mixed-density static kernels)
   int Tb;                      // buckets per window = T << split
   int64_t total;               // total events in the batch
@@ -187,6 +188,8 @@ int launch_md_tile(const Geom& g, const Workspace& ws, const MdPlan& plan, const
 int launch_event_stack_tile(const Geom& g, const Workspace& ws, int stack_size, float* out, cudaStream_t stream);
 int launch_time_surface_tile(const Geom& g, const Workspace& ws, int S, double tau, float* out, cudaStream_t stream);
 int launch_tore_tile(const Geom& g, const Workspace& ws, int k, float* out, cudaStream_t stream);
+int launch_filter_tile(const Geom& g, const Workspace& ws, const Events& ev, int filter, double param, void* state, unsigned char* mask,
+                       cudaStream_t stream);
 
 int launch_voxel(const Events& ev, const int64_t* win_offsets_host, const Geom& g, const Workspace& ws, int flavour,
                  int n_bins, int normalize, const int64_t* t0_t1_host, float* out, cudaStream_t stream);

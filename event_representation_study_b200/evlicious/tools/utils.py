@@ -33,3 +33,46 @@ def events_to_voxel_grid_cuda(events, num_bins, normalize=True, t0_us=None, t1_u
     """-> torch float32 (num_bins, height, width) on `device`."""
     with torch.cuda.device(torch.device(device)):
         return _grid(events, num_bins, normalize, t0_us, t1_us).to(device)
+
+
+# ---- stateful per-pixel filters (reference :143-158, 184-200): same positional signatures, arrays updated in place ----
+def _run_filter(kind, x, y, t, p, state_np, param):
+    H, W = state_np.shape
+    n = len(x)
+    if n == 0:
+        return np.zeros(0, bool)
+    xs = np.asarray(x)
+    ys = np.asarray(y)
+    ev = one_window(xs, ys, np.asarray(t) if t is not None else np.arange(n, dtype=np.int64),
+                    np.asarray(p) if p is not None else np.ones(n, np.int8), H, W)
+    st = torch.from_numpy(np.ascontiguousarray(state_np)).to(ev.x.device)[None].contiguous()
+    mask, st = eb.filter_events(ev, H, W, kind, param, st)
+    state_np[...] = st[0].cpu().numpy()
+    return mask.cpu().numpy().astype(bool)
+
+
+def _refractory_period(mask, x, y, t, period, last_timestamp):
+    """utils.py:193-200: mask[i] = False where t[i] - last_timestamp[y, x] < period, else last_timestamp[y, x] = t[i]"""
+    keep = _run_filter("refractory", x, y, t, None, last_timestamp, period)
+    mask[~keep] = False
+    return mask
+
+
+def _contrast_threshold_control(activity, mask, x, y, p, factor):
+    """utils.py:184-191: activity[y, x] += p; mask[i] = True and activity reset where |activity| >= factor"""
+    keep = _run_filter("contrast", x, y, None, p, activity, factor)
+    mask[keep] = True
+    return mask
+
+
+def _filter_events_resize(x, y, p, mask, change_map, fx, fy):
+    """utils.py:143-158: per fx x fy cell, change += p / (fx fy); pass the event and subtract p when |change| >= 1"""
+    H, W = change_map.shape
+    n = len(x)
+    if n:
+        ev = one_window(np.asarray(x), np.asarray(y), np.arange(n, dtype=np.int64), np.asarray(p), H * fy, W * fx)
+        st = torch.from_numpy(np.ascontiguousarray(change_map)).to(ev.x.device)[None].contiguous()
+        keep, st = eb.filter_events(ev, H, W, "resize", 0.0, st, fx, fy)
+        change_map[...] = st[0].cpu().numpy()
+        mask[keep.cpu().numpy().astype(bool)] = True
+    return mask, change_map

@@ -31,6 +31,8 @@
  *   evrep_gw_kl                  representation_search/gromov_wasserstein.py:39-69 (OTMI.__init__ + solve, GWD-B:
  *                                POT ot.gromov.gromov_wasserstein(Ks, Kt, p, q, "kl_loss"))
  *   evrep_gemm_nt_3xtf32         the tensor product constC - hC1 T hC2^T inside that solve (POT ot/gromov tensor_product)
+ *   evrep_filter_batched         ev-licious/src/evlicious/tools/utils.py:143-158, 184-200 (_filter_events_resize,
+ *                                _contrast_threshold_control, _refractory_period) as used by tools/filters.py:57-109
  *   evrep_est_quantize_batched   ev-YOLOv6/yolov6/models/learned_repr.py:143-172 (QuantizationLayer.forward, inference only)
  *   evrep_image_pipeline_batched ev-YOLOv6/yolov6/data/gen1_2yolo.py:230-265,321-341,397 (resize_image, letterbox, CHW + reversal),
  *                                gen4/precompute_reps.py:216-251 (resize_image_process), yolov6/core/engine.py:629-635 (/ 255)
@@ -61,6 +63,7 @@ extern "C" {
 #define EVREP_OP_TORE 4
 #define EVREP_OP_VOXEL 5
 #define EVREP_OP_HISTOGRAM 6
+#define EVREP_OP_FILTER 7
 
 /* MixedDensityEventStack vocabulary (operations.py:39-89; mixed_density_event_stack.py:48-109) */
 #define EVREP_FUNC_TIMESTAMP 0
@@ -226,6 +229,24 @@ int evrep_gemm_nt_3xtf32(const float* A, const float* B, float* C, int M, int N,
 #define EVREP_INTERP_LINEAR_TORCH 3 /* torch interpolate(bilinear, align_corners=False) arithmetic + letterbox_image_batch placement (learned_repr.py:94-141) */
 int evrep_image_pipeline_batched(const float* rep, int B, int H, int W, int C, int img_size, int mode, int interp, float scale_in,
                                  float scale_out, float pad_value, int reverse_channels, float* out, evrep_stream_t stream);
+
+/* ev-licious' per-pixel stateful filters over B event windows (streams): mask[i] = 1 if event i passes, 0 otherwise
+ * (DEVICE uint8, one per event, fully overwritten; events with x or y outside the sensor get 0 and raise
+ * EVREP_WF_OUT_OF_RANGE).  `state` is DEVICE memory, (B, H, W) read AND written, so that a stream can be fed in pieces:
+ *   EVREP_FILTER_REFRACTORY  float64 last kept timestamp per pixel (start at -inf); param = period.  Keeps an event iff
+ *                            t - state >= period, then state = t (utils.py:193-200).
+ *   EVREP_FILTER_CONTRAST    int32 activity per pixel (start at 0); param = factor.  activity += p; keeps the event and
+ *                            resets the pixel when |activity| >= factor (utils.py:184-191).  p must be -1 / +1.
+ *   EVREP_FILTER_RESIZE      float32 change map per CELL of fx x fy pixels; here H, W are the cell grid (height, width of
+ *                            the change map) and x / fx, y / fy index it.  change += p / (fx fy); keeps the event when
+ *                            |change| >= 1 and then subtracts p (utils.py:143-158).  fx, fy >= 1 (ignored by the others).
+ * Events of a window must be in stream order.  Windows of at most 33 M events. */
+#define EVREP_FILTER_REFRACTORY 0
+#define EVREP_FILTER_CONTRAST 1
+#define EVREP_FILTER_RESIZE 2
+int evrep_filter_batched(const uint16_t* x, const uint16_t* y, const void* t, int t_bytes, const int8_t* p, const int64_t* win_offsets,
+                         int B, int H, int W, int filter, double param, int fx, int fy, void* state, unsigned char* mask,
+                         void* workspace, size_t workspace_bytes, evrep_stream_t stream);
 
 /* EST, the reference's learned quantisation layer, forward only (ev-YOLOv6/yolov6/models/learned_repr.py:143-172):
  * out[b, y, x, p * C + i] = sum over the events of window b at (x, y, p) of tn * f(tn - i / (C - 1)), tn = t / max(t of the

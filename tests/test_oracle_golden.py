@@ -193,3 +193,21 @@ def test_est_oracle_matches_reference_fixtures(name, path):
     with torch.no_grad():
         vox, lb = oest.est_forward(torch.tensor(g["events"]), ws, bs, tuple(int(v) for v in g["dim"]), int(g["image_size"]))
     assert np.allclose(lb.numpy(), g["out"], rtol=1e-6, atol=1e-6) and np.allclose(vox.numpy(), g["vox"], rtol=1e-6, atol=1e-6)
+
+
+# ---- ev-licious stateful filters: oracle vs fixtures made with the reference's numba kernels ----
+@pytest.mark.parametrize("name,path", golden("filter_*"), ids=[n for n, _ in golden("filter_*")])
+def test_filter_oracle_matches_reference_fixtures(name, path):
+    from oracle import filters as ofil
+    g = load(path)
+    H, W, n = int(g["H"]), int(g["W"]), len(g["x"])
+    x, y, t, p = g["x"], g["y"], g["t"], g["p"]
+    last = np.full((H, W), -np.inf)
+    assert np.array_equal(ofil.refractory_period(np.ones(n, bool), x, y, t, float(g["refr_period"]), last), g["refr_mask"])
+    assert np.array_equal(last, g["refr_state1"])
+    act = np.zeros((H, W), np.int32)
+    assert np.array_equal(ofil.contrast_threshold_control(act, np.zeros(n, bool), x, y, p, float(g["ctc_factor"])), g["ctc_mask"])
+    assert np.array_equal(act, g["ctc_state1"])
+    fx, fy = int(g["fx"]), int(g["fy"])
+    m, cm = ofil.filter_events_resize(x, y, p, np.zeros(n, bool), np.zeros((H // fy, W // fx), np.float32), fx, fy)
+    assert np.array_equal(m, g["rsz_mask"]) and np.array_equal(cm, g["rsz_state1"])
