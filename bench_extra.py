@@ -63,7 +63,7 @@ def rep_line(name, ev_per_step, sec, alg_bytes, cpu_ev_per_s, cpu_note, extra=No
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--only", default="config1,config2,config3,gwd,gwdb,img,est")
+    ap.add_argument("--only", default="config1,config2,config3,gwd,gwdb,img,est,filters")
     a = ap.parse_args()
     import torch
     import event_representation_study_b200.batched as eb
@@ -180,6 +180,33 @@ def main():
                           "cpu_baseline": {"value": N / c / 1e9, "unit": "Gevents/s", "cores": "torch CPU threads", "kind": "port",
                                            "sample": f"{n} windows, oracle/est.py (the reference's forward restated on CPU tensors: MLP evaluated {C} times per event)"},
                           "speedup_vs_cpu_port": (B * N / sec_f) / (N / c)}), flush=True)
+
+    if "filters" in only:  # ev-licious' stateful per-pixel filters, 8 streams x 1 M events at 1 Mpx
+        from oracle import filters as ofil
+        H, W, B, N = 720, 1280, 8, 1_000_000
+        ev = batch(B, N, H, W, 9000)
+        try:
+            import numba
+            jit = {k: numba.njit(getattr(ofil, k)) for k in ("refractory_period", "contrast_threshold_control", "filter_events_resize")}
+            how = "the oracle's loops compiled with numba (what the reference does)"
+        except Exception:
+            jit = {k: getattr(ofil, k) for k in ("refractory_period", "contrast_threshold_control", "filter_events_resize")}
+            how = "the oracle's plain-Python loops (numba unavailable)"
+        w = poisson_window(9000, N, H, W)
+        xs, ys, ts, ps = w["x"].astype(np.int64), w["y"].astype(np.int64), w["t"].astype(np.int64), w["p"].astype(np.int8)
+        for kind, param, shape, kw, cpu_fn in [
+            ("refractory", 1000.0, (H, W), {}, lambda i: jit["refractory_period"](np.ones(N, np.bool_), xs, ys, ts, 1000.0, np.full((H, W), -np.inf))),
+            ("contrast", 2.0, (H, W), {}, lambda i: jit["contrast_threshold_control"](np.zeros((H, W), np.int32), np.zeros(N, np.bool_), xs, ys, ps, 2.0)),
+            ("resize", 0.0, (H // 2, W // 2), {"fx": 2, "fy": 2}, lambda i: jit["filter_events_resize"](xs, ys, ps, np.zeros(N, np.bool_), np.zeros((H // 2, W // 2), np.float32), 2, 2)),
+        ]:
+            st = eb.filter_state(kind, B, shape[0], shape[1])
+            sec = timed(lambda: eb.filter_events(ev, shape[0], shape[1], kind, param, st, **kw), max(3, a.steps // 2))
+            cpu_fn(0)  # numba compile
+            c, n = cpu_time(cpu_fn, 4.0, 10)
+            print(json.dumps({"workload": f"ev-licious {kind} filter, {B} streams x {N} events, 1280x720", "value": B * N / sec / 1e9, "unit": "Gevents/s",
+                              "ms_per_step": sec * 1e3, "cpu_baseline": {"value": N / c / 1e9, "unit": "Gevents/s", "cores": 1, "kind": "port",
+                                                                        "sample": f"{n} streams of {N} events, {how}"},
+                              "speedup_vs_cpu_port": (B * N / sec) / (N / c)}), flush=True)
 
     if "gwdb" in only:  # config 5, GWD-B: conditional-gradient GW with the KL loss, LMO = auction on the GPU.  An exact CPU
         # assignment solve costs ~1 s per iteration at n = 1000 on these structured costs (scipy and our host solver alike),

@@ -4,8 +4,13 @@ stream in two pieces, like two `insert` calls of a filter object (tools/filters.
 each piece."""
 import os
 import sys
+import tempfile
 
 import numpy as np
+
+# _filter_events_resize is jitted with cache=True; its module is loaded by path under a synthetic name, and a cache entry
+# written by one run cannot be unpickled by the next ("No module named '<dynamic>'"): give every run a fresh cache
+os.environ["NUMBA_CACHE_DIR"] = tempfile.mkdtemp(prefix="numba_cache_")
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
