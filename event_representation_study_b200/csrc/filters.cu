@@ -21,6 +21,7 @@ namespace evrep {
 
 constexpr int FT_THREADS = 512;
 constexpr int FT_ITEMS = 16;
+constexpr int FT_ITEMS_SMALL = 4;
 constexpr int FT_CAP = FT_THREADS * FT_ITEMS;  // 8192 records per segment = the longest possible run of one super-chunk
 constexpr int FT_MAX_SC = 4096;                // super-chunks per window whose run table fits shared memory (33 M events)
 static_assert(FT_CAP >= SUPER, "a segment must hold a whole super-chunk run");
@@ -43,11 +44,14 @@ __global__ void __launch_bounds__(FT_THREADS) k_filter_tile(const uint2* __restr
                                                             unsigned char* __restrict__ mask) {
   using ST = typename FilterState<FILTER>::type;
   using Sort = cub::BlockRadixSort<unsigned long long, FT_THREADS, FT_ITEMS>;
+  using SortSmall = cub::BlockRadixSort<unsigned long long, FT_THREADS, FT_ITEMS_SMALL>;
+  static_assert(sizeof(typename SortSmall::TempStorage) <= sizeof(typename Sort::TempStorage), "the small sort reuses the large one's scratch");
   extern __shared__ __align__(16) unsigned char ft_raw[];
   // the sort's scratch and the sorted keys share one region: the keys are written back after the sort is done with it
   constexpr size_t SORT_BYTES = sizeof(typename Sort::TempStorage) > sizeof(unsigned long long) * FT_CAP ? sizeof(typename Sort::TempStorage)
                                                                                                         : sizeof(unsigned long long) * FT_CAP;
   typename Sort::TempStorage& sort_tmp = *reinterpret_cast<typename Sort::TempStorage*>(ft_raw);
+  typename SortSmall::TempStorage& sort_small = *reinterpret_cast<typename SortSmall::TempStorage*>(ft_raw);
   unsigned long long* sorted = reinterpret_cast<unsigned long long*>(ft_raw);                    // FT_CAP keys
   uint32_t* runs = reinterpret_cast<uint32_t*>(ft_raw + ((SORT_BYTES + 15) & ~(size_t)15));      // FT_MAX_SC + 1 run starts
   int* first = reinterpret_cast<int*>(runs + FT_MAX_SC + 1);                                    // TP: first sorted slot of a pixel
@@ -82,20 +86,31 @@ __global__ void __launch_bounds__(FT_THREADS) k_filter_tile(const uint2* __restr
     __syncthreads();
     const int s_end = s_seg_end;
     const uint32_t a = runs[s_begin], n = runs[s_end] - a;
-    unsigned long long keys[FT_ITEMS];
+    auto load_key = [&](uint32_t i) -> unsigned long long {
+      if (i >= n) return ~0ull;  // padding and null records sort to the end
+      const uint2 r = __ldg(rec + a + i);
+      if (rec_is_null(r.y)) return ~0ull;
+      return ((unsigned long long)(r.y & 0xffffu) << 33) | ((unsigned long long)r.x << 2) | ((r.y >> 24) & 3u);
+    };
+    // sort by (pixel, stream index); the index is unique, so the polarity bits need no pass.  Most buckets hold about a
+    // thousand records: a quarter-size sort (4 keys per thread) covers them, the full one is for hot tiles.
+    if (n <= (uint32_t)(FT_THREADS * FT_ITEMS_SMALL)) {
+      unsigned long long keys[FT_ITEMS_SMALL];
 #pragma unroll
-    for (int k = 0; k < FT_ITEMS; ++k) {
-      const uint32_t i = (uint32_t)(tid * FT_ITEMS + k);
-      keys[k] = ~0ull;  // padding and null records sort to the end
-      if (i < n) {
-        const uint2 r = __ldg(rec + a + i);
-        if (!rec_is_null(r.y)) keys[k] = ((unsigned long long)(r.y & 0xffffu) << 33) | ((unsigned long long)r.x << 2) | ((r.y >> 24) & 3u);
-      }
+      for (int k = 0; k < FT_ITEMS_SMALL; ++k) keys[k] = load_key((uint32_t)(tid * FT_ITEMS_SMALL + k));
+      SortSmall(sort_small).Sort(keys, 2, 49);
+      __syncthreads();  // the scratch is about to be overwritten with the sorted keys
+#pragma unroll
+      for (int k = 0; k < FT_ITEMS_SMALL; ++k) sorted[tid * FT_ITEMS_SMALL + k] = keys[k];
+    } else {
+      unsigned long long keys[FT_ITEMS];
+#pragma unroll
+      for (int k = 0; k < FT_ITEMS; ++k) keys[k] = load_key((uint32_t)(tid * FT_ITEMS + k));
+      Sort(sort_tmp).Sort(keys, 2, 49);
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < FT_ITEMS; ++k) sorted[tid * FT_ITEMS + k] = keys[k];
     }
-    Sort(sort_tmp).Sort(keys, 2, 49);  // (pixel, stream index); the index is unique, so the polarity bits need no pass
-    __syncthreads();                   // the scratch is about to be overwritten with the sorted keys
-#pragma unroll
-    for (int k = 0; k < FT_ITEMS; ++k) sorted[tid * FT_ITEMS + k] = keys[k];
     __syncthreads();
     for (uint32_t j = tid; j < n; j += FT_THREADS) {
       const unsigned long long key = sorted[j];
