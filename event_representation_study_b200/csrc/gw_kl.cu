@@ -295,11 +295,7 @@ int launch_gemm_nt_3xtf32(const float* A, const float* B, float* C, int M, int N
     set_error("gemm: empty problem");
     return EVREP_EINVAL;
   }
-  static bool configured = false;
-  if (!configured) {
-    EVREP_CUDA_OK(cudaFuncSetAttribute(k_gemm_nt_3xtf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GB_SMEM));
-    configured = true;
-  }
+  EVREP_CUDA_OK(cudaFuncSetAttribute(k_gemm_nt_3xtf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GB_SMEM));  // per device: cheap, not cached
   dim3 grid((unsigned)((N + GB_N - 1) / GB_N), (unsigned)((M + GB_M - 1) / GB_M));
   k_gemm_nt_3xtf32<<<grid, GB_THREADS, GB_SMEM, stream>>>(A, B, C, M, N, K, alpha, rv, cv, (al16(A) && K % 4 == 0) ? 1 : 0,
                                                           (al16(B) && K % 4 == 0) ? 1 : 0, (al16(C) && N % 4 == 0) ? 1 : 0);
