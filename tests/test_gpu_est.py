@@ -79,3 +79,19 @@ def test_est_argument_checks(M):
         est.quantize(ev, 8, 8, 1, tab)  # C - 1 == 0: the reference divides by zero
     out = est.quantize(ev, 8, 8, 2, tab)  # f == 0 everywhere
     assert float(out.abs().max()) == 0.0
+
+
+def test_est_batch_with_an_empty_window(M):
+    """an empty window gives an all-zero grid (the reference would fail on max() of an empty tensor)"""
+    import torch
+    eb, est = M
+    wins = [{"x": np.array([3, 3], np.uint16), "y": np.array([1, 1], np.uint16), "t": np.array([10, 20], np.int64), "p": np.array([1, 0], np.int8)},
+            {"x": np.zeros(0, np.uint16), "y": np.zeros(0, np.uint16), "t": np.zeros(0, np.int64), "p": np.zeros(0, np.int8)}]
+    ev = eb.pack_events(wins, "cuda")
+    tab = (torch.zeros(0, dtype=torch.float64, device="cuda"), torch.tensor([0.0], dtype=torch.float64, device="cuda"),
+           torch.tensor([2.0], dtype=torch.float64, device="cuda"))  # f(u) = 2
+    out = est.quantize(ev, 4, 6, 2, tab)
+    assert float(out[1].abs().max()) == 0.0
+    # window 0: tn = 0.5 and 1.0; every bin adds tn * 2 at (y = 1, x = 3), polarity 1 -> channels 2, 3; polarity 0 -> channels 0, 1
+    assert out[0, 1, 3].cpu().numpy().tolist() == [2.0, 2.0, 1.0, 1.0]
+    assert float(out[0].sum()) == 6.0

@@ -86,3 +86,21 @@ def test_evlicious_filter_function_mirrors(E):
     got, cm2 = U._filter_events_resize(x, y, p, np.zeros(5000, bool), cm, 2, 3)
     want, _ = ofil.filter_events_resize(x, y, p, np.zeros(5000, bool), cm_w, 2, 3)
     assert np.array_equal(got, want) and np.array_equal(cm, cm_w) and cm2 is cm
+
+
+def test_filters_empty_windows_and_out_of_range_events(E):
+    """a batch with empty streams; events outside the sensor get mask 0, raise the flag and leave the state alone"""
+    import torch
+    H, W = 8, 8
+    wins = [{"x": np.zeros(0, np.uint16), "y": np.zeros(0, np.uint16), "t": np.zeros(0, np.int64), "p": np.zeros(0, np.int8)},
+            {"x": np.array([1, 1, 200, 1], np.uint16), "y": np.array([2, 2, 2, 2], np.uint16), "t": np.array([0, 5, 6, 20], np.int64),
+             "p": np.array([1, 1, 1, -1], np.int8)},
+            {"x": np.zeros(0, np.uint16), "y": np.zeros(0, np.uint16), "t": np.zeros(0, np.int64), "p": np.zeros(0, np.int8)}]
+    ev = E.pack_events(wins, "cuda")
+    m, st = E.filter_events(ev, H, W, "refractory", 10.0)
+    assert m.cpu().numpy().tolist() == [1, 0, 0, 1]
+    assert int(E.window_flags(ev)[1]) & 0x100
+    assert torch.isinf(st[0]).all() and torch.isinf(st[2]).all() and float(st[1, 2, 1]) == 20.0
+    none = E.pack_events([wins[0]], "cuda")
+    m0, _ = E.filter_events(none, H, W, "contrast", 2.0)
+    assert m0.numel() == 0

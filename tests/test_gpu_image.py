@@ -78,3 +78,11 @@ def test_image_pipeline_rejects_what_it_does_not_mirror(E):
     assert e.value.code == EUNSUPPORTED
     with pytest.raises(ValueError):
         E.detector_input(torch.zeros((1, 8, 8, 12)), 16)
+
+
+def test_image_pipeline_empty_batch_and_single_pixel(E):
+    import torch
+    out = E.detector_input(torch.zeros((0, 8, 8, 12), device="cuda"), 16)
+    assert tuple(out.shape) == (0, 12, 16, 16)
+    one = E.detector_input(torch.full((1, 1, 1, 12), 0.5, device="cuda"), 4, scale_in=1.0, scale_out=1.0).cpu().numpy()
+    assert np.allclose(one, 0.5)  # a 1 x 1 image enlarged to 4 x 4: every tap is the single pixel, no border
