@@ -259,7 +259,7 @@ def gwd_kernel_l1(Xs_list, Xt_list, h=0.7, device="cuda"):
     return out
 
 
-def gemm_nt_3xtf32(A, B, alpha=1.0, row_vec=None, col_vec=None, out=None):
+def gemm_nt_3xtf32(A, B, alpha=1.0, row_vec=None, col_vec=None, out=None, packed=True):
     """alpha * A @ B.T + row_vec[:, None] + col_vec[None, :] on the tcgen05 tensor cores with fp32-class accuracy
     (3 x TF32 split).  A (M, K), B (N, K): float32 CUDA tensors.  This is the contraction of GWD-B's tensor product."""
     if not (A.is_cuda and B.is_cuda):
@@ -275,8 +275,10 @@ def gemm_nt_3xtf32(A, B, alpha=1.0, row_vec=None, col_vec=None, out=None):
     rv = row_vec.contiguous().float() if row_vec is not None else None
     cv = col_vec.contiguous().float() if col_vec is not None else None
     stream = torch.cuda.current_stream(A.device).cuda_stream
+    ws = _workspace(A.device, stream, lib.evrep_gemm_workspace_bytes(M, N, K)) if packed else None  # packed: TMA-fed kernel
     check(lib.evrep_gemm_nt_3xtf32(A.data_ptr(), B.data_ptr(), out.data_ptr(), M, N, K, float(alpha),
-                                   rv.data_ptr() if rv is not None else None, cv.data_ptr() if cv is not None else None, stream))
+                                   rv.data_ptr() if rv is not None else None, cv.data_ptr() if cv is not None else None,
+                                   ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0, stream))
     return out
 
 

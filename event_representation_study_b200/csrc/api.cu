@@ -57,8 +57,9 @@ size_t gw_kl_workspace_bytes(int n, int m);
 int run_gw_kl(const double* Xs, int n, int ds, const double* Xt, int m, int dt, double h, int max_iter, double tol_rel, double tol_abs,
               int lmo, double* gw_dist_host, float* T_out, int* iters_host, int* lmo_stats_host, void* workspace, size_t workspace_bytes,
               cudaStream_t stream);
-int launch_gemm_nt_3xtf32(const float* A, const float* B, float* C, int M, int N, int K, float alpha, const float* rv, const float* cv,
-                          cudaStream_t stream);
+size_t gemm_workspace_bytes(int M, int N, int K);
+int launch_gemm_nt_3xtf32_ws(const float* A, const float* B, float* C, int M, int N, int K, float alpha, const float* rv, const float* cv,
+                             void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 size_t est_workspace_bytes(int B);
 int launch_est(const uint16_t* x, const uint16_t* y, const float* t, const int8_t* p, const int64_t* win_offsets_host, int B, int H, int W, int C,
@@ -458,11 +459,13 @@ int evrep_assignment_auction(const float* cost, int n, double eps_rel, int* sigm
   EVREP_GUARD_END
 }
 
+size_t evrep_gemm_workspace_bytes(int M, int N, int K) { return gemm_workspace_bytes(M, N, K); }
+
 int evrep_gemm_nt_3xtf32(const float* A, const float* B, float* C, int M, int N, int K, float alpha, const float* rv, const float* cv,
-                         evrep_stream_t stream) {
+                         void* workspace, size_t workspace_bytes, evrep_stream_t stream) {
   EVREP_GUARD_BEGIN
   if (!A || !B || !C) { set_error("null matrix"); return EVREP_EINVAL; }
-  return launch_gemm_nt_3xtf32(A, B, C, M, N, K, alpha, rv, cv, (cudaStream_t)stream);
+  return launch_gemm_nt_3xtf32_ws(A, B, C, M, N, K, alpha, rv, cv, workspace, workspace_bytes, (cudaStream_t)stream);
   EVREP_GUARD_END
 }
 

@@ -292,7 +292,7 @@ __global__ void k_snap_init(const TT* __restrict__ t, const WinParams* __restric
 // pass 1: bucket counts of one super-chunk -> one row of cc.  Counts every event with a valid pixel.
 // HBM: reads x, y (+ p when the buckets are split by polarity).
 // ---------------------------------------------------------------------------------------------
-template <bool SPLIT>
+template <bool SPLIT, bool DIV>
 __global__ void __launch_bounds__(BIN_THREADS) k_hist(const uint16_t* __restrict__ x, const uint16_t* __restrict__ y,
                                                       const int8_t* __restrict__ p, const WinParams* __restrict__ wp,
                                                       const int32_t* __restrict__ sc_prefix, const int32_t* __restrict__ sc_win,
@@ -320,8 +320,10 @@ __global__ void __launch_bounds__(BIN_THREADS) k_hist(const uint16_t* __restrict
     const bool interior = idx0 >= 0 && idx0 + EPT <= n;
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
-      if (g.div_x > 1) xs[e] /= (uint32_t)g.div_x;
-      if (g.div_y > 1) ys[e] /= (uint32_t)g.div_y;
+      if (DIV) {  // pixels are cells of div_x x div_y sensor pixels (the resize filter)
+        xs[e] /= (uint32_t)g.div_x;
+        ys[e] /= (uint32_t)g.div_y;
+      }
       const bool ok = (interior || (uint32_t)(idx0 + e) < (uint32_t)n) && xs[e] < Wd && ys[e] < Hd;
       uint32_t bin = (ys[e] * Wd + xs[e]) >> g.tile_shift;
       if (SPLIT) bin = (bin << 1) | (ps[e] > 0 ? 0u : 1u);
@@ -413,7 +415,7 @@ __global__ void __launch_bounds__(BIN_THREADS) k_scan(const uint32_t* __restrict
 // ---------------------------------------------------------------------------------------------
 // pass 3: scatter the events into their buckets as 8-byte records.  HBM: reads 9 B/event, writes 8 B/event.
 // ---------------------------------------------------------------------------------------------
-template <typename TT, int MODE, bool SPLIT>
+template <typename TT, int MODE, bool SPLIT, bool DIV>
 #ifndef EVREP_BIN_CTAS
 #define EVREP_BIN_CTAS 2
 #endif
@@ -509,8 +511,10 @@ __global__ void __launch_bounds__(BIN_THREADS, EVREP_BIN_CTAS) k_bin(const uint1
       if (!interior && (uint32_t)idx >= (uint32_t)n) continue;
       const TT te = qt.get(e);
       uint32_t xe = raw_u16(qx, e), ye = raw_u16(qy, e);
-      if (g.div_x > 1) xe /= (uint32_t)g.div_x;
-      if (g.div_y > 1) ye /= (uint32_t)g.div_y;
+      if (DIV) {
+        xe /= (uint32_t)g.div_x;
+        ye /= (uint32_t)g.div_y;
+      }
       const int pe = raw_i8(qp, e);
       if (have_prev && te < t_prev) my_flags |= EVREP_WF_UNSORTED;
       t_prev = te;
@@ -580,11 +584,11 @@ __global__ void __launch_bounds__(BIN_THREADS, EVREP_BIN_CTAS) k_bin(const uint1
   for (uint32_t i = tid; i < total; i += BIN_THREADS) dst[sdest[i]] = stage[i];
 }
 
-template <typename TT, int MODE, bool SPLIT>
+template <typename TT, int MODE, bool SPLIT, bool DIV = false>
 static int launch_bin(const Events& ev, const Geom& g, const Workspace& ws, int n_sc, bool vec, cudaStream_t stream) {
   const size_t smem = (size_t)SUPER * (sizeof(uint2) + sizeof(uint32_t)) + 2 * sizeof(uint32_t) * (size_t)g.Tb;
-  EVREP_CUDA_OK(cudaFuncSetAttribute(k_bin<TT, MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_bin<TT, MODE, SPLIT><<<n_sc, BIN_THREADS, smem, stream>>>(ev.x, ev.y, (const TT*)ev.t, ev.p, ws.wp, ws.snap, ws.sc_prefix, ws.sc_win, g, vec,
+  EVREP_CUDA_OK(cudaFuncSetAttribute(k_bin<TT, MODE, SPLIT, DIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_bin<TT, MODE, SPLIT, DIV><<<n_sc, BIN_THREADS, smem, stream>>>(ev.x, ev.y, (const TT*)ev.t, ev.p, ws.wp, ws.snap, ws.sc_prefix, ws.sc_win, g, vec,
                                                               ws.base, ws.cc, ws.cp, ws.records);
   EVREP_CUDA_OK(cudaGetLastError());
   return EVREP_OK;
@@ -594,7 +598,9 @@ static int launch_bin_mode(int mode, const Events& ev, const Geom& g, const Work
   switch (mode) {
     case REC_T_WMASK:
       return g.split ? launch_bin<TT, REC_T_WMASK, true>(ev, g, ws, n_sc, vec, stream) : launch_bin<TT, REC_T_WMASK, false>(ev, g, ws, n_sc, vec, stream);
-    case REC_IDX: return launch_bin<TT, REC_IDX, false>(ev, g, ws, n_sc, vec, stream);
+    case REC_IDX:
+      return (g.div_x > 1 || g.div_y > 1) ? launch_bin<TT, REC_IDX, false, true>(ev, g, ws, n_sc, vec, stream)
+                                          : launch_bin<TT, REC_IDX, false>(ev, g, ws, n_sc, vec, stream);
     case REC_T_SNAP: return launch_bin<TT, REC_T_SNAP, false>(ev, g, ws, n_sc, vec, stream);
     case REC_T_TORE: return launch_bin<TT, REC_T_TORE, false>(ev, g, ws, n_sc, vec, stream);
     default: return launch_bin<TT, REC_T_ONLY, false>(ev, g, ws, n_sc, vec, stream);
@@ -688,9 +694,11 @@ int run_binning(const Events& ev, const int64_t* win_offsets_host, const Geom& g
   if (n_sc > 0) {
     prof_begin(EVREP_K_COUNT, stream);
     if (g.split)
-      k_hist<true><<<n_sc, BIN_THREADS, sizeof(uint32_t) * (size_t)g.Tb, stream>>>(ev.x, ev.y, ev.p, ws.wp, ws.sc_prefix, ws.sc_win, g, vec, ws.cc);
+      k_hist<true, false><<<n_sc, BIN_THREADS, sizeof(uint32_t) * (size_t)g.Tb, stream>>>(ev.x, ev.y, ev.p, ws.wp, ws.sc_prefix, ws.sc_win, g, vec, ws.cc);
+    else if (g.div_x > 1 || g.div_y > 1)
+      k_hist<false, true><<<n_sc, BIN_THREADS, sizeof(uint32_t) * (size_t)g.Tb, stream>>>(ev.x, ev.y, ev.p, ws.wp, ws.sc_prefix, ws.sc_win, g, vec, ws.cc);
     else
-      k_hist<false><<<n_sc, BIN_THREADS, sizeof(uint32_t) * (size_t)g.Tb, stream>>>(ev.x, ev.y, ev.p, ws.wp, ws.sc_prefix, ws.sc_win, g, vec, ws.cc);
+      k_hist<false, false><<<n_sc, BIN_THREADS, sizeof(uint32_t) * (size_t)g.Tb, stream>>>(ev.x, ev.y, ev.p, ws.wp, ws.sc_prefix, ws.sc_win, g, vec, ws.cc);
     prof_end(EVREP_K_COUNT, stream);
     EVREP_CUDA_OK(cudaGetLastError());
   }

@@ -156,6 +156,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 // relative at K = 300), and the GW loss is a 30:1 cancellation of this product against constC.  Each k-block of 32
 // therefore gets a FRESH accumulator (two TMEM buffers, ping-pong) which four warps add into registers with
 // round-to-nearest while the tensor core works on the next k-block: fp32 blocked summation, error ~ sqrt(K / 32) ulp.
+//
+// PACKED = true: A and B are not matrices but the "operand images" written by k_gemm_pack - for every (128-row tile,
+// 32-column k-block) the two swizzled TF32 tiles (hi, lo) exactly as they must sit in shared memory, 32 KB contiguous.  One
+// thread then feeds the pipeline with two cp.async.bulk (TMA, SASS UBLKCP) per k-block that complete on the stage's
+// mbarrier; no thread touches the operands.  This is the path evrep_gw_kl uses: hC1 is packed once per solve and reused
+// by every conditional-gradient step, the gathered hC2 columns are packed by the gather itself.
+template <bool PACKED>
 __global__ void __launch_bounds__(GB_THREADS, 1) k_gemm_nt_3xtf32(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
                                                                   int M, int N, int K, float alpha, const float* __restrict__ rv,
                                                                   const float* __restrict__ cv, int vecA, int vecB, int vecC) {
@@ -174,7 +181,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) k_gemm_nt_3xtf32(const float* _
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < GB_STAGES; ++s) {
-      mbar_init(full_bar(s), 128);  // every producer thread arrives
+      mbar_init(full_bar(s), PACKED ? 1 : 128);  // every producer thread arrives (PACKED: the one that issues the bulk copies)
       mbar_init(empty_bar(s), 1);   // one tcgen05.commit
     }
     for (int q = 0; q < 2; ++q) {
@@ -192,7 +199,25 @@ __global__ void __launch_bounds__(GB_THREADS, 1) k_gemm_nt_3xtf32(const float* _
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
 
-  if (warp < 4) {
+  if (PACKED && warp < 4) {
+    // ---- producer: one thread, two bulk copies per k-block ----
+    if (threadIdx.x == 0) {
+      const unsigned char* ga = reinterpret_cast<const unsigned char*>(A) + (size_t)blockIdx.y * nkb * (2 * GB_TILE_BYTES);
+      const unsigned char* gbp = reinterpret_cast<const unsigned char*>(B) + (size_t)blockIdx.x * nkb * (2 * GB_TILE_BYTES);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % GB_STAGES;
+        mbar_wait(empty_bar(s), ((uint32_t)(kb / GB_STAGES) & 1u) ^ 1u);
+        const uint32_t st = smem_u32(tiles + (size_t)s * GB_STAGE_BYTES);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_bar(s)), "r"((uint32_t)GB_STAGE_BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(st),
+                     "l"(ga + (size_t)kb * (2 * GB_TILE_BYTES)), "r"((uint32_t)(2 * GB_TILE_BYTES)), "r"(full_bar(s))
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(st + 2 * GB_TILE_BYTES),
+                     "l"(gbp + (size_t)kb * (2 * GB_TILE_BYTES)), "r"((uint32_t)(2 * GB_TILE_BYTES)), "r"(full_bar(s))
+                     : "memory");
+      }
+    }
+  } else if (warp < 4) {
     // ---- producers ----
     const int t = threadIdx.x;
     float4 va[GB_M / 16], vb[GB_N / 16];
@@ -288,6 +313,87 @@ __global__ void __launch_bounds__(GB_THREADS, 1) k_gemm_nt_3xtf32(const float* _
 }
 
 static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+int launch_gemm_nt_3xtf32(const float* A, const float* B, float* C, int M, int N, int K, float alpha, const float* rv, const float* cv,
+                          cudaStream_t stream);
+
+// Operand image of X (rows x K, row major): tile (rt, kb) at byte (rt * nkb + kb) * 32 KB = [hi tile | lo tile], each 128
+// rows x 128 bytes with the 16-byte chunks of row r at position chunk ^ (r mod 8).  With `sigma` the columns are gathered
+// first: element (j, k) is X[j, sigma[k]] (the GW step's hC2[:, sigma]).  Rows / columns past the matrix are zero.
+__global__ void __launch_bounds__(256) k_gemm_pack(const float* __restrict__ X, int rows, int K, int ldx, const int* __restrict__ sigma,
+                                                   unsigned char* __restrict__ img) {
+  const int nkb = (K + GB_K - 1) / GB_K;
+  const int n_rt = (rows + GB_M - 1) / GB_M;
+  const size_t total = (size_t)n_rt * nkb * GB_M * 8;  // one thread per (tile, row, 16-byte chunk)
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int c4 = (int)(e & 7);
+    const int r = (int)((e >> 3) & (GB_M - 1));
+    const size_t tile = e >> 10;  // GB_M * 8 = 1024 chunks per tile
+    const int kb = (int)(tile % nkb), rt = (int)(tile / nkb);
+    const int gr = rt * GB_M + r, gk = kb * GB_K + 4 * c4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (gr < rows) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (gk + q < K) v[q] = __ldg(X + (size_t)gr * ldx + (sigma ? sigma[gk + q] : gk + q));
+    }
+    uint4 h, l;
+    h.x = to_tf32(v[0]); l.x = to_tf32(v[0] - __uint_as_float(h.x));
+    h.y = to_tf32(v[1]); l.y = to_tf32(v[1] - __uint_as_float(h.y));
+    h.z = to_tf32(v[2]); l.z = to_tf32(v[2] - __uint_as_float(h.z));
+    h.w = to_tf32(v[3]); l.w = to_tf32(v[3] - __uint_as_float(h.w));
+    unsigned char* t0 = img + tile * (size_t)(2 * GB_TILE_BYTES);
+    const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c4 ^ (r & 7)) << 4);
+    *reinterpret_cast<uint4*>(t0 + off) = h;
+    *reinterpret_cast<uint4*>(t0 + GB_TILE_BYTES + off) = l;
+  }
+}
+
+size_t gemm_image_bytes(int rows, int K) { return (size_t)((rows + GB_M - 1) / GB_M) * (size_t)((K + GB_K - 1) / GB_K) * (size_t)(2 * GB_TILE_BYTES); }
+
+int launch_gemm_pack(const float* X, int rows, int K, int ldx, const int* sigma, void* img, cudaStream_t stream) {
+  const size_t total = gemm_image_bytes(rows, K) / 32;  // 16-byte chunk pairs
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)148 * 16);
+  k_gemm_pack<<<blocks, 256, 0, stream>>>(X, rows, K, ldx, sigma, (unsigned char*)img);
+  EVREP_CUDA_OK(cudaGetLastError());
+  return EVREP_OK;
+}
+
+// C = alpha * A * B^T + rv + cv from two operand images (k_gemm_pack)
+int launch_gemm_packed(const void* imgA, const void* imgB, float* C, int M, int N, int K, float alpha, const float* rv, const float* cv,
+                       cudaStream_t stream) {
+  EVREP_CUDA_OK(cudaFuncSetAttribute(k_gemm_nt_3xtf32<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GB_SMEM));
+  dim3 grid((unsigned)((N + GB_N - 1) / GB_N), (unsigned)((M + GB_M - 1) / GB_M));
+  k_gemm_nt_3xtf32<true><<<grid, GB_THREADS, GB_SMEM, stream>>>((const float*)imgA, (const float*)imgB, C, M, N, K, alpha, rv, cv, 0, 0,
+                                                                (al16(C) && N % 4 == 0) ? 1 : 0);
+  EVREP_CUDA_OK(cudaGetLastError());
+  return EVREP_OK;
+}
+
+size_t gemm_workspace_bytes(int M, int N, int K) {
+  if (M < 1 || N < 1 || K < 1) return 0;
+  return align_up(gemm_image_bytes(M, K), 256) + align_up(gemm_image_bytes(N, K), 256);
+}
+
+// with a workspace of gemm_workspace_bytes: pack both operands, then the TMA-fed kernel; without: the register-staged kernel
+int launch_gemm_nt_3xtf32_ws(const float* A, const float* B, float* C, int M, int N, int K, float alpha, const float* rv, const float* cv,
+                             void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (M < 1 || N < 1 || K < 1) {
+    set_error("gemm: empty problem");
+    return EVREP_EINVAL;
+  }
+  if (!workspace) return launch_gemm_nt_3xtf32(A, B, C, M, N, K, alpha, rv, cv, stream);
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255u) || workspace_bytes < gemm_workspace_bytes(M, N, K)) {
+    set_error("gemm: workspace must be 256-byte aligned and hold %zu bytes", gemm_workspace_bytes(M, N, K));
+    return EVREP_EWORKSPACE;
+  }
+  void* imgA = workspace;
+  void* imgB = (char*)workspace + align_up(gemm_image_bytes(M, K), 256);
+  int rc = launch_gemm_pack(A, M, K, K, nullptr, imgA, stream);
+  if (rc) return rc;
+  rc = launch_gemm_pack(B, N, K, K, nullptr, imgB, stream);
+  if (rc) return rc;
+  return launch_gemm_packed(imgA, imgB, C, M, N, K, alpha, rv, cv, stream);
+}
 
 int launch_gemm_nt_3xtf32(const float* A, const float* B, float* C, int M, int N, int K, float alpha, const float* rv, const float* cv,
                           cudaStream_t stream) {
@@ -295,10 +401,10 @@ int launch_gemm_nt_3xtf32(const float* A, const float* B, float* C, int M, int N
     set_error("gemm: empty problem");
     return EVREP_EINVAL;
   }
-  EVREP_CUDA_OK(cudaFuncSetAttribute(k_gemm_nt_3xtf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GB_SMEM));  // per device: cheap, not cached
+  EVREP_CUDA_OK(cudaFuncSetAttribute(k_gemm_nt_3xtf32<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GB_SMEM));  // per device: cheap, not cached
   dim3 grid((unsigned)((N + GB_N - 1) / GB_N), (unsigned)((M + GB_M - 1) / GB_M));
-  k_gemm_nt_3xtf32<<<grid, GB_THREADS, GB_SMEM, stream>>>(A, B, C, M, N, K, alpha, rv, cv, (al16(A) && K % 4 == 0) ? 1 : 0,
-                                                          (al16(B) && K % 4 == 0) ? 1 : 0, (al16(C) && N % 4 == 0) ? 1 : 0);
+  k_gemm_nt_3xtf32<false><<<grid, GB_THREADS, GB_SMEM, stream>>>(A, B, C, M, N, K, alpha, rv, cv, (al16(A) && K % 4 == 0) ? 1 : 0,
+                                                                 (al16(B) && K % 4 == 0) ? 1 : 0, (al16(C) && N % 4 == 0) ? 1 : 0);
   EVREP_CUDA_OK(cudaGetLastError());
   return EVREP_OK;
 }
@@ -680,6 +786,7 @@ int launch_auction(const float* cost, int n, double eps_rel, int* sigma, int* st
 
 struct GwbWs {
   float *hC1, *hC2, *G, *AG, *AGc, *Mi, *Bp, *cr, *cc;
+  void *imgA, *imgB;  // operand images of the contraction (k_gemm_pack)
   double *rs_a1, *rs_a2, *rs_h1, *rs_h2, *red, *msq;
   int *sigma, *stats;
   size_t bytes;
@@ -701,6 +808,8 @@ static GwbWs gwb_carve(void* basep, int n, int m) {
   w.AGc = (float*)take(sizeof(float) * nm);
   w.Mi = (float*)take(sizeof(float) * nm);
   w.Bp = (float*)take(sizeof(float) * nm);
+  w.imgA = take(gemm_image_bytes(std::max(n, m), std::max(n, m)));
+  w.imgB = take(gemm_image_bytes(std::max(n, m), std::max(n, m)));
   w.cr = (float*)take(sizeof(float) * (size_t)n);
   w.cc = (float*)take(sizeof(float) * (size_t)m);
   w.rs_a1 = (double*)take(sizeof(double) * (size_t)n);
@@ -748,6 +857,10 @@ int run_gw_kl(const double* Xs, int n, int ds, const double* Xt, int m, int dt, 
   k_gwb_init<<<eb, 256, 0, stream>>>(n, m, w.rs_a1, w.rs_a2, w.rs_h1, w.rs_h2, w.cr, w.cc, w.G, w.AG);
   EVREP_CUDA_OK(cudaGetLastError());
 
+  {  // hC1 is the A operand of every step's contraction: pack it once
+    const int rc = launch_gemm_pack(w.hC1, n, n, n, nullptr, w.imgA, stream);
+    if (rc) return rc;
+  }
   const bool device_lmo = lmo == 0 && n <= AUC_MAX_N;
   if (device_lmo) EVREP_CUDA_OK(cudaFuncSetAttribute(k_auction, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)auction_smem_bytes(n)));
   std::vector<float> Mi_host;
@@ -796,9 +909,10 @@ int run_gw_kl(const double* Xs, int n, int ds, const double* Xt, int m, int dt, 
       EVREP_CUDA_OK(cudaMemcpyAsync(w.sigma, sigma.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, stream));
     }
     if (it == 0) f_val = red_host[0];
-    // hC1 Gc hC2^T = (1 / n) hC1 (hC2[:, sigma])^T : gather, then the tensor-core contraction
-    k_gwb_gather<<<eb, 256, 0, stream>>>(w.hC2, w.sigma, m, n, w.Bp);
-    const int rc = launch_gemm_nt_3xtf32(w.hC1, w.Bp, w.AGc, n, m, n, 1.f / (float)n, nullptr, nullptr, stream);
+    // hC1 Gc hC2^T = (1 / n) hC1 (hC2[:, sigma])^T : the gather writes the B operand image, then the tensor-core contraction
+    int rc = launch_gemm_pack(w.hC2, m, n, m, w.sigma, w.imgB, stream);
+    if (rc) return rc;
+    rc = launch_gemm_packed(w.imgA, w.imgB, w.AGc, n, m, n, 1.f / (float)n, nullptr, nullptr, stream);
     if (rc) return rc;
     EVREP_CUDA_OK(cudaMemsetAsync(w.red, 0, sizeof(double) * 8, stream));
     k_gwb_linesearch<<<eb, 256, 0, stream>>>(n, m, w.cr, w.cc, w.AG, w.AGc, w.G, w.sigma, w.red);

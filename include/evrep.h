@@ -208,10 +208,14 @@ int evrep_gw_kl(const double* Xs, int n, int ds, const double* Xt, int m, int dt
 int evrep_assignment_auction(const float* cost, int n, double eps_rel, int* sigma, int* stats, evrep_stream_t stream);
 
 /* C[M x N] = alpha * A[M x K] * B[N x K]^T + rv[i] + cv[j] on the tcgen05 tensor cores: every fp32 operand is split
- * into two TF32 terms while it is staged and hi*hi + lo*hi + hi*lo is accumulated in fp32 (error about 2^-21 relative
- * to |A| |B|).  All pointers DEVICE float32, row major, K contiguous in A and B; rv (M) and cv (N) may be NULL. */
+ * into two TF32 terms (round to nearest) and lo*hi + hi*lo + hi*hi is accumulated, k-blocks of 32 summed in fp32 with
+ * round-to-nearest (error about 2^-22 relative to |A| |B|).  All pointers DEVICE float32, row major, K contiguous in A
+ * and B; rv (M) and cv (N) may be NULL.  With a workspace of evrep_gemm_workspace_bytes(M, N, K) (DEVICE, 256-byte
+ * aligned) the operands are first packed into swizzled tile images and the kernel is fed by TMA bulk copies; with
+ * workspace == NULL a slower variant stages the operands through registers. */
+size_t evrep_gemm_workspace_bytes(int M, int N, int K);
 int evrep_gemm_nt_3xtf32(const float* A, const float* B, float* C, int M, int N, int K, float alpha, const float* rv,
-                         const float* cv, evrep_stream_t stream);
+                         const float* cv, void* workspace, size_t workspace_bytes, evrep_stream_t stream);
 
 /* The image pipeline that follows a representation in the detector's datasets, fused: out = letterbox(resize(rep *
  * scale_in)) * scale_out, HWC -> CHW, optionally with the channel order reversed (`img.transpose(2, 0, 1)[::-1]`).

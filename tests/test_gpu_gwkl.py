@@ -20,9 +20,10 @@ def E(cuda_device):
     return eb
 
 
+@pytest.mark.parametrize("packed", [True, False], ids=["tma-packed", "register-staged"])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 128, 256), (256, 384, 96), (1000, 1000, 1000), (130, 70, 45), (1, 1, 1),
                                    (257, 129, 1001), (64, 300, 8)])
-def test_gemm_nt_3xtf32_matches_float64(E, M, N, K):
+def test_gemm_nt_3xtf32_matches_float64(E, M, N, K, packed):
     import torch
     rng = np.random.default_rng(M * 7 + N * 3 + K)
     A = rng.standard_normal((M, K)).astype(np.float32)
@@ -30,7 +31,7 @@ def test_gemm_nt_3xtf32_matches_float64(E, M, N, K):
     rv = rng.standard_normal(M).astype(np.float32)
     cv = rng.standard_normal(N).astype(np.float32)
     got = E.gemm_nt_3xtf32(torch.as_tensor(A).cuda(), torch.as_tensor(B).cuda(), alpha=0.5, row_vec=torch.as_tensor(rv).cuda(),
-                           col_vec=torch.as_tensor(cv).cuda()).cpu().numpy().astype(np.float64)
+                           col_vec=torch.as_tensor(cv).cuda(), packed=packed).cpu().numpy().astype(np.float64)
     A64, B64 = A.astype(np.float64), B.astype(np.float64)
     want = 0.5 * A64 @ B64.T + rv[:, None] + cv[None, :]
     bound = 1e-6 * (0.5 * np.abs(A64) @ np.abs(B64).T + np.abs(rv)[:, None] + np.abs(cv)[None, :]) + 1e-30
