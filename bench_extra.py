@@ -120,6 +120,9 @@ def main():
             rep_line(f"config3 {name} 1Mpx 1280x720 500k ev/window batch 32", B * N, sec, per, cpu_n / c, f"{n} windows, {note}")
         sec = timed(lambda: (eb.time_surface(ev, H, W, 6, 50000.0, out=o1), eb.event_stack(ev, H, W, 12, out=o2), eb.tore(ev, H, W, 6, out=o3)), a.steps)
         rep_line("config3 all three (three calls; events counted once in the algorithmic bytes)", B * N, sec, B * (N * 9 + 3 * H * W * 12 * 4), float("nan"), "n/a")
+        outs = (o2, o1, o3)
+        sec = timed(lambda: eb.order_ops_fused(ev, H, W, 50000.0, out=outs), a.steps)
+        rep_line("config3 all three FUSED (one bucketing pass, evrep_order_ops_fused_batched)", B * N, sec, B * (N * 9 + 3 * H * W * 12 * 4), float("nan"), "n/a")
 
     if "gwd" in only:  # config 5, reading (ii): 12 representations x S samples, each pair subsampled to n = m = 1000 points
         R, S, n = 12, 256, 1000

@@ -38,6 +38,7 @@ SIGNATURES = {
     "evrep_event_stack_batched": (_i, _EV + [_i] + _TAIL),
     "evrep_time_surface_batched": (_i, _EV + [_vp, _i, _d] + _TAIL),
     "evrep_tore_batched": (_i, _EV + [_i] + _TAIL),
+    "evrep_order_ops_fused_batched": (_i, _EV + [_d, _vp, _vp] + _TAIL),
     "evrep_voxel_batched": (_i, _EV + [_i, _i, _i, _vp] + _TAIL),
     "evrep_histogram_batched": (_i, _EV + _TAIL),
     "evrep_gwd_workspace_bytes": (_sz, [_vp, _vp, _i]),

@@ -203,6 +203,18 @@ def tore(ev, H, W, k=6, out=None):
     return out
 
 
+def order_ops_fused(ev, H, W, tau=50000.0, out=None):
+    """BASELINE configs[2] in one call: (EventStack(12) (B, H, W, 12), TimeSurface(6 snapshots) (B, 6, 2, H, W), TORE(k=6)
+    (B, H, W, 12)) from a single bucketing pass; each equals the separate call bit for bit.  Windows < 2^20 events."""
+    head, ws, stream = _prep(ev, _lib.OP_TORE, H, W, 12)
+    es, ts, tr = out if out is not None else (None, None, None)
+    es = _out(ev, (ev.B, H, W, 12), es)
+    ts = _out(ev, (ev.B, 6, 2, H, W), ts)
+    tr = _out(ev, (ev.B, H, W, 12), tr)
+    check(lib.evrep_order_ops_fused_batched(*head, float(tau), es.data_ptr(), ts.data_ptr(), tr.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+    return es, ts, tr
+
+
 def voxel_grid(ev, H, W, n_bins, flavour="tonic", normalize=True, t0_us=None, t1_us=None, out=None):
     """flavour 'tonic' -> (B, n_bins, H, W); 'evlicious' -> (B, n_bins, H, W); 'gwd' -> (B, H, W, n_bins)."""
     fl = {"tonic": _lib.VOXEL_TONIC, "evlicious": _lib.VOXEL_EVLICIOUS, "gwd": _lib.VOXEL_GWD}[flavour]

@@ -335,6 +335,30 @@ int evrep_tore_batched(const uint16_t* x, const uint16_t* y, const void* t, int 
   EVREP_GUARD_END
 }
 
+int evrep_order_ops_fused_batched(const uint16_t* x, const uint16_t* y, const void* t, int t_bytes, const int8_t* p, const int64_t* win_offsets,
+                                  int B, int H, int W, double tau, float* out_es, float* out_ts, float* out_tore, void* workspace,
+                                  size_t workspace_bytes, evrep_stream_t stream) {
+  EVREP_GUARD_BEGIN
+  Events ev;
+  int64_t total = 0, n_max = 0;
+  EVREP_TRY(check_events(x, y, t, t_bytes, p, win_offsets, B, out_es, &ev, &total, &n_max));
+  if (!(tau > 0.0)) { set_error("tau must be positive"); return EVREP_EINVAL; }
+  if (B == 0) return EVREP_OK;
+  if (!out_ts || !out_tore) { set_error("null output"); return EVREP_EINVAL; }
+  if (n_max >= ((int64_t)1 << 20)) { set_error("fused order ops: windows must hold fewer than 2^20 events (got %lld)", (long long)n_max); return EVREP_EUNSUPPORTED; }
+  Geom g;
+  memset(&g, 0, sizeof(g));
+  EVREP_TRY(choose_tile(H, W, 60, &g));  // 1024-pixel tiles: what TORE's staged kernel wants and the fused record's 10 pixel bits allow
+  if (g.tile_px > 1024) { set_error("fused order ops: sensor too large for 1024-pixel tiles"); return EVREP_EUNSUPPORTED; }
+  g.B = B;
+  g.total = total;
+  Workspace ws;
+  EVREP_TRY(carve_checked(workspace, workspace_bytes, B, total, g.Tb, &ws));
+  EVREP_TRY(run_binning(ev, win_offsets, g, ws, REC_T_IDX, 6, nullptr, (cudaStream_t)stream));
+  return launch_order_ops_fused(g, ws, tau, out_es, out_ts, out_tore, (cudaStream_t)stream);
+  EVREP_GUARD_END
+}
+
 int evrep_voxel_batched(const uint16_t* x, const uint16_t* y, const void* t, int t_bytes, const int8_t* p, const int64_t* win_offsets,
                         int B, int H, int W, int flavour, int n_bins, int normalize, const int64_t* t0_t1_us, float* out,
                         void* workspace, size_t workspace_bytes, evrep_stream_t stream) {

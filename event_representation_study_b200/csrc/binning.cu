@@ -554,7 +554,14 @@ __global__ void __launch_bounds__(BIN_THREADS, EVREP_BIN_CTAS) k_bin(const uint1
       } else if (MODE == REC_T_TORE) {  // strict `<` against the sample time = last timestamp (tore.py:17)
         if (t_rel >= tlast_rel) keep = false;
       }
-      if (keep) {
+      if (MODE == REC_T_IDX) {
+        rec = make_uint2(0u, FUSED_NULL_META);
+        if (keep) {
+          my_tmin = min(my_tmin, t_rel);
+          my_tmax = max(my_tmax, t_rel);
+          rec = make_uint2(k, fused_meta(lin & (uint32_t)(g.tile_px - 1), (uint32_t)idx, (uint32_t)pv & 3u));
+        }
+      } else if (keep) {
         my_tmin = min(my_tmin, t_rel);
         my_tmax = max(my_tmax, t_rel);
         rec = make_uint2(k, rec_meta(lin & (uint32_t)(g.tile_px - 1), aux, (uint32_t)pv & 3u));
@@ -603,6 +610,7 @@ static int launch_bin_mode(int mode, const Events& ev, const Geom& g, const Work
                                           : launch_bin<TT, REC_IDX, false>(ev, g, ws, n_sc, vec, stream);
     case REC_T_SNAP: return launch_bin<TT, REC_T_SNAP, false>(ev, g, ws, n_sc, vec, stream);
     case REC_T_TORE: return launch_bin<TT, REC_T_TORE, false>(ev, g, ws, n_sc, vec, stream);
+    case REC_T_IDX: return launch_bin<TT, REC_T_IDX, false>(ev, g, ws, n_sc, vec, stream);
     default: return launch_bin<TT, REC_T_ONLY, false>(ev, g, ws, n_sc, vec, stream);
   }
 }
@@ -679,7 +687,7 @@ int run_binning(const Events& ev, const int64_t* win_offsets_host, const Geom& g
   EVREP_CUDA_OK(cudaMemsetAsync(ws.ticket, 0, sizeof(uint32_t) * 64, stream));
   const bool vec = events_vectorisable(ev);
 
-  if (rec_mode == REC_T_SNAP) {
+  if (rec_mode == REC_T_SNAP || rec_mode == REC_T_IDX) {
     const int64_t* user = nullptr;
     if (snap_indices_host) {
       EVREP_CUDA_OK(cudaMemcpyAsync(ws.snap_in, snap_indices_host, sizeof(int64_t) * (size_t)g.B * n_snap, cudaMemcpyHostToDevice, stream));

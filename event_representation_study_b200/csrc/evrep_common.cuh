@@ -34,7 +34,14 @@ enum RecMode : int {
   REC_T_SNAP = 2,   // key = t_rel, aux = first snapshot it feeds    (time surface)
   REC_T_TORE = 3,   // key = t_rel, events with t >= t_last dropped  (TORE)
   REC_T_ONLY = 4,   // key = t_rel, aux = 0: windows are derived from t later (mixed density, SBT)
+  REC_T_IDX = 5,    // key = t_rel, meta = pixel (10 b) | stream index (20 b) | polarity code (2 b): EventStack + TimeSurface + TORE from one pass
 };
+// the fused record of REC_T_IDX (tiles of at most 1024 pixels, windows of fewer than 2^20 events)
+__host__ __device__ inline uint32_t fused_meta(uint32_t pix, uint32_t idx, uint32_t pc) { return pix | (idx << 10) | (pc << 30); }
+__host__ __device__ inline uint32_t fused_pix(uint32_t m) { return m & 0x3ffu; }
+__host__ __device__ inline uint32_t fused_idx(uint32_t m) { return (m >> 10) & 0xfffffu; }
+__host__ __device__ inline uint32_t fused_pc(uint32_t m) { return m >> 30; }  // 2 = null record
+constexpr uint32_t FUSED_NULL_META = 2u << 30;
 // meta word: [15:0] pixel inside tile, [23:16] aux, [25:24] polarity code (p & 3: 0 -> 0, 1 -> +1, 3 -> -1; 2 = null record)
 __host__ __device__ inline uint32_t rec_meta(uint32_t pix, uint32_t aux, uint32_t pc) { return pix | (aux << 16) | (pc << 24); }
 // A null record fills the slot of an event that was counted (valid x, y) but then dropped (timestamp out of range, after
@@ -188,6 +195,7 @@ int launch_md_tile(const Geom& g, const Workspace& ws, const MdPlan& plan, const
 int launch_event_stack_tile(const Geom& g, const Workspace& ws, int stack_size, float* out, cudaStream_t stream);
 int launch_time_surface_tile(const Geom& g, const Workspace& ws, int S, double tau, float* out, cudaStream_t stream);
 int launch_tore_tile(const Geom& g, const Workspace& ws, int k, float* out, cudaStream_t stream);
+int launch_order_ops_fused(const Geom& g, const Workspace& ws, double tau, float* out_es, float* out_ts, float* out_tore, cudaStream_t stream);
 int launch_filter_tile(const Geom& g, const Workspace& ws, const Events& ev, int filter, double param, void* state, unsigned char* mask,
                        cudaStream_t stream);
 

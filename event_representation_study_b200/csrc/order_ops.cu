@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_event_stack_tile(const uint2* 
 // pixels are staged in shared memory ([pixel][K], 16-byte stores at a 48-byte stride are conflict free) and leave as
 // consecutive float4: no integer division, no per-element address arithmetic (ncu r01: the generic kernel spent 38
 // instructions per output element and was issue bound at 42 % of the DRAM peak).
-template <int K>
+template <int K, bool FUSED>
 __global__ void __launch_bounds__(TILE_THREADS) k_event_stack_tile_k(const uint2* __restrict__ records, const uint32_t* __restrict__ base,
                                                                      const uint32_t* __restrict__ hist, const WinParams* __restrict__ wp,
                                                                      const Geom g, float* __restrict__ out) {
@@ -89,6 +89,11 @@ __global__ void __launch_bounds__(TILE_THREADS) k_event_stack_tile_k(const uint2
   __syncthreads();
   for (uint32_t i = tid; i < count; i += TILE_THREADS) {
     const uint2 r = __ldg(rec + i);
+    if (FUSED) {  // REC_T_IDX records: the stream index travels in the meta word
+      if (fused_pc(r.y) == 2u) continue;
+      atomicMax(&acc[fused_pix(r.y)], ((fused_idx(r.y) + 1u) << 1) | (fused_pc(r.y) == 1u ? 1u : 0u));
+      continue;
+    }
     if (rec_is_null(r.y)) continue;
     const uint32_t pol = (((r.y >> 24) & 3u) == 1u) ? 1u : 0u;  // p > 0
     atomicMax(&acc[r.y & 0xffffu], ((r.x + 1u) << 1) | pol);
@@ -121,9 +126,9 @@ __global__ void __launch_bounds__(TILE_THREADS) k_event_stack_tile_k(const uint2
 int launch_event_stack_tile(const Geom& g, const Workspace& ws, int stack_size, float* out, cudaStream_t stream) {
   if (stack_size == 12 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
     const size_t smem12 = sizeof(uint32_t) * (size_t)g.tile_px + sizeof(float) * 12 * TILE_THREADS;
-    EVREP_CUDA_OK(cudaFuncSetAttribute(k_event_stack_tile_k<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem12));
+    EVREP_CUDA_OK(cudaFuncSetAttribute(k_event_stack_tile_k<12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem12));
     prof_begin(EVREP_K_TILE, stream);
-    k_event_stack_tile_k<12><<<g.B * g.T, TILE_THREADS, smem12, stream>>>(ws.records, ws.base, ws.hist, ws.wp, g, out);
+    k_event_stack_tile_k<12, false><<<g.B * g.T, TILE_THREADS, smem12, stream>>>(ws.records, ws.base, ws.hist, ws.wp, g, out);
     prof_end(EVREP_K_TILE, stream);
     EVREP_CUDA_OK(cudaGetLastError());
     return EVREP_OK;
@@ -199,13 +204,14 @@ __global__ void __launch_bounds__(TILE_THREADS) k_time_surface_tile(const uint2*
 // Compile-time S (the reference's 6 snapshots): the snapshot loop is unrolled, the running maximum lives in a register
 // and the S stores of a thread go to one base pointer plus constant strides (the generic kernel: 62 instructions per
 // output element, issue bound at 23 % of the DRAM peak).
-template <int S>
+template <int S, bool FUSED>
 __global__ void __launch_bounds__(TILE_THREADS) k_time_surface_tile_s(const uint2* __restrict__ records, const uint32_t* __restrict__ base,
                                                                       const uint32_t* __restrict__ hist, const WinParams* __restrict__ wp,
                                                                       const SnapParams* __restrict__ snap, const Geom g, double tau,
                                                                       float* __restrict__ out) {
   extern __shared__ __align__(16) uint32_t acc[];  // [S][2][TP]
   __shared__ int32_t s_trel[S];
+  __shared__ int32_t s_sidx[S];
   __shared__ float s_empty[S];
   __shared__ int s_nvalid;
   const int tid = threadIdx.x;
@@ -216,6 +222,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_time_surface_tile_s(const uint
   if (tid < S) {
     const int32_t tr = snap[b].t_rel[tid];
     s_trel[tid] = tr;
+    s_sidx[tid] = snap[b].idx[tid];
     // untouched pixels: exp((-(3 tau + 1) - t_snapshot) / tau) with the ABSOLUTE snapshot timestamp
     s_empty[tid] = (float)exp((-(tau * 3.0 + 1.0) - (double)(w.t_base + (int64_t)tr)) / tau);
   }
@@ -226,6 +233,15 @@ __global__ void __launch_bounds__(TILE_THREADS) k_time_surface_tile_s(const uint
   __syncthreads();
   for (uint32_t i = tid; i < count; i += TILE_THREADS) {
     const uint2 r = __ldg(rec + i);
+    if (FUSED) {  // REC_T_IDX records: the first snapshot an event feeds is found from its stream index here
+      if (fused_pc(r.y) == 2u) continue;
+      const int idx = (int)fused_idx(r.y), ns = s_nvalid;
+      int sn = 0;
+      while (sn < ns && idx > s_sidx[sn]) ++sn;
+      if (sn >= ns) continue;  // after the last emitted surface
+      atomicMax(&acc[((uint32_t)sn * 2u + (fused_pc(r.y) == 1u ? 1u : 0u)) * TP + fused_pix(r.y)], (uint32_t)((int32_t)r.x - tmin) + 1u);
+      continue;
+    }
     if (rec_is_null(r.y)) continue;
     const uint32_t sn = (r.y >> 16) & 0xffu;
     const uint32_t plane = (((r.y >> 24) & 3u) == 1u) ? 1u : 0u;
@@ -261,9 +277,9 @@ __global__ void __launch_bounds__(TILE_THREADS) k_time_surface_tile_s(const uint
 int launch_time_surface_tile(const Geom& g, const Workspace& ws, int S, double tau, float* out, cudaStream_t stream) {
   if (S == 6) {
     const size_t smem6 = sizeof(uint32_t) * (size_t)g.tile_px * 2 * 6;
-    EVREP_CUDA_OK(cudaFuncSetAttribute(k_time_surface_tile_s<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));
+    EVREP_CUDA_OK(cudaFuncSetAttribute(k_time_surface_tile_s<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));
     prof_begin(EVREP_K_TILE, stream);
-    k_time_surface_tile_s<6><<<g.B * g.T, TILE_THREADS, smem6, stream>>>(ws.records, ws.base, ws.hist, ws.wp, ws.snap, g, tau, out);
+    k_time_surface_tile_s<6, false><<<g.B * g.T, TILE_THREADS, smem6, stream>>>(ws.records, ws.base, ws.hist, ws.wp, ws.snap, g, tau, out);
     prof_end(EVREP_K_TILE, stream);
     EVREP_CUDA_OK(cudaGetLastError());
     return EVREP_OK;
@@ -330,7 +346,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tore_tile(const uint2* __restr
 
 // Compile-time K (the reference's k = 6): one thread per pixel, 2K outputs staged as [pixel][2K] and copied out as
 // consecutive float4; logf only runs for warps that hold a filled slot (slots beyond the first are nearly always empty).
-template <int K>
+template <int K, bool FUSED>
 __global__ void __launch_bounds__(TILE_THREADS) k_tore_tile_k(const uint2* __restrict__ records, const uint32_t* __restrict__ base,
                                                               const uint32_t* __restrict__ hist, const WinParams* __restrict__ wp,
                                                               const Geom g, float* __restrict__ out) {
@@ -349,10 +365,18 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tore_tile_k(const uint2* __res
   __syncthreads();
   for (uint32_t i = tid; i < count; i += TILE_THREADS) {
     const uint2 r = __ldg(rec + i);
-    if (rec_is_null(r.y)) continue;
-    const uint32_t plane = (((r.y >> 24) & 3u) == 1u) ? 0u : 1u;  // positive first (tore.py:63-65)
+    uint32_t plane, pix;
+    if (FUSED) {  // REC_T_IDX records: the strict `t < sample time` cut of tore.py:17 is applied here
+      if (fused_pc(r.y) == 2u || (int32_t)r.x >= w.tlast_rel) continue;
+      plane = fused_pc(r.y) == 1u ? 0u : 1u;
+      pix = fused_pix(r.y);
+    } else {
+      if (rec_is_null(r.y)) continue;
+      plane = (((r.y >> 24) & 3u) == 1u) ? 0u : 1u;  // positive first (tore.py:63-65)
+      pix = r.y & 0xffffu;
+    }
     uint32_t v = (uint32_t)((int32_t)r.x - tmin) + 1u;
-    uint32_t* slot = &acc[plane * K * TP + (r.y & 0xffffu)];
+    uint32_t* slot = &acc[plane * K * TP + pix];
 #pragma unroll
     for (int j = 0; j < K; ++j) {
       if (!v) break;
@@ -406,9 +430,9 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tore_tile_k(const uint2* __res
 int launch_tore_tile(const Geom& g, const Workspace& ws, int k, float* out, cudaStream_t stream) {
   if (k == 6 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
     const size_t smem6 = sizeof(uint32_t) * (size_t)g.tile_px * 12 + sizeof(float) * 12 * TILE_THREADS;
-    EVREP_CUDA_OK(cudaFuncSetAttribute(k_tore_tile_k<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));
+    EVREP_CUDA_OK(cudaFuncSetAttribute(k_tore_tile_k<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));
     prof_begin(EVREP_K_TILE, stream);
-    k_tore_tile_k<6><<<g.B * g.T, TILE_THREADS, smem6, stream>>>(ws.records, ws.base, ws.hist, ws.wp, g, out);
+    k_tore_tile_k<6, false><<<g.B * g.T, TILE_THREADS, smem6, stream>>>(ws.records, ws.base, ws.hist, ws.wp, g, out);
     prof_end(EVREP_K_TILE, stream);
     EVREP_CUDA_OK(cudaGetLastError());
     return EVREP_OK;
@@ -417,6 +441,24 @@ int launch_tore_tile(const Geom& g, const Workspace& ws, int k, float* out, cuda
   EVREP_CUDA_OK(cudaFuncSetAttribute(k_tore_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   prof_begin(EVREP_K_TILE, stream);
   k_tore_tile<<<g.B * g.T, TILE_THREADS, smem, stream>>>(ws.records, ws.base, ws.hist, ws.wp, g, k, out);
+  prof_end(EVREP_K_TILE, stream);
+  EVREP_CUDA_OK(cudaGetLastError());
+  return EVREP_OK;
+}
+
+// EventStack(12) + TimeSurface(6 snapshots) + TORE(k = 6) from ONE binning pass (REC_T_IDX records, 1024-pixel tiles):
+// BASELINE configs[2] asks for the three together, and two of the three binning passes were pure repetition.
+int launch_order_ops_fused(const Geom& g, const Workspace& ws, double tau, float* out_es, float* out_ts, float* out_tore, cudaStream_t stream) {
+  const size_t sm_es = sizeof(uint32_t) * (size_t)g.tile_px + sizeof(float) * 12 * TILE_THREADS;
+  const size_t sm_ts = sizeof(uint32_t) * (size_t)g.tile_px * 12;
+  const size_t sm_tore = sizeof(uint32_t) * (size_t)g.tile_px * 12 + sizeof(float) * 12 * TILE_THREADS;
+  EVREP_CUDA_OK(cudaFuncSetAttribute(k_event_stack_tile_k<12, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_es));
+  EVREP_CUDA_OK(cudaFuncSetAttribute(k_time_surface_tile_s<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_ts));
+  EVREP_CUDA_OK(cudaFuncSetAttribute(k_tore_tile_k<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_tore));
+  prof_begin(EVREP_K_TILE, stream);
+  k_event_stack_tile_k<12, true><<<g.B * g.T, TILE_THREADS, sm_es, stream>>>(ws.records, ws.base, ws.hist, ws.wp, g, out_es);
+  k_time_surface_tile_s<6, true><<<g.B * g.T, TILE_THREADS, sm_ts, stream>>>(ws.records, ws.base, ws.hist, ws.wp, ws.snap, g, tau, out_ts);
+  k_tore_tile_k<6, true><<<g.B * g.T, TILE_THREADS, sm_tore, stream>>>(ws.records, ws.base, ws.hist, ws.wp, g, out_tore);
   prof_end(EVREP_K_TILE, stream);
   EVREP_CUDA_OK(cudaGetLastError());
   return EVREP_OK;

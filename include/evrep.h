@@ -160,6 +160,14 @@ int evrep_tore_batched(const uint16_t* x, const uint16_t* y, const void* t, int 
                        const int64_t* win_offsets, int B, int H, int W, int k, float* out, void* workspace,
                        size_t workspace_bytes, evrep_stream_t stream);
 
+/* BASELINE configs[2] in one call: EventStack (stack_size 12), TimeSurface (6 snapshots by the gen1_transforms.py rule, tau)
+ * and TORE (k = 6) of the same windows from a single bucketing pass.  out_es: (B, H, W, 12), out_ts: (B, 6, 2, H, W),
+ * out_tore: (B, H, W, 12); each is bit-identical to what the separate entry points write.  Windows of fewer than 2^20
+ * events (EVREP_EUNSUPPORTED otherwise).  Workspace: evrep_workspace_bytes(EVREP_OP_TORE, ...). */
+int evrep_order_ops_fused_batched(const uint16_t* x, const uint16_t* y, const void* t, int t_bytes, const int8_t* p,
+                                  const int64_t* win_offsets, int B, int H, int W, double tau, float* out_es, float* out_ts,
+                                  float* out_tore, void* workspace, size_t workspace_bytes, evrep_stream_t stream);
+
 /* flavour = EVREP_VOXEL_*.  normalize and t0_t1_us (HOST, 2 entries: the t0_us / t1_us arguments of
  * events_to_voxel_grid, or NULL for first / last timestamp of each window) apply to the ev-licious flavour
  * only.  A window with fewer than 2 events gives zeros in the ev-licious flavour (utils.py:52-53). */

@@ -436,3 +436,22 @@ def test_binning_boundaries_all_tile_ops(E, sizes):
     assert np.array_equal(np.nan_to_num(alone), np.nan_to_num(er[k]))
     again = np_(E.ergo12(ev, H, W))
     assert np.array_equal(np.nan_to_num(again), np.nan_to_num(er))
+
+
+@pytest.mark.parametrize("H,W,sizes", [(240, 304, [50_000, 1, 33_333, 0, 8193]), (720, 1280, [400_000, 90_000])], ids=["gen1", "1mpx"])
+def test_order_ops_fused_equals_the_separate_calls(E, H, W, sizes):
+    """BASELINE configs[2] from one bucketing pass: bit-identical to the three separate entry points"""
+    wins = streams(H, W, sizes, 910)
+    ev = E.pack_events(wins, "cuda")
+    es, ts, tr = E.order_ops_fused(ev, H, W, 50000.0)
+    assert np.array_equal(np_(es), np_(E.event_stack(ev, H, W, 12)))
+    assert np.array_equal(np_(ts), np_(E.time_surface(ev, H, W, 6, 50000.0)))
+    assert np.array_equal(np_(tr), np_(E.tore(ev, H, W, 6)))
+
+
+def test_order_ops_fused_rejects_windows_of_2_pow_20_events(E):
+    from event_representation_study_b200._lib import EvrepError, EUNSUPPORTED
+    ev = E.pack_events(streams(64, 64, [1 << 20], 3), "cuda")
+    with pytest.raises(EvrepError) as e:
+        E.order_ops_fused(ev, 64, 64)
+    assert e.value.code == EUNSUPPORTED
