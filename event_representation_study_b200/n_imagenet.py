@@ -122,3 +122,81 @@ def reshape_then_time_surface(event_tensor, augment=None, **kwargs):
     rep = rep.reshape((-1, rep.shape[-2], rep.shape[-1]))
     rep = torch.tensor(rep.transpose(1, 2, 0)) if not torch.is_tensor(rep) else rep.permute(1, 2, 0)
     return rep.float()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Upstream N-ImageNet count / latest-timestamp representations (imagenet.py:169-343) that are instances of the same
+# per-pixel reductions: each is a MixedDensityEventStack tuple over the whole window (window 0), so one CUDA launch
+# through evrep_mixed_density_batched produces all of its planes.
+#   bincount of positive / negative events          = (count_pos | count_neg, sum)
+#   scatter_max of (t - t_first) / (t_last - t_first) = (timestamp_pos | timestamp_neg, max)   (untouched pixels 0 in both)
+# Timestamps arrive as float seconds; only their position inside the window matters, so they go onto a 2^30 integer
+# grid first (error < 1e-9 of the window).  scatter_min (reshape_then_acc_time) and the sorted / DiST variants are not built.
+# ---------------------------------------------------------------------------------------------------------------------
+def _window_reduce(event_tensor, H, W, functions, aggregations):
+    from . import batched as eb
+    from ._single import one_window
+    ev_np = event_tensor.numpy() if torch.is_tensor(event_tensor) else np.asarray(event_tensor)
+    t = ev_np[:, 2].astype(np.float64)
+    span = float(t[-1] - t[0])
+    if not (span > 0 and np.all(np.diff(t) >= 0)):
+        raise ValueError("the N-ImageNet representations on the GPU need time-sorted events with t[-1] > t[0]")
+    ti = np.rint((t - t[0]) / span * float(2**30 - 2)).astype(np.int64)
+    p = ev_np[:, 3]
+    if np.any(p == 0):
+        raise ValueError("polarities must be -1 / +1 (imagenet.py splits on p > 0 / p < 0)")
+    ev = one_window(ev_np[:, 0].astype(np.int64), ev_np[:, 1].astype(np.int64), ti, np.sign(p).astype(np.int8), H, W)
+    return eb.mixed_density(ev, H, W, [0] * len(functions), functions, aggregations)[0]  # (H, W, C) float32 on the GPU
+
+
+def _empty_guard(event_tensor):
+    """imagenet.py:258-262: an empty sample becomes ten fake positive events at pixel (0, 0)"""
+    if len(event_tensor) == 0:
+        event_tensor = torch.zeros([10, 4]).float()
+        event_tensor[:, 2] = torch.arange(10) / 10.0
+        event_tensor[:, -1] = 1
+    return event_tensor
+
+
+def reshape_then_acc_count(event_tensor, augment=None, **kwargs):
+    """imagenet.py:250-293 -> (4, H, W): positive count, latest positive time, negative count, latest negative time"""
+    if augment is not None:
+        event_tensor = augment(event_tensor)
+    event_tensor = _empty_guard(event_tensor)
+    H = kwargs.get("height", IMAGE_H)
+    W = kwargs.get("width", IMAGE_W)
+    rep = _window_reduce(event_tensor, H, W, ["count_pos", "timestamp_pos", "count_neg", "timestamp_neg"], ["sum", "max", "sum", "max"])
+    return rep.permute(2, 0, 1).float().cpu()
+
+
+def reshape_then_acc(event_tensor, augment=None, **kwargs):
+    """imagenet.py:169-210: like reshape_then_acc_count with each count plane divided by its maximum"""
+    if augment is not None:
+        event_tensor = augment(event_tensor)
+    H = kwargs.get("height", IMAGE_H)
+    W = kwargs.get("width", IMAGE_W)
+    rep = _window_reduce(event_tensor, H, W, ["count_pos", "timestamp_pos", "count_neg", "timestamp_neg"], ["sum", "max", "sum", "max"])
+    rep = rep.permute(2, 0, 1).contiguous()
+    rep[0] = rep[0] / rep[0].max()
+    rep[2] = rep[2] / rep[2].max()
+    return rep.float().cpu()
+
+
+def reshape_then_acc_count_pol(event_tensor, augment=None, **kwargs):
+    """imagenet.py:296-321 -> (2, H, W): positive count, negative count"""
+    if augment is not None:
+        event_tensor = augment(event_tensor)
+    H = kwargs.get("height", IMAGE_H)
+    W = kwargs.get("width", IMAGE_W)
+    rep = _window_reduce(event_tensor, H, W, ["count_pos", "count_neg"], ["sum", "sum"])
+    return rep.permute(2, 0, 1).float().cpu()
+
+
+def reshape_then_acc_count_only(event_tensor, augment=None, **kwargs):
+    """imagenet.py:324-343 -> (1, H, W): events per pixel"""
+    if augment is not None:
+        event_tensor = augment(event_tensor)
+    H = kwargs.get("height", IMAGE_H)
+    W = kwargs.get("width", IMAGE_W)
+    rep = _window_reduce(event_tensor, H, W, ["count"], ["sum"])
+    return rep.permute(2, 0, 1).float().cpu()

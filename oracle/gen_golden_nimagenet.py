@@ -22,10 +22,7 @@ sys.path.insert(0, REF)
 sys.path.insert(0, os.path.join(REF, "representations"))
 np.int = int  # noqa: removed alias used by the reference
 
-import torch_scatter  # noqa: E402  (the shim)
-for name in ("scatter_max", "scatter_min"):  # imported at module level by imagenet.py, used by loaders outside this scope
-    if not hasattr(torch_scatter, name):
-        setattr(torch_scatter, name, lambda *a, **k: (_ for _ in ()).throw(NotImplementedError(name)))
+import torch_scatter  # noqa: E402,F401  (the shim: scatter, scatter_max, scatter_min)
 
 spec = importlib.util.spec_from_file_location("ref_imagenet", os.path.join(REF, "n_imagenet", "real_cnn_model", "data", "imagenet.py"))
 ref = importlib.util.module_from_spec(spec)
@@ -50,6 +47,11 @@ def main():
     for name, data in [("voxel_grid", ev), ("optimized", ev_us), ("event_stack", ev), ("tore", ev_us)]:
         rep = getattr(ref, "reshape_then_" + name)(torch.tensor(data.copy()), height=H, width=W)
         out[name] = rep.numpy()
+        print(name, tuple(rep.shape), rep.dtype)
+    # upstream count / latest-time representations (imagenet.py:169-343), on the seconds-stamped tensor as the loader gives it
+    for name in ("acc_count", "acc", "acc_count_pol", "acc_count_only"):
+        rep = getattr(ref, "reshape_then_" + name)(torch.tensor(ev.copy()), height=H, width=W)
+        out["up_" + name] = rep.numpy()
         print(name, tuple(rep.shape), rep.dtype)
     # reshape_then_time_surface cannot run: it writes `.astype(int)` back into the f8 fields, which stay float, and
     # numba refuses float indices in to_timesurface_numpy (time_surface.py:67).  Expected output = the same lines with the

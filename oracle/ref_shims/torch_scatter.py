@@ -31,3 +31,17 @@ def scatter(src, index, dim=-1, out=None, dim_size=None, reduce="sum"):
             o.scatter_reduce_(0, index, src, "amax", include_self=False)
         return o
     raise ValueError(reduce)
+
+
+def scatter_max(src, index, dim=-1, out=None, dim_size=None):
+    """torch_scatter.scatter_max -> (values, argmax); untouched entries are 0 (argmax not modelled: the call sites in
+    imagenet.py:169-293 discard it)"""
+    return scatter(src, index, dim, out, dim_size, "max"), None
+
+
+def scatter_min(src, index, dim=-1, out=None, dim_size=None):
+    assert src.dim() == 1 and index.dim() == 1
+    o = torch.zeros(dim_size, dtype=src.dtype)
+    if index.numel():
+        o.scatter_reduce_(0, index, src, "amin", include_self=False)
+    return o, None

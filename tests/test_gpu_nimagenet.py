@@ -55,3 +55,26 @@ def test_augment_hook_is_applied_first(N, G):
     a = N.reshape_then_to_image(torch.tensor(G["events_s"].copy()), augment=flip, height=H, width=W)
     b = N.reshape_then_to_image(torch.tensor(G["events_s"].copy()), height=H, width=W)
     assert np.array_equal(a.numpy(), b.numpy()[:, ::-1])
+
+
+@pytest.mark.parametrize("name", ["acc_count", "acc", "acc_count_pol", "acc_count_only"])
+def test_upstream_count_representations_match_the_reference(N, G, name):
+    """imagenet.py:169-343 through one mixed-density launch each; counts exact, normalised times to 1e-5 (2^30 time grid)"""
+    import torch
+    H, W = int(G["H"]), int(G["W"])
+    rep = getattr(N, "reshape_then_" + name)(torch.tensor(G["events_s"].copy()), height=H, width=W)
+    want = G["up_" + name]
+    assert rep.dtype == torch.float32 and tuple(rep.shape) == want.shape
+    assert_close(rep.numpy(), want, rtol=1e-5, atol=1e-7, what=name)
+    if name in ("acc_count", "acc_count_pol", "acc_count_only"):
+        planes = {"acc_count": (0, 2), "acc_count_pol": (0, 1), "acc_count_only": (0,)}[name]
+        for c in planes:
+            assert np.array_equal(rep.numpy()[c], want[c])
+
+
+def test_upstream_acc_count_empty_sample(N):
+    """imagenet.py:258-262: an empty sample is replaced by ten fake positive events at pixel (0, 0)"""
+    import torch
+    rep = N.reshape_then_acc_count(torch.zeros((0, 4), dtype=torch.float64), height=8, width=8)
+    assert float(rep[0, 0, 0]) == 10.0 and float(rep[0].sum()) == 10.0 and float(rep[2].sum()) == 0.0
+    assert abs(float(rep[1, 0, 0]) - 1.0) < 1e-6
