@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_time_surface_tile_s(const uint
     atomicMax(&acc[(sn * 2u + plane) * TP + (r.y & 0xffffu)], (uint32_t)((int32_t)r.x - tmin) + 1u);
   }
   __syncthreads();
-  const double inv_tau = 1.0 / tau;
+  const double inv_tau_log2e = 1.4426950408889634 / tau;
   const int nvalid = s_nvalid;
   int32_t trel[S];
   float empty[S];
@@ -267,7 +267,9 @@ __global__ void __launch_bounds__(TILE_THREADS) k_time_surface_tile_s(const uint
         m = max(m, acc[(k * 2 + plane) * TP + pix]);
         float o = empty[k];
         // (mem - t_snapshot) / tau with mem = key - 1 + tmin, t_snapshot = trel - 1 + tmin: the difference of the keys
-        if (m && k < nvalid) o = expf((float)((double)((int32_t)m - trel[k]) * inv_tau));
+        // exp(d / tau) = 2^(d log2(e) / tau): the product in double, one rounding to float (|argument| < 150: 5e-6
+        // relative at the underflow edge, 1e-6 for values above 1e-9 - the same as rounding d / tau for expf), then ex2
+        if (m && k < nvalid) o = exp2f((float)((double)((int32_t)m - trel[k]) * inv_tau_log2e));
         __stcs(dst + k * snap_stride + pix, o);
       }
     }
