@@ -108,9 +108,10 @@ inline Workspace carve(void* basep, int B, int64_t total, int T) {
     return p;
   };
   w.wp = (WinParams*)take(sizeof(WinParams) * (size_t)B);
-  w.offsets = (int64_t*)take(sizeof(int64_t) * (size_t)(B + 1));
+  // offsets and the super-chunk prefix are uploaded with ONE host-to-device copy: keep them contiguous
+  w.offsets = (int64_t*)take(sizeof(int64_t) * (size_t)(B + 1) + sizeof(int32_t) * (size_t)(B + 1));
+  w.sc_prefix = base ? (int32_t*)(w.offsets + (B + 1)) : nullptr;
   const size_t n_sc = total > 0 ? (size_t)max_super_chunks(B, total) : 1;
-  w.sc_prefix = (int32_t*)take(sizeof(int32_t) * (size_t)(B + 1));
   w.sc_win = (int32_t*)take(sizeof(int32_t) * n_sc);
   w.ticket = (uint32_t*)take(sizeof(uint32_t) * 64);
   w.hist = (uint32_t*)take(sizeof(uint32_t) * (size_t)B * T);
