@@ -156,7 +156,7 @@ def main():
                               "roofline": {"bound": "hbm", "achieved": alg / sec / 1e9, "peak": peak(), "unit": "GB/s", "frac": alg / sec / 1e9 / peak(),
                                            "algorithmic_bytes_per_step": alg},
                               "cpu_baseline": {"value": 1.0 / c, "unit": "windows/s", "cores": 1, "kind": "reference",
-                                               "sample": f"{n} windows, cv2 {what.split()[3] if False else ''}resize + letterbox + transpose per window (oracle/image_pipeline.py around cv2)"}}), flush=True)
+                                               "sample": f"{n} windows, cv2 resize + letterbox + transpose per window (oracle/image_pipeline.py around cv2)"}}), flush=True)
 
     if "est" in only:  # the learned EST quantisation layer, forward (dim = (6, 240, 304), image 640: yolo.py:56-61)
         import event_representation_study_b200.est as est
