@@ -455,3 +455,27 @@ def test_order_ops_fused_rejects_windows_of_2_pow_20_events(E):
     with pytest.raises(EvrepError) as e:
         E.order_ops_fused(ev, 64, 64)
     assert e.value.code == EUNSUPPORTED
+
+
+def test_unaligned_event_arrays_take_the_scalar_load_path(E):
+    """event arrays that do not start on a 16-byte boundary (a view one element into a larger buffer): the binning
+    kernels fall back from 16-byte vector loads to scalar loads; results must not change"""
+    import torch
+    H, W = 96, 128
+    wins = streams(H, W, [20_000, 8193, 5], 321)
+    ev = E.pack_events(wins, "cuda")
+
+    def shifted(tn):
+        buf = torch.empty(tn.numel() + 1, dtype=tn.dtype, device=tn.device)
+        buf[1:] = tn
+        v = buf[1:]
+        assert v.data_ptr() % 16 != 0
+        return v
+
+    ev2 = E.EventBatch(shifted(ev.x), shifted(ev.y), shifted(ev.t), shifted(ev.p), ev.offsets)
+    assert np.array_equal(np.nan_to_num(np_(E.ergo12(ev2, H, W))), np.nan_to_num(np_(E.ergo12(ev, H, W))))
+    assert np.array_equal(np_(E.event_stack(ev2, H, W, 12)), np_(E.event_stack(ev, H, W, 12)))
+    assert np.array_equal(np_(E.tore(ev2, H, W, 6)), np_(E.tore(ev, H, W, 6)))
+    m1, _ = E.filter_events(ev, H, W, "contrast", 2.0)
+    m2, _ = E.filter_events(ev2, H, W, "contrast", 2.0)
+    assert np.array_equal(np_(m1), np_(m2))
