@@ -229,47 +229,67 @@ def run_gpu_arm(a):
     value = world * B * N * a.steps / (ms_all * 1e-3) / 1e9
 
     # ---- end to end: pinned host events -> H2D -> kernels -> per-window checksum -> D2H ----------
-    # The batch is cut into groups of windows that alternate between two CUDA streams, so the host->device copy of one
-    # group overlaps the kernels of the previous one (public API only: EventBatch + ergo12 on the current stream).
+    # Public API only (EventBatch + ergo12).  Every step copies its own 288 MB of events from pinned host memory and reads
+    # its own result back inside the timed region.  The step is cut into groups of windows; a copy stream runs ahead of the
+    # compute stream (one device buffer per group, recycled when the group's kernels are done), so the copies of step s + 1
+    # are already queued when the host waits for the result of step s - the prefetch any input pipeline does.
     host = {k: d[k].cpu().pin_memory() for k in ("x", "y", "t", "p")}
-    res_host = torch.empty(B, dtype=torch.float64).pin_memory()
     n_groups = min(a.e2e_groups, B)
     bounds = [B * g // n_groups for g in range(n_groups + 1)]
-    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
-    cap = max(int(ev.offsets[bounds[g + 1]] - ev.offsets[bounds[g]]) for g in range(n_groups))
-    dbuf = [{k: torch.empty(cap, dtype=d[k].dtype, device=dev) for k in ("x", "y", "t", "p")} for _ in range(2)]
     offs = ev.offsets
+    res_host = [torch.empty(B, dtype=torch.float64).pin_memory() for _ in range(2)]
+    copy_st, comp_st = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    dbuf = [{k: torch.empty(int(offs[bounds[g + 1]] - offs[bounds[g]]), dtype=d[k].dtype, device=dev) for k in ("x", "y", "t", "p")}
+            for g in range(n_groups)]
+    ready = [torch.cuda.Event() for _ in range(n_groups)]   # group's events are on the device
+    done = [torch.cuda.Event() for _ in range(n_groups)]    # group's kernels no longer read its buffer
 
-    def e2e_step():
-        cur = torch.cuda.current_stream(dev)
-        for s_ in streams:
-            s_.wait_stream(cur)
-        for g_ in range(n_groups):
-            st = streams[g_ % 2]
-            w0, w1 = bounds[g_], bounds[g_ + 1]
-            e0, e1 = int(offs[w0]), int(offs[w1])
-            buf = dbuf[g_ % 2]
-            with torch.cuda.stream(st):
+    def enqueue_copies(first):
+        with torch.cuda.stream(copy_st):
+            for g_ in range(n_groups):
+                if not first:
+                    copy_st.wait_event(done[g_])
+                e0, e1 = int(offs[bounds[g_]]), int(offs[bounds[g_ + 1]])
                 for k in ("x", "y", "t", "p"):
-                    buf[k][: e1 - e0].copy_(host[k][e0:e1], non_blocking=True)
-                sub = eb.EventBatch(buf["x"], buf["y"], buf["t"], buf["p"], offs[w0:w1 + 1] - e0)
-                o = eb.ergo12(sub, H, W, out=out[w0:w1])
-                res_host[w0:w1].copy_(o.view(w1 - w0, -1).sum(1, dtype=torch.float64), non_blocking=True)
-        for s_ in streams:
-            cur.wait_stream(s_)
-        torch.cuda.synchronize()  # the caller reads the result before the next step
-        return res_host
+                    dbuf[g_][k].copy_(host[k][e0:e1], non_blocking=True)
+                ready[g_].record(copy_st)
 
-    for _ in range(2):
-        e2e_step()
+    def enqueue_compute(step):
+        rh = res_host[step & 1]
+        with torch.cuda.stream(comp_st):
+            for g_ in range(n_groups):
+                w0, w1 = bounds[g_], bounds[g_ + 1]
+                comp_st.wait_event(ready[g_])
+                sub = eb.EventBatch(dbuf[g_]["x"], dbuf[g_]["y"], dbuf[g_]["t"], dbuf[g_]["p"], offs[w0:w1 + 1] - int(offs[w0]))
+                o = eb.ergo12(sub, H, W, out=out[w0:w1])
+                done[g_].record(comp_st)
+                rh[w0:w1].copy_(o.view(w1 - w0, -1).sum(1, dtype=torch.float64), non_blocking=True)
+            fin = torch.cuda.Event()
+            fin.record(comp_st)
+        return fin, rh
+
+    def e2e_run(steps):
+        enqueue_copies(first=True)
+        last = None
+        for s_ in range(steps):
+            fin, rh = enqueue_compute(s_)
+            if s_ + 1 < steps:
+                enqueue_copies(first=False)   # step s + 1's events: queued before the host blocks on step s's result
+            fin.synchronize()                 # the caller reads this step's result
+            last = float(rh.sum())
+        return last
+
+    e2e_run(2)
     barrier()
+    t_e2e0 = time.perf_counter()
     e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0_.record()
-    for _ in range(a.steps):
-        e2e_step()
+    e2e_run(a.steps)
+    torch.cuda.current_stream(dev).wait_stream(comp_st)
     e1_.record()
     barrier()
-    ms_e2e = torch.tensor([e0_.elapsed_time(e1_)], device=dev, dtype=torch.float64)
+    wall_ms = (time.perf_counter() - t_e2e0) * 1e3
+    ms_e2e = torch.tensor([max(e0_.elapsed_time(e1_), wall_ms)], device=dev, dtype=torch.float64)  # events on another stream: trust the slower clock
     if world > 1:
         dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
     e2e_value = world * B * N * a.steps / (float(ms_e2e.item()) * 1e-3) / 1e9
@@ -288,7 +308,8 @@ def run_gpu_arm(a):
             "ms_per_step": ms_all / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32/f64->f32",
             "data": "synthetic", "config": config_dict(a, B),
             "e2e": {"value": e2e_value, "unit": "Gevents/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * 8,
-                    "note": f"PCIe-bound: 9 B/event over the host link, {n_groups} window groups double-buffered on 2 streams; the dense output stays on the GPU for the model"},
+                    "gpu_launches": e2e_launches,
+                    "note": f"PCIe-bound: 9 B/event over the host link; {n_groups} window groups per step, copy stream prefetching the next step's events; the dense output stays on the GPU for the model"},
             "gpu_launches": a.steps * KERNELS_PER_CALL,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_md_tile (per-tile reduction + finalise, writes the output)",
