@@ -435,7 +435,9 @@ __global__ void __launch_bounds__(TILE_THREADS, (PS::value.stride * TP * 4 <= 74
   int cur = blockIdx.x, nxt = blockIdx.x + (int)gridDim.x;
   if (cur >= n_tiles) return;
 
-  TileHdr h = md_load_hdr<SPLIT>(cur, g, TP, records, base, hist, wp);
+  // buckets are taken last window first: k_bin wrote the last windows' records most recently, so they are the ones
+  // still in L2 when this kernel starts
+  TileHdr h = md_load_hdr<SPLIT>(n_tiles - 1 - cur, g, TP, records, base, hist, wp);
   uint2 pre[PRE];
 #pragma unroll
   for (int j = 0; j < PRE; ++j) {
@@ -464,7 +466,7 @@ __global__ void __launch_bounds__(TILE_THREADS, (PS::value.stride * TP * 4 <= 74
     }
     const bool more = nxt < n_tiles;
     TileHdr hn = h;
-    if (more) hn = md_load_hdr<SPLIT>(nxt, g, TP, records, base, hist, wp);  // in flight during the atomics below
+    if (more) hn = md_load_hdr<SPLIT>(n_tiles - 1 - nxt, g, TP, records, base, hist, wp);  // in flight during the atomics below
     __syncthreads();
 
     if (!skip) {
