@@ -65,7 +65,7 @@ class ClockSampler:
     def __init__(self, uuid):
         self.p = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", uuid, f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", uuid, f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.p = None
@@ -200,16 +200,24 @@ def run_gpu_arm(a):
         if world > 1:
             dist.barrier()
 
-    for _ in range(max(a.warmup, 3)):
-        eb.ergo12(ev, H, W, out=out)
+    # clocks: nvidia-smi needs ~100 ms to start reporting, the timed region is ~15 ms - start it before the warm-up (the
+    # same work as the timed steps, so every sample is taken under load) and keep the GPU busy until the region ends
+    uuid = str(torch.cuda.get_device_properties(local).uuid)
+    uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+    eb.ergo12(ev, H, W, out=out)
     torch.cuda.synchronize()
     flags = eb.window_flags(ev)
     assert (flags == 0).all(), f"window flags {flags}"
+    sampler = ClockSampler(uuid) if rank == 0 else None
+    t_w = time.perf_counter()
+    n_w = 0
+    while n_w < max(a.warmup, 3) or time.perf_counter() - t_w < 0.25:
+        eb.ergo12(ev, H, W, out=out)
+        n_w += 1
+        if n_w % 8 == 0:
+            torch.cuda.synchronize()
 
     # ---- device-resident throughput, with per-kernel events ------------------------------------
-    uuid = str(torch.cuda.get_device_properties(local).uuid)
-    uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
-    sampler = ClockSampler(uuid) if rank == 0 else None
     _lib.profile_enable(a.steps)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -279,7 +287,8 @@ def run_gpu_arm(a):
             last = float(rh.sum())
         return last
 
-    e2e_run(2)
+    sampler2 = ClockSampler(uuid) if rank == 0 else None
+    e2e_run(max(2, min(40, int(0.25 / max(ms_all / a.steps * 8e-3, 1e-4)))))  # ~0.25 s of the same work while nvidia-smi starts
     barrier()
     t_e2e0 = time.perf_counter()
     e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -293,6 +302,13 @@ def run_gpu_arm(a):
     if world > 1:
         dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
     e2e_value = world * B * N * a.steps / (float(ms_e2e.item()) * 1e-3) / 1e9
+    if sampler2 is not None:  # merge the samples of both timed regions (the first one is only ~15 ms long)
+        c2 = sampler2.stop()
+        if clocks and c2.get("samples"):
+            n1, n2 = clocks.get("samples", 0), c2["samples"]
+            clocks = {"sm_mhz": c2["sm_mhz"] if n2 >= n1 else clocks["sm_mhz"], "sm_max_mhz": max(clocks["sm_max_mhz"] or 0, c2["sm_max_mhz"] or 0),
+                      "reasons": sorted(set(clocks["reasons"]) | set(c2["reasons"])), "samples": n1 + n2,
+                      "regions": {"device_resident": {"sm_mhz": clocks["sm_mhz"], "samples": n1}, "end_to_end": {"sm_mhz": c2["sm_mhz"], "samples": n2}}}
     h2d = int(sum(host[k].numel() * host[k].element_size() for k in host))
     e2e_launches = a.steps * n_groups * KERNELS_PER_CALL
 
@@ -304,7 +320,7 @@ def run_gpu_arm(a):
         achieved = alg / tile_avg_s / 1e9
         step_s = ms_all / a.steps * 1e-3
         line = {
-            "metric": METRIC, "value": value, "unit": "Gevents/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "metric": METRIC, "value": value, "unit": "Gevents/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "warmup_note": "warm-up runs at least --warmup steps and at least 0.25 s (clock sampler start-up)",
             "ms_per_step": ms_all / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32/f64->f32",
             "data": "synthetic", "config": config_dict(a, B),
             "e2e": {"value": e2e_value, "unit": "Gevents/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * 8,
