@@ -183,3 +183,34 @@ def test_value_layer_compiles_to_the_same_piecewise_linear_function():
         want = (h @ np.asarray(ws[-1], np.float64).T + np.asarray(bs[-1], np.float64))[:, 0]
         j = np.searchsorted(br, u, side="right")
         assert np.abs(sl[j] * u + ic[j] - want).max() <= 1e-12 * max(1.0, np.abs(want).max())
+
+
+def test_n_imagenet_host_helpers():
+    """pure host pieces of the N-ImageNet mirrors (imagenet.py:1002-1006, 258-262): no GPU needed"""
+    import torch
+    from event_representation_study_b200 import n_imagenet as N
+    ev = np.array([[3.0, 4.0, 0.25, -1.0], [5.0, 6.0, 0.5, 1.0]])
+    s = N.fix_events_training(ev.copy())
+    assert s.dtype.names == ("x", "y", "t", "p") and s.shape == (2,) and float(s["t"][1]) == 0.5 and float(s["p"][0]) == -1.0
+    fake = N._empty_guard(torch.zeros((0, 4)))
+    assert tuple(fake.shape) == (10, 4) and float(fake[:, 3].min()) == 1.0 and abs(float(fake[-1, 2]) - 0.9) < 1e-6
+    keep = torch.ones((3, 4))
+    assert N._empty_guard(keep) is keep
+
+
+def test_new_entry_points_validate_before_touching_cuda(L):
+    """argument checks of the round's new C entry points return EVREP_E* codes without a device"""
+    import ctypes
+    _lib = L
+    L = _lib.lib
+    assert L.evrep_gemm_workspace_bytes(0, 4, 4) == 0 and L.evrep_gemm_workspace_bytes(128, 128, 32) == 2 * 32768
+    assert L.evrep_gw_kl_workspace_bytes(0, 5) == 0 and L.evrep_gw_kl_workspace_bytes(100, 100) > 0
+    assert L.evrep_est_workspace_bytes(-1) == 0 and L.evrep_est_workspace_bytes(4) > 0
+    assert L.evrep_image_pipeline_batched(None, 1, 8, 8, 12, 16, 7, 0, 255.0, 1 / 255.0, 114.0, 1, None, None) == _lib.EINVAL   # unknown mode
+    assert L.evrep_image_pipeline_batched(None, 1, 8, 8, 12, 16, 0, 9, 255.0, 1 / 255.0, 114.0, 1, None, None) == _lib.EINVAL   # unknown interpolation
+    assert L.evrep_assignment_auction(None, 4, 1e-9, None, None, None) == _lib.EINVAL
+    d = ctypes.c_double(0.0)
+    assert L.evrep_gw_kl(None, 4, 4, None, 4, 4, 0.7, 10, 1e-9, 1e-9, 0, ctypes.byref(d), None, None, None, None, 0, None) == _lib.EINVAL  # null arrays
+    offs = (ctypes.c_int64 * 2)(0, 0)
+    assert L.evrep_filter_batched(None, None, None, 4, None, offs, 1, 8, 8, 9, 1.0, 1, 1, None, None, None, 0, None) == _lib.EINVAL   # unknown filter
+    assert L.evrep_est_quantize_batched(None, None, None, None, offs, 1, 8, 8, 1, None, None, None, 0, None, None, 0, None) == _lib.EINVAL  # C < 2
