@@ -190,10 +190,10 @@ def main():
         ev = batch(B, N, H, W, 9000)
         try:
             import numba
-            jit = {k: numba.njit(getattr(ofil, k)) for k in ("refractory_period", "contrast_threshold_control", "filter_events_resize")}
+            jit = {k: numba.njit(getattr(ofil, k)) for k in ("refractory_period", "contrast_threshold_control", "filter_events_resize", "background_activity_filter")}
             how = "the oracle's loops compiled with numba (what the reference does)"
         except Exception:
-            jit = {k: getattr(ofil, k) for k in ("refractory_period", "contrast_threshold_control", "filter_events_resize")}
+            jit = {k: getattr(ofil, k) for k in ("refractory_period", "contrast_threshold_control", "filter_events_resize", "background_activity_filter")}
             how = "the oracle's plain-Python loops (numba unavailable)"
         w = poisson_window(9000, N, H, W)
         xs, ys, ts, ps = w["x"].astype(np.int64), w["y"].astype(np.int64), w["t"].astype(np.int64), w["p"].astype(np.int8)
@@ -201,6 +201,7 @@ def main():
             ("refractory", 1000.0, (H, W), {}, lambda i: jit["refractory_period"](np.ones(N, np.bool_), xs, ys, ts, 1000.0, np.full((H, W), -np.inf))),
             ("contrast", 2.0, (H, W), {}, lambda i: jit["contrast_threshold_control"](np.zeros((H, W), np.int32), np.zeros(N, np.bool_), xs, ys, ps, 2.0)),
             ("resize", 0.0, (H // 2, W // 2), {"fx": 2, "fy": 2}, lambda i: jit["filter_events_resize"](xs, ys, ps, np.zeros(N, np.bool_), np.zeros((H // 2, W // 2), np.float32), 2, 2)),
+            ("background", 2000.0, (H, W), {"fx": 1}, lambda i: jit["background_activity_filter"](np.ones(N, np.bool_), np.full((H, W), -np.inf), xs, ys, ts, 2000.0, 1)),
         ]:
             st = eb.filter_state(kind, B, shape[0], shape[1])
             sec = timed(lambda: eb.filter_events(ev, shape[0], shape[1], kind, param, st, **kw), max(3, a.steps // 2))

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libevrep.so")
 OK, EINVAL, EWORKSPACE, ECUDA, EUNSUPPORTED = 0, -1, -2, -3, -4
 OP_MIXED_DENSITY, OP_EVENT_STACK, OP_TIME_SURFACE, OP_TORE, OP_VOXEL, OP_HISTOGRAM, OP_FILTER = 1, 2, 3, 4, 5, 6, 7
 FUNCS = {"timestamp": 0, "polarity": 1, "count": 2, "timestamp_pos": 3, "timestamp_neg": 4, "count_pos": 5, "count_neg": 6}
-AGGS = {"sum": 0, "mean": 1, "max": 2, "variance": 3}
+AGGS = {"sum": 0, "mean": 1, "max": 2, "variance": 3, "min": 4}
 STACKING = {"SBN": 0, "SBT": 1}
 VOXEL_TONIC, VOXEL_EVLICIOUS, VOXEL_GWD = 0, 1, 2
 K_COUNT, K_SCAN, K_BIN, K_TILE = 0, 1, 2, 3
@@ -46,6 +46,8 @@ SIGNATURES = {
     "evrep_gw_kl_workspace_bytes": (_sz, [_i, _i]),
     "evrep_gw_kl": (_i, [_vp, _i, _i, _vp, _i, _i, _d, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "evrep_filter_batched": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _d, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "evrep_filter_background_workspace_bytes": (_sz, [_i, _i64, _i, _i, _i, _i]),
+    "evrep_filter_background_batched": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _d, _i, _vp, _vp, _vp, _sz, _vp]),
     "evrep_est_workspace_bytes": (_sz, [_i]),
     "evrep_est_quantize_batched": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "evrep_assignment_auction": (_i, [_vp, _i, _d, _vp, _vp, _vp]),

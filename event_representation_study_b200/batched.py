@@ -365,13 +365,13 @@ def assignment_auction(cost, eps_rel=1e-9):
     return sigma, {"rounds": r, "bids": b, "status": status}
 
 
-FILTERS = {"refractory": 0, "contrast": 1, "resize": 2}
-_FILTER_STATE_DTYPE = {"refractory": torch.float64, "contrast": torch.int32, "resize": torch.float32}
+FILTERS = {"refractory": 0, "contrast": 1, "resize": 2, "background": 3}
+_FILTER_STATE_DTYPE = {"refractory": torch.float64, "contrast": torch.int32, "resize": torch.float32, "background": torch.float64}
 
 
 def filter_state(kind, B, H, W, device="cuda"):
-    """Fresh state for `filter_events`: -inf last timestamps (refractory), zero activity (contrast) / change map (resize)."""
-    fill = float("-inf") if kind == "refractory" else 0
+    """Fresh state for `filter_events`: -inf last timestamps (refractory, background), zero activity (contrast) / change map (resize)."""
+    fill = float("-inf") if kind in ("refractory", "background") else 0
     return torch.full((B, H, W), fill, dtype=_FILTER_STATE_DTYPE[kind], device=device)
 
 
@@ -379,7 +379,8 @@ def filter_events(ev, H, W, kind, param=0.0, state=None, fx=1, fy=1):
     """ev-licious' per-pixel stateful filters over a batch of streams (utils.py:143-158, 184-200) -> (mask, state):
     mask is a uint8 CUDA tensor with one entry per event (1 = the event passes), state the (B, H, W) per-pixel state,
     updated in place, to pass to the next call of the same streams.  kind: "refractory" (param = period), "contrast"
-    (param = factor) or "resize" (H, W = the change-map size, fx, fy = cell size)."""
+    (param = factor), "resize" (H, W = the change-map size, fx, fy = cell size) or "background" (utils.py:169-178; param =
+    depth_us, fx = radius; the polarities are not read)."""
     B = len(ev.offsets) - 1
     dev = ev.x.device
     if state is None:
@@ -389,8 +390,17 @@ def filter_events(ev, H, W, kind, param=0.0, state=None, fx=1, fy=1):
     total = int(ev.offsets[-1])
     mask = torch.empty(max(total, 1), dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev).cuda_stream
-    ws = _workspace(dev, stream, lib.evrep_workspace_bytes(7, B, total, H, W, 1))
     offs = np.ascontiguousarray(ev.offsets, np.int64)
+    if kind == "background":
+        radius = int(fx)
+        need = lib.evrep_filter_background_workspace_bytes(B, total, H, W, radius, ev.t.element_size())
+        if need == 0:
+            raise ValueError(f"background-activity filter: unsupported radius {radius} (1..4) or sizes")
+        ws = _workspace(dev, stream, need)
+        check(lib.evrep_filter_background_batched(ev.x.data_ptr(), ev.y.data_ptr(), ev.t.data_ptr(), ev.t.element_size(), offs.ctypes.data, B, H, W,
+                                                  float(param), radius, state.data_ptr(), mask.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+        return mask[:total], state
+    ws = _workspace(dev, stream, lib.evrep_workspace_bytes(7, B, total, H, W, 1))
     check(lib.evrep_filter_batched(ev.x.data_ptr(), ev.y.data_ptr(), ev.t.data_ptr(), ev.t.element_size(), ev.p.data_ptr(), offs.ctypes.data,
                                    B, H, W, FILTERS[kind], float(param), int(fx), int(fy), state.data_ptr(), mask.data_ptr(), ws.data_ptr(),
                                    ws.numel(), stream))

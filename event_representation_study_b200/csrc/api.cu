@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <new>
+#include <vector>
 
 #include "evrep_common.cuh"
 
@@ -456,6 +457,84 @@ int evrep_filter_batched(const uint16_t* x, const uint16_t* y, const void* t, in
   EVREP_CUDA_OK(cudaMemsetAsync(mask, 0, (size_t)total, (cudaStream_t)stream));
   EVREP_TRY(run_binning(ev, win_offsets, g, ws, REC_IDX, 0, nullptr, (cudaStream_t)stream));
   return launch_filter_tile(g, ws, ev, filter, param, state, mask, (cudaStream_t)stream);
+  EVREP_GUARD_END
+}
+
+// workspace of the background-activity filter: [binning workspace of the expanded stream][x_e][y_e][t_e][p_e][mask_e]
+namespace {
+struct BaCarve {
+  size_t bin_bytes, off_x, off_y, off_t, off_p, off_m, bytes;
+};
+bool ba_carve(int B, int64_t total, int H, int W, int radius, int t_bytes, BaCarve* c) {
+  if (B < 0 || total < 0 || H < 1 || W < 1 || radius < 1 || radius > 4 || (t_bytes != 4 && t_bytes != 8)) return false;
+  const int64_t K = 4 * (int64_t)radius * radius;
+  if (total > ((int64_t)1 << 40) / K) return false;
+  const int64_t ne = total * K;
+  c->bin_bytes = evrep_workspace_bytes(EVREP_OP_FILTER, B, ne, H, W, 1);
+  if (!c->bin_bytes) return false;
+  size_t o = evrep::align_up(c->bin_bytes, 256);
+  c->off_x = o; o = evrep::align_up(o + sizeof(uint16_t) * (size_t)ne, 256);
+  c->off_y = o; o = evrep::align_up(o + sizeof(uint16_t) * (size_t)ne, 256);
+  c->off_t = o; o = evrep::align_up(o + (size_t)t_bytes * (size_t)ne, 256);
+  c->off_p = o; o = evrep::align_up(o + (size_t)ne, 256);
+  c->off_m = o; o = evrep::align_up(o + (size_t)ne, 256);
+  c->bytes = o;
+  return true;
+}
+}  // namespace
+
+size_t evrep_filter_background_workspace_bytes(int B, int64_t total_events, int H, int W, int radius, int t_bytes) {
+  BaCarve c;
+  return ba_carve(B, total_events, H, W, radius, t_bytes, &c) ? c.bytes : 0;
+}
+
+int evrep_filter_background_batched(const uint16_t* x, const uint16_t* y, const void* t, int t_bytes, const int64_t* win_offsets, int B, int H,
+                                    int W, double depth_us, int radius, double* state, unsigned char* mask, void* workspace,
+                                    size_t workspace_bytes, evrep_stream_t stream) {
+  EVREP_GUARD_BEGIN
+  Events ev;
+  int64_t total = 0, n_max = 0;
+  static const int8_t dummy_p = 0;  // the filter never reads polarities
+  EVREP_TRY(check_events(x, y, t, t_bytes, &dummy_p, win_offsets, B, mask, &ev, &total, &n_max));
+  if (radius < 1 || radius > 4) { set_error("background-activity filter: radius must be in 1..4, got %d", radius); return EVREP_EINVAL; }
+  if (B == 0) return EVREP_OK;
+  if (!state) { set_error("null state"); return EVREP_EINVAL; }
+  const int K = 4 * radius * radius;
+  if (n_max * K > (int64_t)4096 * SUPER - 16) {
+    set_error("background-activity filter: at most %lld events per window at radius %d", (long long)(((int64_t)4096 * SUPER - 16) / K), radius);
+    return EVREP_EUNSUPPORTED;
+  }
+  BaCarve c;
+  if (!ba_carve(B, total, H, W, radius, t_bytes, &c)) { set_error("sensor size %d x %d or batch unsupported", W, H); return EVREP_EINVAL; }
+  if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) { set_error("workspace must be non-null and 256-byte aligned"); return EVREP_EWORKSPACE; }
+  if (c.bytes > workspace_bytes) { set_error("workspace too small: need %zu bytes, got %zu", c.bytes, workspace_bytes); return EVREP_EWORKSPACE; }
+  for (int b = 0; b < B; ++b)
+    if (win_offsets[b + 1] < win_offsets[b] || win_offsets[b] < 0) { set_error("win_offsets must be non-decreasing and non-negative"); return EVREP_EINVAL; }
+  unsigned char* wsb = (unsigned char*)workspace;
+  uint16_t* xe = (uint16_t*)(wsb + c.off_x);
+  uint16_t* ye = (uint16_t*)(wsb + c.off_y);
+  void* te = wsb + c.off_t;
+  int8_t* pe = (int8_t*)(wsb + c.off_p);
+  unsigned char* me = wsb + c.off_m;
+  const int64_t ne = total * K;
+  std::vector<int64_t> offs_e((size_t)B + 1);
+  for (int b = 0; b <= B; ++b) offs_e[(size_t)b] = win_offsets[b] * K;
+  cudaStream_t st = (cudaStream_t)stream;
+  EVREP_TRY(launch_ba_expand(ev, total, H, W, radius, xe, ye, te, pe, st));
+  Events eve;
+  eve.x = xe; eve.y = ye; eve.t = te; eve.t_bytes = t_bytes; eve.p = pe;
+  Geom g;
+  memset(&g, 0, sizeof(g));
+  EVREP_TRY(choose_tile(H, W, 96, &g));
+  g.B = B;
+  g.total = ne;
+  Workspace ws;
+  EVREP_TRY(carve_checked(workspace, c.bin_bytes, B, ne, g.Tb, &ws));
+  EVREP_CUDA_OK(cudaMemsetAsync(me, 0, (size_t)ne, st));
+  EVREP_CUDA_OK(cudaMemsetAsync(mask, 0, (size_t)total, st));
+  EVREP_TRY(run_binning(eve, offs_e.data(), g, ws, REC_IDX, 0, nullptr, st));
+  EVREP_TRY(launch_filter_tile(g, ws, eve, EVREP_FILTER_BACKGROUND, depth_us, state, me, st));
+  return launch_ba_collect(me, total, K, mask, st);
   EVREP_GUARD_END
 }
 

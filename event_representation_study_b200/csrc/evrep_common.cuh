@@ -147,7 +147,7 @@ void prof_end(int kernel_id, cudaStream_t stream);
 // ------------------------------------------------------------------------------------------------
 // Mixed-density accumulator plan (built on the host from the (window, function, aggregation) tuple)
 // ------------------------------------------------------------------------------------------------
-enum { G_CNT = 1, G_PRES = 2, G_MAX = 4, G_ST = 8, G_ST2 = 16 };
+enum { G_CNT = 1, G_PRES = 2, G_MAX = 4, G_ST = 8, G_ST2 = 16, G_MIN = 32 };
 constexpr int MD_MAX_GROUPS = 32;
 
 struct MdGroup {   // one (window, polarity class) pair that some channel reads
@@ -156,6 +156,7 @@ struct MdGroup {   // one (window, polarity class) pair that some channel reads
   uint8_t w_cnt, w_max, w_st, w_st2;  // accumulator word indices
   uint8_t pres_bit;
   uint8_t cnt_shift;  // packed plans keep two 16-bit counters per word: 0 or 16
+  uint8_t w_min;      // earliest timestamp, kept as the maximum of ~t (0 = untouched)
 };
 struct MdChan {
   uint8_t func, agg, win, valid;
@@ -199,6 +200,9 @@ int launch_tore_tile(const Geom& g, const Workspace& ws, int k, float* out, cuda
 int launch_order_ops_fused(const Geom& g, const Workspace& ws, double tau, float* out_es, float* out_ts, float* out_tore, cudaStream_t stream);
 int launch_filter_tile(const Geom& g, const Workspace& ws, const Events& ev, int filter, double param, void* state, unsigned char* mask,
                        cudaStream_t stream);
+
+int launch_ba_expand(const Events& ev, int64_t total, int H, int W, int radius, uint16_t* xe, uint16_t* ye, void* te, int8_t* pe, cudaStream_t stream);
+int launch_ba_collect(const unsigned char* mask_e, int64_t total, int K, unsigned char* mask, cudaStream_t stream);
 
 int launch_voxel(const Events& ev, const int64_t* win_offsets_host, const Geom& g, const Workspace& ws, int flavour,
                  int n_bins, int normalize, const int64_t* t0_t1_host, float* out, cudaStream_t stream);

@@ -4,6 +4,13 @@
 //   _contrast_threshold_control :184-191  activity[y, x] += p; keep and reset when |activity| >= factor
 //   _filter_events_resize       :143-158  per fx x fy cell: change += p / (fx fy); keep when |change| >= 1, then change -= p
 // Each is a state machine per pixel (or cell) over that pixel's events IN STREAM ORDER; pixels are independent.
+//   _background_activity_filter :169-178  reads timestamps[y, x], then writes t into the (2 radius)^2 block
+//                                         [y - radius, y + radius) x [x - radius, x + radius).  Pixels are NOT independent
+//                                         there, but every pixel's own sequence of reads and writes is: the stream is
+//                                         expanded into one record per written pixel (k_ba_expand; the event's own pixel
+//                                         first, flagged "read, then write"; writes clipped by the sensor border become
+//                                         repeated writes of the own pixel) and the expanded stream runs through the same
+//                                         per-pixel machine with state = the last timestamp written.
 //
 // On the GPU the events are bucketed by tile with key = stream index (binning.cu, REC_IDX); a CTA owns one (window,
 // tile) bucket, takes it in segments made of whole super-chunk runs (runs of different super-chunks are in stream
@@ -34,6 +41,8 @@ template <>
 struct FilterState<EVREP_FILTER_CONTRAST> { using type = int32_t; };
 template <>
 struct FilterState<EVREP_FILTER_RESIZE> { using type = float; };
+template <>
+struct FilterState<EVREP_FILTER_BACKGROUND> { using type = double; };
 
 template <int FILTER, typename TT>
 __global__ void __launch_bounds__(FT_THREADS) k_filter_tile(const uint2* __restrict__ records, const uint32_t* __restrict__ base,
@@ -134,6 +143,10 @@ __global__ void __launch_bounds__(FT_THREADS) k_filter_tile(const uint2* __restr
           const double tt = (double)t[w.start + idx];
           keep = !(tt - (double)st < param);
           if (keep) st = (ST)tt;
+        } else if (FILTER == EVREP_FILTER_BACKGROUND) {  // pc == 1: the event's own pixel (read, then write); else a neighbour's write
+          const double tt = (double)t[w.start + idx];
+          keep = pc == 1u && !((double)st > 0.0 && tt - (double)st > param);
+          st = (ST)tt;
         } else if (FILTER == EVREP_FILTER_CONTRAST) {
           st = (ST)((int32_t)st + pv);
           keep = fabs((double)(int32_t)st) >= param;
@@ -177,14 +190,73 @@ int launch_filter_tile(const Geom& g, const Workspace& ws, const Events& ev, int
     switch (filter) {
       case EVREP_FILTER_REFRACTORY: return launch_filter<EVREP_FILTER_REFRACTORY, int32_t>(g, ws, ev, param, state, mask, stream);
       case EVREP_FILTER_CONTRAST: return launch_filter<EVREP_FILTER_CONTRAST, int32_t>(g, ws, ev, param, state, mask, stream);
+      case EVREP_FILTER_BACKGROUND: return launch_filter<EVREP_FILTER_BACKGROUND, int32_t>(g, ws, ev, param, state, mask, stream);
       default: return launch_filter<EVREP_FILTER_RESIZE, int32_t>(g, ws, ev, param, state, mask, stream);
     }
   }
   switch (filter) {
     case EVREP_FILTER_REFRACTORY: return launch_filter<EVREP_FILTER_REFRACTORY, int64_t>(g, ws, ev, param, state, mask, stream);
     case EVREP_FILTER_CONTRAST: return launch_filter<EVREP_FILTER_CONTRAST, int64_t>(g, ws, ev, param, state, mask, stream);
+    case EVREP_FILTER_BACKGROUND: return launch_filter<EVREP_FILTER_BACKGROUND, int64_t>(g, ws, ev, param, state, mask, stream);
     default: return launch_filter<EVREP_FILTER_RESIZE, int64_t>(g, ws, ev, param, state, mask, stream);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// background-activity filter: expansion of the stream into per-pixel write records, and the mask read-back
+// ---------------------------------------------------------------------------------------------
+// Record k of event i (K = (2 radius)^2 records per event, expanded index K i + k): k = 0 is the event's own pixel with
+// p = +1 ("read the state, decide, then write t"); k >= 1 walks the other offsets of the block with p = -1 ("write t").
+// An offset outside the sensor is what numpy's slice clips away: it becomes another write of t to the own pixel, which
+// sorts after record 0 and changes nothing.  Events outside the sensor get coordinates the binning drops.
+template <typename TT>
+__global__ void __launch_bounds__(256) k_ba_expand(const uint16_t* __restrict__ x, const uint16_t* __restrict__ y, const TT* __restrict__ t,
+                                                   int64_t total, int H, int W, int radius, uint16_t* __restrict__ xe,
+                                                   uint16_t* __restrict__ ye, TT* __restrict__ te, int8_t* __restrict__ pe) {
+  const int side = 2 * radius, K = side * side, own = radius * side + radius;
+  const int64_t n = total * K;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = j / K;
+    const int k = (int)(j - i * K);
+    const int xi = (int)__ldg(x + i), yi = (int)__ldg(y + i);
+    int px = xi, py = yi;
+    if (xi >= W || yi >= H) {
+      px = py = 0xffff;
+    } else if (k > 0) {
+      const int o = (k - 1 < own) ? k - 1 : k;
+      const int qx = xi + (o % side) - radius, qy = yi + (o / side) - radius;
+      if (qx >= 0 && qx < W && qy >= 0 && qy < H) { px = qx; py = qy; }
+    }
+    xe[j] = (uint16_t)px;
+    ye[j] = (uint16_t)py;
+    te[j] = __ldg(t + i);
+    pe[j] = k == 0 ? (int8_t)1 : (int8_t)-1;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_ba_collect(const unsigned char* __restrict__ mask_e, int64_t total, int K, unsigned char* __restrict__ mask) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) mask[i] = mask_e[i * K];
+}
+
+int launch_ba_expand(const Events& ev, int64_t total, int H, int W, int radius, uint16_t* xe, uint16_t* ye, void* te, int8_t* pe, cudaStream_t stream) {
+  if (total == 0) return EVREP_OK;
+  const int K = 4 * radius * radius;
+  const int64_t n = total * K;
+  const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 32);
+  if (ev.t_bytes == 4)
+    k_ba_expand<int32_t><<<grid, 256, 0, stream>>>(ev.x, ev.y, (const int32_t*)ev.t, total, H, W, radius, xe, ye, (int32_t*)te, pe);
+  else
+    k_ba_expand<int64_t><<<grid, 256, 0, stream>>>(ev.x, ev.y, (const int64_t*)ev.t, total, H, W, radius, xe, ye, (int64_t*)te, pe);
+  EVREP_CUDA_OK(cudaGetLastError());
+  return EVREP_OK;
+}
+
+int launch_ba_collect(const unsigned char* mask_e, int64_t total, int K, unsigned char* mask, cudaStream_t stream) {
+  if (total == 0) return EVREP_OK;
+  const unsigned grid = (unsigned)std::min<int64_t>((total + 255) / 256, 148 * 32);
+  k_ba_collect<<<grid, 256, 0, stream>>>(mask_e, total, K, mask);
+  EVREP_CUDA_OK(cudaGetLastError());
+  return EVREP_OK;
 }
 
 }  // namespace evrep

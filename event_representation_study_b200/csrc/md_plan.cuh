@@ -49,7 +49,7 @@ constexpr int md_plan_build(const int8_t* win, const int8_t* func, const int8_t*
     ch.g_main = ch.g_pos = ch.g_neg = ch.g_oth = -1;
     // an unknown window / function / aggregation raises inside the reference's make_stack and is
     // swallowed into an all-zero channel (mixed_density_event_stack.py:120-127)
-    if (wi < 0 || wi >= n_win || func[c] < 0 || func[c] > EVREP_FUNC_COUNT_NEG || agg[c] < 0 || agg[c] > EVREP_AGG_VARIANCE) {
+    if (wi < 0 || wi >= n_win || func[c] < 0 || func[c] > EVREP_FUNC_COUNT_NEG || agg[c] < 0 || agg[c] > EVREP_AGG_MIN) {
       ch.valid = 0;
       continue;
     }
@@ -69,9 +69,9 @@ constexpr int md_plan_build(const int8_t* win, const int8_t* func, const int8_t*
       bool count_needed = false;
       if (is_count) {
         if (a == EVREP_AGG_SUM) count_needed = true;
-        else if (a != EVREP_AGG_VARIANCE) main_need = G_PRES;  // mean / max of ones: "touched"; variance of a constant is 0
+        else if (a != EVREP_AGG_VARIANCE) main_need = G_PRES;  // mean / max / min of ones: "touched"; variance of a constant is 0
       } else {
-        main_need = a == EVREP_AGG_SUM ? (G_ST | G_PRES) : a == EVREP_AGG_MEAN ? G_ST : a == EVREP_AGG_MAX ? G_MAX : (G_ST | G_ST2);
+        main_need = a == EVREP_AGG_SUM ? (G_ST | G_PRES) : a == EVREP_AGG_MEAN ? G_ST : a == EVREP_AGG_MAX ? G_MAX : a == EVREP_AGG_MIN ? G_MIN : (G_ST | G_ST2);
         count_needed = (a == EVREP_AGG_MEAN || a == EVREP_AGG_VARIANCE);
       }
       if (count_needed) {
@@ -99,7 +99,7 @@ constexpr int md_plan_build(const int8_t* win, const int8_t* func, const int8_t*
   for (int g = 0; g < P.G; ++g) {
     MdGroup& G = P.grp[g];
     if (G.flags & G_CNT) G.flags &= (uint8_t)~G_PRES;                          // a count subsumes the presence bit
-    if ((G.flags & G_PRES) && (G.flags & G_MAX)) G.flags &= (uint8_t)~G_PRES;  // so does a latest-timestamp word
+    if ((G.flags & G_PRES) && (G.flags & (G_MAX | G_MIN))) G.flags &= (uint8_t)~G_PRES;  // so does a latest / earliest-timestamp word
     if (G.flags & G_PRES) any_pres = true;
   }
   if (any_pres) P.w_pres = words++;
@@ -119,6 +119,7 @@ constexpr int md_plan_build(const int8_t* win, const int8_t* func, const int8_t*
     MdGroup& G = P.grp[g];
     if (G.flags & G_PRES) G.pres_bit = (uint8_t)pres_bits++;
     if (G.flags & G_MAX) G.w_max = (uint8_t)words++;
+    if (G.flags & G_MIN) G.w_min = (uint8_t)words++;
     if (G.flags & G_ST) { G.w_st = (uint8_t)words; words += P.nl1; }
     if (G.flags & G_ST2) { G.w_st2 = (uint8_t)words; words += P.nl2; }
     if (words > 250) return 1;

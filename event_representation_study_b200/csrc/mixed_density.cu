@@ -81,6 +81,7 @@ __device__ __forceinline__ uint32_t md_count(const MdPlan& P, const MdChan& ch, 
   const MdGroup& G = P.grp[ch.g_main];
   if (G.flags & G_CNT) return md_cnt(P, G, a);
   if (G.flags & G_MAX) return a[G.w_max] != 0u;
+  if (G.flags & G_MIN) return a[G.w_min] != 0u;
   if (G.flags & G_PRES) return (a[P.w_pres] >> G.pres_bit) & 1u;
   return 0u;
 }
@@ -113,6 +114,7 @@ __device__ __forceinline__ float md_value(const MdPlan& P, const MdChan& ch, con
       const unsigned long long num = (unsigned long long)(uint32_t)(c1 + cm) * (uint32_t)call - (unsigned long long)(dd * dd);
       return __fdividef(__ull2float_rn(num), __ull2float_rn((unsigned long long)(uint32_t)call * (uint32_t)call));
     }
+    if (ch.agg == EVREP_AGG_MIN) return cm > 0 ? -1.f : (call - c1 - cm > 0 ? 0.f : 1.f);  // min of the raw polarities
     return c1 > 0 ? 1.f : (call - c1 - cm > 0 ? 0.f : -1.f);  // max of the raw polarities
   }
   const bool is_count = (ch.func == EVREP_FUNC_COUNT || ch.func == EVREP_FUNC_COUNT_POS || ch.func == EVREP_FUNC_COUNT_NEG);
@@ -125,6 +127,10 @@ __device__ __forceinline__ float md_value(const MdPlan& P, const MdChan& ch, con
   if (ch.agg == EVREP_AGG_MAX) {
     const uint32_t v = a[G.w_max] - 1u;
     return (v == delta_u && delta_u) ? 1.f : (float)v * inv_delta;  // the window's last event maps to exactly 1
+  }
+  if (ch.agg == EVREP_AGG_MIN) {
+    const uint32_t v = ~a[G.w_min];
+    return (v == delta_u && delta_u) ? 1.f : (float)v * inv_delta;
   }
   // sum of t: below 2^63 (fewer than 2^32 events of t < 2^31), exact in 64-bit integers
   unsigned long long sti = a[G.w_st + P.nl1 - 1];
@@ -199,6 +205,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_md_tile(const uint2* __restric
       if (G.flags & G_CNT) atomicAdd(a + G.w_cnt, 1u << G.cnt_shift);
       if (G.flags & G_PRES) pres |= 1u << G.pres_bit;
       if (G.flags & G_MAX) atomicMax(a + G.w_max, tt + 1u);
+      if (G.flags & G_MIN) atomicMax(a + G.w_min, ~tt);  // tt < 2^31: never 0
       if (G.flags & G_ST) {
         uint32_t v = tt;
         for (int l = 0; l < P.nl1 && v; ++l, v >>= P.lw) {

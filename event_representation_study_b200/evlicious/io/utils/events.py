@@ -41,6 +41,11 @@ class Events:
     def __len__(self):
         return len(self.x)
 
+    def __getitem__(self, item):
+        """events.py:60-67: a copy of the selected events (mask, index array or slice)"""
+        return Events(x=self._x[item].copy(), y=self._y[item].copy(), t=self.t[item].copy(), p=self.p[item].copy(), width=self.width,
+                      height=self.height, divider=self.divider)
+
     def to_dict(self, format="xytp"):
         return {k: getattr(self, k) for k in format}
 

@@ -35,7 +35,7 @@ def events_to_voxel_grid_cuda(events, num_bins, normalize=True, t0_us=None, t1_u
         return _grid(events, num_bins, normalize, t0_us, t1_us).to(device)
 
 
-# ---- stateful per-pixel filters (reference :143-158, 184-200): same positional signatures, arrays updated in place ----
+# ---- stateful per-pixel filters (reference :143-158, 169-200): same positional signatures, arrays updated in place ----
 def _run_filter(kind, x, y, t, p, state_np, param):
     H, W = state_np.shape
     n = len(x)
@@ -55,6 +55,21 @@ def _refractory_period(mask, x, y, t, period, last_timestamp):
     """utils.py:193-200: mask[i] = False where t[i] - last_timestamp[y, x] < period, else last_timestamp[y, x] = t[i]"""
     keep = _run_filter("refractory", x, y, t, None, last_timestamp, period)
     mask[~keep] = False
+    return mask
+
+
+def _background_activity_filter(mask, timestamps, x, y, t, depth_us, radius=1):
+    """utils.py:169-178: mask[i] = not (timestamps[y, x] > 0 and t - timestamps[y, x] > depth_us), then the block
+    timestamps[y - radius : y + radius, x - radius : x + radius] = t"""
+    H, W = timestamps.shape
+    n = len(x)
+    if n == 0:
+        return mask
+    ev = one_window(np.asarray(x), np.asarray(y), np.asarray(t), np.ones(n, np.int8), H, W)
+    st = torch.from_numpy(np.ascontiguousarray(timestamps, dtype=np.float64)).to(ev.x.device)[None].contiguous()
+    keep, st = eb.filter_events(ev, H, W, "background", float(depth_us), st, fx=int(radius))
+    timestamps[...] = st[0].cpu().numpy()
+    mask[...] = keep.cpu().numpy().astype(bool)
     return mask
 
 

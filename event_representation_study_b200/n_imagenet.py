@@ -131,17 +131,23 @@ def reshape_then_time_surface(event_tensor, augment=None, **kwargs):
 #   bincount of positive / negative events          = (count_pos | count_neg, sum)
 #   scatter_max of (t - t_first) / (t_last - t_first) = (timestamp_pos | timestamp_neg, max)   (untouched pixels 0 in both)
 # Timestamps arrive as float seconds; only their position inside the window matters, so they go onto a 2^30 integer
-# grid first (error < 1e-9 of the window).  scatter_min (reshape_then_acc_time) and the sorted / DiST variants are not built.
+# grid first (error < 1e-9 of the window).
+#   scatter_min of the same normalised times          = (timestamp_pos | timestamp_neg, min)   (EVREP_AGG_MIN)
+#   "some event touched the pixel" (reshape_then_flat*) = (count | count_pos | count_neg, max)
+# The sorted / DiST variants (reshape_then_acc_sort, _acc_intensity, _acc_adj_sort, imagenet.py:513-999) are not built.
 # ---------------------------------------------------------------------------------------------------------------------
-def _window_reduce(event_tensor, H, W, functions, aggregations):
+def _window_reduce(event_tensor, H, W, functions, aggregations, need_time=True):
     from . import batched as eb
     from ._single import one_window
     ev_np = event_tensor.numpy() if torch.is_tensor(event_tensor) else np.asarray(event_tensor)
-    t = ev_np[:, 2].astype(np.float64)
-    span = float(t[-1] - t[0])
-    if not (span > 0 and np.all(np.diff(t) >= 0)):
-        raise ValueError("the N-ImageNet representations on the GPU need time-sorted events with t[-1] > t[0]")
-    ti = np.rint((t - t[0]) / span * float(2**30 - 2)).astype(np.int64)
+    if need_time:
+        t = ev_np[:, 2].astype(np.float64)
+        span = float(t[-1] - t[0])
+        if not (span > 0 and np.all(np.diff(t) >= 0)):
+            raise ValueError("the N-ImageNet representations on the GPU need time-sorted events with t[-1] > t[0]")
+        ti = np.rint((t - t[0]) / span * float(2**30 - 2)).astype(np.int64)
+    else:  # presence planes: the timestamps are never read (imagenet.py:397-438)
+        ti = np.arange(len(ev_np), dtype=np.int64)
     p = ev_np[:, 3]
     if np.any(p == 0):
         raise ValueError("polarities must be -1 / +1 (imagenet.py splits on p > 0 / p < 0)")
@@ -199,4 +205,79 @@ def reshape_then_acc_count_only(event_tensor, augment=None, **kwargs):
     H = kwargs.get("height", IMAGE_H)
     W = kwargs.get("width", IMAGE_W)
     rep = _window_reduce(event_tensor, H, W, ["count"], ["sum"])
+    return rep.permute(2, 0, 1).float().cpu()
+
+
+def reshape_then_acc_time(event_tensor, augment=None, **kwargs):
+    """imagenet.py:213-247 -> (4, H, W): earliest / latest positive time, earliest / latest negative time"""
+    if augment is not None:
+        event_tensor = augment(event_tensor)
+    H = kwargs.get("height", IMAGE_H)
+    W = kwargs.get("width", IMAGE_W)
+    rep = _window_reduce(event_tensor, H, W, ["timestamp_pos", "timestamp_pos", "timestamp_neg", "timestamp_neg"], ["min", "max", "min", "max"])
+    return rep.permute(2, 0, 1).float().cpu()
+
+
+def reshape_then_acc_all(event_tensor, augment=None, **kwargs):
+    """imagenet.py:346-394 -> (6, H, W): counts, latest times, earliest times (positive, negative each).  An empty sample
+    gives zeros of the DEFAULT size, whatever height / width say (imagenet.py:353-354)."""
+    if augment is not None:
+        event_tensor = augment(event_tensor)
+    if event_tensor.shape[0] == 0:
+        return torch.zeros([6, IMAGE_H, IMAGE_W])
+    H = kwargs.get("height", IMAGE_H)
+    W = kwargs.get("width", IMAGE_W)
+    rep = _window_reduce(event_tensor, H, W, ["count_pos", "count_neg", "timestamp_pos", "timestamp_neg", "timestamp_pos", "timestamp_neg"],
+                         ["sum", "sum", "max", "max", "min", "min"])
+    return rep.permute(2, 0, 1).float().cpu()
+
+
+def reshape_then_acc_time_pol(event_tensor, augment=None, **kwargs):
+    """imagenet.py:475-510 -> (2, H, W): latest positive time, latest negative time"""
+    if augment is not None:
+        event_tensor = augment(event_tensor)
+    event_tensor = _empty_guard(event_tensor)
+    H = kwargs.get("height", IMAGE_H)
+    W = kwargs.get("width", IMAGE_W)
+    rep = _window_reduce(event_tensor, H, W, ["timestamp_pos", "timestamp_neg"], ["max", "max"])
+    return rep.permute(2, 0, 1).float().cpu()
+
+
+EXP_TAU = 0.3  # imagenet.py:20
+
+
+def reshape_then_acc_exp(event_tensor, augment=None, **kwargs):
+    """imagenet.py:441-472 -> (2, H, W): exp(-(1 - latest time) / EXP_TAU) per polarity; untouched pixels count as time 0,
+    like the reference (the exponential is taken of the whole scatter_max plane).  The exponential is an elementwise
+    epilogue on the GPU tensor."""
+    if augment is not None:
+        event_tensor = augment(event_tensor)
+    H = kwargs.get("height", IMAGE_H)
+    W = kwargs.get("width", IMAGE_W)
+    rep = _window_reduce(event_tensor, H, W, ["timestamp_pos", "timestamp_neg"], ["max", "max"])
+    rep = torch.exp(-(1 - rep.double()) / EXP_TAU)
+    return rep.permute(2, 0, 1).float().cpu()
+
+
+def reshape_then_flat(event_tensor, augment=None, **kwargs):
+    """imagenet.py:397-413 -> (1, H, W): 1 where any event fell (the reference augments AFTER reading the sizes)"""
+    H = kwargs.get("height", IMAGE_H)
+    W = kwargs.get("width", IMAGE_W)
+    if augment is not None:
+        event_tensor = augment(event_tensor)
+    if len(event_tensor) == 0:
+        return torch.zeros([1, H, W])
+    rep = _window_reduce(event_tensor, H, W, ["count"], ["max"], need_time=False)
+    return rep.permute(2, 0, 1).float().cpu()
+
+
+def reshape_then_flat_pol(event_tensor, augment=None, **kwargs):
+    """imagenet.py:416-438 -> (2, H, W): 1 where a positive / a negative event fell"""
+    H = kwargs.get("height", IMAGE_H)
+    W = kwargs.get("width", IMAGE_W)
+    if augment is not None:
+        event_tensor = augment(event_tensor)
+    if len(event_tensor) == 0:
+        return torch.zeros([2, H, W])
+    rep = _window_reduce(event_tensor, H, W, ["count_pos", "count_neg"], ["max", "max"], need_time=False)
     return rep.permute(2, 0, 1).float().cpu()

@@ -33,6 +33,8 @@
  *   evrep_gemm_nt_3xtf32         the tensor product constC - hC1 T hC2^T inside that solve (POT ot/gromov tensor_product)
  *   evrep_filter_batched         ev-licious/src/evlicious/tools/utils.py:143-158, 184-200 (_filter_events_resize,
  *                                _contrast_threshold_control, _refractory_period) as used by tools/filters.py:57-109
+ *   evrep_filter_background_batched  ev-licious/src/evlicious/tools/utils.py:169-178 (_background_activity_filter) as used by
+ *                                tools/filters.py:57-69 (BackgroundActivity.insert)
  *   evrep_est_quantize_batched   ev-YOLOv6/yolov6/models/learned_repr.py:143-172 (QuantizationLayer.forward, inference only)
  *   evrep_image_pipeline_batched ev-YOLOv6/yolov6/data/gen1_2yolo.py:230-265,321-341,397 (resize_image, letterbox, CHW + reversal),
  *                                gen4/precompute_reps.py:216-251 (resize_image_process), yolov6/core/engine.py:629-635 (/ 255)
@@ -77,6 +79,7 @@ extern "C" {
 #define EVREP_AGG_MEAN 1
 #define EVREP_AGG_MAX 2
 #define EVREP_AGG_VARIANCE 3
+#define EVREP_AGG_MIN 4 /* torch_scatter reduce="min" (untouched pixels 0): Operations passes the string straight to scatter (operations.py:30-35); used by the N-ImageNet scatter_min planes (imagenet.py:241-244, 383-386) */
 #define EVREP_STACK_SBN 0 /* windows by number of events (the one ERGO-12 uses) */
 #define EVREP_STACK_SBT 1 /* windows by time */
 #define EVREP_MAX_CHANNELS 32
@@ -259,6 +262,19 @@ int evrep_image_pipeline_batched(const float* rep, int B, int H, int W, int C, i
 int evrep_filter_batched(const uint16_t* x, const uint16_t* y, const void* t, int t_bytes, const int8_t* p, const int64_t* win_offsets,
                          int B, int H, int W, int filter, double param, int fx, int fy, void* state, unsigned char* mask,
                          void* workspace, size_t workspace_bytes, evrep_stream_t stream);
+
+/* ev-licious' background-activity filter (utils.py:169-178): for every event in stream order, t_last = state[y, x];
+ * mask = !(t_last > 0 && t - t_last > depth_us); then state[y - radius .. y + radius - 1, x - radius .. x + radius - 1] = t
+ * (clipped to the sensor, like the numpy slice).  `state` is DEVICE float64 (B, H, W), read and written (start at -inf,
+ * tools/filters.py:64-65), so a stream can be fed in pieces; `mask` DEVICE uint8, one per event, fully overwritten (events
+ * outside the sensor get 0, write nothing and raise EVREP_WF_OUT_OF_RANGE).  radius in 1..4.  The stream is expanded into
+ * (2 radius)^2 per-pixel write records inside the workspace (evrep_filter_background_workspace_bytes), so a window may
+ * hold at most 33 M / (2 radius)^2 events.  The filter id below is only valid through this entry point. */
+#define EVREP_FILTER_BACKGROUND 3
+size_t evrep_filter_background_workspace_bytes(int B, int64_t total_events, int H, int W, int radius, int t_bytes);
+int evrep_filter_background_batched(const uint16_t* x, const uint16_t* y, const void* t, int t_bytes, const int64_t* win_offsets, int B,
+                                    int H, int W, double depth_us, int radius, double* state, unsigned char* mask, void* workspace,
+                                    size_t workspace_bytes, evrep_stream_t stream);
 
 /* EST, the reference's learned quantisation layer, forward only (ev-YOLOv6/yolov6/models/learned_repr.py:143-172):
  * out[b, y, x, p * C + i] = sum over the events of window b at (x, y, p) of tn * f(tn - i / (C - 1)), tn = t / max(t of the

@@ -71,8 +71,20 @@ def main():
         d.update(rsz_mask=np.concatenate(masks), rsz_state0=states[0], rsz_state1=states[1], fx=fx, fy=fy)
         m2, _ = ofil.filter_events_resize(x, y, p, np.zeros(n, bool), np.zeros((H // fy, W // fx), np.float32), fx, fy)
         assert np.array_equal(m2, d["rsz_mask"]), name
+        # background activity, radius 1 and 2 (timestamps start at -inf like tools/filters.py:64-65)
+        for r in (1, 2):
+            ts = np.full((H, W), -np.inf)
+            masks, states = [], []
+            for sl in (slice(0, cut), slice(cut, n)):
+                m = np.ones(len(x[sl]), bool)
+                masks.append(U._background_activity_filter(m, ts, x[sl], y[sl], t[sl], 300, r).copy())
+                states.append(ts.copy())
+            d.update({f"ba{r}_mask": np.concatenate(masks), f"ba{r}_state0": states[0], f"ba{r}_state1": states[1], "ba_depth": 300})
+            chk = ofil.background_activity_filter(np.ones(n, bool), np.full((H, W), -np.inf), x, y, t, 300, r)
+            assert np.array_equal(chk, d[f"ba{r}_mask"]), (name, r)
         np.savez_compressed(os.path.join(out, f"filter_{name}.npz"), **d)
-        print(name, n, "kept", int(d["refr_mask"].sum()), int(d["ctc_mask"].sum()), int(d["rsz_mask"].sum()))
+        print(name, n, "kept", int(d["refr_mask"].sum()), int(d["ctc_mask"].sum()), int(d["rsz_mask"].sum()), int(d["ba1_mask"].sum()),
+              int(d["ba2_mask"].sum()))
 
 
 if __name__ == "__main__":

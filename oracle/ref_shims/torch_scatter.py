@@ -8,6 +8,7 @@ Semantics restated from torch_scatter 2.1 (`scatter(src, index, dim=-1, dim_size
   sum  : out[i] = sum of src[j] with index[j] == i, 0 for untouched i
   mean : sum / clamp(count, min=1)   (true division for floating src)
   max  : max of src[j]; untouched i -> 0
+  min  : min of src[j]; untouched i -> 0
 """
 import torch
 
@@ -29,6 +30,11 @@ def scatter(src, index, dim=-1, out=None, dim_size=None, reduce="sum"):
         o = torch.zeros(dim_size, dtype=src.dtype)
         if index.numel():
             o.scatter_reduce_(0, index, src, "amax", include_self=False)
+        return o
+    if reduce == "min":
+        o = torch.zeros(dim_size, dtype=src.dtype)
+        if index.numel():
+            o.scatter_reduce_(0, index, src, "amin", include_self=False)
         return o
     raise ValueError(reduce)
 

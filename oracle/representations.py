@@ -17,7 +17,7 @@ import numpy as np
 # MixedDensityEventStack / ERGO-12
 # ----------------------------------------------------------------------------------------------
 FUNCTIONS = ["timestamp", "polarity", "count", "timestamp_pos", "timestamp_neg", "count_pos", "count_neg"]
-AGGREGATIONS = ["sum", "mean", "max", "variance"]
+AGGREGATIONS = ["sum", "mean", "max", "variance", "min"]  # "min": torch_scatter's fifth reduce, legal through operations.py:30-35
 
 # representations/optimized_representation.py:86-115 (v2, active) and :16-66 (v1, commented)
 ERGO12_V2 = (
@@ -63,13 +63,15 @@ def _sbt_window_masks(t_s):
 
 
 def _scatter(src, index, size, reduce):
-    """torch_scatter.scatter semantics (operations.py:15-37): sum / mean / max, empty -> 0."""
+    """torch_scatter.scatter semantics (operations.py:15-37): sum / mean / max / min, empty -> 0."""
     if reduce == "sum":
         return np.bincount(index, weights=src, minlength=size).astype(np.float64)
     if reduce == "mean":
         s = np.bincount(index, weights=src, minlength=size)
         c = np.bincount(index, minlength=size).astype(np.float64)
         return s / np.maximum(c, 1.0)
+    if reduce == "min":
+        return -_scatter(-src, index, size, "max")
     if reduce == "max":
         o = np.full(size, -np.inf)
         nan_hit = np.zeros(size, bool)  # NaN sources propagate (torch amax semantics of the shim)

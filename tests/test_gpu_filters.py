@@ -104,3 +104,92 @@ def test_filters_empty_windows_and_out_of_range_events(E):
     none = E.pack_events([wins[0]], "cuda")
     m0, _ = E.filter_events(none, H, W, "contrast", 2.0)
     assert m0.numel() == 0
+
+
+@pytest.mark.parametrize("name,path", golden("filter_*"), ids=[n for n, _ in golden("filter_*")])
+@pytest.mark.parametrize("radius", [1, 2])
+def test_background_activity_matches_reference_numba_kernel(E, name, path, radius):
+    """utils.py:169-178 run by the reference itself (oracle/gen_golden_filters.py), stream fed in two pieces"""
+    g = load(path)
+    H, W, n, cut = int(g["H"]), int(g["W"]), len(g["x"]), int(g["cut"])
+    st = E.filter_state("background", 1, H, W)
+    masks = []
+    for k, (lo, hi) in enumerate(((0, cut), (cut, n))):
+        m, st = E.filter_events(_pieces(E, g, lo, hi), H, W, "background", float(g["ba_depth"]), st, fx=radius)
+        masks.append(m.cpu().numpy().astype(bool))
+        assert np.array_equal(st[0].cpu().numpy(), g[f"ba{radius}_state{k}"]), f"{name} state after piece {k}"
+    assert np.array_equal(np.concatenate(masks), g[f"ba{radius}_mask"]), name
+
+
+@pytest.mark.parametrize("radius", [1, 3])
+def test_background_activity_batched_vs_oracle(E, radius):
+    """several streams, events on every border and corner (clipped blocks), a hot pixel, int32 and int64 timestamps"""
+    from oracle import filters as ofil
+    H, W = 37, 53
+    rng = np.random.default_rng(11 + radius)
+    wins = []
+    for n, t0 in ((20000, 0), (8193, 5_000_000_000), (1, 7), (30000, 100)):
+        x = rng.integers(0, W, n).astype(np.uint16)
+        y = rng.integers(0, H, n).astype(np.uint16)
+        edge = rng.random(n) < 0.2
+        x[edge] = rng.choice(np.array([0, W - 1], np.uint16), int(edge.sum()))
+        edge = rng.random(n) < 0.2
+        y[edge] = rng.choice(np.array([0, H - 1], np.uint16), int(edge.sum()))
+        hot = rng.random(n) < 0.2
+        x[hot], y[hot] = 5, 6
+        wins.append({"x": x, "y": y, "t": t0 + np.cumsum(rng.integers(0, 25, n)).astype(np.int64), "p": np.ones(n, np.int8)})
+    for tdt in (np.int64, None):
+        use = wins if tdt is not None else [wins[0], wins[2], wins[3]]  # the second stream needs 64-bit stamps
+        ev = E.pack_events(use, "cuda") if tdt is None else E.pack_events(use, "cuda", np.int64)
+        m, s = E.filter_events(ev, H, W, "background", 150.0, fx=radius)
+        offs = ev.offsets
+        for b, w in enumerate(use):
+            n = len(w["x"])
+            ts = np.full((H, W), -np.inf)
+            want = ofil.background_activity_filter(np.ones(n, bool), ts, w["x"], w["y"], w["t"], 150.0, radius)
+            got = m[int(offs[b]):int(offs[b + 1])].cpu().numpy().astype(bool)
+            assert np.array_equal(got, want), f"stream {b}: {int((got != want).sum())} of {n} differ"
+            assert np.array_equal(s[b].cpu().numpy(), ts), f"stream {b} state"
+        assert not (E.window_flags(ev) & 0x100).any()  # clipped blocks are not out-of-range events
+
+
+def test_evlicious_filter_objects(E):
+    """tools/filters.py:23-129: the filter classes, state kept as numpy arrays across insert() calls"""
+    from event_representation_study_b200.evlicious import Events
+    from event_representation_study_b200.evlicious.tools import filters as F
+    from oracle import filters as ofil
+    g = load(golden("filter_hot")[0][1])
+    H, W, n = int(g["H"]), int(g["W"]), 12000
+    mk = lambda lo, hi: Events(g["x"][lo:hi].copy(), g["y"][lo:hi].copy(), g["t"][lo:hi].copy(), g["p"][lo:hi].copy(), W, H)  # noqa: E731
+    ba = F.from_flags(type("Flags", (), {"filter_type": int(F.Filtering_Type.BackgroundActivity), "depth_us": 300, "radius": 1}))
+    kept = [ba.insert(mk(0, 5000)), ba.insert(mk(5000, n))]
+    ts = np.full((H, W), -np.inf)
+    want = ofil.background_activity_filter(np.ones(n, bool), ts, g["x"][:n], g["y"][:n], g["t"][:n], 300, 1)
+    assert np.array_equal(np.concatenate([k.t for k in kept]), g["t"][:n][want]) and np.array_equal(ba.timestamps, ts)
+    rp = F.RefractoryPeriod(depth_us=2000)
+    last = np.full((H, W), -np.inf)
+    want = ofil.refractory_period(np.ones(n, bool), g["x"][:n], g["y"][:n], g["t"][:n], 2000, last)
+    assert len(rp.insert(mk(0, n))) == int(want.sum()) and np.array_equal(rp.timestamps, last)
+    ct = F.ContrastThresholdIncrease(contrast_threshold_multiplier=3)
+    act = np.zeros((H, W), np.int32)
+    want = ofil.contrast_threshold_control(act, np.zeros(n, bool), g["x"][:n], g["y"][:n], g["p"][:n], 3)
+    assert np.array_equal(ct.insert(mk(0, n)).t, g["t"][:n][want]) and np.array_equal(ct.counter_map, act)
+    hp = F.HotPixel()
+    out = hp.insert(mk(0, n))  # half of this stream sits on six pixels: they are calibrated away
+    want_mask = ofil.hot_pixel_mask(g["x"][:n], g["y"][:n], H, W)
+    assert np.array_equal(hp.hot_pixel_mask, want_mask) and not want_mask.all()
+    assert np.array_equal(out.t, g["t"][:n][want_mask[g["y"][:n], g["x"][:n]]])
+    u = load(golden("filter_uniform")[0][1])
+    hp2 = F.HotPixel()
+    ev_u = Events(u["x"][:n].copy(), u["y"][:n].copy(), u["t"][:n].copy(), u["p"][:n].copy(), W, H)
+    assert len(hp2.insert(ev_u)) == n and hp2.hot_pixel_mask.all()  # no pixel stands out: everything passes
+    assert F.Filtering_Type.summary().count("=") == 5 and len(F.Random(4).insert(mk(0, 1000))) == 250
+
+
+def test_background_activity_argument_checks(E):
+    g = load(golden("filter_tiny")[0][1])
+    ev = _pieces(E, g, 0, len(g["x"]))
+    with pytest.raises(ValueError):
+        E.filter_events(ev, int(g["H"]), int(g["W"]), "background", 10.0, fx=5)
+    m, st = E.filter_events(E.pack_events([{k: g[k][:0] for k in "xytp"}], "cuda"), 6, 6, "background", 10.0, fx=1)
+    assert m.numel() == 0 and np.isinf(st.cpu().numpy()).all()

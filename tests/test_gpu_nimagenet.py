@@ -57,17 +57,19 @@ def test_augment_hook_is_applied_first(N, G):
     assert np.array_equal(a.numpy(), b.numpy()[:, ::-1])
 
 
-@pytest.mark.parametrize("name", ["acc_count", "acc", "acc_count_pol", "acc_count_only"])
+@pytest.mark.parametrize("name", ["acc_count", "acc", "acc_count_pol", "acc_count_only", "acc_time", "acc_all", "acc_time_pol", "acc_exp",
+                                  "flat", "flat_pol"])
 def test_upstream_count_representations_match_the_reference(N, G, name):
-    """imagenet.py:169-343 through one mixed-density launch each; counts exact, normalised times to 1e-5 (2^30 time grid)"""
+    """imagenet.py:169-510 through one mixed-density launch each; counts and presence planes exact, normalised times
+    (latest = max, earliest = min) to 1e-5 (2^30 time grid)"""
     import torch
     H, W = int(G["H"]), int(G["W"])
     rep = getattr(N, "reshape_then_" + name)(torch.tensor(G["events_s"].copy()), height=H, width=W)
     want = G["up_" + name]
     assert rep.dtype == torch.float32 and tuple(rep.shape) == want.shape
     assert_close(rep.numpy(), want, rtol=1e-5, atol=1e-7, what=name)
-    if name in ("acc_count", "acc_count_pol", "acc_count_only"):
-        planes = {"acc_count": (0, 2), "acc_count_pol": (0, 1), "acc_count_only": (0,)}[name]
+    if name in ("acc_count", "acc_count_pol", "acc_count_only", "acc_all", "flat", "flat_pol"):
+        planes = {"acc_count": (0, 2), "acc_count_pol": (0, 1), "acc_count_only": (0,), "acc_all": (0, 1), "flat": (0,), "flat_pol": (0, 1)}[name]
         for c in planes:
             assert np.array_equal(rep.numpy()[c], want[c])
 
@@ -78,3 +80,22 @@ def test_upstream_acc_count_empty_sample(N):
     rep = N.reshape_then_acc_count(torch.zeros((0, 4), dtype=torch.float64), height=8, width=8)
     assert float(rep[0, 0, 0]) == 10.0 and float(rep[0].sum()) == 10.0 and float(rep[2].sum()) == 0.0
     assert abs(float(rep[1, 0, 0]) - 1.0) < 1e-6
+
+
+def test_upstream_empty_samples(N):
+    """imagenet.py:353-354 (zeros of the default size), :397-438 (empty index lists leave zeros), :483-486 (fake events)"""
+    import torch
+    e = torch.zeros((0, 4), dtype=torch.float64)
+    assert tuple(N.reshape_then_acc_all(e, height=8, width=8).shape) == (6, N.IMAGE_H, N.IMAGE_W)
+    assert tuple(N.reshape_then_flat(e, height=8, width=8).shape) == (1, 8, 8) and not N.reshape_then_flat_pol(e, height=8, width=8).any()
+    rep = N.reshape_then_acc_time_pol(e, height=8, width=8)
+    assert abs(float(rep[0, 0, 0]) - 1.0) < 1e-6 and float(rep.sum()) == float(rep[0, 0, 0])
+
+
+def test_flat_ignores_timestamps(N, G):
+    """reshape_then_flat* never read the time column: unsorted / constant stamps are fine"""
+    import torch
+    H, W = int(G["H"]), int(G["W"])
+    ev = G["events_s"].copy()
+    ev[:, 2] = 0.0
+    assert np.array_equal(N.reshape_then_flat_pol(torch.tensor(ev), height=H, width=W).numpy(), G["up_flat_pol"])

@@ -214,3 +214,24 @@ def test_new_entry_points_validate_before_touching_cuda(L):
     offs = (ctypes.c_int64 * 2)(0, 0)
     assert L.evrep_filter_batched(None, None, None, 4, None, offs, 1, 8, 8, 9, 1.0, 1, 1, None, None, None, 0, None) == _lib.EINVAL   # unknown filter
     assert L.evrep_est_quantize_batched(None, None, None, None, offs, 1, 8, 8, 1, None, None, None, 0, None, None, 0, None) == _lib.EINVAL  # C < 2
+    # background-activity filter: radius outside 1..4, and the workspace query
+    assert L.evrep_filter_background_workspace_bytes(1, 1000, 8, 8, 0, 4) == 0 and L.evrep_filter_background_workspace_bytes(1, 1000, 8, 8, 5, 8) == 0
+    w1, w2 = L.evrep_filter_background_workspace_bytes(1, 1000, 8, 8, 1, 4), L.evrep_filter_background_workspace_bytes(1, 1000, 8, 8, 2, 4)
+    assert 0 < w1 < w2
+    assert L.evrep_filter_background_batched(None, None, None, 4, offs, 1, 8, 8, 10.0, 7, None, None, None, 0, None) == _lib.EINVAL
+
+
+def test_evlicious_filter_module_mirrors_the_reference_names():
+    """tools/filters.py:7-129: class names, enum values and the flag dispatch (host logic only)"""
+    from event_representation_study_b200.evlicious.tools import filters as F
+    assert [int(v) for v in F.Filtering_Type] == [1, 2, 3, 4, 5] and "HotPixel=5" in F.Filtering_Type.summary()
+    mk = lambda **kw: type("Flags", (), kw)  # noqa: E731
+    assert isinstance(F.from_flags(mk(filter_type=1, depth_us=10, radius=1)), F.BackgroundActivity)
+    assert isinstance(F.from_flags(mk(filter_type=2, random_downsampling_factor=3)), F.Random)
+    assert isinstance(F.from_flags(mk(filter_type=3, contrast_threshold_multiplier=2)), F.ContrastThresholdIncrease)
+    assert isinstance(F.from_flags(mk(filter_type=4, depth_us=10)), F.RefractoryPeriod)
+    assert isinstance(F.from_flags(mk(filter_type=5)), F.HotPixel)
+    with pytest.raises(ValueError):
+        F.from_flags(mk(filter_type=9))
+    with pytest.raises(AssertionError):
+        F.from_flags(mk(filter_type=1, depth_us=0, radius=1))

@@ -40,7 +40,7 @@ def test_ergo12_f8_seconds():
     assert_close(out, g["out"], rtol=1e-12, atol=1e-15)
 
 
-MDES = golden("mdes_*")
+MDES = golden("mdes_*") + golden("mdmin_*")  # mdmin: the aggregation "min" (oracle/gen_golden_min.py)
 
 
 @pytest.mark.parametrize("name,path", MDES, ids=ids(MDES))
@@ -211,3 +211,7 @@ def test_filter_oracle_matches_reference_fixtures(name, path):
     fx, fy = int(g["fx"]), int(g["fy"])
     m, cm = ofil.filter_events_resize(x, y, p, np.zeros(n, bool), np.zeros((H // fy, W // fx), np.float32), fx, fy)
     assert np.array_equal(m, g["rsz_mask"]) and np.array_equal(cm, g["rsz_state1"])
+    for r in (1, 2):  # background activity (utils.py:169-178), whole stream in one go = the two pieces of the fixture
+        ts = np.full((H, W), -np.inf)
+        got = ofil.background_activity_filter(np.ones(n, bool), ts, x, y, t, float(g["ba_depth"]), r)
+        assert np.array_equal(got, g[f"ba{r}_mask"]) and np.array_equal(ts, g[f"ba{r}_state1"])
