@@ -538,6 +538,8 @@ __global__ void __launch_bounds__(BIN_THREADS, EVREP_BIN_CTAS) k_bin(const uint1
         if (d >= T_REL_LIMIT || d <= -T_REL_LIMIT) { my_flags |= EVREP_WF_T_RANGE; keep = false; }
         t_rel = (int32_t)d;
       }
+      // index-keyed records (EventStack, the filters) carry no timestamp: a stream longer than 2^30 us only raises the flag
+      if (MODE == REC_IDX) keep = true;
       int pv = pe;
       if (pv > 1 || pv < -1) { my_flags |= EVREP_WF_BAD_POLARITY; pv = pv > 0 ? 1 : -1; }
       uint32_t aux = 0, k = (uint32_t)t_rel;

@@ -92,7 +92,8 @@ extern "C" {
 /* per-window status bits written by every batched op (read back with evrep_window_flags) */
 #define EVREP_WF_OUT_OF_RANGE 0x100u /* an event had x >= W or y >= H; it was dropped */
 #define EVREP_WF_UNSORTED 0x200u     /* timestamps decrease somewhere inside the window */
-#define EVREP_WF_T_RANGE 0x400u      /* |t - t_first| does not fit 31 bits; the event was dropped */
+#define EVREP_WF_T_RANGE 0x400u      /* |t - t_first| does not fit 31 bits; the event was dropped (EventStack and the filters do
+                                        not key on time: there the flag is only informative and every event is kept) */
 #define EVREP_WF_BAD_POLARITY 0x800u /* p outside {-1,0,1}; treated as sign(p) */
 
 /* kernels of the tile pipeline, for evrep_profile_read */

@@ -193,3 +193,27 @@ def test_background_activity_argument_checks(E):
         E.filter_events(ev, int(g["H"]), int(g["W"]), "background", 10.0, fx=5)
     m, st = E.filter_events(E.pack_events([{k: g[k][:0] for k in "xytp"}], "cuda"), 6, 6, "background", 10.0, fx=1)
     assert m.numel() == 0 and np.isinf(st.cpu().numpy()).all()
+
+
+def test_index_keyed_ops_keep_events_beyond_the_time_span_limit(E):
+    """a stream spanning more than 2^30 us (18 min): the filters and EventStack key on the stream index, so every event is
+    kept and EVREP_WF_T_RANGE is only informative"""
+    from oracle import filters as ofil
+    from oracle import representations as orep
+    H, W, n = 24, 32, 20000
+    rng = np.random.default_rng(77)
+    w = {"x": rng.integers(0, W, n).astype(np.uint16), "y": rng.integers(0, H, n).astype(np.uint16),
+         "t": np.cumsum(rng.integers(0, 300_000, n)).astype(np.int64), "p": rng.choice(np.array([-1, 1], np.int8), n)}
+    assert int(w["t"][-1] - w["t"][0]) > 2 * 2**30
+    ev = E.pack_events([w], "cuda", np.int64)
+    m, s = E.filter_events(ev, H, W, "refractory", 5e5)
+    assert int(E.window_flags(ev)[0]) & 0x400
+    last = np.full((H, W), -np.inf)
+    want = ofil.refractory_period(np.ones(n, bool), w["x"], w["y"], w["t"], 5e5, last)
+    assert np.array_equal(m.cpu().numpy().astype(bool), want) and np.array_equal(s[0].cpu().numpy(), last)
+    m, s = E.filter_events(ev, H, W, "background", 4e5, fx=1)
+    ts = np.full((H, W), -np.inf)
+    want = ofil.background_activity_filter(np.ones(n, bool), ts, w["x"], w["y"], w["t"], 4e5, 1)
+    assert np.array_equal(m.cpu().numpy().astype(bool), want) and np.array_equal(s[0].cpu().numpy(), ts)
+    es = E.event_stack(ev, H, W, 12).cpu().numpy()[0]
+    assert np.array_equal(es, orep.event_stack(w["x"], w["y"], w["t"], (w["p"].astype(np.int32) + 1) // 2, H, W, 12))
