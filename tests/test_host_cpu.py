@@ -58,6 +58,20 @@ def test_ergo12_plan(L):
     assert rc == 0 and info[3] < 24 and info[2] == -(-240 * 304 // info[1])
 
 
+def test_plan_for_the_min_aggregation(L):
+    """EVREP_AGG_MIN: one word per (window, class) like "max"; a (count, min) channel only needs a presence bit"""
+    T, CP, TP = L.FUNCS["timestamp"], L.FUNCS["count_pos"], L.FUNCS["timestamp_pos"]
+    MIN, MAX = L.AGGS["min"], L.AGGS["max"]
+    assert MIN == 4
+    rc, one = plan_info(L, 64, 64, [0], [TP], [MAX], 0, 1000)
+    rc2, two = plan_info(L, 64, 64, [0, 0], [TP, TP], [MAX, MIN], 0, 1000)
+    rc3, mixed = plan_info(L, 64, 64, [0, 0, 1], [TP, T, CP], [MIN, MIN, MIN], 0, 1000)
+    assert rc == rc2 == rc3 == 0
+    assert one[3] == 1 and two[3] == 2 and mixed[3] == 3  # accumulator words: latest + earliest; two earliest words + presence
+    rc, _ = plan_info(L, 64, 64, [0], [T], [5], 0, 1000)   # an unknown aggregation is a zero channel, not an error
+    assert rc == 0
+
+
 def test_plan_rejects_bad_arguments(L):
     rc, _ = plan_info(L, 720, 1280, [0] * 33, [0] * 33, [0] * 33, 0, 1000)
     assert rc == L.EINVAL and b"outside" in L.lib.evrep_last_error()
