@@ -281,3 +281,49 @@ def reshape_then_flat_pol(event_tensor, augment=None, **kwargs):
         return torch.zeros([2, H, W])
     rep = _window_reduce(event_tensor, H, W, ["count_pos", "count_neg"], ["max", "max"], need_time=False)
     return rep.permute(2, 0, 1).float().cpu()
+
+
+def reshape_then_acc_intensity(event_tensor, augment=None, **kwargs):
+    """imagenet.py:841-870 -> (1, H, W): positive minus negative count per pixel, min-max normalised over the plane (0 / 0 =
+    NaN for a constant plane, as in the reference).  The difference is the ("polarity", "sum") plane; the normalisation is an
+    elementwise epilogue on the GPU tensor."""
+    if augment is not None:
+        event_tensor = augment(event_tensor)
+    H = kwargs.get("height", IMAGE_H)
+    W = kwargs.get("width", IMAGE_W)
+    if len(event_tensor) == 0:
+        rep = torch.zeros((H, W, 1))
+    else:
+        rep = _window_reduce(event_tensor, H, W, ["polarity"], ["sum"], need_time=False)
+    lo, hi = rep.min(), rep.max()
+    return ((rep - lo) / (hi - lo)).permute(2, 0, 1).float().cpu()
+
+
+def loader_for(loader_type):
+    """ImageNetDataset.__init__'s choice of loader (imagenet.py:1232-1272): `loader_type` string -> function.  The two sorted /
+    DiST loaders ("sorted_time_surface", "dist", ...) are not built and raise NotImplementedError; an unknown string gives
+    None, where the reference leaves `self.loader` unset."""
+    table = [
+        ((None, "event_image", "reshape_then_acc"), reshape_then_acc),
+        (("reshape_then_acc_time",), reshape_then_acc_time),
+        (("reshape_then_acc_count",), reshape_then_acc_count),
+        (("reshape_then_acc_all",), reshape_then_acc_all),
+        (("reshape_then_flat_pol",), reshape_then_flat_pol),
+        (("binary_event_image", "reshape_then_flat"), reshape_then_flat),
+        (("timestamp_image", "reshape_then_acc_time_pol"), reshape_then_acc_time_pol),
+        (("event_histogram", "reshape_then_acc_count_pol"), reshape_then_acc_count_pol),
+        (("reshape_then_acc_exp",), reshape_then_acc_exp),
+        (("reshape_then_acc_intensity",), reshape_then_acc_intensity),
+        (("reshape_then_voxel_grid",), reshape_then_voxel_grid),
+        (("reshape_then_optimized",), reshape_then_optimized),
+        (("reshape_then_event_stack",), reshape_then_event_stack),
+        (("reshape_then_to_image",), reshape_then_to_image),
+        (("reshape_then_tore",), reshape_then_tore),
+        (("reshape_then_time_surface",), reshape_then_time_surface),
+    ]
+    for names, fn in table:
+        if loader_type in names:
+            return fn
+    if loader_type in ("sorted_time_surface", "reshape_then_acc_sort", "dist", "DiST", "reshape_then_acc_adj_sort"):
+        raise NotImplementedError(f"loader_type {loader_type!r}: the sorted / DiST representations (imagenet.py:513-999) are not built")
+    return None

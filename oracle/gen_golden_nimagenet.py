@@ -49,7 +49,7 @@ def main():
         out[name] = rep.numpy()
         print(name, tuple(rep.shape), rep.dtype)
     # upstream count / latest-time representations (imagenet.py:169-343), on the seconds-stamped tensor as the loader gives it
-    for name in ("acc_count", "acc", "acc_count_pol", "acc_count_only", "acc_time", "acc_all", "acc_time_pol", "acc_exp", "flat", "flat_pol"):
+    for name in ("acc_count", "acc", "acc_count_pol", "acc_count_only", "acc_time", "acc_all", "acc_time_pol", "acc_exp", "flat", "flat_pol", "acc_intensity"):
         rep = getattr(ref, "reshape_then_" + name)(torch.tensor(ev.copy()), height=H, width=W)
         out["up_" + name] = rep.numpy()
         print(name, tuple(rep.shape), rep.dtype)

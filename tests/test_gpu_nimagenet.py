@@ -58,7 +58,7 @@ def test_augment_hook_is_applied_first(N, G):
 
 
 @pytest.mark.parametrize("name", ["acc_count", "acc", "acc_count_pol", "acc_count_only", "acc_time", "acc_all", "acc_time_pol", "acc_exp",
-                                  "flat", "flat_pol"])
+                                  "flat", "flat_pol", "acc_intensity"])
 def test_upstream_count_representations_match_the_reference(N, G, name):
     """imagenet.py:169-510 through one mixed-density launch each; counts and presence planes exact, normalised times
     (latest = max, earliest = min) to 1e-5 (2^30 time grid)"""
@@ -69,7 +69,7 @@ def test_upstream_count_representations_match_the_reference(N, G, name):
     assert rep.dtype == torch.float32 and tuple(rep.shape) == want.shape
     assert_close(rep.numpy(), want, rtol=1e-5, atol=1e-7, what=name)
     if name in ("acc_count", "acc_count_pol", "acc_count_only", "acc_all", "flat", "flat_pol"):
-        planes = {"acc_count": (0, 2), "acc_count_pol": (0, 1), "acc_count_only": (0,), "acc_all": (0, 1), "flat": (0,), "flat_pol": (0, 1)}[name]
+        planes = {"acc_count": (0, 2), "acc_count_pol": (0, 1), "acc_count_only": (0,), "acc_all": (0, 1), "flat": (0,), "flat_pol": (0, 1)}[name]  # acc_intensity: a float32 quotient, held to 1e-5 above
         for c in planes:
             assert np.array_equal(rep.numpy()[c], want[c])
 
@@ -99,3 +99,12 @@ def test_flat_ignores_timestamps(N, G):
     ev = G["events_s"].copy()
     ev[:, 2] = 0.0
     assert np.array_equal(N.reshape_then_flat_pol(torch.tensor(ev), height=H, width=W).numpy(), G["up_flat_pol"])
+
+
+def test_loader_table_matches_the_dataset_dispatch(N):
+    """imagenet.py:1232-1272"""
+    assert N.loader_for(None) is N.reshape_then_acc and N.loader_for("event_histogram") is N.reshape_then_acc_count_pol
+    assert N.loader_for("timestamp_image") is N.reshape_then_acc_time_pol and N.loader_for("binary_event_image") is N.reshape_then_flat
+    assert N.loader_for("reshape_then_optimized") is N.reshape_then_optimized and N.loader_for("no such loader") is None
+    with pytest.raises(NotImplementedError):
+        N.loader_for("DiST")

@@ -210,6 +210,11 @@ def test_n_imagenet_host_helpers():
     assert tuple(fake.shape) == (10, 4) and float(fake[:, 3].min()) == 1.0 and abs(float(fake[-1, 2]) - 0.9) < 1e-6
     keep = torch.ones((3, 4))
     assert N._empty_guard(keep) is keep
+    # ImageNetDataset's loader_type dispatch (imagenet.py:1232-1272)
+    assert N.loader_for("event_image") is N.reshape_then_acc and N.loader_for("reshape_then_acc_intensity") is N.reshape_then_acc_intensity
+    assert N.loader_for("reshape_then_tore") is N.reshape_then_tore and N.loader_for("nope") is None
+    with pytest.raises(NotImplementedError):
+        N.loader_for("sorted_time_surface")
 
 
 def test_new_entry_points_validate_before_touching_cuda(L):
