@@ -254,3 +254,45 @@ def test_evlicious_filter_module_mirrors_the_reference_names():
         F.from_flags(mk(filter_type=9))
     with pytest.raises(AssertionError):
         F.from_flags(mk(filter_type=1, depth_us=0, radius=1))
+
+
+def test_evlicious_filter_objects_host_logic(monkeypatch):
+    """the filter classes' own logic (lazy state, start mask, events[mask]) with the GPU calls replaced by the oracle loops"""
+    from event_representation_study_b200.evlicious import Events
+    from event_representation_study_b200.evlicious.tools import filters as F
+    from event_representation_study_b200.evlicious.tools import utils as U
+    from oracle import filters as ofil
+    monkeypatch.setattr(U, "_background_activity_filter", ofil.background_activity_filter)
+    monkeypatch.setattr(U, "_refractory_period", ofil.refractory_period)
+    monkeypatch.setattr(U, "_contrast_threshold_control", ofil.contrast_threshold_control)
+    rng = np.random.default_rng(3)
+    H, W, n = 10, 12, 600
+    x, y = rng.integers(0, W, n).astype(np.uint16), rng.integers(0, H, n).astype(np.uint16)
+    t, p = np.cumsum(rng.integers(1, 40, n)).astype(np.int64), rng.choice(np.array([-1, 1], np.int8), n)
+    mk = lambda lo, hi: Events(x[lo:hi].copy(), y[lo:hi].copy(), t[lo:hi].copy(), p[lo:hi].copy(), W, H)  # noqa: E731
+    ba = F.BackgroundActivity(depth_us=100, radius=2)
+    assert ba.timestamps is None
+    kept = np.concatenate([ba.insert(mk(0, 250)).t, ba.insert(mk(250, n)).t])
+    ts = np.full((H, W), -np.inf)
+    want = ofil.background_activity_filter(np.ones(n, bool), ts, x, y, t, 100, 2)
+    assert np.array_equal(kept, t[want]) and np.array_equal(ba.timestamps, ts) and ba.timestamps.dtype == np.float64
+    rp = F.RefractoryPeriod(depth_us=300)
+    last = np.full((H, W), -np.inf)
+    want = ofil.refractory_period(np.ones(n, bool), x, y, t, 300, last)
+    assert np.array_equal(rp.insert(mk(0, n)).t, t[want]) and np.array_equal(rp.timestamps, last)
+    ct = F.ContrastThresholdIncrease(contrast_threshold_multiplier=2)
+    act = np.zeros((H, W), np.int32)
+    want = ofil.contrast_threshold_control(act, np.zeros(n, bool), x, y, p, 2)
+    got = ct.insert(mk(0, n))
+    assert np.array_equal(got.t, t[want]) and np.array_equal(ct.counter_map, act) and ct.counter_map.dtype == np.int32
+    assert got.width == W and got.height == H and len(F.Random(3).insert(mk(0, 100))) == 33
+    monkeypatch.setattr(F, "_pixel_counts", lambda ev: np.bincount(ev.y.astype(int) * W + ev.x.astype(int), minlength=H * W).reshape(H, W) * 1.0)
+    xh = x.copy()
+    xh[: n // 2] = 1
+    yh = y.copy()
+    yh[: n // 2] = 2
+    hot = Events(xh, yh, t.copy(), p.copy(), W, H)
+    hp = F.HotPixel()
+    out = hp.insert(hot)
+    assert np.array_equal(hp.hot_pixel_mask, ofil.hot_pixel_mask(xh, yh, H, W)) and not hp.hot_pixel_mask[2, 1] and hp.hot_pixel_mask.sum() == H * W - 1
+    assert len(out) == int((~((xh == 1) & (yh == 2))).sum())
