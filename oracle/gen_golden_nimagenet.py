@@ -7,7 +7,6 @@ numpy's ndarray subclass a `float` method returning a float32 tensor."""
 import importlib.util
 import os
 import sys
-import types
 
 import numpy as np
 import torch
