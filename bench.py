@@ -119,7 +119,7 @@ def _cpu_one(args):
     return time.perf_counter() - t0, float(out[:, :, 5].sum())
 
 
-def cpu_baseline_scalar(n_events, budget_s=12.0, max_windows=24):
+def cpu_baseline_scalar(n_events, budget_s=12.0, max_windows=64):
     """Single-process oracle on a bounded sample of the same workload (windows of the bench's size)."""
     done, spent = 0, 0.0
     while done < max_windows and spent < budget_s:
