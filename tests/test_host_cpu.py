@@ -296,3 +296,34 @@ def test_evlicious_filter_objects_host_logic(monkeypatch):
     out = hp.insert(hot)
     assert np.array_equal(hp.hot_pixel_mask, ofil.hot_pixel_mask(xh, yh, H, W)) and not hp.hot_pixel_mask[2, 1] and hp.hot_pixel_mask.sum() == H * W - 1
     assert len(out) == int((~((xh == 1) & (yh == 2))).sum())
+
+
+def test_header_is_plain_c_and_a_c_program_links_against_the_library(tmp_path):
+    """include/evrep.h is the drop-in boundary: it must compile as C99 (no C++ / torch types) and a C caller must link and
+    run against libevrep.so (argument checks only - no device here)"""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "event_representation_study_b200", "lib")
+    src = tmp_path / "caller.c"
+    src.write_text('''#include <stdio.h>
+#include <string.h>
+#include "evrep.h"
+int main(void) {
+  long long offs[2] = {0, 10};
+  if (evrep_version() != 100) return 1;
+  if (evrep_ergo12_batched(NULL, NULL, NULL, 4, NULL, (const int64_t*)offs, 1, 30, 40, 2, NULL, NULL, 0, NULL) != EVREP_EINVAL) return 2;
+  if (!strstr(evrep_last_error(), "null")) return 3;
+  if (evrep_workspace_bytes(EVREP_OP_MIXED_DENSITY, 1, 1000, 240, 304, 12) == 0) return 4;
+  if (evrep_filter_background_workspace_bytes(1, 1000, 8, 8, 1, 4) == 0) return 5;
+  puts("ok");
+  return 0;
+}
+''')
+    exe = tmp_path / "caller"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(root, "include"), str(src), "-L", libdir, "-levrep",
+                    f"-Wl,-rpath,{libdir}", "-o", str(exe)], check=True, capture_output=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", (r.returncode, r.stdout, r.stderr)
