@@ -1,5 +1,6 @@
 """Writes tests/golden/est_*.npz with the reference's own ValueLayer / QuantizationLayer (learned_repr.py).  Runs only where
-/root/reference exists.  The reference builds its MLP on "cuda" and returns `.cuda()`: both are patched to CPU no-ops."""
+/root/reference exists.  The reference builds its MLP on "cuda" and returns `.cuda()`: both are patched to CPU no-ops.
+TEST INFRASTRUCTURE ONLY (fixture generator; nothing in the product package imports it)."""
 import importlib.util
 import os
 import sys

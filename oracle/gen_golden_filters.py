@@ -1,7 +1,8 @@
 """Writes tests/golden/filter_*.npz with the reference's own numba filter kernels (ev-licious/src/evlicious/tools/utils.py,
 loaded by path exactly like oracle/gen_golden.py does).  Runs only where /root/reference exists.  Every fixture feeds the
 stream in two pieces, like two `insert` calls of a filter object (tools/filters.py:57-109), and stores the state after
-each piece."""
+each piece.
+TEST INFRASTRUCTURE ONLY (fixture generator; nothing in the product package imports it)."""
 import os
 import sys
 import tempfile

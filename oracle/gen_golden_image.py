@@ -4,7 +4,7 @@ Runs only where /root/reference exists.  letterbox is the reference's own functi
 path); resize_image / resize_image_process are dataset METHODS whose modules need h5py / torch_geometric (absent
 offline), so their ten lines are restated in oracle/image_pipeline.py around the same cv2 calls and this script checks
 that the oracle's letterbox equals the reference's before writing anything.
-"""
+TEST INFRASTRUCTURE ONLY (fixture generator; nothing in the product package imports it)."""
 import importlib.util
 import os
 import sys

@@ -3,7 +3,8 @@
 /root/reference exists.  Third-party imports absent offline come from oracle/ref_shims (tonic, torch_scatter - the wrappers
 only need the module to import); `np.int` (removed from numpy, used at imagenet.py:1125-1126) is restored as `int`; the
 last line of reshape_then_to_image calls `.float()` on a numpy array, so that wrapper is run up to that line by giving
-numpy's ndarray subclass a `float` method returning a float32 tensor."""
+numpy's ndarray subclass a `float` method returning a float32 tensor.
+TEST INFRASTRUCTURE ONLY (fixture generator; nothing in the product package imports it)."""
 import importlib.util
 import os
 import sys
