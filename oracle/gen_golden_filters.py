@@ -72,8 +72,8 @@ def main():
         d.update(rsz_mask=np.concatenate(masks), rsz_state0=states[0], rsz_state1=states[1], fx=fx, fy=fy)
         m2, _ = ofil.filter_events_resize(x, y, p, np.zeros(n, bool), np.zeros((H // fy, W // fx), np.float32), fx, fy)
         assert np.array_equal(m2, d["rsz_mask"]), name
-        # background activity, radius 1 and 2 (timestamps start at -inf like tools/filters.py:64-65)
-        for r in (1, 2):
+        # background activity, radius 1 to 4 (timestamps start at -inf like tools/filters.py:64-65)
+        for r in (1, 2, 3, 4):
             ts = np.full((H, W), -np.inf)
             masks, states = [], []
             for sl in (slice(0, cut), slice(cut, n)):

@@ -211,7 +211,7 @@ def test_filter_oracle_matches_reference_fixtures(name, path):
     fx, fy = int(g["fx"]), int(g["fy"])
     m, cm = ofil.filter_events_resize(x, y, p, np.zeros(n, bool), np.zeros((H // fy, W // fx), np.float32), fx, fy)
     assert np.array_equal(m, g["rsz_mask"]) and np.array_equal(cm, g["rsz_state1"])
-    for r in (1, 2):  # background activity (utils.py:169-178), whole stream in one go = the two pieces of the fixture
+    for r in (1, 2, 3, 4):  # background activity (utils.py:169-178), whole stream in one go = the two pieces of the fixture
         ts = np.full((H, W), -np.inf)
         got = ofil.background_activity_filter(np.ones(n, bool), ts, x, y, t, float(g["ba_depth"]), r)
         assert np.array_equal(got, g[f"ba{r}_mask"]) and np.array_equal(ts, g[f"ba{r}_state1"])
