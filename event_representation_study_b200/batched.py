@@ -93,6 +93,46 @@ def pack_events(windows, device="cuda", t_dtype=np.int32, pin=False):
                       up(cat("p", np.int8)), offs)
 
 
+def split_collated(events, num_windows=None):
+    """The reference's raw-event mini-batch - rows [x, y, t, p, b] with b the sample index, as `collate_fn` builds it for the
+    learned representation (ev-YOLOv6/yolov6/data/gen1_2yolo.py:433-445) and `QuantizationLayer.forward` consumes it
+    (models/learned_repr.py:143-156) - split into the SoA fields and CSR offsets of an EventBatch, on the tensor's own device:
+    -> (x, y, t, p, offsets).  Rows must be grouped by ascending b (the collate concatenates the samples in order);
+    t is truncated to integer microseconds like the reference's own `.astype(np.int64)` and narrowed to int32 when it fits;
+    `num_windows` keeps trailing empty samples (default: b.max() + 1)."""
+    ev = torch.as_tensor(events)
+    if ev.dim() != 2 or ev.shape[1] != 5:
+        raise ValueError(f"expected rows [x, y, t, p, b]: shape (N, 5), got {tuple(ev.shape)}")
+    n = ev.shape[0]
+    b = ev[:, 4].to(torch.int64)
+    if n and bool((b[1:] < b[:-1]).any()):
+        raise ValueError("rows must be grouped by sample index b in ascending order")
+    B = int(num_windows) if num_windows is not None else (int(b[-1]) + 1 if n else 0)
+    if n and (int(b[0]) < 0 or int(b[-1]) >= B):
+        raise ValueError(f"sample indices must lie in [0, {B})")
+    offsets = np.zeros(B + 1, np.int64)
+    if n:
+        offsets[1:] = torch.bincount(b, minlength=B).cumsum(0).cpu().numpy()
+    xy = ev[:, :2].to(torch.int64)
+    if n and (int(xy.min()) < 0 or int(xy.max()) > 65535):
+        raise IndexError("x / y outside the uint16 range of the event layout")
+    u16 = lambda v: (v.to(torch.int32) & 0xFFFF).to(torch.int16).contiguous()  # noqa: E731  (uint16 values in int16 storage)
+    t = ev[:, 2].to(torch.int64)
+    if n == 0 or (int(t.min()) >= -2**31 and int(t.max()) < 2**31):
+        t = t.to(torch.int32)
+    p = ev[:, 3].to(torch.int64)
+    if n and (int(p.min()) < -1 or int(p.max()) > 1):
+        raise ValueError("polarities must be in {-1, 0, 1}")
+    return u16(xy[:, 0]), u16(xy[:, 1]), t.contiguous(), p.to(torch.int8).contiguous(), offsets
+
+
+def from_collated(events, num_windows=None, device="cuda"):
+    """`split_collated` + upload: the (N, 5) [x, y, t, p, b] tensor of the reference's collate -> EventBatch on `device`
+    (the batched call site the learned representation already has)."""
+    x, y, t, p, offsets = split_collated(events, num_windows)
+    return EventBatch(x.to(device), y.to(device), t.to(device), p.to(device), offsets)
+
+
 _workspaces = {}
 
 

@@ -327,3 +327,38 @@ int main(void) {
                     f"-Wl,-rpath,{libdir}", "-o", str(exe)], check=True, capture_output=True)
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.strip() == "ok", (r.returncode, r.stdout, r.stderr)
+
+
+def test_split_collated_raw_event_batch():
+    """the reference's collate for raw events, rows [x, y, t, p, b] (gen1_2yolo.py:433-445) -> SoA fields + CSR offsets"""
+    import torch
+    from event_representation_study_b200 import batched as eb
+    rng = np.random.default_rng(8)
+    samples = [np.stack([rng.integers(0, 304, n), rng.integers(0, 240, n), np.sort(rng.integers(0, 90_000, n)), rng.choice([-1, 1], n)], 1).astype(np.float32)
+               for n in (5, 0, 3, 7)]
+    col = np.concatenate([np.concatenate([d, i * np.ones((len(d), 1), np.float32)], 1) for i, d in enumerate(samples)], 0)  # what collate_fn does
+    x, y, t, p, offs = eb.split_collated(torch.from_numpy(col))
+    assert offs.tolist() == [0, 5, 5, 8, 15] and x.dtype == torch.int16 and t.dtype == torch.int32 and p.dtype == torch.int8
+    cat = np.concatenate(samples, 0)
+    assert np.array_equal(x.numpy().view(np.uint16), cat[:, 0].astype(np.uint16)) and np.array_equal(y.numpy(), cat[:, 1].astype(np.int16))
+    assert np.array_equal(t.numpy(), cat[:, 2].astype(np.int64)) and np.array_equal(p.numpy(), cat[:, 3].astype(np.int8))
+    assert eb.split_collated(torch.from_numpy(col), num_windows=6)[4].tolist() == [0, 5, 5, 8, 15, 15, 15]  # trailing empty samples
+    assert eb.split_collated(torch.zeros((0, 5)))[4].tolist() == [0]
+    big = col.astype(np.float64).copy()
+    big[:, 2] += 3e9
+    assert eb.split_collated(torch.from_numpy(big))[2].dtype == torch.int64
+    wide = col.copy()
+    wide[0, 0] = 40000  # a uint16 value above int16: kept bit for bit
+    assert int(eb.split_collated(torch.from_numpy(wide))[0].numpy().view(np.uint16)[0]) == 40000
+    with pytest.raises(ValueError):
+        eb.split_collated(torch.from_numpy(col[::-1].copy()))       # not grouped by ascending b
+    with pytest.raises(ValueError):
+        eb.split_collated(torch.zeros((4, 4)))
+    with pytest.raises(ValueError):
+        eb.split_collated(torch.from_numpy(col), num_windows=2)
+    bad = col.copy()
+    bad[1, 3] = 2
+    with pytest.raises(ValueError):
+        eb.split_collated(torch.from_numpy(bad))
+    with pytest.raises(ValueError):
+        eb.from_collated(torch.from_numpy(col), device="cpu")      # an EventBatch lives on the GPU: there is no CPU path
