@@ -125,6 +125,10 @@ struct RawT<int32_t> {
       b = make_int4(v[4], v[5], v[6], v[7]);
     }
   }
+  __device__ __forceinline__ void load_vec(const int32_t* __restrict__ p, int64_t g0) {  // g0 % 8 == 0, all 8 in bounds
+    a = __ldg(reinterpret_cast<const int4*>(p + g0));
+    b = __ldg(reinterpret_cast<const int4*>(p + g0) + 1);
+  }
   __device__ __forceinline__ int32_t get(int e) const {
     return e == 0 ? a.x : e == 1 ? a.y : e == 2 ? a.z : e == 3 ? a.w : e == 4 ? b.x : e == 5 ? b.y : e == 6 ? b.z : b.w;
   }
@@ -143,6 +147,10 @@ struct RawT<int64_t> {
         q[e].y = (g0 + 2 * e + 1 < total) ? __ldg(p + g0 + 2 * e + 1) : 0;
       }
     }
+  }
+  __device__ __forceinline__ void load_vec(const int64_t* __restrict__ p, int64_t g0) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) q[e] = __ldg(reinterpret_cast<const longlong2*>(p + g0) + e);
   }
   __device__ __forceinline__ int64_t get(int e) const { return (e & 1) ? q[e >> 1].y : q[e >> 1].x; }
 };
@@ -292,6 +300,8 @@ __global__ void k_snap_init(const TT* __restrict__ t, const WinParams* __restric
 // ---------------------------------------------------------------------------------------------
 // pass 1: bucket counts of one super-chunk -> one row of cc.  Counts every event with a valid pixel.
 // HBM: reads x, y (+ p when the buckets are split by polarity).
+// A thread's EPT events take the vector path (three 16-byte loads, no per-event bounds tests) whenever they all lie
+// inside the window; only the first / last few threads of a window run the scalar path.
 // ---------------------------------------------------------------------------------------------
 template <bool SPLIT, bool DIV>
 __global__ void __launch_bounds__(BIN_THREADS) k_hist(const uint16_t* __restrict__ x, const uint16_t* __restrict__ y,
@@ -303,32 +313,47 @@ __global__ void __launch_bounds__(BIN_THREADS) k_hist(const uint16_t* __restrict
   const int scl = blockIdx.x - __ldg(sc_prefix + b);
   const int64_t start = wp[b].start;
   const int n = (int)wp[b].n;
-  for (int i = threadIdx.x; i < g.Tb; i += BIN_THREADS) sh_hist[i] = 0;
-  __syncthreads();
   const int64_t c0 = (start & ~(int64_t)(EPT - 1)) + (int64_t)scl * SUPER;  // first event of this CTA's super-chunk
-  const uint32_t hbase = (uint32_t)__cvta_generic_to_shared(sh_hist);
-  const uint32_t Wd = (uint32_t)g.W, Hd = (uint32_t)g.H;
+  // the loads of both sub-chunks are issued before the histogram is cleared
+  uint4 qx[SC_CHUNKS], qy[SC_CHUNKS];
+  uint2 qp[SC_CHUNKS];
+  bool full[SC_CHUNKS];
 #pragma unroll
   for (int sub = 0; sub < SC_CHUNKS; ++sub) {
     const int64_t g0 = c0 + (int64_t)sub * CHUNK + (int64_t)threadIdx.x * EPT;
     const int idx0 = (int)(g0 - start);
-    if (idx0 >= n || idx0 + EPT <= 0) continue;
-    uint32_t xs[EPT], ys[EPT];
-    int ps[EPT];
-    load8_u16(x, g0, g.total, vec, xs);
-    load8_u16(y, g0, g.total, vec, ys);
-    if (SPLIT) load8_i8(p, g0, g.total, vec, ps);
-    const bool interior = idx0 >= 0 && idx0 + EPT <= n;
+    full[sub] = vec && idx0 >= 0 && idx0 + EPT <= n;
+    if (full[sub]) {
+      qx[sub] = __ldg(reinterpret_cast<const uint4*>(x + g0));
+      qy[sub] = __ldg(reinterpret_cast<const uint4*>(y + g0));
+      if (SPLIT) qp[sub] = __ldg(reinterpret_cast<const uint2*>(p + g0));
+    }
+  }
+  for (int i = threadIdx.x; i < g.Tb; i += BIN_THREADS) sh_hist[i] = 0;
+  __syncthreads();
+  const uint32_t hbase = (uint32_t)__cvta_generic_to_shared(sh_hist);
+  const uint32_t Wd = (uint32_t)g.W, Hd = (uint32_t)g.H;
+  auto count = [&](uint32_t xe, uint32_t ye, int pe) {
+    if (DIV) {  // pixels are cells of div_x x div_y sensor pixels (the resize filter)
+      xe /= (uint32_t)g.div_x;
+      ye /= (uint32_t)g.div_y;
+    }
+    uint32_t bin = (ye * Wd + xe) >> g.tile_shift;
+    if (SPLIT) bin = (bin << 1) | (pe > 0 ? 0u : 1u);
+    if (xe < Wd && ye < Hd) smem_inc(hbase + (bin << 2));
+  };
 #pragma unroll
-    for (int e = 0; e < EPT; ++e) {
-      if (DIV) {  // pixels are cells of div_x x div_y sensor pixels (the resize filter)
-        xs[e] /= (uint32_t)g.div_x;
-        ys[e] /= (uint32_t)g.div_y;
-      }
-      const bool ok = (interior || (uint32_t)(idx0 + e) < (uint32_t)n) && xs[e] < Wd && ys[e] < Hd;
-      uint32_t bin = (ys[e] * Wd + xs[e]) >> g.tile_shift;
-      if (SPLIT) bin = (bin << 1) | (ps[e] > 0 ? 0u : 1u);
-      if (ok) smem_inc(hbase + (bin << 2));
+  for (int sub = 0; sub < SC_CHUNKS; ++sub) {
+    if (full[sub]) {
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) count(raw_u16(qx[sub], e), raw_u16(qy[sub], e), SPLIT ? raw_i8(qp[sub], e) : 0);
+    } else {
+      const int64_t g0 = c0 + (int64_t)sub * CHUNK + (int64_t)threadIdx.x * EPT;
+      const int idx0 = (int)(g0 - start);
+      if (idx0 >= n || idx0 + EPT <= 0) continue;
+#pragma unroll 1
+      for (int e = 0; e < EPT; ++e)
+        if ((uint32_t)(idx0 + e) < (uint32_t)n) count(__ldg(x + g0 + e), __ldg(y + g0 + e), SPLIT ? (int)__ldg(p + g0 + e) : 0);
     }
   }
   __syncthreads();
@@ -415,7 +440,21 @@ __global__ void __launch_bounds__(BIN_THREADS) k_scan(const uint32_t* __restrict
 
 // ---------------------------------------------------------------------------------------------
 // pass 3: scatter the events into their buckets as 8-byte records.  HBM: reads 9 B/event, writes 8 B/event.
+//
+// A thread owns EPT consecutive events per sub-chunk.  All its loads are issued before the bucket tables are
+// read.  The EPT events take the FAST path when they lie inside the window, are time-sorted (also against the
+// event before them), carry valid polarities and the first / last of them are inside the 31-bit time range
+// (sorted => so are the ones between): then the per-event work is pixel -> bucket -> one returning shared-memory
+// atomic -> one 8-byte + one 2-byte staged store.  Anything else (window edges, unsorted or out-of-range data)
+// goes through the per-event checks of the slow path, which re-reads its events with scalar loads.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool polarities_valid4(uint32_t w) {  // every byte in {0x00, 0x01, 0xff}
+  const uint32_t a = w & 0xfefefefeu, nb = ~w;
+  const uint32_t nza = (((a & 0x7f7f7f7fu) + 0x7f7f7f7fu) | a) & 0x80808080u;     // byte not in {0, 1}
+  const uint32_t nzb = (((nb & 0x7f7f7f7fu) + 0x7f7f7f7fu) | nb) & 0x80808080u;  // byte != 0xff
+  return (nza & nzb) == 0u;
+}
+
 template <typename TT, int MODE, bool SPLIT, bool DIV>
 #ifndef EVREP_BIN_CTAS
 #define EVREP_BIN_CTAS 2
@@ -428,10 +467,10 @@ __global__ void __launch_bounds__(BIN_THREADS, EVREP_BIN_CTAS) k_bin(const uint1
                                                      const uint16_t* __restrict__ cc, const uint32_t* __restrict__ cp,
                                                      uint2* __restrict__ records) {
   extern __shared__ __align__(16) unsigned char sh_raw[];
-  uint2* stage = reinterpret_cast<uint2*>(sh_raw);                    // SUPER records, sorted by bucket
-  uint32_t* sdest = reinterpret_cast<uint32_t*>(stage + SUPER);       // SUPER destinations (relative to the window's first record)
-  uint32_t* lcur = sdest + SUPER;                                     // Tb: next free staged slot of every bucket
-  uint32_t* delta = lcur + g.Tb;                                      // Tb: destination minus staged slot
+  uint2* stage = reinterpret_cast<uint2*>(sh_raw);                 // SUPER records, sorted by bucket
+  uint16_t* sbkt = reinterpret_cast<uint16_t*>(stage + SUPER);     // SUPER: the bucket of every staged record
+  uint32_t* lcur = reinterpret_cast<uint32_t*>(sbkt + SUPER);      // Tb: next free staged slot of every bucket
+  uint32_t* delta = lcur + g.Tb;                                   // Tb: destination minus staged slot
   __shared__ int sh_tmin, sh_tmax;
   __shared__ uint32_t sh_flags, sh_m1;
   __shared__ int32_t sh_snap_idx[MAX_SNAP];
@@ -446,23 +485,25 @@ __global__ void __launch_bounds__(BIN_THREADS, EVREP_BIN_CTAS) k_bin(const uint1
   const int32_t tlast_rel = wp[b].tlast_rel;
   const int64_t c0 = (start & ~(int64_t)(EPT - 1)) + (int64_t)scl * SUPER;
 
-  // the first chunk's events are requested (packed, 18-26 registers) before the bucket tables are built
-  uint4 qx = make_uint4(0, 0, 0, 0), qy = qx;
-  uint2 qp = make_uint2(0, 0);
-  RawT<TT> qt;
-  TT t_before = 0;
-  auto fetch = [&](int sub) {
+  // every event of the thread is requested before the bucket tables are built
+  uint4 qx[SC_CHUNKS], qy[SC_CHUNKS];
+  uint2 qp[SC_CHUNKS];
+  RawT<TT> qt[SC_CHUNKS];
+  TT t_before[SC_CHUNKS];
+  bool full[SC_CHUNKS];
+#pragma unroll
+  for (int sub = 0; sub < SC_CHUNKS; ++sub) {
     const int64_t g0 = c0 + (int64_t)sub * CHUNK + (int64_t)tid * EPT;
-    const int idx0 = (int)(g0 - start);
-    if (idx0 < n && idx0 + EPT > 0) {
-      qx = load8_u16_raw(x, g0, g.total, vec);
-      qy = load8_u16_raw(y, g0, g.total, vec);
-      qp = load8_i8_raw(p, g0, g.total, vec);
-      qt.load(t, g0, g.total, vec);
-      if (idx0 >= 1) t_before = __ldg(t + g0 - 1);
+    const int idx0 = (int)(g0 - start);  // may be < 0 at the head of the window
+    full[sub] = vec && idx0 >= 0 && idx0 + EPT <= n;
+    if (full[sub]) {
+      qx[sub] = __ldg(reinterpret_cast<const uint4*>(x + g0));
+      qy[sub] = __ldg(reinterpret_cast<const uint4*>(y + g0));
+      qp[sub] = __ldg(reinterpret_cast<const uint2*>(p + g0));
+      if (sizeof(TT) == 4 || sub == 0) qt[sub].load_vec(t, g0);  // 64-bit timestamps of later sub-chunks: fetched when needed (registers)
+      t_before[sub] = __ldg(t + g0 - (idx0 >= 1 ? 1 : 0));  // the window's first event is compared with itself
     }
-  };
-  fetch(0);
+  }
 
   const uint16_t* crow = cc + (size_t)blockIdx.x * (g.Tb + 1);  // first staged slot of every bucket (k_hist), then the total
   const uint32_t* brow = base + (size_t)b * g.Tb;
@@ -484,93 +525,116 @@ __global__ void __launch_bounds__(BIN_THREADS, EVREP_BIN_CTAS) k_bin(const uint1
   const int n3 = n / 3, s4 = n / 2, s5 = s4 + n / 4, s6 = s5 + n / 8;
   const uint32_t cur_base = (uint32_t)__cvta_generic_to_shared(lcur);
   const uint32_t Wd = (uint32_t)g.W, Hd = (uint32_t)g.H;
+  const uint32_t pix_mask = (uint32_t)(g.tile_px - 1);
+  const int ns = MODE == REC_T_SNAP ? sh_nsnap : 0;
   int my_tmin = INT_MAX, my_tmax = INT_MIN;
   uint32_t my_flags = 0, my_m1 = 0;
 
-#pragma unroll 1
-  for (int sub = 0; sub < SC_CHUNKS; ++sub) {
-    if (sub) fetch(sub);
-    const int idx0 = (int)(c0 + (int64_t)sub * CHUNK + (int64_t)tid * EPT - start);  // may be < 0 at the head of the window
-    if (idx0 >= n || idx0 + EPT <= 0) continue;
-    const bool interior = idx0 >= 0 && idx0 + EPT <= n;
-    TT t_prev = t_before;
-    bool have_prev = idx0 >= 1;
-    // SBN window mask of an index; a thread's EPT consecutive events nearly always share it
-    auto sbn_mask = [&](int idx) {
+  // SBN window mask of an index / first time-surface snapshot an index feeds; both change monotonically with the
+  // index, so a thread's EPT consecutive events nearly always share one value
+  auto aux_of = [&](int idx) -> uint32_t {
+    if (MODE == REC_T_WMASK)
       return 1u | (idx < n3 ? 2u : (idx < 2 * n3 ? 4u : (idx < 3 * n3 ? 8u : 0u))) | (idx >= s4 ? 16u : 0u) | (idx >= s5 ? 32u : 0u) |
              (idx >= s6 ? 64u : 0u);
-    };
-    uint32_t aux_first = 0;
-    bool aux_uniform = false;
-    if (MODE == REC_T_WMASK) {
-      aux_first = sbn_mask(idx0);
-      aux_uniform = aux_first == sbn_mask(idx0 + EPT - 1);  // the mask changes monotonically with the index
+    if (MODE == REC_T_SNAP) {
+      int s = 0;
+      while (s < ns && idx > sh_snap_idx[s]) ++s;
+      return (uint32_t)s;
     }
+    return 0u;
+  };
+  // one event with a valid pixel and polarity pv in {-1, 0, 1}: rank it inside its bucket and stage its record.
+  // `keep` = false leaves a null record in the slot (the event was counted by k_hist).  Shared memory is addressed
+  // through 32-bit shared-window addresses (the generic form rebuilds the window base around every access).
+  const uint32_t stage_base = (uint32_t)__cvta_generic_to_shared(stage), sbkt_base = (uint32_t)__cvta_generic_to_shared(sbkt);
+  const int tile_shift = g.tile_shift;
+  auto place = [&](uint32_t lin, int pv, int32_t t_rel, int idx, uint32_t aux, bool keep) {
+    uint32_t bin = lin >> tile_shift;
+    if (SPLIT) bin = bin + bin + (pv > 0 ? 0u : 1u);
+    const uint32_t slot = smem_fetch_inc(cur_base + (bin << 2));
+    uint32_t k = (uint32_t)t_rel;
+    if (MODE == REC_IDX) k = (uint32_t)idx;
+    if (MODE == REC_T_SNAP && aux >= (uint32_t)ns) keep = false;  // after the last emitted surface: feeds nothing
+    if (MODE == REC_T_TORE && t_rel >= tlast_rel) keep = false;   // strict `<` against the sample time (tore.py:17)
+    uint32_t meta;
+    if (MODE == REC_T_IDX)
+      meta = fused_meta(lin & pix_mask, (uint32_t)idx, (uint32_t)pv & 3u);
+    else
+      meta = rec_meta(lin & pix_mask, aux, (uint32_t)pv & 3u);
+    if (keep) {
+      my_tmin = min(my_tmin, t_rel);
+      my_tmax = max(my_tmax, t_rel);
+      if (MODE == REC_T_WMASK) my_m1 |= pv == -1 ? aux : 0u;
+    } else {
+      k = 0u;
+      meta = MODE == REC_T_IDX ? FUSED_NULL_META : REC_NULL_META;
+    }
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(stage_base + (slot << 3)), "r"(k), "r"(meta) : "memory");
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(sbkt_base + (slot << 1)), "h"((uint16_t)bin) : "memory");
+  };
+
 #pragma unroll
-    for (int e = 0; e < EPT; ++e) {
-      const int idx = idx0 + e;
-      if (!interior && (uint32_t)idx >= (uint32_t)n) continue;
-      const TT te = qt.get(e);
-      uint32_t xe = raw_u16(qx, e), ye = raw_u16(qy, e);
-      if (DIV) {
-        xe /= (uint32_t)g.div_x;
-        ye /= (uint32_t)g.div_y;
+  for (int sub = 0; sub < SC_CHUNKS; ++sub) {
+    const int64_t g0 = c0 + (int64_t)sub * CHUNK + (int64_t)tid * EPT;
+    const int idx0 = (int)(g0 - start);
+    bool fast = full[sub];
+    if (fast) {
+      if (sizeof(TT) == 8 && sub > 0) qt[sub].load_vec(t, g0);
+      // sorted (also against the previous event), valid polarities, first and last inside the 31-bit range
+      TT prev = t_before[sub];
+      bool sorted = true;
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        const TT te = qt[sub].get(e);
+        sorted &= !(te < prev);
+        prev = te;
       }
-      const int pe = raw_i8(qp, e);
-      if (have_prev && te < t_prev) my_flags |= EVREP_WF_UNSORTED;
-      t_prev = te;
-      have_prev = true;
-      if ((xe >= Wd) | (ye >= Hd)) { my_flags |= EVREP_WF_OUT_OF_RANGE; continue; }  // not counted by k_hist: no slot
-      const uint32_t lin = ye * Wd + xe;
-      uint32_t bin = lin >> g.tile_shift;
-      if (SPLIT) bin = (bin << 1) | (pe > 0 ? 0u : 1u);
-      const uint32_t slot = smem_fetch_inc(cur_base + (bin << 2));
-      uint2 rec = make_uint2(0u, REC_NULL_META);
-      bool keep = true;
-      int32_t t_rel;
-      if constexpr (sizeof(TT) == 4) {  // 32-bit timestamps: the difference in wrapping arithmetic plus an overflow test
-        const int32_t tb = (int32_t)t_base;
-        t_rel = (int32_t)((uint32_t)te - (uint32_t)tb);
-        const bool ovf = (((int32_t)te ^ tb) & ((int32_t)te ^ t_rel)) < 0;
-        if (ovf || (uint32_t)t_rel + (uint32_t)(T_REL_LIMIT - 1) >= 2u * (uint32_t)T_REL_LIMIT - 1u) { my_flags |= EVREP_WF_T_RANGE; keep = false; }
-      } else {
+      const int64_t d0 = (int64_t)qt[sub].get(0) - t_base, d7 = (int64_t)qt[sub].get(EPT - 1) - t_base;
+      const bool in_range = d0 > -(int64_t)T_REL_LIMIT && d7 < (int64_t)T_REL_LIMIT;
+      fast = sorted && in_range && polarities_valid4(qp[sub].x) && polarities_valid4(qp[sub].y);
+    }
+    const uint32_t aux_first = aux_of(idx0);
+    if ((MODE == REC_T_WMASK || MODE == REC_T_SNAP) && aux_first != aux_of(idx0 + EPT - 1)) fast = false;  // a window boundary inside
+    if (fast) {
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        uint32_t xe = raw_u16(qx[sub], e), ye = raw_u16(qy[sub], e);
+        if (DIV) {
+          xe /= (uint32_t)g.div_x;
+          ye /= (uint32_t)g.div_y;
+        }
+        if ((xe >= Wd) | (ye >= Hd)) { my_flags |= EVREP_WF_OUT_OF_RANGE; continue; }  // not counted by k_hist: no slot
+        const int32_t t_rel = sizeof(TT) == 4 ? (int32_t)((uint32_t)qt[sub].get(e) - (uint32_t)t_base) : (int32_t)((int64_t)qt[sub].get(e) - t_base);
+        place(ye * Wd + xe, raw_i8(qp[sub], e), t_rel, idx0 + e, aux_first, true);
+      }
+    } else {
+      if (idx0 >= n || idx0 + EPT <= 0) continue;
+      TT t_prev = 0;
+      bool have_prev = idx0 >= 1;
+      if (have_prev) t_prev = __ldg(t + g0 - 1);
+#pragma unroll 1
+      for (int e = 0; e < EPT; ++e) {
+        const int idx = idx0 + e;
+        if ((uint32_t)idx >= (uint32_t)n) continue;
+        const TT te = __ldg(t + g0 + e);
+        uint32_t xe = __ldg(x + g0 + e), ye = __ldg(y + g0 + e);
+        if (DIV) {
+          xe /= (uint32_t)g.div_x;
+          ye /= (uint32_t)g.div_y;
+        }
+        int pv = __ldg(p + g0 + e);
+        if (have_prev && te < t_prev) my_flags |= EVREP_WF_UNSORTED;
+        t_prev = te;
+        have_prev = true;
+        if ((xe >= Wd) | (ye >= Hd)) { my_flags |= EVREP_WF_OUT_OF_RANGE; continue; }
+        bool keep = true;
         const int64_t d = (int64_t)te - t_base;
         if (d >= T_REL_LIMIT || d <= -T_REL_LIMIT) { my_flags |= EVREP_WF_T_RANGE; keep = false; }
-        t_rel = (int32_t)d;
+        // index-keyed records (EventStack, the filters) carry no timestamp: a stream longer than 2^30 us only raises the flag
+        if (MODE == REC_IDX) keep = true;
+        if (pv > 1 || pv < -1) { my_flags |= EVREP_WF_BAD_POLARITY; pv = pv > 0 ? 1 : -1; }
+        place(ye * Wd + xe, pv, (int32_t)d, idx, aux_of(idx), keep);
       }
-      // index-keyed records (EventStack, the filters) carry no timestamp: a stream longer than 2^30 us only raises the flag
-      if (MODE == REC_IDX) keep = true;
-      int pv = pe;
-      if (pv > 1 || pv < -1) { my_flags |= EVREP_WF_BAD_POLARITY; pv = pv > 0 ? 1 : -1; }
-      uint32_t aux = 0, k = (uint32_t)t_rel;
-      if (MODE == REC_T_WMASK) {
-        aux = aux_uniform ? aux_first : sbn_mask(idx);
-        if (keep) my_m1 |= pv == -1 ? aux : 0u;
-      } else if (MODE == REC_IDX) {
-        k = (uint32_t)idx;
-      } else if (MODE == REC_T_SNAP) {
-        const int ns = sh_nsnap;
-        int s = 0;
-        while (s < ns && idx > sh_snap_idx[s]) ++s;
-        if (s >= ns) keep = false;  // after the last emitted surface: feeds nothing
-        aux = (uint32_t)s;
-      } else if (MODE == REC_T_TORE) {  // strict `<` against the sample time = last timestamp (tore.py:17)
-        if (t_rel >= tlast_rel) keep = false;
-      }
-      if (MODE == REC_T_IDX) {
-        rec = make_uint2(0u, FUSED_NULL_META);
-        if (keep) {
-          my_tmin = min(my_tmin, t_rel);
-          my_tmax = max(my_tmax, t_rel);
-          rec = make_uint2(k, fused_meta(lin & (uint32_t)(g.tile_px - 1), (uint32_t)idx, (uint32_t)pv & 3u));
-        }
-      } else if (keep) {
-        my_tmin = min(my_tmin, t_rel);
-        my_tmax = max(my_tmax, t_rel);
-        rec = make_uint2(k, rec_meta(lin & (uint32_t)(g.tile_px - 1), aux, (uint32_t)pv & 3u));
-      }
-      stage[slot] = rec;
-      sdest[slot] = slot + delta[bin];
     }
   }
   // CTA-wide reductions of the per-window scalars
@@ -591,12 +655,13 @@ __global__ void __launch_bounds__(BIN_THREADS, EVREP_BIN_CTAS) k_bin(const uint1
   }
   // copy out: consecutive threads hold consecutive records of a run
   uint2* dst = records + start;
-  for (uint32_t i = tid; i < total; i += BIN_THREADS) dst[sdest[i]] = stage[i];
+#pragma unroll 4
+  for (uint32_t i = tid; i < total; i += BIN_THREADS) dst[i + delta[sbkt[i]]] = stage[i];
 }
 
 template <typename TT, int MODE, bool SPLIT, bool DIV = false>
 static int launch_bin(const Events& ev, const Geom& g, const Workspace& ws, int n_sc, bool vec, cudaStream_t stream) {
-  const size_t smem = (size_t)SUPER * (sizeof(uint2) + sizeof(uint32_t)) + 2 * sizeof(uint32_t) * (size_t)g.Tb;
+  const size_t smem = (size_t)SUPER * (sizeof(uint2) + sizeof(uint16_t)) + 2 * sizeof(uint32_t) * (size_t)g.Tb;
   EVREP_CUDA_OK(cudaFuncSetAttribute(k_bin<TT, MODE, SPLIT, DIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_bin<TT, MODE, SPLIT, DIV><<<n_sc, BIN_THREADS, smem, stream>>>(ev.x, ev.y, (const TT*)ev.t, ev.p, ws.wp, ws.snap, ws.sc_prefix, ws.sc_win, g, vec,
                                                               ws.base, ws.cc, ws.cp, ws.records);

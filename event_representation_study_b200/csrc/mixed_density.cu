@@ -347,12 +347,17 @@ __device__ __forceinline__ void md_accumulate_at(uint32_t* acc, const uint2 r, u
 }
 
 // TP = pixels per tile (compile time here), PPT = pixels per thread.
-// Persistent CTAs (two per SM) pull (window, tile) buckets from a ticket counter.  Timeline of one bucket:
-// zero the accumulators -> atomics over the bucket's records (already in registers: they were fetched while
-// the previous bucket was being finalised) -> finalise every pixel into registers -> repack the tile's
-// output slice contiguously in shared memory (over the dead accumulators) -> four threads hand 12 KB each to
-// the TMA engine (cp.async.bulk shared -> global).  Header and record loads of the next bucket are issued
-// early, so no global-load latency sits on the critical path after the first bucket.
+// Persistent CTAs (three per SM) pull (window, tile) buckets from a ticket counter.  A warp owns PPT * 32
+// consecutive pixels of the tile, i.e. one contiguous slab of the accumulator array.  Timeline of one bucket:
+//   atomics over the bucket's records (already in registers: they were fetched while the previous bucket was
+//   being finalised)                                                     -> __syncthreads (A)
+//   per warp, no CTA-wide barrier: finalise its pixels into registers, repack the 12 floats of each pixel
+//   contiguously at the head of its own slab (over accumulators it has already consumed), hand the slab's
+//   output (PPT * 32 * C * 4 bytes, contiguous in the output tensor) to the TMA engine with ONE
+//   cp.async.bulk shared -> global, prefetch the next bucket's records, wait until the engine has read the
+//   slab, zero the slab                                                  -> __syncthreads (B)
+// Two CTA barriers per bucket; header and record loads of the next bucket are issued early, so no global-load
+// latency sits on the critical path after the first bucket.
 struct TileHdr {
   int b, pix0;
   uint32_t count, n_pos, has_m1, delta_u;
@@ -384,42 +389,49 @@ __device__ __forceinline__ TileHdr md_load_hdr(int id, const Geom& g, int TP, co
   return h;
 }
 
-// finalise + repack + TMA store of one tile (all threads of the CTA); leaves the bulk store in flight
+// finalise + repack + TMA store of one warp's slab; leaves the bulk store in flight (lane 0 owns the bulk group)
 template <typename PS, int TP>
-__device__ __forceinline__ void md_finalise_store(uint32_t* acc, const TileHdr& h, const Geom& g, float* __restrict__ out) {
+__device__ __forceinline__ void md_finalise_store_warp(uint32_t* slab, const TileHdr& h, const Geom& g, float* __restrict__ out) {
   constexpr int STRIDE = PS::value.stride, C = PS::value.C, PPT = TP / TILE_THREADS;
-  const int tid = threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const double delta = (double)h.delta_u;
   const float inv_delta = 1.f / (float)h.delta_u;
-  float o[PPT][C];
+  float4* stage = reinterpret_cast<float4*>(slab);  // [PPT * 32][C] floats, contiguous = the global layout of the slab's pixels
 #pragma unroll
-  for (int k = 0; k < PPT; ++k)
-    md_finalise_static<PS>(acc + (tid + k * TILE_THREADS) * STRIDE, inv_delta, delta, h.delta_u, h.has_m1, o[k], std::make_integer_sequence<int, C>{});
-  __syncthreads();
-  float4* stage = reinterpret_cast<float4*>(acc);  // [TP][C] floats, contiguous = the global layout of the slice
+  for (int k = 0; k < PPT; ++k) {
+    float o[C];
+    md_finalise_static<PS>(slab + (k * 32 + lane) * STRIDE, inv_delta, delta, h.delta_u, h.has_m1, o, std::make_integer_sequence<int, C>{});
+    __syncwarp();  // every lane has read its accumulators: rows k*32 .. may now be overwritten (C <= STRIDE keeps row k+1 intact)
 #pragma unroll
-  for (int k = 0; k < PPT; ++k)
-#pragma unroll
-    for (int q = 0; q < C / 4; ++q)
-      stage[(tid + k * TILE_THREADS) * (C / 4) + q] = make_float4(o[k][4 * q], o[k][4 * q + 1], o[k][4 * q + 2], o[k][4 * q + 3]);
+    for (int q = 0; q < C / 4; ++q) stage[(k * 32 + lane) * (C / 4) + q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+  }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  __syncthreads();
-  constexpr int SLICE_PX = TP / 4;  // four issuing threads, one per quarter of the tile
-  if ((tid & 31) == 0 && tid < 128) {
-    const int npix = min(TP, g.HW - h.pix0);
-    const int p0 = (tid >> 5) * SLICE_PX;
-    const int np = min(SLICE_PX, npix - p0);
+  __syncwarp();
+  if (lane == 0) {
+    const int p0 = warp * (PPT * 32);
+    const int np = min(PPT * 32, min(TP, g.HW - h.pix0) - p0);
     if (np > 0) {
       float* dst = out + ((size_t)h.b * g.HW + h.pix0 + p0) * C;
-      const uint32_t src = (uint32_t)__cvta_generic_to_shared(acc + p0 * C);
+      const uint32_t src = (uint32_t)__cvta_generic_to_shared(slab);
       const uint32_t bytes = (uint32_t)np * C * 4u;
       asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   }
 }
-__device__ __forceinline__ void md_wait_store() {  // the four issuing threads: the TMA engine has read its source
-  if ((threadIdx.x & 31) == 0 && threadIdx.x < 128) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+// the warp's slab may be written again once the TMA engine has read it
+__device__ __forceinline__ void md_wait_store_warp() {
+  if ((threadIdx.x & 31) == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  __syncwarp();
+}
+template <int WORDS>
+__device__ __forceinline__ void md_zero_slab(uint32_t* slab) {
+  static_assert(WORDS % 4 == 0, "slab size");
+  uint4* a4 = reinterpret_cast<uint4*>(slab);
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < (WORDS / 4 + 31) / 32; ++i)
+    if (i * 32 + lane < WORDS / 4) a4[i * 32 + lane] = make_uint4(0, 0, 0, 0);
 }
 
 // LIGHT_ONLY: the plan is a packed one (16-bit counters / limbs); buckets with >= 65536 events are left to
@@ -430,10 +442,12 @@ __global__ void __launch_bounds__(TILE_THREADS, (PS::value.stride * TP * 4 <= 74
                      const WinParams* __restrict__ wp, const Geom g, uint32_t* __restrict__ ticket, float* __restrict__ out) {
   extern __shared__ __align__(128) uint32_t acc[];
   __shared__ int s_next;
-  constexpr int STRIDE = PS::value.stride, C = PS::value.C;
+  constexpr int STRIDE = PS::value.stride, C = PS::value.C, PPT = TP / TILE_THREADS;
+  constexpr int SLAB = PPT * 32 * STRIDE;  // accumulator words of one warp's pixels
   constexpr int PRE = 3;
   static_assert(PS::value.stacking == EVREP_STACK_SBN && (C & 3) == 0 && TP % TILE_THREADS == 0, "static path: SBN, C % 4 == 0");
   static_assert(C <= STRIDE, "outputs must fit the accumulator footprint");
+  static_assert((SLAB * 4) % 16 == 0, "slabs must start on 16-byte boundaries");
   static_assert(!LIGHT_ONLY || PS::value.packed, "only packed plans have an event limit");
   const int tid = threadIdx.x;
   const int n_tiles = g.B * g.T;
@@ -441,6 +455,7 @@ __global__ void __launch_bounds__(TILE_THREADS, (PS::value.stride * TP * 4 <= 74
   // after next is requested a whole iteration early so that its round trip never stalls the CTA
   int cur = blockIdx.x, nxt = blockIdx.x + (int)gridDim.x;
   if (cur >= n_tiles) return;
+  uint32_t* slab = acc + (tid >> 5) * SLAB;
 
   // buckets are taken last window first: k_bin wrote the last windows' records most recently, so they are the ones
   // still in L2 when this kernel starts
@@ -451,30 +466,16 @@ __global__ void __launch_bounds__(TILE_THREADS, (PS::value.stride * TP * 4 <= 74
     const uint32_t i = tid + j * TILE_THREADS;
     pre[j] = i < h.count ? __ldg(h.rec + i) : make_uint2(0u, 0u);  // meta 0: member of no window, touches nothing
   }
+  md_zero_slab<SLAB>(slab);
+  __syncthreads();
 
-  bool pending = false;  // a TMA store issued by this CTA may still be reading shared memory
   while (true) {
     const bool skip = LIGHT_ONLY && h.count >= MD_PACKED_LIMIT;  // CTA-uniform
     int my_ticket = 0;
     if (tid == 0) my_ticket = (int)atomicAdd(ticket, 1u);  // consumed after the atomics phase
-    if (!skip) {
-      // the first TP*C words may still be read by the TMA store of the previous bucket: clear the rest first
-      uint4* a4 = reinterpret_cast<uint4*>(acc);
-      constexpr int N4 = (STRIDE * TP + 3) / 4, S4 = TP * C / 4;
-#pragma unroll 4
-      for (int i = S4 + tid; i < N4; i += TILE_THREADS) a4[i] = make_uint4(0, 0, 0, 0);
-      if (pending) {
-        md_wait_store();
-        __syncthreads();
-        pending = false;
-      }
-#pragma unroll 4
-      for (int i = tid; i < S4; i += TILE_THREADS) a4[i] = make_uint4(0, 0, 0, 0);
-    }
     const bool more = nxt < n_tiles;
     TileHdr hn = h;
     if (more) hn = md_load_hdr<SPLIT>(n_tiles - 1 - nxt, g, TP, records, base, hist, wp);  // in flight during the atomics below
-    __syncthreads();
 
     if (!skip) {
       const uint32_t not_m1 = ~h.has_m1;
@@ -490,20 +491,19 @@ __global__ void __launch_bounds__(TILE_THREADS, (PS::value.stride * TP * 4 <= 74
       pre[j] = (more && i < hn.count) ? __ldg(hn.rec + i) : make_uint2(0u, 0u);
     }
     if (tid == 0) s_next = my_ticket + 2 * (int)gridDim.x;
-    __syncthreads();
+    __syncthreads();  // (A) every record of the bucket is accumulated
     const int nn = s_next;
 
     if (!skip) {
-      md_finalise_store<PS, TP>(acc, h, g, out);
-      pending = true;
+      md_finalise_store_warp<PS, TP>(slab, h, g, out);
+      md_wait_store_warp();  // shared memory must outlive the engine's read (also at the end of the kernel)
+      md_zero_slab<SLAB>(slab);
     }
-    if (!more) {
-      if (pending) md_wait_store();  // shared memory must outlive the read
-      break;
-    }
+    if (!more) break;
     h = hn;
     cur = nxt;
     nxt = nn;
+    __syncthreads();  // (B) every slab is zero again; s_next may be rewritten
   }
 }
 
@@ -536,8 +536,8 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_md_tile_heavy(const uint2* 
         const uint32_t not_m1 = ~h.has_m1;
         for (uint32_t i = tid; i < h.count; i += TILE_THREADS) md_accumulate_at<PS, SPLIT>(acc, __ldg(h.rec + i), i, h.n_pos, h.tmin, not_m1);
         __syncthreads();
-        md_finalise_store<PS, TP>(acc, h, g, out);
-        md_wait_store();
+        md_finalise_store_warp<PS, TP>(acc + (tid >> 5) * (TP / TILE_THREADS * 32 * STRIDE), h, g, out);
+        md_wait_store_warp();
         __syncthreads();
       }
     }
