@@ -339,9 +339,10 @@ LMO = {"auction": 0, "host": 1}
 
 def gw_kl(Xs, Xt, h=0.7, max_iter=10000, tol_rel=1e-9, tol_abs=1e-9, return_plan=False, device="cuda", lmo="auction", stats=None):
     """GWD-B (gromov_wasserstein.py:39-69): Gaussian kernels of Xs (n, ds) and Xt (m, dt), then conditional-gradient
-    Gromov-Wasserstein with the KL loss.  -> (gw_dist, iterations[, plan (n, m) float32 CUDA tensor]).  n == m only.
-    lmo: "auction" (assignment solved on the GPU) or "host" (exact solver on the CPU); `stats`, if a dict, receives the
-    auction's round / bid counts and the number of steps that fell back to the host solver."""
+    Gromov-Wasserstein with the KL loss.  -> (gw_dist, iterations[, plan (n, m) float32 CUDA tensor]).
+    lmo: "auction" (assignment solved on the GPU, n == m) or "host" (exact solver on the CPU; always used for n != m, where
+    the vertex is a transportation plan); `stats`, if a dict, receives the auction's round / bid counts and the number of
+    steps solved on the host."""
     import ctypes
     dev = torch.device(device)
     Xs = torch.as_tensor(Xs).to(device=dev, dtype=torch.float64).contiguous()
@@ -403,6 +404,25 @@ def assignment_auction(cost, eps_rel=1e-9):
                                        torch.cuda.current_stream(cost.device).cuda_stream))
     r, b, status = (int(v) for v in st.cpu())
     return sigma, {"rounds": r, "bids": b, "status": status}
+
+
+def transport_plan_host(cost):
+    """The rectangular LMO of gw_kl on its own (HOST, no GPU involved): an optimal vertex of
+    min <cost, G> s.t. G 1 = 1/n, G^T 1 = 1/m, G >= 0 for a float32 (n, m) numpy cost -> dense float64 (n, m) plan."""
+    import ctypes
+    import numpy as np
+    cost = np.ascontiguousarray(cost, dtype=np.float32)
+    n, m = cost.shape
+    cap = 2 * (n + m) + 16
+    rp = np.zeros(n + 1, np.int32)
+    col = np.zeros(cap, np.int32)
+    w = np.zeros(cap, np.float64)
+    nnz = ctypes.c_int(0)
+    check(lib.evrep_transport_plan_host(cost.ctypes.data, n, m, cap, rp.ctypes.data, col.ctypes.data, w.ctypes.data, ctypes.byref(nnz)))
+    G = np.zeros((n, m))
+    for i in range(n):
+        G[i, col[rp[i]:rp[i + 1]]] = w[rp[i]:rp[i + 1]]
+    return G
 
 
 FILTERS = {"refractory": 0, "contrast": 1, "resize": 2, "background": 3}

@@ -67,6 +67,7 @@ int launch_est(const uint16_t* x, const uint16_t* y, const float* t, const int8_
                const double* breaks, const double* slope, const double* icpt, int K, float* out, void* workspace, size_t workspace_bytes,
                cudaStream_t stream);
 int launch_auction(const float* cost, int n, double eps_rel, int* sigma, int* stats, cudaStream_t stream);
+int transport_plan_host(const float* cost, int n, int m, int cap, int* row_ptr, int* col, double* weight, int* nnz_out);
 int launch_image_pipeline(const float* rep, int B, int H, int W, int C, int img_size, int mode, int interp, float scale_in, float scale_out,
                           float pad, int reverse, float* out, cudaStream_t stream);
 
@@ -559,6 +560,13 @@ int evrep_assignment_auction(const float* cost, int n, double eps_rel, int* sigm
   EVREP_GUARD_BEGIN
   if (!cost || !sigma || !stats) { set_error("null argument"); return EVREP_EINVAL; }
   return launch_auction(cost, n, eps_rel, sigma, stats, (cudaStream_t)stream);
+  EVREP_GUARD_END
+}
+
+int evrep_transport_plan_host(const float* cost, int n, int m, int cap, int* row_ptr, int* col, double* weight, int* nnz) {
+  EVREP_GUARD_BEGIN
+  if (!cost || !row_ptr || !col || !weight || cap < 1) { set_error("null argument or cap < 1"); return EVREP_EINVAL; }
+  return transport_plan_host(cost, n, m, cap, row_ptr, col, weight, nnz);
   EVREP_GUARD_END
 }
 

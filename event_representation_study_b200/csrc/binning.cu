@@ -331,29 +331,48 @@ __global__ void __launch_bounds__(BIN_THREADS) k_hist(const uint16_t* __restrict
   }
   for (int i = threadIdx.x; i < g.Tb; i += BIN_THREADS) sh_hist[i] = 0;
   __syncthreads();
-  const uint32_t hbase = (uint32_t)__cvta_generic_to_shared(sh_hist);
+  uint32_t hbase = (uint32_t)__cvta_generic_to_shared(sh_hist);
+  asm volatile("" : "+r"(hbase));  // opaque: otherwise the window base is rebuilt around every atomic
   const uint32_t Wd = (uint32_t)g.W, Hd = (uint32_t)g.H;
-  auto count = [&](uint32_t xe, uint32_t ye, int pe) {
-    if (DIV) {  // pixels are cells of div_x x div_y sensor pixels (the resize filter)
-      xe /= (uint32_t)g.div_x;
-      ye /= (uint32_t)g.div_y;
-    }
-    uint32_t bin = (ye * Wd + xe) >> g.tile_shift;
-    if (SPLIT) bin = (bin << 1) | (pe > 0 ? 0u : 1u);
-    if (xe < Wd && ye < Hd) smem_inc(hbase + (bin << 2));
+  const int tile_shift = g.tile_shift;
+  auto bucket = [&](uint32_t xe, uint32_t ye, int pe) {
+    uint32_t bin = (ye * Wd + xe) >> tile_shift;
+    if (SPLIT) bin = bin + bin + (pe > 0 ? 0u : 1u);
+    return bin;
   };
 #pragma unroll
   for (int sub = 0; sub < SC_CHUNKS; ++sub) {
-    if (full[sub]) {
+    bool fast = full[sub];
+    uint32_t xs[EPT], ys[EPT];
+    if (fast) {  // all EPT pixels valid: the common case runs without a branch per event
 #pragma unroll
-      for (int e = 0; e < EPT; ++e) count(raw_u16(qx[sub], e), raw_u16(qy[sub], e), SPLIT ? raw_i8(qp[sub], e) : 0);
+      for (int e = 0; e < EPT; ++e) {
+        xs[e] = raw_u16(qx[sub], e);
+        ys[e] = raw_u16(qy[sub], e);
+        if (DIV) {  // pixels are cells of div_x x div_y sensor pixels (the resize filter)
+          xs[e] /= (uint32_t)g.div_x;
+          ys[e] /= (uint32_t)g.div_y;
+        }
+        fast &= (xs[e] < Wd) & (ys[e] < Hd);
+      }
+    }
+    if (fast) {
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) smem_inc(hbase + (bucket(xs[e], ys[e], SPLIT ? raw_i8(qp[sub], e) : 0) << 2));
     } else {
       const int64_t g0 = c0 + (int64_t)sub * CHUNK + (int64_t)threadIdx.x * EPT;
       const int idx0 = (int)(g0 - start);
       if (idx0 >= n || idx0 + EPT <= 0) continue;
 #pragma unroll 1
-      for (int e = 0; e < EPT; ++e)
-        if ((uint32_t)(idx0 + e) < (uint32_t)n) count(__ldg(x + g0 + e), __ldg(y + g0 + e), SPLIT ? (int)__ldg(p + g0 + e) : 0);
+      for (int e = 0; e < EPT; ++e) {
+        if ((uint32_t)(idx0 + e) >= (uint32_t)n) continue;
+        uint32_t xe = __ldg(x + g0 + e), ye = __ldg(y + g0 + e);
+        if (DIV) {
+          xe /= (uint32_t)g.div_x;
+          ye /= (uint32_t)g.div_y;
+        }
+        if (xe < Wd && ye < Hd) smem_inc(hbase + (bucket(xe, ye, SPLIT ? (int)__ldg(p + g0 + e) : 0) << 2));
+      }
     }
   }
   __syncthreads();
@@ -361,7 +380,7 @@ __global__ void __launch_bounds__(BIN_THREADS) k_hist(const uint16_t* __restrict
   // by bucket) followed by the total: k_bin needs exactly that, k_colscan recovers a count as a difference
   __shared__ uint32_t warp_tot[BIN_THREADS / 32 + 1];
   const uint32_t total = block_exclusive_scan(sh_hist, g.Tb, warp_tot);
-  uint16_t* dst = cc + (size_t)blockIdx.x * (g.Tb + 1);
+  uint16_t* dst = cc + (size_t)blockIdx.x * cc_stride(g.Tb);
   for (int i = threadIdx.x; i < g.Tb; i += BIN_THREADS) dst[i] = (uint16_t)sh_hist[i];  // <= SUPER = 8192
   if (threadIdx.x == 0) dst[g.Tb] = (uint16_t)total;
 }
@@ -388,7 +407,7 @@ __global__ void __launch_bounds__(256) k_colscan(const uint16_t* __restrict__ cc
     uint32_t lo[U], ex[U];
 #pragma unroll
     for (int k = 0; k < U; ++k) {
-      const uint16_t* row = cc + (size_t)(r + k) * (Tb + 1);
+      const uint16_t* row = cc + (size_t)(r + k) * cc_stride(Tb);
       const bool live = ok && r + k < r1;
       lo[k] = live ? (uint32_t)row[c] : 0u;
       ex[k] = (live && edge) ? (uint32_t)row[c + 1] : 0u;
@@ -455,10 +474,224 @@ __device__ __forceinline__ bool polarities_valid4(uint32_t w) {  // every byte i
   return (nza & nzb) == 0u;
 }
 
-template <typename TT, int MODE, bool SPLIT, bool DIV>
 #ifndef EVREP_BIN_CTAS
 #define EVREP_BIN_CTAS 2
 #endif
+
+// what a CTA needs to know about one super-chunk
+struct ChunkHdr {
+  int b, n;        // window, its event count (< 2^31 - 8, checked on the host)
+  int64_t start;   // absolute index of the window's first event
+  int64_t t_base;  // timestamp of the window's first event
+  int64_t c0;      // absolute index of the super-chunk's first event slot (a multiple of EPT)
+  int32_t tlast_rel;
+};
+__device__ __forceinline__ ChunkHdr chunk_hdr(int sc, const WinParams* __restrict__ wp, const int32_t* __restrict__ sc_prefix,
+                                              const int32_t* __restrict__ sc_win) {
+  ChunkHdr h;
+  h.b = __ldg(sc_win + sc);
+  const int scl = sc - __ldg(sc_prefix + h.b);
+  h.start = wp[h.b].start;
+  h.n = (int)wp[h.b].n;
+  h.t_base = wp[h.b].t_base;
+  h.tlast_rel = wp[h.b].tlast_rel;
+  h.c0 = (h.start & ~(int64_t)(EPT - 1)) + (int64_t)scl * SUPER;
+  return h;
+}
+
+// one thread's events of one super-chunk, as loaded (packed)
+template <typename TT>
+struct ChunkRegs {
+  uint4 qx[SC_CHUNKS], qy[SC_CHUNKS];
+  uint2 qp[SC_CHUNKS];
+  RawT<TT> qt[SC_CHUNKS];
+  TT t_before[SC_CHUNKS];
+  bool full[SC_CHUNKS];
+};
+// issues the loads of the thread's events of one sub-chunk; a sub-chunk that is not entirely inside the window (or unaligned
+// arrays) is left to the slow path of chunk_rank, which reads its events with scalar loads
+template <typename TT>
+__device__ __forceinline__ void chunk_fetch_sub(ChunkRegs<TT>& r, const int sub, const ChunkHdr& h, const uint16_t* __restrict__ x,
+                                                const uint16_t* __restrict__ y, const TT* __restrict__ t, const int8_t* __restrict__ p, bool vec,
+                                                int tid) {
+  const int64_t g0 = h.c0 + (int64_t)sub * CHUNK + (int64_t)tid * EPT;
+  const int idx0 = (int)(g0 - h.start);  // may be < 0 at the head of the window
+  r.full[sub] = vec && idx0 >= 0 && idx0 + EPT <= h.n;
+  if (r.full[sub]) {
+    r.qx[sub] = __ldg(reinterpret_cast<const uint4*>(x + g0));
+    r.qy[sub] = __ldg(reinterpret_cast<const uint4*>(y + g0));
+    r.qp[sub] = __ldg(reinterpret_cast<const uint2*>(p + g0));
+    if (sizeof(TT) == 4 || sub == 0) r.qt[sub].load_vec(t, g0);  // 64-bit timestamps of later sub-chunks: fetched when needed (registers)
+    r.t_before[sub] = __ldg(t + g0 - (idx0 >= 1 ? 1 : 0));       // the window's first event is compared with itself
+  }
+}
+template <typename TT>
+__device__ __forceinline__ void chunk_fetch(ChunkRegs<TT>& r, const ChunkHdr& h, const uint16_t* __restrict__ x, const uint16_t* __restrict__ y,
+                                            const TT* __restrict__ t, const int8_t* __restrict__ p, bool vec, int tid) {
+#pragma unroll
+  for (int sub = 0; sub < SC_CHUNKS; ++sub) chunk_fetch_sub<TT>(r, sub, h, x, y, t, p, vec, tid);
+}
+
+struct BinAcc {  // per-thread partial results of the window scalars
+  int tmin = INT_MAX, tmax = INT_MIN;
+  uint32_t flags = 0, m1 = 0;
+};
+struct BinSmem {  // 32-bit shared-window addresses (opaque to the compiler: no rebuild of the window base per access)
+  uint32_t stage, sbkt, lcur;
+};
+
+// ranks the thread's events of one super-chunk inside their buckets and stages their records
+template <typename TT, int MODE, bool SPLIT, bool DIV>
+__device__ __forceinline__ void chunk_rank(ChunkRegs<TT>& r, const ChunkHdr& h, const uint16_t* __restrict__ x, const uint16_t* __restrict__ y,
+                                           const TT* __restrict__ t, const int8_t* __restrict__ p, const Geom& g, const BinSmem sm,
+                                           const int32_t* sh_snap_idx, const int ns, BinAcc& acc, int tid) {
+  const int n = h.n;
+  const int64_t start = h.start, t_base = h.t_base;
+  const int32_t tlast_rel = h.tlast_rel;
+  // index boundaries of the SBN windows (mixed_density_event_stack.py:55-74)
+  const int n3 = n / 3, s4 = n / 2, s5 = s4 + n / 4, s6 = s5 + n / 8;
+  const uint32_t Wd = (uint32_t)g.W, Hd = (uint32_t)g.H;
+  const uint32_t pix_mask = (uint32_t)(g.tile_px - 1);
+  const int tile_shift = g.tile_shift;
+
+  // SBN window mask of an index / first time-surface snapshot an index feeds; both change monotonically with the
+  // index, so a thread's EPT consecutive events nearly always share one value
+  auto aux_of = [&](int idx) -> uint32_t {
+    if (MODE == REC_T_WMASK)
+      return 1u | (idx < n3 ? 2u : (idx < 2 * n3 ? 4u : (idx < 3 * n3 ? 8u : 0u))) | (idx >= s4 ? 16u : 0u) | (idx >= s5 ? 32u : 0u) |
+             (idx >= s6 ? 64u : 0u);
+    if (MODE == REC_T_SNAP) {
+      int s = 0;
+      while (s < ns && idx > sh_snap_idx[s]) ++s;
+      return (uint32_t)s;
+    }
+    return 0u;
+  };
+  // one event with a valid pixel and polarity pv in {-1, 0, 1}: rank it inside its bucket and stage its record.
+  // `keep` = false leaves a null record in the slot (the event was counted by k_hist).
+  auto place = [&](uint32_t lin, int pv, int32_t t_rel, int idx, uint32_t aux, bool keep) {
+    uint32_t bin = lin >> tile_shift;
+    if (SPLIT) bin = bin + bin + (pv > 0 ? 0u : 1u);
+    const uint32_t slot = smem_fetch_inc(sm.lcur + (bin << 2));
+    uint32_t k = (uint32_t)t_rel;
+    if (MODE == REC_IDX) k = (uint32_t)idx;
+    if (MODE == REC_T_SNAP && aux >= (uint32_t)ns) keep = false;  // after the last emitted surface: feeds nothing
+    if (MODE == REC_T_TORE && t_rel >= tlast_rel) keep = false;   // strict `<` against the sample time (tore.py:17)
+    uint32_t meta;
+    if (MODE == REC_T_IDX)
+      meta = fused_meta(lin & pix_mask, (uint32_t)idx, (uint32_t)pv & 3u);
+    else
+      meta = rec_meta(lin & pix_mask, aux, (uint32_t)pv & 3u);
+    if (keep) {
+      acc.tmin = min(acc.tmin, t_rel);
+      acc.tmax = max(acc.tmax, t_rel);
+      if (MODE == REC_T_WMASK) acc.m1 |= pv == -1 ? aux : 0u;
+    } else {
+      k = 0u;
+      meta = MODE == REC_T_IDX ? FUSED_NULL_META : REC_NULL_META;
+    }
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sm.stage + (slot << 3)), "r"(k), "r"(meta) : "memory");
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(sm.sbkt + (slot << 1)), "h"((uint16_t)bin) : "memory");
+  };
+
+#pragma unroll
+  for (int sub = 0; sub < SC_CHUNKS; ++sub) {
+    const int64_t g0 = h.c0 + (int64_t)sub * CHUNK + (int64_t)tid * EPT;
+    const int idx0 = (int)(g0 - start);
+    bool fast = r.full[sub];
+    if (fast) {
+      if (sizeof(TT) == 8 && sub > 0) r.qt[sub].load_vec(t, g0);
+      // sorted (also against the previous event), valid polarities, first and last inside the 31-bit range
+      TT prev = r.t_before[sub];
+      bool sorted = true;
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        const TT te = r.qt[sub].get(e);
+        sorted &= !(te < prev);
+        prev = te;
+      }
+      const int64_t d0 = (int64_t)r.qt[sub].get(0) - t_base, d7 = (int64_t)r.qt[sub].get(EPT - 1) - t_base;
+      const bool in_range = d0 > -(int64_t)T_REL_LIMIT && d7 < (int64_t)T_REL_LIMIT;
+      fast = sorted && in_range && polarities_valid4(r.qp[sub].x) && polarities_valid4(r.qp[sub].y);
+    }
+    const uint32_t aux_first = aux_of(idx0);
+    if ((MODE == REC_T_WMASK || MODE == REC_T_SNAP) && aux_first != aux_of(idx0 + EPT - 1)) fast = false;  // a window boundary inside
+    uint32_t lin[EPT];
+    if (fast) {  // every pixel valid (an invalid one has no slot: k_hist did not count it)
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        uint32_t xe = raw_u16(r.qx[sub], e), ye = raw_u16(r.qy[sub], e);
+        if (DIV) {
+          xe /= (uint32_t)g.div_x;
+          ye /= (uint32_t)g.div_y;
+        }
+        fast &= (xe < Wd) & (ye < Hd);
+        lin[e] = ye * Wd + xe;
+      }
+    }
+    if (fast) {
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        const int32_t t_rel = sizeof(TT) == 4 ? (int32_t)((uint32_t)r.qt[sub].get(e) - (uint32_t)t_base) : (int32_t)((int64_t)r.qt[sub].get(e) - t_base);
+        place(lin[e], raw_i8(r.qp[sub], e), t_rel, idx0 + e, aux_first, true);
+      }
+    } else {
+      if (idx0 >= n || idx0 + EPT <= 0) continue;
+      TT t_prev = 0;
+      bool have_prev = idx0 >= 1;
+      if (have_prev) t_prev = __ldg(t + g0 - 1);
+#pragma unroll 1
+      for (int e = 0; e < EPT; ++e) {
+        const int idx = idx0 + e;
+        if ((uint32_t)idx >= (uint32_t)n) continue;
+        const TT te = __ldg(t + g0 + e);
+        uint32_t xe = __ldg(x + g0 + e), ye = __ldg(y + g0 + e);
+        if (DIV) {
+          xe /= (uint32_t)g.div_x;
+          ye /= (uint32_t)g.div_y;
+        }
+        int pv = __ldg(p + g0 + e);
+        if (have_prev && te < t_prev) acc.flags |= EVREP_WF_UNSORTED;
+        t_prev = te;
+        have_prev = true;
+        if ((xe >= Wd) | (ye >= Hd)) { acc.flags |= EVREP_WF_OUT_OF_RANGE; continue; }  // not counted by k_hist: no slot
+        bool keep = true;
+        const int64_t d = (int64_t)te - t_base;
+        if (d >= T_REL_LIMIT || d <= -T_REL_LIMIT) { acc.flags |= EVREP_WF_T_RANGE; keep = false; }
+        // index-keyed records (EventStack, the filters) carry no timestamp: a stream longer than 2^30 us only raises the flag
+        if (MODE == REC_IDX) keep = true;
+        if (pv > 1 || pv < -1) { acc.flags |= EVREP_WF_BAD_POLARITY; pv = pv > 0 ? 1 : -1; }
+        place(ye * Wd + xe, pv, (int32_t)d, idx, aux_of(idx), keep);
+      }
+    }
+  }
+}
+
+// CTA-wide reduction of the per-window scalars into wp[b] (ends with the threads past a __syncthreads)
+__device__ __forceinline__ void bin_publish(BinAcc acc, WinParams* __restrict__ wpb, int* sh_tmin, int* sh_tmax, uint32_t* sh_flags, uint32_t* sh_m1,
+                                            int tid) {
+  acc.tmin = __reduce_min_sync(0xffffffffu, acc.tmin);
+  acc.tmax = __reduce_max_sync(0xffffffffu, acc.tmax);
+  acc.flags = __reduce_or_sync(0xffffffffu, acc.flags);
+  acc.m1 = __reduce_or_sync(0xffffffffu, acc.m1);
+  if ((tid & 31) == 0) {
+    if (acc.tmin != INT_MAX) { atomicMin(sh_tmin, acc.tmin); atomicMax(sh_tmax, acc.tmax); }
+    if (acc.flags) atomicOr(sh_flags, acc.flags);
+    if (acc.m1) atomicOr(sh_m1, acc.m1);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (*sh_tmin != INT_MAX) { atomicMin(&wpb->tmin_rel, *sh_tmin); atomicMax(&wpb->tmax_rel, *sh_tmax); }
+    if (*sh_flags) atomicOr(&wpb->flags, *sh_flags);
+    if (*sh_m1) atomicOr(&wpb->has_m1, *sh_m1);
+  }
+}
+
+// one CTA per super-chunk.  (A persistent, software-pipelined variant - next super-chunk's events in registers and its table
+// rows on their way by cp.async during the copy-out - was measured slower, 0.212 against 0.169 ms: the kernel is bound by the
+// shared-memory pipe (l1tex 70 % busy), not by exposed global-load latency, and the second CTA of the SM already fills
+// the head of the first; profiles/README.md.)
+template <typename TT, int MODE, bool SPLIT, bool DIV>
 __global__ void __launch_bounds__(BIN_THREADS, EVREP_BIN_CTAS) k_bin(const uint16_t* __restrict__ x, const uint16_t* __restrict__ y,
                                                      const TT* __restrict__ t, const int8_t* __restrict__ p,
                                                      WinParams* __restrict__ wp, const SnapParams* __restrict__ snap,
@@ -477,36 +710,12 @@ __global__ void __launch_bounds__(BIN_THREADS, EVREP_BIN_CTAS) k_bin(const uint1
   __shared__ int sh_nsnap;
 
   const int tid = threadIdx.x;
-  const int b = __ldg(sc_win + blockIdx.x);
-  const int scl = blockIdx.x - __ldg(sc_prefix + b);
-  const int64_t start = wp[b].start;
-  const int n = (int)wp[b].n;  // < 2^31 - 8 (checked on the host)
-  const int64_t t_base = wp[b].t_base;
-  const int32_t tlast_rel = wp[b].tlast_rel;
-  const int64_t c0 = (start & ~(int64_t)(EPT - 1)) + (int64_t)scl * SUPER;
+  const ChunkHdr h = chunk_hdr(blockIdx.x, wp, sc_prefix, sc_win);
+  ChunkRegs<TT> r;
+  chunk_fetch<TT>(r, h, x, y, t, p, vec, tid);  // every event of the thread is requested before the bucket tables are built
 
-  // every event of the thread is requested before the bucket tables are built
-  uint4 qx[SC_CHUNKS], qy[SC_CHUNKS];
-  uint2 qp[SC_CHUNKS];
-  RawT<TT> qt[SC_CHUNKS];
-  TT t_before[SC_CHUNKS];
-  bool full[SC_CHUNKS];
-#pragma unroll
-  for (int sub = 0; sub < SC_CHUNKS; ++sub) {
-    const int64_t g0 = c0 + (int64_t)sub * CHUNK + (int64_t)tid * EPT;
-    const int idx0 = (int)(g0 - start);  // may be < 0 at the head of the window
-    full[sub] = vec && idx0 >= 0 && idx0 + EPT <= n;
-    if (full[sub]) {
-      qx[sub] = __ldg(reinterpret_cast<const uint4*>(x + g0));
-      qy[sub] = __ldg(reinterpret_cast<const uint4*>(y + g0));
-      qp[sub] = __ldg(reinterpret_cast<const uint2*>(p + g0));
-      if (sizeof(TT) == 4 || sub == 0) qt[sub].load_vec(t, g0);  // 64-bit timestamps of later sub-chunks: fetched when needed (registers)
-      t_before[sub] = __ldg(t + g0 - (idx0 >= 1 ? 1 : 0));  // the window's first event is compared with itself
-    }
-  }
-
-  const uint16_t* crow = cc + (size_t)blockIdx.x * (g.Tb + 1);  // first staged slot of every bucket (k_hist), then the total
-  const uint32_t* brow = base + (size_t)b * g.Tb;
+  const uint16_t* crow = cc + (size_t)blockIdx.x * cc_stride(g.Tb);  // first staged slot of every bucket (k_hist), then the total
+  const uint32_t* brow = base + (size_t)h.b * g.Tb;
   const uint32_t* prow = cp + (size_t)blockIdx.x * g.Tb;
   for (int i = tid; i < g.Tb; i += BIN_THREADS) {
     const uint32_t lo = (uint32_t)__ldg(crow + i);
@@ -516,145 +725,21 @@ __global__ void __launch_bounds__(BIN_THREADS, EVREP_BIN_CTAS) k_bin(const uint1
   const uint32_t total = (uint32_t)__ldg(crow + g.Tb);
   if (tid == 0) { sh_tmin = INT_MAX; sh_tmax = INT_MIN; sh_flags = 0; sh_m1 = 0; sh_nsnap = 0; }
   if (MODE == REC_T_SNAP) {
-    if (tid < MAX_SNAP) sh_snap_idx[tid] = snap[b].idx[tid];
-    if (tid == 0) sh_nsnap = snap[b].n_valid;
+    if (tid < MAX_SNAP) sh_snap_idx[tid] = snap[h.b].idx[tid];
+    if (tid == 0) sh_nsnap = snap[h.b].n_valid;
   }
   __syncthreads();
 
-  // index boundaries of the SBN windows (mixed_density_event_stack.py:55-74)
-  const int n3 = n / 3, s4 = n / 2, s5 = s4 + n / 4, s6 = s5 + n / 8;
-  const uint32_t cur_base = (uint32_t)__cvta_generic_to_shared(lcur);
-  const uint32_t Wd = (uint32_t)g.W, Hd = (uint32_t)g.H;
-  const uint32_t pix_mask = (uint32_t)(g.tile_px - 1);
-  const int ns = MODE == REC_T_SNAP ? sh_nsnap : 0;
-  int my_tmin = INT_MAX, my_tmax = INT_MIN;
-  uint32_t my_flags = 0, my_m1 = 0;
-
-  // SBN window mask of an index / first time-surface snapshot an index feeds; both change monotonically with the
-  // index, so a thread's EPT consecutive events nearly always share one value
-  auto aux_of = [&](int idx) -> uint32_t {
-    if (MODE == REC_T_WMASK)
-      return 1u | (idx < n3 ? 2u : (idx < 2 * n3 ? 4u : (idx < 3 * n3 ? 8u : 0u))) | (idx >= s4 ? 16u : 0u) | (idx >= s5 ? 32u : 0u) |
-             (idx >= s6 ? 64u : 0u);
-    if (MODE == REC_T_SNAP) {
-      int s = 0;
-      while (s < ns && idx > sh_snap_idx[s]) ++s;
-      return (uint32_t)s;
-    }
-    return 0u;
-  };
-  // one event with a valid pixel and polarity pv in {-1, 0, 1}: rank it inside its bucket and stage its record.
-  // `keep` = false leaves a null record in the slot (the event was counted by k_hist).  Shared memory is addressed
-  // through 32-bit shared-window addresses (the generic form rebuilds the window base around every access).
-  const uint32_t stage_base = (uint32_t)__cvta_generic_to_shared(stage), sbkt_base = (uint32_t)__cvta_generic_to_shared(sbkt);
-  const int tile_shift = g.tile_shift;
-  auto place = [&](uint32_t lin, int pv, int32_t t_rel, int idx, uint32_t aux, bool keep) {
-    uint32_t bin = lin >> tile_shift;
-    if (SPLIT) bin = bin + bin + (pv > 0 ? 0u : 1u);
-    const uint32_t slot = smem_fetch_inc(cur_base + (bin << 2));
-    uint32_t k = (uint32_t)t_rel;
-    if (MODE == REC_IDX) k = (uint32_t)idx;
-    if (MODE == REC_T_SNAP && aux >= (uint32_t)ns) keep = false;  // after the last emitted surface: feeds nothing
-    if (MODE == REC_T_TORE && t_rel >= tlast_rel) keep = false;   // strict `<` against the sample time (tore.py:17)
-    uint32_t meta;
-    if (MODE == REC_T_IDX)
-      meta = fused_meta(lin & pix_mask, (uint32_t)idx, (uint32_t)pv & 3u);
-    else
-      meta = rec_meta(lin & pix_mask, aux, (uint32_t)pv & 3u);
-    if (keep) {
-      my_tmin = min(my_tmin, t_rel);
-      my_tmax = max(my_tmax, t_rel);
-      if (MODE == REC_T_WMASK) my_m1 |= pv == -1 ? aux : 0u;
-    } else {
-      k = 0u;
-      meta = MODE == REC_T_IDX ? FUSED_NULL_META : REC_NULL_META;
-    }
-    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(stage_base + (slot << 3)), "r"(k), "r"(meta) : "memory");
-    asm volatile("st.shared.u16 [%0], %1;" ::"r"(sbkt_base + (slot << 1)), "h"((uint16_t)bin) : "memory");
-  };
-
-#pragma unroll
-  for (int sub = 0; sub < SC_CHUNKS; ++sub) {
-    const int64_t g0 = c0 + (int64_t)sub * CHUNK + (int64_t)tid * EPT;
-    const int idx0 = (int)(g0 - start);
-    bool fast = full[sub];
-    if (fast) {
-      if (sizeof(TT) == 8 && sub > 0) qt[sub].load_vec(t, g0);
-      // sorted (also against the previous event), valid polarities, first and last inside the 31-bit range
-      TT prev = t_before[sub];
-      bool sorted = true;
-#pragma unroll
-      for (int e = 0; e < EPT; ++e) {
-        const TT te = qt[sub].get(e);
-        sorted &= !(te < prev);
-        prev = te;
-      }
-      const int64_t d0 = (int64_t)qt[sub].get(0) - t_base, d7 = (int64_t)qt[sub].get(EPT - 1) - t_base;
-      const bool in_range = d0 > -(int64_t)T_REL_LIMIT && d7 < (int64_t)T_REL_LIMIT;
-      fast = sorted && in_range && polarities_valid4(qp[sub].x) && polarities_valid4(qp[sub].y);
-    }
-    const uint32_t aux_first = aux_of(idx0);
-    if ((MODE == REC_T_WMASK || MODE == REC_T_SNAP) && aux_first != aux_of(idx0 + EPT - 1)) fast = false;  // a window boundary inside
-    if (fast) {
-#pragma unroll
-      for (int e = 0; e < EPT; ++e) {
-        uint32_t xe = raw_u16(qx[sub], e), ye = raw_u16(qy[sub], e);
-        if (DIV) {
-          xe /= (uint32_t)g.div_x;
-          ye /= (uint32_t)g.div_y;
-        }
-        if ((xe >= Wd) | (ye >= Hd)) { my_flags |= EVREP_WF_OUT_OF_RANGE; continue; }  // not counted by k_hist: no slot
-        const int32_t t_rel = sizeof(TT) == 4 ? (int32_t)((uint32_t)qt[sub].get(e) - (uint32_t)t_base) : (int32_t)((int64_t)qt[sub].get(e) - t_base);
-        place(ye * Wd + xe, raw_i8(qp[sub], e), t_rel, idx0 + e, aux_first, true);
-      }
-    } else {
-      if (idx0 >= n || idx0 + EPT <= 0) continue;
-      TT t_prev = 0;
-      bool have_prev = idx0 >= 1;
-      if (have_prev) t_prev = __ldg(t + g0 - 1);
-#pragma unroll 1
-      for (int e = 0; e < EPT; ++e) {
-        const int idx = idx0 + e;
-        if ((uint32_t)idx >= (uint32_t)n) continue;
-        const TT te = __ldg(t + g0 + e);
-        uint32_t xe = __ldg(x + g0 + e), ye = __ldg(y + g0 + e);
-        if (DIV) {
-          xe /= (uint32_t)g.div_x;
-          ye /= (uint32_t)g.div_y;
-        }
-        int pv = __ldg(p + g0 + e);
-        if (have_prev && te < t_prev) my_flags |= EVREP_WF_UNSORTED;
-        t_prev = te;
-        have_prev = true;
-        if ((xe >= Wd) | (ye >= Hd)) { my_flags |= EVREP_WF_OUT_OF_RANGE; continue; }
-        bool keep = true;
-        const int64_t d = (int64_t)te - t_base;
-        if (d >= T_REL_LIMIT || d <= -T_REL_LIMIT) { my_flags |= EVREP_WF_T_RANGE; keep = false; }
-        // index-keyed records (EventStack, the filters) carry no timestamp: a stream longer than 2^30 us only raises the flag
-        if (MODE == REC_IDX) keep = true;
-        if (pv > 1 || pv < -1) { my_flags |= EVREP_WF_BAD_POLARITY; pv = pv > 0 ? 1 : -1; }
-        place(ye * Wd + xe, pv, (int32_t)d, idx, aux_of(idx), keep);
-      }
-    }
-  }
-  // CTA-wide reductions of the per-window scalars
-  my_tmin = __reduce_min_sync(0xffffffffu, my_tmin);
-  my_tmax = __reduce_max_sync(0xffffffffu, my_tmax);
-  my_flags = __reduce_or_sync(0xffffffffu, my_flags);
-  my_m1 = __reduce_or_sync(0xffffffffu, my_m1);
-  if ((tid & 31) == 0) {
-    if (my_tmin != INT_MAX) { atomicMin(&sh_tmin, my_tmin); atomicMax(&sh_tmax, my_tmax); }
-    if (my_flags) atomicOr(&sh_flags, my_flags);
-    if (my_m1) atomicOr(&sh_m1, my_m1);
-  }
-  __syncthreads();
-  if (tid == 0) {
-    if (sh_tmin != INT_MAX) { atomicMin(&wp[b].tmin_rel, sh_tmin); atomicMax(&wp[b].tmax_rel, sh_tmax); }
-    if (sh_flags) atomicOr(&wp[b].flags, sh_flags);
-    if (sh_m1) atomicOr(&wp[b].has_m1, sh_m1);
-  }
+  BinSmem sm;
+  sm.stage = (uint32_t)__cvta_generic_to_shared(stage);
+  sm.sbkt = (uint32_t)__cvta_generic_to_shared(sbkt);
+  sm.lcur = (uint32_t)__cvta_generic_to_shared(lcur);
+  asm volatile("" : "+r"(sm.stage), "+r"(sm.sbkt), "+r"(sm.lcur));
+  BinAcc acc;
+  chunk_rank<TT, MODE, SPLIT, DIV>(r, h, x, y, t, p, g, sm, sh_snap_idx, MODE == REC_T_SNAP ? sh_nsnap : 0, acc, tid);
+  bin_publish(acc, wp + h.b, &sh_tmin, &sh_tmax, &sh_flags, &sh_m1, tid);
   // copy out: consecutive threads hold consecutive records of a run
-  uint2* dst = records + start;
+  uint2* dst = records + h.start;
 #pragma unroll 4
   for (uint32_t i = tid; i < total; i += BIN_THREADS) dst[i + delta[sbkt[i]]] = stage[i];
 }

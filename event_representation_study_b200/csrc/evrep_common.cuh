@@ -85,7 +85,7 @@ struct Workspace {  // device pointers carved out of the caller's buffer
   uint32_t* ticket;    // 64 words: work counters of persistent kernels
   uint32_t* hist;      // B*Tb  bucket sizes (events with valid x, y; dropped ones keep a null record)
   uint32_t* base;      // B*Tb  bucket start, relative to the window's first record
-  uint16_t* cc;        // n_sc*(Tb+1)  per super-chunk: exclusive scan of its bucket counts, then the total (<= SUPER)
+  uint16_t* cc;        // n_sc*cc_stride(Tb)  per super-chunk: exclusive scan of its bucket counts, then the total (<= SUPER)
   uint32_t* cp;        // n_sc*Tb  exclusive prefix of cc over the window's super-chunks: where the super-chunk's run starts inside the bucket
   SnapParams* snap;    // B
   int64_t* snap_in;  // B*MAX_SNAP caller-supplied snapshot indices
@@ -95,6 +95,8 @@ struct Workspace {  // device pointers carved out of the caller's buffer
 };
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+// row stride of `cc` in entries: Tb offsets + the total, padded to an even count so that every row starts 4-byte aligned
+__host__ __device__ inline int cc_stride(int Tb) { return (Tb + 2) & ~1; }
 
 // Carves the workspace; with base == nullptr only computes the size.
 inline int64_t max_super_chunks(int B, int64_t total) { return total / SUPER + 2 * (int64_t)B + 1; }
@@ -116,7 +118,7 @@ inline Workspace carve(void* basep, int B, int64_t total, int T) {
   w.ticket = (uint32_t*)take(sizeof(uint32_t) * 64);
   w.hist = (uint32_t*)take(sizeof(uint32_t) * (size_t)B * T);
   w.base = (uint32_t*)take(sizeof(uint32_t) * (size_t)B * T);
-  w.cc = (uint16_t*)take(sizeof(uint16_t) * n_sc * ((size_t)T + 1));
+  w.cc = (uint16_t*)take(sizeof(uint16_t) * n_sc * (size_t)cc_stride(T));
   w.cp = (uint32_t*)take(sizeof(uint32_t) * n_sc * (size_t)T);
   w.snap = (SnapParams*)take(sizeof(SnapParams) * (size_t)B);
   w.snap_in = (int64_t*)take(sizeof(int64_t) * (size_t)B * MAX_SNAP);

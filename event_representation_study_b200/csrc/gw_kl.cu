@@ -539,14 +539,14 @@ __global__ void __launch_bounds__(256) k_gwb_grad(int n, int m, const float* __r
 //   red[0] = sum AdG * dG,  red[1] = sum constC * dG,  red[2] = sum AG * dG,  red[3] = sum AdG * G
 __global__ void __launch_bounds__(256) k_gwb_linesearch(int n, int m, const float* __restrict__ cr, const float* __restrict__ cc,
                                                         const float* __restrict__ AG, const float* __restrict__ AGc, const float* __restrict__ G,
-                                                        const int* __restrict__ sigma, double* __restrict__ red) {
+                                                        const int* __restrict__ sigma, const float* __restrict__ Gc, double* __restrict__ red) {
   const size_t total = (size_t)n * m;
   const double inv_n = 1.0 / (double)n;
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     const int i = (int)(e / m), j = (int)(e - (size_t)i * m);
     const double g = (double)G[e];
-    const double dg = ((sigma[i] == j) ? inv_n : 0.0) - g;
+    const double dg = (Gc ? (double)Gc[e] : ((sigma[i] == j) ? inv_n : 0.0)) - g;  // Gc: dense vertex (rectangular plans)
     const double ag = (double)AG[e];
     const double adg = (double)AGc[e] - ag;
     s0 += adg * dg;
@@ -569,15 +569,35 @@ __global__ void __launch_bounds__(256) k_gwb_linesearch(int n, int m, const floa
 }
 
 // G += alpha (Gc - G),  AG += alpha (AGc - AG)
-__global__ void k_gwb_step(int n, int m, float alpha, const int* __restrict__ sigma, const float* __restrict__ AGc, float* __restrict__ G,
-                           float* __restrict__ AG) {
+__global__ void k_gwb_step(int n, int m, float alpha, const int* __restrict__ sigma, const float* __restrict__ Gc, const float* __restrict__ AGc,
+                           float* __restrict__ G, float* __restrict__ AG) {
   const size_t total = (size_t)n * m;
   const float inv_n = 1.f / (float)n;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     const int i = (int)(e / m), j = (int)(e - (size_t)i * m);
     const float g = G[e], ag = AG[e];
-    G[e] = g + alpha * (((sigma[i] == j) ? inv_n : 0.f) - g);
+    G[e] = g + alpha * ((Gc ? Gc[e] : ((sigma[i] == j) ? inv_n : 0.f)) - g);
     AG[e] = ag + alpha * (AGc[e] - ag);
+  }
+}
+
+// Rectangular plans (n != m): the LMO vertex comes from the host in CSR form (transport.cu).
+// Gc (dense n x m) = the vertex, for the line search and the update
+__global__ void k_gwb_plan_scatter(const int* __restrict__ row_ptr, const int* __restrict__ col, const float* __restrict__ wgt, int n, int m,
+                                   float* __restrict__ Gc) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    for (int e = row_ptr[i]; e < row_ptr[i + 1]; ++e) Gc[(size_t)i * m + col[e]] = wgt[e];
+}
+// XT[j, k] = sum_l Gc[k, l] hC2[j, l]  (m x n): the sparse half of hC1 Gc hC2^T; the dense half is one GEMM with hC1
+__global__ void k_gwb_sparse_xt(const float* __restrict__ hC2, const int* __restrict__ row_ptr, const int* __restrict__ col,
+                                const float* __restrict__ wgt, int m, int n, float* __restrict__ XT) {
+  const size_t total = (size_t)m * n;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(e / n), k = (int)(e - (size_t)j * n);
+    const float* row = hC2 + (size_t)j * m;
+    float s = 0.f;
+    for (int q = row_ptr[k]; q < row_ptr[k + 1]; ++q) s = fmaf(wgt[q], row[col[q]], s);
+    XT[e] = s;
   }
 }
 
@@ -596,6 +616,8 @@ __global__ void k_gwb_step(int n, int m, float alpha, const int* __restrict__ si
 // nearly constant cost matrix of an n = 2 problem before the shift); rounds are separated by __syncthreads only.  A round with few
 // bidders costs one row scan (~3 us), which is what most of the thousands of rounds are.
 // ---------------------------------------------------------------------------------------------
+int transport_plan_host(const float* cost, int n, int m, int cap, int* row_ptr, int* col, double* weight, int* nnz_out);  // transport.cu
+
 constexpr int AUC_THREADS = 1024;
 constexpr int AUC_MAX_N = 4096;
 static size_t auction_smem_bytes(int n) { return (size_t)n * (3 * sizeof(double) + 5 * sizeof(int)) + 16; }
@@ -786,6 +808,9 @@ int launch_auction(const float* cost, int n, double eps_rel, int* sigma, int* st
 
 struct GwbWs {
   float *hC1, *hC2, *G, *AG, *AGc, *Mi, *Bp, *cr, *cc;
+  float *Gc, *plan_w;          // n != m: dense LMO vertex, CSR weights
+  int *plan_rp, *plan_col;     // CSR of the vertex (capacity plan_cap)
+  int plan_cap;
   void *imgA, *imgB;  // operand images of the contraction (k_gemm_pack)
   double *rs_a1, *rs_a2, *rs_h1, *rs_h2, *red, *msq;
   int *sigma, *stats;
@@ -820,6 +845,11 @@ static GwbWs gwb_carve(void* basep, int n, int m) {
   w.msq = (double*)take(sizeof(double) * 2);
   w.sigma = (int*)take(sizeof(int) * (size_t)n);
   w.stats = (int*)take(sizeof(int) * 4);
+  w.plan_cap = 2 * (n + m) + 16;
+  w.Gc = (float*)take(n != m ? sizeof(float) * nm : 0);
+  w.plan_rp = (int*)take(n != m ? sizeof(int) * ((size_t)n + 1) : 0);
+  w.plan_col = (int*)take(n != m ? sizeof(int) * (size_t)w.plan_cap : 0);
+  w.plan_w = (float*)take(n != m ? sizeof(float) * (size_t)w.plan_cap : 0);
   w.bytes = off;
   return w;
 }
@@ -830,11 +860,8 @@ size_t gw_kl_workspace_bytes(int n, int m) { return (n < 1 || m < 1) ? 0 : gwb_c
 int run_gw_kl(const double* Xs, int n, int ds, const double* Xt, int m, int dt, double h, int max_iter, double tol_rel, double tol_abs,
               int lmo, double* gw_dist_host, float* T_out, int* iters_host, int* lmo_stats_host, void* workspace, size_t workspace_bytes,
               cudaStream_t stream) {
-  if (n != m) {
-    set_error("gw_kl: only n == m (uniform marginals => the LMO is an assignment problem) is implemented; got n = %d, m = %d", n, m);
-    return EVREP_EUNSUPPORTED;
-  }
-  if (n < 1 || ds < 1 || dt < 1 || ds > GK_MAX_D || dt > GK_MAX_D) {
+  const bool rect = n != m;  // the LMO is a transportation problem (host, transport.cu) instead of an assignment
+  if (n < 1 || m < 1 || ds < 1 || dt < 1 || ds > GK_MAX_D || dt > GK_MAX_D) {
     set_error("gw_kl: need n >= 1 and 1 <= ds, dt <= %d", GK_MAX_D);
     return EVREP_EINVAL;
   }
@@ -861,10 +888,11 @@ int run_gw_kl(const double* Xs, int n, int ds, const double* Xt, int m, int dt, 
     const int rc = launch_gemm_pack(w.hC1, n, n, n, nullptr, w.imgA, stream);
     if (rc) return rc;
   }
-  const bool device_lmo = lmo == 0 && n <= AUC_MAX_N;
+  const bool device_lmo = !rect && lmo == 0 && n <= AUC_MAX_N;
   if (device_lmo) EVREP_CUDA_OK(cudaFuncSetAttribute(k_auction, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)auction_smem_bytes(n)));
-  std::vector<float> Mi_host;
-  std::vector<int> sigma;
+  std::vector<float> Mi_host, plan_wf;
+  std::vector<double> plan_wd;
+  std::vector<int> sigma, plan_rp, plan_col;
   double red_host[4];
   double f_val = 0.0;
   int it = 0;
@@ -905,17 +933,43 @@ int run_gw_kl(const double* Xs, int n, int ds, const double* Xt, int m, int dt, 
       EVREP_CUDA_OK(cudaMemcpyAsync(Mi_host.data(), w.Mi, sizeof(float) * nm, cudaMemcpyDeviceToHost, stream));
       EVREP_CUDA_OK(cudaMemcpyAsync(red_host, w.red, sizeof(double), cudaMemcpyDeviceToHost, stream));
       EVREP_CUDA_OK(cudaStreamSynchronize(stream));
-      lap_solve(Mi_host.data(), n, sigma);
-      EVREP_CUDA_OK(cudaMemcpyAsync(w.sigma, sigma.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, stream));
+      if (rect) {
+        plan_rp.resize((size_t)n + 1);
+        plan_col.resize((size_t)w.plan_cap);
+        plan_wd.resize((size_t)w.plan_cap);
+        plan_wf.resize((size_t)w.plan_cap);
+        int nnz = 0;
+        const int rcp = transport_plan_host(Mi_host.data(), n, m, w.plan_cap, plan_rp.data(), plan_col.data(), plan_wd.data(), &nnz);
+        if (rcp) return rcp;
+        for (int e = 0; e < nnz; ++e) plan_wf[(size_t)e] = (float)plan_wd[(size_t)e];
+        ++lmo_fallbacks;
+        EVREP_CUDA_OK(cudaMemcpyAsync(w.plan_rp, plan_rp.data(), sizeof(int) * ((size_t)n + 1), cudaMemcpyHostToDevice, stream));
+        EVREP_CUDA_OK(cudaMemcpyAsync(w.plan_col, plan_col.data(), sizeof(int) * (size_t)std::max(nnz, 1), cudaMemcpyHostToDevice, stream));
+        EVREP_CUDA_OK(cudaMemcpyAsync(w.plan_w, plan_wf.data(), sizeof(float) * (size_t)std::max(nnz, 1), cudaMemcpyHostToDevice, stream));
+      } else {
+        lap_solve(Mi_host.data(), n, sigma);
+        EVREP_CUDA_OK(cudaMemcpyAsync(w.sigma, sigma.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, stream));
+      }
     }
     if (it == 0) f_val = red_host[0];
-    // hC1 Gc hC2^T = (1 / n) hC1 (hC2[:, sigma])^T : the gather writes the B operand image, then the tensor-core contraction
-    int rc = launch_gemm_pack(w.hC2, m, n, m, w.sigma, w.imgB, stream);
-    if (rc) return rc;
-    rc = launch_gemm_packed(w.imgA, w.imgB, w.AGc, n, m, n, 1.f / (float)n, nullptr, nullptr, stream);
+    int rc;
+    if (rect) {
+      // hC1 Gc hC2^T = hC1 X with X^T[j, k] = sum_l Gc[k, l] hC2[j, l] (a vertex has <= n + m - 1 entries): sparse product, pack, contraction
+      EVREP_CUDA_OK(cudaMemsetAsync(w.Gc, 0, sizeof(float) * nm, stream));
+      k_gwb_plan_scatter<<<(n + 255) / 256, 256, 0, stream>>>(w.plan_rp, w.plan_col, w.plan_w, n, m, w.Gc);
+      k_gwb_sparse_xt<<<eb, 256, 0, stream>>>(w.hC2, w.plan_rp, w.plan_col, w.plan_w, m, n, w.Bp);
+      rc = launch_gemm_pack(w.Bp, m, n, n, nullptr, w.imgB, stream);
+      if (rc) return rc;
+      rc = launch_gemm_packed(w.imgA, w.imgB, w.AGc, n, m, n, 1.f, nullptr, nullptr, stream);
+    } else {
+      // hC1 Gc hC2^T = (1 / n) hC1 (hC2[:, sigma])^T : the gather writes the B operand image, then the tensor-core contraction
+      rc = launch_gemm_pack(w.hC2, m, n, m, w.sigma, w.imgB, stream);
+      if (rc) return rc;
+      rc = launch_gemm_packed(w.imgA, w.imgB, w.AGc, n, m, n, 1.f / (float)n, nullptr, nullptr, stream);
+    }
     if (rc) return rc;
     EVREP_CUDA_OK(cudaMemsetAsync(w.red, 0, sizeof(double) * 8, stream));
-    k_gwb_linesearch<<<eb, 256, 0, stream>>>(n, m, w.cr, w.cc, w.AG, w.AGc, w.G, w.sigma, w.red);
+    k_gwb_linesearch<<<eb, 256, 0, stream>>>(n, m, w.cr, w.cc, w.AG, w.AGc, w.G, w.sigma, rect ? w.Gc : nullptr, w.red);
     EVREP_CUDA_OK(cudaMemcpyAsync(red_host, w.red, sizeof(double) * 4, cudaMemcpyDeviceToHost, stream));
     EVREP_CUDA_OK(cudaStreamSynchronize(stream));
     // f(G + alpha dG) = f(G) + b alpha + a alpha^2 with
@@ -927,7 +981,7 @@ int run_gw_kl(const double* Xs, int n, int ds, const double* Xt, int m, int dt, 
     else alpha = (a + b < 0) ? 1.0 : 0.0;
     const double old = f_val;
     f_val = old + a * alpha * alpha + b * alpha;
-    if (alpha != 0.0) k_gwb_step<<<eb, 256, 0, stream>>>(n, m, (float)alpha, w.sigma, w.AGc, w.G, w.AG);
+    if (alpha != 0.0) k_gwb_step<<<eb, 256, 0, stream>>>(n, m, (float)alpha, w.sigma, rect ? w.Gc : nullptr, w.AGc, w.G, w.AG);
     EVREP_CUDA_OK(cudaGetLastError());
     // POT's stopping rule (|df| < tol_abs or |df| / |f| < tol_rel), with both tolerances floored at the resolution of
     // the float32 gradient (4 ulp of the loss): below it the predicted decrease is rounding noise and the iteration

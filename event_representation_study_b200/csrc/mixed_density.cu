@@ -145,6 +145,73 @@ __device__ __forceinline__ float md_value(const MdPlan& P, const MdChan& ch, con
   return __fdividef((float)fma((double)c, st2, -st * st), (float)(cd * cd));
 }
 
+// The same channel formulas for the compile-time specialised kernels, trimmed for instruction count (the finalise phase
+// is ~40 % of the headline kernel's instructions): reciprocals are single MUFU.RCP approximations (<= 1 ulp; every
+// divisor is a non-negative integer, 0 gives inf and 0 * inf = NaN reproduces the reference's 0/0), packed plans
+// (buckets below 65536 events) do the polarity variance in 32-bit integers, and sums of t are converted limb by limb in
+// fp32 (limb sums stay below 2^32).  Every result stays within 4e-7 relative of the reference's fp64 value.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float md_value_fast(const MdPlan& P, const MdChan& ch, const uint32_t* a, float inv_delta, double delta, uint32_t delta_u,
+                                               uint32_t has_m1) {
+  if (!ch.valid) return 0.f;
+  if (ch.func == EVREP_FUNC_POLARITY) {
+    const uint32_t c1 = md_cnt(P, P.grp[ch.g_pos], a);
+    const uint32_t cn = md_cnt(P, P.grp[ch.g_neg], a);
+    const uint32_t cm = ((has_m1 >> ch.win) & 1u) ? cn : 0u;  // the "negative" class holds the p == 0 events when the window has no -1
+    if (ch.agg == EVREP_AGG_SUM) return (float)((int)c1 - (int)cm);
+    const uint32_t call = c1 + cn + md_cnt(P, P.grp[ch.g_oth], a);
+    if (ch.agg == EVREP_AGG_MEAN) return call ? (float)((int)c1 - (int)cm) * rcp_approx((float)call) : 0.f;
+    if (ch.agg == EVREP_AGG_VARIANCE) {  // mean(p^2) - mean(p)^2 = ((c1+cm) call - (c1-cm)^2) / call^2, exact in integers
+      if (P.packed) {                    // call < 65536: everything fits 32 bits
+        const int d = (int)c1 - (int)cm;
+        const uint32_t num = (c1 + cm) * call - (uint32_t)(d * d);
+        return call ? (float)num * rcp_approx((float)(call * call)) : 0.f;
+      }
+      const long long dd = (long long)((int)c1 - (int)cm);
+      const unsigned long long num = (unsigned long long)(c1 + cm) * call - (unsigned long long)(dd * dd);
+      return call ? __ull2float_rn(num) * rcp_approx(__ull2float_rn((unsigned long long)call * call)) : 0.f;
+    }
+    if (call == 0u) return 0.f;
+    if (ch.agg == EVREP_AGG_MIN) return cm > 0 ? -1.f : (call - c1 - cm > 0 ? 0.f : 1.f);  // min of the raw polarities
+    return c1 > 0 ? 1.f : (call - c1 - cm > 0 ? 0.f : -1.f);                               // max of the raw polarities
+  }
+  const bool is_count = (ch.func == EVREP_FUNC_COUNT || ch.func == EVREP_FUNC_COUNT_POS || ch.func == EVREP_FUNC_COUNT_NEG);
+  if (ch.g_main < 0 && ch.g_pos < 0) return 0.f;  // variance of a constant
+  if (is_count) {
+    const uint32_t c = md_count(P, ch, a);
+    return ch.agg == EVREP_AGG_SUM ? (float)c : (c ? 1.f : 0.f);  // torch_scatter leaves untouched pixels at 0
+  }
+  // timestamps: t_s = (t - t_min) / (t_max - t_min); delta == 0 gives NaN exactly like the reference
+  const MdGroup& G = P.grp[ch.g_main];
+  if (ch.agg == EVREP_AGG_MAX || ch.agg == EVREP_AGG_MIN) {
+    const uint32_t w = ch.agg == EVREP_AGG_MAX ? a[G.w_max] : a[G.w_min];
+    const uint32_t v = ch.agg == EVREP_AGG_MAX ? w - 1u : ~w;
+    float r = (float)v * inv_delta;
+    if (v == delta_u && delta_u) r = 1.f;  // the window's last event maps to exactly 1
+    return w ? r : 0.f;
+  }
+  const uint32_t c = md_count(P, ch, a);
+  if (c == 0u) return 0.f;
+  if (ch.agg == EVREP_AGG_SUM || ch.agg == EVREP_AGG_MEAN) {
+    float st = (float)a[G.w_st + P.nl1 - 1];
+    for (int l = P.nl1 - 2; l >= 0; --l) st = fmaf(st, (float)(1u << P.lw), (float)a[G.w_st + l]);
+    st *= inv_delta;
+    return ch.agg == EVREP_AGG_SUM ? st : st * rcp_approx((float)c);
+  }
+  if (c == 1u && delta_u) return 0.f;  // a single event: t_s^2 - t_s^2, exactly 0 in the reference too (NaN when delta == 0)
+  unsigned long long sti = a[G.w_st + P.nl1 - 1];
+  for (int l = P.nl1 - 2; l >= 0; --l) sti = (sti << P.lw) + a[G.w_st + l];
+  const double st = (double)sti;
+  const double cd = (double)c * delta;
+  const double st2 = md_limb_sum(a, G.w_st2, P.nl2, P.lw);
+  // mean(t_s^2) - mean(t_s)^2 = (c sum(t^2) - sum(t)^2) / (c delta)^2
+  return (float)fma((double)c, st2, -st * st) * rcp_approx((float)(cd * cd));
+}
+
 template <int CMAX>
 __global__ void __launch_bounds__(TILE_THREADS) k_md_tile(const uint2* __restrict__ records, const uint32_t* __restrict__ base,
                                                           const uint32_t* __restrict__ hist, const WinParams* __restrict__ wp,
@@ -304,7 +371,7 @@ template <typename PS, int CI>
 __device__ __forceinline__ float md_value_static(const uint32_t* a, float inv_delta, double delta, uint32_t delta_u, uint32_t has_m1) {
   constexpr MdPlan P = PS::value;
   constexpr MdChan ch = PS::value.ch[CI];
-  return md_value(P, ch, a, inv_delta, delta, delta_u, has_m1);
+  return md_value_fast(P, ch, a, inv_delta, delta, delta_u, has_m1);
 }
 template <typename PS, int... CI>
 __device__ __forceinline__ void md_finalise_static(const uint32_t* a, float inv_delta, double delta, uint32_t delta_u, uint32_t has_m1,
@@ -395,7 +462,7 @@ __device__ __forceinline__ void md_finalise_store_warp(uint32_t* slab, const Til
   constexpr int STRIDE = PS::value.stride, C = PS::value.C, PPT = TP / TILE_THREADS;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const double delta = (double)h.delta_u;
-  const float inv_delta = 1.f / (float)h.delta_u;
+  const float inv_delta = rcp_approx((float)h.delta_u);
   float4* stage = reinterpret_cast<float4*>(slab);  // [PPT * 32][C] floats, contiguous = the global layout of the slab's pixels
 #pragma unroll
   for (int k = 0; k < PPT; ++k) {

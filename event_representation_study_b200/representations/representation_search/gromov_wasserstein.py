@@ -1,7 +1,8 @@
 """Mirror of representations/representation_search/gromov_wasserstein.py: `compute_repr` (reference :72-82), the 5-bin
 bilinear voxel grid used by its __main__ experiment, `compute_kernel`, and `OTMI` (reference :39-69), whose `solve()` is
 POT's conditional-gradient Gromov-Wasserstein with the KL loss: here `evrep_gw_kl` (tcgen05 contraction on the GPU,
-exact assignment LMO on the host; n == m only, see include/evrep.h)."""
+auction LMO on the GPU for n == m, exact transportation LMO on the host for n != m - the reference's own call shape,
+N events against the non-empty pixels; see include/evrep.h)."""
 import numpy as np
 
 from ... import batched as eb

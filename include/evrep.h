@@ -204,8 +204,10 @@ int evrep_gwd_kernel_l1(const double* Xs, const int64_t* s_offsets, int ds, cons
  * EVREP_LMO_AUCTION, Bertsekas' forward auction with epsilon scaling on the GPU (optimal up to n * 1e-9 * cost range; n <=
  * 4096; a step that hits the round limit is redone by the host solver) or, with EVREP_LMO_HOST, an exact shortest-
  * augmenting-path solve on the host.  Either way a few scalars come back every iteration, so the call SYNCHRONISES the
- * stream.  lmo_stats (HOST, 3 ints, may be NULL): auction rounds, auction bids, steps redone on the host.  Implemented for
- * n == m only (uniform marginals make every vertex a permutation); EVREP_EUNSUPPORTED otherwise.  ds, dt <= 64. */
+ * stream.  lmo_stats (HOST, 3 ints, may be NULL): auction rounds, auction bids, steps solved on the host.  For n != m (the
+ * reference's own call shape: n events against m pixels) every vertex is a transportation plan with up to n + m - 1
+ * entries: the LMO is then always evrep_transport_plan_host (the gradient is read back, the plan uploaded in CSR form)
+ * and the step's contraction is hC1 (Gc hC2^T) with the sparse product formed by a small kernel.  ds, dt <= 64. */
 #define EVREP_LMO_AUCTION 0
 #define EVREP_LMO_HOST 1
 size_t evrep_gw_kl_workspace_bytes(int n, int m);
@@ -218,6 +220,15 @@ int evrep_gw_kl(const double* Xs, int n, int ds, const double* Xt, int m, int dt
  * n * eps_rel * (max cost - min cost) of the optimum.  stats (DEVICE, 3 ints): rounds, bids, status (0 ok, 1 round limit,
  * 2 non-finite costs; sigma is not a permutation unless status is 0).  n <= 4096.  Enqueued on `stream`, no sync. */
 int evrep_assignment_auction(const float* cost, int n, double eps_rel, int* sigma, int* stats, evrep_stream_t stream);
+
+/* The LMO of evrep_gw_kl for rectangular plans (n != m): an optimal vertex of the transportation problem
+ *     min <cost, G>  s.t.  G 1 = 1/n,  G^T 1 = 1/m,  G >= 0
+ * (what POT's ot.emd returns inside ot.gromov.gromov_wasserstein; gromov_wasserstein.py:62-69).  HOST function, HOST
+ * pointers, no GPU involved: `cost` is n x m float32 row major; the plan comes back in CSR form - row_ptr (n + 1), col and
+ * weight (capacity `cap`, n + m suffices unless costs tie), *nnz entries (may be NULL).  Exact: successive shortest paths
+ * with integer flows (unit gcd(n, m) / (n m)); EVREP_EWORKSPACE when the plan does not fit `cap`, EVREP_EINVAL for
+ * non-finite costs. */
+int evrep_transport_plan_host(const float* cost, int n, int m, int cap, int* row_ptr, int* col, double* weight, int* nnz);
 
 /* C[M x N] = alpha * A[M x K] * B[N x K]^T + rv[i] + cv[j] on the tcgen05 tensor cores: every fp32 operand is split
  * into two TF32 terms (round to nearest) and lo*hi + hi*lo + hi*hi is accumulated, k-blocks of 32 summed in fp32 with

@@ -135,11 +135,39 @@ def test_gw_kl_descends_from_the_product_plan(E):
     assert got <= f0 + 1e-9 and iters >= 1
 
 
-def test_gw_kl_rejects_unequal_sizes(E):
-    from event_representation_study_b200._lib import EvrepError, EUNSUPPORTED
-    with pytest.raises(EvrepError) as e:
-        E.gw_kl(np.random.rand(10, 4), np.random.rand(12, 4))
-    assert e.value.code == EUNSUPPORTED
+@pytest.mark.parametrize("n,m,seed", [(10, 12, 0), (30, 21, 1), (64, 40, 2), (33, 100, 3), (96, 64, 4)])
+def test_gw_kl_rectangular_matches_the_oracle(E, n, m, seed):
+    """n != m (gromov_wasserstein.py:85-184 pairs N events with the non-empty pixels): the LMO is a transportation problem.
+    The oracle solves it with scipy's linprog (oracle/gwd.py::_emd); equal losses where both take the same vertices,
+    and in every case a feasible plan whose reported loss is its float64 loss and does not exceed the oracle's by > 10 %."""
+    from oracle import gwd as ogwd
+    rng = np.random.default_rng(seed)
+    Xs = rng.random((n, 4))
+    Xt = np.concatenate([rng.random((m, 5)) * 3, rng.random((m, 2))], 1)
+    want = ogwd.gwd_b_cost(Xs, Xt, 0.7)
+    st = {}
+    got, iters, plan = E.gw_kl(Xs, Xt, 0.7, return_plan=True, stats=st)
+    T = plan.double().cpu().numpy()
+    assert T.shape == (n, m) and (T >= -1e-9).all()
+    assert np.abs(T.sum(1) - 1.0 / n).max() <= 1e-6 / n and np.abs(T.sum(0) - 1.0 / m).max() <= 1e-6 / m
+    Ks, Kt = ogwd.compute_kernel(ogwd.pairwise_euclidean(Xs), ogwd.pairwise_euclidean(Xt), 0.7)
+    constC, hC1, hC2 = ogwd.gw_kl_init(Ks, Kt, np.ones(n) / n, np.ones(m) / m)
+    f64 = float(np.sum((constC - hC1 @ T @ hC2.T) * T))
+    assert abs(got - f64) <= 1e-5 * abs(f64), (got, f64)
+    assert got <= want * 1.1 + 1e-12, (got, want, iters)
+    assert st["host_fallbacks"] == iters or iters == 0  # every step's LMO ran on the host
+    if n <= 30:
+        assert abs(got - want) <= 1e-5 * abs(want), (got, want)
+
+
+def test_otmi_mirror_rectangular(E):
+    """the reference's own call shape: more events than pixels"""
+    from event_representation_study_b200.representations.representation_search.gromov_wasserstein import OTMI
+    rng = np.random.default_rng(8)
+    Xs, Xt = rng.random((50, 4)), rng.random((35, 7))
+    T, dist = OTMI(Xs, Xt, 0.7).solve()
+    assert T.shape == (50, 35) and np.isfinite(dist)
+    assert np.abs(T.sum(1) - 1 / 50).max() < 1e-7 and np.abs(T.sum(0) - 1 / 35).max() < 1e-7
 
 
 def test_otmi_mirror_of_gromov_wasserstein_py(E):
