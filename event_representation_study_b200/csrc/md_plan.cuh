@@ -94,39 +94,98 @@ constexpr int md_plan_build(const int8_t* win, const int8_t* func, const int8_t*
       }
     }
   }
-  int words = 0, pres_bits = 0, half = 0, cnt_word = 0;
-  bool any_pres = false;
-  for (int g = 0; g < P.G; ++g) {
-    MdGroup& G = P.grp[g];
-    if (G.flags & G_CNT) G.flags &= (uint8_t)~G_PRES;                          // a count subsumes the presence bit
-    if ((G.flags & G_PRES) && (G.flags & (G_MAX | G_MIN))) G.flags &= (uint8_t)~G_PRES;  // so does a latest / earliest-timestamp word
-    if (G.flags & G_PRES) any_pres = true;
-  }
-  if (any_pres) P.w_pres = words++;
-  for (int g = 0; g < P.G; ++g) {  // counters first: packed plans pair them up
-    MdGroup& G = P.grp[g];
-    if (!(G.flags & G_CNT)) continue;
-    if (packed) {
-      if (half == 0) cnt_word = words++;
-      G.w_cnt = (uint8_t)cnt_word;
-      G.cnt_shift = (uint8_t)(16 * half);
-      half ^= 1;
-    } else {
-      G.w_cnt = (uint8_t)words++;
+  // Packed plans pair their 16-bit counters two per word.  An event can bump both counters of a word with ONE
+  // shared-memory atomic when it belongs to both groups, so pairs are chosen greedily by how many events hit both
+  // (same polarity class - or class "all" - and overlapping index windows), and presence bits become counters when that
+  // does not widen the per-pixel footprint: a presence bit costs a read and an atomicOr of its own, a counter that
+  // shares a word with one the event bumps anyway costs nothing.
+  for (int pass = packed ? 0 : 1; pass < 2; ++pass) {
+    const bool convert = pass == 0;  // pass 0: presence -> counter; kept only if the stride does not grow (else pass 1 redoes it)
+    MdPlan Q = P;
+    int words = 0, pres_bits = 0;
+    bool any_pres = false;
+    for (int g = 0; g < Q.G; ++g) {
+      MdGroup& G = Q.grp[g];
+      if (G.flags & G_CNT) G.flags &= (uint8_t)~G_PRES;                          // a count subsumes the presence bit
+      if ((G.flags & G_PRES) && (G.flags & (G_MAX | G_MIN))) G.flags &= (uint8_t)~G_PRES;  // so does a latest / earliest-timestamp word
+      if ((G.flags & G_PRES) && convert) G.flags = (uint8_t)((G.flags & ~G_PRES) | G_CNT);
+      if (G.flags & G_PRES) any_pres = true;
     }
+    if (any_pres) Q.w_pres = words++;
+    if (packed) {
+      // index windows in units of n / 24 (mixed_density_event_stack.py:55-74): W0 all, W1-W3 thirds, W4-W6 nested suffixes
+      const int lo[8] = {0, 0, 8, 16, 12, 18, 21, 0}, hi[8] = {24, 8, 16, 24, 24, 24, 24, 0};
+      int cg[MD_MAX_GROUPS] = {}, nc = 0;
+      bool done[MD_MAX_GROUPS] = {};
+      for (int g = 0; g < Q.G; ++g)
+        if (Q.grp[g].flags & G_CNT) cg[nc++] = g;
+      for (int left = nc; left > 0;) {
+        int bi = -1, bj = -1, best = -1;
+        for (int i = 0; i < nc; ++i) {
+          if (done[i]) continue;
+          if (bi < 0) bi = i;  // fallback: the first free counter, alone or with the next free one
+          for (int j = i + 1; j < nc; ++j) {
+            if (done[j]) continue;
+            const int ci = Q.grp[cg[i]].bit >> 3, cj = Q.grp[cg[j]].bit >> 3, wi = Q.grp[cg[i]].bit & 7, wj = Q.grp[cg[j]].bit & 7;
+            if (ci != cj && ci != 0 && cj != 0) continue;  // no event is in both
+            const int a0 = lo[wi] > lo[wj] ? lo[wi] : lo[wj], a1 = hi[wi] < hi[wj] ? hi[wi] : hi[wj];
+            int score = (a1 > a0 ? a1 - a0 : 0) * ((ci == 0 && cj == 0) ? 2 : 1);
+            if (ci == 3 || cj == 3) score = score > 0 ? 1 : 0;  // "neither" class: p == 0 next to p == -1, rare
+            if (score > best) { best = score; bi = i; bj = j; }
+          }
+        }
+        if (best <= 0) {  // nothing left that merges: pair the remaining counters in order
+          bj = -1;
+          for (int j = bi + 1; j < nc; ++j)
+            if (!done[j]) { bj = j; break; }
+        }
+        Q.grp[cg[bi]].w_cnt = (uint8_t)words;
+        Q.grp[cg[bi]].cnt_shift = 0;
+        done[bi] = true;
+        --left;
+        if (bj >= 0) {
+          Q.grp[cg[bj]].w_cnt = (uint8_t)words;
+          Q.grp[cg[bj]].cnt_shift = 16;
+          done[bj] = true;
+          --left;
+        }
+        ++words;
+      }
+    } else {
+      for (int g = 0; g < Q.G; ++g)
+        if (Q.grp[g].flags & G_CNT) Q.grp[g].w_cnt = (uint8_t)words++;
+    }
+    for (int g = 0; g < Q.G; ++g) {
+      MdGroup& G = Q.grp[g];
+      if (G.flags & G_PRES) G.pres_bit = (uint8_t)pres_bits++;
+      if (G.flags & G_MAX) G.w_max = (uint8_t)words++;
+      if (G.flags & G_MIN) G.w_min = (uint8_t)words++;
+      if (G.flags & G_ST) { G.w_st = (uint8_t)words; words += Q.nl1; }
+      if (G.flags & G_ST2) { G.w_st2 = (uint8_t)words; words += Q.nl2; }
+      if (words > 250) return 1;
+    }
+    if (words == 0) words = 1;
+    Q.words = words;
+    Q.stride = (words > C ? words : C) | 1;  // odd: bank-conflict-free, and room for the C outputs written in place
+    if (convert) {  // compare with the footprint without the conversion
+      int base_words = 0, halves = 0;
+      bool pres = false;
+      for (int g = 0; g < P.G; ++g) {
+        uint8_t f = P.grp[g].flags;
+        if (f & G_CNT) f &= (uint8_t)~G_PRES;
+        if ((f & G_PRES) && (f & (G_MAX | G_MIN))) f &= (uint8_t)~G_PRES;
+        if (f & G_PRES) pres = true;
+        if (f & G_CNT) ++halves;
+        base_words += ((f & G_MAX) ? 1 : 0) + ((f & G_MIN) ? 1 : 0) + ((f & G_ST) ? P.nl1 : 0) + ((f & G_ST2) ? P.nl2 : 0);
+      }
+      base_words += (pres ? 1 : 0) + (halves + 1) / 2;
+      if (base_words == 0) base_words = 1;
+      const int base_stride = (base_words > C ? base_words : C) | 1;
+      if (Q.stride > base_stride) continue;  // conversion would cost shared memory: redo without it
+    }
+    P = Q;
+    return 0;
   }
-  for (int g = 0; g < P.G; ++g) {
-    MdGroup& G = P.grp[g];
-    if (G.flags & G_PRES) G.pres_bit = (uint8_t)pres_bits++;
-    if (G.flags & G_MAX) G.w_max = (uint8_t)words++;
-    if (G.flags & G_MIN) G.w_min = (uint8_t)words++;
-    if (G.flags & G_ST) { G.w_st = (uint8_t)words; words += P.nl1; }
-    if (G.flags & G_ST2) { G.w_st2 = (uint8_t)words; words += P.nl2; }
-    if (words > 250) return 1;
-  }
-  if (words == 0) words = 1;
-  P.words = words;
-  P.stride = (words > C ? words : C) | 1;  // odd: bank-conflict-free, and room for the C outputs written in place
   return 0;
 }
 

@@ -334,6 +334,46 @@ __global__ void __launch_bounds__(TILE_THREADS) k_md_tile(const uint2* __restric
 // ---------------------------------------------------------------------------------------------
 // CLS selects the groups an event can belong to: 0 = any (buckets not split by polarity), 1 = the event has p > 0
 // (groups of class "all" and "positive"), 2 = it has not (classes "all", "negative", "neither").
+// counter word WI of a packed plan: both 16-bit counters with ONE atomic (md_plan.cuh pairs counters that the same
+// event tends to bump); wide plans have one counter per word
+template <typename PS>
+constexpr int md_cnt_group_at(int word, int shift) {  // the group whose counter lives in that half-word, or -1
+  for (int g = 0; g < PS::value.G; ++g)
+    if ((PS::value.grp[g].flags & G_CNT) && PS::value.grp[g].w_cnt == word && PS::value.grp[g].cnt_shift == shift) return g;
+  return -1;
+}
+template <typename PS, int CLS>
+constexpr bool md_group_live(int g) {  // can an event of class CLS belong to group g at all?
+  if (g < 0) return false;
+  const int gcls = PS::value.grp[g].bit >> 3;
+  return !((CLS == 1 && gcls >= 2) || (CLS == 2 && gcls == 1));
+}
+template <typename PS, int WI, int CLS>
+__device__ __forceinline__ void md_acc_cnt_word(uint32_t* a, uint32_t M) {
+  constexpr int g_lo = md_cnt_group_at<PS>(WI, 0), g_hi = md_cnt_group_at<PS>(WI, 16);
+  constexpr bool l_lo = md_group_live<PS, CLS>(g_lo), l_hi = md_group_live<PS, CLS>(g_hi);
+  uint32_t inc = 0;
+  if constexpr (l_lo) inc |= (M >> PS::value.grp[g_lo].bit) & 1u;
+  if constexpr (l_hi) inc |= ((M >> PS::value.grp[g_hi].bit) & 1u) << 16;
+  if constexpr (l_lo || l_hi) {
+    if (inc) atomicAdd(a + WI, inc);
+  }
+}
+template <typename PS, int CLS, int... WI>
+__device__ __forceinline__ void md_acc_cnt_all(uint32_t* a, uint32_t M, std::integer_sequence<int, WI...>) {
+  (md_acc_cnt_word<PS, WI, CLS>(a, M), ...);
+}
+// highest counter word index + 1 (counter words are contiguous, after the presence word)
+template <typename PS>
+constexpr int md_cnt_words_end() {
+  int e = 0;
+  for (int g = 0; g < PS::value.G; ++g)
+    if ((PS::value.grp[g].flags & G_CNT) && PS::value.grp[g].w_cnt + 1 > e) e = PS::value.grp[g].w_cnt + 1;
+  return e;
+}
+
+// CLS selects the groups an event can belong to: 0 = any (buckets not split by polarity), 1 = the event has p > 0
+// (groups of class "all" and "positive"), 2 = it has not (classes "all", "negative", "neither").
 template <typename PS, int GI, int CLS>
 __device__ __forceinline__ void md_acc_group(uint32_t* a, uint32_t M, uint32_t tt, unsigned long long tt2, uint32_t& pres) {
   constexpr MdGroup G = PS::value.grp[GI];
@@ -345,8 +385,8 @@ __device__ __forceinline__ void md_acc_group(uint32_t* a, uint32_t M, uint32_t t
     pres |= ((M >> G.bit) & 1u) << G.pres_bit;
     return;
   }
+  if constexpr ((G.flags & ~G_CNT) == 0) return;  // counters are handled word by word (md_acc_cnt_word)
   if (!((M >> G.bit) & 1u)) return;
-  if constexpr (G.flags & G_CNT) atomicAdd(a + G.w_cnt, 1u << G.cnt_shift);
   if constexpr (G.flags & G_PRES) pres |= 1u << G.pres_bit;
   if constexpr (G.flags & G_MAX) atomicMax(a + G.w_max, tt + 1u);
   if constexpr (G.flags & G_ST) {
@@ -364,6 +404,7 @@ __device__ __forceinline__ void md_acc_group(uint32_t* a, uint32_t M, uint32_t t
 template <typename PS, int CLS, int... GI>
 __device__ __forceinline__ void md_acc_all(uint32_t* a, uint32_t M, uint32_t tt, uint32_t& pres, std::integer_sequence<int, GI...>) {
   const unsigned long long tt2 = (unsigned long long)tt * (unsigned long long)tt;
+  md_acc_cnt_all<PS, CLS>(a, M, std::make_integer_sequence<int, md_cnt_words_end<PS>()>{});
   (md_acc_group<PS, GI, CLS>(a, M, tt, tt2, pres), ...);
 }
 
@@ -397,7 +438,7 @@ __device__ __forceinline__ void md_accumulate_static(uint32_t* acc, const uint2 
   }
   uint32_t pres = 0;
   md_acc_all<PS, CLS>(a, M, tt, pres, std::make_integer_sequence<int, G>{});
-  if (pres) {
+  if (pres) {  // only plans that still keep presence bits
     uint32_t* pw = a + PS::value.w_pres;
     if ((*(volatile uint32_t*)pw & pres) != pres) atomicOr(pw, pres);
   }
@@ -623,7 +664,7 @@ static int sm_count(int* n_sm) {
   return EVREP_OK;
 }
 
-static_assert(ErgoPlan<2, 16, true>::value.words == 16 && ErgoPlan<2, 16, true>::value.stride == 17, "packed ERGO-12 v2 plan: 16 words per pixel");
+static_assert(ErgoPlan<2, 16, true>::value.words == 17 && ErgoPlan<2, 16, true>::value.stride == 17, "packed ERGO-12 v2 plan: 17 words per pixel");
 static_assert(ErgoPlan<2, 12, false>::value.words == 24, "wide ERGO-12 v2 plan at 2^20 events: 24 words per pixel");
 
 // ERGO-12 at the standard 1024-pixel tile: packed plan on every bucket below 65536 events, wide plan on the rest
