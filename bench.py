@@ -13,6 +13,12 @@ e2e       same through the public batched API with HOST (pinned) event arrays: p
           of the events, the kernels, and the device->host read of a per-window checksum of the output
 roofline  the kernel that writes the output (k_md_tile), timed with CUDA events inside the timed region
 cpu_baseline  the numpy oracle (a port of the reference algorithm) on the host cores, bounded sample
+gwd       BASELINE.json's second metric ("GWD pairs/s vs CPU ref", configs[4]): the 12 x 1000 GWD-A matrix, columns sharded
+          over the ranks, one NCCL all-gather when N > 1; plus one pair at the paper's problem sizes (compute_otmi.py:96-211)
+configs   BASELINE configs[1] (ERGO-12 Gen1, batch 32) and configs[2] (TimeSurface + EventStack + TORE, fused call)
+parity_spot_check  windows of the TIMED output buffers against the oracle on the same events
+dropin    the per-window numpy -> numpy call the reference pipelines make today (get_item_transform), full output copied back
+(the last three on rank 0 at N = 1 only; --no-extras skips them and gwd)
 """
 import argparse
 import json
@@ -26,6 +32,19 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+
+def _load_synth():
+    """synth.py by path: the CPU arms must not import the product package (its __init__ dlopens libevrep.so)"""
+    import importlib.util
+    name = "_evrep_bench_synth"
+    if name in sys.modules:
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "event_representation_study_b200", "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
 
 H, W, C = 720, 1280, 12
 BYTES_PER_EVENT = 9  # x u16 + y u16 + t i32 + p i8: SURVEY.md 8(d)
@@ -109,7 +128,7 @@ def _cpu_one(args):
     timed steps contain the representation work only (like the GPU arm, whose inputs are generated before timing)."""
     slot, n = args
     from oracle import representations as orep
-    from event_representation_study_b200.synth import poisson_window
+    poisson_window = _load_synth().poisson_window
     key = (slot, n) if slot >= 0 else n  # slot < 0: one cached window per worker process
     w = _CPU_CACHE.get(key)
     if w is None:
@@ -168,6 +187,214 @@ def config_dict(a, windows):
     return {"workload": f"ERGO-12 v2, {W}x{H}, {a.events} ev/window, {windows} windows/GPU (BASELINE configs[3] shard: 256 windows over 8 GPUs)",
             "windows_per_gpu": windows, "events_per_window": a.events, "stream": "poisson-uniform" + ("-clustered" if a.clustered else ""),
             "l2": "inputs (288 MB) and outputs (1.4 GB) per step exceed the 126 MB L2; no explicit flush"}
+
+
+# ------------------------------------------------------------------------------------------------
+# the other BASELINE metrics and configs, under the same clock ("put every BASELINE metric under the driver")
+# ------------------------------------------------------------------------------------------------
+def _timed(fn, steps, warm=3):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps * 1e-3
+
+
+def gwd_pair_inputs(r, s, n, rng_seed=900):
+    """deterministic synthetic pair: what otmi() hands to OTMI after its quadrant split (shapes and ranges only)"""
+    rng = np.random.default_rng(rng_seed + s)
+    Xs = rng.random((n, 4))                                     # events [x, y, t, p] in [0, 1]
+    rr = np.random.default_rng(rng_seed * 7 + r * 100003 + s)
+    Xt = np.concatenate([rr.random((n, 12)) * 255 * (rr.random((n, 12)) < 0.4), rr.random((n, 2))], 1)  # pixels [12 channels x 255, row, col]
+    return Xs, Xt
+
+
+def bench_gwd(rank, world, dev, steps, with_cpu):
+    """BASELINE configs[4]: 12 representations x 1000 samples, every entry one GWD-A pair (compute_otmi.py:50-93) of
+    n = m = 1000 points (SURVEY 8d reading ii).  Columns are sharded over the ranks; ONE all-gather assembles the matrix."""
+    import torch
+    import torch.distributed as dist
+    import event_representation_study_b200.batched as eb
+    from event_representation_study_b200 import sharding
+    R, S, n = 12, 1000, 1000
+    lo, hi = sharding.shard_range(S, world, rank)
+    Xs_list, Xt_list = [], []
+    for s_ in range(lo, hi):
+        xs = None
+        for r in range(R):
+            Xs, Xt = gwd_pair_inputs(r, s_, n)
+            if xs is None:
+                xs = torch.as_tensor(Xs, device=dev)
+            Xs_list.append(xs)
+            Xt_list.append(torch.as_tensor(Xt, device=dev))
+
+    def step():
+        local = eb.gwd_kernel_l1(Xs_list, Xt_list, 0.7, device=dev).reshape(hi - lo, R).t().contiguous()  # (R, S_local)
+        return sharding.gather_cost_matrix(local)
+
+    M = step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        M = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    sec = float(ms.item()) * 1e-3 / steps
+    if rank != 0:
+        return None
+    rec = {"metric": "GWD pairs/s (GWD-A: compute_otmi.py OTMI.solve in closed form)", "value": R * S / sec, "unit": "pairs/s", "ms_per_matrix": sec * 1e3,
+           "steps": steps, "scaling": "strong", "config": {"workload": f"{R} representations x {S} samples, n = m = {n} points per pair (BASELINE configs[4])",
+                                                           "sharding": f"sample columns over {world} rank(s), one all-gather of the {R} x {S} float64 matrix" if world > 1 else "one GPU"},
+           "ranking": [float(v) for v in M.mean(1).tolist()]}
+    if with_cpu:
+        from oracle import gwd as ogwd
+        t0 = time.perf_counter()
+        k, errs = 0, []
+        while k < 8 and time.perf_counter() - t0 < 8.0:
+            r, s_ = k % R, (k * 131) % S
+            Xs, Xt = gwd_pair_inputs(r, s_, n)
+            want = ogwd.gwd_a_cost(Xs, Xt, 0.7)
+            errs.append(abs(float(M[r, s_]) - want) / abs(want))
+            k += 1
+        cpu = (time.perf_counter() - t0) / k
+        rec["max_rel_err_vs_oracle"] = max(errs)
+        rec["pairs_checked"] = k
+        rec["cpu_baseline"] = {"value": 1.0 / cpu, "unit": "pairs/s", "cores": "numpy/BLAS threads", "kind": "port",
+                               "sample": f"{k} of the same pairs, oracle/gwd.py::gwd_a_cost (closed form of POT's max_iter=0 estimate; POT not installable offline)"}
+        rec["speedup_vs_cpu_port"] = rec["value"] * cpu
+        # SURVEY 8d reading (i): the paper's problem sizes - one quadrant of a 50 k-event Gen1 window against a 120 x 120 quadrant
+        # of a letterboxed 12-channel representation (compute_otmi.py:96-211): n ~ 10 k events, m = 14 400 pixels
+        n_e, m_p = 10_000, 14_400
+        rng = np.random.default_rng(77)
+        Xs_b = rng.random((n_e, 4))
+        Xt_b = np.concatenate([rng.random((m_p, 12)) * 255 * (rng.random((m_p, 12)) < 0.4), rng.random((m_p, 2))], 1)
+        a_, b_ = torch.as_tensor(Xs_b, device=dev), torch.as_tensor(Xt_b, device=dev)
+        sec_b = _timed(lambda: eb.gwd_kernel_l1([a_], [b_], 0.7, device=dev), 5, warm=1)
+        # CPU at a quarter of the linear size (the oracle materialises n^2 + m^2 float64 matrices: 2.5 GB at full size), scaled by L^2
+        q = 4
+        t0 = time.perf_counter()
+        want_q = ogwd.gwd_a_cost(Xs_b[: n_e // q], Xt_b[: m_p // q], 0.7)
+        cpu_q = time.perf_counter() - t0
+        got_q = float(eb.gwd_kernel_l1([a_[: n_e // q]], [b_[: m_p // q]], 0.7, device=dev)[0])
+        rec["paper_shaped"] = {"n_events": n_e, "m_pixels": m_p, "ms_per_pair": sec_b * 1e3, "pairs_per_s": 1.0 / sec_b,
+                               "rel_err_vs_oracle_at_quarter_size": abs(got_q - want_q) / abs(want_q),
+                               "cpu_baseline": {"value": 1.0 / (cpu_q * q * q), "unit": "pairs/s", "kind": "port", "cores": "numpy/BLAS threads",
+                                                "sample": f"one pair at n = {n_e // q}, m = {m_p // q} ({cpu_q:.2f} s), scaled by {q * q} (cost ~ L^2)"},
+                               "speedup_vs_cpu_port": cpu_q * q * q / sec_b}
+    return rec
+
+
+def bench_configs(dev, steps):
+    """BASELINE configs[1] and configs[2] on one GPU: whole call, CUDA events, roofline by SURVEY 8d's algorithmic bytes."""
+    import torch
+    import event_representation_study_b200.batched as eb
+    from event_representation_study_b200.synth import device_batch
+    peak, _ = measured_peak()
+
+    def batch(B, N, h, w, seed):
+        d = device_batch(B, N, h, w, dev, seed=seed)
+        return eb.EventBatch(d["x"], d["y"], d["t"], d["p"], d["offsets"].cpu().numpy())
+
+    out = {}
+    h, w, N, B = 240, 304, 200_000, 32
+    ev = batch(B, N, h, w, 2000)
+    o = torch.empty((B, h, w, 12), device=dev)
+    sec = _timed(lambda: eb.ergo12(ev, h, w, out=o), steps)
+    alg = B * (N * BYTES_PER_EVENT + h * w * 12 * 4)
+    out["config2_ergo12_gen1"] = {"workload": "ERGO-12, Gen1 304x240, 200k ev/window, batch 32 (BASELINE configs[1])", "value": B * N / sec / 1e9,
+                                  "unit": "Gevents/s", "ms_per_step": sec * 1e3,
+                                  "roofline": {"bound": "hbm", "achieved": alg / sec / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / sec / 1e9 / peak,
+                                               "algorithmic_bytes_per_step": alg, "note": "170 MB per step: partly L2 resident, launch bound"}}
+    del ev, o
+    h, w, N, B = 720, 1280, 500_000, 32
+    ev = batch(B, N, h, w, 3000)
+    o_ts = torch.empty((B, 6, 2, h, w), device=dev)
+    o_es = torch.empty((B, h, w, 12), device=dev)
+    o_to = torch.empty((B, h, w, 12), device=dev)
+    sec = _timed(lambda: eb.order_ops_fused(ev, h, w, 50000.0, out=(o_es, o_ts, o_to)), steps)
+    alg = B * (N * BYTES_PER_EVENT + 3 * h * w * 12 * 4)
+    out["config3_fused"] = {"workload": "TimeSurface + EventStack + TORE in one call, 1 Mpx, 500k ev/window, batch 32 (BASELINE configs[2])",
+                            "value": B * N / sec / 1e9, "unit": "Gevents/s", "ms_per_step": sec * 1e3,
+                            "roofline": {"bound": "hbm", "achieved": alg / sec / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / sec / 1e9 / peak,
+                                         "algorithmic_bytes_per_step": alg, "note": "events counted once, three 44 MB outputs per window"}}
+    # parity of the timed buffers: window 0 of every output against the oracle on the same events
+    from oracle import representations as orep
+    n0 = int(ev.offsets[1])
+    x, y, t, p = (v[:n0].cpu().numpy() for v in (ev.x, ev.y, ev.t, ev.p))
+    x, y = x.view(np.uint16).astype(np.int64), y.view(np.uint16).astype(np.int64)
+    t64, p32 = t.astype(np.int64), p.astype(np.int32)
+    p01 = (p32 + 1) // 2
+    want_es = orep.event_stack(x, y, t64, p01, h, w, 12)
+    want_ts = orep.time_surface(x, y, t64, p01, orep.time_surface_indices(t64, 6), h, w, 50000.0)
+    want_to = orep.tore(x + 1, y + 1, t64, p32, int(t64[-1]), 6, (h, w))
+    got_es, got_ts, got_to = o_es[0].cpu().numpy(), o_ts[0].cpu().numpy().astype(np.float64), o_to[0].cpu().numpy()
+    rel = lambda g, wv, floor: float((np.abs(g - wv) / (np.abs(wv) * 1e-5 + floor)).max())
+    out["config3_fused"]["parity_spot_check"] = {
+        "window": 0, "events": n0, "event_stack_bit_exact": bool(np.array_equal(got_es, want_es)),
+        "time_surface_err_over_tol": rel(got_ts, want_ts.reshape(got_ts.shape), 1e-30), "tore_err_over_tol": rel(got_to, want_to, 1e-6),
+        "tol": "1e-5 relative (+1e-6 absolute for TORE: log(age + 1) - log(151) in float32); a value <= 1 passes"}
+    return out
+
+
+def parity_spot_check(ev, out, windows):
+    """windows of the TIMED ERGO-12 output buffer against oracle/representations.py::ergo12 on the same events"""
+    from oracle import representations as orep
+    res = []
+    int_ch = [2, 3, 4, 5, 7, 11]
+    for i in windows:
+        e0, e1 = int(ev.offsets[i]), int(ev.offsets[i + 1])
+        x, y, t, p = (v[e0:e1].cpu().numpy() for v in (ev.x, ev.y, ev.t, ev.p))
+        want = orep.ergo12(x.view(np.uint16), y.view(np.uint16), t.astype(np.int64), p, H, W)
+        got = out[i].cpu().numpy()
+        err = np.abs(got - want)
+        res.append({"window": int(i), "events": e1 - e0, "integer_channels_bit_exact": bool(np.array_equal(got[..., int_ch], want[..., int_ch].astype(np.float32))),
+                    "max_err_over_tol": float((err / (2e-7 + 1e-5 * np.abs(want))).max()), "max_abs_err": float(err.max())})
+    return {"oracle": "oracle/representations.py::ergo12 (pinned on reference-generated fixtures)", "tol": "2e-7 + 1e-5 |ref|; a value <= 1 passes",
+            "windows": res, "pass": all(r["integer_channels_bit_exact"] and r["max_err_over_tol"] <= 1.0 for r in res)}
+
+
+def bench_dropin(dev):
+    """The call the reference pipelines make per window today (gen1_2yolo.py:296-304): get_item_transform(structured numpy events)
+    -> dense numpy array; upload, the kernel chain of one window, the FULL output copied back, x255 on the host."""
+    import torch
+    from event_representation_study_b200.representations.gen1_transforms import get_item_transform
+    from event_representation_study_b200.representations.representation_search.mixed_density_event_stack import MixedDensityEventStack
+    from oracle import representations as orep
+    synth = _load_synth()
+    out = {}
+    for name, (h, w, N) in {"gen1_50k": (240, 304, 50_000), "1mpx_1M": (720, 1280, 1_000_000)}.items():
+        wdw = synth.poisson_window(4242, N, h, w)
+        data = synth.structured(wdw, "<i4")
+        call = lambda: get_item_transform(data.copy(), str(MixedDensityEventStack), MixedDensityEventStack, h, w, N)
+        rep = call()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(7):
+            t0 = time.perf_counter()
+            rep = call()
+            ts.append(time.perf_counter() - t0)
+        ms = float(np.median(ts)) * 1e3
+        t0 = time.perf_counter()
+        want = orep.ergo12(wdw["x"], wdw["y"], wdw["t"], wdw["p"], h, w) * 255
+        cpu_ms = (time.perf_counter() - t0) * 1e3
+        out[name] = {"call": "get_item_transform(events, 'MixedDensityEventStack', ...) -> (H, W, 12) float64 numpy", "sensor": f"{w}x{h}", "events": N,
+                     "ms_per_window": ms, "Mevents_per_s": N / ms / 1e3, "h2d_bytes": N * 13, "d2h_bytes": h * w * 12 * 4,
+                     "port_ms_per_window": cpu_ms, "speedup_vs_port": cpu_ms / ms,
+                     "max_err_over_tol": float((np.abs(rep - want) / (255 * 2e-7 + 1e-5 * np.abs(want))).max()),
+                     "note": "per-window latency path: dominated by the device-to-host copy of the dense output and the float64 upcast the reference's dtype contract asks for; the batched API keeps the output on the GPU"}
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -337,8 +564,21 @@ def run_gpu_arm(a):
         }
         if world == 1 and not a.no_cpu:
             line["cpu_baseline"] = cpu_baseline_scalar(N)
+    else:
+        line = None
+    if not a.no_extras:
+        del dbuf, host  # 0.6 GB of device / pinned buffers of the end-to-end leg
+        gwd = bench_gwd(rank, world, dev, 3, with_cpu=(world == 1 and not a.no_cpu))
+        if rank == 0:
+            line["gwd"] = gwd
+            if world == 1:
+                line["parity_spot_check"] = parity_spot_check(ev, out, [0, B - 1])
+                line["configs"] = bench_configs(dev, a.steps)
+                line["dropin"] = bench_dropin(dev)
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -352,7 +592,8 @@ def main():
     ap.add_argument("--events", type=int, default=1_000_000, help="events per window")
     ap.add_argument("--clustered", action="store_true", help="80%% of the events on 5%% of the pixels (contention stress; not the headline)")
     ap.add_argument("--e2e-groups", type=int, default=4, help="window groups per step in the end-to-end leg (copy/compute overlap)")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--no-extras", action="store_true", help="headline + e2e only: skip the gwd / configs / parity_spot_check / dropin records")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference_arm(a)

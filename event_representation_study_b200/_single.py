@@ -20,13 +20,27 @@ def as_u16_coords(v, name, limit):
     return a.astype(np.uint16).view(np.int16)
 
 
-def one_window(x, y, t, p, H, W, dev=None):
-    """Arrays of one window -> EventBatch with B = 1 (t as int64 when it does not fit int32)."""
+T_SPAN_LIMIT = 2**30  # the kernels key events by t - t_first in 31 bits (include/evrep.h, EVREP_WF_T_RANGE)
+
+
+def one_window(x, y, t, p, H, W, dev=None, require_sorted=False):
+    """Arrays of one window -> EventBatch with B = 1 (t as int64 when it does not fit int32).
+
+    Everything the kernels would only FLAG per window (include/evrep.h EVREP_WF_*) is checked here on the host and raised,
+    so that a per-window drop-in never returns a tensor with silently dropped events: coordinates outside the sensor
+    (IndexError, like the reference's indexing), polarities outside {-1, 0, 1}, a timestamp span of 2^30 us or more
+    (the reference handles any int64 span; rescale the timestamps or use the batched API and read window_flags), and, for
+    the order-dependent representations, unsorted timestamps."""
     dev = dev or device()
     t = np.asarray(t)
     if t.dtype.kind == "f":
         t = t.astype(np.int64)  # the reference's own .astype(np.int64) (mixed_density_event_stack.py:29)
     t = t.astype(np.int64, copy=False)
+    if t.size and int(t.max()) - int(t.min()) >= T_SPAN_LIMIT:
+        raise ValueError(f"timestamps span {int(t.max()) - int(t.min())} us; the GPU kernels need t.max() - t.min() < 2^30 us (about 17.9 min): "
+                         "rescale or split the window")
+    if require_sorted and t.size > 1 and np.any(t[1:] < t[:-1]):
+        raise ValueError("this representation depends on the event order: the window must be time sorted")
     t_dtype = np.int32 if (t.size == 0 or (t.min() >= -2**31 and t.max() < 2**31)) else np.int64
     pp = np.asarray(p)
     if pp.size and (pp.min() < -1 or pp.max() > 1):

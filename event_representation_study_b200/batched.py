@@ -148,6 +148,7 @@ def _workspace(device, stream_ptr, nbytes):
 def _prep(ev, op, H, W, C):
     if not torch.cuda.is_available():
         raise RuntimeError("event_representation_study_b200 needs a CUDA device; there is no CPU fallback")
+    _require_current(ev.device)
     stream = torch.cuda.current_stream(ev.device).cuda_stream
     nbytes = lib.evrep_workspace_bytes(op, ev.B, ev.total, H, W, C)
     if nbytes == 0:
@@ -156,6 +157,15 @@ def _prep(ev, op, H, W, C):
     head = (ev.x.data_ptr(), ev.y.data_ptr(), ev.t.data_ptr(), ev.t.element_size(), ev.p.data_ptr(), ev.offsets.ctypes.data,
             ev.B, H, W)
     return head, ws, stream
+
+
+def _require_current(device):
+    """libevrep launches on the calling thread's current device: refuse tensors that live elsewhere instead of failing
+    inside CUDA with an invalid resource handle"""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx != torch.cuda.current_device():
+        raise ValueError(f"the events live on cuda:{idx} but the current device is cuda:{torch.cuda.current_device()}: wrap the call in "
+                         f"`with torch.cuda.device({idx}):`")
 
 
 def _out(ev, shape, out):
@@ -173,6 +183,23 @@ def window_flags(ev):
     ws = _workspaces[key]
     flags = np.zeros(ev.B, np.uint32)
     check(lib.evrep_window_flags(ws.data_ptr(), ev.B, flags.ctypes.data, stream))
+    return flags
+
+
+WF_NAMES = {_lib.WF_OUT_OF_RANGE: "an event outside the sensor was dropped", _lib.WF_UNSORTED: "timestamps decrease inside the window",
+            _lib.WF_T_RANGE: "|t - t_first| >= 2^30 us: the event was dropped", _lib.WF_BAD_POLARITY: "a polarity outside {-1, 0, 1} was clamped"}
+
+
+def raise_on_flags(ev, ignore=0):
+    """Reads the per-window status words of the last op on the current stream (synchronises) and raises ValueError when any
+    window carries an EVREP_WF_* bit not in `ignore` - the batched counterpart of the exceptions the reference's per-window
+    code raises (the kernels themselves only flag: they cannot raise)."""
+    flags = window_flags(ev)
+    bad = flags & ~np.uint32(ignore)
+    if bad.any():
+        w = int(np.nonzero(bad)[0][0])
+        what = "; ".join(v for k, v in WF_NAMES.items() if int(bad[w]) & k) or hex(int(bad[w]))
+        raise ValueError(f"window {w} (of {int((bad != 0).sum())} flagged): {what}")
     return flags
 
 

@@ -22,11 +22,13 @@ void set_error(const char* fmt, ...) {
 }
 
 // ---- optional kernel timing -------------------------------------------------------------------
-static struct Prof {
+// thread-local like the error text: a host thread that profiles its own calls neither sees nor disturbs another thread's
+struct Prof {
   int max_calls = 0, call = -1;
   cudaEvent_t* ev = nullptr;  // [max_calls][EVREP_K_N][2]
   unsigned char* used = nullptr;
-} g_prof;
+};
+static thread_local Prof g_prof;
 
 static void prof_free() {
   if (g_prof.ev) {

@@ -653,14 +653,17 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_md_tile_heavy(const uint2* 
   }
 }
 
-static int sm_count(int* n_sm) {
-  static int cached = 0;
-  if (!cached) {
-    int dev = 0;
-    EVREP_CUDA_OK(cudaGetDevice(&dev));
-    EVREP_CUDA_OK(cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev));
+static int sm_count(int* n_sm) {  // of the calling thread's current device (cached per device ordinal)
+  constexpr int MAX_DEV = 64;
+  static int cached[MAX_DEV] = {};
+  int dev = 0;
+  EVREP_CUDA_OK(cudaGetDevice(&dev));
+  int n = (dev >= 0 && dev < MAX_DEV) ? cached[dev] : 0;
+  if (!n) {
+    EVREP_CUDA_OK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    if (dev >= 0 && dev < MAX_DEV) cached[dev] = n;  // benign race: every writer stores the same value
   }
-  *n_sm = cached;
+  *n_sm = n;
   return EVREP_OK;
 }
 

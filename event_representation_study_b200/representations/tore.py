@@ -18,8 +18,12 @@ def events2ToreFeature(x, y, ts, pol, sampleTimes, k, frameSize):
         raise IndexError("index out of bounds for the TORE frame")  # what numpy raises in the reference
     xi = np.where(xi < 0, xi + Wf, xi).astype(np.uint16).view(np.int16)
     yi = np.where(yi < 0, yi + Hf, yi).astype(np.uint16).view(np.int16)
-    t = np.asarray(ts).astype(np.int64)
-    T = int(np.asarray(sampleTimes).reshape(-1)[0])
+    # integer microseconds on the GPU; fractional stamps are rounded to the nearest (the reference ages on the floats:
+    # |d age| <= 0.5 us, i.e. <= 3e-3 relative in log(age + 1) - log(151) at the 150 us floor and far less above it)
+    t = np.rint(np.asarray(ts, dtype=np.float64)).astype(np.int64) if np.asarray(ts).dtype.kind == "f" else np.asarray(ts).astype(np.int64)
+    T = int(np.rint(float(np.asarray(sampleTimes).reshape(-1)[0])))
+    if t.size and max(int(t.max()), T) - min(int(t.min()), T) >= 2**30:
+        raise ValueError("timestamps span 2^30 us or more; the GPU kernels need a window shorter than about 17.9 min")
     p = np.where(np.asarray(pol) > 0, 1, -1).astype(np.int8)
     # a sentinel event at the sample time makes it the window's last timestamp; the kernel drops it (t < T is strict)
     xi, yi = np.append(xi, np.int16(0)), np.append(yi, np.int16(0))

@@ -112,7 +112,8 @@ const char* evrep_last_error(void);
  * CUDA events around their kernels on the caller's stream (no synchronisation, a few microseconds of
  * stream time per call); n = 0 switches it off and frees the events.  evrep_profile_read synchronises on
  * the recorded events and returns, for one kernel, the summed milliseconds and the number of launches
- * timed since the last enable.  Process-global, not thread safe: benchmark use only. */
+ * timed since the last enable.  The state is per host thread (like evrep_last_error): a thread times its own calls and
+ * never sees another thread's; benchmark use only. */
 int evrep_profile_enable(int max_calls);
 int evrep_profile_read(int kernel_id, float* total_ms, int* launches);
 

@@ -1,5 +1,6 @@
-"""The N-ImageNet loader wrappers (n_imagenet/real_cnn_model/data/imagenet.py:1002-1134, SURVEY.md 8b caller ii) through
-the drop-in module, against outputs of the reference's own wrappers (tests/golden/nimg_wrappers.npz, made by
+"""The N-ImageNet loader wrappers (n_imagenet/real_cnn_model/data/imagenet.py:1002-1134, SURVEY.md 8b caller ii; kept as
+caller code in tests/nimagenet_callers.py: the reference's call sequence over this package's mirrors) and the upstream
+count / time representations of the drop-in module, against outputs of the reference's own wrappers (tests/golden/nimg_wrappers.npz, made by
 oracle/gen_golden_nimagenet.py; the time-surface wrapper of the reference cannot run - see that script - and is pinned
 through the reference's ToTimesurface with the casts the wrapper intends)."""
 import numpy as np
@@ -17,12 +18,18 @@ def N(cuda_device):
 
 
 @pytest.fixture(scope="module")
+def C(cuda_device):
+    import nimagenet_callers
+    return nimagenet_callers
+
+
+@pytest.fixture(scope="module")
 def G():
     return load(golden("nimg_wrappers")[0][1])
 
 
-def test_fix_events_training(N, G):
-    s = N.fix_events_training(G["events_s"].copy())
+def test_fix_events_training(C, G):
+    s = C.fix_events_training(G["events_s"].copy())
     assert s.dtype.names == ("x", "y", "t", "p") and all(s.dtype[k] == np.dtype("<f8") for k in s.dtype.names)
     assert np.array_equal(s["t"], G["events_s"][:, 2])
 
@@ -35,10 +42,10 @@ def test_fix_events_training(N, G):
     ("time_surface", "events_us", 1e-5, 1e-30),
     ("to_image", "events_s", 0, 0),
 ])
-def test_reshape_then_wrappers_match_the_reference(N, G, name, src, rtol, atol):
+def test_reshape_then_wrappers_match_the_reference(C, G, name, src, rtol, atol):
     import torch
     H, W = int(G["H"]), int(G["W"])
-    rep = getattr(N, "reshape_then_" + name)(torch.tensor(G[src].copy()), height=H, width=W)
+    rep = getattr(C, "reshape_then_" + name)(torch.tensor(G[src].copy()), height=H, width=W)
     assert torch.is_tensor(rep) and rep.dtype == torch.float32 and not rep.is_cuda
     want = G[name]
     assert tuple(rep.shape) == want.shape
@@ -52,9 +59,25 @@ def test_augment_hook_is_applied_first(N, G):
     import torch
     H, W = int(G["H"]), int(G["W"])
     flip = lambda e: torch.stack([W - 1 - e[:, 0], e[:, 1], e[:, 2], e[:, 3]], 1)  # noqa: E731
-    a = N.reshape_then_to_image(torch.tensor(G["events_s"].copy()), augment=flip, height=H, width=W)
-    b = N.reshape_then_to_image(torch.tensor(G["events_s"].copy()), height=H, width=W)
-    assert np.array_equal(a.numpy(), b.numpy()[:, ::-1])
+    a = N.reshape_then_acc_count_pol(torch.tensor(G["events_s"].copy()), augment=flip, height=H, width=W)
+    b = N.reshape_then_acc_count_pol(torch.tensor(G["events_s"].copy()), height=H, width=W)
+    assert np.array_equal(a.numpy(), b.numpy()[:, :, ::-1])
+
+
+def test_count_loaders_accept_degenerate_samples(N):
+    """imagenet.py:296-343 never read the time column (count_only not even the polarity): a one-event, zero-span, unsorted or
+    empty sample gives a valid count image like torch.bincount(minlength=H * W) does"""
+    import torch
+    one = torch.tensor([[2.0, 1.0, 0.5, 1.0]], dtype=torch.float64)
+    r = N.reshape_then_acc_count_only(one, height=4, width=4)
+    assert float(r.sum()) == 1.0 and float(r[0, 1, 2]) == 1.0
+    flat_t = torch.tensor([[0.0, 0.0, 0.3, 1.0], [1.0, 0.0, 0.3, -1.0], [1.0, 0.0, 0.1, 0.0]], dtype=torch.float64)  # zero span, unsorted, a p == 0 event
+    r = N.reshape_then_acc_count_only(flat_t, height=2, width=2)
+    assert float(r[0, 0, 0]) == 1.0 and float(r[0, 0, 1]) == 2.0
+    r2 = N.reshape_then_acc_count_pol(flat_t[:2], height=2, width=2)
+    assert float(r2[0, 0, 0]) == 1.0 and float(r2[1, 0, 1]) == 1.0
+    e = torch.zeros((0, 4), dtype=torch.float64)
+    assert tuple(N.reshape_then_acc_count_only(e, height=3, width=5).shape) == (1, 3, 5) and not N.reshape_then_acc_count_pol(e, height=3, width=5).any()
 
 
 @pytest.mark.parametrize("name", ["acc_count", "acc", "acc_count_pol", "acc_count_only", "acc_time", "acc_all", "acc_time_pol", "acc_exp",
@@ -105,6 +128,6 @@ def test_loader_table_matches_the_dataset_dispatch(N):
     """imagenet.py:1232-1272"""
     assert N.loader_for(None) is N.reshape_then_acc and N.loader_for("event_histogram") is N.reshape_then_acc_count_pol
     assert N.loader_for("timestamp_image") is N.reshape_then_acc_time_pol and N.loader_for("binary_event_image") is N.reshape_then_flat
-    assert N.loader_for("reshape_then_optimized") is N.reshape_then_optimized and N.loader_for("no such loader") is None
+    assert N.loader_for("reshape_then_optimized") is None and N.loader_for("no such loader") is None  # caller-side wrappers: not in this module
     with pytest.raises(NotImplementedError):
         N.loader_for("DiST")

@@ -213,6 +213,40 @@ def test_ergo12_vs_oracle(E, H, W, sizes, kw):
             assert np.array_equal(out[i][:, :, c], want[:, :, c].astype(np.float32))
 
 
+@pytest.mark.parametrize("clustered", [False, True], ids=["uniform", "clustered"])
+def test_ergo12_vs_oracle_at_the_headline_size(E, clustered):
+    """BASELINE configs[3]'s window: 1,000,000 events at 1280x720 (what bench.py times), two windows per stream kind against
+    the oracle; count / polarity-sum / presence channels bit exact (optimized_representation.py:86-134)."""
+    from oracle import representations as orep
+    H, W = 720, 1280
+    wins = streams(H, W, [1_000_000, 1_000_000], 4100 + int(clustered), clustered=clustered)
+    ev = E.pack_events(wins, "cuda")
+    out = np_(E.ergo12(ev, H, W))
+    assert (E.window_flags(ev) == 0).all()
+    for i, w in enumerate(wins):
+        want = orep.ergo12(w["x"], w["y"], w["t"], w["p"], H, W)
+        assert_close(out[i], want, rtol=RTOL, atol=VAR_ATOL, what=f"1 M-event window {i}")
+        for c in (2, 3, 4, 5, 7, 11):
+            assert np.array_equal(out[i][:, :, c], want[:, :, c].astype(np.float32))
+
+
+def test_order_ops_fused_vs_oracle_at_config3_size(E):
+    """BASELINE configs[2]'s window: 500,000 events at 1280x720, all three outputs of the fused call against the oracle"""
+    from oracle import representations as orep
+    H, W = 720, 1280
+    w = streams(H, W, [500_000], 4200)[0]
+    ev = E.pack_events([w], "cuda")
+    es, ts, to = E.order_ops_fused(ev, H, W, 50000.0)
+    x, y, t = w["x"].astype(np.int64), w["y"].astype(np.int64), w["t"].astype(np.int64)
+    p32 = w["p"].astype(np.int32)
+    p01 = (p32 + 1) // 2
+    assert np.array_equal(np_(es)[0], orep.event_stack(x, y, t, p01, H, W, 12))
+    want_ts = orep.time_surface(x, y, t, p01, orep.time_surface_indices(t, 6), H, W, 50000.0)
+    assert_close(np_(ts)[0].reshape(want_ts.shape), want_ts, rtol=RTOL, atol=1e-30, what="time surface")
+    want_to = orep.tore(x + 1, y + 1, t, p32, int(t[-1]), 6, (H, W))
+    assert_close(np_(to)[0], want_to, rtol=RTOL, atol=TORE_ATOL, what="tore")
+
+
 def test_ergo12_hot_tile(E):
     """More than 65535 events inside one 1024-pixel tile: the packed (16-bit) plan must hand the bucket to the wide plan."""
     from oracle import representations as orep
