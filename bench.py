@@ -464,14 +464,18 @@ def run_gpu_arm(a):
     value = world * B * N * a.steps / (ms_all * 1e-3) / 1e9
 
     # ---- end to end: pinned host events -> H2D -> kernels -> per-window checksum -> D2H ----------
-    # Public API only (EventBatch + ergo12).  Every step copies its own 288 MB of events from pinned host memory and reads
+    # Public API only (EventBatch / packed.decode + ergo12).  Every step copies its own events from pinned host memory and reads
     # its own result back inside the timed region.  The step is cut into groups of windows; a copy stream runs ahead of the
     # compute stream (one device buffer per group, recycled when the group's kernels are done), so the copies of step s + 1
     # are already queued when the host waits for the result of step s - the prefetch any input pipeline does.
+    # Two host formats: the SoA arrays (9 B/event) and the packed wire format of packed.py (4 B/event here), which the loader
+    # side produces once per sample; packing is not part of the timed region, exactly like slicing / casting the raw arrays.
+    from event_representation_study_b200 import packed as pk_mod
     host = {k: d[k].cpu().pin_memory() for k in ("x", "y", "t", "p")}
     n_groups = min(a.e2e_groups, B)
     bounds = [B * g // n_groups for g in range(n_groups + 1)]
     offs = ev.offsets
+    pk = pk_mod.pack_host(host["x"].numpy().view(np.uint16), host["y"].numpy().view(np.uint16), host["t"].numpy(), host["p"].numpy(), offs, H, W, pin=True)
     res_host = [torch.empty(B, dtype=torch.float64).pin_memory() for _ in range(2)]
     copy_st, comp_st = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     dbuf = [{k: torch.empty(int(offs[bounds[g + 1]] - offs[bounds[g]]), dtype=d[k].dtype, device=dev) for k in ("x", "y", "t", "p")}
@@ -479,56 +483,77 @@ def run_gpu_arm(a):
     ready = [torch.cuda.Event() for _ in range(n_groups)]   # group's events are on the device
     done = [torch.cuda.Event() for _ in range(n_groups)]    # group's kernels no longer read its buffer
 
-    def enqueue_copies(first):
-        with torch.cuda.stream(copy_st):
-            for g_ in range(n_groups):
-                if not first:
-                    copy_st.wait_event(done[g_])
-                e0, e1 = int(offs[bounds[g_]]), int(offs[bounds[g_ + 1]])
-                for k in ("x", "y", "t", "p"):
-                    dbuf[g_][k].copy_(host[k][e0:e1], non_blocking=True)
-                ready[g_].record(copy_st)
+    def e2e_leg(use_packed):
+        if use_packed:
+            blk = [pk.block_range(bounds[g], bounds[g + 1]) for g in range(n_groups)]
+            pbuf = [{"word": torch.empty(int(offs[bounds[g + 1]] - offs[bounds[g]]), dtype=torch.int32, device=dev),
+                     "dt16": torch.empty(int(offs[bounds[g + 1]] - offs[bounds[g]]), dtype=torch.int16, device=dev) if pk.dt16 is not None else None,
+                     "tbase": torch.empty(blk[g][1] - blk[g][0], dtype=torch.int32, device=dev)} for g in range(n_groups)]
 
-    def enqueue_compute(step):
-        rh = res_host[step & 1]
-        with torch.cuda.stream(comp_st):
-            for g_ in range(n_groups):
-                w0, w1 = bounds[g_], bounds[g_ + 1]
-                comp_st.wait_event(ready[g_])
-                sub = eb.EventBatch(dbuf[g_]["x"], dbuf[g_]["y"], dbuf[g_]["t"], dbuf[g_]["p"], offs[w0:w1 + 1] - int(offs[w0]))
-                o = eb.ergo12(sub, H, W, out=out[w0:w1])
-                done[g_].record(comp_st)
-                rh[w0:w1].copy_(o.view(w1 - w0, -1).sum(1, dtype=torch.float64), non_blocking=True)
-            fin = torch.cuda.Event()
-            fin.record(comp_st)
-        return fin, rh
+        def enqueue_copies(first):
+            with torch.cuda.stream(copy_st):
+                for g_ in range(n_groups):
+                    if not first:
+                        copy_st.wait_event(done[g_])
+                    e0, e1 = int(offs[bounds[g_]]), int(offs[bounds[g_ + 1]])
+                    if use_packed:
+                        pbuf[g_]["word"].copy_(pk.word[e0:e1], non_blocking=True)
+                        if pk.dt16 is not None:
+                            pbuf[g_]["dt16"].copy_(pk.dt16[e0:e1], non_blocking=True)
+                        pbuf[g_]["tbase"].copy_(pk.tbase[blk[g_][0]:blk[g_][1]], non_blocking=True)
+                    else:
+                        for k in ("x", "y", "t", "p"):
+                            dbuf[g_][k].copy_(host[k][e0:e1], non_blocking=True)
+                    ready[g_].record(copy_st)
 
-    def e2e_run(steps):
-        enqueue_copies(first=True)
-        last = None
-        for s_ in range(steps):
-            fin, rh = enqueue_compute(s_)
-            if s_ + 1 < steps:
-                enqueue_copies(first=False)   # step s + 1's events: queued before the host blocks on step s's result
-            fin.synchronize()                 # the caller reads this step's result
-            last = float(rh.sum())
-        return last
+        def enqueue_compute(step):
+            rh = res_host[step & 1]
+            with torch.cuda.stream(comp_st):
+                for g_ in range(n_groups):
+                    w0, w1 = bounds[g_], bounds[g_ + 1]
+                    comp_st.wait_event(ready[g_])
+                    lo = offs[w0:w1 + 1] - int(offs[w0])
+                    if use_packed:
+                        sub = pk_mod.decode(pbuf[g_]["word"], pbuf[g_]["dt16"], pbuf[g_]["tbase"], lo, pk.fmt, pk.x_bits, pk.y_bits, pk.block_shift, out=dbuf[g_])
+                    else:
+                        sub = eb.EventBatch(dbuf[g_]["x"], dbuf[g_]["y"], dbuf[g_]["t"], dbuf[g_]["p"], lo)
+                    o = eb.ergo12(sub, H, W, out=out[w0:w1])
+                    done[g_].record(comp_st)
+                    rh[w0:w1].copy_(o.view(w1 - w0, -1).sum(1, dtype=torch.float64), non_blocking=True)
+                fin = torch.cuda.Event()
+                fin.record(comp_st)
+            return fin, rh
+
+        def e2e_run(steps):
+            enqueue_copies(first=True)
+            last = None
+            for s_ in range(steps):
+                fin, rh = enqueue_compute(s_)
+                if s_ + 1 < steps:
+                    enqueue_copies(first=False)   # step s + 1's events: queued before the host blocks on step s's result
+                fin.synchronize()                 # the caller reads this step's result
+                last = float(rh.sum())
+            return last
+
+        e2e_run(max(2, min(40, int(0.25 / max(ms_all / a.steps * 8e-3, 1e-4)))))  # ~0.25 s of the same work while nvidia-smi starts
+        barrier()
+        t_e2e0 = time.perf_counter()
+        e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0_.record()
+        checksum = e2e_run(a.steps)
+        torch.cuda.current_stream(dev).wait_stream(comp_st)
+        e1_.record()
+        barrier()
+        wall_ms = (time.perf_counter() - t_e2e0) * 1e3
+        ms_e2e = torch.tensor([max(e0_.elapsed_time(e1_), wall_ms)], device=dev, dtype=torch.float64)  # events on another stream: trust the slower clock
+        if world > 1:
+            dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
+        return world * B * N * a.steps / (float(ms_e2e.item()) * 1e-3) / 1e9, checksum
 
     sampler2 = ClockSampler(uuid) if rank == 0 else None
-    e2e_run(max(2, min(40, int(0.25 / max(ms_all / a.steps * 8e-3, 1e-4)))))  # ~0.25 s of the same work while nvidia-smi starts
-    barrier()
-    t_e2e0 = time.perf_counter()
-    e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0_.record()
-    e2e_run(a.steps)
-    torch.cuda.current_stream(dev).wait_stream(comp_st)
-    e1_.record()
-    barrier()
-    wall_ms = (time.perf_counter() - t_e2e0) * 1e3
-    ms_e2e = torch.tensor([max(e0_.elapsed_time(e1_), wall_ms)], device=dev, dtype=torch.float64)  # events on another stream: trust the slower clock
-    if world > 1:
-        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * N * a.steps / (float(ms_e2e.item()) * 1e-3) / 1e9
+    e2e_soa, chk_soa = e2e_leg(False)
+    e2e_value, chk_pk = (e2e_leg(True) if pk is not None else (e2e_soa, chk_soa))
+    assert pk is None or chk_pk == chk_soa, f"packed and SoA end-to-end legs disagree: {chk_pk} vs {chk_soa}"
     if sampler2 is not None:  # merge the samples of both timed regions (the first one is only ~15 ms long)
         c2 = sampler2.stop()
         if clocks and c2.get("samples"):
@@ -536,8 +561,9 @@ def run_gpu_arm(a):
             clocks = {"sm_mhz": c2["sm_mhz"] if n2 >= n1 else clocks["sm_mhz"], "sm_max_mhz": max(clocks["sm_max_mhz"] or 0, c2["sm_max_mhz"] or 0),
                       "reasons": sorted(set(clocks["reasons"]) | set(c2["reasons"])), "samples": n1 + n2,
                       "regions": {"device_resident": {"sm_mhz": clocks["sm_mhz"], "samples": n1}, "end_to_end": {"sm_mhz": c2["sm_mhz"], "samples": n2}}}
-    h2d = int(sum(host[k].numel() * host[k].element_size() for k in host))
-    e2e_launches = a.steps * n_groups * KERNELS_PER_CALL
+    h2d_soa = int(sum(host[k].numel() * host[k].element_size() for k in host))
+    h2d = int(pk.nbytes) if pk is not None else h2d_soa
+    e2e_launches = a.steps * n_groups * (KERNELS_PER_CALL + (1 if pk is not None else 0))
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -552,7 +578,12 @@ def run_gpu_arm(a):
             "data": "synthetic", "config": config_dict(a, B),
             "e2e": {"value": e2e_value, "unit": "Gevents/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * 8,
                     "gpu_launches": e2e_launches,
-                    "note": f"PCIe-bound: 9 B/event over the host link; {n_groups} window groups per step, copy stream prefetching the next step's events; the dense output stays on the GPU for the model"},
+                    "host_format": (f"packed wire format {pk.fmt} ({h2d / (B * N):.2f} B/event: x, y, polarity and the offset to the base timestamp of a block of "
+                                    f"{1 << pk.block_shift} events in one 32-bit word; packed.pack_host on the loader side, evrep_unpack_events on the GPU)") if pk is not None
+                                   else "SoA arrays, 9 B/event (the stream does not fit the packed formats)",
+                    "soa9": {"value": e2e_soa, "h2d_bytes_per_step": h2d_soa, "note": "same leg with the unpacked SoA arrays (x u16, y u16, t i32, p i8) as host format"},
+                    "note": f"host-link bound; {n_groups} window groups per step, copy stream prefetching the next step's events; both legs return the same per-window "
+                            "checksums; the dense output stays on the GPU for the model (the numpy-in / numpy-out call with the full output copied back is the `dropin` record)"},
             "gpu_launches": a.steps * KERNELS_PER_CALL,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_md_tile (per-tile reduction + finalise, writes the output)",
@@ -567,7 +598,7 @@ def run_gpu_arm(a):
     else:
         line = None
     if not a.no_extras:
-        del dbuf, host  # 0.6 GB of device / pinned buffers of the end-to-end leg
+        del dbuf, host, pk  # device / pinned buffers of the end-to-end legs
         gwd = bench_gwd(rank, world, dev, 3, with_cpu=(world == 1 and not a.no_cpu))
         if rank == 0:
             line["gwd"] = gwd

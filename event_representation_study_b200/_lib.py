@@ -51,6 +51,8 @@ SIGNATURES = {
     "evrep_est_workspace_bytes": (_sz, [_i]),
     "evrep_est_quantize_batched": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "evrep_assignment_auction": (_i, [_vp, _i, _d, _vp, _vp, _vp]),
+    "evrep_unpack_workspace_bytes": (_sz, [_i, _i64]),
+    "evrep_unpack_events": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "evrep_transport_plan_host": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "evrep_gemm_workspace_bytes": (_sz, [_i, _i, _i]),
     "evrep_gemm_nt_3xtf32": (_i, [_vp, _vp, _vp, _i, _i, _i, _c.c_float, _vp, _vp, _vp, _sz, _vp]),

@@ -12,7 +12,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = ["api.cu", "binning.cu", "mixed_density.cu", "order_ops.cu", "voxel.cu", "gwd.cu", "gw_kl.cu", "image_pipeline.cu", "est.cu", "filters.cu",
-       "transport.cu", "otmi_prep.cu"]
+       "transport.cu", "unpack.cu", "otmi_prep.cu"]
 HEADERS = ["evrep_common.cuh", "md_plan.cuh"]
 OUT = os.path.join(HERE, "lib", "libevrep.so")
 OBJ_DIR = os.path.join(HERE, "build")

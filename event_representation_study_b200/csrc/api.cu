@@ -70,6 +70,9 @@ int launch_est(const uint16_t* x, const uint16_t* y, const float* t, const int8_
                cudaStream_t stream);
 int launch_auction(const float* cost, int n, double eps_rel, int* sigma, int* stats, cudaStream_t stream);
 int transport_plan_host(const float* cost, int n, int m, int cap, int* row_ptr, int* col, double* weight, int* nnz_out);
+size_t unpack_workspace_bytes(int B, int64_t total);
+int launch_unpack(const uint32_t* word, const uint16_t* dt16, const int32_t* tbase, const int64_t* win_offsets_host, int B, int fmt, int xb, int yb,
+                  int blk_shift, uint16_t* x, uint16_t* y, int32_t* t, int8_t* p, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 int launch_image_pipeline(const float* rep, int B, int H, int W, int C, int img_size, int mode, int interp, float scale_in, float scale_out,
                           float pad, int reverse, float* out, cudaStream_t stream);
 
@@ -562,6 +565,19 @@ int evrep_assignment_auction(const float* cost, int n, double eps_rel, int* sigm
   EVREP_GUARD_BEGIN
   if (!cost || !sigma || !stats) { set_error("null argument"); return EVREP_EINVAL; }
   return launch_auction(cost, n, eps_rel, sigma, stats, (cudaStream_t)stream);
+  EVREP_GUARD_END
+}
+
+size_t evrep_unpack_workspace_bytes(int B, int64_t total_events) { return (B < 0 || total_events < 0) ? 0 : unpack_workspace_bytes(B, total_events); }
+
+int evrep_unpack_events(const uint32_t* word, const uint16_t* dt16, const int32_t* tbase, const int64_t* win_offsets, int B, int format, int x_bits,
+                        int y_bits, int block_shift, uint16_t* x, uint16_t* y, int32_t* t, int8_t* p, void* workspace, size_t workspace_bytes,
+                        evrep_stream_t stream) {
+  EVREP_GUARD_BEGIN
+  if (B < 0 || !win_offsets) { set_error("B must be >= 0 and win_offsets non-null"); return EVREP_EINVAL; }
+  if (B == 0 || win_offsets[B] == 0) return EVREP_OK;
+  if (!word || !tbase || !x || !y || !t || !p || (format == 6 && !dt16)) { set_error("null array"); return EVREP_EINVAL; }
+  return launch_unpack(word, dt16, tbase, win_offsets, B, format, x_bits, y_bits, block_shift, x, y, t, p, workspace, workspace_bytes, (cudaStream_t)stream);
   EVREP_GUARD_END
 }
 

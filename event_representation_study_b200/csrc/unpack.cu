@@ -1,0 +1,110 @@
+// Packed host wire format -> the SoA event arrays of the engine.
+//
+// End to end the engine is bound by the host link: 9 B/event (x u16, y u16, t i32, p i8) at ~54 GB/s is 6 Gevents/s into a
+// pipeline that consumes 56 Gevents/s from HBM.  The data loader can pack an event into ONE 32-bit word
+//     x | y << xb | pc << (xb + yb) | dt << (xb + yb + 2)        pc = p & 3 (0, +1, -1 -> 0, 1, 3)
+// where dt = t - (base timestamp of the event's block of 2^blk_shift consecutive events of its window) as long as every dt
+// fits the 30 - xb - yb bits that are left (format 4: 4 B/event + 4 B/block; at 1280x720, 9 bits: blocks of 64 events may span
+// 511 us), or into that word plus a 16-bit dt (format 6: 6 B/event, any sensor up to 16384^2, blocks may span 65 ms).
+// Block bases are relative to the window's first timestamp: every representation only uses timestamp differences inside
+// a window, so the decoded int32 timestamps equal the originals up to one constant per window.
+//
+// One decode kernel writes x, y, t, p (9 B/event) for the regular entry points; its 13 B/event of HBM traffic are
+// ~0.1 ms per 32 M events, against 2.4 ms that the 4-byte format saves on the link.
+#include <algorithm>
+#include <vector>
+
+#include "evrep_common.cuh"
+
+namespace evrep {
+
+// grid-stride over events; win_of_chunk maps a chunk of UNPACK_CHUNK consecutive events of ONE window to (window, first local index)
+constexpr int UNPACK_CHUNK = 1024;
+
+template <bool SEP16>
+__global__ void __launch_bounds__(256) k_unpack(const uint32_t* __restrict__ word, const uint16_t* __restrict__ dt16, const int32_t* __restrict__ tbase,
+                                                const int64_t* __restrict__ offsets, const int64_t* __restrict__ blk_prefix,
+                                                const int32_t* __restrict__ chunk_win, const int32_t* __restrict__ chunk_local, int n_chunks, int xb,
+                                                int yb, int blk_shift, uint16_t* __restrict__ x, uint16_t* __restrict__ y, int32_t* __restrict__ t,
+                                                int8_t* __restrict__ p) {
+  const uint32_t xm = (1u << xb) - 1u, ym = (1u << yb) - 1u;
+  const int ps = xb + yb, ds = xb + yb + 2;
+  for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    const int w = __ldg(chunk_win + c);
+    const int64_t w0 = __ldg(offsets + w), n = __ldg(offsets + w + 1) - w0;
+    const int64_t l0 = (int64_t)__ldg(chunk_local + c) * UNPACK_CHUNK;
+    const int32_t* base = tbase + __ldg(blk_prefix + w);
+#pragma unroll
+    for (int k = 0; k < UNPACK_CHUNK / 256; ++k) {
+      const int64_t l = l0 + k * 256 + threadIdx.x;
+      if (l >= n) break;
+      const int64_t e = w0 + l;
+      const uint32_t v = __ldg(word + e);
+      const uint32_t pc = (v >> ps) & 3u;
+      const int32_t d = SEP16 ? (int32_t)__ldg(dt16 + e) : (int32_t)(v >> ds);
+      x[e] = (uint16_t)(v & xm);
+      y[e] = (uint16_t)((v >> xb) & ym);
+      t[e] = __ldg(base + (l >> blk_shift)) + d;
+      p[e] = (int8_t)(pc == 3u ? -1 : (int)pc);  // pc == 2 never leaves the packer
+    }
+  }
+}
+
+size_t unpack_workspace_bytes(int B, int64_t total) {
+  const int64_t n_chunks = total / UNPACK_CHUNK + B + 1;
+  return align_up(sizeof(int64_t) * (size_t)(B + 1), 256) * 2 + align_up(sizeof(int32_t) * (size_t)n_chunks, 256) * 2;
+}
+
+// win_offsets: HOST, B + 1.  word / dt16 / tbase: DEVICE (the packed payload, already uploaded).  workspace: DEVICE.
+int launch_unpack(const uint32_t* word, const uint16_t* dt16, const int32_t* tbase, const int64_t* win_offsets_host, int B, int fmt, int xb, int yb,
+                  int blk_shift, uint16_t* x, uint16_t* y, int32_t* t, int8_t* p, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if ((fmt != 4 && fmt != 6) || xb < 1 || yb < 1 || blk_shift < 0 || blk_shift > 16 || (fmt == 4 && xb + yb > 29) || (fmt == 6 && xb + yb > 30)) {
+    set_error("unpack: bad format (fmt %d, xb %d, yb %d, blk_shift %d)", fmt, xb, yb, blk_shift);
+    return EVREP_EINVAL;
+  }
+  const int64_t total = win_offsets_host[B];
+  if (total == 0) return EVREP_OK;
+  if (workspace_bytes < unpack_workspace_bytes(B, total) || !workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) {
+    set_error("unpack: workspace must be 256-byte aligned and hold %zu bytes", unpack_workspace_bytes(B, total));
+    return EVREP_EWORKSPACE;
+  }
+  // host tables: offsets, block prefix per window, (window, local chunk) per chunk - one upload
+  const int64_t max_chunks = total / UNPACK_CHUNK + B + 1;
+  const size_t o_bytes = align_up(sizeof(int64_t) * (size_t)(B + 1), 256), c_bytes = align_up(sizeof(int32_t) * (size_t)max_chunks, 256);
+  std::vector<unsigned char> host(2 * o_bytes + 2 * c_bytes, 0);
+  int64_t* offs = reinterpret_cast<int64_t*>(host.data());
+  int64_t* bpre = reinterpret_cast<int64_t*>(host.data() + o_bytes);
+  int32_t* cwin = reinterpret_cast<int32_t*>(host.data() + 2 * o_bytes);
+  int32_t* cloc = reinterpret_cast<int32_t*>(host.data() + 2 * o_bytes + c_bytes);
+  int64_t nb = 0, nc = 0;
+  const int64_t bs = (int64_t)1 << blk_shift;
+  for (int b = 0; b <= B; ++b) offs[b] = win_offsets_host[b];
+  for (int b = 0; b < B; ++b) {
+    const int64_t n = win_offsets_host[b + 1] - win_offsets_host[b];
+    if (n < 0) {
+      set_error("win_offsets must be non-decreasing");
+      return EVREP_EINVAL;
+    }
+    bpre[b] = nb;
+    nb += (n + bs - 1) / bs;
+    for (int64_t l = 0; l * UNPACK_CHUNK < n; ++l) {
+      cwin[nc] = b;
+      cloc[nc] = (int32_t)l;
+      ++nc;
+    }
+  }
+  bpre[B] = nb;
+  EVREP_CUDA_OK(cudaMemcpyAsync(workspace, host.data(), host.size(), cudaMemcpyHostToDevice, stream));  // pageable source: staged before the call returns
+  const unsigned char* d = (const unsigned char*)workspace;
+  const int grid = (int)std::min<int64_t>(nc, 148 * 16);
+  if (fmt == 6)
+    k_unpack<true><<<grid, 256, 0, stream>>>(word, dt16, tbase, (const int64_t*)d, (const int64_t*)(d + o_bytes), (const int32_t*)(d + 2 * o_bytes),
+                                             (const int32_t*)(d + 2 * o_bytes + c_bytes), (int)nc, xb, yb, blk_shift, x, y, t, p);
+  else
+    k_unpack<false><<<grid, 256, 0, stream>>>(word, nullptr, tbase, (const int64_t*)d, (const int64_t*)(d + o_bytes), (const int32_t*)(d + 2 * o_bytes),
+                                              (const int32_t*)(d + 2 * o_bytes + c_bytes), (int)nc, xb, yb, blk_shift, x, y, t, p);
+  EVREP_CUDA_OK(cudaGetLastError());
+  return EVREP_OK;
+}
+
+}  // namespace evrep

@@ -222,6 +222,21 @@ int evrep_gw_kl(const double* Xs, int n, int ds, const double* Xt, int m, int dt
  * 2 non-finite costs; sigma is not a permutation unless status is 0).  n <= 4096.  Enqueued on `stream`, no sync. */
 int evrep_assignment_auction(const float* cost, int n, double eps_rel, int* sigma, int* stats, evrep_stream_t stream);
 
+/* Packed host wire format (the end-to-end path is bound by the host link: 9 B/event of SoA arrays at ~54 GB/s).  The loader
+ * packs an event into one 32-bit word  x | y << x_bits | (p & 3) << (x_bits + y_bits) | dt << (x_bits + y_bits + 2)  with
+ * dt = t - tbase[block], blocks of 2^block_shift consecutive events of a window, block bases int32 relative to the
+ * window's first timestamp (format 4: 4 B/event; needs every dt < 2^(30 - x_bits - y_bits)), or with dt in a separate uint16
+ * array (format 6: 6 B/event, dt < 65536).  evrep_unpack_events decodes a batch into the SoA arrays every other entry
+ * point takes: x, y (uint16), t (int32, equal to the original timestamps up to one constant per window - representations
+ * only use differences inside a window), p (int8 in {-1, 0, +1}).  word, dt16 (format 6 only, else NULL), tbase (one entry
+ * per block, windows concatenated: window b owns ceil(n_b / 2^block_shift) blocks) and the outputs are DEVICE pointers;
+ * win_offsets is HOST (B + 1); workspace: DEVICE, evrep_unpack_workspace_bytes.  Enqueued on `stream`.
+ * Python side: event_representation_study_b200.packed (pack_host / upload). */
+size_t evrep_unpack_workspace_bytes(int B, int64_t total_events);
+int evrep_unpack_events(const uint32_t* word, const uint16_t* dt16, const int32_t* tbase, const int64_t* win_offsets, int B, int format,
+                        int x_bits, int y_bits, int block_shift, uint16_t* x, uint16_t* y, int32_t* t, int8_t* p, void* workspace,
+                        size_t workspace_bytes, evrep_stream_t stream);
+
 /* The LMO of evrep_gw_kl for rectangular plans (n != m): an optimal vertex of the transportation problem
  *     min <cost, G>  s.t.  G 1 = 1/n,  G^T 1 = 1/m,  G >= 0
  * (what POT's ot.emd returns inside ot.gromov.gromov_wasserstein; gromov_wasserstein.py:62-69).  HOST function, HOST

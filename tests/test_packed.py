@@ -1,0 +1,70 @@
+"""Packed host wire format (event_representation_study_b200/packed.py, evrep_unpack_events): the numpy packer against its numpy
+decoder on the CPU, the CUDA decode kernel against both on the GPU, and ERGO-12 from a packed batch against the SoA batch."""
+import numpy as np
+import pytest
+
+
+def _batch(sizes, H, W, seed=0, polarity="pm1", duration_us=300_000):
+    from event_representation_study_b200.synth import pack_batch, poisson_window
+    wins = [poisson_window(seed + i, n, H, W, polarity=polarity, duration_us=duration_us) for i, n in enumerate(sizes)]
+    for i, w in enumerate(wins):
+        w["t"] = w["t"] + 1_000_000 * (i + 1)  # absolute stamps: the format stores them relative to the window's first event
+    return wins, pack_batch(wins)
+
+
+@pytest.mark.parametrize("sizes,H,W,fmt,dur", [([5000, 0, 64, 65, 1, 12345], 240, 304, 4, 2_000), ([5000, 0, 256, 257, 1, 12345], 240, 304, 6, 50_000),
+                                               ([20000, 777], 720, 1280, None, 2_000), ([3000], 4000, 5000, None, 300_000)])
+def test_pack_roundtrip_on_the_host(sizes, H, W, fmt, dur):
+    from event_representation_study_b200 import packed
+    wins, b = _batch(sizes, H, W, 3, duration_us=dur)
+    pk = packed.pack_host(b["x"], b["y"], b["t"], b["p"], b["offsets"], H, W, fmt=fmt)
+    assert pk is not None and pk.fmt == (fmt or (4 if W <= 2048 else 6))
+    x, y, t, p = packed.unpack_numpy(pk)
+    assert np.array_equal(x, b["x"]) and np.array_equal(y, b["y"]) and np.array_equal(p, b["p"])
+    n = np.diff(b["offsets"])
+    first = np.repeat(b["t"].astype(np.int64)[b["offsets"][:-1][n > 0]], n[n > 0])
+    assert np.array_equal(t, b["t"].astype(np.int64) - first)
+    per_event = pk.nbytes / max(1, int(b["offsets"][-1]))
+    assert per_event < (4.2 if pk.fmt == 4 else 6.1) or int(b["offsets"][-1]) < 5000
+
+
+def test_pack_falls_back_when_a_block_spans_too_long():
+    from event_representation_study_b200 import packed
+    wins, b = _batch([4000], 240, 304, 5, duration_us=300_000_000)  # 75 ms between events: no block of 64 fits 2^13 us
+    assert packed.pack_host(b["x"], b["y"], b["t"], b["p"], b["offsets"], 240, 304, fmt=4) is None
+    pk = packed.pack_host(b["x"], b["y"], b["t"], b["p"], b["offsets"], 240, 304)
+    assert pk is None or pk.fmt == 6
+    wins, b = _batch([300], 240, 304, 6, duration_us=2_000_000_000)
+    assert packed.pack_host(b["x"], b["y"], b["t"], b["p"], b["offsets"], 240, 304) is None  # caller uploads the SoA arrays
+    with pytest.raises(IndexError):
+        packed.pack_host(np.array([400]), np.array([0]), np.array([0]), np.array([1]), np.array([0, 1]), 240, 304)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fmt", [4, 6])
+@pytest.mark.parametrize("polarity", ["pm1", "01"])
+def test_decode_kernel_matches_the_host_decoder(cuda_device, fmt, polarity):
+    from event_representation_study_b200 import packed
+    H, W = 720, 1280
+    # dense enough for the 9 offset bits format 4 has at this sensor size (a block of 64 events may span 511 us)
+    wins, b = _batch([100_000, 0, 1, 63, 64, 65, 1023, 1024, 1025, 4097, 250_001], H, W, 11, polarity=polarity, duration_us=400 if fmt == 4 else 40_000)
+    pk = packed.pack_host(b["x"], b["y"], b["t"], b["p"], b["offsets"], H, W, fmt=fmt, pin=True)
+    ev = packed.upload(pk, "cuda")
+    x, y, t, p = packed.unpack_numpy(pk)
+    assert np.array_equal(ev.x.cpu().numpy().view(np.uint16), x) and np.array_equal(ev.y.cpu().numpy().view(np.uint16), y)
+    assert np.array_equal(ev.t.cpu().numpy().astype(np.int64), t) and np.array_equal(ev.p.cpu().numpy(), p)
+
+
+@pytest.mark.gpu
+def test_ergo12_from_a_packed_batch_equals_the_soa_batch(cuda_device):
+    """timestamps come back shifted by one constant per window: ERGO-12 (t - t.min() first thing) must not see it"""
+    import torch
+    import event_representation_study_b200.batched as eb
+    from event_representation_study_b200 import packed
+    H, W = 240, 304
+    wins, b = _batch([60_000, 30_001, 7], H, W, 21, duration_us=20_000)
+    want = eb.ergo12(eb.pack_events(wins, "cuda", t_dtype=np.int64), H, W)
+    pk = packed.pack_host(b["x"], b["y"], b["t"], b["p"], b["offsets"], H, W)
+    assert pk is not None
+    got = eb.ergo12(packed.upload(pk, "cuda"), H, W)
+    assert torch.equal(got, want)
