@@ -433,6 +433,31 @@ def assignment_auction(cost, eps_rel=1e-9):
     return sigma, {"rounds": r, "bids": b, "status": status}
 
 
+class GraphedCall:
+    """A fixed sequence of batched calls captured into a CUDA graph: `fn` is run (twice eagerly, then once under capture) on
+    a private stream and `replay()` re-issues all of its kernels with ONE launch.  Valid as long as the device buffers `fn`
+    touches keep their addresses and the window offsets stay the same (fixed-size windows, e.g. Gen1's num_events = 50 000,
+    ev-YOLOv6/tools/train.py:43); event values may change between replays.  Batches of up to 319 windows only: their window
+    tables travel as kernel arguments, larger ones need a host-to-device copy that a capture cannot hold.  This is what
+    makes small batches (BASELINE configs[1]: 6.4 M events per step) stop being launch bound."""
+
+    def __init__(self, fn, warmup=2):
+        self._stream = torch.cuda.Stream()
+        self._stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._stream):
+            for _ in range(max(1, warmup)):  # workspaces and shared-memory attributes are set up outside the capture
+                fn()
+        torch.cuda.current_stream().wait_stream(self._stream)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=self._stream):
+            self.result = fn()
+
+    def replay(self):
+        self.graph.replay()
+        return self.result
+
+
 def transport_plan_host(cost):
     """The rectangular LMO of gw_kl on its own (HOST, no GPU involved): an optimal vertex of
     min <cost, G> s.t. G 1 = 1/n, G^T 1 = 1/m, G >= 0 for a float32 (n, m) numpy cost -> dense float64 (n, m) plan."""

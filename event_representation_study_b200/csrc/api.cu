@@ -253,6 +253,7 @@ int evrep_mixed_density_batched(const uint16_t* x, const uint16_t* y, const void
   if (g.tile_px != 1024) g.split = 0, g.Tb = g.T;
   g.B = B;
   g.total = total;
+  g.n_max = n_max;
   Workspace ws;
   EVREP_TRY(carve_checked(workspace, workspace_bytes, B, total, g.Tb, &ws));
   EVREP_TRY(run_binning(ev, win_offsets, g, ws, stacking == EVREP_STACK_SBN ? REC_T_WMASK : REC_T_ONLY, 0, nullptr, (cudaStream_t)stream));

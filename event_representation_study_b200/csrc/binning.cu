@@ -20,6 +20,7 @@
 // (representations/representation_search/mixed_density_event_stack.py:111-151, operations.py:39-89)
 // and the np.put passes of event_stack.py:118-131.
 #include <limits.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -217,16 +218,38 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t* a, int n, uin
 // ---------------------------------------------------------------------------------------------
 // per-window initialisation: one CTA per window; also labels the window's super-chunks
 // ---------------------------------------------------------------------------------------------
-template <typename TT>
-__global__ void k_init(const TT* __restrict__ t, const int64_t* __restrict__ offsets, const int32_t* __restrict__ sc_prefix,
-                       int32_t* __restrict__ sc_win, WinParams* __restrict__ wp) {
+// Offsets and super-chunk prefix of a small batch travel as a kernel argument (no host-to-device copy at all: nothing for
+// the driver to stage, and the whole call can be captured into a CUDA graph); larger batches upload them.
+constexpr int INIT_TABLE_MAX = 320;  // windows (+ 1): 12 bytes each, under the 4 KB kernel-parameter limit
+struct InitTable {
+  int64_t offsets[INIT_TABLE_MAX];
+  int32_t sc_prefix[INIT_TABLE_MAX];
+};
+
+template <typename TT, bool BY_VALUE>
+__global__ void k_init(const TT* __restrict__ t, int64_t* __restrict__ offsets, int32_t* __restrict__ sc_prefix, const __grid_constant__ InitTable tab,
+                       int B, int32_t* __restrict__ sc_win, WinParams* __restrict__ wp, uint32_t* __restrict__ ticket) {
   const int b = blockIdx.x;
+  if (b == 0 && threadIdx.x < 64) ticket[threadIdx.x] = 0;  // work counters of the persistent tile kernels
+  int64_t o0, o1;
+  int32_t s0, s1;
+  if (BY_VALUE) {
+    o0 = tab.offsets[b]; o1 = tab.offsets[b + 1];
+    s0 = tab.sc_prefix[b]; s1 = tab.sc_prefix[b + 1];
+    if (threadIdx.x == 0) {  // the tables also live in the workspace for the kernels that follow
+      offsets[b] = o0; sc_prefix[b] = s0;
+      if (b == B - 1) { offsets[B] = o1; sc_prefix[B] = s1; }
+    }
+  } else {
+    o0 = offsets[b]; o1 = offsets[b + 1];
+    s0 = sc_prefix[b]; s1 = sc_prefix[b + 1];
+  }
   if (sc_win)
-    for (int s = sc_prefix[b] + (int)threadIdx.x; s < sc_prefix[b + 1]; s += (int)blockDim.x) sc_win[s] = b;
+    for (int s = s0 + (int)threadIdx.x; s < s1; s += (int)blockDim.x) sc_win[s] = b;
   if (threadIdx.x != 0) return;
   WinParams w;
-  w.start = offsets[b];
-  w.n = offsets[b + 1] - offsets[b];
+  w.start = o0;
+  w.n = o1 - o0;
   w.flags = 0;
   w.has_m1 = 0;
   w.pad = 0;
@@ -744,6 +767,185 @@ __global__ void __launch_bounds__(BIN_THREADS, EVREP_BIN_CTAS) k_bin(const uint1
   for (uint32_t i = tid; i < total; i += BIN_THREADS) dst[i + delta[sbkt[i]]] = stage[i];
 }
 
+// ---------------------------------------------------------------------------------------------
+// Single-pass alternative for consumers that can GATHER (the compile-time specialised ERGO-12 tile kernel): a CTA sorts its
+// super-chunk by bucket entirely on chip and writes the records back where the events were - no global histogram, no
+// column / bucket scans, no second read of the events, and the record write is one contiguous stream.  What replaces the
+// global placement is the per-super-chunk offset row `cc` (exclusive bucket offsets + total, as k_hist writes it): the
+// records of bucket k of super-chunk s are records[first(s) + cc[s][k] .. first(s) + cc[s][k + 1]), first(s) = max(start of the
+// window, first event slot of the super-chunk).  Per event: one returning shared-memory atomic (its rank inside its
+// bucket; kept in a register), after the block scan one offset load and one 8-byte staged store.
+// ---------------------------------------------------------------------------------------------
+template <typename TT, bool SPLIT>
+__global__ void __launch_bounds__(BIN_THREADS, EVREP_BIN_CTAS) k_sortbin(const uint16_t* __restrict__ x, const uint16_t* __restrict__ y,
+                                                         const TT* __restrict__ t, const int8_t* __restrict__ p,
+                                                         WinParams* __restrict__ wp, const int32_t* __restrict__ sc_prefix,
+                                                         const int32_t* __restrict__ sc_win, const Geom g, const bool vec,
+                                                         uint16_t* __restrict__ cc, uint2* __restrict__ records) {
+  extern __shared__ __align__(16) unsigned char sh_raw[];
+  uint2* stage = reinterpret_cast<uint2*>(sh_raw);            // SUPER records, sorted by bucket
+  uint32_t* hist = reinterpret_cast<uint32_t*>(stage + SUPER);  // Tb: counts, then exclusive offsets
+  __shared__ int sh_tmin, sh_tmax;
+  __shared__ uint32_t sh_flags, sh_m1;
+  __shared__ uint32_t warp_tot[BIN_THREADS / 32 + 1];
+
+  const int tid = threadIdx.x;
+  const ChunkHdr h = chunk_hdr(blockIdx.x, wp, sc_prefix, sc_win);
+  ChunkRegs<TT> r;
+  chunk_fetch<TT>(r, h, x, y, t, p, vec, tid);
+  for (int i = tid; i < g.Tb; i += BIN_THREADS) hist[i] = 0;
+  if (tid == 0) { sh_tmin = INT_MAX; sh_tmax = INT_MIN; sh_flags = 0; sh_m1 = 0; }
+  __syncthreads();
+
+  uint32_t hbase = (uint32_t)__cvta_generic_to_shared(hist), sbase = (uint32_t)__cvta_generic_to_shared(stage);
+  asm volatile("" : "+r"(hbase), "+r"(sbase));
+  const int n = h.n;
+  const int64_t start = h.start, t_base = h.t_base;
+  const int n3 = n / 3, s4 = n / 2, s5 = s4 + n / 4, s6 = s5 + n / 8;
+  const uint32_t Wd = (uint32_t)g.W, Hd = (uint32_t)g.H;
+  const uint32_t pix_mask = (uint32_t)(g.tile_px - 1);
+  const int tile_shift = g.tile_shift;
+  auto sbn = [&](int idx) -> uint32_t {
+    return 1u | (idx < n3 ? 2u : (idx < 2 * n3 ? 4u : (idx < 3 * n3 ? 8u : 0u))) | (idx >= s4 ? 16u : 0u) | (idx >= s5 ? 32u : 0u) | (idx >= s6 ? 64u : 0u);
+  };
+  auto bucket = [&](uint32_t lin, int pv) {
+    uint32_t bin = lin >> tile_shift;
+    if (SPLIT) bin = bin + bin + (pv > 0 ? 0u : 1u);
+    return bin;
+  };
+  BinAcc acc;
+  // staging of one record at a known slot
+  auto stage_rec = [&](uint32_t slot, uint32_t lin, int pv, int32_t t_rel, uint32_t aux, bool keep) {
+    uint32_t k = (uint32_t)t_rel, meta = rec_meta(lin & pix_mask, aux, (uint32_t)pv & 3u);
+    if (keep) {
+      acc.tmin = min(acc.tmin, t_rel);
+      acc.tmax = max(acc.tmax, t_rel);
+      acc.m1 |= pv == -1 ? aux : 0u;
+    } else {
+      k = 0u;
+      meta = REC_NULL_META;
+    }
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sbase + (slot << 3)), "r"(k), "r"(meta) : "memory");
+  };
+
+  // Is every event of this CTA on the fast path (inside the window, valid pixel / polarity, sorted, in the 31-bit time range, one
+  // SBN mask per thread chunk)?  Nearly always, except in the first and last super-chunk of a window; the decision is CTA-wide
+  // so that the two passes below stay free of per-event checks.
+  bool mine = true;
+#pragma unroll
+  for (int sub = 0; sub < SC_CHUNKS; ++sub) {
+    const int64_t g0 = h.c0 + (int64_t)sub * CHUNK + (int64_t)tid * EPT;
+    const int idx0 = (int)(g0 - start);
+    if (idx0 >= n || idx0 + EPT <= 0) continue;  // no events here
+    bool f = r.full[sub];
+    if (f) {
+      TT prev = r.t_before[sub];
+      bool sorted = true;
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        const TT te = r.qt[sub].get(e);
+        sorted &= !(te < prev);
+        prev = te;
+      }
+      const int64_t d0 = (int64_t)r.qt[sub].get(0) - t_base, d7 = (int64_t)r.qt[sub].get(EPT - 1) - t_base;
+      f = sorted && d0 > -(int64_t)T_REL_LIMIT && d7 < (int64_t)T_REL_LIMIT && polarities_valid4(r.qp[sub].x) && polarities_valid4(r.qp[sub].y) &&
+          sbn(idx0) == sbn(idx0 + EPT - 1);
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) f &= (raw_u16(r.qx[sub], e) < Wd) & (raw_u16(r.qy[sub], e) < Hd);
+    }
+    mine &= f;
+  }
+  const bool cta_fast = __syncthreads_and(mine);
+  uint32_t total;
+  if (cta_fast) {
+    // pass 1: rank every event inside its bucket (two 16-bit ranks per register)
+    uint32_t rk[SC_CHUNKS][EPT / 2];
+#pragma unroll
+    for (int sub = 0; sub < SC_CHUNKS; ++sub) {
+      const int idx0 = (int)(h.c0 + (int64_t)sub * CHUNK + (int64_t)tid * EPT - start);
+#pragma unroll
+      for (int k = 0; k < EPT / 2; ++k) rk[sub][k] = 0;
+      if (idx0 >= n || idx0 + EPT <= 0) continue;
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        const uint32_t lin = raw_u16(r.qy[sub], e) * Wd + raw_u16(r.qx[sub], e);
+        rk[sub][e >> 1] |= smem_fetch_inc(hbase + (bucket(lin, raw_i8(r.qp[sub], e)) << 2)) << (16 * (e & 1));
+      }
+    }
+    __syncthreads();
+    total = block_exclusive_scan(hist, g.Tb, warp_tot);  // ends with a barrier
+    // pass 2: stage every record at offset[bucket] + rank
+#pragma unroll
+    for (int sub = 0; sub < SC_CHUNKS; ++sub) {
+      const int idx0 = (int)(h.c0 + (int64_t)sub * CHUNK + (int64_t)tid * EPT - start);
+      if (idx0 >= n || idx0 + EPT <= 0) continue;
+      const uint32_t aux = sbn(idx0);
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        const uint32_t lin = raw_u16(r.qy[sub], e) * Wd + raw_u16(r.qx[sub], e);
+        const int pv = raw_i8(r.qp[sub], e);
+        const int32_t t_rel = sizeof(TT) == 4 ? (int32_t)((uint32_t)r.qt[sub].get(e) - (uint32_t)t_base) : (int32_t)((int64_t)r.qt[sub].get(e) - t_base);
+        uint32_t off;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(off) : "r"(hbase + (bucket(lin, pv) << 2)) : "memory");
+        stage_rec(off + ((rk[sub][e >> 1] >> (16 * (e & 1))) & 0xffffu), lin, pv, t_rel, aux, true);
+      }
+    }
+  } else {
+    // generic path (window edges, unsorted / out-of-range data): count, scan, then one more returning atomic per event for its
+    // slot; every event is re-read with scalar loads and fully checked
+    auto visit = [&](bool place) {
+#pragma unroll 1
+      for (int sub = 0; sub < SC_CHUNKS; ++sub) {
+        const int64_t g0 = h.c0 + (int64_t)sub * CHUNK + (int64_t)tid * EPT;
+        const int idx0 = (int)(g0 - start);
+        if (idx0 >= n || idx0 + EPT <= 0) continue;
+        TT t_prev = 0;
+        bool have_prev = idx0 >= 1;
+        if (have_prev) t_prev = __ldg(t + g0 - 1);
+#pragma unroll 1
+        for (int e = 0; e < EPT; ++e) {
+          const int idx = idx0 + e;
+          if ((uint32_t)idx >= (uint32_t)n) continue;
+          const TT te = __ldg(t + g0 + e);
+          const uint32_t xe = __ldg(x + g0 + e), ye = __ldg(y + g0 + e);
+          int pv = __ldg(p + g0 + e);
+          if (have_prev && te < t_prev) acc.flags |= EVREP_WF_UNSORTED;
+          t_prev = te;
+          have_prev = true;
+          if ((xe >= Wd) | (ye >= Hd)) { acc.flags |= EVREP_WF_OUT_OF_RANGE; continue; }
+          bool keep = true;
+          const int64_t d = (int64_t)te - t_base;
+          if (d >= T_REL_LIMIT || d <= -T_REL_LIMIT) { acc.flags |= EVREP_WF_T_RANGE; keep = false; }
+          if (pv > 1 || pv < -1) { acc.flags |= EVREP_WF_BAD_POLARITY; pv = pv > 0 ? 1 : -1; }
+          const uint32_t lin = ye * Wd + xe;
+          const uint32_t slot = smem_fetch_inc(hbase + (bucket(lin, pv) << 2));
+          if (place) stage_rec(slot, lin, pv, (int32_t)d, sbn(idx), keep);
+        }
+      }
+    };
+    visit(false);
+    __syncthreads();
+    total = block_exclusive_scan(hist, g.Tb, warp_tot);
+    // the offsets go to global memory before the second pass turns them into cursors
+    {
+      uint16_t* dst = cc + (size_t)blockIdx.x * cc_stride(g.Tb);
+      for (int i = tid; i < g.Tb; i += BIN_THREADS) dst[i] = (uint16_t)hist[i];
+      if (tid == 0) dst[g.Tb] = (uint16_t)total;
+    }
+    __syncthreads();
+    visit(true);
+  }
+  if (cta_fast) {
+    uint16_t* dst = cc + (size_t)blockIdx.x * cc_stride(g.Tb);
+    for (int i = tid; i < g.Tb; i += BIN_THREADS) dst[i] = (uint16_t)hist[i];
+    if (tid == 0) dst[g.Tb] = (uint16_t)total;
+  }
+  bin_publish(acc, wp + h.b, &sh_tmin, &sh_tmax, &sh_flags, &sh_m1, tid);  // contains the barrier after the staging
+  // copy out: the sorted super-chunk as one contiguous run
+  uint2* dst = records + (h.c0 > start ? h.c0 : start);
+  for (uint32_t i = tid; i < total; i += BIN_THREADS) dst[i] = stage[i];
+}
+
 template <typename TT, int MODE, bool SPLIT, bool DIV = false>
 static int launch_bin(const Events& ev, const Geom& g, const Workspace& ws, int n_sc, bool vec, cudaStream_t stream) {
   const size_t smem = (size_t)SUPER * (sizeof(uint2) + sizeof(uint16_t)) + 2 * sizeof(uint32_t) * (size_t)g.Tb;
@@ -813,19 +1015,30 @@ int prepare_windows(const Events& ev, const int64_t* win_offsets_host, const Geo
     set_error("internal: super-chunk bound exceeded");
     return EVREP_EINVAL;
   }
-  // pageable-source async copies are staged before the call returns, so the host vectors may die here
-  // one copy for both tables (each pageable-source copy costs several microseconds of staging on the host: at Gen1 batch
-  // sizes the whole call is ~130 us)
-  std::vector<int64_t> pack((size_t)(g.B + 1) + ((size_t)(g.B + 1) + 1) / 2);
-  memcpy(pack.data(), win_offsets_host, sizeof(int64_t) * (size_t)(g.B + 1));
-  memcpy(pack.data() + (g.B + 1), prefix.data(), sizeof(int32_t) * (size_t)(g.B + 1));
-  EVREP_CUDA_OK(cudaMemcpyAsync(ws.offsets, pack.data(), sizeof(int64_t) * (size_t)(g.B + 1) + sizeof(int32_t) * (size_t)(g.B + 1),
-                                cudaMemcpyHostToDevice, stream));
   int32_t* sc_win = g.Tb > 0 ? ws.sc_win : nullptr;
-  if (ev.t_bytes == 4)
-    k_init<int32_t><<<g.B, 64, 0, stream>>>((const int32_t*)ev.t, ws.offsets, ws.sc_prefix, sc_win, ws.wp);
-  else
-    k_init<int64_t><<<g.B, 64, 0, stream>>>((const int64_t*)ev.t, ws.offsets, ws.sc_prefix, sc_win, ws.wp);
+  if (g.B + 1 <= INIT_TABLE_MAX) {
+    InitTable tab;
+    memcpy(tab.offsets, win_offsets_host, sizeof(int64_t) * (size_t)(g.B + 1));
+    memcpy(tab.sc_prefix, prefix.data(), sizeof(int32_t) * (size_t)(g.B + 1));
+    if (ev.t_bytes == 4)
+      k_init<int32_t, true><<<g.B, 64, 0, stream>>>((const int32_t*)ev.t, ws.offsets, ws.sc_prefix, tab, g.B, sc_win, ws.wp, ws.ticket);
+    else
+      k_init<int64_t, true><<<g.B, 64, 0, stream>>>((const int64_t*)ev.t, ws.offsets, ws.sc_prefix, tab, g.B, sc_win, ws.wp, ws.ticket);
+  } else {
+    // pageable-source async copies are staged before the call returns, so the host vectors may die here
+    // one copy for both tables (each pageable-source copy costs several microseconds of staging on the host)
+    std::vector<int64_t> pack((size_t)(g.B + 1) + ((size_t)(g.B + 1) + 1) / 2);
+    memcpy(pack.data(), win_offsets_host, sizeof(int64_t) * (size_t)(g.B + 1));
+    memcpy(pack.data() + (g.B + 1), prefix.data(), sizeof(int32_t) * (size_t)(g.B + 1));
+    EVREP_CUDA_OK(cudaMemcpyAsync(ws.offsets, pack.data(), sizeof(int64_t) * (size_t)(g.B + 1) + sizeof(int32_t) * (size_t)(g.B + 1),
+                                  cudaMemcpyHostToDevice, stream));
+    InitTable tab;  // unused
+    tab.offsets[0] = 0;
+    if (ev.t_bytes == 4)
+      k_init<int32_t, false><<<g.B, 64, 0, stream>>>((const int32_t*)ev.t, ws.offsets, ws.sc_prefix, tab, g.B, sc_win, ws.wp, ws.ticket);
+    else
+      k_init<int64_t, false><<<g.B, 64, 0, stream>>>((const int64_t*)ev.t, ws.offsets, ws.sc_prefix, tab, g.B, sc_win, ws.wp, ws.ticket);
+  }
   EVREP_CUDA_OK(cudaGetLastError());
   return EVREP_OK;
 }
@@ -842,8 +1055,7 @@ int run_binning(const Events& ev, const int64_t* win_offsets_host, const Geom& g
   }
   int rc = prepare_windows(ev, win_offsets_host, g, ws, &n_sc, stream);
   if (rc) return rc;
-  EVREP_CUDA_OK(cudaMemsetAsync(ws.ticket, 0, sizeof(uint32_t) * 64, stream));
-  const bool vec = events_vectorisable(ev);
+  const bool vec = events_vectorisable(ev);  // (k_init zeroed the ticket counters)
 
   if (rec_mode == REC_T_SNAP || rec_mode == REC_T_IDX) {
     const int64_t* user = nullptr;
@@ -857,7 +1069,17 @@ int run_binning(const Events& ev, const int64_t* win_offsets_host, const Geom& g
       k_snap_init<int64_t><<<g.B, 32, 0, stream>>>((const int64_t*)ev.t, ws.wp, user, n_snap, ws.snap);
     EVREP_CUDA_OK(cudaGetLastError());
   }
-  if (n_sc > 0) {
+  if (n_sc > 0 && rec_mode == REC_T_WMASK && g.split && ev.t_bytes == 4 && getenv("EVREP_SORTBIN_TEST") && getenv("EVREP_SORTBIN_TEST")[0] == '1') {  // experiment: time the single-pass kernel alone
+    const size_t smem = (size_t)SUPER * sizeof(uint2) + sizeof(uint32_t) * (size_t)g.Tb;
+    if (ev.t_bytes == 4) {
+      EVREP_CUDA_OK(cudaFuncSetAttribute(k_sortbin<int32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      prof_begin(EVREP_K_COUNT, stream);
+      k_sortbin<int32_t, true><<<n_sc, BIN_THREADS, smem, stream>>>(ev.x, ev.y, (const int32_t*)ev.t, ev.p, ws.wp, ws.sc_prefix, ws.sc_win, g, vec, ws.cc, ws.records);
+      prof_end(EVREP_K_COUNT, stream);
+    }
+    EVREP_CUDA_OK(cudaGetLastError());
+    prepare_windows(ev, win_offsets_host, g, ws, &n_sc, stream);  // reset the window scalars the test kernel touched
+  } else if (n_sc > 0) {
     prof_begin(EVREP_K_COUNT, stream);
     if (g.split)
       k_hist<true, false><<<n_sc, BIN_THREADS, sizeof(uint32_t) * (size_t)g.Tb, stream>>>(ev.x, ev.y, ev.p, ws.wp, ws.sc_prefix, ws.sc_win, g, vec, ws.cc);

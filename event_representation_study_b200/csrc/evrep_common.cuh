@@ -74,6 +74,7 @@ struct Geom {
   int split;                   // 1: every tile has two buckets, p > 0 first, then the rest (mixed-density static kernels)
   int Tb;                      // buckets per window = T << split
   int64_t total;               // total events in the batch
+  int64_t n_max;               // events of the largest window (0 = unknown)
   unsigned long long t_magic;  // ceil(2^44 / T): id / T == (id * t_magic) >> 44 for id < 2^32, T <= 4096
 };
 

@@ -690,8 +690,9 @@ static int launch_static(const Geom& g, const Workspace& ws, float* out, cudaStr
   const int grid = n_tiles < per_sm * n_sm ? n_tiles : per_sm * n_sm;
   prof_begin(EVREP_K_TILE, stream);
   light<<<grid, TILE_THREADS, smem_l, stream>>>(ws.records, ws.base, ws.hist, ws.wp, g, ws.ticket, out);
-  heavy<<<(n_tiles + TILE_THREADS - 1) / TILE_THREADS < n_sm ? (n_tiles + TILE_THREADS - 1) / TILE_THREADS : n_sm, TILE_THREADS, smem_h, stream>>>(
-      ws.records, ws.base, ws.hist, ws.wp, g, out);
+  if (!(g.n_max > 0 && g.n_max < (int64_t)MD_PACKED_LIMIT))  // a bucket cannot hold more events than its window: nothing for the wide plan
+    heavy<<<(n_tiles + TILE_THREADS - 1) / TILE_THREADS < n_sm ? (n_tiles + TILE_THREADS - 1) / TILE_THREADS : n_sm, TILE_THREADS, smem_h, stream>>>(
+        ws.records, ws.base, ws.hist, ws.wp, g, out);
   prof_end(EVREP_K_TILE, stream);
   EVREP_CUDA_OK(cudaGetLastError());
   return EVREP_OK;

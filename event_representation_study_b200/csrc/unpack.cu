@@ -18,21 +18,28 @@
 
 namespace evrep {
 
-// grid-stride over events; win_of_chunk maps a chunk of UNPACK_CHUNK consecutive events of ONE window to (window, first local index)
+// grid-stride over chunks of UNPACK_CHUNK consecutive events of ONE window; chunk_prefix[b] = number of chunks before window b
+// (the window of a chunk is found by binary search: the three per-window tables are a few hundred bytes, small enough for
+// the driver to embed the upload in the command stream - a larger pageable upload would make every call wait for the stream)
 constexpr int UNPACK_CHUNK = 1024;
 
 template <bool SEP16>
 __global__ void __launch_bounds__(256) k_unpack(const uint32_t* __restrict__ word, const uint16_t* __restrict__ dt16, const int32_t* __restrict__ tbase,
                                                 const int64_t* __restrict__ offsets, const int64_t* __restrict__ blk_prefix,
-                                                const int32_t* __restrict__ chunk_win, const int32_t* __restrict__ chunk_local, int n_chunks, int xb,
-                                                int yb, int blk_shift, uint16_t* __restrict__ x, uint16_t* __restrict__ y, int32_t* __restrict__ t,
-                                                int8_t* __restrict__ p) {
+                                                const int64_t* __restrict__ chunk_prefix, int B, int xb, int yb, int blk_shift,
+                                                uint16_t* __restrict__ x, uint16_t* __restrict__ y, int32_t* __restrict__ t, int8_t* __restrict__ p) {
   const uint32_t xm = (1u << xb) - 1u, ym = (1u << yb) - 1u;
   const int ps = xb + yb, ds = xb + yb + 2;
-  for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
-    const int w = __ldg(chunk_win + c);
+  const int64_t n_chunks = __ldg(chunk_prefix + B);
+  for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    int lo = 0, hi = B;  // last window with chunk_prefix[w] <= c (windows without events own no chunk and are skipped)
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(chunk_prefix + mid) <= c) lo = mid; else hi = mid;
+    }
+    const int w = lo;
     const int64_t w0 = __ldg(offsets + w), n = __ldg(offsets + w + 1) - w0;
-    const int64_t l0 = (int64_t)__ldg(chunk_local + c) * UNPACK_CHUNK;
+    const int64_t l0 = (c - __ldg(chunk_prefix + w)) * UNPACK_CHUNK;
     const int32_t* base = tbase + __ldg(blk_prefix + w);
 #pragma unroll
     for (int k = 0; k < UNPACK_CHUNK / 256; ++k) {
@@ -51,8 +58,8 @@ __global__ void __launch_bounds__(256) k_unpack(const uint32_t* __restrict__ wor
 }
 
 size_t unpack_workspace_bytes(int B, int64_t total) {
-  const int64_t n_chunks = total / UNPACK_CHUNK + B + 1;
-  return align_up(sizeof(int64_t) * (size_t)(B + 1), 256) * 2 + align_up(sizeof(int32_t) * (size_t)n_chunks, 256) * 2;
+  (void)total;
+  return align_up(3 * sizeof(int64_t) * (size_t)(B + 1), 256);
 }
 
 // win_offsets: HOST, B + 1.  word / dt16 / tbase: DEVICE (the packed payload, already uploaded).  workspace: DEVICE.
@@ -68,14 +75,10 @@ int launch_unpack(const uint32_t* word, const uint16_t* dt16, const int32_t* tba
     set_error("unpack: workspace must be 256-byte aligned and hold %zu bytes", unpack_workspace_bytes(B, total));
     return EVREP_EWORKSPACE;
   }
-  // host tables: offsets, block prefix per window, (window, local chunk) per chunk - one upload
-  const int64_t max_chunks = total / UNPACK_CHUNK + B + 1;
-  const size_t o_bytes = align_up(sizeof(int64_t) * (size_t)(B + 1), 256), c_bytes = align_up(sizeof(int32_t) * (size_t)max_chunks, 256);
-  std::vector<unsigned char> host(2 * o_bytes + 2 * c_bytes, 0);
-  int64_t* offs = reinterpret_cast<int64_t*>(host.data());
-  int64_t* bpre = reinterpret_cast<int64_t*>(host.data() + o_bytes);
-  int32_t* cwin = reinterpret_cast<int32_t*>(host.data() + 2 * o_bytes);
-  int32_t* cloc = reinterpret_cast<int32_t*>(host.data() + 2 * o_bytes + c_bytes);
+  std::vector<int64_t> host(3 * (size_t)(B + 1));
+  int64_t* offs = host.data();
+  int64_t* bpre = offs + (B + 1);
+  int64_t* cpre = bpre + (B + 1);
   int64_t nb = 0, nc = 0;
   const int64_t bs = (int64_t)1 << blk_shift;
   for (int b = 0; b <= B; ++b) offs[b] = win_offsets_host[b];
@@ -86,23 +89,19 @@ int launch_unpack(const uint32_t* word, const uint16_t* dt16, const int32_t* tba
       return EVREP_EINVAL;
     }
     bpre[b] = nb;
+    cpre[b] = nc;
     nb += (n + bs - 1) / bs;
-    for (int64_t l = 0; l * UNPACK_CHUNK < n; ++l) {
-      cwin[nc] = b;
-      cloc[nc] = (int32_t)l;
-      ++nc;
-    }
+    nc += (n + UNPACK_CHUNK - 1) / UNPACK_CHUNK;
   }
   bpre[B] = nb;
-  EVREP_CUDA_OK(cudaMemcpyAsync(workspace, host.data(), host.size(), cudaMemcpyHostToDevice, stream));  // pageable source: staged before the call returns
-  const unsigned char* d = (const unsigned char*)workspace;
+  cpre[B] = nc;
+  EVREP_CUDA_OK(cudaMemcpyAsync(workspace, host.data(), sizeof(int64_t) * host.size(), cudaMemcpyHostToDevice, stream));
+  const int64_t* d = (const int64_t*)workspace;
   const int grid = (int)std::min<int64_t>(nc, 148 * 16);
   if (fmt == 6)
-    k_unpack<true><<<grid, 256, 0, stream>>>(word, dt16, tbase, (const int64_t*)d, (const int64_t*)(d + o_bytes), (const int32_t*)(d + 2 * o_bytes),
-                                             (const int32_t*)(d + 2 * o_bytes + c_bytes), (int)nc, xb, yb, blk_shift, x, y, t, p);
+    k_unpack<true><<<grid, 256, 0, stream>>>(word, dt16, tbase, d, d + (B + 1), d + 2 * (B + 1), B, xb, yb, blk_shift, x, y, t, p);
   else
-    k_unpack<false><<<grid, 256, 0, stream>>>(word, nullptr, tbase, (const int64_t*)d, (const int64_t*)(d + o_bytes), (const int32_t*)(d + 2 * o_bytes),
-                                              (const int32_t*)(d + 2 * o_bytes + c_bytes), (int)nc, xb, yb, blk_shift, x, y, t, p);
+    k_unpack<false><<<grid, 256, 0, stream>>>(word, nullptr, tbase, d, d + (B + 1), d + 2 * (B + 1), B, xb, yb, blk_shift, x, y, t, p);
   EVREP_CUDA_OK(cudaGetLastError());
   return EVREP_OK;
 }

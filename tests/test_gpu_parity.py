@@ -514,3 +514,21 @@ def test_unaligned_event_arrays_take_the_scalar_load_path(E):
     m1, _ = E.filter_events(ev, H, W, "contrast", 2.0)
     m2, _ = E.filter_events(ev2, H, W, "contrast", 2.0)
     assert np.array_equal(np_(m1), np_(m2))
+
+
+def test_graphed_call_replays_the_same_result(E):
+    """batched.GraphedCall: the whole ERGO-12 call (window tables as kernel arguments, no copy) captured into a CUDA graph;
+    replays see new event values in the same buffers"""
+    import torch
+    H, W = 240, 304
+    wins = streams(H, W, [20_000, 20_000, 5_000], 900)
+    ev = E.pack_events(wins, "cuda")
+    out = torch.empty((3, H, W, 12), dtype=torch.float32, device="cuda")
+    want = E.ergo12(ev, H, W).clone()
+    g = E.GraphedCall(lambda: E.ergo12(ev, H, W, out=out))
+    out.zero_()
+    assert torch.equal(g.replay(), want)
+    ev.p.neg_()  # same buffers, same offsets, different events
+    want2 = E.ergo12(ev, H, W).clone()
+    assert not torch.equal(want2, want)
+    assert torch.equal(g.replay(), want2)
