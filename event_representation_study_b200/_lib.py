@@ -40,6 +40,7 @@ SIGNATURES = {
     "evrep_tore_batched": (_i, _EV + [_i] + _TAIL),
     "evrep_order_ops_fused_batched": (_i, _EV + [_d, _vp, _vp] + _TAIL),
     "evrep_voxel_batched": (_i, _EV + [_i, _i, _i, _vp] + _TAIL),
+    "evrep_voxel_subpixel_batched": (_i, _EV + [_i, _i, _i, _vp] + _TAIL),
     "evrep_histogram_batched": (_i, _EV + _TAIL),
     "evrep_gwd_workspace_bytes": (_sz, [_vp, _vp, _i]),
     "evrep_gwd_kernel_l1": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _d, _vp, _vp, _sz, _vp]),
@@ -50,6 +51,7 @@ SIGNATURES = {
     "evrep_filter_background_batched": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _d, _i, _vp, _vp, _vp, _sz, _vp]),
     "evrep_est_workspace_bytes": (_sz, [_i]),
     "evrep_est_quantize_batched": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
+    "evrep_est_backward_batched": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "evrep_assignment_auction": (_i, [_vp, _i, _d, _vp, _vp, _vp]),
     "evrep_unpack_workspace_bytes": (_sz, [_i, _i64]),
     "evrep_unpack_events": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -282,9 +282,13 @@ def order_ops_fused(ev, H, W, tau=50000.0, out=None):
     return es, ts, tr
 
 
-def voxel_grid(ev, H, W, n_bins, flavour="tonic", normalize=True, t0_us=None, t1_us=None, out=None):
-    """flavour 'tonic' -> (B, n_bins, H, W); 'evlicious' -> (B, n_bins, H, W); 'gwd' -> (B, H, W, n_bins)."""
+def voxel_grid(ev, H, W, n_bins, flavour="tonic", normalize=True, t0_us=None, t1_us=None, out=None, divider=1):
+    """flavour 'tonic' -> (B, n_bins, H, W); 'evlicious' -> (B, n_bins, H, W); 'gwd' -> (B, H, W, n_bins).
+    divider > 1 (ev-licious only): ev.x / ev.y hold sub-pixel integers, the event sits at (x / divider, y / divider) and is
+    spread over its four neighbours (utils.py:93-103); H x W is the grid."""
     fl = {"tonic": _lib.VOXEL_TONIC, "evlicious": _lib.VOXEL_EVLICIOUS, "gwd": _lib.VOXEL_GWD}[flavour]
+    if divider != 1 and fl != _lib.VOXEL_EVLICIOUS:
+        raise ValueError("divider applies to the ev-licious flavour only")
     t01 = None
     if (t0_us is not None or t1_us is not None) and fl == _lib.VOXEL_EVLICIOUS:
         if t0_us is None or t1_us is None:
@@ -293,6 +297,10 @@ def voxel_grid(ev, H, W, n_bins, flavour="tonic", normalize=True, t0_us=None, t1
     head, ws, stream = _prep(ev, _lib.OP_VOXEL, H, W, n_bins)
     shape = (ev.B, H, W, n_bins) if fl == _lib.VOXEL_GWD else (ev.B, n_bins, H, W)
     out = _out(ev, shape, out)
+    if divider != 1:
+        check(lib.evrep_voxel_subpixel_batched(*head, int(divider), int(n_bins), int(bool(normalize)), None if t01 is None else t01.ctypes.data,
+                                               out.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+        return out
     check(lib.evrep_voxel_batched(*head, fl, int(n_bins), int(bool(normalize)), None if t01 is None else t01.ctypes.data,
                                   out.data_ptr(), ws.data_ptr(), ws.numel(), stream))
     return out

@@ -68,6 +68,9 @@ size_t est_workspace_bytes(int B);
 int launch_est(const uint16_t* x, const uint16_t* y, const float* t, const int8_t* p, const int64_t* win_offsets_host, int B, int H, int W, int C,
                const double* breaks, const double* slope, const double* icpt, int K, float* out, void* workspace, size_t workspace_bytes,
                cudaStream_t stream);
+int launch_est_backward(const uint16_t* x, const uint16_t* y, const float* t, const int8_t* p, const int64_t* win_offsets_host, int B, int H, int W,
+                        int C, const double* breaks, int K, const float* grad_out, double* seg_sums, void* workspace, size_t workspace_bytes,
+                        cudaStream_t stream);
 int launch_auction(const float* cost, int n, double eps_rel, int* sigma, int* stats, cudaStream_t stream);
 int transport_plan_host(const float* cost, int n, int m, int cap, int* row_ptr, int* col, double* weight, int* nnz_out);
 size_t unpack_workspace_bytes(int B, int64_t total);
@@ -367,15 +370,15 @@ int evrep_order_ops_fused_batched(const uint16_t* x, const uint16_t* y, const vo
   EVREP_GUARD_END
 }
 
-int evrep_voxel_batched(const uint16_t* x, const uint16_t* y, const void* t, int t_bytes, const int8_t* p, const int64_t* win_offsets,
-                        int B, int H, int W, int flavour, int n_bins, int normalize, const int64_t* t0_t1_us, float* out,
-                        void* workspace, size_t workspace_bytes, evrep_stream_t stream) {
-  EVREP_GUARD_BEGIN
+static int voxel_common(const uint16_t* x, const uint16_t* y, const void* t, int t_bytes, const int8_t* p, const int64_t* win_offsets, int B, int H,
+                        int W, int flavour, int n_bins, int normalize, const int64_t* t0_t1_us, int divider, float* out, void* workspace,
+                        size_t workspace_bytes, evrep_stream_t stream) {
   Events ev;
   int64_t total = 0, n_max = 0;
   EVREP_TRY(check_events(x, y, t, t_bytes, p, win_offsets, B, out, &ev, &total, &n_max));
   if (flavour < EVREP_VOXEL_TONIC || flavour > EVREP_VOXEL_GWD) { set_error("unknown voxel flavour %d", flavour); return EVREP_EINVAL; }
   if (n_bins < 1 || n_bins > 1024) { set_error("n_bins outside 1..1024"); return EVREP_EINVAL; }
+  if (divider < 1 || divider > 65535) { set_error("divider outside 1..65535"); return EVREP_EINVAL; }
   if (B == 0) return EVREP_OK;
   Geom g;
   memset(&g, 0, sizeof(g));
@@ -385,7 +388,23 @@ int evrep_voxel_batched(const uint16_t* x, const uint16_t* y, const void* t, int
   Workspace ws;
   g.Tb = 0;  // direct scatter: no buckets
   EVREP_TRY(carve_checked(workspace, workspace_bytes, B, 0, 1, &ws));
-  return launch_voxel(ev, win_offsets, g, ws, flavour, n_bins, normalize, t0_t1_us, out, (cudaStream_t)stream);
+  return launch_voxel(ev, win_offsets, g, ws, flavour, n_bins, normalize, t0_t1_us, divider, out, (cudaStream_t)stream);
+}
+
+int evrep_voxel_batched(const uint16_t* x, const uint16_t* y, const void* t, int t_bytes, const int8_t* p, const int64_t* win_offsets,
+                        int B, int H, int W, int flavour, int n_bins, int normalize, const int64_t* t0_t1_us, float* out,
+                        void* workspace, size_t workspace_bytes, evrep_stream_t stream) {
+  EVREP_GUARD_BEGIN
+  return voxel_common(x, y, t, t_bytes, p, win_offsets, B, H, W, flavour, n_bins, normalize, t0_t1_us, 1, out, workspace, workspace_bytes, stream);
+  EVREP_GUARD_END
+}
+
+int evrep_voxel_subpixel_batched(const uint16_t* x, const uint16_t* y, const void* t, int t_bytes, const int8_t* p, const int64_t* win_offsets,
+                                 int B, int H, int W, int divider, int n_bins, int normalize, const int64_t* t0_t1_us, float* out,
+                                 void* workspace, size_t workspace_bytes, evrep_stream_t stream) {
+  EVREP_GUARD_BEGIN
+  return voxel_common(x, y, t, t_bytes, p, win_offsets, B, H, W, EVREP_VOXEL_EVLICIOUS, n_bins, normalize, t0_t1_us, divider, out, workspace,
+                      workspace_bytes, stream);
   EVREP_GUARD_END
 }
 
@@ -559,6 +578,21 @@ int evrep_est_quantize_batched(const uint16_t* x, const uint16_t* y, const float
   if (B == 0) return EVREP_OK;
   if (!out || (win_offsets[B] > 0 && (!x || !y || !t || !p))) { set_error("null array"); return EVREP_EINVAL; }
   return launch_est(x, y, t, p, win_offsets, B, H, W, C, breaks, slope, icpt, K, out, workspace, workspace_bytes, (cudaStream_t)stream);
+  EVREP_GUARD_END
+}
+
+int evrep_est_backward_batched(const uint16_t* x, const uint16_t* y, const float* t, const int8_t* p, const int64_t* win_offsets, int B, int H,
+                               int W, int C, const double* breaks, int K, const float* grad_out, double* seg_sums, void* workspace,
+                               size_t workspace_bytes, evrep_stream_t stream) {
+  EVREP_GUARD_BEGIN
+  if (B < 0 || !win_offsets) { set_error("B must be >= 0 and win_offsets non-null"); return EVREP_EINVAL; }
+  if (B > 65535) { set_error("at most 65535 windows per call"); return EVREP_EUNSUPPORTED; }
+  if (H < 1 || W < 1 || H > 65535 || W > 65535) { set_error("sensor size %d x %d unsupported", W, H); return EVREP_EINVAL; }
+  if (C < 2 || C > 64) { set_error("EST needs 2 <= C <= 64 temporal bins"); return EVREP_EINVAL; }
+  if (K < 0 || (K > 0 && !breaks) || !seg_sums) { set_error("bad piecewise-linear table / null seg_sums"); return EVREP_EINVAL; }
+  if (B == 0) return EVREP_OK;
+  if (!grad_out || (win_offsets[B] > 0 && (!x || !y || !t || !p))) { set_error("null array"); return EVREP_EINVAL; }
+  return launch_est_backward(x, y, t, p, win_offsets, B, H, W, C, breaks, K, grad_out, seg_sums, workspace, workspace_bytes, (cudaStream_t)stream);
   EVREP_GUARD_END
 }
 

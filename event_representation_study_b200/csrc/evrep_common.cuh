@@ -208,7 +208,7 @@ int launch_ba_expand(const Events& ev, int64_t total, int H, int W, int radius, 
 int launch_ba_collect(const unsigned char* mask_e, int64_t total, int K, unsigned char* mask, cudaStream_t stream);
 
 int launch_voxel(const Events& ev, const int64_t* win_offsets_host, const Geom& g, const Workspace& ws, int flavour,
-                 int n_bins, int normalize, const int64_t* t0_t1_host, float* out, cudaStream_t stream);
+                 int n_bins, int normalize, const int64_t* t0_t1_host, int divider, float* out, cudaStream_t stream);
 int launch_histogram(const Events& ev, const int64_t* win_offsets_host, const Geom& g, const Workspace& ws, float* out,
                      cudaStream_t stream);
 

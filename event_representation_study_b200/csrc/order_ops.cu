@@ -110,16 +110,19 @@ __global__ void __launch_bounds__(TILE_THREADS) k_event_stack_tile_k(const uint2
     float o[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) o[k] = (v && idx >= start[k]) ? sgn : 0.f;
+    // a warp repacks its own 32 pixels ([pixel][K] -> consecutive float4) in its own slice of the staging area: no CTA barrier
+    float4* wst = stage + (tid & ~31) * (K / 4);
+    const int lane = tid & 31;
 #pragma unroll
-    for (int q = 0; q < K / 4; ++q) stage[tid * (K / 4) + q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-    __syncthreads();
-    const int n4 = min(TILE_THREADS, npix - p0) * (K / 4);
+    for (int q = 0; q < K / 4; ++q) wst[lane * (K / 4) + q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+    __syncwarp();
+    const int n4 = min(32, npix - p0 - (tid & ~31)) * (K / 4);  // may be <= 0 in the last tile of the image
 #pragma unroll
     for (int q = 0; q < K / 4; ++q) {
-      const int e = q * TILE_THREADS + tid;
-      if (e < n4) __stcs(dst4 + (size_t)p0 * (K / 4) + e, stage[e]);
+      const int e = q * 32 + lane;
+      if (e < n4) __stcs(dst4 + (size_t)(p0 + (tid & ~31)) * (K / 4) + e, wst[e]);
     }
-    __syncthreads();
+    __syncwarp();
   }
 }
 
@@ -258,19 +261,39 @@ __global__ void __launch_bounds__(TILE_THREADS) k_time_surface_tile_s(const uint
     empty[k] = k < nvalid ? s_empty[k] : 0.f;
   }
   const size_t plane_stride = (size_t)g.HW, snap_stride = 2 * (size_t)g.HW;
+  // (mem - t_snapshot) / tau with mem = key - 1 + tmin, t_snapshot = trel - 1 + tmin: the difference d of the keys, and
+  // exp(d / tau) = 2^(d log2(e) / tau).  Keys lie in [1, t_max - t_min + 1]: for windows shorter than 2^24 us (16.7 s) d is
+  // exact in float32 and the product with the constant, split into a float32 head and tail, carries one rounding
+  // (<= 6e-8 |argument|, i.e. 3e-6 relative in the result at |argument| = 80 where the result is 1e-24); ex2.approx is good
+  // to 2^-22.  No conversion or double-precision instruction per output: the int -> double -> float path kept the XU pipe
+  // 51 % busy and the kernel at 23 instructions per output (ncu, profiles/README.md).  Longer windows take that path.
+  const uint32_t delta_u = (w.tmax_rel >= w.tmin_rel) ? (uint32_t)(w.tmax_rel - w.tmin_rel) : 0u;
+  const bool small = delta_u < (1u << 24) - 1u;  // CTA-uniform
+  const float c_hi = (float)inv_tau_log2e, c_lo = (float)(inv_tau_log2e - (double)c_hi);
   for (int plane = 0; plane < 2; ++plane) {
     float* dst = out + ((size_t)b * S * 2 + plane) * plane_stride + pix0;
-    for (int pix = tid; pix < npix; pix += TILE_THREADS) {
-      uint32_t m = 0;
+    if (small) {
+      for (int pix = tid; pix < npix; pix += TILE_THREADS) {
+        uint32_t m = 0;
 #pragma unroll
-      for (int k = 0; k < S; ++k) {
-        m = max(m, acc[(k * 2 + plane) * TP + pix]);
-        float o = empty[k];
-        // (mem - t_snapshot) / tau with mem = key - 1 + tmin, t_snapshot = trel - 1 + tmin: the difference of the keys
-        // exp(d / tau) = 2^(d log2(e) / tau): the product in double, one rounding to float (|argument| < 150: 5e-6
-        // relative at the underflow edge, 1e-6 for values above 1e-9 - the same as rounding d / tau for expf), then ex2
-        if (m && k < nvalid) o = exp2f((float)((double)((int32_t)m - trel[k]) * inv_tau_log2e));
-        __stcs(dst + k * snap_stride + pix, o);
+        for (int k = 0; k < S; ++k) {
+          m = max(m, acc[(k * 2 + plane) * TP + pix]);
+          const float df = (float)((int32_t)m - trel[k]);
+          float e;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(df, c_lo, df * c_hi)));
+          __stcs(dst + k * snap_stride + pix, (m && k < nvalid) ? e : empty[k]);
+        }
+      }
+    } else {
+      for (int pix = tid; pix < npix; pix += TILE_THREADS) {
+        uint32_t m = 0;
+#pragma unroll
+        for (int k = 0; k < S; ++k) {
+          m = max(m, acc[(k * 2 + plane) * TP + pix]);
+          float o = empty[k];
+          if (m && k < nvalid) o = exp2f((float)((double)((int32_t)m - trel[k]) * inv_tau_log2e));
+          __stcs(dst + k * snap_stride + pix, o);
+        }
       }
     }
   }
@@ -416,16 +439,19 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tore_tile_k(const uint2* __res
         }
       }
     }
+    // a warp repacks its own 32 pixels in its own slice of the staging area: no CTA barrier
+    float4* wst = stage + (tid & ~31) * (C / 4);
+    const int lane = tid & 31;
 #pragma unroll
-    for (int q = 0; q < C / 4; ++q) stage[tid * (C / 4) + q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-    __syncthreads();
-    const int n4 = min(TILE_THREADS, npix - p0) * (C / 4);
+    for (int q = 0; q < C / 4; ++q) wst[lane * (C / 4) + q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+    __syncwarp();
+    const int n4 = min(32, npix - p0 - (tid & ~31)) * (C / 4);  // may be <= 0 in the last tile of the image
 #pragma unroll
     for (int q = 0; q < C / 4; ++q) {
-      const int e = q * TILE_THREADS + tid;
-      if (e < n4) __stcs(dst4 + (size_t)p0 * (C / 4) + e, stage[e]);
+      const int e = q * 32 + lane;
+      if (e < n4) __stcs(dst4 + (size_t)(p0 + (tid & ~31)) * (C / 4) + e, wst[e]);
     }
-    __syncthreads();
+    __syncwarp();
   }
 }
 

@@ -14,6 +14,7 @@ namespace evrep {
 struct VoxelArgs {
   int flavour, n_bins, has_t0t1;
   int64_t t0, t1;
+  int divider;  // ev-licious only: > 1 = x, y are sub-pixel integers, the event sits at (x / divider, y / divider)
 };
 
 template <typename TT>
@@ -31,10 +32,34 @@ __global__ void __launch_bounds__(256) k_voxel(const uint16_t* __restrict__ x, c
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < w.n; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t ai = w.start + i;
     const uint32_t xv = x[ai], yv = y[ai];
-    if (xv >= (uint32_t)g.W || yv >= (uint32_t)g.H) { flags |= EVREP_WF_OUT_OF_RANGE; continue; }
     const int64_t tv = (int64_t)t[ai];
     int pv = p[ai];
     if (pv > 1 || pv < -1) { flags |= EVREP_WF_BAD_POLARITY; pv = pv > 0 ? 1 : -1; }
+    if (a.flavour == EVREP_VOXEL_EVLICIOUS && a.divider > 1) {
+      // Events.x = _x.astype(float32) / divider (events.py:37-47); _draw_xy_to_voxel_grid (utils.py:93-103): the four pixels
+      // around (x, y) with weights (1 - |xlim - x|)(1 - |ylim - y|) in float64 (int32 - float32 promotes), taps outside the
+      // grid dropped (:105-108); in time the floor bin gets p and the next bin weight 0 (the quirk of :74)
+      const float xf = __fdiv_rn((float)xv, (float)a.divider), yf = __fdiv_rn((float)yv, (float)a.divider);
+      if (xf > (float)(g.W - 1) || yf > (float)(g.H - 1)) { flags |= EVREP_WF_OUT_OF_RANGE; continue; }  // Events asserts max(x) <= width - 1
+      const int64_t t0 = a.has_t0t1 ? a.t0 : t_first, t1 = a.has_t0t1 ? a.t1 : t_last;
+      const double dT = (t1 - t0) == 0 ? 1.0 : (double)(t1 - t0);
+      const double tn = (double)((int64_t)(nb - 1) * (tv - t0)) / dT;
+      const int ti = (int)fmax(fmin(tn, 2.0e9), -2.0e9);
+      if (ti < 0 || ti >= nb) continue;
+      const double pol = pv == 0 ? -1.0 : (double)pv;
+      const int xi = (int)xf, yi = (int)yf;
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx)
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+          const int xl = xi + dx, yl = yi + dy;
+          if (xl >= g.W || yl >= g.H) continue;
+          const double wgt = (1.0 - fabs((double)xl - (double)xf)) * (1.0 - fabs((double)yl - (double)yf));
+          atomicAdd(grid + (size_t)ti * g.HW + (size_t)yl * g.W + xl, (float)(wgt * pol));
+        }
+      continue;
+    }
+    if (xv >= (uint32_t)g.W || yv >= (uint32_t)g.H) { flags |= EVREP_WF_OUT_OF_RANGE; continue; }
     const uint32_t lin = yv * (uint32_t)g.W + xv;
     if (a.flavour == EVREP_VOXEL_TONIC) {
       // ts = n_bins * (t - t[0]) / (t[-1] - t[0]); value p*(1-dt) into bin int(ts), p*dt into the next
@@ -106,7 +131,7 @@ __global__ void __launch_bounds__(256) k_voxel_norm(float* __restrict__ out, siz
 }
 
 int launch_voxel(const Events& ev, const int64_t* win_offsets_host, const Geom& g, const Workspace& ws, int flavour, int n_bins,
-                 int normalize, const int64_t* t0_t1_host, float* out, cudaStream_t stream) {
+                 int normalize, const int64_t* t0_t1_host, int divider, float* out, cudaStream_t stream) {
   int n_chunks = 0;
   int rc = prepare_windows(ev, win_offsets_host, g, ws, &n_chunks, stream);
   if (rc) return rc;
@@ -118,6 +143,7 @@ int launch_voxel(const Events& ev, const int64_t* win_offsets_host, const Geom& 
   a.has_t0t1 = t0_t1_host != nullptr;
   a.t0 = t0_t1_host ? t0_t1_host[0] : 0;
   a.t1 = t0_t1_host ? t0_t1_host[1] : 0;
+  a.divider = divider;
   int64_t n_max = 0;
   for (int b = 0; b < g.B; ++b) n_max = std::max<int64_t>(n_max, win_offsets_host[b + 1] - win_offsets_host[b]);
   if (n_max > 0) {

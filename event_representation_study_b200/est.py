@@ -1,4 +1,4 @@
-"""EST (learned Event Spike Tensor quantisation layer), inference path.
+"""EST (learned Event Spike Tensor quantisation layer): forward and backward with respect to the ValueLayer weights.
 
 Reference: ev-YOLOv6/yolov6/models/learned_repr.py - ValueLayer (:9-77, an MLP 1 -> 100 -> 100 -> 1 with LeakyReLU(0.1)
 applied to ONE scalar per event and bin) and QuantizationLayer.forward (:143-179).
@@ -7,7 +7,13 @@ A LeakyReLU network with a scalar input is a piecewise-linear function of that s
 weights into that function exactly (float64 breakpoints, slope and intercept per segment): hidden layer by hidden layer,
 every segment on which the current activations are affine is cut where a pre-activation changes sign.  The CUDA kernel
 (csrc/est.cu) then evaluates the layer with a binary search and one FMA per (event, bin) instead of 2 x 10^4 MACs.
-Forward only: gradients with respect to the weights are not available (training the layer stays with the reference).
+
+Training: inside segment j the layer is f(u) = a_j u + c_j with a_j, c_j smooth functions of the weights, so
+dL/dtheta = sum_j (G1_j da_j/dtheta + G0_j dc_j/dtheta), where G0_j / G1_j are the sums of g and g u over the (event, bin)
+samples of the segment (g = upstream gradient times t).  `evrep_est_backward_batched` reduces the upstream gradient to those
+2 (K + 1) numbers in one pass over the events; `EstQuantize.backward` then evaluates the torch MLP at two points per segment
+with coefficients that reproduce (G0, G1) and lets autograd produce the parameter gradients - exactly the gradient the
+reference gets from back-propagating through C MLP evaluations per event (learned_repr.py:164-172).
 """
 import numpy as np
 import torch
@@ -70,6 +76,76 @@ def quantize(ev, H, W, C, tables, t_float=None):
                                          breaks.data_ptr(), slope.data_ptr(), icpt.data_ptr(), int(breaks.numel()), out.data_ptr(),
                                          ws.data_ptr(), ws.numel(), stream))
     return out
+
+
+def _mlp_double(params, u, negative_slope):
+    """ValueLayer.forward (learned_repr.py:32-43) in float64 on a vector of scalars; params = [w0, b0, w1, b1, ...]"""
+    h = u.reshape(-1, 1)
+    n_layers = len(params) // 2
+    for l in range(n_layers):
+        h = torch.nn.functional.linear(h, params[2 * l].double(), params[2 * l + 1].double())
+        if l + 1 < n_layers:
+            h = torch.nn.functional.leaky_relu(h, negative_slope)
+    return h.reshape(-1)
+
+
+class EstQuantize(torch.autograd.Function):
+    """out = quantize(events; value-layer weights), differentiable with respect to the weights.
+    apply(ev, H, W, C, negative_slope, t_float, *params) with params = [w0, b0, w1, b1, ...] (the nn.Linear weights and biases
+    of ValueLayer.mlp, any device) -> (B, H, W, 2C) float32 CUDA tensor."""
+
+    @staticmethod
+    def forward(ctx, ev, H, W, C, negative_slope, t_float, *params):
+        ws = [p.detach().cpu().double().numpy() for p in params[0::2]]
+        bs = [p.detach().cpu().double().numpy() for p in params[1::2]]
+        br, sl, ic = compile_value_layer(ws, bs, negative_slope)
+        dev = ev.x.device
+        tables = tuple(torch.as_tensor(v, dtype=torch.float64, device=dev).contiguous() for v in (br, sl, ic))
+        t = ev.t.float() if t_float is None else t_float.float().contiguous()
+        out = quantize(ev, H, W, C, tables, t_float=t)
+        ctx.ev, ctx.geom, ctx.tables, ctx.t, ctx.slope = ev, (H, W, C), tables, t, negative_slope
+        ctx.save_for_backward(*params)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        ev, (H, W, C), (breaks, _, _), t = ctx.ev, ctx.geom, ctx.tables, ctx.t
+        params = ctx.saved_tensors
+        dev = ev.x.device
+        K = int(breaks.numel())
+        seg = torch.empty(2 * (K + 1), dtype=torch.float64, device=dev)
+        g = grad_out.contiguous().float()
+        B = len(ev.offsets) - 1
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        ws = eb._workspace(dev, stream, lib.evrep_est_workspace_bytes(B))
+        offs = np.ascontiguousarray(ev.offsets, np.int64)
+        check(lib.evrep_est_backward_batched(ev.x.data_ptr(), ev.y.data_ptr(), t.data_ptr(), ev.p.data_ptr(), offs.ctypes.data, B, H, W, C,
+                                             breaks.data_ptr(), K, g.data_ptr(), seg.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+        G0, G1 = seg[:K + 1], seg[K + 1:]
+        # two points strictly inside every segment (the outermost segments are half lines)
+        if K:
+            lo = torch.cat([breaks[:1] - 2.0, breaks])
+            hi = torch.cat([breaks, breaks[-1:] + 2.0])
+        else:
+            lo, hi = torch.tensor([-2.0], dtype=torch.float64, device=dev), torch.tensor([2.0], dtype=torch.float64, device=dev)
+        u1, u2 = lo + (hi - lo) / 3.0, lo + 2.0 * (hi - lo) / 3.0
+        beta = (G1 - G0 * u1) / (u2 - u1)
+        alpha = G0 - beta
+        with torch.enable_grad():
+            ps = [p.detach().to(dev).requires_grad_(True) for p in params]
+            f1, f2 = _mlp_double(ps, u1, ctx.slope), _mlp_double(ps, u2, ctx.slope)
+            surrogate = (alpha * f1 + beta * f2).sum()  # = sum_j (G1_j a_j + G0_j c_j) as a function of the weights
+            grads = torch.autograd.grad(surrogate, ps, allow_unused=True)
+        out = [None if gr is None else gr.to(device=p.device, dtype=p.dtype) for gr, p in zip(grads, params)]
+        return (None, None, None, None, None, None, *out)
+
+
+def quantize_trainable(ev, H, W, C, value_layer, negative_slope=0.1, t_float=None):
+    """Differentiable `quantize`: gradients flow to `value_layer.mlp`'s weights and biases (a torch ValueLayer-like module)."""
+    params = []
+    for m in value_layer.mlp:
+        params += [m.weight, m.bias]
+    return EstQuantize.apply(ev, H, W, C, float(negative_slope), t_float, *params)
 
 
 def forward(ev, H, W, C, tables, image_size=640, t_float=None):

@@ -4,7 +4,8 @@ Both run the same deterministic GPU kernel.  The reference's numpy version passe
 (`_bil_w(t_norm_int, tlim)`, :74), so it is a floor-bin polarity histogram; that quirk is kept.  The reference's torch
 version scatters with `put_` WITHOUT accumulation (:38, last writer wins, nondeterministic) - a bug we do not reproduce:
 `events_to_voxel_grid_cuda` returns the accumulate semantics of the numpy version, as a torch tensor on `device`.
-Only integer pixel coordinates (divider == 1) are supported on the GPU."""
+Sub-pixel events (`Events.divider > 1`: float32 coordinates, 4-tap bilinear scatter, utils.py:93-103) go through
+evrep_voxel_subpixel_batched on the raw integer coordinates."""
 import numpy as np
 import torch
 
@@ -13,15 +14,17 @@ from ..._single import one_window
 
 
 def _grid(events, num_bins, normalize, t0_us, t1_us):
-    if events.divider > 1:
-        raise NotImplementedError("sub-pixel coordinates (divider > 1) are not supported by the GPU voxel grid")
     H, W = events.height, events.width
-    ev = one_window(events.x, events.y, events.t, events.p, H, W)
+    div = int(events.divider)
+    if div > 1:  # raw sub-pixel integers; one_window checks them against the unscaled extent
+        ev = one_window(events._x, events._y, events.t, events.p, (H - 1) * div + 1, (W - 1) * div + 1)
+    else:
+        ev = one_window(events.x, events.y, events.t, events.p, H, W)
     if len(events) < 2:
         return torch.zeros((num_bins, H, W), dtype=torch.float32, device=ev.device)
     t0 = int(t0_us) if t0_us is not None else int(events.t[0])
     t1 = int(t1_us) if t1_us is not None else int(events.t[-1])
-    return eb.voxel_grid(ev, H, W, num_bins, "evlicious", normalize=normalize, t0_us=t0, t1_us=t1)[0]
+    return eb.voxel_grid(ev, H, W, num_bins, "evlicious", normalize=normalize, t0_us=t0, t1_us=t1, divider=max(div, 1))[0]
 
 
 def events_to_voxel_grid(events, num_bins, normalize=True, t0_us=None, t1_us=None):

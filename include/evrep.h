@@ -35,7 +35,8 @@
  *                                _contrast_threshold_control, _refractory_period) as used by tools/filters.py:57-109
  *   evrep_filter_background_batched  ev-licious/src/evlicious/tools/utils.py:169-178 (_background_activity_filter) as used by
  *                                tools/filters.py:57-69 (BackgroundActivity.insert)
- *   evrep_est_quantize_batched   ev-YOLOv6/yolov6/models/learned_repr.py:143-172 (QuantizationLayer.forward, inference only)
+ *   evrep_est_quantize_batched   ev-YOLOv6/yolov6/models/learned_repr.py:143-172 (QuantizationLayer.forward);
+ *   evrep_est_backward_batched   its backward pass with respect to the ValueLayer weights (:9-77 under autograd)
  *   evrep_image_pipeline_batched ev-YOLOv6/yolov6/data/gen1_2yolo.py:230-265,321-341,397 (resize_image, letterbox, CHW + reversal),
  *                                gen4/precompute_reps.py:216-251 (resize_image_process), yolov6/core/engine.py:629-635 (/ 255)
  */
@@ -181,6 +182,16 @@ int evrep_voxel_batched(const uint16_t* x, const uint16_t* y, const void* t, int
                         const int64_t* t0_t1_us, float* out, void* workspace, size_t workspace_bytes,
                         evrep_stream_t stream);
 
+/* The ev-licious voxel grid for events with SUB-PIXEL coordinates (Events.divider > 1, events.py:37-47: the event sits at
+ * (x / divider, y / divider) in float32; utils.py:70-76, 93-103): x, y hold the raw integers, H x W is the grid (the scaled
+ * sensor), every event is spread over the four pixels around it with bilinear weights, taps outside the grid are dropped;
+ * time binning, normalize and t0_t1_us as in the ev-licious flavour of evrep_voxel_batched.  out: (B, n_bins, H, W).
+ * Float reductions: reproducible to the last ulp, not bit for bit. */
+int evrep_voxel_subpixel_batched(const uint16_t* x, const uint16_t* y, const void* t, int t_bytes, const int8_t* p,
+                                 const int64_t* win_offsets, int B, int H, int W, int divider, int n_bins, int normalize,
+                                 const int64_t* t0_t1_us, float* out, void* workspace, size_t workspace_bytes,
+                                 evrep_stream_t stream);
+
 /* out: (B, 2, H, W) float32 event counts, plane 0 = p <= 0, plane 1 = p > 0. */
 int evrep_histogram_batched(const uint16_t* x, const uint16_t* y, const void* t, int t_bytes, const int8_t* p,
                             const int64_t* win_offsets, int B, int H, int W, float* out, void* workspace,
@@ -304,7 +315,7 @@ int evrep_filter_background_batched(const uint16_t* x, const uint16_t* y, const 
                                     int H, int W, double depth_us, int radius, double* state, unsigned char* mask, void* workspace,
                                     size_t workspace_bytes, evrep_stream_t stream);
 
-/* EST, the reference's learned quantisation layer, forward only (ev-YOLOv6/yolov6/models/learned_repr.py:143-172):
+/* EST, the reference's learned quantisation layer, forward pass (ev-YOLOv6/yolov6/models/learned_repr.py:143-172):
  * out[b, y, x, p * C + i] = sum over the events of window b at (x, y, p) of tn * f(tn - i / (C - 1)), tn = t / max(t of the
  * window) in float32, f = the ValueLayer MLP given as the piecewise-linear function it is: `breaks` (K sorted float64
  * breakpoints), `slope` and `icpt` (K + 1 float64 each; segment j covers breaks[j-1] <= u < breaks[j]) - compile them from
@@ -315,6 +326,15 @@ int evrep_filter_background_batched(const uint16_t* x, const uint16_t* y, const 
 size_t evrep_est_workspace_bytes(int B);
 int evrep_est_quantize_batched(const uint16_t* x, const uint16_t* y, const float* t, const int8_t* p, const int64_t* win_offsets, int B,
                                int H, int W, int C, const double* breaks, const double* slope, const double* icpt, int K, float* out,
+                               void* workspace, size_t workspace_bytes, evrep_stream_t stream);
+
+/* Backward pass of the EST layer with respect to the ValueLayer weights (training: learned_repr.py:9-77, 143-172 under
+ * autograd).  Inside segment j the layer is f(u) = a_j u + c_j, so dL/dtheta = sum_j (G1_j da_j/dtheta + G0_j dc_j/dtheta)
+ * with G0_j = sum g, G1_j = sum g u over the (event, bin) samples of segment j and g = grad_out[b, y, x, p C + i] * tn.
+ * seg_sums (DEVICE float64, 2 (K + 1) entries: G0 then G1) is overwritten; est.py::EstQuantize turns it into parameter
+ * gradients.  Same events, tables and workspace as the forward call; grad_out: DEVICE float32 (B, H, W, 2C). */
+int evrep_est_backward_batched(const uint16_t* x, const uint16_t* y, const float* t, const int8_t* p, const int64_t* win_offsets, int B,
+                               int H, int W, int C, const double* breaks, int K, const float* grad_out, double* seg_sums,
                                void* workspace, size_t workspace_bytes, evrep_stream_t stream);
 
 #ifdef __cplusplus

@@ -323,9 +323,10 @@ def voxel_tonic(x, y, t, p, H, W, n_bins):
     return grid.reshape(n_bins, H, W)
 
 
-def voxel_evlicious(x, y, t, p, H, W, num_bins, normalize=True, t0_us=None, t1_us=None):
-    """evlicious.tools.events_to_voxel_grid, integer-coordinate (uint16, divider == 1) branch
-    (ev-licious/src/evlicious/tools/utils.py:51-85, 105-108) -> float32 (num_bins, H, W).
+def voxel_evlicious(x, y, t, p, H, W, num_bins, normalize=True, t0_us=None, t1_us=None, divider=1):
+    """evlicious.tools.events_to_voxel_grid (ev-licious/src/evlicious/tools/utils.py:51-85) -> float32 (num_bins, H, W):
+    the integer-coordinate branch (uint16 x, y, divider == 1, :105-108) and, with divider > 1, the sub-pixel branch
+    (Events.x = _x.astype(float32) / divider, events.py:37-47; 4-tap bilinear scatter, utils.py:93-103).
     Keeps the reference's weight quirk: _bil_w is fed t_norm_int, so the floor bin gets weight p and
     the next bin gets weight 0 (:74)."""
     grid = np.zeros((num_bins, H, W), np.float32)
@@ -340,13 +341,26 @@ def voxel_evlicious(x, y, t, p, H, W, num_bins, normalize=True, t0_us=None, t1_u
     t_norm = (num_bins - 1) * (t - t0) / dT
     ti = t_norm.astype("int32")
     pp = np.asarray(p).astype(np.int8)
-    xx = np.asarray(x).astype(np.int64)
-    yy = np.asarray(y).astype(np.int64)
-    for tl in [ti, ti + 1]:
-        m = (tl >= 0) & (tl < num_bins)
-        w = (1 - np.abs(tl - ti)) * pp
-        mm = m & (xx >= 0) & (yy >= 0) & (xx < W) & (yy < H)
-        np.add.at(grid, (tl[mm], yy[mm], xx[mm]), w[mm])
+    if divider > 1:
+        xf = np.asarray(x).astype("float32") / divider
+        yf = np.asarray(y).astype("float32") / divider
+        xi, yi = xf.astype("int32"), yf.astype("int32")
+        for tl in [ti, ti + 1]:
+            m = (tl >= 0) & (tl < num_bins)
+            val = ((1 - np.abs(tl - ti)) * pp)[m]
+            for xl in [xi[m], xi[m] + 1]:
+                for yl in [yi[m], yi[m] + 1]:
+                    w = (1 - np.abs(xl - xf[m])) * (1 - np.abs(yl - yf[m])) * val
+                    mm = (xl >= 0) & (yl >= 0) & (xl < W) & (yl < H)
+                    np.add.at(grid, (tl[m][mm], yl[mm], xl[mm]), w[mm])
+    else:
+        xx = np.asarray(x).astype(np.int64)
+        yy = np.asarray(y).astype(np.int64)
+        for tl in [ti, ti + 1]:
+            m = (tl >= 0) & (tl < num_bins)
+            w = (1 - np.abs(tl - ti)) * pp
+            mm = m & (xx >= 0) & (yy >= 0) & (xx < W) & (yy < H)
+            np.add.at(grid, (tl[mm], yy[mm], xx[mm]), w[mm])
     if normalize:
         nz = np.nonzero(grid)
         if nz[0].size > 0:

@@ -256,3 +256,19 @@ def test_tonic_compat_shapes():
     assert out.shape == g["out"].shape and out.dtype == np.float64
     assert_close(out, g["out"], rtol=RTOL, atol=2e-6)
     assert "ToVoxelGrid" in str(tt.ToVoxelGrid) and "ToImage" in str(tt.ToImage)
+
+
+@pytest.mark.parametrize("name,path", golden("voxel_subpixel_*"), ids=[n for n, _ in golden("voxel_subpixel_*")])
+def test_events_to_voxel_grid_subpixel(name, path):
+    """ev-licious Events with divider > 1 (float32 sub-pixel coordinates): the 4-tap bilinear scatter of
+    evlicious/tools/utils.py:93-103 against fixtures made by the reference's own events_to_voxel_grid.  float32 sums of
+    signed bilinear weights: 1e-5 relative + 2e-6 absolute per accumulated event weight."""
+    from event_representation_study_b200.evlicious.io.utils.events import Events
+    from event_representation_study_b200.evlicious.tools.utils import events_to_voxel_grid, events_to_voxel_grid_cuda
+    g = load(path)
+    E = Events(g["x"].copy(), g["y"].copy(), g["t"].copy(), g["p"].copy(), int(g["W"]), int(g["H"]), divider=int(g["divider"]))
+    out = events_to_voxel_grid(E, int(g["bins"]), normalize=bool(g["normalize"]))
+    assert out.dtype == np.float32 and out.shape == g["out"].shape
+    assert_close(out, g["out"], rtol=RTOL, atol=2e-5, what=name)
+    out_t = events_to_voxel_grid_cuda(E, int(g["bins"]), normalize=bool(g["normalize"]))
+    assert_close(out_t.cpu().numpy(), g["out"], rtol=RTOL, atol=2e-5, what=name + " (cuda entry point)")

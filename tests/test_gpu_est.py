@@ -95,3 +95,53 @@ def test_est_batch_with_an_empty_window(M):
     # window 0: tn = 0.5 and 1.0; every bin adds tn * 2 at (y = 1, x = 3), polarity 1 -> channels 2, 3; polarity 0 -> channels 0, 1
     assert out[0, 1, 3].cpu().numpy().tolist() == [2.0, 2.0, 1.0, 1.0]
     assert float(out[0].sum()) == 6.0
+
+
+def test_est_backward_matches_autograd_through_the_reference_forward(M):
+    """training the layer (learned_repr.py:9-77 under autograd): gradients of a random linear functional of the quantised
+    tensor with respect to every ValueLayer weight, from evrep_est_backward_batched + the segment surrogate, against
+    torch autograd through the reference's forward restated in float64 (C MLP evaluations per event, put_ accumulate)"""
+    import torch
+    eb, est = M
+    torch.manual_seed(0)
+    rng = np.random.default_rng(3)
+    C, H, W, B, n = 6, 12, 16, 2, 700
+    mlp = torch.nn.ModuleList([torch.nn.Linear(1, 20), torch.nn.Linear(20, 20), torch.nn.Linear(20, 1)])
+
+    class VL(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.mlp = mlp
+    vl = VL()
+    ev_np = np.stack([rng.integers(0, W, B * n), rng.integers(0, H, B * n), np.concatenate([np.sort(rng.integers(1, 90000, n)) for _ in range(B)]),
+                      rng.integers(0, 2, B * n), np.repeat(np.arange(B), n)], 1).astype(np.float32)
+    ev = _batch(eb, ev_np, B)
+    proj = torch.as_tensor(rng.standard_normal((B, H, W, 2 * C)), dtype=torch.float32, device="cuda")
+    out = est.quantize_trainable(ev, H, W, C, vl, 0.1, t_float=torch.as_tensor(ev_np[:, 2]).cuda())
+    (out * proj).sum().backward()
+    got = [p.grad.detach().double().cpu().clone() for p in vl.parameters()]
+    for p in vl.parameters():
+        p.grad = None
+    # the reference forward, float64, on the CPU
+    e = torch.as_tensor(ev_np, dtype=torch.float64)
+    x, y, t, pol, b = e.t()
+    t = t.clone()
+    t32 = torch.as_tensor(ev_np[:, 2])
+    for bi in range(B):
+        m = e[:, -1] == bi
+        t[m] = (t32[m] / t32[m].max()).double()  # the layer normalises in float32
+    vox = torch.zeros(B * H * W * 2 * C, dtype=torch.float64)
+    params = [q.double() for q in vl.parameters()]
+    for i_bin in range(C):
+        u = (t.float() - i_bin / (C - 1)).double()  # float32 tensor minus a Python float, as in the reference
+        vals = t * est._mlp_double(list(vl.parameters()), u, 0.1)
+        idx = (((b * H + y) * W + x) * (2 * C) + pol * C + i_bin).long()  # (B, H, W, 2C) layout of the CUDA output
+        vox = vox.index_put((idx,), vals, accumulate=True)
+    (vox * proj.double().cpu().reshape(-1)).sum().backward()
+    want = [p.grad.detach().double().cpu() for p in vl.parameters()]
+    for g_, w_ in zip(got, want):
+        scale = max(float(w_.abs().max()), 1e-12)
+        assert float((g_ - w_).abs().max()) <= 2e-5 * scale, (float((g_ - w_).abs().max()), scale)
+    # and the forward of the trainable path is the inference path
+    tables = est.value_layer_tables(vl)
+    assert torch.allclose(out.detach(), est.quantize(ev, H, W, C, tables, t_float=torch.as_tensor(ev_np[:, 2]).cuda()), rtol=1e-6, atol=1e-7)

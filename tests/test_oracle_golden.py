@@ -111,6 +111,18 @@ def test_voxel_tonic(name, path):
     assert_close(out[:, None], g["out"], rtol=1e-12, atol=1e-15, what=name)
 
 
+VS = golden("voxel_subpixel_*")
+
+
+@pytest.mark.parametrize("name,path", VS, ids=[n for n, _ in VS])
+def test_voxel_evlicious_subpixel(name, path):
+    """divider > 1: float32 coordinates, 4-tap bilinear scatter (utils.py:93-103), fixtures from the reference's own code"""
+    g = load(path)
+    out = orep.voxel_evlicious(g["x"], g["y"], g["t"], g["p"], int(g["H"]), int(g["W"]), int(g["bins"]), bool(g["normalize"]), divider=int(g["divider"]))
+    assert out.dtype == g["out"].dtype and out.shape == g["out"].shape
+    assert np.array_equal(out, g["out"])  # the same float32 additions in the same order
+
+
 VE = golden("voxel_evlicious_*")
 
 
