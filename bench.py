@@ -29,6 +29,8 @@ import time
 
 import numpy as np
 
+_OUT = sys.stdout  # main() swaps in a duplicate of the original fd 1
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -180,7 +182,7 @@ def run_reference_arm(a):
         "data": "synthetic", "config": config_dict(a, a.windows),
         "cpu_baseline": {"value": val, "unit": "Gevents/s", "cores": procs, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "Gevents/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    }), file=_OUT, flush=True)
 
 
 def config_dict(a, windows):
@@ -619,7 +621,7 @@ def run_gpu_arm(a):
                 line["configs"] = bench_configs(dev, a.steps)
                 line["dropin"] = bench_dropin(dev)
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -638,6 +640,12 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--no-extras", action="store_true", help="headline + e2e only: skip the gwd / configs / parity_spot_check / dropin records")
     a = ap.parse_args()
+    # stdout carries the ONE JSON line and nothing else: NCCL prints its version banner to fd 1 at communicator creation,
+    # so fd 1 is pointed at stderr for the run and the line is written to the saved descriptor
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if a.impl == "reference":
         run_reference_arm(a)
     else:
