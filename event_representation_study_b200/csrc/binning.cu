@@ -767,184 +767,11 @@ __global__ void __launch_bounds__(BIN_THREADS, EVREP_BIN_CTAS) k_bin(const uint1
   for (uint32_t i = tid; i < total; i += BIN_THREADS) dst[i + delta[sbkt[i]]] = stage[i];
 }
 
-// ---------------------------------------------------------------------------------------------
-// Single-pass alternative for consumers that can GATHER (the compile-time specialised ERGO-12 tile kernel): a CTA sorts its
-// super-chunk by bucket entirely on chip and writes the records back where the events were - no global histogram, no
-// column / bucket scans, no second read of the events, and the record write is one contiguous stream.  What replaces the
-// global placement is the per-super-chunk offset row `cc` (exclusive bucket offsets + total, as k_hist writes it): the
-// records of bucket k of super-chunk s are records[first(s) + cc[s][k] .. first(s) + cc[s][k + 1]), first(s) = max(start of the
-// window, first event slot of the super-chunk).  Per event: one returning shared-memory atomic (its rank inside its
-// bucket; kept in a register), after the block scan one offset load and one 8-byte staged store.
-// ---------------------------------------------------------------------------------------------
-template <typename TT, bool SPLIT>
-__global__ void __launch_bounds__(BIN_THREADS, EVREP_BIN_CTAS) k_sortbin(const uint16_t* __restrict__ x, const uint16_t* __restrict__ y,
-                                                         const TT* __restrict__ t, const int8_t* __restrict__ p,
-                                                         WinParams* __restrict__ wp, const int32_t* __restrict__ sc_prefix,
-                                                         const int32_t* __restrict__ sc_win, const Geom g, const bool vec,
-                                                         uint16_t* __restrict__ cc, uint2* __restrict__ records) {
-  extern __shared__ __align__(16) unsigned char sh_raw[];
-  uint2* stage = reinterpret_cast<uint2*>(sh_raw);            // SUPER records, sorted by bucket
-  uint32_t* hist = reinterpret_cast<uint32_t*>(stage + SUPER);  // Tb: counts, then exclusive offsets
-  __shared__ int sh_tmin, sh_tmax;
-  __shared__ uint32_t sh_flags, sh_m1;
-  __shared__ uint32_t warp_tot[BIN_THREADS / 32 + 1];
-
-  const int tid = threadIdx.x;
-  const ChunkHdr h = chunk_hdr(blockIdx.x, wp, sc_prefix, sc_win);
-  ChunkRegs<TT> r;
-  chunk_fetch<TT>(r, h, x, y, t, p, vec, tid);
-  for (int i = tid; i < g.Tb; i += BIN_THREADS) hist[i] = 0;
-  if (tid == 0) { sh_tmin = INT_MAX; sh_tmax = INT_MIN; sh_flags = 0; sh_m1 = 0; }
-  __syncthreads();
-
-  uint32_t hbase = (uint32_t)__cvta_generic_to_shared(hist), sbase = (uint32_t)__cvta_generic_to_shared(stage);
-  asm volatile("" : "+r"(hbase), "+r"(sbase));
-  const int n = h.n;
-  const int64_t start = h.start, t_base = h.t_base;
-  const int n3 = n / 3, s4 = n / 2, s5 = s4 + n / 4, s6 = s5 + n / 8;
-  const uint32_t Wd = (uint32_t)g.W, Hd = (uint32_t)g.H;
-  const uint32_t pix_mask = (uint32_t)(g.tile_px - 1);
-  const int tile_shift = g.tile_shift;
-  auto sbn = [&](int idx) -> uint32_t {
-    return 1u | (idx < n3 ? 2u : (idx < 2 * n3 ? 4u : (idx < 3 * n3 ? 8u : 0u))) | (idx >= s4 ? 16u : 0u) | (idx >= s5 ? 32u : 0u) | (idx >= s6 ? 64u : 0u);
-  };
-  auto bucket = [&](uint32_t lin, int pv) {
-    uint32_t bin = lin >> tile_shift;
-    if (SPLIT) bin = bin + bin + (pv > 0 ? 0u : 1u);
-    return bin;
-  };
-  BinAcc acc;
-  // staging of one record at a known slot
-  auto stage_rec = [&](uint32_t slot, uint32_t lin, int pv, int32_t t_rel, uint32_t aux, bool keep) {
-    uint32_t k = (uint32_t)t_rel, meta = rec_meta(lin & pix_mask, aux, (uint32_t)pv & 3u);
-    if (keep) {
-      acc.tmin = min(acc.tmin, t_rel);
-      acc.tmax = max(acc.tmax, t_rel);
-      acc.m1 |= pv == -1 ? aux : 0u;
-    } else {
-      k = 0u;
-      meta = REC_NULL_META;
-    }
-    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sbase + (slot << 3)), "r"(k), "r"(meta) : "memory");
-  };
-
-  // Is every event of this CTA on the fast path (inside the window, valid pixel / polarity, sorted, in the 31-bit time range, one
-  // SBN mask per thread chunk)?  Nearly always, except in the first and last super-chunk of a window; the decision is CTA-wide
-  // so that the two passes below stay free of per-event checks.
-  bool mine = true;
-#pragma unroll
-  for (int sub = 0; sub < SC_CHUNKS; ++sub) {
-    const int64_t g0 = h.c0 + (int64_t)sub * CHUNK + (int64_t)tid * EPT;
-    const int idx0 = (int)(g0 - start);
-    if (idx0 >= n || idx0 + EPT <= 0) continue;  // no events here
-    bool f = r.full[sub];
-    if (f) {
-      TT prev = r.t_before[sub];
-      bool sorted = true;
-#pragma unroll
-      for (int e = 0; e < EPT; ++e) {
-        const TT te = r.qt[sub].get(e);
-        sorted &= !(te < prev);
-        prev = te;
-      }
-      const int64_t d0 = (int64_t)r.qt[sub].get(0) - t_base, d7 = (int64_t)r.qt[sub].get(EPT - 1) - t_base;
-      f = sorted && d0 > -(int64_t)T_REL_LIMIT && d7 < (int64_t)T_REL_LIMIT && polarities_valid4(r.qp[sub].x) && polarities_valid4(r.qp[sub].y) &&
-          sbn(idx0) == sbn(idx0 + EPT - 1);
-#pragma unroll
-      for (int e = 0; e < EPT; ++e) f &= (raw_u16(r.qx[sub], e) < Wd) & (raw_u16(r.qy[sub], e) < Hd);
-    }
-    mine &= f;
-  }
-  const bool cta_fast = __syncthreads_and(mine);
-  uint32_t total;
-  if (cta_fast) {
-    // pass 1: rank every event inside its bucket (two 16-bit ranks per register)
-    uint32_t rk[SC_CHUNKS][EPT / 2];
-#pragma unroll
-    for (int sub = 0; sub < SC_CHUNKS; ++sub) {
-      const int idx0 = (int)(h.c0 + (int64_t)sub * CHUNK + (int64_t)tid * EPT - start);
-#pragma unroll
-      for (int k = 0; k < EPT / 2; ++k) rk[sub][k] = 0;
-      if (idx0 >= n || idx0 + EPT <= 0) continue;
-#pragma unroll
-      for (int e = 0; e < EPT; ++e) {
-        const uint32_t lin = raw_u16(r.qy[sub], e) * Wd + raw_u16(r.qx[sub], e);
-        rk[sub][e >> 1] |= smem_fetch_inc(hbase + (bucket(lin, raw_i8(r.qp[sub], e)) << 2)) << (16 * (e & 1));
-      }
-    }
-    __syncthreads();
-    total = block_exclusive_scan(hist, g.Tb, warp_tot);  // ends with a barrier
-    // pass 2: stage every record at offset[bucket] + rank
-#pragma unroll
-    for (int sub = 0; sub < SC_CHUNKS; ++sub) {
-      const int idx0 = (int)(h.c0 + (int64_t)sub * CHUNK + (int64_t)tid * EPT - start);
-      if (idx0 >= n || idx0 + EPT <= 0) continue;
-      const uint32_t aux = sbn(idx0);
-#pragma unroll
-      for (int e = 0; e < EPT; ++e) {
-        const uint32_t lin = raw_u16(r.qy[sub], e) * Wd + raw_u16(r.qx[sub], e);
-        const int pv = raw_i8(r.qp[sub], e);
-        const int32_t t_rel = sizeof(TT) == 4 ? (int32_t)((uint32_t)r.qt[sub].get(e) - (uint32_t)t_base) : (int32_t)((int64_t)r.qt[sub].get(e) - t_base);
-        uint32_t off;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(off) : "r"(hbase + (bucket(lin, pv) << 2)) : "memory");
-        stage_rec(off + ((rk[sub][e >> 1] >> (16 * (e & 1))) & 0xffffu), lin, pv, t_rel, aux, true);
-      }
-    }
-  } else {
-    // generic path (window edges, unsorted / out-of-range data): count, scan, then one more returning atomic per event for its
-    // slot; every event is re-read with scalar loads and fully checked
-    auto visit = [&](bool place) {
-#pragma unroll 1
-      for (int sub = 0; sub < SC_CHUNKS; ++sub) {
-        const int64_t g0 = h.c0 + (int64_t)sub * CHUNK + (int64_t)tid * EPT;
-        const int idx0 = (int)(g0 - start);
-        if (idx0 >= n || idx0 + EPT <= 0) continue;
-        TT t_prev = 0;
-        bool have_prev = idx0 >= 1;
-        if (have_prev) t_prev = __ldg(t + g0 - 1);
-#pragma unroll 1
-        for (int e = 0; e < EPT; ++e) {
-          const int idx = idx0 + e;
-          if ((uint32_t)idx >= (uint32_t)n) continue;
-          const TT te = __ldg(t + g0 + e);
-          const uint32_t xe = __ldg(x + g0 + e), ye = __ldg(y + g0 + e);
-          int pv = __ldg(p + g0 + e);
-          if (have_prev && te < t_prev) acc.flags |= EVREP_WF_UNSORTED;
-          t_prev = te;
-          have_prev = true;
-          if ((xe >= Wd) | (ye >= Hd)) { acc.flags |= EVREP_WF_OUT_OF_RANGE; continue; }
-          bool keep = true;
-          const int64_t d = (int64_t)te - t_base;
-          if (d >= T_REL_LIMIT || d <= -T_REL_LIMIT) { acc.flags |= EVREP_WF_T_RANGE; keep = false; }
-          if (pv > 1 || pv < -1) { acc.flags |= EVREP_WF_BAD_POLARITY; pv = pv > 0 ? 1 : -1; }
-          const uint32_t lin = ye * Wd + xe;
-          const uint32_t slot = smem_fetch_inc(hbase + (bucket(lin, pv) << 2));
-          if (place) stage_rec(slot, lin, pv, (int32_t)d, sbn(idx), keep);
-        }
-      }
-    };
-    visit(false);
-    __syncthreads();
-    total = block_exclusive_scan(hist, g.Tb, warp_tot);
-    // the offsets go to global memory before the second pass turns them into cursors
-    {
-      uint16_t* dst = cc + (size_t)blockIdx.x * cc_stride(g.Tb);
-      for (int i = tid; i < g.Tb; i += BIN_THREADS) dst[i] = (uint16_t)hist[i];
-      if (tid == 0) dst[g.Tb] = (uint16_t)total;
-    }
-    __syncthreads();
-    visit(true);
-  }
-  if (cta_fast) {
-    uint16_t* dst = cc + (size_t)blockIdx.x * cc_stride(g.Tb);
-    for (int i = tid; i < g.Tb; i += BIN_THREADS) dst[i] = (uint16_t)hist[i];
-    if (tid == 0) dst[g.Tb] = (uint16_t)total;
-  }
-  bin_publish(acc, wp + h.b, &sh_tmin, &sh_tmax, &sh_flags, &sh_m1, tid);  // contains the barrier after the staging
-  // copy out: the sorted super-chunk as one contiguous run
-  uint2* dst = records + (h.c0 > start ? h.c0 : start);
-  for (uint32_t i = tid; i < total; i += BIN_THREADS) dst[i] = stage[i];
-}
+// A single-pass alternative was measured and dropped (profiles/README.md, round 2: "k_sortbin"): one kernel that sorts a
+// super-chunk by bucket on chip and writes the records back in place (0.152 ms for the 32 x 1 M step against 0.244 ms for
+// k_hist + scans + k_bin).  Its records stay fragmented per super-chunk (about 2.3 records per bucket and super-chunk at
+// 1 Mpx), so the tile kernel would have to gather ~120 18-byte pieces per bucket; the estimated net gain (-0.05 ms) did not
+// justify a second record layout through every consumer.
 
 template <typename TT, int MODE, bool SPLIT, bool DIV = false>
 static int launch_bin(const Events& ev, const Geom& g, const Workspace& ws, int n_sc, bool vec, cudaStream_t stream) {
@@ -1069,17 +896,7 @@ int run_binning(const Events& ev, const int64_t* win_offsets_host, const Geom& g
       k_snap_init<int64_t><<<g.B, 32, 0, stream>>>((const int64_t*)ev.t, ws.wp, user, n_snap, ws.snap);
     EVREP_CUDA_OK(cudaGetLastError());
   }
-  if (n_sc > 0 && rec_mode == REC_T_WMASK && g.split && ev.t_bytes == 4 && getenv("EVREP_SORTBIN_TEST") && getenv("EVREP_SORTBIN_TEST")[0] == '1') {  // experiment: time the single-pass kernel alone
-    const size_t smem = (size_t)SUPER * sizeof(uint2) + sizeof(uint32_t) * (size_t)g.Tb;
-    if (ev.t_bytes == 4) {
-      EVREP_CUDA_OK(cudaFuncSetAttribute(k_sortbin<int32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      prof_begin(EVREP_K_COUNT, stream);
-      k_sortbin<int32_t, true><<<n_sc, BIN_THREADS, smem, stream>>>(ev.x, ev.y, (const int32_t*)ev.t, ev.p, ws.wp, ws.sc_prefix, ws.sc_win, g, vec, ws.cc, ws.records);
-      prof_end(EVREP_K_COUNT, stream);
-    }
-    EVREP_CUDA_OK(cudaGetLastError());
-    prepare_windows(ev, win_offsets_host, g, ws, &n_sc, stream);  // reset the window scalars the test kernel touched
-  } else if (n_sc > 0) {
+  if (n_sc > 0) {
     prof_begin(EVREP_K_COUNT, stream);
     if (g.split)
       k_hist<true, false><<<n_sc, BIN_THREADS, sizeof(uint32_t) * (size_t)g.Tb, stream>>>(ev.x, ev.y, ev.p, ws.wp, ws.sc_prefix, ws.sc_win, g, vec, ws.cc);

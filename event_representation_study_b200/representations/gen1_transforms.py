@@ -18,8 +18,7 @@ def get_item_transform(reshaped_return_data, representation_name, transform, hei
         rep = rep.transpose(1, 2, 0) * 255
 
     elif "MixedDensityEventStack" in representation_name:
-        rep = get_optimized_representation(reshaped_return_data, num_events, height, width)
-        rep *= 255
+        rep = get_optimized_representation(reshaped_return_data, num_events, height, width, _scale=255.0)  # rep *= 255, done on the GPU
 
     elif "EventStack" in representation_name:
         reshaped_return_data["p"] = (reshaped_return_data["p"] + 1) // 2

@@ -2,7 +2,9 @@
 import numpy as np
 
 from ... import batched as eb
-from ..._single import one_window
+import torch
+
+from ..._single import one_window, one_window_structured, to_host
 from .operations import Operations
 
 
@@ -22,24 +24,29 @@ class MixedDensityEventStack:
         pad = lambda lst, fill: [lst[i] if i < len(lst) else fill for i in range(n)]
         return pad(list(w), 127), pad(list(f), "<missing>"), pad(list(a), "<missing>")
 
-    def _run(self, x, y, p, t):
+    def _run(self, x, y, p, t, _scale=None, _records=None):
         if len(t) == 0:
             raise ValueError("zero-size array to reduction operation minimum which has no identity")  # t.min() (reference :33)
         w, f, a = self._spec()
         try:
-            ev = one_window(x, y, t, p, self.height, self.width)
+            ev = one_window_structured(_records, self.height, self.width) if _records is not None else None
+            if ev is None:
+                ev = one_window(x, y, t, p, self.height, self.width)
         except IndexError:
             # an out-of-range pixel makes every torch_scatter call raise inside make_stack: all channels zero (reference :120-127)
             return np.zeros((self.height, self.width, self.stack_size), np.float64)
-        return eb.mixed_density(ev, self.height, self.width, w, f, a, self.stacking_type)[0].double().cpu().numpy()
+        return to_host(eb.mixed_density(ev, self.height, self.width, w, f, a, self.stacking_type)[0], torch.float64, _scale)
 
-    def stack(self, event_sequence):
-        x = event_sequence["x"].astype(np.int32)
-        y = event_sequence["y"].astype(np.int32)
-        p = event_sequence["p"].astype(np.int32)
-        t = event_sequence["t"].astype(np.int64)
+    def stack(self, event_sequence, _scale=None):
+        """_scale (not in the reference): multiply the float64 result on the GPU before it is copied back - the `rep *= 255`
+        of get_item_transform (gen1_transforms.py:36) without a pass over 88 MB on one host core."""
+        x, y, p, t = event_sequence["x"], event_sequence["y"], event_sequence["p"], event_sequence["t"]
         assert len(x) == len(y) == len(p) == len(t)
-        return self._run(x, y, p, t)
+        if isinstance(event_sequence, np.ndarray) and all(v.dtype == np.dtype("<i4") for v in (x, y, p, t)):
+            # the `<i4` record layout of the detection loaders: the reference's .astype(np.int32) / (np.int64) are value
+            # preserving, so the records go to the GPU as they are (one copy) and are split there
+            return self._run(x, y, p, t, _scale, _records=event_sequence)
+        return self._run(x.astype(np.int32), y.astype(np.int32), p.astype(np.int32), t.astype(np.int64), _scale)
 
     def create_windows(self, x, y, p, t):
         """The 7 (SBN) / 8 (SBT) event subsets, as host array views like the reference (reference :48-109).

@@ -5,7 +5,9 @@ from typing import Tuple, Union
 import numpy as np
 
 from .. import batched as eb
-from .._single import one_window
+import torch
+
+from .._single import one_window, to_host
 
 
 def _surfaces(x, y, t, p, indices, n_pol, H, W, tau):
@@ -15,7 +17,7 @@ def _surfaces(x, y, t, p, indices, n_pol, H, W, tau):
     t, tau = _integer_time(t, tau)
     ev = one_window(x, y, t, p, H, W, require_sorted=True)
     idx = np.asarray(indices, np.int64).reshape(1, -1)
-    return eb.time_surface(ev, H, W, idx.shape[1], float(tau), indices=idx)[0].double().cpu().numpy()
+    return to_host(eb.time_surface(ev, H, W, idx.shape[1], float(tau), indices=idx)[0], torch.float64)
 
 
 def _integer_time(t, tau):

@@ -3,7 +3,7 @@ import numpy as np
 import torch
 
 from .. import batched as eb
-from .._single import device
+from .._single import device, to_host
 
 
 def events2ToreFeature(x, y, ts, pol, sampleTimes, k, frameSize):
@@ -31,4 +31,4 @@ def events2ToreFeature(x, y, ts, pol, sampleTimes, k, frameSize):
     t_dtype = np.int32 if (t.min() >= -2**31 and t.max() < 2**31) else np.int64
     up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     ev = eb.EventBatch(up(xi), up(yi), up(t.astype(t_dtype)), up(p), np.array([0, len(t)], np.int64))
-    return eb.tore(ev, Hf, Wf, int(k))[0].cpu().numpy()
+    return to_host(eb.tore(ev, Hf, Wf, int(k))[0])

@@ -177,6 +177,32 @@ def test_mixed_density_class(name, path):
     assert len(wins) == (7 if str(g["stacking"]) == "SBN" else 8)
 
 
+def test_mixed_density_record_fast_path_equals_the_general_path():
+    """`<i4` records go to the GPU in one copy and are split there (_single.one_window_structured); every other layout takes
+    the host path: same values, same exceptions, zeros for an out-of-range pixel (reference :120-127)"""
+    from event_representation_study_b200.representations.optimized_representation import get_optimized_representation
+    from event_representation_study_b200 import _single
+    from event_representation_study_b200.synth import poisson_window
+    H, W, N = 240, 304, 120_000  # 5.5 MB of float64 output: the pinned read-back path
+    w = poisson_window(77, N, H, W)
+    fast, slow = structured(w, "<i4"), structured(w, "<i8")
+    assert _single.one_window_structured(fast, H, W) is not None and _single.one_window_structured(slow, H, W) is None
+    a, b = get_optimized_representation(fast, N, H, W), get_optimized_representation(slow, N, H, W)
+    assert a.dtype == np.float64 and a.flags.writeable and np.array_equal(a, b)
+    assert np.array_equal(get_optimized_representation(fast, N, H, W, _scale=255.0), b * 255)
+    bad = fast.copy()
+    bad["x"][5] = W
+    assert not get_optimized_representation(bad, N, H, W).any()
+    bad = fast.copy()
+    bad["p"][5] = 2
+    with pytest.raises(ValueError):
+        get_optimized_representation(bad, N, H, W)
+    bad = fast.copy()
+    bad["t"][-1] = bad["t"][0] + 2**30
+    with pytest.raises(ValueError):
+        get_optimized_representation(bad, N, H, W)
+
+
 def test_operations_exec():
     from event_representation_study_b200.representations.representation_search.operations import Operations
     from oracle import representations as orep
