@@ -270,6 +270,32 @@ __global__ void __launch_bounds__(TILE_THREADS) k_time_surface_tile_s(const uint
   const uint32_t delta_u = (w.tmax_rel >= w.tmin_rel) ? (uint32_t)(w.tmax_rel - w.tmin_rel) : 0u;
   const bool small = delta_u < (1u << 24) - 1u;  // CTA-uniform
   const float c_hi = (float)inv_tau_log2e, c_lo = (float)(inv_tau_log2e - (double)c_hi);
+  if (small && (npix & 3) == 0 && (g.HW & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
+    // four consecutive pixels of one polarity plane per thread: one 16-byte shared load and one 16-byte streaming store
+    // per snapshot (the scalar version spent ~18 instructions per output, most of them addressing and loop control)
+    const int nq = npix >> 2;
+    for (int item = tid; item < 2 * nq; item += TILE_THREADS) {
+      const int plane = item >= nq ? 1 : 0, q = item - plane * nq;
+      float* dst = out + ((size_t)b * S * 2 + plane) * plane_stride + pix0 + 4 * q;
+      uint4 m = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int k = 0; k < S; ++k) {
+        const uint4 a = *reinterpret_cast<const uint4*>(&acc[(k * 2 + plane) * TP + 4 * q]);
+        m.x = max(m.x, a.x), m.y = max(m.y, a.y), m.z = max(m.z, a.z), m.w = max(m.w, a.w);
+        const float em = empty[k];
+        auto val = [&](uint32_t mm) {
+          const float df = (float)((int32_t)mm - trel[k]);
+          float e;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(df, c_lo, df * c_hi)));
+          return mm ? e : em;
+        };
+        float4 o = make_float4(em, em, em, em);  // k >= nvalid: zeros
+        if (k < nvalid) o = make_float4(val(m.x), val(m.y), val(m.z), val(m.w));
+        __stcs(reinterpret_cast<float4*>(dst + k * snap_stride), o);
+      }
+    }
+    return;
+  }
   for (int plane = 0; plane < 2; ++plane) {
     float* dst = out + ((size_t)b * S * 2 + plane) * plane_stride + pix0;
     if (small) {
@@ -431,11 +457,11 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tore_tile_k(const uint2* __res
         if (alive) {
           const uint32_t v = live ? acc[c * TP + p0 + tid] : 0u;
           alive = __any_sync(0xffffffffu, v != 0u);
-          if (v) {
-            float age = (float)(age0 - (int32_t)v);
-            age = fminf(age, max_time);
-            o[c] = fmaxf(logf(age + 1.f) - log151, 0.f);
-          }
+          // log(age + 1) through lg2.approx (|error| <= 2^-22 in log2, 1.7e-7 here) and one fused multiply-add: inside the
+          // 1e-6 absolute floor the float32 reference itself needs around age = 150; logf cost ~25 instructions per slot
+          const float age = fminf((float)(age0 - (int32_t)v), max_time);
+          const float lg = fmaxf(fmaf(__log2f(age + 1.f), 0.693147180559945f, -log151), 0.f);
+          o[c] = v ? lg : empty;
         }
       }
     }
