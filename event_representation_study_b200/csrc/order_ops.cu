@@ -226,14 +226,16 @@ __global__ void __launch_bounds__(TILE_THREADS) k_time_surface_tile_s(const uint
     const int32_t tr = snap[b].t_rel[tid];
     s_trel[tid] = tr;
     s_sidx[tid] = snap[b].idx[tid];
-    // untouched pixels: exp((-(3 tau + 1) - t_snapshot) / tau) with the ABSOLUTE snapshot timestamp
-    s_empty[tid] = (float)exp((-(tau * 3.0 + 1.0) - (double)(w.t_base + (int64_t)tr)) / tau);
   }
   if (tid == 0) s_nvalid = snap[b].n_valid;
   const uint32_t count = hist[blockIdx.x];
   const uint2* rec = records + w.start + base[blockIdx.x];
   const int32_t tmin = w.tmin_rel;
   __syncthreads();
+  // untouched pixels: exp((-(3 tau + 1) - t_snapshot) / tau) with the ABSOLUTE snapshot timestamp.  A double-precision exp
+  // (~100 dependent instructions) that only the finalise needs: evaluated by S threads while the CTA accumulates instead of
+  // ahead of the barrier every warp waits at
+  if (tid < S) s_empty[tid] = (float)exp((-(tau * 3.0 + 1.0) - (double)(w.t_base + (int64_t)s_trel[tid])) / tau);
   for (uint32_t i = tid; i < count; i += TILE_THREADS) {
     const uint2 r = __ldg(rec + i);
     if (FUSED) {  // REC_T_IDX records: the first snapshot an event feeds is found from its stream index here
@@ -344,6 +346,12 @@ int launch_time_surface_tile(const Geom& g, const Workspace& ws, int S, double t
   return EVREP_OK;
 }
 
+// float32 constants of tore.py:69-79 as literals (nvcc does not fold log() of a constant: every thread spent ~60 instructions,
+// most of them double precision, on them - ncu r02): log(minTime + 1) and the value of a slot that never saw an event,
+// log(float32(maxTime) + 1) - log(151) in float32 as numpy evaluates it
+#define TORE_LOG151 __uint_as_float(0x40a08d8eu)  /* 5.0172796 */
+#define TORE_EMPTY __uint_as_float(0x41703497u)   /* 15.012839 */
+
 // ---------------------------------------------------------------------------------------------
 // TORE: per pixel and polarity class the k most recent ages T - t among events with t < T
 // (T = timestamp of the window's last event), ascending, then the float32 log compression of
@@ -377,8 +385,8 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tore_tile(const uint2* __restr
   }
   __syncthreads();
   const float max_time = 500e6f;
-  const float log151 = (float)log(151.0);
-  const float empty = fmaxf(logf(max_time + 1.f) - log151, 0.f);
+  const float log151 = TORE_LOG151;
+  const float empty = TORE_EMPTY;
   float* dst = out + ((size_t)b * g.HW + pix0) * (2 * K);
   const int n_el = npix * 2 * K;
   for (int e = tid; e < n_el; e += TILE_THREADS) {
@@ -437,8 +445,8 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tore_tile_k(const uint2* __res
   }
   __syncthreads();
   const float max_time = 500e6f;
-  const float log151 = (float)log(151.0);
-  const float empty = fmaxf(logf(max_time + 1.f) - log151, 0.f);
+  const float log151 = TORE_LOG151;
+  const float empty = TORE_EMPTY;
   const int32_t age0 = w.tlast_rel - tmin + 1;  // age = tlast_rel - (key - 1 + tmin)
   float4* dst4 = reinterpret_cast<float4*>(out + ((size_t)b * g.HW + pix0) * C);
   for (int p0 = 0; p0 < npix; p0 += TILE_THREADS) {
@@ -460,7 +468,9 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tore_tile_k(const uint2* __res
           // log(age + 1) through lg2.approx (|error| <= 2^-22 in log2, 1.7e-7 here) and one fused multiply-add: inside the
           // 1e-6 absolute floor the float32 reference itself needs around age = 150; logf cost ~25 instructions per slot
           const float age = fminf((float)(age0 - (int32_t)v), max_time);
-          const float lg = fmaxf(fmaf(__log2f(age + 1.f), 0.693147180559945f, -log151), 0.f);
+          float l2;
+          asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(age + 1.f));  // argument >= 1: no denormal handling needed
+          const float lg = fmaxf(fmaf(l2, 0.693147180559945f, -log151), 0.f);
           o[c] = v ? lg : empty;
         }
       }
