@@ -39,10 +39,21 @@ def scatter(src, index, dim=-1, out=None, dim_size=None, reduce="sum"):
     raise ValueError(reduce)
 
 
+def _arg_of(src, index, values, dim_size):
+    """torch_scatter's arg output: position of the element that set each output (the CPU kernel updates on a STRICT
+    comparison, so among equal values the first one stays), `src.numel()` for untouched outputs."""
+    n = src.numel()
+    arg = torch.full((dim_size,), n, dtype=torch.long)
+    if n:
+        cand = torch.where(src == values[index], torch.arange(n), torch.full((n,), n))
+        arg.scatter_reduce_(0, index, cand, "amin", include_self=True)
+    return arg
+
+
 def scatter_max(src, index, dim=-1, out=None, dim_size=None):
-    """torch_scatter.scatter_max -> (values, argmax); untouched entries are 0 (argmax not modelled: the call sites in
-    imagenet.py:169-293 discard it)"""
-    return scatter(src, index, dim, out, dim_size, "max"), None
+    """torch_scatter.scatter_max -> (values, argmax); untouched entries: value 0, arg = src.numel()"""
+    v = scatter(src, index, dim, out, dim_size, "max")
+    return v, _arg_of(src, index, v, v.numel())
 
 
 def scatter_min(src, index, dim=-1, out=None, dim_size=None):
@@ -50,4 +61,4 @@ def scatter_min(src, index, dim=-1, out=None, dim_size=None):
     o = torch.zeros(dim_size, dtype=src.dtype)
     if index.numel():
         o.scatter_reduce_(0, index, src, "amin", include_self=False)
-    return o, None
+    return o, _arg_of(src, index, o, dim_size)

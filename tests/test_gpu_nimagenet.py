@@ -129,5 +129,59 @@ def test_loader_table_matches_the_dataset_dispatch(N):
     assert N.loader_for(None) is N.reshape_then_acc and N.loader_for("event_histogram") is N.reshape_then_acc_count_pol
     assert N.loader_for("timestamp_image") is N.reshape_then_acc_time_pol and N.loader_for("binary_event_image") is N.reshape_then_flat
     assert N.loader_for("reshape_then_optimized") is None and N.loader_for("no such loader") is None  # caller-side wrappers: not in this module
-    with pytest.raises(NotImplementedError):
-        N.loader_for("DiST")
+    assert N.loader_for("DiST") is N.reshape_then_acc_adj_sort and N.loader_for("sorted_time_surface") is N.reshape_then_acc_sort
+
+
+# the rank-based loaders (imagenet.py:513-999) against the reference's own functions (oracle/gen_golden_nimagenet_sorted.py)
+SORT_BASE = dict(neglect_polarity=False, global_time=True, strict=False, use_image=False, denoise_sort=False, denoise_image=False,
+                 filter_flash=False, filter_noise=False, quantize_sort=None)
+SORT_CASES = {
+    "default": {}, "neglect": dict(neglect_polarity=True), "strict": dict(strict=True), "strict_neglect": dict(strict=True, neglect_polarity=True),
+    "image": dict(use_image=True), "image_neglect_strict": dict(use_image=True, neglect_polarity=True, strict=True), "quant8": dict(quantize_sort=8),
+    "quant_list": dict(quantize_sort=[4, 16], use_image=True), "quant_list_neglect": dict(quantize_sort=[4, 16], neglect_polarity=True, strict=True),
+    "local_time": dict(global_time=False), "local_time_strict": dict(global_time=False, strict=True),
+}
+
+
+@pytest.fixture(scope="module")
+def GS():
+    return load(golden("nimg_sorted")[0][1])
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+@pytest.mark.parametrize("case", sorted(SORT_CASES))
+def test_sorted_time_surface_matches_the_reference(N, GS, tag, case):
+    """ranks, presence images and quantised copies are integers or ratios of small integers: bit exact"""
+    import torch
+    H, W = int(GS[tag + "_H"]), int(GS[tag + "_W"])
+    rep = N.reshape_then_acc_sort(torch.tensor(GS[tag + "_events"].copy()), height=H, width=W, **{**SORT_BASE, **SORT_CASES[case]})
+    want = GS[f"{tag}_sort_{case}"]
+    assert rep.dtype == torch.float32 and tuple(rep.shape) == want.shape and not rep.is_cuda
+    assert np.array_equal(rep.numpy(), want)
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_dist_matches_the_reference(N, GS, tag):
+    """DiST: the kernel's planes are exact (ranks mapped back to the float64 stamps), the image-domain steps are the reference's
+    own float32 torch ops: bit exact"""
+    import torch
+    H, W = int(GS[tag + "_H"]), int(GS[tag + "_W"])
+    rep = N.reshape_then_acc_adj_sort(torch.tensor(GS[tag + "_events"].copy()), height=H, width=W, **SORT_BASE)
+    want = GS[tag + "_dist"]
+    assert rep.dtype == torch.float32 and tuple(rep.shape) == want.shape
+    assert np.array_equal(rep.numpy(), want), float(np.abs(rep.numpy() - want).max())
+
+
+def test_sorted_loaders_edge_cases(N):
+    """a polarity without events becomes one fake event at pixel (0, 0) (imagenet.py:641-646): strict gives a zero plane with the
+    fake count visible in the image, non-strict raises like `hot.max()` on an empty tensor; the undefined denoise helper raises
+    NameError as in the reference"""
+    import torch
+    ev = torch.tensor([[1.0, 2.0, 0.5, 1.0], [3.0, 0.0, 0.6, 1.0], [1.0, 2.0, 0.7, 1.0]], dtype=torch.float64)
+    r = N.reshape_then_acc_sort(ev, height=4, width=4, **{**SORT_BASE, "strict": True, "use_image": True})
+    assert tuple(r.shape) == (4, 4, 4) and float(r[0, 2, 1]) == 1.0 and float(r[1, 2, 1]) == 1.0 and float(r[1, 0, 3]) == 0.0
+    assert float(r[2, 0, 0]) == 1.0 and float(r[2].sum()) == 1.0 and not r[3].any()
+    with pytest.raises(RuntimeError):
+        N.reshape_then_acc_sort(ev, height=4, width=4, **SORT_BASE)
+    with pytest.raises(NameError):
+        N.reshape_then_acc_sort(ev, height=4, width=4, **{**SORT_BASE, "denoise_sort": True, "strict": True})

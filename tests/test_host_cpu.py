@@ -222,8 +222,16 @@ def test_n_imagenet_host_helpers():
     # ImageNetDataset's loader_type dispatch (imagenet.py:1232-1272)
     assert N.loader_for("event_image") is N.reshape_then_acc and N.loader_for("reshape_then_acc_intensity") is N.reshape_then_acc_intensity
     assert N.loader_for("reshape_then_tore") is None and N.loader_for("nope") is None
-    with pytest.raises(NotImplementedError):
-        N.loader_for("sorted_time_surface")
+    assert N.loader_for("sorted_time_surface") is N.reshape_then_acc_sort and N.loader_for("dist") is N.reshape_then_acc_adj_sort
+    # the rank-based loaders' image-domain helpers (imagenet.py:567-583, 606-621)
+    v = torch.tensor([[5.0, 0.0], [9.0, 5.0]], dtype=torch.float64)
+    r = N._dense_rank_normalised(v, v > 0)
+    assert r.dtype == torch.float32 and r.tolist() == [[0.0, 0.0], [1.0, 0.0]]
+    assert N._dense_rank_normalised(v, v > 100).tolist() == [[0.0, 0.0], [0.0, 0.0]]
+    q = N._quantize(torch.tensor([[0.3, 0.8]]), [4, 16])
+    assert tuple(q.shape) == (1, 2, 2) and q[0, 0, 0] == 0.25 and q[0, 1, 1] == 0.8125
+    with pytest.raises(RuntimeError):
+        N._hot_check(torch.zeros(3, 3))
 
 
 def test_new_entry_points_validate_before_touching_cuda(L):
