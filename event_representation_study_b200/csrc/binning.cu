@@ -230,6 +230,8 @@ template <typename TT, bool BY_VALUE>
 __global__ void k_init(const TT* __restrict__ t, int64_t* __restrict__ offsets, int32_t* __restrict__ sc_prefix, const __grid_constant__ InitTable tab,
                        int B, int32_t* __restrict__ sc_win, WinParams* __restrict__ wp, uint32_t* __restrict__ ticket) {
   const int b = blockIdx.x;
+  pdl_wait();  // the previous call's kernels may still be reading the workspace
+  pdl_trigger();
   if (b == 0 && threadIdx.x < 64) ticket[threadIdx.x] = 0;  // work counters of the persistent tile kernels
   int64_t o0, o1;
   int32_t s0, s1;
@@ -332,6 +334,8 @@ __global__ void __launch_bounds__(BIN_THREADS) k_hist(const uint16_t* __restrict
                                                       const int32_t* __restrict__ sc_prefix, const int32_t* __restrict__ sc_win,
                                                       const Geom g, const bool vec, uint16_t* __restrict__ cc) {
   extern __shared__ uint32_t sh_hist[];
+  pdl_wait();
+  pdl_trigger();
   const int b = __ldg(sc_win + blockIdx.x);
   const int scl = blockIdx.x - __ldg(sc_prefix + b);
   const int64_t start = wp[b].start;
@@ -416,6 +420,8 @@ __global__ void __launch_bounds__(256) k_colscan(const uint16_t* __restrict__ cc
                                                  uint32_t* __restrict__ cp, uint32_t* __restrict__ hist) {
   constexpr int U = 8;
   __shared__ uint32_t tot[8][32];
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
   const int c0 = blockIdx.x * 32, c = c0 + lane;
@@ -473,6 +479,8 @@ __global__ void __launch_bounds__(256) k_colscan(const uint16_t* __restrict__ cc
 __global__ void __launch_bounds__(BIN_THREADS) k_scan(const uint32_t* __restrict__ hist, uint32_t* __restrict__ base, int T) {
   __shared__ uint32_t a[MAX_TILES];
   __shared__ uint32_t warp_tot[BIN_THREADS / 32 + 1];
+  pdl_wait();
+  pdl_trigger();
   const size_t o = (size_t)blockIdx.x * T;
   for (int i = threadIdx.x; i < T; i += BIN_THREADS) a[i] = hist[o + i];
   __syncthreads();
@@ -733,6 +741,8 @@ __global__ void __launch_bounds__(BIN_THREADS, EVREP_BIN_CTAS) k_bin(const uint1
   __shared__ int sh_nsnap;
 
   const int tid = threadIdx.x;
+  pdl_wait();
+  pdl_trigger();
   const ChunkHdr h = chunk_hdr(blockIdx.x, wp, sc_prefix, sc_win);
   ChunkRegs<TT> r;
   chunk_fetch<TT>(r, h, x, y, t, p, vec, tid);  // every event of the thread is requested before the bucket tables are built
@@ -777,8 +787,8 @@ template <typename TT, int MODE, bool SPLIT, bool DIV = false>
 static int launch_bin(const Events& ev, const Geom& g, const Workspace& ws, int n_sc, bool vec, cudaStream_t stream) {
   const size_t smem = (size_t)SUPER * (sizeof(uint2) + sizeof(uint16_t)) + 2 * sizeof(uint32_t) * (size_t)g.Tb;
   EVREP_CUDA_OK(cudaFuncSetAttribute(k_bin<TT, MODE, SPLIT, DIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_bin<TT, MODE, SPLIT, DIV><<<n_sc, BIN_THREADS, smem, stream>>>(ev.x, ev.y, (const TT*)ev.t, ev.p, ws.wp, ws.snap, ws.sc_prefix, ws.sc_win, g, vec,
-                                                              ws.base, ws.cc, ws.cp, ws.records);
+  EVREP_CUDA_OK(launch_pdl(k_bin<TT, MODE, SPLIT, DIV>, n_sc, BIN_THREADS, smem, stream, ev.x, ev.y, (const TT*)ev.t, ev.p, ws.wp, ws.snap, ws.sc_prefix,
+                           ws.sc_win, g, vec, ws.base, ws.cc, ws.cp, ws.records));
   EVREP_CUDA_OK(cudaGetLastError());
   return EVREP_OK;
 }
@@ -848,9 +858,9 @@ int prepare_windows(const Events& ev, const int64_t* win_offsets_host, const Geo
     memcpy(tab.offsets, win_offsets_host, sizeof(int64_t) * (size_t)(g.B + 1));
     memcpy(tab.sc_prefix, prefix.data(), sizeof(int32_t) * (size_t)(g.B + 1));
     if (ev.t_bytes == 4)
-      k_init<int32_t, true><<<g.B, 64, 0, stream>>>((const int32_t*)ev.t, ws.offsets, ws.sc_prefix, tab, g.B, sc_win, ws.wp, ws.ticket);
+      EVREP_CUDA_OK(launch_pdl(k_init<int32_t, true>, g.B, 64, 0, stream, (const int32_t*)ev.t, ws.offsets, ws.sc_prefix, tab, g.B, sc_win, ws.wp, ws.ticket));
     else
-      k_init<int64_t, true><<<g.B, 64, 0, stream>>>((const int64_t*)ev.t, ws.offsets, ws.sc_prefix, tab, g.B, sc_win, ws.wp, ws.ticket);
+      EVREP_CUDA_OK(launch_pdl(k_init<int64_t, true>, g.B, 64, 0, stream, (const int64_t*)ev.t, ws.offsets, ws.sc_prefix, tab, g.B, sc_win, ws.wp, ws.ticket));
   } else {
     // pageable-source async copies are staged before the call returns, so the host vectors may die here
     // one copy for both tables (each pageable-source copy costs several microseconds of staging on the host)
@@ -868,6 +878,14 @@ int prepare_windows(const Events& ev, const int64_t* win_offsets_host, const Geo
   }
   EVREP_CUDA_OK(cudaGetLastError());
   return EVREP_OK;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("EVREP_NO_PDL");
+    return !(e && e[0] == '1');
+  }();
+  return on;
 }
 
 bool events_vectorisable(const Events& ev) { return aligned16(ev.x) && aligned16(ev.y) && aligned16(ev.t) && aligned16(ev.p); }
@@ -899,11 +917,11 @@ int run_binning(const Events& ev, const int64_t* win_offsets_host, const Geom& g
   if (n_sc > 0) {
     prof_begin(EVREP_K_COUNT, stream);
     if (g.split)
-      k_hist<true, false><<<n_sc, BIN_THREADS, sizeof(uint32_t) * (size_t)g.Tb, stream>>>(ev.x, ev.y, ev.p, ws.wp, ws.sc_prefix, ws.sc_win, g, vec, ws.cc);
+      EVREP_CUDA_OK(launch_pdl(k_hist<true, false>, n_sc, BIN_THREADS, sizeof(uint32_t) * (size_t)g.Tb, stream, ev.x, ev.y, ev.p, ws.wp, ws.sc_prefix, ws.sc_win, g, vec, ws.cc));
     else if (g.div_x > 1 || g.div_y > 1)
-      k_hist<false, true><<<n_sc, BIN_THREADS, sizeof(uint32_t) * (size_t)g.Tb, stream>>>(ev.x, ev.y, ev.p, ws.wp, ws.sc_prefix, ws.sc_win, g, vec, ws.cc);
+      EVREP_CUDA_OK(launch_pdl(k_hist<false, true>, n_sc, BIN_THREADS, sizeof(uint32_t) * (size_t)g.Tb, stream, ev.x, ev.y, ev.p, ws.wp, ws.sc_prefix, ws.sc_win, g, vec, ws.cc));
     else
-      k_hist<false, false><<<n_sc, BIN_THREADS, sizeof(uint32_t) * (size_t)g.Tb, stream>>>(ev.x, ev.y, ev.p, ws.wp, ws.sc_prefix, ws.sc_win, g, vec, ws.cc);
+      EVREP_CUDA_OK(launch_pdl(k_hist<false, false>, n_sc, BIN_THREADS, sizeof(uint32_t) * (size_t)g.Tb, stream, ev.x, ev.y, ev.p, ws.wp, ws.sc_prefix, ws.sc_win, g, vec, ws.cc));
     prof_end(EVREP_K_COUNT, stream);
     EVREP_CUDA_OK(cudaGetLastError());
   }
@@ -911,9 +929,9 @@ int run_binning(const Events& ev, const int64_t* win_offsets_host, const Geom& g
   // bucket sizes (also for windows without events: an empty column range gives 0), then bucket starts
   for (int b0 = 0; b0 < g.B; b0 += 65535) {
     const int nb = std::min(65535, g.B - b0);
-    k_colscan<<<dim3((unsigned)((g.Tb + 31) / 32), (unsigned)nb), 256, 0, stream>>>(ws.cc, ws.sc_prefix + b0, g.Tb, ws.cp + 0, ws.hist + (size_t)b0 * g.Tb);
+    EVREP_CUDA_OK(launch_pdl(k_colscan, dim3((unsigned)((g.Tb + 31) / 32), (unsigned)nb), 256, 0, stream, ws.cc, ws.sc_prefix + b0, g.Tb, ws.cp + 0, ws.hist + (size_t)b0 * g.Tb));
   }
-  k_scan<<<g.B, BIN_THREADS, 0, stream>>>(ws.hist, ws.base, g.Tb);
+  EVREP_CUDA_OK(launch_pdl(k_scan, g.B, BIN_THREADS, 0, stream, ws.hist, ws.base, g.Tb));
   prof_end(EVREP_K_SCAN, stream);
   EVREP_CUDA_OK(cudaGetLastError());
   if (n_sc > 0) {

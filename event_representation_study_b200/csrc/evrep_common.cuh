@@ -135,6 +135,33 @@ void set_error(const char* fmt, ...);
 // Optional per-kernel timing with CUDA events on the caller's stream (api.cu; evrep_profile_* in evrep.h).
 // No-ops unless profiling was enabled; never synchronise.
 void prof_next_call();
+// Programmatic dependent launch between the kernels of one call (and from one call to the next): a kernel launched through
+// launch_pdl may be scheduled while its predecessor in the stream drains - its CTAs become resident as the predecessor's
+// retire and run up to pdl_wait(), which returns once the predecessor has completed and its writes are visible.  Every
+// kernel of the chain calls pdl_wait() before its first global-memory access and pdl_trigger() right after it (so a
+// dependent never runs ahead of a kernel that has not itself seen ITS predecessor complete); launched the ordinary way both
+// are no-ops.  What it hides is the launch latency and the ramp of each of the six kernels of a call (~2 us apiece).
+// EVREP_NO_PDL=1 falls back to ordinary launches (A/B measurements).
+bool pdl_enabled();
+template <typename... P, typename... A>
+inline cudaError_t launch_pdl(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at{};
+  at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at.val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = &at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<P>(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 void prof_begin(int kernel_id, cudaStream_t stream);
 void prof_end(int kernel_id, cudaStream_t stream);
 

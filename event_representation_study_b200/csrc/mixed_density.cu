@@ -564,6 +564,9 @@ __global__ void __launch_bounds__(TILE_THREADS, (PS::value.stride * TP * 4 <= 74
   int cur = blockIdx.x, nxt = blockIdx.x + (int)gridDim.x;
   if (cur >= n_tiles) return;
   uint32_t* slab = acc + (tid >> 5) * SLAB;
+  md_zero_slab<SLAB>(slab);  // before the wait: runs while k_bin drains
+  pdl_wait();                // k_bin's records and bucket tables
+  pdl_trigger();
 
   // buckets are taken last window first: k_bin wrote the last windows' records most recently, so they are the ones
   // still in L2 when this kernel starts
@@ -574,7 +577,6 @@ __global__ void __launch_bounds__(TILE_THREADS, (PS::value.stride * TP * 4 <= 74
     const uint32_t i = tid + j * TILE_THREADS;
     pre[j] = i < h.count ? __ldg(h.rec + i) : make_uint2(0u, 0u);  // meta 0: member of no window, touches nothing
   }
-  md_zero_slab<SLAB>(slab);
   __syncthreads();
 
   while (true) {
@@ -689,7 +691,7 @@ static int launch_static(const Geom& g, const Workspace& ws, float* out, cudaStr
   if (per_sm < 1) per_sm = 1;
   const int grid = n_tiles < per_sm * n_sm ? n_tiles : per_sm * n_sm;
   prof_begin(EVREP_K_TILE, stream);
-  light<<<grid, TILE_THREADS, smem_l, stream>>>(ws.records, ws.base, ws.hist, ws.wp, g, ws.ticket, out);
+  EVREP_CUDA_OK(launch_pdl(light, grid, TILE_THREADS, smem_l, stream, ws.records, ws.base, ws.hist, ws.wp, g, ws.ticket, out));
   if (!(g.n_max > 0 && g.n_max < (int64_t)MD_PACKED_LIMIT))  // a bucket cannot hold more events than its window: nothing for the wide plan
     heavy<<<(n_tiles + TILE_THREADS - 1) / TILE_THREADS < n_sm ? (n_tiles + TILE_THREADS - 1) / TILE_THREADS : n_sm, TILE_THREADS, smem_h, stream>>>(
         ws.records, ws.base, ws.hist, ws.wp, g, out);
