@@ -422,6 +422,8 @@ def run_gpu_arm(a):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from event_representation_study_b200.sharding import bind_to_gpu_cpus
+    placement = bind_to_gpu_cpus(local)  # before any pinned allocation: first touch on the GPU's own NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -568,6 +570,30 @@ def run_gpu_arm(a):
     e2e_soa, chk_soa = e2e_leg(False)
     e2e_value, chk_pk = (e2e_leg(True) if pk is not None else (e2e_soa, chk_soa))
     assert pk is None or chk_pk == chk_soa, f"packed and SoA end-to-end legs disagree: {chk_pk} vs {chk_soa}"
+
+    # the ceiling of that leg: the same pinned buffers copied host -> device and nothing else, on every rank at once (the GPUs of
+    # a node share the host's memory controllers and root complexes, so the per-GPU rate drops as N grows)
+    def h2d_ceiling():
+        srcs = [pk.word, pk.tbase] + ([pk.dt16] if pk.dt16 is not None else []) if pk is not None else [host[k] for k in ("x", "y", "t", "p")]
+        dsts = [torch.empty_like(s_, device=dev) for s_ in srcs]
+        reps = max(3, min(a.steps, 20))
+        with torch.cuda.stream(copy_st):
+            for s_, d_ in zip(srcs, dsts):
+                d_.copy_(s_, non_blocking=True)
+        copy_st.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(copy_st):
+            for _ in range(reps):
+                for s_, d_ in zip(srcs, dsts):
+                    d_.copy_(s_, non_blocking=True)
+        copy_st.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        nbytes = sum(s_.numel() * s_.element_size() for s_ in srcs)
+        return nbytes * reps / float(dt.item()) / 1e9
+    link_gbs = h2d_ceiling()
     if sampler2 is not None:  # merge the samples of both timed regions (the first one is only ~15 ms long)
         c2 = sampler2.stop()
         if clocks and c2.get("samples"):
@@ -595,6 +621,10 @@ def run_gpu_arm(a):
                     "host_format": (f"packed wire format {pk.fmt} ({h2d / (B * N):.2f} B/event: x, y, polarity and the offset to the base timestamp of a block of "
                                     f"{1 << pk.block_shift} events in one 32-bit word; packed.pack_host on the loader side, evrep_unpack_events on the GPU)") if pk is not None
                                    else "SoA arrays, 9 B/event (the stream does not fit the packed formats)",
+                    "link": {"h2d_gbs_per_gpu_all_ranks_copying": link_gbs, "e2e_h2d_gbs_per_gpu": e2e_value / world * 1e9 * (h2d / (B * N)) / 1e9,
+                             "frac_of_link": (e2e_value / world * (h2d / (B * N))) / link_gbs,
+                             "note": "ceiling = the leg's own pinned buffers copied host -> device and nothing else, all ranks at once, slowest rank"},
+                    "placement": placement,
                     "soa9": {"value": e2e_soa, "h2d_bytes_per_step": h2d_soa, "note": "same leg with the unpacked SoA arrays (x u16, y u16, t i32, p i8) as host format"},
                     "note": f"host-link bound; {n_groups} window groups per step, copy stream prefetching the next step's events; both legs return the same per-window "
                             "checksums; the dense output stays on the GPU for the model (the numpy-in / numpy-out call with the full output copied back is the `dropin` record)"},

@@ -42,3 +42,37 @@ def gather_cost_matrix(local_costs, group=None):
     parts = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(parts, pad, group=group)
     return torch.cat([p[:, :w] for p, w in zip(parts, widths)], dim=1)
+
+
+def bind_to_gpu_cpus(device_index=None):
+    """Pin the calling process to the CPUs that NVML reports as local to its GPU, so that the pinned host buffers it allocates
+    afterwards are first-touched on the GPU's NUMA node and its copy / launch threads run next to the root complex the GPU hangs
+    on.  One process per GPU (torchrun): call it right after torch.cuda.set_device.  Returns a small report
+    ({"cpus": n, "of": total, "numa_nodes": [...]}) or {"skipped": reason}; never raises - on a single-node host (every GPU
+    local to all CPUs) it changes nothing."""
+    import os
+    try:
+        import pynvml
+        import torch
+        idx = torch.cuda.current_device() if device_index is None else int(device_index)
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(idx).uuid)
+        handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (n_cpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus:
+            return {"skipped": "NVML reports no local CPU inside this process's affinity mask"}
+        os.sched_setaffinity(0, cpus)
+        nodes = set()
+        for c in cpus:
+            base = f"/sys/devices/system/cpu/cpu{c}"
+            try:
+                nodes |= {int(n[4:]) for n in os.listdir(base) if n.startswith("node") and n[4:].isdigit()}
+            except OSError:
+                pass
+        return {"cpus": len(cpus), "of": len(allowed), "numa_nodes": sorted(nodes)}
+    except Exception as e:  # noqa: BLE001  (placement is an optimisation: report, never fail the job)
+        return {"skipped": f"{type(e).__name__}: {e}"}

@@ -379,3 +379,14 @@ def test_split_collated_raw_event_batch():
         eb.split_collated(torch.from_numpy(bad))
     with pytest.raises(ValueError):
         eb.from_collated(torch.from_numpy(col), device="cpu")      # an EventBatch lives on the GPU: there is no CPU path
+
+
+def test_bind_to_gpu_cpus_never_raises():
+    """rank placement is an optimisation: without a GPU / NVML it reports why it was skipped and leaves the mask alone"""
+    import os
+    from event_representation_study_b200.sharding import bind_to_gpu_cpus
+    before = os.sched_getaffinity(0)
+    rep = bind_to_gpu_cpus(0)
+    assert isinstance(rep, dict) and ("skipped" in rep or rep["cpus"] >= 1)
+    if "skipped" in rep:
+        assert os.sched_getaffinity(0) == before
