@@ -74,8 +74,16 @@ __global__ void __launch_bounds__(TILE_THREADS) k_event_stack_tile_k(const uint2
   const int b = blockIdx.x / g.T, tile = blockIdx.x - b * g.T;
   const int TP = g.tile_px, pix0 = tile << g.tile_shift, npix = min(TP, g.HW - pix0);
   float4* stage = reinterpret_cast<float4*>(acc + TP);
-  zero_smem(acc, TP);
   const WinParams w = wp[b];
+  const uint32_t count = hist[blockIdx.x];
+  const uint2* rec = records + w.start + base[blockIdx.x];
+  // the thread's first records are requested before the accumulators are cleared: the header -> record dependent chain of
+  // global loads (ncu: 11 warps per issue slot waiting on it) then runs under the zeroing and the barrier
+  constexpr int PRE = 2;
+  uint2 pre[PRE];
+#pragma unroll
+  for (int j = 0; j < PRE; ++j) pre[j] = (uint32_t)(tid + j * TILE_THREADS) < count ? __ldg(rec + tid + j * TILE_THREADS) : make_uint2(0u, 0u);
+  zero_smem(acc, TP);
   if (tid == 0) {
     int64_t c = w.n, st = 0;
     for (int k = 0; k < K; ++k) {
@@ -84,20 +92,21 @@ __global__ void __launch_bounds__(TILE_THREADS) k_event_stack_tile_k(const uint2
       st += c;
     }
   }
-  const uint32_t count = hist[blockIdx.x];
-  const uint2* rec = records + w.start + base[blockIdx.x];
-  __syncthreads();
-  for (uint32_t i = tid; i < count; i += TILE_THREADS) {
-    const uint2 r = __ldg(rec + i);
+  auto feed = [&](const uint2 r) {
     if (FUSED) {  // REC_T_IDX records: the stream index travels in the meta word
-      if (fused_pc(r.y) == 2u) continue;
+      if (fused_pc(r.y) == 2u) return;
       atomicMax(&acc[fused_pix(r.y)], ((fused_idx(r.y) + 1u) << 1) | (fused_pc(r.y) == 1u ? 1u : 0u));
-      continue;
+      return;
     }
-    if (rec_is_null(r.y)) continue;
+    if (rec_is_null(r.y)) return;
     const uint32_t pol = (((r.y >> 24) & 3u) == 1u) ? 1u : 0u;  // p > 0
     atomicMax(&acc[r.y & 0xffffu], ((r.x + 1u) << 1) | pol);
-  }
+  };
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < PRE; ++j)
+    if ((uint32_t)(tid + j * TILE_THREADS) < count) feed(pre[j]);
+  for (uint32_t i = tid + PRE * TILE_THREADS; i < count; i += TILE_THREADS) feed(__ldg(rec + i));
   __syncthreads();
   uint32_t start[K];
 #pragma unroll
@@ -220,38 +229,45 @@ __global__ void __launch_bounds__(TILE_THREADS) k_time_surface_tile_s(const uint
   const int tid = threadIdx.x;
   const int b = blockIdx.x / g.T, tile = blockIdx.x - b * g.T;
   const int TP = g.tile_px, pix0 = tile << g.tile_shift, npix = min(TP, g.HW - pix0);
-  zero_smem(acc, S * 2 * TP);
   const WinParams w = wp[b];
+  const uint32_t count = hist[blockIdx.x];
+  const uint2* rec = records + w.start + base[blockIdx.x];
+  constexpr int PRE = 2;  // first records requested before the accumulators are cleared (see k_event_stack_tile_k)
+  uint2 pre[PRE];
+#pragma unroll
+  for (int j = 0; j < PRE; ++j) pre[j] = (uint32_t)(tid + j * TILE_THREADS) < count ? __ldg(rec + tid + j * TILE_THREADS) : make_uint2(0u, 0u);
+  zero_smem(acc, S * 2 * TP);
   if (tid < S) {
     const int32_t tr = snap[b].t_rel[tid];
     s_trel[tid] = tr;
     s_sidx[tid] = snap[b].idx[tid];
   }
   if (tid == 0) s_nvalid = snap[b].n_valid;
-  const uint32_t count = hist[blockIdx.x];
-  const uint2* rec = records + w.start + base[blockIdx.x];
   const int32_t tmin = w.tmin_rel;
   __syncthreads();
   // untouched pixels: exp((-(3 tau + 1) - t_snapshot) / tau) with the ABSOLUTE snapshot timestamp.  A double-precision exp
   // (~100 dependent instructions) that only the finalise needs: evaluated by S threads while the CTA accumulates instead of
   // ahead of the barrier every warp waits at
   if (tid < S) s_empty[tid] = (float)exp((-(tau * 3.0 + 1.0) - (double)(w.t_base + (int64_t)s_trel[tid])) / tau);
-  for (uint32_t i = tid; i < count; i += TILE_THREADS) {
-    const uint2 r = __ldg(rec + i);
+  auto feed = [&](const uint2 r) {
     if (FUSED) {  // REC_T_IDX records: the first snapshot an event feeds is found from its stream index here
-      if (fused_pc(r.y) == 2u) continue;
+      if (fused_pc(r.y) == 2u) return;
       const int idx = (int)fused_idx(r.y), ns = s_nvalid;
       int sn = 0;
       while (sn < ns && idx > s_sidx[sn]) ++sn;
-      if (sn >= ns) continue;  // after the last emitted surface
+      if (sn >= ns) return;  // after the last emitted surface
       atomicMax(&acc[((uint32_t)sn * 2u + (fused_pc(r.y) == 1u ? 1u : 0u)) * TP + fused_pix(r.y)], (uint32_t)((int32_t)r.x - tmin) + 1u);
-      continue;
+      return;
     }
-    if (rec_is_null(r.y)) continue;
+    if (rec_is_null(r.y)) return;
     const uint32_t sn = (r.y >> 16) & 0xffu;
     const uint32_t plane = (((r.y >> 24) & 3u) == 1u) ? 1u : 0u;
     atomicMax(&acc[(sn * 2u + plane) * TP + (r.y & 0xffffu)], (uint32_t)((int32_t)r.x - tmin) + 1u);
-  }
+  };
+#pragma unroll
+  for (int j = 0; j < PRE; ++j)
+    if ((uint32_t)(tid + j * TILE_THREADS) < count) feed(pre[j]);
+  for (uint32_t i = tid + PRE * TILE_THREADS; i < count; i += TILE_THREADS) feed(__ldg(rec + i));
   __syncthreads();
   const double inv_tau_log2e = 1.4426950408889634 / tau;
   const int nvalid = s_nvalid;
@@ -416,21 +432,23 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tore_tile_k(const uint2* __res
   const int b = blockIdx.x / g.T, tile = blockIdx.x - b * g.T;
   const int TP = g.tile_px, pix0 = tile << g.tile_shift, npix = min(TP, g.HW - pix0);
   float4* stage = reinterpret_cast<float4*>(acc + C * TP);
-  zero_smem(acc, C * TP);
   const WinParams w = wp[b];
   const uint32_t count = hist[blockIdx.x];
   const uint2* rec = records + w.start + base[blockIdx.x];
+  constexpr int PRE = 2;  // first records requested before the accumulators are cleared (see k_event_stack_tile_k)
+  uint2 pre[PRE];
+#pragma unroll
+  for (int j = 0; j < PRE; ++j) pre[j] = (uint32_t)(tid + j * TILE_THREADS) < count ? __ldg(rec + tid + j * TILE_THREADS) : make_uint2(0u, 0u);
+  zero_smem(acc, C * TP);
   const int32_t tmin = w.tmin_rel;
-  __syncthreads();
-  for (uint32_t i = tid; i < count; i += TILE_THREADS) {
-    const uint2 r = __ldg(rec + i);
+  auto feed = [&](const uint2 r) {
     uint32_t plane, pix;
     if (FUSED) {  // REC_T_IDX records: the strict `t < sample time` cut of tore.py:17 is applied here
-      if (fused_pc(r.y) == 2u || (int32_t)r.x >= w.tlast_rel) continue;
+      if (fused_pc(r.y) == 2u || (int32_t)r.x >= w.tlast_rel) return;
       plane = fused_pc(r.y) == 1u ? 0u : 1u;
       pix = fused_pix(r.y);
     } else {
-      if (rec_is_null(r.y)) continue;
+      if (rec_is_null(r.y)) return;
       plane = (((r.y >> 24) & 3u) == 1u) ? 0u : 1u;  // positive first (tore.py:63-65)
       pix = r.y & 0xffffu;
     }
@@ -442,7 +460,12 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tore_tile_k(const uint2* __res
       const uint32_t old = atomicMax(slot + j * TP, v);
       v = min(old, v);
     }
-  }
+  };
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < PRE; ++j)
+    if ((uint32_t)(tid + j * TILE_THREADS) < count) feed(pre[j]);
+  for (uint32_t i = tid + PRE * TILE_THREADS; i < count; i += TILE_THREADS) feed(__ldg(rec + i));
   __syncthreads();
   const float max_time = 500e6f;
   const float log151 = TORE_LOG151;
