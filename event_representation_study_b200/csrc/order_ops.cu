@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_event_stack_tile(const uint2* 
 // consecutive float4: no integer division, no per-element address arithmetic (ncu r01: the generic kernel spent 38
 // instructions per output element and was issue bound at 42 % of the DRAM peak).
 template <int K, bool FUSED>
-__global__ void __launch_bounds__(TILE_THREADS) k_event_stack_tile_k(const uint2* __restrict__ records, const uint32_t* __restrict__ base,
+__global__ void __launch_bounds__(TILE_THREADS, 4) k_event_stack_tile_k(const uint2* __restrict__ records, const uint32_t* __restrict__ base,
                                                                      const uint32_t* __restrict__ hist, const WinParams* __restrict__ wp,
                                                                      const Geom g, float* __restrict__ out) {
   static_assert(K % 4 == 0, "float4 staging");
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_time_surface_tile(const uint2*
 // and the S stores of a thread go to one base pointer plus constant strides (the generic kernel: 62 instructions per
 // output element, issue bound at 23 % of the DRAM peak).
 template <int S, bool FUSED>
-__global__ void __launch_bounds__(TILE_THREADS) k_time_surface_tile_s(const uint2* __restrict__ records, const uint32_t* __restrict__ base,
+__global__ void __launch_bounds__(TILE_THREADS, 4) k_time_surface_tile_s(const uint2* __restrict__ records, const uint32_t* __restrict__ base,
                                                                       const uint32_t* __restrict__ hist, const WinParams* __restrict__ wp,
                                                                       const SnapParams* __restrict__ snap, const Geom g, double tau,
                                                                       float* __restrict__ out) {
