@@ -295,6 +295,26 @@ def bench_gwd(rank, world, dev, steps, with_cpu):
                                "cpu_baseline": {"value": 1.0 / (cpu_q * q * q), "unit": "pairs/s", "kind": "port", "cores": "numpy/BLAS threads",
                                                 "sample": f"one pair at n = {n_e // q}, m = {m_p // q} ({cpu_q:.2f} s), scaled by {q * q} (cost ~ L^2)"},
                                "speedup_vs_cpu_port": cpu_q * q * q / sec_b}
+        # the whole otmi(events, rep, ...) call of one Gen1 sample as gen1_compute.py:96-102 makes it: 50 k events (int32 tensor), a
+        # 240 x 240 x 12 letterboxed representation -> quadrant preparation on the GPU (evrep_otmi_prepare) + three GWD-A pairs
+        from event_representation_study_b200.representations.representation_search.compute_otmi import otmi as otmi_gpu
+        Hs, Ws, Ss = 240, 304, 240
+        ev_s = np.stack([rng.integers(0, Ws, 50_000), rng.integers(0, Hs, 50_000), np.sort(rng.integers(0, 100_000, 50_000)), rng.choice([-1, 1], 50_000)], 1).astype(np.int32)
+        rep_s = rng.random((Ss, Ss, 12)) * 255 * (rng.random((Ss, Ss, 1)) < 0.5)
+        ev_t, rep_t = torch.tensor(ev_s).to(dev), torch.as_tensor(rep_s, device=dev)
+        otmi_gpu(ev_t, rep_t, Hs, Ws, Ss)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            c_gpu = otmi_gpu(ev_t, rep_t, Hs, Ws, Ss)
+            ts.append(time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        eb.otmi_prepare(ev_t, rep_t, Hs, Ws, Ss)
+        prep = time.perf_counter() - t0
+        rec["otmi_call"] = {"call": "otmi(events int32 (50000, 4), rep (240, 240, 12), 240, 304, 240) -> mean GWD-A cost of three quadrants",
+                            "ms_per_sample": float(np.median(ts)) * 1e3, "prepare_ms": prep * 1e3, "cost": c_gpu,
+                            "note": "wall clock including the row-count read-back of the preparation and the final .item()"}
     return rec
 
 

@@ -489,6 +489,46 @@ FILTERS = {"refractory": 0, "contrast": 1, "resize": 2, "background": 3}
 _FILTER_STATE_DTYPE = {"refractory": torch.float64, "contrast": torch.int32, "resize": torch.float32, "background": torch.float64}
 
 
+def otmi_prepare(events, rep, height, width, rep_size):
+    """The data preparation of otmi() (compute_otmi.py:96-203) in eight small kernels (evrep_otmi_prepare): `events` (N, 4)
+    [x, y, t, p], an integer array / tensor (the reference's own call: exact differences, float32 quotients like torch's int / int)
+    or float32 / float64 (the array's precision), `rep`
+    (rep_size, rep_size, C).  -> (pairs, info): pairs = three (Xs (n_i, 4), Xt (m_i, C + 2)) float64 CUDA tensor views, ready
+    for gwd_kernel_l1; info = {"dropped": quadrant, "events_per_quadrant": [...]}.  Raises ValueError when one of the quadrants
+    2..4 is empty (the reference's min() of an empty column)."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    ev = events if torch.is_tensor(events) else torch.as_tensor(np.ascontiguousarray(events))
+    if ev.dtype not in (torch.int32, torch.float32, torch.float64):
+        if ev.dtype.is_floating_point:
+            ev = ev.float()  # half precisions: torch would divide in them; not a case the reference produces
+        else:
+            if ev.numel() and (int(ev.min()) < -2**31 or int(ev.max()) >= 2**31):
+                raise ValueError("integer events outside the int32 range")
+            ev = ev.to(torch.int32)  # torch divides any integer tensor in float32
+    ev_type = {torch.int32: 0, torch.float32: 1, torch.float64: 2}[ev.dtype]
+    ev = ev.to(dev).contiguous()
+    if ev.dim() != 2 or ev.shape[1] != 4:
+        raise ValueError("events must be (N, 4): x, y, t, p")
+    rp = (rep if torch.is_tensor(rep) else torch.as_tensor(np.ascontiguousarray(rep))).to(dev).double().contiguous()
+    if rp.dim() != 3 or rp.shape[0] < rep_size or rp.shape[1] < rep_size:
+        raise ValueError("rep must be (rep_size, rep_size, C)")
+    if rp.shape[0] != rep_size or rp.shape[1] != rep_size:
+        raise ValueError(f"rep is {tuple(rp.shape[:2])}, rep_size says {rep_size}")
+    N, C = int(ev.shape[0]), int(rp.shape[2])
+    cap_s, cap_t = max(N, 1), (rep_size // 2 + 2) ** 2
+    Xs = torch.empty((3, cap_s, 4), dtype=torch.float64, device=dev)
+    Xt = torch.empty((3, cap_t, C + 2), dtype=torch.float64, device=dev)
+    info = np.zeros(12, np.int64)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    ws = _workspace(dev, stream, lib.evrep_otmi_workspace_bytes(N, rep_size))
+    check(lib.evrep_otmi_prepare(ev.data_ptr(), ev_type, N, rp.data_ptr(), rep_size, C, int(height), int(width), Xs.data_ptr(), cap_s,
+                                 Xt.data_ptr(), cap_t, info.ctypes.data, ws.data_ptr(), ws.numel(), stream))
+    if info[7]:
+        raise ValueError("min() arg is an empty sequence")  # compute_otmi.py:140-147 on an empty quadrant
+    pairs = [(Xs[s, :int(info[s])], Xt[s, :int(info[3 + s])]) for s in range(3)]
+    return pairs, {"dropped": int(info[6]), "events_per_quadrant": [int(v) for v in info[8:12]]}
+
+
 def filter_state(kind, B, H, W, device="cuda"):
     """Fresh state for `filter_events`: -inf last timestamps (refractory, background), zero activity (contrast) / change map (resize)."""
     fill = float("-inf") if kind in ("refractory", "background") else 0

@@ -74,6 +74,9 @@ int launch_est_backward(const uint16_t* x, const uint16_t* y, const float* t, co
 int launch_auction(const float* cost, int n, double eps_rel, int* sigma, int* stats, cudaStream_t stream);
 int transport_plan_host(const float* cost, int n, int m, int cap, int* row_ptr, int* col, double* weight, int* nnz_out);
 size_t unpack_workspace_bytes(int B, int64_t total);
+size_t otmi_workspace_bytes(long long N, int R);
+int launch_otmi_prepare(const void* ev, int ev_type, long long N, const double* rep, int R, int C, int height, int width, double* Xs, long long xs_cap,
+                        double* Xt, long long xt_cap, long long* info_host, void* workspace, cudaStream_t stream);
 int launch_unpack(const uint32_t* word, const uint16_t* dt16, const int32_t* tbase, const int64_t* win_offsets_host, int B, int fmt, int xb, int yb,
                   int blk_shift, uint16_t* x, uint16_t* y, int32_t* t, int8_t* p, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 int launch_image_pipeline(const float* rep, int B, int H, int W, int C, int img_size, int mode, int interp, float scale_in, float scale_out,
@@ -620,6 +623,33 @@ int evrep_transport_plan_host(const float* cost, int n, int m, int cap, int* row
   EVREP_GUARD_BEGIN
   if (!cost || !row_ptr || !col || !weight || cap < 1) { set_error("null argument or cap < 1"); return EVREP_EINVAL; }
   return transport_plan_host(cost, n, m, cap, row_ptr, col, weight, nnz);
+  EVREP_GUARD_END
+}
+
+size_t evrep_otmi_workspace_bytes(int64_t n_events, int rep_size) {
+  if (n_events < 0 || rep_size < 1 || rep_size > 65535) return 0;
+  return otmi_workspace_bytes((long long)n_events, rep_size);
+}
+
+int evrep_otmi_prepare(const void* events, int ev_type, int64_t n_events, const double* rep, int rep_size, int C, int height, int width, double* Xs,
+                       int64_t xs_capacity, double* Xt, int64_t xt_capacity, int64_t* info, void* workspace, size_t workspace_bytes,
+                       evrep_stream_t stream) {
+  EVREP_GUARD_BEGIN
+  if (!events || !rep || !Xs || !Xt || !info || !workspace) { set_error("null argument"); return EVREP_EINVAL; }
+  if (ev_type < EVREP_OTMI_INT32 || ev_type > EVREP_OTMI_FLOAT64) { set_error("ev_type must be EVREP_OTMI_INT32 / FLOAT32 / FLOAT64"); return EVREP_EINVAL; }
+  if (n_events < 0 || rep_size < 1 || rep_size > 65535 || C < 1 || C > 62 || height < 2 || width < 2) { set_error("bad otmi geometry"); return EVREP_EINVAL; }
+  const int64_t half = (int64_t)rep_size / 2 + 2;
+  if (xs_capacity < n_events || xt_capacity < half * half) {
+    set_error("otmi: capacity per point set too small (need %lld event rows and %lld pixel rows)", (long long)n_events, (long long)(half * half));
+    return EVREP_EWORKSPACE;
+  }
+  if (workspace_bytes < otmi_workspace_bytes((long long)n_events, rep_size) || (reinterpret_cast<uintptr_t>(workspace) & 255u)) {
+    set_error("otmi: workspace too small or not 256-byte aligned");
+    return EVREP_EWORKSPACE;
+  }
+  static_assert(sizeof(long long) == sizeof(int64_t), "info layout");
+  return launch_otmi_prepare(events, ev_type, (long long)n_events, rep, rep_size, C, height, width, Xs, (long long)xs_capacity, Xt, (long long)xt_capacity,
+                             (long long*)info, workspace, (cudaStream_t)stream);
   EVREP_GUARD_END
 }
 

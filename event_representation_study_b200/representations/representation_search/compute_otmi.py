@@ -48,46 +48,15 @@ class OTMI:
 
 
 def _otmi_pairs(events, rep, height, width, rep_size):
-    """The data preparation of otmi() (reference :96-203) with torch on the GPU: quadrant split, densest quadrant
+    """The data preparation of otmi() (reference :96-203) on the GPU (evrep_otmi_prepare): quadrant split, densest quadrant
     dropped, coordinates normalised, representation cropped with two positional channels, empty pixels removed."""
-    dev = "cuda"
-    ev = torch.as_tensor(np.asarray(events) if not torch.is_tensor(events) else events).to(dev)
-    X, Y = ev[:, 0], ev[:, 1]
-    w2, h2 = width / 2 - 1, height / 2 - 1
-    masks = [(X >= 0) & (X <= w2) & (Y >= 0) & (Y <= h2), (X > w2) & (X <= width - 1) & (Y >= 0) & (Y <= h2),
-             (X >= 0) & (X <= w2) & (Y > h2) & (Y <= height - 1), (X > w2) & (X <= width - 1) & (Y > h2) & (Y <= height - 1)]
-    quads = [ev[m].clone() for m in masks]
-    sizes = [q.shape[0] for q in quads]
-    ind = sizes.index(max(sizes))
-    for q in quads[1:]:
-        if q.shape[0] == 0:
-            raise RuntimeError("min(): Expected reduction dim to be specified for input.numel() == 0")  # what torch raises in the reference
-        q[:, 0] = q[:, 0] - q[:, 0].min()
-        q[:, 1] = q[:, 1] - q[:, 1].min()
-    r = rep_size
-    xys = [([0, r // 2 - 1], [0, r / 2 - 1]), ([r / 2 - 1, r - 1], [0, r / 2 - 1]), ([0, r / 2 - 1], [r / 2 - 1, r - 1]),
-           ([r / 2 - 1, r - 1], [r / 2 - 1, r - 1])]
-    rep_t = torch.as_tensor(np.asarray(rep), device=dev).double()
-    pairs = []
-    for i, q in enumerate(quads):
-        if i == ind:
-            continue
-        x = q[:, 0] / ((width - 1) // 2)
-        y = q[:, 1] / ((height - 1) // 2)
-        t = q[:, 2]
-        t = (t - t[0]) / (t[-1] - t[0])
-        p = q[:, 3]
-        p = (p - p.min()) / (p.max() - p.min())
-        mask = (q[:, 0] < (width - 1) // 2) & (q[:, 1] < (height - 1) // 2)
-        Xs = torch.stack([x[mask], y[mask], t[mask], p[mask]], dim=-1).double()
-        cx, cy = xys[i]
-        rp = rep_t[int(cy[0]): int(cy[1]) + 1, int(cx[0]): int(cx[1]) + 1, :]
-        a, b = rp.shape[0], rp.shape[1]
-        xe = (torch.arange(a, device=dev, dtype=torch.float64) / (a - 1)).reshape(a, 1).expand(a, b)
-        ye = (torch.arange(b, device=dev, dtype=torch.float64) / (b - 1)).reshape(1, b).expand(a, b)
-        rp = torch.cat((rp, xe[..., None], ye[..., None]), dim=2).reshape(-1, rep_t.shape[2] + 2)
-        rp = rp[rp[:, :-2].abs().sum(-1) > 0]
-        pairs.append((Xs, rp))
+    ev = np.asarray(events) if not torch.is_tensor(events) else events
+    if len(ev) == 0:
+        raise ValueError("min() arg is an empty sequence")
+    pairs, info = eb.otmi_prepare(ev, rep, height, width, rep_size)
+    kept = [q for q in range(4) if q != info["dropped"]]
+    if any(info["events_per_quadrant"][q] == 0 for q in kept):
+        raise IndexError("index 0 is out of bounds for axis 0 with size 0")  # t[0] of an empty first quadrant (reference :167)
     return pairs
 
 

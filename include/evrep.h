@@ -28,6 +28,7 @@
  *                                representation_search/gromov_wasserstein.py:72-82 (compute_repr)
  *   evrep_histogram_batched      tonic ToImage (gen1_transforms.py:44-49)
  *   evrep_gwd_kernel_l1          representation_search/compute_otmi.py:50-93 (OTMI.__init__ + solve, GWD-A)
+ *   evrep_otmi_prepare           representation_search/compute_otmi.py:96-203 (otmi: quadrant split, normalisation, crops -> point sets)
  *   evrep_gw_kl                  representation_search/gromov_wasserstein.py:39-69 (OTMI.__init__ + solve, GWD-B:
  *                                POT ot.gromov.gromov_wasserstein(Ks, Kt, p, q, "kl_loss"))
  *   evrep_gemm_nt_3xtf32         the tensor product constC - hC1 T hC2^T inside that solve (POT ot/gromov tensor_product)
@@ -206,6 +207,27 @@ size_t evrep_gwd_workspace_bytes(const int64_t* s_offsets, const int64_t* t_offs
 int evrep_gwd_kernel_l1(const double* Xs, const int64_t* s_offsets, int ds, const double* Xt, const int64_t* t_offsets,
                         int dt, int n_pairs, double h, double* out, void* workspace, size_t workspace_bytes,
                         evrep_stream_t stream);
+
+/* The data preparation of otmi() (compute_otmi.py:96-203) for ONE sample: `events` (DEVICE, n_events x 4 row major [x, y, t,
+ * p]; ev_type EVREP_OTMI_INT32 - what the reference's caller passes, a torch int32 tensor (gen1_compute.py:57-59): exact
+ * integer differences, float32 quotients like torch's int / int - or EVREP_OTMI_FLOAT32 / FLOAT64: the array's own precision) are split
+ * into the four sensor quadrants, the densest is dropped (first maximum), the other three are rebased (not the first), scaled
+ * by (W - 1) // 2 and (H - 1) // 2, their t and p normalised over the quadrant and the rows with rebased x, y below those
+ * divisors kept, in stream order -> Xs, three point sets of 4 float64 columns; `rep` (DEVICE float64, rep_size x rep_size x
+ * C, HWC) is cropped per quadrant (the reference's int() of its float bounds), two positional channels i / (a - 1), j /
+ * (b - 1) are appended and the pixels whose C channels are all zero dropped, in row-major order -> Xt, three point sets of C
+ * + 2 columns.  Point set s (s = 0..2: the kept quadrants in quadrant order) starts at Xs + s * xs_capacity * 4 and Xt +
+ * s * xt_capacity * (C + 2); capacities are in rows (xs_capacity >= n_events, xt_capacity >= (rep_size / 2 + 2)^2).
+ * info (HOST, 12 int64): [0..2] rows of the three Xs, [3..5] rows of the three Xt, [6] the dropped quadrant, [7] 1 + index of
+ * an empty quadrant among 1..3 (the reference raises on it; 0 if none), [8..11] events per quadrant before the final mask.
+ * The call SYNCHRONISES the stream (the caller needs the row counts).  The point sets feed evrep_gwd_kernel_l1 directly. */
+#define EVREP_OTMI_INT32 0
+#define EVREP_OTMI_FLOAT32 1
+#define EVREP_OTMI_FLOAT64 2
+size_t evrep_otmi_workspace_bytes(int64_t n_events, int rep_size);
+int evrep_otmi_prepare(const void* events, int ev_type, int64_t n_events, const double* rep, int rep_size, int C, int height, int width,
+                       double* Xs, int64_t xs_capacity, double* Xt, int64_t xt_capacity, int64_t* info, void* workspace,
+                       size_t workspace_bytes, evrep_stream_t stream);
 
 /* GWD-B for ONE pair: builds the Gaussian kernels Ks (n x n) and Kt (m x m) of Xs (n x ds) and Xt (m x dt) (DEVICE
  * float64, row major, bandwidth h * std as in compute_kernel), then runs conditional-gradient Gromov-Wasserstein with

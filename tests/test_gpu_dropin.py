@@ -266,6 +266,61 @@ def test_otmi_and_OTMI():
     assert_close(Kx, Ky, rtol=1e-12)  # the bandwidth is relative to the matrix' own scale
 
 
+def _otmi_case(seed, N, H, W, S, C):
+    rng = np.random.default_rng(seed)
+    ev = np.stack([rng.integers(0, W, N), rng.integers(0, H, N), np.sort(rng.integers(0, 300000, N)), rng.choice([-1, 1], N)], 1).astype(np.int32)
+    ev[: N // 3, 0] = rng.integers(0, W // 2 - 1, N // 3)  # one quadrant clearly the densest
+    ev[: N // 3, 1] = rng.integers(0, H // 2 - 1, N // 3)
+    rep = rng.random((S, S, C)) * 255.0
+    rep[rng.random((S, S)) < 0.4] = 0.0  # empty pixels are dropped from Xt
+    return ev, rep
+
+
+@pytest.mark.parametrize("seed,N,H,W,S,C", [(1, 3000, 60, 80, 64, 3), (2, 50000, 240, 304, 240, 12), (3, 700, 33, 47, 31, 1)])
+def test_otmi_prepare_matches_the_oracle_pairs(seed, N, H, W, S, C):
+    """evrep_otmi_prepare against oracle/gwd.py::otmi_pairs (itself pinned on compute_otmi.py run unmodified, fixture otmi_small):
+    the reference's own call shape - a torch int32 tensor, so float32 quotients - bit exact, rows in stream / row-major order"""
+    import torch
+    import event_representation_study_b200.batched as eb
+    from oracle import gwd as ogwd
+    ev, rep = _otmi_case(seed, N, H, W, S, C)
+    want = ogwd.otmi_pairs(ev, rep, H, W, S)
+    pairs, info = eb.otmi_prepare(torch.tensor(ev), rep, H, W, S)
+    assert len(pairs) == 3 == len(want) and info["dropped"] == 0 and sum(info["events_per_quadrant"]) <= N
+    for (xs, xt), (ws, wt) in zip(pairs, want):
+        assert xs.dtype == torch.float64 and xs.is_cuda and tuple(xs.shape) == ws.shape and tuple(xt.shape) == wt.shape
+        assert np.array_equal(xs.cpu().numpy(), ws.astype(np.float64), equal_nan=True)
+        assert np.array_equal(xt.cpu().numpy(), wt.astype(np.float64), equal_nan=True)
+
+
+def test_otmi_prepare_float64_events_and_errors():
+    """float64 events divide in float64 (numpy semantics of compute_otmi.py:164-169); an empty quadrant raises like min() does"""
+    import torch
+    import event_representation_study_b200.batched as eb
+    ev, rep = _otmi_case(5, 4000, 60, 80, 64, 2)
+    H, W, S = 60, 80, 64
+    pairs, info = eb.otmi_prepare(ev.astype(np.float64), rep, H, W, S)
+    e = ev.astype(np.float64)
+    X, Y = e[:, 0], e[:, 1]
+    w2, h2 = W / 2 - 1, H / 2 - 1
+    quads = [e[(X >= 0) & (X <= w2) & (Y >= 0) & (Y <= h2)], e[(X > w2) & (X <= W - 1) & (Y >= 0) & (Y <= h2)],
+             e[(X >= 0) & (X <= w2) & (Y > h2) & (Y <= H - 1)], e[(X > w2) & (X <= W - 1) & (Y > h2) & (Y <= H - 1)]]
+    kept = [q for q in range(4) if q != info["dropped"]]
+    assert info["dropped"] == int(np.argmax([len(q) for q in quads]))
+    for (xs, _), qi in zip(pairs, kept):
+        q = quads[qi].copy()
+        if qi:
+            q[:, 0] -= q[:, 0].min()
+            q[:, 1] -= q[:, 1].min()
+        t, p = q[:, 2], q[:, 3]
+        m = (q[:, 0] < (W - 1) // 2) & (q[:, 1] < (H - 1) // 2)
+        want = np.stack([q[:, 0] / ((W - 1) // 2), q[:, 1] / ((H - 1) // 2), (t - t[0]) / (t[-1] - t[0]), (p - p.min()) / (p.max() - p.min())], -1)[m]
+        assert np.array_equal(xs.cpu().numpy(), want)
+    lone = ev[(ev[:, 0] <= W / 2 - 1) | (ev[:, 1] <= H / 2 - 1)]  # nothing in the fourth quadrant
+    with pytest.raises(ValueError):
+        eb.otmi_prepare(torch.tensor(lone), rep, H, W, S)
+
+
 def test_compute_repr():
     from event_representation_study_b200.representations.representation_search.gromov_wasserstein import compute_repr
     g = load(golden("voxel_gwd_small")[0][1])

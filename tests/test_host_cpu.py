@@ -390,3 +390,12 @@ def test_bind_to_gpu_cpus_never_raises():
     assert isinstance(rep, dict) and ("skipped" in rep or rep["cpus"] >= 1)
     if "skipped" in rep:
         assert os.sched_getaffinity(0) == before
+
+
+def test_otmi_prepare_validates_before_touching_cuda(L):
+    """evrep_otmi_prepare: argument checks return EVREP_E* codes without a device"""
+    lib = L.lib
+    assert lib.evrep_otmi_workspace_bytes(-1, 64) == 0 and lib.evrep_otmi_workspace_bytes(1000, 0) == 0
+    assert lib.evrep_otmi_workspace_bytes(50000, 240) > 0
+    assert lib.evrep_otmi_prepare(0, 0, 10, 0, 64, 3, 60, 80, 0, 10, 0, 2000, 0, 0, 0, 0) == L.EINVAL  # null pointers
+    assert b"null" in lib.evrep_last_error()
