@@ -15,4 +15,29 @@ A = torch.rand(200, 77, device="cuda"); B = torch.rand(130, 77, device="cuda"); 
 rng = np.random.default_rng(0); Xs = rng.random((40, 4)); Xt = rng.random((40, 6))
 print(eb.gw_kl(Xs, Xt, 0.7, max_iter=5))
 print(eb.gwd_kernel_l1([Xs], [Xt], 0.7))
+# round 2: fused order ops, sub-pixel voxel grid, packed wire format, rectangular GWD-B, EST forward / backward, filters, otmi preparation,
+# the N-ImageNet rank loaders, a CUDA-graph replay (programmatic dependent launches inside a capture)
+eb.order_ops_fused(ev, H, W)
+eb.voxel_grid(ev, H, W, 5, "evlicious", normalize=True, divider=2)
+from event_representation_study_b200 import packed, est
+hx = {k: getattr(ev, k).cpu().numpy() for k in "xytp"}
+pk = packed.pack_host(hx["x"].view(np.uint16), hx["y"].view(np.uint16), hx["t"], hx["p"], ev.offsets, H, W)
+if pk is not None:
+    eb.ergo12(packed.upload(pk), H, W)
+print(eb.gw_kl(rng.random((30, 4)), rng.random((45, 6)), 0.7, max_iter=4))
+ws_ = [rng.standard_normal((8, 1)), rng.standard_normal((8, 8)), rng.standard_normal((1, 8))]
+bs_ = [rng.standard_normal(8), rng.standard_normal(8), rng.standard_normal(1)]
+tabs = tuple(torch.as_tensor(v, dtype=torch.float64, device="cuda") for v in est.compile_value_layer(ws_, bs_))
+tn = (ev.t.double() / float(ev.t.max())).float()
+q = est.quantize(ev, H, W, 4, tabs, t_float=tn)
+for kind, prm in (("refractory", 500.0), ("contrast", 2.0), ("resize", 0.0)):
+    eb.filter_events(ev, H, W, kind, prm, fx=2 if kind == "resize" else 1, fy=2 if kind == "resize" else 1)
+eo = np.stack([rng.integers(0, W, 4000), rng.integers(0, H, 4000), np.sort(rng.integers(0, 9000, 4000)), rng.choice([-1, 1], 4000)], 1).astype(np.int32)
+eb.otmi_prepare(torch.tensor(eo), rng.random((64, 64, 3)) * (rng.random((64, 64, 1)) < 0.5), H, W, 64)
+import event_representation_study_b200.n_imagenet as nimg
+en = torch.tensor(np.stack([rng.integers(0, 32, 3000).astype(float), rng.integers(0, 24, 3000).astype(float), np.sort(rng.random(3000)) * 0.04 + 1.0, rng.choice([-1.0, 1.0], 3000)], 1))
+nimg.reshape_then_acc_adj_sort(en, height=24, width=32)
+out_g = torch.empty((ev.B, H, W, 12), device="cuda")
+call = eb.GraphedCall(lambda: eb.ergo12(ev, H, W, out=out_g))
+call.replay(); call.replay()
 torch.cuda.synchronize(); print("sanitizer workload done")
