@@ -686,7 +686,7 @@ def main():
     ap.add_argument("--windows", type=int, default=32, help="windows per GPU")
     ap.add_argument("--events", type=int, default=1_000_000, help="events per window")
     ap.add_argument("--clustered", action="store_true", help="80%% of the events on 5%% of the pixels (contention stress; not the headline)")
-    ap.add_argument("--e2e-groups", type=int, default=4, help="window groups per step in the end-to-end leg (copy/compute overlap)")
+    ap.add_argument("--e2e-groups", type=int, default=2, help="window groups per step in the end-to-end leg (copy/compute overlap)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--no-extras", action="store_true", help="headline + e2e only: skip the gwd / configs / parity_spot_check / dropin records")
     a = ap.parse_args()
