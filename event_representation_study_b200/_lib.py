@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libevrep.so")
 
 # return codes (include/evrep.h)
 OK, EINVAL, EWORKSPACE, ECUDA, EUNSUPPORTED = 0, -1, -2, -3, -4
+MAX_TILES = 4096  # csrc/evrep_common.cuh: buckets per window
 OP_MIXED_DENSITY, OP_EVENT_STACK, OP_TIME_SURFACE, OP_TORE, OP_VOXEL, OP_HISTOGRAM, OP_FILTER = 1, 2, 3, 4, 5, 6, 7
 FUNCS = {"timestamp": 0, "polarity": 1, "count": 2, "timestamp_pos": 3, "timestamp_neg": 4, "count_pos": 5, "count_neg": 6}
 AGGS = {"sum": 0, "mean": 1, "max": 2, "variance": 3, "min": 4}

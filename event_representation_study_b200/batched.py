@@ -272,9 +272,14 @@ def tore(ev, H, W, k=6, out=None):
 
 def order_ops_fused(ev, H, W, tau=50000.0, out=None):
     """BASELINE configs[2] in one call: (EventStack(12) (B, H, W, 12), TimeSurface(6 snapshots) (B, 6, 2, H, W), TORE(k=6)
-    (B, H, W, 12)) from a single bucketing pass; each equals the separate call bit for bit.  Windows < 2^20 events."""
-    head, ws, stream = _prep(ev, _lib.OP_TORE, H, W, 12)
+    (B, H, W, 12)) from a single bucketing pass; each equals the separate call bit for bit.  The fused record carries a 20-bit
+    stream index and a 10-bit pixel: a batch with a window of 2^20 events or more, or a sensor too large for 1024-pixel tiles,
+    is served by the three separate calls instead (same outputs, two more bucketing passes)."""
     es, ts, tr = out if out is not None else (None, None, None)
+    n_max = int(np.diff(ev.offsets).max()) if ev.B else 0
+    if n_max >= (1 << 20) or H * W > 1024 * _lib.MAX_TILES:
+        return event_stack(ev, H, W, 12, out=es), time_surface(ev, H, W, 6, tau, out=ts), tore(ev, H, W, 6, out=tr)
+    head, ws, stream = _prep(ev, _lib.OP_TORE, H, W, 12)
     es = _out(ev, (ev.B, H, W, 12), es)
     ts = _out(ev, (ev.B, 6, 2, H, W), ts)
     tr = _out(ev, (ev.B, H, W, 12), tr)

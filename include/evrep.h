@@ -296,7 +296,8 @@ int evrep_gemm_nt_3xtf32(const float* A, const float* B, float* C, int M, int N,
  * square with pad_value (114) like letterbox(auto=False, scaleup=False); mode EVREP_IMG_SQUASH: precompute_reps.py -
  * resize straight to img_size x img_size.  interp EVREP_INTERP_AUTO follows the reference (INTER_AREA when r < 1, the
  * non-augmented branch, else INTER_LINEAR); the arithmetic follows cv::resize on float images tap for tap.
- * INTER_AREA is implemented for shrinking axes with scale <= 4 (EVREP_EUNSUPPORTED otherwise). */
+ * INTER_AREA is implemented for shrinking axes at any factor (tap tables up to 4, taps generated on the fly beyond); an
+ * enlarging axis, where cv::resize switches to a linear variant, returns EVREP_EUNSUPPORTED. */
 #define EVREP_IMG_LETTERBOX 0
 #define EVREP_IMG_SQUASH 1
 #define EVREP_INTERP_AUTO 0

@@ -71,13 +71,20 @@ def test_image_pipeline_feeds_from_the_representation(E):
 
 def test_image_pipeline_rejects_what_it_does_not_mirror(E):
     import torch
-    from event_representation_study_b200._lib import EvrepError, EUNSUPPORTED
-    t = torch.zeros((1, 64, 2000, 12), device="cuda")
-    with pytest.raises(EvrepError) as e:  # scale 2000 / 64 > 4
-        E.detector_input(t, 64, mode="letterbox")
-    assert e.value.code == EUNSUPPORTED
     with pytest.raises(ValueError):
         E.detector_input(torch.zeros((1, 8, 8, 12)), 16)
+
+
+@pytest.mark.parametrize("H,W,S,mode", [(64, 2000, 64, "letterbox"), (720, 1280, 96, "squash"), (720, 1280, 100, "letterbox"), (333, 517, 31, "squash")])
+def test_image_pipeline_large_inter_area_scales(E, H, W, S, mode):
+    """INTER_AREA at any shrink factor (round 1 stopped at 4): taps are generated on the fly, 31 x per axis here"""
+    import torch
+    from oracle import image_pipeline as oimg
+    rng = np.random.default_rng(H + W + S)
+    rep = (rng.random((2, H, W, 12)) * (rng.random((2, H, W, 12)) < 0.5)).astype(np.float32)
+    got = E.detector_input(torch.as_tensor(rep).cuda(), S, mode=mode).cpu().numpy()
+    for b in range(2):
+        assert_close(got[b], oimg.detector_input(rep[b], S, mode), rtol=1e-5, atol=ATOL, what=f"window {b}")
 
 
 def test_image_pipeline_empty_batch_and_single_pixel(E):

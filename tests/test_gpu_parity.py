@@ -484,12 +484,15 @@ def test_order_ops_fused_equals_the_separate_calls(E, H, W, sizes):
     assert np.array_equal(np_(tr), np_(E.tore(ev, H, W, 6)))
 
 
-def test_order_ops_fused_rejects_windows_of_2_pow_20_events(E):
-    from event_representation_study_b200._lib import EvrepError, EUNSUPPORTED
+def test_fused_c_entry_point_rejects_windows_of_2_pow_20_events(E):
+    """the C entry point itself reports the limit of its record format (the Python wrapper falls back to three calls)"""
+    import torch
+    from event_representation_study_b200 import _lib
     ev = E.pack_events(streams(64, 64, [1 << 20], 3), "cuda")
-    with pytest.raises(EvrepError) as e:
-        E.order_ops_fused(ev, 64, 64)
-    assert e.value.code == EUNSUPPORTED
+    head, ws, stream = E._prep(ev, _lib.OP_TORE, 64, 64, 12)
+    outs = [torch.empty(n, device="cuda") for n in (64 * 64 * 12, 6 * 2 * 64 * 64, 64 * 64 * 12)]
+    rc = _lib.lib.evrep_order_ops_fused_batched(*head, 50000.0, outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), ws.data_ptr(), ws.numel(), stream)
+    assert rc == _lib.EUNSUPPORTED and b"2^20" in _lib.lib.evrep_last_error()
 
 
 def test_unaligned_event_arrays_take_the_scalar_load_path(E):
@@ -532,3 +535,21 @@ def test_graphed_call_replays_the_same_result(E):
     want2 = E.ergo12(ev, H, W).clone()
     assert not torch.equal(want2, want)
     assert torch.equal(g.replay(), want2)
+
+
+def test_order_ops_fused_falls_back_for_huge_windows(cuda_device):
+    """a window of 2^20 events or more does not fit the fused record's 20 index bits: the wrapper serves it with the three
+    separate calls, bit-identical to them by construction; checked against the oracle's event stack on the big window"""
+    import torch
+    import event_representation_study_b200.batched as eb
+    from event_representation_study_b200.synth import poisson_window
+    from oracle import representations as orep
+    H, W = 96, 128
+    wins = [poisson_window(31, (1 << 20) + 5, H, W), poisson_window(32, 4000, H, W)]
+    ev = eb.pack_events(wins, "cuda")
+    es, ts, tr = eb.order_ops_fused(ev, H, W)
+    assert tuple(es.shape) == (2, H, W, 12) and tuple(ts.shape) == (2, 6, 2, H, W) and tuple(tr.shape) == (2, H, W, 12)
+    assert torch.equal(es, eb.event_stack(ev, H, W, 12)) and torch.equal(tr, eb.tore(ev, H, W, 6))
+    w = wins[0]
+    want = orep.event_stack(w["x"], w["y"], w["t"], (w["p"].astype(np.int32) + 1) // 2, H, W, 12)
+    assert np.array_equal(es[0].cpu().numpy(), want)
