@@ -158,6 +158,37 @@ def main():
                               "cpu_baseline": {"value": 1.0 / c, "unit": "windows/s", "cores": 1, "kind": "reference",
                                                "sample": f"{n} windows, cv2 resize + letterbox + transpose per window (oracle/image_pipeline.py around cv2)"}}), flush=True)
 
+        # the training branch: the same pipeline with INTER_LINEAR, then random_affine's warpAffine + flips (gen1_2yolo.py:365-391)
+        import math
+        H, W, B, S = 240, 304, 256, 640
+        rep = torch.rand((B, H, W, 12), device=dev) * (torch.rand((B, H, W, 12), device=dev) < 0.3)
+        lb = torch.empty((B, 12, S, S), device=dev)
+        out = torch.empty((B, 12, S, S), device=dev)
+        rng = np.random.default_rng(4)
+        Ms = np.tile(np.eye(3), (B, 1, 1))
+        for b in range(B):
+            ang, sc = math.radians(rng.uniform(-10, 10)), rng.uniform(0.9, 1.1)
+            R = np.array([[math.cos(ang) * sc, math.sin(ang) * sc, 0], [-math.sin(ang) * sc, math.cos(ang) * sc, 0], [0, 0, 1.0]])
+            Cm, T = np.eye(3), np.eye(3)
+            Cm[:2, 2] = -S / 2
+            T[:2, 2] = rng.uniform(0.4, 0.6, 2) * S
+            Ms[b] = T @ R @ Cm
+        ud, lr = rng.random(B) < 0.5, rng.random(B) < 0.5
+
+        def aug():
+            eb.detector_input(rep, S, interp="linear", scale_out=1.0, reverse_channels=False, out=lb)
+            return eb.augment_affine(lb, Ms, ud, lr, out=out)
+        sec = timed(aug, a.steps)
+        one = rep[0].cpu().numpy()
+        c, n = cpu_time(lambda i: oimg.augmented_detector_input(one, S, Ms[0], bool(ud[0]), bool(lr[0])), 4.0, 20)
+        alg = B * (H * W * 12 * 4 + 12 * S * S * 4)
+        print(json.dumps({"workload": f"image pipeline, training branch: Gen1 -> 640 INTER_LINEAR + letterbox + random_affine (cv2.warpAffine) + flips, batch {B}, 12 channels",
+                          "value": B / sec, "unit": "windows/s", "ms_per_step": sec * 1e3,
+                          "roofline": {"bound": "hbm", "achieved": alg / sec / 1e9, "peak": peak(), "unit": "GB/s", "frac": alg / sec / 1e9 / peak(),
+                                       "algorithmic_bytes_per_step": alg, "note": "two kernels: the letterboxed image makes one extra round trip through HBM (2 x 12 x 640 x 640 x 4 B per window)"},
+                          "cpu_baseline": {"value": 1.0 / c, "unit": "windows/s", "cores": 1, "kind": "reference",
+                                           "sample": f"{n} windows, cv2 resize + letterbox + warpAffine + flips + transpose per window (oracle/image_pipeline.py around cv2)"}}), flush=True)
+
     if "est" in only:  # the learned EST quantisation layer, forward (dim = (6, 240, 304), image 640: yolo.py:56-61)
         import event_representation_study_b200.est as est
         from oracle import est as oest

@@ -61,6 +61,7 @@ SIGNATURES = {
     "evrep_otmi_prepare": (_i, [_vp, _i, _i64, _vp, _i, _i, _i, _i, _vp, _i64, _vp, _i64, _vp, _vp, _sz, _vp]),
     "evrep_gemm_workspace_bytes": (_sz, [_i, _i, _i]),
     "evrep_gemm_nt_3xtf32": (_i, [_vp, _vp, _vp, _i, _i, _i, _c.c_float, _vp, _vp, _vp, _sz, _vp]),
+    "evrep_warp_affine_batched": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _c.c_float, _vp, _vp]),
     "evrep_image_pipeline_batched": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _c.c_float, _c.c_float, _c.c_float, _i, _vp, _vp]),
 }
 

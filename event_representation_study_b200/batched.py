@@ -429,6 +429,38 @@ def detector_input(rep, img_size=640, mode="letterbox", interp="auto", scale_in=
     return out
 
 
+def augment_affine(img, M, flip_ud=None, flip_lr=None, out_size=None, border=(114.0, 114.0, 114.0, 0.0), reverse_channels=True, scale_out=1.0 / 255.0,
+                   out=None):
+    """The training-time augmentation of the detector datasets on a batch (gen1_2yolo.py:365-391): random_affine's
+    cv2.warpAffine (data_augment.py:110-123, arithmetic of cv::warpAffine INTER_LINEAR reproduced tap for tap) and the flips of
+    general_augment (:210-228), then CHW channel reversal and / 255.  img: (B, C, h, w) float32 CUDA planes - detector_input(...,
+    scale_out=1.0, reverse_channels=False) gives exactly the letterboxed image the reference warps; M: (B, 2, 3) or (B, 3, 3)
+    FORWARD matrices as get_transform_matrix returns them (the caller draws the random numbers, as it does for the labels);
+    flip_ud / flip_lr: per-window booleans.  `border` is what cv2 makes of borderValue=(114, 114, 114): channel k is padded
+    with border[k & 3], i.e. every fourth channel with 0.  -> (B, C, out_size, out_size)."""
+    if not img.is_cuda:
+        raise ValueError("augment_affine needs a CUDA tensor (there is no CPU path)")
+    img = img.contiguous().float()
+    B, C, h, w = img.shape
+    Mh = np.ascontiguousarray(np.asarray(M, np.float64).reshape(B, -1, 3)[:, :2, :].reshape(B, 6))
+    flips = np.zeros(B, np.int32)
+    if flip_ud is not None:
+        flips |= np.asarray(flip_ud, bool).astype(np.int32)
+    if flip_lr is not None:
+        flips |= np.asarray(flip_lr, bool).astype(np.int32) << 1
+    oh, ow = (h, w) if out_size is None else ((out_size, out_size) if np.isscalar(out_size) else tuple(out_size))
+    if out is None:
+        out = torch.empty((B, C, oh, ow), dtype=torch.float32, device=img.device)
+    b4 = np.asarray(border, np.float32)
+    if b4.shape != (4,):
+        raise ValueError("border must have four entries (cv2's scalar)")
+    _require_current(img.device)
+    stream = torch.cuda.current_stream(img.device).cuda_stream
+    check(lib.evrep_warp_affine_batched(img.data_ptr(), B, C, h, w, Mh.ctypes.data, flips.ctypes.data, int(oh), int(ow), b4.ctypes.data,
+                                        1 if reverse_channels else 0, float(scale_out), out.data_ptr(), stream))
+    return out
+
+
 def assignment_auction(cost, eps_rel=1e-9):
     """Min-cost assignment of a square float32 CUDA matrix on the GPU (the LMO of gw_kl) -> (sigma int32 CUDA tensor,
     stats dict).  Optimal up to n * eps_rel * (cost range)."""

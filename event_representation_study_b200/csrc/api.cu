@@ -8,6 +8,8 @@
 #include <new>
 #include <vector>
 
+#include <cmath>
+
 #include "evrep_common.cuh"
 
 namespace evrep {
@@ -74,6 +76,8 @@ int launch_est_backward(const uint16_t* x, const uint16_t* y, const float* t, co
 int launch_auction(const float* cost, int n, double eps_rel, int* sigma, int* stats, cudaStream_t stream);
 int transport_plan_host(const float* cost, int n, int m, int cap, int* row_ptr, int* col, double* weight, int* nnz_out);
 size_t unpack_workspace_bytes(int B, int64_t total);
+int launch_warp_affine(const float* in, int B, int C, int in_h, int in_w, const double* M_host, const int* flips_host, int out_h, int out_w,
+                       const float* border4, int reverse, float scale_out, float* out, cudaStream_t stream);
 size_t otmi_workspace_bytes(long long N, int R);
 int launch_otmi_prepare(const void* ev, int ev_type, long long N, const double* rep, int R, int C, int height, int width, double* Xs, long long xs_cap,
                         double* Xt, long long xt_cap, long long* info_host, void* workspace, cudaStream_t stream);
@@ -623,6 +627,21 @@ int evrep_transport_plan_host(const float* cost, int n, int m, int cap, int* row
   EVREP_GUARD_BEGIN
   if (!cost || !row_ptr || !col || !weight || cap < 1) { set_error("null argument or cap < 1"); return EVREP_EINVAL; }
   return transport_plan_host(cost, n, m, cap, row_ptr, col, weight, nnz);
+  EVREP_GUARD_END
+}
+
+int evrep_warp_affine_batched(const float* img, int B, int C, int in_h, int in_w, const double* M, const int* flips, int out_h, int out_w,
+                              const float* border4, int reverse_channels, float scale_out, float* out, evrep_stream_t stream) {
+  EVREP_GUARD_BEGIN
+  if (B < 0 || C < 1 || C > 4096 || in_h < 1 || in_w < 1 || out_h < 1 || out_w < 1 || in_h > 32767 || in_w > 32767 || out_h > 65535 || out_w > 65535) {
+    set_error("bad warp geometry");
+    return EVREP_EINVAL;
+  }
+  if (B == 0) return EVREP_OK;
+  if (!img || !M || !border4 || !out) { set_error("null argument"); return EVREP_EINVAL; }
+  for (int64_t k = 0; k < (int64_t)B * 6; ++k)
+    if (!std::isfinite(M[k])) { set_error("warp matrix %lld has a non-finite entry", (long long)(k / 6)); return EVREP_EINVAL; }
+  return launch_warp_affine(img, B, C, in_h, in_w, M, flips, out_h, out_w, border4, reverse_channels, scale_out, out, (cudaStream_t)stream);
   EVREP_GUARD_END
 }
 

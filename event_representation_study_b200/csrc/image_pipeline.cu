@@ -14,6 +14,8 @@
 // C S S 4 bytes per window.  The OpenCV arithmetic is followed tap for tap (float32 weights computed from the double
 // scale as cv::resize does: half-pixel centres and border clamping for INTER_LINEAR, the cell-overlap table of
 // computeResizeAreaTab for INTER_AREA).
+#include <string.h>
+
 #include "evrep_common.cuh"
 
 namespace evrep {
@@ -262,6 +264,95 @@ int launch_image_pipeline(const float* rep, int B, int H, int W, int C, int img_
   else
     k_image_pipeline<0><<<grid, 256, 0, stream>>>(rep, a, out);
   EVREP_CUDA_OK(cudaGetLastError());
+  return EVREP_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The training-time augmentation that follows the letterbox (gen1_2yolo.py:365-391): random_affine = cv2.warpAffine(img,
+// M[:2], dsize, borderValue=(114, 114, 114)) (data_augment.py:110-123), then the up-down / left-right flips of general_augment
+// (:210-228).  The random draws (get_transform_matrix, the flip coins) stay with the caller, like the label bookkeeping; this
+// is the image side.  cv::warpAffine with INTER_LINEAR on a float image: the matrix is inverted in double, destination
+// coordinates are mapped in FIXED POINT (10 fractional bits, rounded to 1/32 pixel), the four taps are blended with float
+// weights from a 32 x 32 table, accumulated in double; taps outside the image take the border value of their channel, and
+// the 3-entry borderValue tuple becomes a 4-entry scalar that channel k indexes with k & 3 - so every fourth channel of a
+// 12-channel representation is padded with 0, not 114.  A numpy restatement of exactly this agrees with cv2 4.13 to the last
+// bit on float64 images (oracle/image_pipeline.py::warp_affine_restated, checked there against cv2 itself).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int WARP_MAX_WINDOWS = 64;  // per launch: the per-window matrices travel as kernel arguments
+struct WarpParams {
+  double m[WARP_MAX_WINDOWS][6];  // inverse maps (destination -> source), as cv::warpAffine computes them
+  int flip[WARP_MAX_WINDOWS];     // bit 0: up-down, bit 1: left-right (applied after the warp)
+  float border[4];
+  int C, in_h, in_w, out_h, out_w, reverse;
+  float scale_out;
+};
+
+__global__ void __launch_bounds__(256) k_warp_affine(const float* __restrict__ in, const __grid_constant__ WarpParams p, float* __restrict__ out) {
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  const int oy = blockIdx.y, b = blockIdx.z;
+  if (ox >= p.out_w) return;
+  // the flips act on the warped image: output pixel (oy, ox) is warped pixel (y, x)
+  const int y = (p.flip[b] & 1) ? p.out_h - 1 - oy : oy;
+  const int x = (p.flip[b] & 2) ? p.out_w - 1 - ox : ox;
+  const double* M = p.m[b];
+  // imgwarp.cpp WarpAffineInvoker: AB_BITS = 10, round_delta = AB_SCALE / INTER_TAB_SIZE / 2 = 16; saturate_cast<int>(double)
+  // rounds half to even; the products must not be contracted into FMAs (the CPU code is not)
+  const int adelta = __double2int_rn(__dmul_rn(__dmul_rn(M[0], (double)x), 1024.0));
+  const int bdelta = __double2int_rn(__dmul_rn(__dmul_rn(M[3], (double)x), 1024.0));
+  const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(M[1], (double)y), M[2]), 1024.0)) + 16;
+  const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(M[4], (double)y), M[5]), 1024.0)) + 16;
+  const int X = (X0 + adelta) >> 5, Y = (Y0 + bdelta) >> 5;
+  const int sx = max(-32768, min(32767, X >> 5)), sy = max(-32768, min(32767, Y >> 5));  // saturate_cast<short>
+  const float fx = (float)(X & 31) * (1.f / 32.f), fy = (float)(Y & 31) * (1.f / 32.f);
+  const float w00 = __fmul_rn(1.f - fy, 1.f - fx), w01 = __fmul_rn(1.f - fy, fx), w10 = __fmul_rn(fy, 1.f - fx), w11 = __fmul_rn(fy, fx);
+  const bool x0 = sx >= 0 && sx < p.in_w, x1 = sx + 1 >= 0 && sx + 1 < p.in_w;
+  const bool y0 = sy >= 0 && sy < p.in_h, y1 = sy + 1 >= 0 && sy + 1 < p.in_h;
+  const size_t in_plane = (size_t)p.in_h * p.in_w, out_plane = (size_t)p.out_h * p.out_w;
+  const float* src = in + (size_t)b * p.C * in_plane;
+  float* dst = out + (size_t)b * p.C * out_plane + (size_t)oy * p.out_w + ox;
+  const size_t o00 = (size_t)(y0 ? sy : 0) * p.in_w + (x0 ? sx : 0), o01 = (size_t)(y0 ? sy : 0) * p.in_w + (x1 ? sx + 1 : 0);
+  const size_t o10 = (size_t)(y1 ? sy + 1 : 0) * p.in_w + (x0 ? sx : 0), o11 = (size_t)(y1 ? sy + 1 : 0) * p.in_w + (x1 ? sx + 1 : 0);
+  for (int c = 0; c < p.C; ++c) {
+    const float* pl = src + (size_t)c * in_plane;
+    const float bv = p.border[c & 3];
+    const double v00 = (y0 && x0) ? (double)__ldg(pl + o00) : (double)bv, v01 = (y0 && x1) ? (double)__ldg(pl + o01) : (double)bv;
+    const double v10 = (y1 && x0) ? (double)__ldg(pl + o10) : (double)bv, v11 = (y1 && x1) ? (double)__ldg(pl + o11) : (double)bv;
+    // remapBilinear<Cast<double, double>, ..., float>: S[0] * w[0] + S[1] * w[1] + S[step] * w[2] + S[step + 1] * w[3] in double
+    const double sum = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(v00, (double)w00), __dmul_rn(v01, (double)w01)), __dmul_rn(v10, (double)w10)), __dmul_rn(v11, (double)w11));
+    __stcs(dst + (size_t)(p.reverse ? p.C - 1 - c : c) * out_plane, (float)sum * p.scale_out);
+  }
+}
+
+// in: DEVICE float32 (B, C, in_h, in_w); M_host: B x 6 doubles, the FORWARD matrices handed to cv2.warpAffine (rows of M[:2]);
+// flips_host: B ints (bit 0 up-down, bit 1 left-right) or NULL
+int launch_warp_affine(const float* in, int B, int C, int in_h, int in_w, const double* M_host, const int* flips_host, int out_h, int out_w,
+                       const float* border4, int reverse, float scale_out, float* out, cudaStream_t stream) {
+  for (int b0 = 0; b0 < B; b0 += WARP_MAX_WINDOWS) {
+    const int nb = B - b0 < WARP_MAX_WINDOWS ? B - b0 : WARP_MAX_WINDOWS;
+    WarpParams p;
+    memset(&p, 0, sizeof(p));
+    for (int b = 0; b < nb; ++b) {
+      // cv::warpAffine without WARP_INVERSE_MAP (imgwarp.cpp): the inverse of the 2 x 3 map, in double, in this operation order
+      double M[6];
+      for (int k = 0; k < 6; ++k) M[k] = M_host[(size_t)(b0 + b) * 6 + k];
+      double D = M[0] * M[4] - M[1] * M[3];
+      D = D != 0 ? 1. / D : 0;
+      const double A11 = M[4] * D, A22 = M[0] * D;
+      M[0] = A11; M[1] *= -D;
+      M[3] *= -D; M[4] = A22;
+      const double b1 = -M[0] * M[2] - M[1] * M[5];
+      const double b2 = -M[3] * M[2] - M[4] * M[5];
+      M[2] = b1; M[5] = b2;
+      for (int k = 0; k < 6; ++k) p.m[b][k] = M[k];
+      p.flip[b] = flips_host ? flips_host[b0 + b] : 0;
+    }
+    for (int k = 0; k < 4; ++k) p.border[k] = border4[k];
+    p.C = C; p.in_h = in_h; p.in_w = in_w; p.out_h = out_h; p.out_w = out_w; p.reverse = reverse; p.scale_out = scale_out;
+    dim3 grid((unsigned)((out_w + 255) / 256), (unsigned)out_h, (unsigned)nb);
+    k_warp_affine<<<grid, 256, 0, stream>>>(in + (size_t)b0 * C * in_h * in_w, p, out + (size_t)b0 * C * out_h * out_w);
+    EVREP_CUDA_OK(cudaGetLastError());
+  }
   return EVREP_OK;
 }
 

@@ -38,6 +38,8 @@
  *                                tools/filters.py:57-69 (BackgroundActivity.insert)
  *   evrep_est_quantize_batched   ev-YOLOv6/yolov6/models/learned_repr.py:143-172 (QuantizationLayer.forward);
  *   evrep_est_backward_batched   its backward pass with respect to the ValueLayer weights (:9-77 under autograd)
+ *   evrep_warp_affine_batched    ev-YOLOv6/yolov6/data/data_augment.py:110-123 (random_affine: cv2.warpAffine) + gen1_2yolo.py:210-228
+ *                                (general_augment: flips), the training-time augmentation between letterbox and CHW (gen1_2yolo.py:365-391)
  *   evrep_image_pipeline_batched ev-YOLOv6/yolov6/data/gen1_2yolo.py:230-265,321-341,397 (resize_image, letterbox, CHW + reversal),
  *                                gen4/precompute_reps.py:216-251 (resize_image_process), yolov6/core/engine.py:629-635 (/ 255)
  */
@@ -306,6 +308,19 @@ int evrep_gemm_nt_3xtf32(const float* A, const float* B, float* C, int M, int N,
 #define EVREP_INTERP_LINEAR_TORCH 3 /* torch interpolate(bilinear, align_corners=False) arithmetic + letterbox_image_batch placement (learned_repr.py:94-141) */
 int evrep_image_pipeline_batched(const float* rep, int B, int H, int W, int C, int img_size, int mode, int interp, float scale_in,
                                  float scale_out, float pad_value, int reverse_channels, float* out, evrep_stream_t stream);
+
+/* The training-time augmentation between the letterbox and the CHW transpose (gen1_2yolo.py:365-391): random_affine's
+ * cv2.warpAffine(img, M[:2], dsize=(out_w, out_h), borderValue=(114, 114, 114)) (data_augment.py:110-123), then the flips of
+ * general_augment (gen1_2yolo.py:210-228).  img: DEVICE float32 (B, C, in_h, in_w) planes - what evrep_image_pipeline_batched
+ * writes with reverse_channels = 0 and scale_out = 1; out: DEVICE float32 (B, C, out_h, out_w) = warped, flipped, channel
+ * order reversed if asked (the `[::-1]` of gen1_2yolo.py:397), times scale_out (1 / 255).  M: HOST, B x 6 doubles, the FORWARD
+ * 2 x 3 matrices as handed to cv2.warpAffine (the caller draws them: get_transform_matrix uses Python's random); flips: HOST,
+ * B ints, bit 0 = up-down, bit 1 = left-right, may be NULL; border4: HOST, 4 floats - cv2 turns the 3-tuple into the scalar
+ * (114, 114, 114, 0) and channel k takes entry k & 3, so pass exactly that to reproduce the reference.  The arithmetic follows
+ * cv::warpAffine INTER_LINEAR on float images: double inverse map, fixed-point destination coordinates rounded to 1/32 pixel,
+ * float 32 x 32 weight table, double accumulation. */
+int evrep_warp_affine_batched(const float* img, int B, int C, int in_h, int in_w, const double* M, const int* flips, int out_h, int out_w,
+                              const float* border4, int reverse_channels, float scale_out, float* out, evrep_stream_t stream);
 
 /* ev-licious' per-pixel stateful filters over B event windows (streams): mask[i] = 1 if event i passes, 0 otherwise
  * (DEVICE uint8, one per event, fully overwritten; events with x or y outside the sensor get 0 and raise

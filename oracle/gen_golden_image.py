@@ -55,5 +55,33 @@ def main():
         print(name, rep.shape, "->", want.shape)
 
 
+def main_affine():
+    """img_affine_*.npz: the reference's OWN random_affine (data_augment.py:110-150, get_transform_matrix drawing from a seeded
+    `random`) on the letterboxed image, then the flips; the oracle's augmented_detector_input is checked against it first"""
+    import random
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    for i, (name, H, W, C, S, ud, lr) in enumerate([("gen1like", 24, 30, 12, 64, False, True), ("mpx_like", 36, 64, 12, 48, True, False),
+                                                    ("c2", 30, 38, 2, 40, False, False), ("c5", 33, 47, 5, 56, True, True)]):
+        rng = np.random.default_rng(7100 + i)
+        rep = (rng.random((H, W, C)) * (rng.random((H, W, C)) < 0.4)).astype(np.float64)
+        rep[..., 0] -= 0.3 * (rng.random((H, W)) < 0.2)
+        lb = oimg.letterbox(oimg.resize_image(rep * 255, S, augment=True), S)
+        random.seed(900 + i)
+        M, _ = ref.get_transform_matrix(lb.shape[:2], (S, S), 10, 0.1, 10, 0.1)  # the hyper-parameters of configs/*_finetune: degrees, scale, shear, translate
+        random.seed(900 + i)
+        warped, _ = ref.random_affine(lb, (), degrees=10, translate=0.1, scale=0.1, shear=10, new_shape=(S, S))  # draws the same M
+        img = warped
+        if ud:
+            img = np.flipud(img)
+        if lr:
+            img = np.fliplr(img)
+        img = np.ascontiguousarray(img.transpose((2, 0, 1))[::-1])
+        want = (img.astype(np.float32) / 255).astype(np.float32)
+        assert np.array_equal(want, oimg.augmented_detector_input(rep, S, M, ud, lr)), name
+        np.savez_compressed(os.path.join(out_dir, f"img_affine_{name}.npz"), rep=rep, img_size=np.int64(S), M=M, flip_ud=np.bool_(ud), flip_lr=np.bool_(lr), out=want)
+        print("affine", name, rep.shape, "->", want.shape)
+
+
 if __name__ == "__main__":
     main()
+    main_affine()

@@ -18,7 +18,52 @@ def E(cuda_device):
     return eb
 
 
-@pytest.mark.parametrize("name,path", golden("img_*"), ids=[n for n, _ in golden("img_*")])
+IMG = [c for c in golden("img_*") if not c[0].startswith("img_affine")]
+IMG_AFFINE = golden("img_affine_*")
+
+
+@pytest.mark.parametrize("name,path", IMG_AFFINE, ids=[n for n, _ in IMG_AFFINE])
+def test_augmented_pipeline_matches_the_reference_random_affine(E, name, path):
+    """training branch (gen1_2yolo.py:321-397): resize (INTER_LINEAR) + letterbox on the GPU, then evrep_warp_affine_batched with
+    the M the reference's get_transform_matrix drew and the flips, against the reference's own random_affine output"""
+    import torch
+    g = load(path)
+    S = int(g["img_size"])
+    rep = torch.as_tensor(g["rep"].astype(np.float32)).cuda()[None]
+    lb = E.detector_input(rep, S, mode="letterbox", interp="linear", scale_out=1.0, reverse_channels=False)
+    got = E.augment_affine(lb, g["M"][None], [bool(g["flip_ud"])], [bool(g["flip_lr"])])[0].cpu().numpy()
+    assert got.shape == g["out"].shape
+    assert_close(got, g["out"], rtol=1e-5, atol=ATOL, what=name)
+
+
+def test_augmented_pipeline_at_detector_size_vs_cv2_oracle(E):
+    """Gen1 representation -> 640 x 640 with four different draws (one the identity: the reference skips the warp then), batched"""
+    import math
+    import random
+    import torch
+    from oracle import image_pipeline as oimg
+    H, W, S, B = 240, 304, 640, 4
+    rng = np.random.default_rng(11)
+    reps = (rng.random((B, H, W, 12)) * (rng.random((B, H, W, 12)) < 0.3)).astype(np.float32)
+    random.seed(3)
+    Ms = []
+    for b in range(B):
+        a, s_ = random.uniform(-10, 10), random.uniform(0.9, 1.1)
+        Cm, R, Sh, T = np.eye(3), np.eye(3), np.eye(3), np.eye(3)
+        Cm[0, 2], Cm[1, 2] = -S / 2, -S / 2
+        ca, sa = math.cos(math.radians(a)) * s_, math.sin(math.radians(a)) * s_
+        R[:2] = [[ca, sa, 0.0], [-sa, ca, 0.0]]  # cv2.getRotationMatrix2D(angle=a, center=(0, 0), scale=s)
+        Sh[0, 1], Sh[1, 0] = math.tan(math.radians(random.uniform(-10, 10))), math.tan(math.radians(random.uniform(-10, 10)))
+        T[0, 2], T[1, 2] = random.uniform(0.4, 0.6) * S, random.uniform(0.4, 0.6) * S
+        Ms.append(T @ Sh @ R @ Cm if b else np.eye(3))
+    ud, lr = [False, True, False, True], [False, False, True, True]
+    lb = E.detector_input(torch.as_tensor(reps).cuda(), S, interp="linear", scale_out=1.0, reverse_channels=False)
+    got = E.augment_affine(lb, np.stack(Ms), ud, lr).cpu().numpy()
+    for b in range(B):
+        assert_close(got[b], oimg.augmented_detector_input(reps[b], S, Ms[b], ud[b], lr[b]), rtol=1e-5, atol=ATOL, what=f"window {b}")
+
+
+@pytest.mark.parametrize("name,path", IMG, ids=[n for n, _ in IMG])
 def test_image_pipeline_matches_reference_fixtures(E, name, path):
     import torch
     g = load(path)

@@ -186,7 +186,41 @@ def test_window_bounds():
 
 
 # ---- post-representation image pipeline: oracle vs fixtures made with the reference's letterbox ----
-@pytest.mark.parametrize("name,path", golden("img_*"), ids=[n for n, _ in golden("img_*")])
+IMG = [c for c in golden("img_*") if not c[0].startswith("img_affine")]
+IMG_AFFINE = golden("img_affine_*")
+
+
+@pytest.mark.parametrize("name,path", IMG_AFFINE, ids=[n for n, _ in IMG_AFFINE])
+def test_oracle_augmented_image_pipeline_matches_the_reference_random_affine(name, path):
+    """fixtures made with the reference's own random_affine (data_augment.py) and flips; the oracle runs cv2 around the same M"""
+    from oracle import image_pipeline as oimg
+    g = load(path)
+    got = oimg.augmented_detector_input(g["rep"], int(g["img_size"]), g["M"], bool(g["flip_ud"]), bool(g["flip_lr"]))
+    assert np.array_equal(got, g["out"])
+
+
+def test_warp_affine_restatement_equals_cv2():
+    """the description of cv::warpAffine the CUDA kernel implements (fixed-point coordinates, float weight table, double
+    accumulation, border scalar indexed with channel & 3), restated in numpy, against cv2 itself: equal to the last bit"""
+    import cv2
+    from oracle import image_pipeline as oimg
+    rng = np.random.default_rng(5)
+    for k in range(5):
+        H, W = 40 + 7 * k, 64 - 5 * k
+        img = rng.random((H, W, 12)) * 255
+        ang, sc = rng.uniform(-10, 10), rng.uniform(0.9, 1.1)
+        M = cv2.getRotationMatrix2D((W / 2, H / 2), ang, sc)
+        M[:, 2] += rng.uniform(-6, 6, 2)
+        M[0, 1] += rng.uniform(-0.1, 0.1)
+        want = cv2.warpAffine(img, M, dsize=(W + 3, H - 2), borderValue=(114, 114, 114))
+        assert np.array_equal(oimg.warp_affine_restated(img, M, (W + 3, H - 2)), want)
+        assert want[..., 3::4].min() == 0.0 or True  # every fourth channel is padded with 0 (checked below on a corner)
+    far = np.array([[1.0, 0.0, 30.0], [0.0, 1.0, 0.0]])  # shifts the image right: the left columns are pure border
+    out = cv2.warpAffine(np.ones((8, 8, 12)), far, dsize=(8, 8), borderValue=(114, 114, 114))
+    assert out[0, 0].tolist() == [114.0, 114.0, 114.0, 0.0] * 3
+
+
+@pytest.mark.parametrize("name,path", IMG, ids=[n for n, _ in IMG])
 def test_image_pipeline_oracle_matches_reference_fixtures(name, path):
     from oracle import image_pipeline as oimg
     g = load(path)
