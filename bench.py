@@ -506,7 +506,7 @@ def run_gpu_arm(a):
     bounds = [B * g // n_groups for g in range(n_groups + 1)]
     offs = ev.offsets
     pk = pk_mod.pack_host(host["x"].numpy().view(np.uint16), host["y"].numpy().view(np.uint16), host["t"].numpy(), host["p"].numpy(), offs, H, W, pin=True)
-    res_host = [torch.empty(B, dtype=torch.float64).pin_memory() for _ in range(2)]
+    res_host = [torch.empty(B, dtype=torch.float32).pin_memory() for _ in range(2)]
     copy_st, comp_st = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     dbuf = [{k: torch.empty(int(offs[bounds[g + 1]] - offs[bounds[g]]), dtype=d[k].dtype, device=dev) for k in ("x", "y", "t", "p")}
             for g in range(n_groups)]
@@ -515,10 +515,8 @@ def run_gpu_arm(a):
 
     def e2e_leg(use_packed):
         if use_packed:
-            blk = [pk.block_range(bounds[g], bounds[g + 1]) for g in range(n_groups)]
-            pbuf = [{"word": torch.empty(int(offs[bounds[g + 1]] - offs[bounds[g]]), dtype=torch.int32, device=dev),
-                     "dt16": torch.empty(int(offs[bounds[g + 1]] - offs[bounds[g]]), dtype=torch.int16, device=dev) if pk.dt16 is not None else None,
-                     "tbase": torch.empty(blk[g][1] - blk[g][0], dtype=torch.int32, device=dev)} for g in range(n_groups)]
+            hparts = [pk.host_parts(bounds[g], bounds[g + 1]) for g in range(n_groups)]   # pinned views: what a loader ships per group
+            pbuf = [{k: torch.empty_like(v, device=dev) for k, v in hparts[g].items()} for g in range(n_groups)]
 
         def enqueue_copies(first):
             with torch.cuda.stream(copy_st):
@@ -527,10 +525,8 @@ def run_gpu_arm(a):
                         copy_st.wait_event(done[g_])
                     e0, e1 = int(offs[bounds[g_]]), int(offs[bounds[g_ + 1]])
                     if use_packed:
-                        pbuf[g_]["word"].copy_(pk.word[e0:e1], non_blocking=True)
-                        if pk.dt16 is not None:
-                            pbuf[g_]["dt16"].copy_(pk.dt16[e0:e1], non_blocking=True)
-                        pbuf[g_]["tbase"].copy_(pk.tbase[blk[g_][0]:blk[g_][1]], non_blocking=True)
+                        for k, v in hparts[g_].items():
+                            pbuf[g_][k].copy_(v, non_blocking=True)
                     else:
                         for k in ("x", "y", "t", "p"):
                             dbuf[g_][k].copy_(host[k][e0:e1], non_blocking=True)
@@ -544,12 +540,14 @@ def run_gpu_arm(a):
                     comp_st.wait_event(ready[g_])
                     lo = offs[w0:w1 + 1] - int(offs[w0])
                     if use_packed:
-                        sub = pk_mod.decode(pbuf[g_]["word"], pbuf[g_]["dt16"], pbuf[g_]["tbase"], lo, pk.fmt, pk.x_bits, pk.y_bits, pk.block_shift, out=dbuf[g_])
+                        sub = pk.decode_parts(pbuf[g_], lo, out=dbuf[g_])
                     else:
                         sub = eb.EventBatch(dbuf[g_]["x"], dbuf[g_]["y"], dbuf[g_]["t"], dbuf[g_]["p"], lo)
                     o = eb.ergo12(sub, H, W, out=out[w0:w1])
                     done[g_].record(comp_st)
-                    rh[w0:w1].copy_(o.view(w1 - w0, -1).sum(1, dtype=torch.float64), non_blocking=True)
+                    # per-window float32 sum: one pass over the output (a float64 sum made torch materialise a float64 copy of it first,
+                    # 1.3 ms per step - more than the representation itself)
+                    rh[w0:w1].copy_(o.view(w1 - w0, -1).sum(1), non_blocking=True)
                 fin = torch.cuda.Event()
                 fin.record(comp_st)
             return fin, rh
@@ -594,7 +592,7 @@ def run_gpu_arm(a):
     # the ceiling of that leg: the same pinned buffers copied host -> device and nothing else, on every rank at once (the GPUs of
     # a node share the host's memory controllers and root complexes, so the per-GPU rate drops as N grows)
     def h2d_ceiling():
-        srcs = [pk.word, pk.tbase] + ([pk.dt16] if pk.dt16 is not None else []) if pk is not None else [host[k] for k in ("x", "y", "t", "p")]
+        srcs = list(pk.host_parts(0, B).values()) if pk is not None else [host[k] for k in ("x", "y", "t", "p")]
         dsts = [torch.empty_like(s_, device=dev) for s_ in srcs]
         reps = max(3, min(a.steps, 20))
         with torch.cuda.stream(copy_st):
@@ -636,10 +634,10 @@ def run_gpu_arm(a):
             "metric": METRIC, "value": value, "unit": "Gevents/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "warmup_note": "warm-up runs at least --warmup steps and at least 0.25 s (clock sampler start-up)",
             "ms_per_step": ms_all / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32/f64->f32",
             "data": "synthetic", "config": config_dict(a, B),
-            "e2e": {"value": e2e_value, "unit": "Gevents/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * 8,
+            "e2e": {"value": e2e_value, "unit": "Gevents/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * 4,
                     "gpu_launches": e2e_launches,
-                    "host_format": (f"packed wire format {pk.fmt} ({h2d / (B * N):.2f} B/event: x, y, polarity and the offset to the base timestamp of a block of "
-                                    f"{1 << pk.block_shift} events in one 32-bit word; packed.pack_host on the loader side, evrep_unpack_events on the GPU)") if pk is not None
+                    "host_format": (f"packed wire format {pk.fmt} ({h2d / (B * N):.2f} B/event: " + {3: "x, y, a polarity bit and the 2-bit difference to the previous event's timestamp in 3 bytes, larger differences in a side table, ", 4: "x, y, polarity and the offset to the base timestamp of its block in one 32-bit word, ", 6: "a 32-bit word plus a 16-bit time offset, "}[pk.fmt] +
+                                    f"blocks of {1 << pk.block_shift} events; packed.pack_host on the loader side, one decode kernel on the GPU)") if pk is not None
                                    else "SoA arrays, 9 B/event (the stream does not fit the packed formats)",
                     "link": {"h2d_gbs_per_gpu_all_ranks_copying": link_gbs, "e2e_h2d_gbs_per_gpu": e2e_value / world * 1e9 * (h2d / (B * N)) / 1e9,
                              "frac_of_link": (e2e_value / world * (h2d / (B * N))) / link_gbs,

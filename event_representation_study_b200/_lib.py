@@ -56,6 +56,8 @@ SIGNATURES = {
     "evrep_assignment_auction": (_i, [_vp, _i, _d, _vp, _vp, _vp]),
     "evrep_unpack_workspace_bytes": (_sz, [_i, _i64]),
     "evrep_unpack_events": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "evrep_unpack_delta_workspace_bytes": (_sz, [_i]),
+    "evrep_unpack_events_delta": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "evrep_transport_plan_host": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "evrep_otmi_workspace_bytes": (_sz, [_i64, _i]),
     "evrep_otmi_prepare": (_i, [_vp, _i, _i64, _vp, _i, _i, _i, _i, _vp, _i64, _vp, _i64, _vp, _vp, _sz, _vp]),

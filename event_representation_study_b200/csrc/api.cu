@@ -78,6 +78,10 @@ int transport_plan_host(const float* cost, int n, int m, int cap, int* row_ptr, 
 size_t unpack_workspace_bytes(int B, int64_t total);
 int launch_warp_affine(const float* in, int B, int C, int in_h, int in_w, const double* M_host, const int* flips_host, int out_h, int out_w,
                        const float* border4, int reverse, float scale_out, float* out, cudaStream_t stream);
+size_t unpack_delta_workspace_bytes(int B);
+int launch_unpack_delta(const uint8_t* rec3, const int32_t* tbase, const uint32_t* esc_prefix, const uint32_t* esc_dt, const int64_t* win_offsets_host,
+                        int B, int xb, int yb, uint16_t* x, uint16_t* y, int32_t* t, int8_t* p, void* workspace, size_t workspace_bytes,
+                        cudaStream_t stream);
 size_t otmi_workspace_bytes(long long N, int R);
 int launch_otmi_prepare(const void* ev, int ev_type, long long N, const double* rep, int R, int C, int height, int width, double* Xs, long long xs_cap,
                         double* Xt, long long xt_cap, long long* info_host, void* workspace, cudaStream_t stream);
@@ -627,6 +631,19 @@ int evrep_transport_plan_host(const float* cost, int n, int m, int cap, int* row
   EVREP_GUARD_BEGIN
   if (!cost || !row_ptr || !col || !weight || cap < 1) { set_error("null argument or cap < 1"); return EVREP_EINVAL; }
   return transport_plan_host(cost, n, m, cap, row_ptr, col, weight, nnz);
+  EVREP_GUARD_END
+}
+
+size_t evrep_unpack_delta_workspace_bytes(int B) { return B < 0 ? 0 : unpack_delta_workspace_bytes(B); }
+
+int evrep_unpack_events_delta(const uint8_t* rec3, const int32_t* tbase, const uint32_t* esc_prefix, const uint32_t* esc_dt, const int64_t* win_offsets,
+                              int B, int x_bits, int y_bits, uint16_t* x, uint16_t* y, int32_t* t, int8_t* p, void* workspace, size_t workspace_bytes,
+                              evrep_stream_t stream) {
+  EVREP_GUARD_BEGIN
+  if (B < 0 || !win_offsets) { set_error("bad argument"); return EVREP_EINVAL; }
+  if (B == 0 || win_offsets[B] == 0) return EVREP_OK;
+  if (!rec3 || !tbase || !esc_prefix || !x || !y || !t || !p) { set_error("null argument"); return EVREP_EINVAL; }
+  return launch_unpack_delta(rec3, tbase, esc_prefix, esc_dt, win_offsets, B, x_bits, y_bits, x, y, t, p, workspace, workspace_bytes, (cudaStream_t)stream);
   EVREP_GUARD_END
 }
 

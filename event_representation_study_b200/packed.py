@@ -1,9 +1,11 @@
 """Packed host wire format for the end-to-end path (include/evrep.h, evrep_unpack_events).
 
 The engine consumes events from HBM ~9x faster than the host link can deliver them as SoA arrays (9 B/event), so the
-loader side can pack an event into 4 bytes (format 4: x, y, polarity and a small time offset to the base of its block of 64
-events in one 32-bit word) or 6 bytes (format 6: the word plus a 16-bit offset, blocks of 256 events), and one decode kernel
-restores the SoA arrays on the GPU.  Packing is a few vectorised numpy passes per window, the kind of work the reference's
+loader side can pack an event into 3 bytes (format 3: x, y, a polarity bit and the 2-bit difference to the previous event's
+timestamp, larger differences in a side table; blocks of 64 events; needs sorted windows, polarities -1 / +1 and x, y within
+21 bits together), 4 bytes (format 4: x, y, polarity and a small time offset to the base of its block of 64 events in one
+32-bit word) or 6 bytes (format 6: the word plus a 16-bit offset, blocks of 256 events), and one decode kernel restores the
+SoA arrays on the GPU.  Packing is a few vectorised numpy passes per window, the kind of work the reference's
 DataLoader workers already do per sample (ev-YOLOv6/yolov6/data/gen1_2yolo.py:186-208 slices, concatenates and casts the
 same arrays); decoded timestamps equal the originals up to one constant per window, which no representation can see."""
 import ctypes
@@ -16,7 +18,7 @@ import torch
 from . import batched as eb
 from ._lib import check, lib
 
-BLOCK_SHIFT = {4: 6, 6: 8}  # events per block: 64 / 256
+BLOCK_SHIFT = {3: 6, 4: 6, 6: 8}  # events per block: 64 / 64 / 256
 
 
 def _bits(n):
@@ -25,9 +27,11 @@ def _bits(n):
 
 @dataclass
 class PackedEvents:
-    """Host side of a packed batch: `word` (uint32 per event, stored as int32), `dt16` (uint16 per event as int16, format 6
-    only), `tbase` (int32 per block), CSR `offsets` (B + 1) and the format constants.  Tensors may be pinned."""
-    word: torch.Tensor
+    """Host side of a packed batch.  Formats 4 / 6: `word` (uint32 per event, stored as int32), `dt16` (uint16 per event as
+    int16, format 6 only), `tbase` (int32 per block).  Format 3: `rec3` (uint8, 192 bytes per block of 64 events), `tbase`,
+    `esc_prefix` (escapes before each block, int32 storage, blocks + 1 entries) and `esc_dt` (the escaped differences, int32
+    storage).  CSR `offsets` (B + 1) and the format constants.  Tensors may be pinned."""
+    word: Optional[torch.Tensor]
     dt16: Optional[torch.Tensor]
     tbase: torch.Tensor
     offsets: np.ndarray
@@ -35,10 +39,13 @@ class PackedEvents:
     x_bits: int
     y_bits: int
     block_shift: int
+    rec3: Optional[torch.Tensor] = None
+    esc_prefix: Optional[torch.Tensor] = None
+    esc_dt: Optional[torch.Tensor] = None
 
     @property
     def nbytes(self):
-        return sum(v.numel() * v.element_size() for v in (self.word, self.dt16, self.tbase) if v is not None)
+        return sum(v.numel() * v.element_size() for v in (self.word, self.dt16, self.tbase, self.rec3, self.esc_prefix, self.esc_dt) if v is not None)
 
     def block_range(self, w0, w1):
         """[first, last) block of the windows [w0, w1) (blocks never straddle windows)"""
@@ -47,10 +54,67 @@ class PackedEvents:
         pre = np.concatenate([[0], np.cumsum(nb)])
         return int(pre[w0]), int(pre[w1])
 
+    def host_parts(self, w0, w1):
+        """The payload of the windows [w0, w1) as a dict of host tensor views (what a loader ships for that group)"""
+        e0, e1 = int(self.offsets[w0]), int(self.offsets[w1])
+        b0, b1 = self.block_range(w0, w1)
+        if self.fmt == 3:
+            q0, q1 = int(self.esc_prefix[b0]), int(self.esc_prefix[b1])
+            return {"rec3": self.rec3[192 * b0:192 * b1], "tbase": self.tbase[b0:b1], "esc_prefix": self.esc_prefix[b0:b1 + 1],
+                    "esc_dt": self.esc_dt[q0:max(q1, q0 + 1)]}  # never empty: a zero-size copy has no device pointer
+        parts = {"word": self.word[e0:e1], "tbase": self.tbase[b0:b1]}
+        if self.dt16 is not None:
+            parts["dt16"] = self.dt16[e0:e1]
+        return parts
+
+    def decode_parts(self, dev_parts, local_offsets, out=None):
+        """Device copies of host_parts(w0, w1) -> EventBatch of those windows (local_offsets = offsets[w0:w1 + 1] - offsets[w0])"""
+        if self.fmt == 3:
+            return decode_delta(dev_parts["rec3"], dev_parts["tbase"], dev_parts["esc_prefix"], dev_parts["esc_dt"], local_offsets, self.x_bits, self.y_bits,
+                                out=out)
+        return decode(dev_parts["word"], dev_parts.get("dt16"), dev_parts["tbase"], local_offsets, self.fmt, self.x_bits, self.y_bits, self.block_shift, out=out)
+
+
+def _pack3(x, y, p8, rel, offsets, xb, yb, pin):
+    """Format 3 or None: sorted windows, polarities -1 / +1, xb + yb <= 21"""
+    total = int(offsets[-1])
+    if xb + yb > 21 or (total and ((p8 == 0).any())):
+        return None
+    n = np.diff(offsets)
+    nb = (n + 63) >> 6
+    n_blocks = int(nb.sum())
+    local = np.arange(total, dtype=np.int64) - np.repeat(offsets[:-1], n)
+    blk = np.repeat(np.concatenate([[0], np.cumsum(nb)])[:-1], n) + (local >> 6)
+    first = (local & 63) == 0
+    d = np.zeros(total, np.int64)
+    if total:
+        d[1:] = rel[1:] - rel[:-1]
+        d[first] = 0
+        if d.min() < 0 or d.max() >= 2**32 or rel.min() < 0 or rel.max() >= 2**31:
+            return None
+    esc = d > 2
+    code = np.where(esc, 3, d).astype(np.uint32)
+    rec = x | (y << xb) | ((p8 > 0).astype(np.uint32) << (xb + yb)) | (code << (xb + yb + 1))
+    rec3 = np.zeros((n_blocks * 64, 3), np.uint8)
+    slot = blk * 64 + (local & 63)
+    rec3[slot, 0], rec3[slot, 1], rec3[slot, 2] = rec & 255, (rec >> 8) & 255, (rec >> 16) & 255
+    tbase = rel[first].astype(np.int32) if total else np.zeros(0, np.int32)
+    esc_prefix = np.zeros(n_blocks + 1, np.int64)
+    if total:
+        esc_prefix[1:] = np.cumsum(np.bincount(blk[esc], minlength=n_blocks))
+    esc_dt = d[esc].astype(np.uint32)
+    if len(esc_dt) == 0:
+        esc_dt = np.zeros(1, np.uint32)  # keeps the device pointer valid
+    tens = [torch.from_numpy(rec3.reshape(-1)), torch.from_numpy(tbase), torch.from_numpy(esc_prefix.astype(np.uint32).view(np.int32)),
+            torch.from_numpy(esc_dt.view(np.int32))]
+    if pin:
+        tens = [v.pin_memory() for v in tens]
+    return PackedEvents(None, None, tens[1], offsets, 3, xb, yb, 6, rec3=tens[0], esc_prefix=tens[2], esc_dt=tens[3])
+
 
 def pack_host(x, y, t, p, offsets, H, W, fmt=None, pin=False):
-    """SoA numpy events of a CSR batch -> PackedEvents, or None when some block's time span fits neither format (sparse or
-    unsorted streams: upload the SoA arrays instead).  fmt: 4, 6 or None (= the smallest that fits)."""
+    """SoA numpy events of a CSR batch -> PackedEvents, or None when the stream fits none of the formats (sparse or unsorted
+    streams: upload the SoA arrays instead).  fmt: 3, 4, 6 or None (= the smallest that fits)."""
     offsets = np.ascontiguousarray(offsets, np.int64)
     total = int(offsets[-1])
     x = np.asarray(x)[:total].astype(np.uint32)
@@ -65,7 +129,12 @@ def pack_host(x, y, t, p, offsets, H, W, fmt=None, pin=False):
     t64 = np.asarray(t)[:total].astype(np.int64)
     first = np.repeat(t64[offsets[:-1][n > 0]], n[n > 0]) if total else np.zeros(0, np.int64)
     rel = t64 - first
-    for f in ((fmt,) if fmt else (4, 6)):
+    for f in ((fmt,) if fmt else (3, 4, 6)):
+        if f == 3:
+            pk3 = _pack3(x, y, p8, rel, offsets, xb, yb, pin)
+            if pk3 is not None:
+                return pk3
+            continue
         if f == 4 and xb + yb > 29:
             continue
         bs = BLOCK_SHIFT[f]
@@ -98,18 +167,46 @@ def pack_host(x, y, t, p, offsets, H, W, fmt=None, pin=False):
 
 def unpack_numpy(pk):
     """Host reference of the decode (tests): -> x, y, t (relative to each window's first timestamp), p."""
-    word = pk.word.numpy().view(np.uint32)
     xb, yb = pk.x_bits, pk.y_bits
+    n = np.diff(pk.offsets)
+    nb = (n + (1 << pk.block_shift) - 1) >> pk.block_shift
+    local = np.arange(int(pk.offsets[-1])) - np.repeat(pk.offsets[:-1], n)
+    blk = np.repeat(np.concatenate([[0], np.cumsum(nb)])[:-1], n) + (local >> pk.block_shift)
+    if pk.fmt == 3:
+        b3 = pk.rec3.numpy().reshape(-1, 3).astype(np.uint32)
+        rec = (b3[:, 0] | (b3[:, 1] << 8) | (b3[:, 2] << 16))[blk * 64 + (local & 63)]
+        code = (rec >> (xb + yb + 1)) & 3
+        d = code.astype(np.int64)
+        d[code == 3] = pk.esc_dt.numpy().view(np.uint32)[: int((code == 3).sum())]
+        run = np.cumsum(d)
+        first = np.flatnonzero((local & 63) == 0)
+        run = run - np.repeat(run[first], np.diff(np.concatenate([first, [len(d)]])))  # restart at every block (its first code is 0)
+        t = pk.tbase.numpy().astype(np.int64)[blk] + run
+        p = np.where((rec >> (xb + yb)) & 1, 1, -1).astype(np.int8)
+        return (rec & ((1 << xb) - 1)).astype(np.uint16), ((rec >> xb) & ((1 << yb) - 1)).astype(np.uint16), t, p
+    word = pk.word.numpy().view(np.uint32)
     x = word & ((1 << xb) - 1)
     y = (word >> xb) & ((1 << yb) - 1)
     pc = (word >> (xb + yb)) & 3
     p = np.where(pc == 3, -1, pc).astype(np.int8)
     dt = (word >> (xb + yb + 2)).astype(np.int64) if pk.fmt == 4 else pk.dt16.numpy().view(np.uint16).astype(np.int64)
-    n = np.diff(pk.offsets)
-    nb = (n + (1 << pk.block_shift) - 1) >> pk.block_shift
-    local = np.arange(int(pk.offsets[-1])) - np.repeat(pk.offsets[:-1], n)
-    blk = np.repeat(np.concatenate([[0], np.cumsum(nb)])[:-1], n) + (local >> pk.block_shift)
     return x.astype(np.uint16), y.astype(np.uint16), pk.tbase.numpy().astype(np.int64)[blk] + dt, p
+
+
+def decode_delta(rec3, tbase, esc_prefix, esc_dt, offsets, x_bits, y_bits, out=None):
+    """Format-3 payload already on the GPU -> EventBatch (evrep_unpack_events_delta)"""
+    offsets = np.ascontiguousarray(offsets, np.int64)
+    total, B = int(offsets[-1]), len(offsets) - 1
+    dev = rec3.device
+    eb._require_current(dev)
+    if out is None:
+        out = {"x": torch.empty(total, dtype=torch.int16, device=dev), "y": torch.empty(total, dtype=torch.int16, device=dev),
+               "t": torch.empty(total, dtype=torch.int32, device=dev), "p": torch.empty(total, dtype=torch.int8, device=dev)}
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    ws = eb._workspace(dev, ("unpack", stream), max(int(lib.evrep_unpack_delta_workspace_bytes(B)), 256))
+    check(lib.evrep_unpack_events_delta(rec3.data_ptr(), tbase.data_ptr(), esc_prefix.data_ptr(), esc_dt.data_ptr(), offsets.ctypes.data, B, x_bits, y_bits,
+                                        out["x"].data_ptr(), out["y"].data_ptr(), out["t"].data_ptr(), out["p"].data_ptr(), ws.data_ptr(), ws.numel(), stream))
+    return eb.EventBatch(out["x"][:total], out["y"][:total], out["t"][:total], out["p"][:total], offsets)
 
 
 def decode(word, dt16, tbase, offsets, fmt, x_bits, y_bits, block_shift, out=None):
@@ -131,8 +228,8 @@ def decode(word, dt16, tbase, offsets, fmt, x_bits, y_bits, block_shift, out=Non
 
 
 def upload(pk, device="cuda", out=None):
-    """PackedEvents on the host -> EventBatch on `device`: three host-to-device copies and one decode kernel."""
+    """PackedEvents on the host -> EventBatch on `device`: a few host-to-device copies and one decode kernel."""
     dev = torch.device(device)
-    nb = pk.word.is_pinned()
-    to = lambda v: v.to(dev, non_blocking=nb) if v is not None else None
-    return decode(to(pk.word), to(pk.dt16), to(pk.tbase), pk.offsets, pk.fmt, pk.x_bits, pk.y_bits, pk.block_shift, out=out)
+    parts = pk.host_parts(0, len(pk.offsets) - 1)
+    dev_parts = {k: v.to(dev, non_blocking=v.is_pinned()) for k, v in parts.items()}
+    return pk.decode_parts(dev_parts, pk.offsets, out=out)

@@ -272,6 +272,20 @@ int evrep_unpack_events(const uint32_t* word, const uint16_t* dt16, const int32_
                         int x_bits, int y_bits, int block_shift, uint16_t* x, uint16_t* y, int32_t* t, int8_t* p, void* workspace,
                         size_t workspace_bytes, evrep_stream_t stream);
 
+/* Format 3 of the packed host wire format: 3 bytes per event, for time-sorted windows with polarities in {-1, +1} on sensors
+ * with x_bits + y_bits <= 21 (1280 x 720: 11 + 10).  record = x | y << x_bits | (p > 0) << (x_bits + y_bits) | code <<
+ * (x_bits + y_bits + 1), little endian, where code is the event's timestamp MINUS ITS PREDECESSOR'S (0, 1, 2) or 3 = "the
+ * difference is the next entry of esc_dt".  Events are grouped in blocks of 64 of one window; a block occupies exactly 192
+ * bytes of rec3 (the last block of a window is padded with anything), tbase[block] is the timestamp of its first event
+ * relative to the window's first (that event's code is 0), esc_prefix[block] the number of escapes in the blocks before it
+ * (any common offset is removed: the tables of a group of windows may be slices of a batch's), esc_dt the escape values in
+ * stream order.  All DEVICE pointers except win_offsets (HOST, B + 1); x, y, t, p as in evrep_unpack_events.  3.13 B/event
+ * on the host link against 4.06 (format 4) and 9 (SoA arrays).  Lossless (tests/test_packed.py). */
+size_t evrep_unpack_delta_workspace_bytes(int B);
+int evrep_unpack_events_delta(const uint8_t* rec3, const int32_t* tbase, const uint32_t* esc_prefix, const uint32_t* esc_dt,
+                              const int64_t* win_offsets, int B, int x_bits, int y_bits, uint16_t* x, uint16_t* y, int32_t* t, int8_t* p,
+                              void* workspace, size_t workspace_bytes, evrep_stream_t stream);
+
 /* The LMO of evrep_gw_kl for rectangular plans (n != m): an optimal vertex of the transportation problem
  *     min <cost, G>  s.t.  G 1 = 1/n,  G^T 1 = 1/m,  G >= 0
  * (what POT's ot.emd returns inside ot.gromov.gromov_wasserstein; gromov_wasserstein.py:62-69).  HOST function, HOST

@@ -13,19 +13,20 @@ def _batch(sizes, H, W, seed=0, polarity="pm1", duration_us=300_000):
 
 
 @pytest.mark.parametrize("sizes,H,W,fmt,dur", [([5000, 0, 64, 65, 1, 12345], 240, 304, 4, 2_000), ([5000, 0, 256, 257, 1, 12345], 240, 304, 6, 50_000),
-                                               ([20000, 777], 720, 1280, None, 2_000), ([3000], 4000, 5000, None, 300_000)])
+                                               ([20000, 777], 720, 1280, None, 2_000), ([3000], 4000, 5000, None, 300_000),
+                                               ([5000, 0, 64, 65, 1, 12345, 63, 129], 720, 1280, 3, 2_000), ([4000, 130], 240, 304, 3, 3_000_000)])
 def test_pack_roundtrip_on_the_host(sizes, H, W, fmt, dur):
     from event_representation_study_b200 import packed
     wins, b = _batch(sizes, H, W, 3, duration_us=dur)
     pk = packed.pack_host(b["x"], b["y"], b["t"], b["p"], b["offsets"], H, W, fmt=fmt)
-    assert pk is not None and pk.fmt == (fmt or (4 if W <= 2048 else 6))
+    assert pk is not None and pk.fmt == (fmt or (3 if W <= 2048 else 6))  # smallest that fits: 3 needs x, y within 21 bits
     x, y, t, p = packed.unpack_numpy(pk)
     assert np.array_equal(x, b["x"]) and np.array_equal(y, b["y"]) and np.array_equal(p, b["p"])
     n = np.diff(b["offsets"])
     first = np.repeat(b["t"].astype(np.int64)[b["offsets"][:-1][n > 0]], n[n > 0])
     assert np.array_equal(t, b["t"].astype(np.int64) - first)
     per_event = pk.nbytes / max(1, int(b["offsets"][-1]))
-    assert per_event < (4.2 if pk.fmt == 4 else 6.1) or int(b["offsets"][-1]) < 5000
+    assert per_event < {3: 3.3, 4: 4.2, 6: 6.1}[pk.fmt] or int(b["offsets"][-1]) < 5000 or dur > 1_000_000  # sparse streams: escapes
 
 
 def test_pack_falls_back_when_a_block_spans_too_long():
@@ -33,9 +34,13 @@ def test_pack_falls_back_when_a_block_spans_too_long():
     wins, b = _batch([4000], 240, 304, 5, duration_us=300_000_000)  # 75 ms between events: no block of 64 fits 2^13 us
     assert packed.pack_host(b["x"], b["y"], b["t"], b["p"], b["offsets"], 240, 304, fmt=4) is None
     pk = packed.pack_host(b["x"], b["y"], b["t"], b["p"], b["offsets"], 240, 304)
-    assert pk is None or pk.fmt == 6
-    wins, b = _batch([300], 240, 304, 6, duration_us=2_000_000_000)
+    assert pk is not None and pk.fmt == 3  # the delta format takes any gap through its escape table (12 B per escaped event)
+    wins, b = _batch([300], 240, 304, 6, duration_us=2_000_000_000, polarity="01")  # p == 0 events: not format 3; gaps too long for 4 and 6
     assert packed.pack_host(b["x"], b["y"], b["t"], b["p"], b["offsets"], 240, 304) is None  # caller uploads the SoA arrays
+    wins, b = _batch([300], 240, 304, 6)
+    b["t"][10], b["t"][11] = b["t"][11], b["t"][10] + 0  # unsorted: negative difference
+    if b["t"][10] != b["t"][11]:
+        assert packed.pack_host(b["x"], b["y"], b["t"], b["p"], b["offsets"], 240, 304, fmt=3) is None
     with pytest.raises(IndexError):
         packed.pack_host(np.array([400]), np.array([0]), np.array([0]), np.array([1]), np.array([0, 1]), 240, 304)
 
@@ -56,6 +61,31 @@ def test_decode_kernel_matches_the_host_decoder(cuda_device, fmt, polarity):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("dur", [300, 40_000, 30_000_000])
+def test_delta_decode_kernel_matches_the_host_decoder(cuda_device, dur):
+    """format 3: dense streams (codes 0..2 only), ordinary ones, and sparse ones where nearly every event is an escape; also a
+    group of windows decoded from slices of the batch's tables (what the end-to-end leg of bench.py ships per group)"""
+    from event_representation_study_b200 import packed
+    H, W = 720, 1280
+    wins, b = _batch([100_000, 0, 1, 63, 64, 65, 1023, 1024, 1025, 4097, 250_001], H, W, 11, duration_us=dur)
+    pk = packed.pack_host(b["x"], b["y"], b["t"], b["p"], b["offsets"], H, W, fmt=3, pin=True)
+    assert pk is not None and pk.fmt == 3
+    x, y, t, p = packed.unpack_numpy(pk)
+    n = np.diff(b["offsets"])
+    first = np.repeat(b["t"].astype(np.int64)[b["offsets"][:-1][n > 0]], n[n > 0])
+    assert np.array_equal(x, b["x"]) and np.array_equal(y, b["y"]) and np.array_equal(p, b["p"]) and np.array_equal(t, b["t"].astype(np.int64) - first)
+    ev = packed.upload(pk, "cuda")
+    assert np.array_equal(ev.x.cpu().numpy().view(np.uint16), x) and np.array_equal(ev.y.cpu().numpy().view(np.uint16), y)
+    assert np.array_equal(ev.t.cpu().numpy().astype(np.int64), t) and np.array_equal(ev.p.cpu().numpy(), p)
+    w0, w1 = 4, 11  # a group: slices of the tables, escape prefixes not starting at 0
+    parts = {k: v.to("cuda") for k, v in pk.host_parts(w0, w1).items()}
+    sub = pk.decode_parts(parts, b["offsets"][w0:w1 + 1] - b["offsets"][w0])
+    e0, e1 = int(b["offsets"][w0]), int(b["offsets"][w1])
+    assert np.array_equal(sub.t.cpu().numpy().astype(np.int64), t[e0:e1]) and np.array_equal(sub.x.cpu().numpy().view(np.uint16), x[e0:e1])
+    assert np.array_equal(sub.p.cpu().numpy(), p[e0:e1])
+
+
+@pytest.mark.gpu
 def test_ergo12_from_a_packed_batch_equals_the_soa_batch(cuda_device):
     """timestamps come back shifted by one constant per window: ERGO-12 (t - t.min() first thing) must not see it"""
     import torch
@@ -64,7 +94,8 @@ def test_ergo12_from_a_packed_batch_equals_the_soa_batch(cuda_device):
     H, W = 240, 304
     wins, b = _batch([60_000, 30_001, 7], H, W, 21, duration_us=20_000)
     want = eb.ergo12(eb.pack_events(wins, "cuda", t_dtype=np.int64), H, W)
-    pk = packed.pack_host(b["x"], b["y"], b["t"], b["p"], b["offsets"], H, W)
-    assert pk is not None
-    got = eb.ergo12(packed.upload(pk, "cuda"), H, W)
-    assert torch.equal(got, want)
+    for fmt in (3, 4):
+        pk = packed.pack_host(b["x"], b["y"], b["t"], b["p"], b["offsets"], H, W, fmt=fmt)
+        assert pk is not None and pk.fmt == fmt
+        got = eb.ergo12(packed.upload(pk, "cuda"), H, W)
+        assert torch.equal(got, want)
