@@ -236,8 +236,13 @@ def bench_gwd(rank, world, dev, steps, with_cpu):
             Xs_list.append(xs)
             Xt_list.append(torch.as_tensor(Xt, device=dev))
 
+    # the point sets of this rank's columns in the layout the kernel consumes, resident in HBM before the timed region (like the
+    # events of the headline): one float64 array per side + offsets (eb.gwd_pack; otmi_prepare produces the same layout directly)
+    (Xs_p, so), (Xt_p, to) = eb.gwd_pack(Xs_list, dev), eb.gwd_pack(Xt_list, dev)
+    del Xs_list, Xt_list
+
     def step():
-        local = eb.gwd_kernel_l1(Xs_list, Xt_list, 0.7, device=dev).reshape(hi - lo, R).t().contiguous()  # (R, S_local)
+        local = eb.gwd_kernel_l1(Xs_p, Xt_p, 0.7, s_offsets=so, t_offsets=to).reshape(hi - lo, R).t().contiguous()  # (R, S_local)
         return sharding.gather_cost_matrix(local)
 
     M = step()

@@ -319,27 +319,44 @@ def histogram(ev, H, W, out=None):
     return out
 
 
-def gwd_kernel_l1(Xs_list, Xt_list, h=0.7, device="cuda"):
-    """GWD-A cost of every (Xs, Xt) pair (compute_otmi.py:50-93 in closed form) -> float64 CUDA tensor (n_pairs,).
-    Xs_list / Xt_list: lists of (n_i, ds) / (m_i, dt) arrays or tensors (any float dtype)."""
-    if len(Xs_list) != len(Xt_list):
-        raise ValueError("need as many Xs as Xt")
-    n_pairs = len(Xs_list)
+def gwd_pack(point_sets, device="cuda"):
+    """List of (n_i, d) arrays / tensors -> (float64 CUDA tensor (sum n_i, d), host int64 offsets (len + 1)): the layout
+    evrep_gwd_kernel_l1 consumes.  Pack once when the same point sets are evaluated repeatedly (or build the layout directly:
+    otmi_prepare already returns views of it)."""
     dev = torch.device(device)
+    ts = [torch.as_tensor(a).to(device=dev, dtype=torch.float64).reshape(len(a), -1) for a in point_sets]
+    d = ts[0].shape[1] if ts else 1
+    if any(t.shape[1] != d for t in ts):
+        raise ValueError("all point sets must share the feature width")
+    offs = np.zeros(len(ts) + 1, np.int64)
+    offs[1:] = np.cumsum([t.shape[0] for t in ts])
+    return (torch.cat(ts, 0).contiguous() if ts else torch.zeros((0, d), dtype=torch.float64, device=dev)), offs
+
+
+def gwd_kernel_l1(Xs_list, Xt_list, h=0.7, device="cuda", s_offsets=None, t_offsets=None):
+    """GWD-A cost of every (Xs, Xt) pair (compute_otmi.py:50-93 in closed form) -> float64 CUDA tensor (n_pairs,).
+    Xs_list / Xt_list: lists of (n_i, ds) / (m_i, dt) arrays or tensors (any float dtype), packed here on every call - or,
+    with s_offsets / t_offsets (host int64, n_pairs + 1), the already packed float64 CUDA tensors of gwd_pack."""
+    dev = torch.device(device)
+    if s_offsets is not None:
+        Xs, Xt = Xs_list, Xt_list
+        so, to = np.ascontiguousarray(s_offsets, np.int64), np.ascontiguousarray(t_offsets, np.int64)
+        if not (torch.is_tensor(Xs) and torch.is_tensor(Xt) and Xs.is_cuda and Xt.is_cuda and Xs.dtype == torch.float64 and Xt.dtype == torch.float64
+                and Xs.is_contiguous() and Xt.is_contiguous() and Xs.dim() == 2 and Xt.dim() == 2):
+            raise ValueError("packed inputs must be contiguous 2-D float64 CUDA tensors (gwd_pack)")
+        if len(so) != len(to) or Xs.shape[0] < so[-1] or Xt.shape[0] < to[-1]:
+            raise ValueError("offsets do not match the packed tensors")
+        n_pairs, ds, dt = len(so) - 1, int(Xs.shape[1]), int(Xt.shape[1])
+        dev = Xs.device
+    else:
+        if len(Xs_list) != len(Xt_list):
+            raise ValueError("need as many Xs as Xt")
+        n_pairs = len(Xs_list)
+        if n_pairs:
+            (Xs, so), (Xt, to) = gwd_pack(Xs_list, dev), gwd_pack(Xt_list, dev)
+            ds, dt = int(Xs.shape[1]), int(Xt.shape[1])
     if n_pairs == 0:
         return torch.zeros(0, dtype=torch.float64, device=dev)
-
-    def pack(lst):
-        ts = [torch.as_tensor(a).to(device=dev, dtype=torch.float64).reshape(len(a), -1) for a in lst]
-        d = ts[0].shape[1]
-        if any(t.shape[1] != d for t in ts):
-            raise ValueError("all pairs must share the feature width")
-        offs = np.zeros(n_pairs + 1, np.int64)
-        offs[1:] = np.cumsum([t.shape[0] for t in ts])
-        return torch.cat(ts, 0).contiguous(), offs, d
-
-    Xs, so, ds = pack(Xs_list)
-    Xt, to, dt = pack(Xt_list)
     nbytes = lib.evrep_gwd_workspace_bytes(so.ctypes.data, to.ctypes.data, n_pairs)
     if nbytes == 0:
         raise ValueError("invalid pair sizes")
