@@ -288,6 +288,7 @@ struct WarpParams {
   float scale_out;
 };
 
+template <int CT>  // compile-time channel count (unrolled), or 0 for the generic loop
 __global__ void __launch_bounds__(256) k_warp_affine(const float* __restrict__ in, const __grid_constant__ WarpParams p, float* __restrict__ out) {
   const int ox = blockIdx.x * blockDim.x + threadIdx.x;
   const int oy = blockIdx.y, b = blockIdx.z;
@@ -313,7 +314,19 @@ __global__ void __launch_bounds__(256) k_warp_affine(const float* __restrict__ i
   float* dst = out + (size_t)b * p.C * out_plane + (size_t)oy * p.out_w + ox;
   const size_t o00 = (size_t)(y0 ? sy : 0) * p.in_w + (x0 ? sx : 0), o01 = (size_t)(y0 ? sy : 0) * p.in_w + (x1 ? sx + 1 : 0);
   const size_t o10 = (size_t)(y1 ? sy + 1 : 0) * p.in_w + (x0 ? sx : 0), o11 = (size_t)(y1 ? sy + 1 : 0) * p.in_w + (x1 ? sx + 1 : 0);
-  for (int c = 0; c < p.C; ++c) {
+  const int C = CT ? CT : p.C;
+  if (y0 && y1 && x0 && x1) {  // all four taps inside the image (nearly every pixel): no border selects
+#pragma unroll
+    for (int c = 0; c < (CT ? CT : 1); ++c) {
+      for (int cc = c; cc < C; cc += (CT ? C : 1)) {
+        const float* pl = src + (size_t)cc * in_plane;
+        const float sum = fmaf(__ldg(pl + o11), w11, fmaf(__ldg(pl + o10), w10, fmaf(__ldg(pl + o01), w01, __ldg(pl + o00) * w00)));
+        __stcs(dst + (size_t)(p.reverse ? C - 1 - cc : cc) * out_plane, sum * p.scale_out);
+      }
+    }
+    return;
+  }
+  for (int c = 0; c < C; ++c) {
     const float* pl = src + (size_t)c * in_plane;
     const float bv = p.border[c & 3];
     const float v00 = (y0 && x0) ? __ldg(pl + o00) : bv, v01 = (y0 && x1) ? __ldg(pl + o01) : bv;
@@ -322,7 +335,7 @@ __global__ void __launch_bounds__(256) k_warp_affine(const float* __restrict__ i
     // here the image is float32 already, and a float FMA chain stays within 2 ulp of that sum (1e-7 relative, against a bar of
     // 1e-5) at a quarter of the instructions (the double version was issue bound at 2.1 TB/s)
     const float sum = fmaf(v11, w11, fmaf(v10, w10, fmaf(v01, w01, v00 * w00)));
-    __stcs(dst + (size_t)(p.reverse ? p.C - 1 - c : c) * out_plane, sum * p.scale_out);
+    __stcs(dst + (size_t)(p.reverse ? C - 1 - c : c) * out_plane, sum * p.scale_out);
   }
 }
 
@@ -352,7 +365,10 @@ int launch_warp_affine(const float* in, int B, int C, int in_h, int in_w, const 
     for (int k = 0; k < 4; ++k) p.border[k] = border4[k];
     p.C = C; p.in_h = in_h; p.in_w = in_w; p.out_h = out_h; p.out_w = out_w; p.reverse = reverse; p.scale_out = scale_out;
     dim3 grid((unsigned)((out_w + 255) / 256), (unsigned)out_h, (unsigned)nb);
-    k_warp_affine<<<grid, 256, 0, stream>>>(in + (size_t)b0 * C * in_h * in_w, p, out + (size_t)b0 * C * out_h * out_w);
+    if (C == 12)
+      k_warp_affine<12><<<grid, 256, 0, stream>>>(in + (size_t)b0 * C * in_h * in_w, p, out + (size_t)b0 * C * out_h * out_w);
+    else
+      k_warp_affine<0><<<grid, 256, 0, stream>>>(in + (size_t)b0 * C * in_h * in_w, p, out + (size_t)b0 * C * out_h * out_w);
     EVREP_CUDA_OK(cudaGetLastError());
   }
   return EVREP_OK;
