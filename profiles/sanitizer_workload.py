@@ -37,6 +37,17 @@ eb.otmi_prepare(torch.tensor(eo), rng.random((64, 64, 3)) * (rng.random((64, 64,
 import event_representation_study_b200.n_imagenet as nimg
 en = torch.tensor(np.stack([rng.integers(0, 32, 3000).astype(float), rng.integers(0, 24, 3000).astype(float), np.sort(rng.random(3000)) * 0.04 + 1.0, rng.choice([-1.0, 1.0], 3000)], 1))
 nimg.reshape_then_acc_adj_sort(en, height=24, width=32)
+# later round-2 additions: wire format 3, warp-affine augmentation, large INTER_AREA factors, GWD-A on packed point sets (band kernel)
+pk3 = packed.pack_host(hx["x"].view(np.uint16), hx["y"].view(np.uint16), hx["t"], hx["p"], ev.offsets, H, W, fmt=3)
+if pk3 is not None:
+    eb.ergo12(packed.upload(pk3), H, W)
+lb = eb.detector_input(r, 96, interp="linear", scale_out=1.0, reverse_channels=False)
+Ms = np.tile(np.array([[1.02, 0.05, -3.0], [-0.04, 0.97, 4.0], [0, 0, 1.0]]), (ev.B, 1, 1))
+eb.augment_affine(lb, Ms, [True] * ev.B, [False] * ev.B)
+eb.detector_input(r, 16, mode="squash")
+pa, pb = [rng.random((n_, 4)) for n_ in (130, 64, 1, 200)], [rng.random((n_, 6)) for n_ in (70, 64, 3, 333)]
+(Xa, sa), (Xb, sb) = eb.gwd_pack(pa), eb.gwd_pack(pb)
+print(eb.gwd_kernel_l1(Xa, Xb, 0.7, s_offsets=sa, t_offsets=sb))
 out_g = torch.empty((ev.B, H, W, 12), device="cuda")
 call = eb.GraphedCall(lambda: eb.ergo12(ev, H, W, out=out_g))
 call.replay(); call.replay()
