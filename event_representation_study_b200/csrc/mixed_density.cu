@@ -627,6 +627,8 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_md_tile_heavy(const uint2* 
   constexpr int STRIDE = PS::value.stride;
   const int tid = threadIdx.x;
   const int n_tiles = g.B * g.T;
+  pdl_wait();  // the light kernel: its CTAs skip the heavy buckets, and every kernel of the chain waits for its predecessor
+  pdl_trigger();
   for (int base_id = blockIdx.x * TILE_THREADS; base_id < n_tiles; base_id += gridDim.x * TILE_THREADS) {
     const int id = base_id + tid;
     bool heavy = false;
@@ -693,8 +695,8 @@ static int launch_static(const Geom& g, const Workspace& ws, float* out, cudaStr
   prof_begin(EVREP_K_TILE, stream);
   EVREP_CUDA_OK(launch_pdl(light, grid, TILE_THREADS, smem_l, stream, ws.records, ws.base, ws.hist, ws.wp, g, ws.ticket, out));
   if (!(g.n_max > 0 && g.n_max < (int64_t)MD_PACKED_LIMIT))  // a bucket cannot hold more events than its window: nothing for the wide plan
-    heavy<<<(n_tiles + TILE_THREADS - 1) / TILE_THREADS < n_sm ? (n_tiles + TILE_THREADS - 1) / TILE_THREADS : n_sm, TILE_THREADS, smem_h, stream>>>(
-        ws.records, ws.base, ws.hist, ws.wp, g, out);
+    EVREP_CUDA_OK(launch_pdl(heavy, (n_tiles + TILE_THREADS - 1) / TILE_THREADS < n_sm ? (n_tiles + TILE_THREADS - 1) / TILE_THREADS : n_sm, TILE_THREADS, smem_h,
+                             stream, ws.records, ws.base, ws.hist, ws.wp, g, out));
   prof_end(EVREP_K_TILE, stream);
   EVREP_CUDA_OK(cudaGetLastError());
   return EVREP_OK;
