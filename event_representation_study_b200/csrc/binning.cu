@@ -621,8 +621,16 @@ __device__ __forceinline__ void chunk_rank(ChunkRegs<TT>& r, const ChunkHdr& h, 
       k = 0u;
       meta = MODE == REC_T_IDX ? FUSED_NULL_META : REC_NULL_META;
     }
-    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sm.stage + (slot << 3)), "r"(k), "r"(meta) : "memory");
-    asm volatile("st.shared.u16 [%0], %1;" ::"r"(sm.sbkt + (slot << 1)), "h"((uint16_t)bin) : "memory");
+    if (SPLIT) {
+      // split buckets come with 1024-pixel tiles and at most 4096 buckets: the staged record carries its own bucket in the meta
+      // bits the pixel (10 of 16) and the top of the word leave free, and the copy-out strips them again - one random 2-byte
+      // store and one load per event less on the shared-memory pipe that bounds this kernel
+      meta |= ((bin & 63u) << 10) | ((bin >> 6) << 26);
+      asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sm.stage + (slot << 3)), "r"(k), "r"(meta) : "memory");
+    } else {
+      asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sm.stage + (slot << 3)), "r"(k), "r"(meta) : "memory");
+      asm volatile("st.shared.u16 [%0], %1;" ::"r"(sm.sbkt + (slot << 1)), "h"((uint16_t)bin) : "memory");
+    }
   };
 
 #pragma unroll
@@ -773,8 +781,18 @@ __global__ void __launch_bounds__(BIN_THREADS, EVREP_BIN_CTAS) k_bin(const uint1
   bin_publish(acc, wp + h.b, &sh_tmin, &sh_tmax, &sh_flags, &sh_m1, tid);
   // copy out: consecutive threads hold consecutive records of a run
   uint2* dst = records + h.start;
+  if (SPLIT) {
 #pragma unroll 4
-  for (uint32_t i = tid; i < total; i += BIN_THREADS) dst[i + delta[sbkt[i]]] = stage[i];
+    for (uint32_t i = tid; i < total; i += BIN_THREADS) {
+      uint2 rec = stage[i];
+      const uint32_t bin = ((rec.y >> 10) & 63u) | ((rec.y >> 26) << 6);
+      rec.y &= 0x03ff03ffu;
+      dst[i + delta[bin]] = rec;
+    }
+  } else {
+#pragma unroll 4
+    for (uint32_t i = tid; i < total; i += BIN_THREADS) dst[i + delta[sbkt[i]]] = stage[i];
+  }
 }
 
 // A single-pass alternative was measured and dropped (profiles/README.md, round 2: "k_sortbin"): one kernel that sorts a
