@@ -7,7 +7,9 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libevrep.so")
+# EVREP_LIB selects another build of the same library (A/B tuning builds made with EVREP_NVCC_FLAGS / EVREP_LIB_OUT); it
+# must exist - there is still no fallback
+LIB_PATH = os.environ.get("EVREP_LIB") or os.path.join(_HERE, "lib", "libevrep.so")
 
 # return codes (include/evrep.h)
 OK, EINVAL, EWORKSPACE, ECUDA, EUNSUPPORTED = 0, -1, -2, -3, -4
@@ -35,6 +37,9 @@ SIGNATURES = {
     "evrep_window_flags": (_i, [_vp, _i, _vp, _vp]),
     "evrep_mixed_density_plan_info": (_i, [_i, _i, _vp, _vp, _vp, _i, _i, _i64, _vp]),
     "evrep_mixed_density_batched": (_i, _EV + [_vp, _vp, _vp, _i, _i] + _TAIL),
+    "evrep_mixed_density_specialize": (_i, [_vp, _vp, _vp, _i, _i, _i64]),
+    "evrep_mixed_density_specialize_compile_only": (_i, [_vp, _vp, _vp, _i, _i, _i64, _vp]),
+    "evrep_mixed_density_is_specialized": (_i, [_vp, _vp, _vp, _i, _i, _i64]),
     "evrep_ergo12_batched": (_i, _EV + [_i] + _TAIL),
     "evrep_event_stack_batched": (_i, _EV + [_i] + _TAIL),
     "evrep_time_surface_batched": (_i, _EV + [_vp, _i, _d] + _TAIL),

@@ -11,6 +11,7 @@
 #include <cmath>
 
 #include "evrep_common.cuh"
+#include "md_jit.h"
 
 namespace evrep {
 
@@ -247,6 +248,49 @@ int evrep_mixed_density_plan_info(int H, int W, const int8_t* win, const int8_t*
   EVREP_GUARD_END
 }
 
+// tiles of 1024 or 512 pixels, two buckets per tile (p > 0 first): the geometry of the compile-time specialised kernels
+static bool tile_split(int H, int W, int tile_px, Geom* g) {
+  if (H < 1 || W < 1 || H > 65535 || W > 65535) return false;
+  const int shift = tile_px == 512 ? 9 : 10;
+  const int64_t hw = (int64_t)H * W;
+  const int64_t T = (hw + tile_px - 1) >> shift;
+  if (2 * T > MAX_TILES) return false;
+  g->H = H;
+  g->W = W;
+  g->HW = (int)hw;
+  g->tile_shift = shift;
+  g->tile_px = tile_px;
+  g->T = (int)T;
+  g->split = 1;
+  g->div_x = g->div_y = 1;
+  g->Tb = g->T << 1;
+  g->t_magic = ((1ull << 44) + (unsigned long long)g->T - 1) / (unsigned long long)g->T;
+  return true;
+}
+
+int evrep_mixed_density_specialize(const int8_t* win, const int8_t* func, const int8_t* agg, int C, int stacking, int64_t max_events_per_window) {
+  EVREP_GUARD_BEGIN
+  if (!win || !func || !agg) { set_error("null channel description"); return EVREP_EINVAL; }
+  MdPlan plan;
+  EVREP_TRY(build_md_plan(win, func, agg, C, stacking, max_events_per_window > 0 ? max_events_per_window : 1, &plan));
+  if (plan.static_id) return EVREP_OK;  // an ERGO-12 tuple: its kernels were built ahead of time
+  return evrep::md_jit_specialize(win, func, agg, C, stacking, max_events_per_window, true, nullptr);
+  EVREP_GUARD_END
+}
+
+int evrep_mixed_density_specialize_compile_only(const int8_t* win, const int8_t* func, const int8_t* agg, int C, int stacking,
+                                                int64_t max_events_per_window, size_t* cubin_bytes) {
+  EVREP_GUARD_BEGIN
+  if (!win || !func || !agg) { set_error("null channel description"); return EVREP_EINVAL; }
+  return evrep::md_jit_specialize(win, func, agg, C, stacking, max_events_per_window, false, cubin_bytes);
+  EVREP_GUARD_END
+}
+
+int evrep_mixed_density_is_specialized(const int8_t* win, const int8_t* func, const int8_t* agg, int C, int stacking, int64_t max_events_per_window) {
+  if (!win || !func || !agg || C < 1 || C > EVREP_MAX_CHANNELS) return 0;
+  return evrep::md_jit_find(win, func, agg, C, stacking, max_events_per_window) ? 1 : 0;
+}
+
 int evrep_mixed_density_batched(const uint16_t* x, const uint16_t* y, const void* t, int t_bytes, const int8_t* p,
                                 const int64_t* win_offsets, int B, int H, int W, const int8_t* win, const int8_t* func,
                                 const int8_t* agg, int C, int stacking, float* out, void* workspace, size_t workspace_bytes,
@@ -261,6 +305,22 @@ int evrep_mixed_density_batched(const uint16_t* x, const uint16_t* y, const void
   EVREP_TRY(build_md_plan(win, func, agg, C, stacking, n_max, &plan));
   Geom g;
   memset(&g, 0, sizeof(g));
+  // a tuple the caller has specialised (evrep_mixed_density_specialize): the ERGO-12 pipeline with that tuple's kernels
+  if (!plan.static_id && evrep::md_jit_count() > 0) {
+    if (evrep::JitProgram* jp = evrep::md_jit_find(win, func, agg, C, stacking, n_max)) {
+      // (bulk stores move whole 16-byte units: any C on sensors with H * W * C a multiple of 4)
+      if (((int64_t)H * W * C) % 4 == 0 && tile_split(H, W, evrep::md_jit_tile_px(jp), &g)) {
+        g.B = B;
+        g.total = total;
+        g.n_max = n_max;
+        Workspace ws;
+        EVREP_TRY(carve_checked(workspace, workspace_bytes, B, total, g.Tb, &ws));
+        EVREP_TRY(run_binning(ev, win_offsets, g, ws, REC_T_WMASK, 0, nullptr, (cudaStream_t)stream));
+        return evrep::md_jit_launch(jp, g, ws, out, (cudaStream_t)stream);
+      }
+      memset(&g, 0, sizeof(g));
+    }
+  }
   EVREP_TRY(choose_tile(H, W, (size_t)plan.stride * 4, &g));
   // the compile-time specialised ERGO-12 kernels (1024-pixel tiles) want every tile's events split by polarity
   if (plan.static_id && g.tile_px == 1024 && 2 * g.T <= MAX_TILES) EVREP_TRY(choose_tile(H, W, (size_t)plan.stride * 4, &g, 1));

@@ -1,7 +1,7 @@
 // Accumulator plan of the mixed-density tile kernel, buildable at run time (any tuple) and at compile time
 // (the ERGO-12 tuples, so that their kernels are fully specialised).
 #pragma once
-#include "evrep_common.cuh"
+#include "md_device.cuh"
 
 namespace evrep {
 

@@ -8,6 +8,15 @@ from ..._single import one_window, one_window_structured, to_host
 from .operations import Operations
 
 
+# Not in the reference: after this many `stack` calls with one (windows, functions, aggregations) tuple - counted per
+# process, the reference builds a new instance per sample (optimized_representation.py:131-134) - the tuple is compiled into
+# specialised kernels (batched.specialize_mixed_density: ~2 s once, then every call runs the ERGO-12 pipeline with this
+# tuple's kernels instead of the interpreted kernel).  A search that evaluates a candidate over a dataset crosses the
+# threshold after a handful of samples; None disables it.
+SPECIALIZE_AFTER_CALLS = 16
+_TUPLE_CALLS = {}
+
+
 class MixedDensityEventStack:
     def __init__(self, stack_size, num_of_events, height, width, indexes_functions_aggregations, stacking_type):
         self.stack_size = stack_size
@@ -16,6 +25,18 @@ class MixedDensityEventStack:
         self.width = width
         self.indexes_functions_aggregations = indexes_functions_aggregations
         self.stacking_type = stacking_type
+
+    def _maybe_specialize(self, w, f, a, n):
+        if SPECIALIZE_AFTER_CALLS is None or self.stacking_type != "SBN":
+            return
+        key = (tuple(w), tuple(f), tuple(a))
+        calls = _TUPLE_CALLS.get(key, 0) + 1
+        if calls <= SPECIALIZE_AFTER_CALLS:
+            if len(_TUPLE_CALLS) > 4096:
+                _TUPLE_CALLS.clear()
+            _TUPLE_CALLS[key] = calls
+        if calls == SPECIALIZE_AFTER_CALLS:
+            eb.specialize_mixed_density(w, f, a, "SBN", max_events_per_window=max(int(n), 1 << 20))
 
     def _spec(self):
         w, f, a = self.indexes_functions_aggregations
@@ -35,6 +56,7 @@ class MixedDensityEventStack:
         except IndexError:
             # an out-of-range pixel makes every torch_scatter call raise inside make_stack: all channels zero (reference :120-127)
             return np.zeros((self.height, self.width, self.stack_size), np.float64)
+        self._maybe_specialize(w, f, a, len(t))
         return to_host(eb.mixed_density(ev, self.height, self.width, w, f, a, self.stacking_type)[0], torch.float64, _scale)
 
     def stack(self, event_sequence, _scale=None):

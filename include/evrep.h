@@ -143,6 +143,28 @@ int evrep_mixed_density_batched(const uint16_t* x, const uint16_t* y, const void
                                 const int8_t* agg, int C, int stacking, float* out, void* workspace,
                                 size_t workspace_bytes, evrep_stream_t stream);
 
+/* Run-time specialisation of evrep_mixed_density_batched for ONE tuple - what the representation search needs, where a
+ * candidate tuple (mixed_density_event_stack.py:25-46 as driven by the search loop) is evaluated on thousands of windows.
+ * The two ERGO-12 tuples have kernels built ahead of time; any other tuple runs an interpreted kernel that is several times
+ * slower.  This call compiles the same kernel templates for the given tuple with NVRTC (sm_100a; a few seconds, once per
+ * tuple and process) and makes them resident on the current device; from then on evrep_mixed_density_batched launches them
+ * whenever it is called with exactly this tuple (same results within the documented tolerance; integer channels bit exact).
+ * max_events_per_window bounds the largest window of later calls (it picks the limb width of the hot-tile kernel; a later
+ * call with larger windows silently uses the interpreted kernel).  Envelope: SBN stacking, per-pixel accumulators that fit
+ * a tile's shared memory (at most 55 packed words: every 12-channel tuple of the reference's vocabulary does); at call time a
+ * sensor with H * W * C a multiple of 4 and at most 2 Mpx (1 Mpx for tuples above 27 words, which take 512-pixel tiles).
+ * EVREP_EUNSUPPORTED otherwise (and when libnvrtc / the driver library cannot be opened) - the interpreted
+ * kernel keeps serving such tuples.  Host call; thread safe. */
+int evrep_mixed_density_specialize(const int8_t* win, const int8_t* func, const int8_t* agg, int C, int stacking,
+                                   int64_t max_events_per_window);
+/* The same compilation without loading anything on a device (works on a machine without a GPU): *cubin_bytes receives the
+ * size of the sm_100a image.  Used by the build check and the CPU tests. */
+int evrep_mixed_density_specialize_compile_only(const int8_t* win, const int8_t* func, const int8_t* agg, int C, int stacking,
+                                                int64_t max_events_per_window, size_t* cubin_bytes);
+/* 1 when a call with this tuple and largest window would run specialised kernels, else 0. */
+int evrep_mixed_density_is_specialized(const int8_t* win, const int8_t* func, const int8_t* agg, int C, int stacking,
+                                       int64_t max_events_per_window);
+
 /* ERGO-12: version 2 = the active tuple (optimized_representation.py:86-115), 1 = the commented one (:16-66). */
 int evrep_ergo12_batched(const uint16_t* x, const uint16_t* y, const void* t, int t_bytes, const int8_t* p,
                          const int64_t* win_offsets, int B, int H, int W, int version, float* out, void* workspace,

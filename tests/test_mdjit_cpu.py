@@ -1,0 +1,78 @@
+"""Host side of the run-time specialised mixed-density kernels: NVRTC turns a tuple into an sm_100a image without a GPU
+(evrep_mixed_density_specialize_compile_only), tuples outside the envelope are refused, nothing is registered as
+specialised until it has been compiled."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from event_representation_study_b200 import _lib
+
+lib = _lib.lib
+
+
+def codes(wi, fu, ag):
+    return (np.array(wi, np.int8), np.array([_lib.FUNCS[f] for f in fu], np.int8), np.array([_lib.AGGS[a] for a in ag], np.int8))
+
+
+def compile_only(wi, fu, ag, stacking=0, n_max=1 << 20):
+    w, f, a = codes(wi, fu, ag)
+    nb = ctypes.c_size_t(0)
+    rc = lib.evrep_mixed_density_specialize_compile_only(w.ctypes.data, f.ctypes.data, a.ctypes.data, len(wi), stacking, n_max, ctypes.byref(nb))
+    return rc, nb.value
+
+
+TUPLE = ([2, 1, 3, 5, 0, 0, 6, 4, 0, 2, 4, 1],
+         ["timestamp", "polarity", "count", "timestamp_pos", "timestamp_neg", "count_pos", "count_neg", "polarity", "timestamp", "count", "timestamp_neg", "count_pos"],
+         ["variance", "mean", "sum", "max", "mean", "mean", "sum", "variance", "sum", "max", "min", "mean"])
+
+
+def test_nvrtc_compiles_a_tuple_without_a_gpu(tmp_path):
+    dump = tmp_path / "tuple.cubin"
+    os.environ["EVREP_JIT_DUMP"] = str(dump)
+    try:
+        rc, nbytes = compile_only(*TUPLE)
+    finally:
+        del os.environ["EVREP_JIT_DUMP"]
+    assert rc == _lib.OK, lib.evrep_last_error().decode()
+    assert nbytes > 10_000
+    w, f, a = codes(*TUPLE)
+    # compiled, hence known to the library: a later evrep_mixed_density_batched with this tuple would take these kernels
+    assert lib.evrep_mixed_density_is_specialized(w.ctypes.data, f.ctypes.data, a.ctypes.data, 12, 0, 1000) == 1
+    assert lib.evrep_mixed_density_is_specialized(w.ctypes.data, f.ctypes.data, a.ctypes.data, 12, 0, 1 << 23) == 0  # needs a narrower limb than compiled
+    if dump.exists():
+        res = subprocess.run(["cuobjdump", "-res-usage", str(dump)], capture_output=True, text=True)
+        if res.returncode == 0:
+            assert "k_md_tile_static" in res.stdout and "k_md_tile_heavy" in res.stdout
+
+
+def test_second_compilation_is_served_from_the_cache():
+    import time
+    compile_only(*TUPLE)
+    t0 = time.time()
+    rc, nbytes = compile_only(*TUPLE)
+    assert rc == _lib.OK and nbytes > 0 and time.time() - t0 < 0.2
+
+
+@pytest.mark.parametrize("case", ["sbt", "too-many-sums"])
+def test_outside_the_envelope_is_refused(case):
+    wi, fu, ag = TUPLE
+    if case == "sbt":
+        rc, _ = compile_only(wi, fu, ag, stacking=1)
+    else:  # 28 distinct timestamp-variance groups: the packed plan alone exceeds a tile's shared memory
+        wi = [k % 7 for k in range(28)]
+        fu = ["timestamp", "timestamp_pos", "timestamp_neg", "timestamp"][:1] * 7 + ["timestamp_pos"] * 7 + ["timestamp_neg"] * 7 + ["timestamp"] * 7
+        rc, _ = compile_only(wi, fu, ["variance"] * 28)
+    assert rc == _lib.EUNSUPPORTED
+    assert lib.evrep_last_error()
+
+
+def test_ergo_tuples_need_no_compilation():
+    """evrep_mixed_density_specialize on an ERGO-12 tuple returns at once: those kernels are built ahead of time."""
+    wi = [0, 3, 2, 6, 5, 6, 2, 5, 1, 0, 4, 1]
+    fu = ["polarity", "timestamp_neg", "count_neg", "polarity", "count_pos", "count", "timestamp_pos", "count_neg", "timestamp_neg", "timestamp_pos", "timestamp", "count"]
+    ag = ["variance", "variance", "mean", "sum", "mean", "sum", "mean", "mean", "max", "max", "max", "mean"]
+    w, f, a = codes(wi, fu, ag)
+    assert lib.evrep_mixed_density_specialize(w.ctypes.data, f.ctypes.data, a.ctypes.data, 12, 0, 1 << 20) == _lib.OK  # no device needed
