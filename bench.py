@@ -15,7 +15,8 @@ roofline  the kernel that writes the output (k_md_tile), timed with CUDA events 
 cpu_baseline  the numpy oracle (a port of the reference algorithm) on the host cores, bounded sample
 gwd       BASELINE.json's second metric ("GWD pairs/s vs CPU ref", configs[4]): the 12 x 1000 GWD-A matrix, columns sharded
           over the ranks, one NCCL all-gather when N > 1; plus one pair at the paper's problem sizes (compute_otmi.py:96-211)
-configs   BASELINE configs[1] (ERGO-12 Gen1, batch 32) and configs[2] (TimeSurface + EventStack + TORE, fused call)
+configs   BASELINE configs[1] (ERGO-12 Gen1, batch 32) and configs[2] (TimeSurface + EventStack + TORE, fused call); search_tuple:
+          one candidate of the representation search on the headline batch, interpreted and run-time specialised kernels
 parity_spot_check  windows of the TIMED output buffers against the oracle on the same events
 dropin    the per-window numpy -> numpy call the reference pipelines make today (get_item_transform), full output copied back
 (the last three on rank 0 at N = 1 only; --no-extras skips them and gwd)
@@ -378,7 +379,59 @@ def bench_configs(dev, steps):
         "window": 0, "events": n0, "event_stack_bit_exact": bool(np.array_equal(got_es, want_es)),
         "time_surface_err_over_tol": rel(got_ts, want_ts.reshape(got_ts.shape), 1e-30), "tore_err_over_tol": rel(got_to, want_to, 1e-6),
         "tol": "1e-5 relative (+1e-6 absolute for TORE: log(age + 1) - log(151) in float32); a value <= 1 passes"}
+    del ev, o_ts, o_es, o_to
+    out["search_tuple"] = bench_search_tuple(dev, steps, peak)
     return out
+
+
+def bench_search_tuple(dev, steps, peak):
+    """What the representation search runs (mixed_density_event_stack.py:25-151 with an arbitrary tuple): one candidate on the
+    headline batch (32 x 1 M events at 1 Mpx) through the interpreted kernel and, after evrep_mixed_density_specialize, through
+    kernels compiled for that tuple at run time; one window of the timed buffer against the oracle."""
+    import time
+    import torch
+    import event_representation_study_b200.batched as eb
+    from event_representation_study_b200.synth import device_batch
+    from oracle import representations as orep
+    h, w, N, B = H, W, 1_000_000, 32
+    wi = [4, 2, 4, 6, 5, 1, 0, 4, 4, 5, 1, 2]
+    fu = ["timestamp", "timestamp_neg", "count_pos", "timestamp", "timestamp_neg", "timestamp", "timestamp_neg", "polarity", "timestamp_pos",
+          "count_pos", "timestamp_neg", "timestamp_pos"]
+    ag = ["max", "variance", "variance", "max", "max", "mean", "mean", "mean", "sum", "max", "variance", "max"]
+    d = device_batch(B, N, h, w, dev, seed=4000)
+    ev = eb.EventBatch(d["x"], d["y"], d["t"], d["p"], d["offsets"].cpu().numpy())
+    o = torch.empty((B, h, w, 12), device=dev)
+    call = lambda: eb.mixed_density(ev, h, w, wi, fu, ag, "SBN", out=o)
+    rec = {"workload": "one search candidate (random 12-channel tuple, SBN), 1 Mpx, 1M ev/window, batch 32", "unit": "Gevents/s",
+           "windows": wi, "functions": fu, "aggregations": ag}
+    already = eb.mixed_density_is_specialized(wi, fu, ag, "SBN", N)
+    if not already:
+        sec_i = _timed(call, max(3, steps // 4))
+        rec["interpreted"] = {"value": B * N / sec_i / 1e9, "ms_per_step": sec_i * 1e3}
+    t0 = time.time()
+    ok = eb.specialize_mixed_density(wi, fu, ag, "SBN", max_events_per_window=N)
+    rec["specialize_seconds"] = time.time() - t0
+    rec["specialized"] = bool(ok)
+    if ok:
+        sec = _timed(call, steps)
+        alg = B * (N * BYTES_PER_EVENT + h * w * 12 * 4)
+        rec.update({"value": B * N / sec / 1e9, "ms_per_step": sec * 1e3,
+                    "roofline": {"bound": "hbm", "achieved": alg / sec / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / sec / 1e9 / peak,
+                                 "algorithmic_bytes_per_step": alg}})
+        if "interpreted" in rec:
+            rec["speedup_vs_interpreted"] = rec["interpreted"]["ms_per_step"] / rec["ms_per_step"]
+    n0 = int(ev.offsets[1])
+    x, y, t, p = (v[:n0].cpu().numpy() for v in (ev.x, ev.y, ev.t, ev.p))
+    with np.errstate(all="ignore"):
+        want = orep.mixed_density_event_stack(x.view(np.uint16), y.view(np.uint16), t.astype(np.int64), p, h, w, wi, fu, ag, "SBN")
+    got = o[0].cpu().numpy().astype(np.float64)
+    nan_ok = bool(np.array_equal(np.isnan(got), np.isnan(want)))
+    err = np.abs(got - want) / (2e-7 + 1e-5 * np.abs(want))
+    ints = [c for c, (f, a) in enumerate(zip(fu, ag)) if f in ("count", "count_pos", "count_neg", "polarity") and a in ("sum", "max", "min")]
+    rec["parity_spot_check"] = {"window": 0, "events": n0, "err_over_tol": float(np.nanmax(err)), "nan_pattern_equal": nan_ok,
+                                "integer_channels_bit_exact": bool(all(np.array_equal(got[:, :, c], want[:, :, c]) for c in ints)),
+                                "tol": "2e-7 + 1e-5 relative; a value <= 1 passes"}
+    return rec
 
 
 def parity_spot_check(ev, out, windows):
