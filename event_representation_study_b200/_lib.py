@@ -38,6 +38,7 @@ SIGNATURES = {
     "evrep_mixed_density_plan_info": (_i, [_i, _i, _vp, _vp, _vp, _i, _i, _i64, _vp]),
     "evrep_mixed_density_batched": (_i, _EV + [_vp, _vp, _vp, _i, _i] + _TAIL),
     "evrep_mixed_density_specialize": (_i, [_vp, _vp, _vp, _i, _i, _i64]),
+    "evrep_mixed_density_specialize_async": (_i, [_vp, _vp, _vp, _i, _i, _i64]),
     "evrep_mixed_density_specialize_compile_only": (_i, [_vp, _vp, _vp, _i, _i, _i64, _vp]),
     "evrep_mixed_density_is_specialized": (_i, [_vp, _vp, _vp, _i, _i, _i64]),
     "evrep_ergo12_batched": (_i, _EV + [_i] + _TAIL),

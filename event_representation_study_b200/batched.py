@@ -230,18 +230,26 @@ def mixed_density(ev, H, W, windows, functions, aggregations, stacking="SBN", ou
     return out
 
 
-def specialize_mixed_density(windows, functions, aggregations, stacking="SBN", max_events_per_window=1 << 20, device=None):
+def specialize_mixed_density(windows, functions, aggregations, stacking="SBN", max_events_per_window=1 << 20, device=None, wait=True):
     """Compile kernels for ONE (windows, functions, aggregations) tuple at run time (NVRTC, a few seconds, once per process) and
     load them on `device` (default: the current one); `mixed_density` calls with that tuple then run 4 - 6 x faster than the
     interpreted kernel every other non-ERGO tuple takes (C-ABI: evrep_mixed_density_specialize).  What a representation
     search wants before it evaluates a candidate on a dataset.  Returns True, or False when the tuple is outside the
-    specialised envelope (SBT stacking, accumulators beyond a tile's shared memory; list entries the reference would swallow
-    into zero channels are fine) - such tuples keep running on the interpreted kernel."""
+    specialised envelope (accumulators beyond a tile's shared memory; list entries the reference would swallow
+    into zero channels are fine) - such tuples keep running on the interpreted kernel.  wait=False compiles on a background
+    thread and returns at once; `mixed_density` switches kernels when the program is ready (mixed_density_is_specialized)."""
     win, func, agg, C = _codes(windows, functions, aggregations)
-    if stacking != "SBN":
+    if stacking not in STACKING:
         return False
+    st = STACKING[stacking]
+    if not wait:
+        rc = lib.evrep_mixed_density_specialize_async(win.ctypes.data, func.ctypes.data, agg.ctypes.data, C, st, int(max_events_per_window))
+        if rc == _lib.EUNSUPPORTED:
+            return False
+        check(rc)
+        return True
     with torch.cuda.device(device if device is not None else torch.cuda.current_device()):
-        rc = lib.evrep_mixed_density_specialize(win.ctypes.data, func.ctypes.data, agg.ctypes.data, C, STACKING["SBN"], int(max_events_per_window))
+        rc = lib.evrep_mixed_density_specialize(win.ctypes.data, func.ctypes.data, agg.ctypes.data, C, st, int(max_events_per_window))
     if rc == _lib.EUNSUPPORTED:
         return False
     check(rc)
@@ -250,9 +258,9 @@ def specialize_mixed_density(windows, functions, aggregations, stacking="SBN", m
 
 def mixed_density_is_specialized(windows, functions, aggregations, stacking="SBN", max_events_per_window=1):
     win, func, agg, C = _codes(windows, functions, aggregations)
-    if stacking != "SBN":
+    if stacking not in STACKING:
         return False
-    return bool(lib.evrep_mixed_density_is_specialized(win.ctypes.data, func.ctypes.data, agg.ctypes.data, C, STACKING["SBN"], int(max_events_per_window)))
+    return bool(lib.evrep_mixed_density_is_specialized(win.ctypes.data, func.ctypes.data, agg.ctypes.data, C, STACKING[stacking], int(max_events_per_window)))
 
 
 def ergo12(ev, H, W, version=2, out=None):

@@ -278,6 +278,16 @@ int evrep_mixed_density_specialize(const int8_t* win, const int8_t* func, const 
   EVREP_GUARD_END
 }
 
+int evrep_mixed_density_specialize_async(const int8_t* win, const int8_t* func, const int8_t* agg, int C, int stacking, int64_t max_events_per_window) {
+  EVREP_GUARD_BEGIN
+  if (!win || !func || !agg) { set_error("null channel description"); return EVREP_EINVAL; }
+  MdPlan plan;
+  EVREP_TRY(build_md_plan(win, func, agg, C, stacking, max_events_per_window > 0 ? max_events_per_window : 1, &plan));
+  if (plan.static_id) return EVREP_OK;
+  return evrep::md_jit_specialize(win, func, agg, C, stacking, max_events_per_window, false, nullptr, false);
+  EVREP_GUARD_END
+}
+
 int evrep_mixed_density_specialize_compile_only(const int8_t* win, const int8_t* func, const int8_t* agg, int C, int stacking,
                                                 int64_t max_events_per_window, size_t* cubin_bytes) {
   EVREP_GUARD_BEGIN
@@ -309,13 +319,15 @@ int evrep_mixed_density_batched(const uint16_t* x, const uint16_t* y, const void
   if (!plan.static_id && evrep::md_jit_count() > 0) {
     if (evrep::JitProgram* jp = evrep::md_jit_find(win, func, agg, C, stacking, n_max)) {
       // (bulk stores move whole 16-byte units: any C on sensors with H * W * C a multiple of 4)
-      if (((int64_t)H * W * C) % 4 == 0 && tile_split(H, W, evrep::md_jit_tile_px(jp), &g)) {
+      // a program that cannot be loaded on this device (compiled elsewhere, driver library missing) leaves the call to the interpreted kernel
+      if (((int64_t)H * W * C) % 4 == 0 && tile_split(H, W, evrep::md_jit_tile_px(jp), &g) && evrep::md_jit_prepare(jp) == EVREP_OK) {
         g.B = B;
         g.total = total;
         g.n_max = n_max;
         Workspace ws;
         EVREP_TRY(carve_checked(workspace, workspace_bytes, B, total, g.Tb, &ws));
-        EVREP_TRY(run_binning(ev, win_offsets, g, ws, REC_T_WMASK, 0, nullptr, (cudaStream_t)stream));
+        EVREP_TRY(run_binning(ev, win_offsets, g, ws, stacking == EVREP_STACK_SBN ? REC_T_WMASK : REC_T_ONLY, 0, nullptr, (cudaStream_t)stream));
+        if (stacking == EVREP_STACK_SBT) EVREP_TRY(evrep::launch_sbt_negsel(g, ws, ev, (cudaStream_t)stream));
         return evrep::md_jit_launch(jp, g, ws, out, (cudaStream_t)stream);
       }
       memset(&g, 0, sizeof(g));

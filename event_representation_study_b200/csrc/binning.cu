@@ -821,7 +821,8 @@ static int launch_bin_mode(int mode, const Events& ev, const Geom& g, const Work
     case REC_T_SNAP: return launch_bin<TT, REC_T_SNAP, false>(ev, g, ws, n_sc, vec, stream);
     case REC_T_TORE: return launch_bin<TT, REC_T_TORE, false>(ev, g, ws, n_sc, vec, stream);
     case REC_T_IDX: return launch_bin<TT, REC_T_IDX, false>(ev, g, ws, n_sc, vec, stream);
-    default: return launch_bin<TT, REC_T_ONLY, false>(ev, g, ws, n_sc, vec, stream);
+    default:
+      return g.split ? launch_bin<TT, REC_T_ONLY, true>(ev, g, ws, n_sc, vec, stream) : launch_bin<TT, REC_T_ONLY, false>(ev, g, ws, n_sc, vec, stream);
   }
 }
 

@@ -123,6 +123,7 @@ int prepare_windows(const Events& ev, const int64_t* win_offsets_host, const Geo
 bool events_vectorisable(const Events& ev);
 
 int launch_md_tile(const Geom& g, const Workspace& ws, const MdPlan& plan, const Events& ev, float* out, cudaStream_t stream);
+int launch_sbt_negsel(const Geom& g, const Workspace& ws, const Events& ev, cudaStream_t stream);  // SBT: which time windows hold a p == -1 event
 int launch_event_stack_tile(const Geom& g, const Workspace& ws, int stack_size, float* out, cudaStream_t stream);
 int launch_time_surface_tile(const Geom& g, const Workspace& ws, int S, double tau, float* out, cudaStream_t stream);
 int launch_tore_tile(const Geom& g, const Workspace& ws, int k, float* out, cudaStream_t stream);

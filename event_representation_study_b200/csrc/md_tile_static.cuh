@@ -204,13 +204,41 @@ __device__ __forceinline__ void md_finalise_static(const uint32_t* a, float inv_
   ((o[CI] = md_value_static<PS, CI>(a, inv_delta, delta, delta_u, has_m1)), ...);
 }
 
+// SBT windows (mixed_density_event_stack.py:76-107): the reference's float64 comparisons on t_s = (t - t_min) / (t_max - t_min),
+// bit for bit (a zero interval gives NaN / inf: member of window 0 only).  Shared by the interpreted kernel, the
+// specialised kernels and k_sbt_negsel.
+__device__ __forceinline__ uint32_t md_sbt_wmask(uint32_t tt, double delta) {
+  const double ts = (double)tt / delta;
+  const double f = 1.0 / 3.0;
+  uint32_t wmask = 1u;
+  if (ts <= 1.0 * f && ts >= 0.0 * f) wmask |= 2u;
+  if (ts <= 2.0 * f && ts >= 1.0 * f) wmask |= 4u;
+  if (ts <= 3.0 * f && ts >= 2.0 * f) wmask |= 8u;
+  if (ts <= 0.5) wmask |= 16u;
+  if (ts <= 0.25) wmask |= 32u;
+  if (ts <= 0.125) wmask |= 64u;
+  if (ts <= 0.0625) wmask |= 128u;
+  return wmask;
+}
+// prefetch slots past the end of a bucket: a record that touches nothing (SBN: window mask 0; SBT derives the mask from the
+// timestamp, so there it must be the null record proper)
+template <typename PS>
+__device__ __forceinline__ uint2 md_padding_record() {
+  return make_uint2(0u, PS::value.stacking == EVREP_STACK_SBT ? REC_NULL_META : 0u);
+}
+template <typename PS>
+__device__ __forceinline__ bool md_record_live(uint32_t meta) {
+  return PS::value.stacking == EVREP_STACK_SBT ? !rec_is_null(meta) : meta != 0u;
+}
+
 template <typename PS, int CLS>
-__device__ __forceinline__ void md_accumulate_static(uint32_t* acc, const uint2 r, int32_t tmin, uint32_t not_m1) {
+__device__ __forceinline__ void md_accumulate_static(uint32_t* acc, const uint2 r, int32_t tmin, uint32_t not_m1, double delta) {
   constexpr int STRIDE = PS::value.stride, G = PS::value.G;
   uint32_t* a = acc + (r.y & 0xffffu) * STRIDE;
   const uint32_t pc = (r.y >> 24) & 3u;
   const uint32_t tt = (uint32_t)((int32_t)r.x - tmin);
-  const uint32_t wmask = (r.y >> 16) & 0xffu;  // 0 for null and padding records: member of no window
+  uint32_t wmask = (r.y >> 16) & 0xffu;  // 0 for null and padding records: member of no window
+  if constexpr (PS::value.stacking == EVREP_STACK_SBT) wmask = rec_is_null(r.y) ? 0u : md_sbt_wmask(tt, delta);
   uint32_t M;
   if constexpr (CLS == 1) {
     M = wmask | (wmask << 8);
@@ -229,12 +257,12 @@ __device__ __forceinline__ void md_accumulate_static(uint32_t* acc, const uint2 
 }
 // record i of a bucket pair whose first n_pos records are the p > 0 events (n_pos = 0xffffffff: not split, any class)
 template <typename PS, bool SPLIT>
-__device__ __forceinline__ void md_accumulate_at(uint32_t* acc, const uint2 r, uint32_t i, uint32_t n_pos, int32_t tmin, uint32_t not_m1) {
+__device__ __forceinline__ void md_accumulate_at(uint32_t* acc, const uint2 r, uint32_t i, uint32_t n_pos, int32_t tmin, uint32_t not_m1, double delta) {
   if constexpr (SPLIT) {
-    if (i < n_pos) md_accumulate_static<PS, 1>(acc, r, tmin, not_m1);
-    else md_accumulate_static<PS, 2>(acc, r, tmin, not_m1);
+    if (i < n_pos) md_accumulate_static<PS, 1>(acc, r, tmin, not_m1, delta);
+    else md_accumulate_static<PS, 2>(acc, r, tmin, not_m1, delta);
   } else {
-    md_accumulate_static<PS, 0>(acc, r, tmin, not_m1);
+    md_accumulate_static<PS, 0>(acc, r, tmin, not_m1, delta);
   }
 }
 
@@ -343,7 +371,7 @@ __global__ void __launch_bounds__(TILE_THREADS, (PS::value.stride * TP * 4 <= 74
   constexpr int STRIDE = PS::value.stride, C = PS::value.C, PPT = TP / TILE_THREADS;
   constexpr int SLAB = PPT * 32 * STRIDE;  // accumulator words of one warp's pixels
   constexpr int PRE = 3;
-  static_assert(PS::value.stacking == EVREP_STACK_SBN && TP % TILE_THREADS == 0, "static path: SBN windows, whole pixels per thread");
+  static_assert(TP % TILE_THREADS == 0, "whole pixels per thread");
   static_assert(C <= STRIDE, "outputs must fit the accumulator footprint");
   static_assert((SLAB * 4) % 16 == 0, "slabs must start on 16-byte boundaries");
   static_assert(!LIGHT_ONLY || PS::value.packed, "only packed plans have an event limit");
@@ -365,7 +393,7 @@ __global__ void __launch_bounds__(TILE_THREADS, (PS::value.stride * TP * 4 <= 74
 #pragma unroll
   for (int j = 0; j < PRE; ++j) {
     const uint32_t i = tid + j * TILE_THREADS;
-    pre[j] = i < h.count ? __ldg(h.rec + i) : make_uint2(0u, 0u);  // meta 0: member of no window, touches nothing
+    pre[j] = i < h.count ? __ldg(h.rec + i) : md_padding_record<PS>();
   }
   __syncthreads();
 
@@ -379,16 +407,17 @@ __global__ void __launch_bounds__(TILE_THREADS, (PS::value.stride * TP * 4 <= 74
 
     if (!skip) {
       const uint32_t not_m1 = ~h.has_m1;
+      const double delta = (double)h.delta_u;  // (only the SBT window test reads it)
 #pragma unroll
       for (int j = 0; j < PRE; ++j)
-        if (pre[j].y) md_accumulate_at<PS, SPLIT>(acc, pre[j], tid + j * TILE_THREADS, h.n_pos, h.tmin, not_m1);
+        if (md_record_live<PS>(pre[j].y)) md_accumulate_at<PS, SPLIT>(acc, pre[j], tid + j * TILE_THREADS, h.n_pos, h.tmin, not_m1, delta);
       for (uint32_t i = tid + PRE * TILE_THREADS; i < h.count; i += TILE_THREADS)
-        md_accumulate_at<PS, SPLIT>(acc, __ldg(h.rec + i), i, h.n_pos, h.tmin, not_m1);
+        md_accumulate_at<PS, SPLIT>(acc, __ldg(h.rec + i), i, h.n_pos, h.tmin, not_m1, delta);
     }
 #pragma unroll
     for (int j = 0; j < PRE; ++j) {  // next bucket's records: in flight during finalise + store
       const uint32_t i = tid + j * TILE_THREADS;
-      pre[j] = (more && i < hn.count) ? __ldg(hn.rec + i) : make_uint2(0u, 0u);
+      pre[j] = (more && i < hn.count) ? __ldg(hn.rec + i) : md_padding_record<PS>();
     }
     if (tid == 0) s_next = my_ticket + 2 * (int)gridDim.x;
     __syncthreads();  // (A) every record of the bucket is accumulated
@@ -436,7 +465,8 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_md_tile_heavy(const uint2* 
         for (int i = tid; i < (STRIDE * TP + 3) / 4; i += TILE_THREADS) a4[i] = make_uint4(0, 0, 0, 0);
         __syncthreads();
         const uint32_t not_m1 = ~h.has_m1;
-        for (uint32_t i = tid; i < h.count; i += TILE_THREADS) md_accumulate_at<PS, SPLIT>(acc, __ldg(h.rec + i), i, h.n_pos, h.tmin, not_m1);
+        const double delta = (double)h.delta_u;
+        for (uint32_t i = tid; i < h.count; i += TILE_THREADS) md_accumulate_at<PS, SPLIT>(acc, __ldg(h.rec + i), i, h.n_pos, h.tmin, not_m1, delta);
         __syncthreads();
         md_finalise_store_warp<PS, TP>(acc + (tid >> 5) * (TP / TILE_THREADS * 32 * STRIDE), h, g, out);
         md_wait_store_warp();

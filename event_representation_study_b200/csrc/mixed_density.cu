@@ -157,17 +157,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_md_tile(const uint2* __restric
     if (P.stacking == EVREP_STACK_SBN) {
       wmask = (r.y >> 16) & 0xffu;
     } else {
-      // SBT windows (mixed_density_event_stack.py:76-107): float64 comparisons on t_s
-      const double ts = (double)tt / delta;
-      const double f = 1.0 / 3.0;
-      wmask = 1u;
-      if (ts <= 1.0 * f && ts >= 0.0 * f) wmask |= 2u;
-      if (ts <= 2.0 * f && ts >= 1.0 * f) wmask |= 4u;
-      if (ts <= 3.0 * f && ts >= 2.0 * f) wmask |= 8u;
-      if (ts <= 0.5) wmask |= 16u;
-      if (ts <= 0.25) wmask |= 32u;
-      if (ts <= 0.125) wmask |= 64u;
-      if (ts <= 0.0625) wmask |= 128u;
+      wmask = md_sbt_wmask(tt, delta);
     }
     // "negative" events of a window: p == -1, or p == 0 when the window holds no -1 (operations.py:59-61,78-80)
     const uint32_t posm = (pc == 1u) ? wmask : 0u;
@@ -293,30 +283,24 @@ __global__ void k_sbt_negsel(const TT* __restrict__ t, const int8_t* __restrict_
     if (p[w.start + i] != -1) continue;
     const int64_t d = (int64_t)t[w.start + i] - w.t_base;
     if (d >= T_REL_LIMIT || d <= -T_REL_LIMIT) continue;
-    const double ts = (double)(uint32_t)((int32_t)d - w.tmin_rel) / delta;
-    const double f = 1.0 / 3.0;
-    m |= 1u;
-    if (ts <= 1.0 * f && ts >= 0.0 * f) m |= 2u;
-    if (ts <= 2.0 * f && ts >= 1.0 * f) m |= 4u;
-    if (ts <= 3.0 * f && ts >= 2.0 * f) m |= 8u;
-    if (ts <= 0.5) m |= 16u;
-    if (ts <= 0.25) m |= 32u;
-    if (ts <= 0.125) m |= 64u;
-    if (ts <= 0.0625) m |= 128u;
+    m |= md_sbt_wmask((uint32_t)((int32_t)d - w.tmin_rel), delta);
   }
   m = __reduce_or_sync(0xffffffffu, m);
   if ((threadIdx.x & 31) == 0 && m) atomicOr(&wp[b].has_m1, m);
 }
 
+int launch_sbt_negsel(const Geom& g, const Workspace& ws, const Events& ev, cudaStream_t stream) {
+  dim3 grid(64, g.B);
+  if (ev.t_bytes == 4)
+    k_sbt_negsel<int32_t><<<grid, 256, 0, stream>>>((const int32_t*)ev.t, ev.p, ws.wp);
+  else
+    k_sbt_negsel<int64_t><<<grid, 256, 0, stream>>>((const int64_t*)ev.t, ev.p, ws.wp);
+  EVREP_CUDA_OK(cudaGetLastError());
+  return EVREP_OK;
+}
+
 int launch_md_tile(const Geom& g, const Workspace& ws, const MdPlan& plan, const Events& ev, float* out, cudaStream_t stream) {
-  if (plan.stacking == EVREP_STACK_SBT) {
-    dim3 grid(64, g.B);
-    if (ev.t_bytes == 4)
-      k_sbt_negsel<int32_t><<<grid, 256, 0, stream>>>((const int32_t*)ev.t, ev.p, ws.wp);
-    else
-      k_sbt_negsel<int64_t><<<grid, 256, 0, stream>>>((const int64_t*)ev.t, ev.p, ws.wp);
-    EVREP_CUDA_OK(cudaGetLastError());
-  }
+  if (plan.stacking == EVREP_STACK_SBT) EVREP_TRY_RC(launch_sbt_negsel(g, ws, ev, stream));
   const size_t smem = md_tile_smem_bytes(plan, g.tile_px);
   switch (g.tile_px == 1024 ? plan.static_id : 0) {
 #define EVREP_STATIC_CASE(VER, LW) \

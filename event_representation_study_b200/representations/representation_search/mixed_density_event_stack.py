@@ -10,10 +10,10 @@ from .operations import Operations
 
 # Not in the reference: after this many `stack` calls with one (windows, functions, aggregations) tuple - counted per
 # process, the reference builds a new instance per sample (optimized_representation.py:131-134) - the tuple is compiled into
-# specialised kernels (batched.specialize_mixed_density: ~2 s once, then every call runs the ERGO-12 pipeline with this
-# tuple's kernels instead of the interpreted kernel).  A search that evaluates a candidate over a dataset crosses the
-# threshold after a handful of samples; None disables it.
-SPECIALIZE_AFTER_CALLS = 16
+# specialised kernels on a background thread (batched.specialize_mixed_density(wait=False): no call ever stalls; ~0.5 s
+# later calls run the ERGO-12 pipeline with this tuple's kernels instead of the interpreted kernel).  A training run on a
+# searched tuple crosses the threshold within its first batch; None disables it.
+SPECIALIZE_AFTER_CALLS = 64
 _TUPLE_CALLS = {}
 
 
@@ -27,16 +27,16 @@ class MixedDensityEventStack:
         self.stacking_type = stacking_type
 
     def _maybe_specialize(self, w, f, a, n):
-        if SPECIALIZE_AFTER_CALLS is None or self.stacking_type != "SBN":
+        if SPECIALIZE_AFTER_CALLS is None or self.stacking_type not in ("SBN", "SBT"):
             return
-        key = (tuple(w), tuple(f), tuple(a))
+        key = (self.stacking_type, tuple(w), tuple(f), tuple(a))
         calls = _TUPLE_CALLS.get(key, 0) + 1
         if calls <= SPECIALIZE_AFTER_CALLS:
             if len(_TUPLE_CALLS) > 4096:
                 _TUPLE_CALLS.clear()
             _TUPLE_CALLS[key] = calls
         if calls == SPECIALIZE_AFTER_CALLS:
-            eb.specialize_mixed_density(w, f, a, "SBN", max_events_per_window=max(int(n), 1 << 20))
+            eb.specialize_mixed_density(w, f, a, self.stacking_type, max_events_per_window=max(int(n), 1 << 20), wait=False)
 
     def _spec(self):
         w, f, a = self.indexes_functions_aggregations

@@ -150,13 +150,19 @@ int evrep_mixed_density_batched(const uint16_t* x, const uint16_t* y, const void
  * tuple and process) and makes them resident on the current device; from then on evrep_mixed_density_batched launches them
  * whenever it is called with exactly this tuple (same results within the documented tolerance; integer channels bit exact).
  * max_events_per_window bounds the largest window of later calls (it picks the limb width of the hot-tile kernel; a later
- * call with larger windows silently uses the interpreted kernel).  Envelope: SBN stacking, per-pixel accumulators that fit
+ * call with larger windows silently uses the interpreted kernel).  Envelope: SBN or SBT stacking, per-pixel accumulators that fit
  * a tile's shared memory (at most 55 packed words: every 12-channel tuple of the reference's vocabulary does); at call time a
  * sensor with H * W * C a multiple of 4 and at most 2 Mpx (1 Mpx for tuples above 27 words, which take 512-pixel tiles).
  * EVREP_EUNSUPPORTED otherwise (and when libnvrtc / the driver library cannot be opened) - the interpreted
  * kernel keeps serving such tuples.  Host call; thread safe. */
 int evrep_mixed_density_specialize(const int8_t* win, const int8_t* func, const int8_t* agg, int C, int stacking,
                                    int64_t max_events_per_window);
+/* The same, without waiting: the compilation runs on a background host thread and the call returns at once; calls of
+ * evrep_mixed_density_batched keep using the interpreted kernel until the program is ready and switch to the specialised
+ * kernels from then on (results agree within the documented tolerance, integer-valued channels exactly).  For streams of
+ * per-window calls that should never stall (the drop-in class uses it after 64 calls with one tuple). */
+int evrep_mixed_density_specialize_async(const int8_t* win, const int8_t* func, const int8_t* agg, int C, int stacking,
+                                         int64_t max_events_per_window);
 /* The same compilation without loading anything on a device (works on a machine without a GPU): *cubin_bytes receives the
  * size of the sm_100a image.  Used by the build check and the CPU tests. */
 int evrep_mixed_density_specialize_compile_only(const int8_t* win, const int8_t* func, const int8_t* agg, int C, int stacking,

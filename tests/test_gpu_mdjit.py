@@ -31,21 +31,21 @@ def integer_channels(funcs, aggs):
     return [c for c, (f, a) in enumerate(zip(funcs, aggs)) if f in INT_FUNCS and a in ("sum", "max", "min")]
 
 
-MDES = [c for c in golden("mdes_SBN_*") + golden("mdmin_SBN_*")]
+MDES = [c for c in golden("mdes_*") + golden("mdmin_*")]
 
 
 @pytest.mark.parametrize("name,path", MDES, ids=[c[0] for c in MDES])
 def test_specialized_golden(E, name, path):
     g = load(path)
-    win, func, agg = g["win"].tolist(), g["func"].tolist(), g["agg"].tolist()
-    assert E.specialize_mixed_density(win, func, agg, "SBN", max_events_per_window=1 << 20)
-    assert E.mixed_density_is_specialized(win, func, agg, "SBN", len(g["x"]))
-    out = np_(E.mixed_density(batch_of(E, [g]), int(g["H"]), int(g["W"]), win, func, agg, "SBN"))[0]
+    win, func, agg, st = g["win"].tolist(), g["func"].tolist(), g["agg"].tolist(), str(g["stacking"])
+    assert E.specialize_mixed_density(win, func, agg, st, max_events_per_window=1 << 20)
+    assert E.mixed_density_is_specialized(win, func, agg, st, len(g["x"]))
+    out = np_(E.mixed_density(batch_of(E, [g]), int(g["H"]), int(g["W"]), win, func, agg, st))[0]
     assert_close(out, g["out"], rtol=RTOL, atol=VAR_ATOL, what=name)
 
 
 def test_specialized_all_pairs_vs_oracle(E):
-    """Every (function, aggregation) pair on every SBN window, mixed {-1,0,+1} polarities, through specialised kernels."""
+    """Every (function, aggregation) pair on every SBN and SBT window, mixed {-1,0,+1} polarities, through specialised kernels."""
     from oracle import representations as orep
     from event_representation_study_b200.synth import poisson_window
     H, W = 48, 64
@@ -54,15 +54,16 @@ def test_specialized_all_pairs_vs_oracle(E):
     w["p"] = rng.integers(-1, 2, len(w["p"])).astype(np.int8)
     w["p"][: len(w["p"]) // 3] = np.abs(w["p"][: len(w["p"]) // 3])  # first third holds no -1: the p == 0 fallback
     ev = E.pack_events([w, poisson_window(32, 777, H, W)], "cuda")
-    for win in range(7):
-        full = [(win, f, a) for f in orep.FUNCTIONS for a in orep.AGGREGATIONS]  # 35 channels
-        for spec in (full[:20], full[19:]):                                        # 20 + 16
-            wi, fu, ag = [s[0] for s in spec], [s[1] for s in spec], [s[2] for s in spec]
-            assert E.specialize_mixed_density(wi, fu, ag, "SBN", max_events_per_window=30_000)
-            out = np_(E.mixed_density(ev, H, W, wi, fu, ag, "SBN"))[0]
-            with np.errstate(all="ignore"):
-                want = orep.mixed_density_event_stack(w["x"], w["y"], w["t"], w["p"], H, W, wi, fu, ag, "SBN")
-            assert_close(out, want, rtol=RTOL, atol=VAR_ATOL, what=f"SBN window {win}")
+    for st, nwin in (("SBN", 7), ("SBT", 8)):
+        for win in range(nwin):
+            full = [(win, f, a) for f in orep.FUNCTIONS for a in orep.AGGREGATIONS]  # 35 channels
+            for spec in (full[:20], full[19:]):                                        # 20 + 16
+                wi, fu, ag = [s[0] for s in spec], [s[1] for s in spec], [s[2] for s in spec]
+                assert E.specialize_mixed_density(wi, fu, ag, st, max_events_per_window=30_000)
+                out = np_(E.mixed_density(ev, H, W, wi, fu, ag, st))[0]
+                with np.errstate(all="ignore"):
+                    want = orep.mixed_density_event_stack(w["x"], w["y"], w["t"], w["p"], H, W, wi, fu, ag, st)
+                assert_close(out, want, rtol=RTOL, atol=VAR_ATOL, what=f"{st} window {win}")
 
 
 def random_tuple(seed, C=12):
@@ -134,9 +135,9 @@ def test_outside_the_envelope_keeps_the_interpreted_kernel(E):
     w = poisson_window(9, 5000, H, W)
     ev = E.pack_events([w], "cuda")
     wi, fu, ag = random_tuple(21)
-    assert not E.specialize_mixed_density(wi, fu, ag, "SBT")            # windows by time
-    assert E.specialize_mixed_density(wi[:7], fu[:7], ag[:7], "SBN")      # 7 channels: compiled, but 30 * 41 * 7 is odd ...
-    for spec, st, hw in (((wi, fu, ag), "SBT", (30, 40)), ((wi[:7], fu[:7], ag[:7]), "SBN", (30, 41))):  # ... so this call is interpreted
+    assert not E.specialize_mixed_density(wi, fu, ag, "no such stacking")  # the reference builds window 0 only for it
+    assert E.specialize_mixed_density(wi[:7], fu[:7], ag[:7], "SBN")        # 7 channels: compiled, but 30 * 41 * 7 is odd ...
+    for spec, st, hw in (((wi, fu, ag), "no such stacking", (30, 40)), ((wi[:7], fu[:7], ag[:7]), "SBN", (30, 41))):  # ... so this call is interpreted
         H, W = hw
         w = poisson_window(9, 5000, H, W)
         ev = E.pack_events([w], "cuda")
@@ -155,8 +156,10 @@ def test_outside_the_envelope_keeps_the_interpreted_kernel(E):
     assert not out[:, :, 3].any() and not out[:, :, 5].any()
 
 
-def test_mirror_class_specialises_after_repeated_calls(E):
-    """The drop-in class compiles its tuple after SPECIALIZE_AFTER_CALLS stack() calls; results stay the reference's."""
+def test_mirror_class_specialises_in_the_background(E):
+    """The drop-in class hands its tuple to a background compilation after SPECIALIZE_AFTER_CALLS stack() calls: no call waits,
+    later calls run the specialised kernels, and every result stays the reference's."""
+    import time
     from oracle import representations as orep
     from event_representation_study_b200.synth import poisson_window, structured
     from event_representation_study_b200.representations.representation_search import mixed_density_event_stack as M
@@ -164,14 +167,37 @@ def test_mirror_class_specialises_after_repeated_calls(E):
     wi, fu, ag = random_tuple(33)
     w = poisson_window(10, 3000, H, W)
     rec = structured(w)
+    with np.errstate(all="ignore"):
+        want = orep.mixed_density_event_stack(w["x"], w["y"], w["t"], w["p"], H, W, wi, fu, ag, "SBN")
     old = M.SPECIALIZE_AFTER_CALLS
     M.SPECIALIZE_AFTER_CALLS = 3
     try:
-        for k in range(5):
+        for k in range(3):
+            assert not E.mixed_density_is_specialized(wi, fu, ag, "SBN", 3000)
             rep = M.MixedDensityEventStack(12, len(rec), H, W, (wi, fu, ag), "SBN").stack(rec)
-            assert E.mixed_density_is_specialized(wi, fu, ag, "SBN", 3000) == (k >= 2)
-            with np.errstate(all="ignore"):
-                want = orep.mixed_density_event_stack(w["x"], w["y"], w["t"], w["p"], H, W, wi, fu, ag, "SBN")
             assert_close(rep, want, rtol=RTOL, atol=VAR_ATOL, what=f"call {k}")
+        t0 = time.time()
+        while not E.mixed_density_is_specialized(wi, fu, ag, "SBN", 3000):
+            assert time.time() - t0 < 60, "background compilation did not finish"
+            time.sleep(0.05)
+        rep = M.MixedDensityEventStack(12, len(rec), H, W, (wi, fu, ag), "SBN").stack(rec)
+        assert_close(rep, want, rtol=RTOL, atol=VAR_ATOL, what="after the switch")
     finally:
         M.SPECIALIZE_AFTER_CALLS = old
+
+
+def test_specialised_call_replays_as_a_cuda_graph(E):
+    """The driver-API launches of the specialised kernels are captured like the runtime launches of the other kernels."""
+    import torch
+    from event_representation_study_b200.synth import poisson_window
+    H, W = 120, 160
+    wi, fu, ag = random_tuple(44)
+    ev = E.pack_events([poisson_window(50 + i, 20_000 + 17 * i, H, W) for i in range(4)], "cuda")
+    assert E.specialize_mixed_density(wi, fu, ag, "SBN", max_events_per_window=30_000)
+    out = torch.empty((4, H, W, 12), device="cuda")
+    eager = E.mixed_density(ev, H, W, wi, fu, ag, "SBN").clone()
+    call = E.GraphedCall(lambda: E.mixed_density(ev, H, W, wi, fu, ag, "SBN", out=out))
+    out.zero_()
+    call.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(torch.nan_to_num(out, nan=-7.0), torch.nan_to_num(eager, nan=-7.0))

@@ -56,12 +56,15 @@ def test_second_compilation_is_served_from_the_cache():
     assert rc == _lib.OK and nbytes > 0 and time.time() - t0 < 0.2
 
 
-@pytest.mark.parametrize("case", ["sbt", "too-many-sums"])
+def test_sbt_tuples_compile_too():
+    rc, nbytes = compile_only(*TUPLE, stacking=1)
+    assert rc == _lib.OK and nbytes > 10_000, lib.evrep_last_error().decode()
+
+
+@pytest.mark.parametrize("case", ["too-many-sums"])
 def test_outside_the_envelope_is_refused(case):
     wi, fu, ag = TUPLE
-    if case == "sbt":
-        rc, _ = compile_only(wi, fu, ag, stacking=1)
-    else:  # 28 distinct timestamp-variance groups: the packed plan alone exceeds a tile's shared memory
+    if True:  # 28 distinct timestamp-variance groups: the packed plan alone exceeds a tile's shared memory
         wi = [k % 7 for k in range(28)]
         fu = ["timestamp", "timestamp_pos", "timestamp_neg", "timestamp"][:1] * 7 + ["timestamp_pos"] * 7 + ["timestamp_neg"] * 7 + ["timestamp"] * 7
         rc, _ = compile_only(wi, fu, ["variance"] * 28)
@@ -76,3 +79,18 @@ def test_ergo_tuples_need_no_compilation():
     ag = ["variance", "variance", "mean", "sum", "mean", "sum", "mean", "mean", "max", "max", "max", "mean"]
     w, f, a = codes(wi, fu, ag)
     assert lib.evrep_mixed_density_specialize(w.ctypes.data, f.ctypes.data, a.ctypes.data, 12, 0, 1 << 20) == _lib.OK  # no device needed
+
+
+def test_background_compilation_finishes_without_a_gpu():
+    import time
+    wi = [6, 5, 4, 3, 2, 1, 0, 6, 5, 4, 3, 2]
+    w, f, a = codes(wi, TUPLE[1], TUPLE[2])
+    args = (w.ctypes.data, f.ctypes.data, a.ctypes.data, 12, 0, 100_000)
+    assert lib.evrep_mixed_density_is_specialized(*args) == 0
+    t0 = time.time()
+    assert lib.evrep_mixed_density_specialize_async(*args) == _lib.OK
+    assert time.time() - t0 < 0.2, "the asynchronous call must not wait for NVRTC"
+    assert lib.evrep_mixed_density_specialize_async(*args) == _lib.OK  # already pending: no second compilation
+    while lib.evrep_mixed_density_is_specialized(*args) == 0:
+        assert time.time() - t0 < 120
+        time.sleep(0.05)
