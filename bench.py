@@ -401,7 +401,7 @@ def bench_search_tuple(dev, steps, peak):
     d = device_batch(B, N, h, w, dev, seed=4000)
     ev = eb.EventBatch(d["x"], d["y"], d["t"], d["p"], d["offsets"].cpu().numpy())
     o = torch.empty((B, h, w, 12), device=dev)
-    call = lambda: eb.mixed_density(ev, h, w, wi, fu, ag, "SBN", out=o)
+    call = lambda: eb.mixed_density(ev, h, w, wi, fu, ag, "SBN", out=o, specialize=False)  # (explicit below: the legs must not mix)
     rec = {"workload": "one search candidate (random 12-channel tuple, SBN), 1 Mpx, 1M ev/window, batch 32", "unit": "Gevents/s",
            "windows": wi, "functions": fu, "aggregations": ag}
     already = eb.mixed_density_is_specialized(wi, fu, ag, "SBN", N)

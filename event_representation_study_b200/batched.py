@@ -213,9 +213,17 @@ def _codes(windows, functions, aggregations):
     return win, func, agg, C
 
 
-def mixed_density(ev, H, W, windows, functions, aggregations, stacking="SBN", out=None):
+# tuples whose background compilation mixed_density(specialize="auto") has already asked for (one request per tuple and process)
+_AUTO_SPECIALIZE_SEEN = set()
+AUTO_SPECIALIZE_MIN_EVENTS = 4_000_000  # batches below this are launch bound: the interpreted kernel costs them nothing
+
+
+def mixed_density(ev, H, W, windows, functions, aggregations, stacking="SBN", out=None, specialize="auto"):
     """MixedDensityEventStack.stack for every window -> (B, H, W, C) float32.
-    (representations/representation_search/mixed_density_event_stack.py:25-46)"""
+    (representations/representation_search/mixed_density_event_stack.py:25-46)
+    specialize: "auto" - a batch of 4 M events or more asks for kernels compiled for this tuple on a background thread (the call
+    itself never waits; later calls with the tuple run them, see specialize_mixed_density); True - compile now, then run;
+    False - leave the choice of kernels to what has been specialised so far."""
     win, func, agg, C = _codes(windows, functions, aggregations)
     if stacking not in STACKING:
         # create_windows builds only window 0 for an unknown stacking type; every other index raises -> zero channel
@@ -223,6 +231,18 @@ def mixed_density(ev, H, W, windows, functions, aggregations, stacking="SBN", ou
         st = STACKING["SBN"]
     else:
         st = STACKING[stacking]
+    if specialize is True or (specialize == "auto" and ev.total >= AUTO_SPECIALIZE_MIN_EVENTS):
+        key = (st, win.tobytes(), func.tobytes(), agg.tobytes())
+        if specialize is True or key not in _AUTO_SPECIALIZE_SEEN:
+            if len(_AUTO_SPECIALIZE_SEEN) > 65536:
+                _AUTO_SPECIALIZE_SEEN.clear()
+            _AUTO_SPECIALIZE_SEEN.add(key)
+            n_max = int(np.diff(ev.offsets).max()) if ev.B else 1
+            fn = lib.evrep_mixed_density_specialize if specialize is True else lib.evrep_mixed_density_specialize_async
+            with torch.cuda.device(ev.device):
+                rc = fn(win.ctypes.data, func.ctypes.data, agg.ctypes.data, C, st, max(n_max, 1 << 20))
+            if rc not in (_lib.OK, _lib.EUNSUPPORTED, _lib.EINVAL):  # outside the envelope / bad spec: the interpreted kernel serves (or reports) it
+                check(rc)
     head, ws, stream = _prep(ev, _lib.OP_MIXED_DENSITY, H, W, C)
     out = _out(ev, (ev.B, H, W, C), out)
     check(lib.evrep_mixed_density_batched(*head, win.ctypes.data, func.ctypes.data, agg.ctypes.data, C, st, out.data_ptr(),

@@ -11,5 +11,5 @@ fu = ["polarity", "timestamp_neg", "count_neg", "polarity", "count_pos", "count"
 ag = ["variance", "variance", "mean", "sum", "mean", "sum", "mean", "mean", "max", "max", "max", "mean"]
 out = torch.empty((B, H, W, 12), device=dev)
 for _ in range(3):
-    eb.mixed_density(ev, H, W, wi, fu, ag, "SBN", out=out)
+    eb.mixed_density(ev, H, W, wi, fu, ag, "SBN", out=out, specialize=False)
 torch.cuda.synchronize()

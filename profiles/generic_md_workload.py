@@ -43,7 +43,7 @@ for k in range(4):
 cases.append(("ergo12 tuple, SBT windows", ergo_w, ergo_f, ergo_a, "SBT"))
 out = torch.empty((B, H, W, 12), device=dev, dtype=torch.float32)
 for name, w, f, a, st in cases:
-    fn = lambda: eb.mixed_density(ev, H, W, w, f, a, st, out=out)
+    fn = lambda: eb.mixed_density(ev, H, W, w, f, a, st, out=out, specialize=False)
     _lib.lib.evrep_profile_enable(0)
     ms = timed(fn)
     rec = {"case": name, "ms_per_step": round(ms, 4), "gev_s": round(B * N / ms / 1e6, 2)}

@@ -201,3 +201,26 @@ def test_specialised_call_replays_as_a_cuda_graph(E):
     call.replay()
     torch.cuda.synchronize()
     assert torch.equal(torch.nan_to_num(out, nan=-7.0), torch.nan_to_num(eager, nan=-7.0))
+
+
+def test_large_batches_ask_for_their_kernels_by_themselves(E):
+    """mixed_density(specialize="auto"): a batch of 4 M events or more starts a background compilation of its tuple; the call that
+    asked is served by the interpreted kernel, a later one by the specialised kernels, with the same result."""
+    import time
+    from event_representation_study_b200.synth import device_batch
+    import torch
+    H, W = 240, 304
+    wi, fu, ag = random_tuple(55)
+    d = device_batch(32, 150_000, H, W, torch.device("cuda", 0), seed=8)
+    ev = E.EventBatch(d["x"], d["y"], d["t"], d["p"], d["offsets"].cpu().numpy())
+    assert not E.mixed_density_is_specialized(wi, fu, ag, "SBN", 150_000)
+    first = E.mixed_density(ev, H, W, wi, fu, ag, "SBN").clone()
+    t0 = time.time()
+    while not E.mixed_density_is_specialized(wi, fu, ag, "SBN", 150_000):
+        assert time.time() - t0 < 60, "background compilation did not finish"
+        time.sleep(0.05)
+    second = E.mixed_density(ev, H, W, wi, fu, ag, "SBN")
+    a, b = np_(first), np_(second)
+    assert_close(b, a, rtol=RTOL, atol=VAR_ATOL, what="specialised vs interpreted")
+    for c in integer_channels(fu, ag):
+        assert np.array_equal(a[..., c], b[..., c])
