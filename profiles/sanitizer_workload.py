@@ -51,4 +51,16 @@ print(eb.gwd_kernel_l1(Xa, Xb, 0.7, s_offsets=sa, t_offsets=sb))
 out_g = torch.empty((ev.B, H, W, 12), device="cuda")
 call = eb.GraphedCall(lambda: eb.ergo12(ev, H, W, out=out_g))
 call.replay(); call.replay()
+# run-time specialised mixed-density kernels (NVRTC): SBN with 12 channels, SBT with 9 (scalar staging), a fat plan on 512-pixel tiles,
+# the interpreted kernel for comparison, and a hot tile through the specialised wide plan
+wi, fu, ag = [2, 1, 3, 5, 0, 0, 6, 4, 0, 2, 4, 1], ["timestamp", "polarity", "count", "timestamp_pos", "timestamp_neg", "count_pos", "count_neg", "polarity",
+                                                  "timestamp", "count", "timestamp_neg", "count_pos"], ["variance", "mean", "sum", "max", "mean", "mean", "sum", "variance", "sum", "max", "min", "mean"]
+eb.mixed_density(ev, H, W, wi, fu, ag, "SBN", specialize=False)
+eb.mixed_density(ev, H, W, wi, fu, ag, "SBN", specialize=True)
+eb.mixed_density(ev, H, W, wi[:9], fu[:9], ag[:9], "SBT", specialize=True)
+eb.mixed_density(ev, H, W, [0, 1, 2, 3, 4, 5, 6, 0, 0, 1, 2, 3], ["timestamp_pos"] * 7 + ["timestamp_neg", "count", "polarity", "count_pos", "timestamp"],
+                 ["variance"] * 8 + ["sum", "mean", "sum", "max"], "SBN", specialize=True)
+hot = poisson_window(99, 70000, 32, 32)
+hot["x"][:] = 3; hot["y"][:] = 5
+eb.mixed_density(eb.pack_events([hot], "cuda"), 32, 32, wi, fu, ag, "SBN", specialize=True)
 torch.cuda.synchronize(); print("sanitizer workload done")
