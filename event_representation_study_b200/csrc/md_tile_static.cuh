@@ -231,6 +231,24 @@ __device__ __forceinline__ bool md_record_live(uint32_t meta) {
   return PS::value.stacking == EVREP_STACK_SBT ? !rec_is_null(meta) : meta != 0u;
 }
 
+template <typename PS>
+__device__ __forceinline__ void md_acc_presence(uint32_t* a, uint32_t pres) {
+  if (pres) {  // only plans that still keep presence bits
+    uint32_t* pw = a + PS::value.w_pres;
+    if ((*(volatile uint32_t*)pw & pres) != pres) atomicOr(pw, pres);
+  }
+}
+// An event whose SBN window mask is the compile-time constant WM: the membership word M is a constant too, so every group
+// test of md_acc_all folds and what remains is the straight-line list of atomics this (zone, polarity class) owes - no
+// bit tests, and none of the BSSY / BRA / BSYNC triples ptxas puts around a conditional shared-memory atomic.
+template <typename PS, int CLS, uint32_t WM>
+__device__ __forceinline__ void md_acc_fixed(uint32_t* a, uint32_t tt) {
+  constexpr uint32_t M = CLS == 1 ? (WM | (WM << 8)) : (WM | (WM << 16));
+  uint32_t pres = 0;
+  md_acc_all<PS, CLS>(a, M, tt, pres, make_iseq<PS::value.G>{});
+  md_acc_presence<PS>(a, pres);
+}
+
 template <typename PS, int CLS>
 __device__ __forceinline__ void md_accumulate_static(uint32_t* acc, const uint2 r, int32_t tmin, uint32_t not_m1, double delta) {
   constexpr int STRIDE = PS::value.stride, G = PS::value.G;
@@ -239,6 +257,26 @@ __device__ __forceinline__ void md_accumulate_static(uint32_t* acc, const uint2 
   const uint32_t tt = (uint32_t)((int32_t)r.x - tmin);
   uint32_t wmask = (r.y >> 16) & 0xffu;  // 0 for null and padding records: member of no window
   if constexpr (PS::value.stacking == EVREP_STACK_SBT) wmask = rec_is_null(r.y) ? 0u : md_sbt_wmask(tt, delta);
+  if constexpr (PS::value.stacking == EVREP_STACK_SBN && CLS != 0) {
+    // SBN windows are index ranges (mixed_density_event_stack.py:55-74): an event lies in one of seven zones, each with its own
+    // constant mask, and the records of a bucket are in stream order, so the 32 events of a warp nearly always share a zone -
+    // dispatch on the mask and run that zone's specialised list.  Class 2 qualifies when its events count as "negative" in every
+    // window they belong to (p == -1, or p == 0 with no -1 in those windows: operations.py:59-61); anything else - and masks of
+    // degenerate windows, where zone boundaries coincide - takes the generic walk below.
+    if (CLS == 1 || pc == 3u || (wmask & ~not_m1) == 0u) {
+      switch (wmask) {
+        case 0u: return;  // null and padding records
+        case 3u: md_acc_fixed<PS, CLS, 3u>(a, tt); return;      // first third
+        case 5u: md_acc_fixed<PS, CLS, 5u>(a, tt); return;      // second third, first half
+        case 21u: md_acc_fixed<PS, CLS, 21u>(a, tt); return;    // second third, second half
+        case 25u: md_acc_fixed<PS, CLS, 25u>(a, tt); return;    // last third, third quarter
+        case 57u: md_acc_fixed<PS, CLS, 57u>(a, tt); return;    // last third, seventh eighth
+        case 121u: md_acc_fixed<PS, CLS, 121u>(a, tt); return;  // last third, last eighth
+        case 113u: md_acc_fixed<PS, CLS, 113u>(a, tt); return;  // the n % 3 events after the last third
+        default: break;
+      }
+    }
+  }
   uint32_t M;
   if constexpr (CLS == 1) {
     M = wmask | (wmask << 8);
@@ -250,10 +288,7 @@ __device__ __forceinline__ void md_accumulate_static(uint32_t* acc, const uint2 
   }
   uint32_t pres = 0;
   md_acc_all<PS, CLS>(a, M, tt, pres, make_iseq<G>{});
-  if (pres) {  // only plans that still keep presence bits
-    uint32_t* pw = a + PS::value.w_pres;
-    if ((*(volatile uint32_t*)pw & pres) != pres) atomicOr(pw, pres);
-  }
+  md_acc_presence<PS>(a, pres);
 }
 // record i of a bucket pair whose first n_pos records are the p > 0 events (n_pos = 0xffffffff: not split, any class)
 template <typename PS, bool SPLIT>
