@@ -19,6 +19,8 @@
  * Reference interfaces replaced (paths relative to the reference repository root):
  *   evrep_mixed_density_batched  representations/representation_search/mixed_density_event_stack.py:25-46
  *                                (+ operations.py:15-89), one call per window there
+ *   evrep_mixed_density_specialize   the same interface for one candidate tuple of the representation search
+ *                                (representation_search/optimization.py:36-64): kernels compiled for that tuple at run time
  *   evrep_ergo12_batched         representations/optimized_representation.py:86-134
  *   evrep_event_stack_batched    representations/event_stack.py:15-63 as called at gen1_transforms.py:33-42
  *   evrep_time_surface_batched   representations/time_surface.py:25-74 as called at gen1_transforms.py:69-87
