@@ -16,7 +16,8 @@ cpu_baseline  the numpy oracle (a port of the reference algorithm) on the host c
 gwd       BASELINE.json's second metric ("GWD pairs/s vs CPU ref", configs[4]): the 12 x 1000 GWD-A matrix, columns sharded
           over the ranks, one NCCL all-gather when N > 1; plus one pair at the paper's problem sizes (compute_otmi.py:96-211)
 configs   BASELINE configs[1] (ERGO-12 Gen1, batch 32) and configs[2] (TimeSurface + EventStack + TORE, fused call); search_tuple:
-          one candidate of the representation search on the headline batch, interpreted and run-time specialised kernels
+          a tuple other than ERGO-12 (as the representation search produces) on the headline batch, interpreted and run-time
+          specialised kernels
 parity_spot_check  windows of the TIMED output buffers against the oracle on the same events
 dropin    the per-window numpy -> numpy call the reference pipelines make today (get_item_transform), full output copied back
 (the last three on rank 0 at N = 1 only; --no-extras skips them and gwd)
@@ -385,7 +386,7 @@ def bench_configs(dev, steps):
 
 
 def bench_search_tuple(dev, steps, peak):
-    """What the representation search runs (mixed_density_event_stack.py:25-151 with an arbitrary tuple): one candidate on the
+    """A tuple other than ERGO-12 (mixed_density_event_stack.py:25-151 with an arbitrary tuple, as the search produces) on the
     headline batch (32 x 1 M events at 1 Mpx) through the interpreted kernel and, after evrep_mixed_density_specialize, through
     kernels compiled for that tuple at run time; one window of the timed buffer against the oracle."""
     import time
@@ -402,7 +403,7 @@ def bench_search_tuple(dev, steps, peak):
     ev = eb.EventBatch(d["x"], d["y"], d["t"], d["p"], d["offsets"].cpu().numpy())
     o = torch.empty((B, h, w, 12), device=dev)
     call = lambda: eb.mixed_density(ev, h, w, wi, fu, ag, "SBN", out=o, specialize=False)  # (explicit below: the legs must not mix)
-    rec = {"workload": "one search candidate (random 12-channel tuple, SBN), 1 Mpx, 1M ev/window, batch 32", "unit": "Gevents/s",
+    rec = {"workload": "a non-ERGO tuple (random 12-channel tuple, SBN), 1 Mpx, 1M ev/window, batch 32", "unit": "Gevents/s",
            "windows": wi, "functions": fu, "aggregations": ag}
     already = eb.mixed_density_is_specialized(wi, fu, ag, "SBN", N)
     if not already:

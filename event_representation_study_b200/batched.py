@@ -253,8 +253,8 @@ def mixed_density(ev, H, W, windows, functions, aggregations, stacking="SBN", ou
 def specialize_mixed_density(windows, functions, aggregations, stacking="SBN", max_events_per_window=1 << 20, device=None, wait=True):
     """Compile kernels for ONE (windows, functions, aggregations) tuple at run time (NVRTC, a few seconds, once per process) and
     load them on `device` (default: the current one); `mixed_density` calls with that tuple then run 4 - 6 x faster than the
-    interpreted kernel every other non-ERGO tuple takes (C-ABI: evrep_mixed_density_specialize).  What a representation
-    search wants before it evaluates a candidate on a dataset.  Returns True, or False when the tuple is outside the
+    interpreted kernel every other non-ERGO tuple takes (C-ABI: evrep_mixed_density_specialize).  For running a searched
+    representation over a dataset.  Returns True, or False when the tuple is outside the
     specialised envelope (accumulators beyond a tile's shared memory; list entries the reference would swallow
     into zero channels are fine) - such tuples keep running on the interpreted kernel.  wait=False compiles on a background
     thread and returns at once; `mixed_density` switches kernels when the program is ready (mixed_density_is_specialized)."""

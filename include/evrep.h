@@ -19,8 +19,8 @@
  * Reference interfaces replaced (paths relative to the reference repository root):
  *   evrep_mixed_density_batched  representations/representation_search/mixed_density_event_stack.py:25-46
  *                                (+ operations.py:15-89), one call per window there
- *   evrep_mixed_density_specialize   the same interface for one candidate tuple of the representation search
- *                                (representation_search/optimization.py:36-64): kernels compiled for that tuple at run time
+ *   evrep_mixed_density_specialize   the same interface for a tuple other than ERGO-12 (any result or candidate of the representation
+ *                                search, representation_search/optimization.py:36-64): kernels compiled for that tuple at run time
  *   evrep_ergo12_batched         representations/optimized_representation.py:86-134
  *   evrep_event_stack_batched    representations/event_stack.py:15-63 as called at gen1_transforms.py:33-42
  *   evrep_time_surface_batched   representations/time_surface.py:25-74 as called at gen1_transforms.py:69-87
@@ -145,8 +145,10 @@ int evrep_mixed_density_batched(const uint16_t* x, const uint16_t* y, const void
                                 const int8_t* agg, int C, int stacking, float* out, void* workspace,
                                 size_t workspace_bytes, evrep_stream_t stream);
 
-/* Run-time specialisation of evrep_mixed_density_batched for ONE tuple - what the representation search needs, where a
- * candidate tuple (mixed_density_event_stack.py:25-46 as driven by the search loop) is evaluated on thousands of windows.
+/* Run-time specialisation of evrep_mixed_density_batched for ONE tuple - for running a tuple other than ERGO-12 at scale: a
+ * representation found by the search (mixed_density_event_stack.py:25-46 with the tuple optimization.py:36-64 assembles) used to
+ * train or evaluate a model over a dataset, or a search that scores candidates on large batches.  (The reference's own search
+ * scores a candidate on two samples, optimization.py:131-141: that stays on the interpreted kernel and loses nothing.)
  * The two ERGO-12 tuples have kernels built ahead of time; any other tuple runs an interpreted kernel that is several times
  * slower.  This call compiles the same kernel templates for the given tuple with NVRTC (sm_100a; a few seconds, once per
  * tuple and process) and makes them resident on the current device; from then on evrep_mixed_density_batched launches them
