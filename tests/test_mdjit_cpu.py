@@ -94,3 +94,49 @@ def test_background_compilation_finishes_without_a_gpu():
     while lib.evrep_mixed_density_is_specialized(*args) == 0:
         assert time.time() - t0 < 120
         time.sleep(0.05)
+
+
+def test_mirror_class_host_logic_with_the_oracle_patched_in(monkeypatch):
+    """MixedDensityEventStack (the drop-in class): the background specialisation is requested exactly once per tuple, at the
+    SPECIALIZE_AFTER_CALLS-th stack() call counted across instances (the reference builds one instance per sample,
+    optimized_representation.py:131-134), for SBN and SBT but not for a stacking type the reference does not know; the
+    GPU calls are replaced by the numpy oracle here."""
+    import torch
+    from oracle import representations as orep
+    from event_representation_study_b200.representations.representation_search import mixed_density_event_stack as M
+    from event_representation_study_b200.synth import poisson_window, structured
+
+    H, W = 12, 16
+    asked = []
+
+    class FakeBatch:
+        def __init__(self, w):
+            self.w = w
+
+    def fake_one_window_structured(records, height, width):
+        return FakeBatch({k: np.asarray(records[k]) for k in "xytp"})
+
+    def fake_mixed_density(ev, height, width, wi, fu, ag, stacking="SBN", out=None, specialize="auto"):
+        w = ev.w
+        with np.errstate(all="ignore"):
+            rep = orep.mixed_density_event_stack(w["x"], w["y"], w["t"], w["p"], height, width, wi, fu, ag, stacking)
+        return torch.as_tensor(rep[None].astype(np.float32))
+
+    monkeypatch.setattr(M, "one_window_structured", fake_one_window_structured)
+    monkeypatch.setattr(M.eb, "mixed_density", fake_mixed_density)
+    monkeypatch.setattr(M.eb, "specialize_mixed_density", lambda w, f, a, st, max_events_per_window=0, wait=True: asked.append((st, tuple(w), wait)) or True)
+    monkeypatch.setattr(M, "to_host", lambda t, dtype, scale=None: t.to(dtype).numpy() * (1.0 if scale is None else scale))
+    monkeypatch.setattr(M, "SPECIALIZE_AFTER_CALLS", 4)
+    monkeypatch.setattr(M, "_TUPLE_CALLS", {})
+    rec = structured(poisson_window(3, 500, H, W))
+    spec = ([0, 1, 2, 3], ["count", "polarity", "timestamp", "count_pos"], ["sum", "mean", "max", "sum"])
+    for st in ("SBN", "SBT", "no such stacking"):
+        for k in range(9):
+            rep = M.MixedDensityEventStack(4, len(rec), H, W, spec, st).stack(rec)
+            assert rep.shape == (H, W, 4) and rep.dtype == np.float64
+    assert asked == [("SBN", (0, 1, 2, 3), False), ("SBT", (0, 1, 2, 3), False)]
+    monkeypatch.setattr(M, "SPECIALIZE_AFTER_CALLS", None)  # switched off
+    monkeypatch.setattr(M, "_TUPLE_CALLS", {})
+    for k in range(6):
+        M.MixedDensityEventStack(4, len(rec), H, W, spec, "SBN").stack(rec)
+    assert len(asked) == 2
