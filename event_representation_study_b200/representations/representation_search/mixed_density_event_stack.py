@@ -10,7 +10,7 @@ from .operations import Operations
 
 # Not in the reference: after this many `stack` calls with one (windows, functions, aggregations) tuple - counted per
 # process, the reference builds a new instance per sample (optimized_representation.py:131-134) - the tuple is compiled into
-# specialised kernels on a background thread (batched.specialize_mixed_density(wait=False): no call ever stalls; ~0.5 s
+# specialised kernels on a background thread (batched.specialize_mixed_density(wait=False): no call ever stalls; ~1 s
 # later calls run the ERGO-12 pipeline with this tuple's kernels instead of the interpreted kernel).  A training run on a
 # searched tuple crosses the threshold within its first batch; None disables it.
 SPECIALIZE_AFTER_CALLS = 64
