@@ -140,3 +140,47 @@ def test_mirror_class_host_logic_with_the_oracle_patched_in(monkeypatch):
     for k in range(6):
         M.MixedDensityEventStack(4, len(rec), H, W, spec, "SBN").stack(rec)
     assert len(asked) == 2
+
+
+FUN = ["timestamp", "polarity", "count", "timestamp_pos", "timestamp_neg", "count_pos", "count_neg"]
+AGG = ["sum", "mean", "max", "variance", "min"]
+
+
+def _raw_compile(w, f, a, stacking=0, n_max=1 << 20):
+    w, f, a = np.array(w, np.int8), np.array(f, np.int8), np.array(a, np.int8)
+    nb = ctypes.c_size_t(0)
+    rc = lib.evrep_mixed_density_specialize_compile_only(w.ctypes.data, f.ctypes.data, a.ctypes.data, len(w), stacking, n_max, ctypes.byref(nb))
+    return rc, nb.value
+
+
+@pytest.mark.parametrize("name,w,f,a,stacking", [
+    ("one-channel", [0], [2], [0], 0),
+    ("one-channel-sbt", [7], [0], [3], 1),
+    ("counts-only", [0, 1, 2, 3, 4, 5, 6, 0], [2, 5, 6, 2, 5, 6, 2, 5], [0, 0, 0, 1, 1, 2, 2, 3], 0),
+    ("latest-and-earliest", [0, 1, 2, 3, 4, 5], [0, 3, 4, 0, 3, 4], [2, 2, 2, 4, 4, 4], 0),
+    ("all-swallowed", [9, 0, 0, 3], [0, 9, 0, -1], [0, 0, 9, 1], 0),
+    ("polarity-every-aggregation", [0, 1, 2, 3, 4], [1, 1, 1, 1, 1], [0, 1, 2, 3, 4], 0),
+    ("negative-window-index", [-1, -7, 3], [0, 2, 1], [1, 0, 3], 0),
+    ("thirty-two-channels", [c % 7 for c in range(32)], [[2, 5, 6, 1][c % 4] for c in range(32)], [c % 3 for c in range(32)], 0),
+    ("huge-windows", [0, 3, 2, 6], [0, 4, 6, 1], [3, 3, 1, 0], 0),
+])
+def test_unusual_tuples_compile(name, w, f, a, stacking):
+    """The kernel templates must instantiate for every plan shape a caller can ask for - one channel, zero channels left after the
+    reference's swallow-and-zero, presence-only plans, earliest / latest stamps, 32 channels, SBT, limb widths down to 8 bits."""
+    rc, nbytes = _raw_compile(w, f, a, stacking, n_max=(1 << 23) if name == "huge-windows" else (1 << 20))
+    assert rc == _lib.OK and nbytes > 0, (name, lib.evrep_last_error().decode()[:2000])
+
+
+def test_random_tuples_compile():
+    import random
+    rng = random.Random(123)
+    for k in range(6):
+        C = rng.choice([3, 6, 9, 12, 12, 16])
+        w = [rng.randrange(8 if k % 2 else 7) for _ in range(C)]
+        f = [rng.randrange(7) for _ in range(C)]
+        a = [rng.randrange(5) for _ in range(C)]
+        rc, nbytes = _raw_compile(w, f, a, k % 2)
+        if rc == _lib.EUNSUPPORTED:  # a plan too wide for a tile's shared memory: refused, never a compiler error
+            assert b"does not fit" in lib.evrep_last_error() or b"accumulator words" in lib.evrep_last_error()
+            continue
+        assert rc == _lib.OK and nbytes > 0, (w, f, a, lib.evrep_last_error().decode()[:2000])
