@@ -335,6 +335,15 @@ int main(void) {
   if (!strstr(evrep_last_error(), "null")) return 3;
   if (evrep_workspace_bytes(EVREP_OP_MIXED_DENSITY, 1, 1000, 240, 304, 12) == 0) return 4;
   if (evrep_filter_background_workspace_bytes(1, 1000, 8, 8, 1, 4) == 0) return 5;
+  {
+    /* a plain C caller compiles kernels for its own tuple (NVRTC runs on the host: no device needed for this step) */
+    const int8_t win[4] = {0, 3, 6, 1}, func[4] = {EVREP_FUNC_COUNT, EVREP_FUNC_TIMESTAMP_NEG, EVREP_FUNC_POLARITY, EVREP_FUNC_TIMESTAMP_POS};
+    const int8_t agg[4] = {EVREP_AGG_SUM, EVREP_AGG_VARIANCE, EVREP_AGG_MEAN, EVREP_AGG_MAX};
+    size_t nbytes = 0;
+    int rc = evrep_mixed_density_specialize_compile_only(win, func, agg, 4, EVREP_STACK_SBN, 200000, &nbytes);
+    if (rc != EVREP_OK && rc != EVREP_EUNSUPPORTED) return 6;   /* EUNSUPPORTED only where libnvrtc is not installed */
+    if (rc == EVREP_OK && (nbytes == 0 || !evrep_mixed_density_is_specialized(win, func, agg, 4, EVREP_STACK_SBN, 1000))) return 7;
+  }
   puts("ok");
   return 0;
 }
