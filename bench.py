@@ -565,6 +565,21 @@ def run_gpu_arm(a):
     bounds = [B * g // n_groups for g in range(n_groups + 1)]
     offs = ev.offsets
     pk = pk_mod.pack_host(host["x"].numpy().view(np.uint16), host["y"].numpy().view(np.uint16), host["t"].numpy(), host["p"].numpy(), offs, H, W, pin=True)
+    # how fast the loader side can produce that format (reported, not part of any timed region): the library's host encoder on pageable
+    # buffers, all host threads it takes (at most 16)
+    packer = None
+    if rank == 0:
+        try:
+            t_p0 = time.perf_counter()
+            pk_probe = pk_mod.pack_host(host["x"].numpy().view(np.uint16), host["y"].numpy().view(np.uint16), host["t"].numpy(), host["p"].numpy(), offs, H, W,
+                                        fmt=3, pin=False)
+            dt_p = time.perf_counter() - t_p0
+            if pk_probe is not None:
+                packer = {"encoder": "evrep_pack_events_delta_host (C++, one fused pass, host threads)", "Gevents_per_s": B * N / dt_p / 1e9,
+                          "host_threads": min(os.cpu_count() or 1, 16), "note": "includes allocating the output buffers; the numpy restatement of the same encoder: ~0.012 Gev/s per core"}
+            del pk_probe
+        except Exception as e:  # reporting only
+            packer = {"error": f"{type(e).__name__}: {e}"}
     res_host = [torch.empty(B, dtype=torch.float32).pin_memory() for _ in range(2)]
     copy_st, comp_st = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     dbuf = [{k: torch.empty(int(offs[bounds[g + 1]] - offs[bounds[g]]), dtype=d[k].dtype, device=dev) for k in ("x", "y", "t", "p")}
@@ -695,6 +710,7 @@ def run_gpu_arm(a):
             "data": "synthetic", "config": config_dict(a, B),
             "e2e": {"value": e2e_value, "unit": "Gevents/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * 4,
                     "gpu_launches": e2e_launches,
+                    "host_packer": packer,
                     "host_format": (f"packed wire format {pk.fmt} ({h2d / (B * N):.2f} B/event: " + {3: "x, y, a polarity bit and the 2-bit difference to the previous event's timestamp in 3 bytes, larger differences in a side table, ", 4: "x, y, polarity and the offset to the base timestamp of its block in one 32-bit word, ", 6: "a 32-bit word plus a 16-bit time offset, "}[pk.fmt] +
                                     f"blocks of {1 << pk.block_shift} events; packed.pack_host on the loader side, one decode kernel on the GPU)") if pk is not None
                                    else "SoA arrays, 9 B/event (the stream does not fit the packed formats)",

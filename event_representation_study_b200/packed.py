@@ -17,6 +17,7 @@ import torch
 
 from . import batched as eb
 from ._lib import check, lib
+from ._lib import EINVAL as _EINVAL, EUNSUPPORTED as _EUNSUPPORTED, EWORKSPACE as _EWORKSPACE
 
 BLOCK_SHIFT = {3: 6, 4: 6, 6: 8}  # events per block: 64 / 64 / 256
 
@@ -112,11 +113,71 @@ def _pack3(x, y, p8, rel, offsets, xb, yb, pin):
     return PackedEvents(None, None, tens[1], offsets, 3, xb, yb, 6, rec3=tens[0], esc_prefix=tens[2], esc_dt=tens[3])
 
 
-def pack_host(x, y, t, p, offsets, H, W, fmt=None, pin=False):
+def _pack3_native(x, y, t, p, offsets, H, W, pin, threads):
+    """Format 3 through the library's host encoder (evrep_pack_events_delta_host: one fused pass on a few threads, byte-identical
+    to _pack3) -> PackedEvents, None when the stream does not fit the format, or NotImplemented when the arrays are not in the
+    layout the encoder reads (it takes them as they are: no copies)."""
+    total, B = int(offsets[-1]), len(offsets) - 1
+    arrs = []
+    for v, kinds in ((x, (np.uint16, np.int16)), (y, (np.uint16, np.int16)), (t, (np.int32, np.int64)), (p, (np.int8,))):
+        v = np.asarray(v)
+        if v.dtype.type not in kinds or not v.flags.c_contiguous or len(v) < total:
+            return NotImplemented
+        arrs.append(v)
+    x, y, t, p = arrs
+    n_blocks = int(lib.evrep_pack_delta_host_blocks(offsets.ctypes.data, B))
+    if n_blocks < 0:
+        return NotImplemented
+    mk = (lambda n, dt: torch.empty(max(n, 1), dtype=dt).pin_memory()) if pin else (lambda n, dt: torch.empty(max(n, 1), dtype=dt))
+    rec3, tbase, esc_prefix = mk(192 * n_blocks, torch.uint8), mk(n_blocks, torch.int32), mk(n_blocks + 1, torch.int32)
+    cap = max(1024, total // 256)  # a sorted stream of N events in ~0.3 s escapes ~1e-5 of them; grown on demand
+    need = ctypes.c_int64(0)
+    while True:
+        esc_dt = mk(cap, torch.int32)
+        rc = lib.evrep_pack_events_delta_host(x.ctypes.data, y.ctypes.data, t.ctypes.data, t.dtype.itemsize, p.ctypes.data, offsets.ctypes.data, B, H, W,
+                                              rec3.data_ptr(), tbase.data_ptr(), esc_prefix.data_ptr(), esc_dt.data_ptr(), cap, ctypes.byref(need),
+                                              int(threads))
+        if rc == _EWORKSPACE:
+            cap = int(need.value)
+            continue
+        break
+    if rc == _EUNSUPPORTED:
+        return None
+    if rc == _EINVAL and b"outside the sensor" in lib.evrep_last_error():
+        raise IndexError("event outside the sensor")
+    check(rc)
+    n_esc = int(need.value)
+    if n_esc == 0:
+        esc_dt[:1] = 0  # (the numpy packer ships one zero so that the device pointer stays valid)
+    return PackedEvents(None, None, tbase[:n_blocks], offsets, 3, _bits(W), _bits(H), 6, rec3=rec3[:192 * n_blocks],
+                        esc_prefix=esc_prefix[:n_blocks + 1], esc_dt=esc_dt[:max(n_esc, 1)])
+
+
+def pack_host(x, y, t, p, offsets, H, W, fmt=None, pin=False, native=True, threads=0):
     """SoA numpy events of a CSR batch -> PackedEvents, or None when the stream fits none of the formats (sparse or unsorted
-    streams: upload the SoA arrays instead).  fmt: 3, 4, 6 or None (= the smallest that fits)."""
+    streams: upload the SoA arrays instead).  fmt: 3, 4, 6 or None (= the smallest that fits).  Format 3 is written by the
+    library's host encoder when the arrays are uint16 / int16 x, y, int32 / int64 t and int8 p (native=False: the numpy
+    passes, ~40 x slower, kept as the restatement the tests hold the encoder to); threads: host threads of that encoder
+    (0 = as many as the machine has, at most 16)."""
     offsets = np.ascontiguousarray(offsets, np.int64)
     total = int(offsets[-1])
+    if native and fmt in (None, 3):
+        try:
+            pk3 = _pack3_native(x, y, t, p, offsets, H, W, pin, threads)
+        except (IndexError, ValueError):
+            raise
+        except Exception as e:  # e.g. pinned memory unavailable: the numpy passes below write the same bytes
+            import warnings
+            warnings.warn(f"native event packer unavailable ({type(e).__name__}: {e}); packing with numpy")
+            pk3 = NotImplemented
+        if pk3 is not NotImplemented:
+            if pk3 is not None or fmt == 3:
+                return pk3
+            fmt_rest = (4, 6)
+        else:
+            fmt_rest = None
+    else:
+        fmt_rest = None
     x = np.asarray(x)[:total].astype(np.uint32)
     y = np.asarray(y)[:total].astype(np.uint32)
     if total and (x.max() >= W or y.max() >= H):
@@ -129,7 +190,7 @@ def pack_host(x, y, t, p, offsets, H, W, fmt=None, pin=False):
     t64 = np.asarray(t)[:total].astype(np.int64)
     first = np.repeat(t64[offsets[:-1][n > 0]], n[n > 0]) if total else np.zeros(0, np.int64)
     rel = t64 - first
-    for f in ((fmt,) if fmt else (3, 4, 6)):
+    for f in ((fmt,) if fmt else (fmt_rest or (3, 4, 6))):
         if f == 3:
             pk3 = _pack3(x, y, p8, rel, offsets, xb, yb, pin)
             if pk3 is not None:

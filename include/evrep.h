@@ -421,6 +421,20 @@ int evrep_est_backward_batched(const uint16_t* x, const uint16_t* y, const float
                                int H, int W, int C, const double* breaks, int K, const float* grad_out, double* seg_sums,
                                void* workspace, size_t workspace_bytes, evrep_stream_t stream);
 
+/* Host-side encoder of packed wire format 3, the loader's half of evrep_unpack_events_delta (no counterpart in the reference: its
+ * loaders slice, concatenate and cast the event arrays per sample in Python, ev-YOLOv6/yolov6/data/gen1_2yolo.py:186-208).  Every
+ * pointer is a HOST pointer.  x, y, t (t_bytes 4 or 8), p: SoA events of B windows (win_offsets, B + 1).  Outputs, caller
+ * allocated: rec3 (192 bytes per block of 64 events; evrep_pack_delta_host_blocks gives the block count), tbase (one int32 per
+ * block), esc_prefix (blocks + 1 entries) and esc_dt (esc_capacity entries; the number needed comes back in *n_escapes -
+ * EVREP_EWORKSPACE when it does not fit, call again with a larger table).  One fused pass over the events on n_threads host
+ * threads (< 1: as many as the machine has, at most 16); byte-identical to packed.py's numpy packer.  EVREP_EUNSUPPORTED when
+ * the stream does not fit the format (a window not time sorted inside a block, a polarity other than -1 / +1, x and y needing
+ * more than 21 bits, a window spanning 2^31 us): ship formats 4 / 6 or the SoA arrays instead. */
+int64_t evrep_pack_delta_host_blocks(const int64_t* win_offsets, int B);
+int evrep_pack_events_delta_host(const uint16_t* x, const uint16_t* y, const void* t, int t_bytes, const int8_t* p,
+                                 const int64_t* win_offsets, int B, int H, int W, uint8_t* rec3, int32_t* tbase,
+                                 uint32_t* esc_prefix, uint32_t* esc_dt, int64_t esc_capacity, int64_t* n_escapes, int n_threads);
+
 #ifdef __cplusplus
 }
 #endif

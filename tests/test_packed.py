@@ -99,3 +99,69 @@ def test_ergo12_from_a_packed_batch_equals_the_soa_batch(cuda_device):
         assert pk is not None and pk.fmt == fmt
         got = eb.ergo12(packed.upload(pk, "cuda"), H, W)
         assert torch.equal(got, want)
+
+
+def _same(a, b):
+    import torch
+    assert (a is None) == (b is None)
+    if a is None:
+        return
+    assert a.fmt == b.fmt == 3 and a.x_bits == b.x_bits and a.y_bits == b.y_bits and a.block_shift == b.block_shift
+    for k in ("rec3", "tbase", "esc_prefix", "esc_dt"):
+        assert torch.equal(getattr(a, k), getattr(b, k)), k
+
+
+@pytest.mark.parametrize("sizes,H,W,dur,t_dtype,threads", [
+    ([5000, 0, 64, 65, 1, 12345, 63, 129], 720, 1280, 2_000, np.int32, 1),
+    ([4000, 130], 240, 304, 3_000_000, np.int64, 1),        # sparse: one event in four escapes (capacity grown on demand)
+    ([300_000, 1, 0, 280_001], 720, 1280, 300_000, np.int32, 4),  # > 4096 blocks: the threaded path
+    ([0, 0], 240, 304, 1000, np.int32, 2), ([], 240, 304, 1000, np.int32, 1),
+])
+def test_native_host_encoder_equals_the_numpy_packer(sizes, H, W, dur, t_dtype, threads):
+    """evrep_pack_events_delta_host (one fused pass in C++, host threads) writes byte for byte what the numpy passes of
+    packed._pack3 write: block records, base timestamps, escape prefix and escape table."""
+    from event_representation_study_b200 import packed
+    from event_representation_study_b200.synth import pack_batch
+    wins, b = _batch(sizes, H, W, 11, duration_us=dur)
+    if not sizes:
+        b = pack_batch([])
+    t = b["t"].astype(t_dtype) if len(b["t"]) else np.zeros(0, t_dtype)
+    ref = packed.pack_host(b["x"], b["y"], t, b["p"], b["offsets"], H, W, fmt=3, native=False)
+    nat = packed.pack_host(b["x"], b["y"], t, b["p"], b["offsets"], H, W, fmt=3, native=True, threads=threads)
+    assert ref is not None
+    _same(ref, nat)
+    if int(b["offsets"][-1]):
+        x, y, tt, p = packed.unpack_numpy(nat)
+        assert np.array_equal(x, b["x"]) and np.array_equal(y, b["y"]) and np.array_equal(p, b["p"])
+
+
+def test_native_host_encoder_refuses_what_the_numpy_packer_refuses():
+    from event_representation_study_b200 import packed
+    H, W = 240, 304
+    wins, b = _batch([3000, 500], H, W, 21)
+    args = lambda **kw: (kw.get("x", b["x"]), kw.get("y", b["y"]), kw.get("t", b["t"]), kw.get("p", b["p"]), b["offsets"], H, W)
+    t_bad = b["t"].copy()
+    t_bad[100], t_bad[101] = t_bad[101] + 5, t_bad[100]  # a negative difference inside a block
+    p0 = b["p"].copy()
+    p0[7] = 0
+    for kw in ({"t": t_bad}, {"p": p0}):
+        assert packed.pack_host(*args(**kw), fmt=3, native=True) is None
+        assert packed.pack_host(*args(**kw), fmt=3, native=False) is None
+    pk, pk_np = packed.pack_host(*args(p=p0), native=True), packed.pack_host(*args(p=p0), native=False)
+    assert (pk is None) == (pk_np is None) and (pk is None or pk.fmt == pk_np.fmt != 3)  # falls through to the next formats, like the numpy path
+    wins_d, bd = _batch([30000], H, W, 22, duration_us=30_000)
+    pd = bd["p"].copy()
+    pd[7] = 0
+    pk = packed.pack_host(bd["x"], bd["y"], bd["t"], pd, bd["offsets"], H, W, native=True)
+    assert pk is not None and pk.fmt == 4
+    x_bad = b["x"].copy()
+    x_bad[5] = W
+    for native in (True, False):
+        with pytest.raises(IndexError):
+            packed.pack_host(*args(x=x_bad), native=native)
+    # arrays in another layout (int64 coordinates) are packed by the numpy passes: same bytes
+    _same(packed.pack_host(b["x"].astype(np.int64), b["y"].astype(np.int64), b["t"], b["p"].astype(np.int64), b["offsets"], H, W, fmt=3),
+          packed.pack_host(*args(), fmt=3, native=True))
+    # a sensor whose coordinates need more than 21 bits
+    big = packed.pack_host(np.array([4000], np.uint16), np.array([3000], np.uint16), np.array([5], np.int32), np.array([1], np.int8), np.array([0, 1]), 4000, 5000)
+    assert big is not None and big.fmt in (4, 6)
