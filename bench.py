@@ -575,7 +575,7 @@ def run_gpu_arm(a):
                                         fmt=3, pin=False)
             dt_p = time.perf_counter() - t_p0
             if pk_probe is not None:
-                packer = {"encoder": "evrep_pack_events_delta_host (C++, one fused pass, host threads)", "Gevents_per_s": B * N / dt_p / 1e9,
+                packer = {"encoder": "evrep_pack_events_delta_host (C++, one fused pass, AVX2, host threads)", "Gevents_per_s": B * N / dt_p / 1e9,
                           "host_threads": min(os.cpu_count() or 1, 16), "note": "includes allocating the output buffers; the numpy restatement of the same encoder: ~0.012 Gev/s per core"}
             del pk_probe
         except Exception as e:  # reporting only

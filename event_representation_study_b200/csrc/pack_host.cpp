@@ -3,9 +3,10 @@
 //
 // The numpy packer needs ~10 vectorised passes and manages ~12 M events/s on a core; the engine takes 17 G events/s over the
 // link in this format, so a loader that packs on the fly needs a packer that runs at memory speed: one fused pass per block
-// of 64 events, blocks spread over a few host threads.  (The reference's loaders do the equivalent slicing / casting per
+// of 64 events (eight events per step with AVX2), blocks spread over a few host threads.  (The reference's loaders do the equivalent slicing / casting per
 // sample in Python, ev-YOLOv6/yolov6/data/gen1_2yolo.py:186-208; this is the native replacement for that step.)
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -13,7 +14,15 @@
 #include <thread>
 #include <vector>
 
-#include "evrep_common.cuh"
+#include "../../include/evrep.h"
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#define EVREP_PACK_AVX2 1
+#endif
+
+namespace evrep {
+void set_error(const char* fmt, ...);  // api.cu: thread-local error text
+}
 
 namespace {
 
@@ -36,8 +45,71 @@ struct Job {
   int32_t* tbase;
   uint32_t* esc_count;  // per block (pass 1), then exclusive prefix in place -> esc_prefix
   uint32_t* esc_dt;
+  bool avx2 = false;           // full blocks of int32 timestamps take the eight-events-per-step path
   std::atomic<int> status{0};  // bit 0 unsorted, bit 1 polarity not -1 / +1, bit 2 pixel outside the sensor, bit 3 time range
 };
+
+#ifdef EVREP_PACK_AVX2
+// One full block of 64 events with int32 timestamps, eight events per step.  All checks are exact without 64-bit arithmetic:
+// t >= t_first is a signed compare, t - t_first < 2^31 is "the wrapped difference is not negative", and once both neighbours
+// pass those two, their difference cannot wrap.  Returns the `bad` bits; *n_esc_out = escapes of the block.
+__attribute__((target("avx2"))) int block64_avx2(const uint16_t* x, const uint16_t* y, const int32_t* t, const int8_t* p, int32_t t_first, uint32_t Wd,
+                                                  uint32_t Hd, int xb, uint32_t sh_p, uint32_t sh_c, uint8_t* out, uint32_t* n_esc_out) {
+  const __m256i v_first = _mm256_set1_epi32(t_first), v_three = _mm256_set1_epi32(3), v_two = _mm256_set1_epi32(2), v_one = _mm256_set1_epi32(1),
+                v_m1 = _mm256_set1_epi32(-1), v_zero = _mm256_setzero_si256(), v_w = _mm256_set1_epi32((int)Wd - 1), v_h = _mm256_set1_epi32((int)Hd - 1);
+  const __m128i c_xb = _mm_cvtsi32_si128(xb), c_p = _mm_cvtsi32_si128((int)sh_p), c_c = _mm_cvtsi32_si128((int)sh_c);
+  const __m256i pick = _mm256_setr_epi8(0, 1, 2, 4, 5, 6, 8, 9, 10, 12, 13, 14, -1, -1, -1, -1, 0, 1, 2, 4, 5, 6, 8, 9, 10, 12, 13, 14, -1, -1, -1, -1);
+  const __m256i shift_in = _mm256_setr_epi32(0, 0, 1, 2, 3, 4, 5, 6);
+  __m256i f_sort = v_zero, f_pol = v_zero, f_pix = v_zero, f_rng = v_zero;
+  uint32_t n_esc = 0;
+  for (int g = 0; g < 8; ++g) {
+    const __m256i tv = _mm256_loadu_si256((const __m256i*)(t + 8 * g));
+    const __m256i tprev = g ? _mm256_loadu_si256((const __m256i*)(t + 8 * g - 1)) : _mm256_permutevar8x32_epi32(tv, shift_in);  // first event: itself
+    const __m256i xv = _mm256_cvtepu16_epi32(_mm_loadu_si128((const __m128i*)(x + 8 * g)));
+    const __m256i yv = _mm256_cvtepu16_epi32(_mm_loadu_si128((const __m128i*)(y + 8 * g)));
+    const __m256i pv = _mm256_cvtepi8_epi32(_mm_loadl_epi64((const __m128i*)(p + 8 * g)));
+    const __m256i rel = _mm256_sub_epi32(tv, v_first);
+    f_rng = _mm256_or_si256(f_rng, _mm256_cmpgt_epi32(v_zero, rel));   // t - t_first >= 2^31 (or t < t_first, caught below as well)
+    f_sort = _mm256_or_si256(f_sort, _mm256_cmpgt_epi32(v_first, tv));  // before the window's first event
+    const __m256i d = _mm256_sub_epi32(tv, tprev);
+    f_sort = _mm256_or_si256(f_sort, _mm256_cmpgt_epi32(v_zero, d));
+    const __m256i pos = _mm256_cmpeq_epi32(pv, v_one);
+    f_pol = _mm256_or_si256(f_pol, _mm256_andnot_si256(_mm256_or_si256(pos, _mm256_cmpeq_epi32(pv, v_m1)), v_m1));
+    f_pix = _mm256_or_si256(f_pix, _mm256_or_si256(_mm256_cmpgt_epi32(xv, v_w), _mm256_cmpgt_epi32(yv, v_h)));
+    const __m256i esc = _mm256_cmpgt_epi32(d, v_two);
+    n_esc += (uint32_t)__builtin_popcount((unsigned)_mm256_movemask_ps(_mm256_castsi256_ps(esc)));
+    const __m256i code = _mm256_min_epi32(_mm256_max_epi32(d, v_zero), v_three);
+    __m256i rec = _mm256_or_si256(xv, _mm256_sll_epi32(yv, c_xb));
+    rec = _mm256_or_si256(rec, _mm256_sll_epi32(_mm256_and_si256(pos, v_one), c_p));
+    rec = _mm256_or_si256(rec, _mm256_sll_epi32(code, c_c));
+    const __m256i b = _mm256_shuffle_epi8(rec, pick);  // 12 payload bytes at the bottom of each 128-bit half
+    const __m128i lo = _mm256_castsi256_si128(b), hi = _mm256_extracti128_si256(b, 1);
+    _mm_storeu_si128((__m128i*)out, lo);            // 16 bytes: the 4 spare ones are overwritten next
+    _mm_storel_epi64((__m128i*)(out + 12), hi);     // 8 + 4 bytes: exactly the second half's payload
+    const int tail = _mm_extract_epi32(hi, 2);
+    memcpy(out + 20, &tail, 4);
+    out += 24;
+  }
+  *n_esc_out = n_esc;
+  int bad = 0;
+  if (!_mm256_testz_si256(f_sort, f_sort)) bad |= 1;
+  if (!_mm256_testz_si256(f_pol, f_pol)) bad |= 2;
+  if (!_mm256_testz_si256(f_pix, f_pix)) bad |= 4;
+  if (!_mm256_testz_si256(f_rng, f_rng)) bad |= 8;
+  return bad;
+}
+template <typename TT>
+inline bool try_block64(const uint16_t*, const uint16_t*, const TT*, const int8_t*, int64_t, uint32_t, uint32_t, int, uint32_t, uint32_t, uint8_t*, uint32_t*, int*, bool) {
+  return false;  // 64-bit timestamps: the scalar loop
+}
+template <>
+inline bool try_block64<int32_t>(const uint16_t* x, const uint16_t* y, const int32_t* t, const int8_t* p, int64_t t_first, uint32_t Wd, uint32_t Hd, int xb,
+                                 uint32_t sh_p, uint32_t sh_c, uint8_t* out, uint32_t* n_esc, int* bad, bool have_avx2) {
+  if (!have_avx2) return false;
+  *bad |= block64_avx2(x, y, t, p, (int32_t)t_first, Wd, Hd, xb, sh_p, sh_c, out, n_esc);
+  return true;
+}
+#endif
 
 // blocks [b0, b1): pass 1 writes rec3 / tbase / escape counts, pass 2 (fill) writes the escapes at their prefix.
 // Everything the loop reads is copied into locals first: the byte stores into rec3 may alias anything as far as the compiler
@@ -75,6 +147,12 @@ void run_blocks_t(Job& j, int64_t b0, int64_t b1, bool fill) {
     if (rel0 >= ((int64_t)1 << 31)) bad |= 8;
     j.tbase[b] = (int32_t)rel0;
     uint32_t n_esc = 0;
+#ifdef EVREP_PACK_AVX2
+    if (e1 - e0 == 64 && try_block64<TT>(x + e0, y + e0, t + e0, p + e0, t_first, Wd, Hd, xb, sh_p, sh_c, out, &n_esc, &bad, j.avx2)) {
+      j.esc_count[b] = n_esc;
+      continue;
+    }
+#endif
     // one event -> its 24-bit record (the first event of a block is compared with itself: difference 0)
     auto record = [&](int64_t i) -> uint32_t {
       const int64_t ti = (int64_t)t[i];
@@ -161,6 +239,9 @@ extern "C" int evrep_pack_events_delta_host(const uint16_t* x, const uint16_t* y
   j.B = B; j.H = H; j.W = W; j.xb = xb; j.yb = yb;
   j.blk_prefix = blk_prefix.data();
   j.rec3 = rec3; j.tbase = tbase; j.esc_count = esc_prefix; j.esc_dt = esc_dt;
+#ifdef EVREP_PACK_AVX2
+  j.avx2 = __builtin_cpu_supports("avx2") && !getenv("EVREP_PACK_SCALAR");
+#endif
   if (n_threads < 1) n_threads = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
   parallel_blocks(j, n_blocks, n_threads, false);
   const int bad = j.status.load();

@@ -157,7 +157,7 @@ def pack_host(x, y, t, p, offsets, H, W, fmt=None, pin=False, native=True, threa
     """SoA numpy events of a CSR batch -> PackedEvents, or None when the stream fits none of the formats (sparse or unsorted
     streams: upload the SoA arrays instead).  fmt: 3, 4, 6 or None (= the smallest that fits).  Format 3 is written by the
     library's host encoder when the arrays are uint16 / int16 x, y, int32 / int64 t and int8 p (native=False: the numpy
-    passes, ~40 x slower, kept as the restatement the tests hold the encoder to); threads: host threads of that encoder
+    passes, ~30 x slower, kept as the restatement the tests hold the encoder to); threads: host threads of that encoder
     (0 = as many as the machine has, at most 16)."""
     offsets = np.ascontiguousarray(offsets, np.int64)
     total = int(offsets[-1])

@@ -165,3 +165,65 @@ def test_native_host_encoder_refuses_what_the_numpy_packer_refuses():
     # a sensor whose coordinates need more than 21 bits
     big = packed.pack_host(np.array([4000], np.uint16), np.array([3000], np.uint16), np.array([5], np.int32), np.array([1], np.int8), np.array([0, 1]), 4000, 5000)
     assert big is not None and big.fmt in (4, 6)
+
+
+def test_simd_and_scalar_host_encoders_agree_on_adversarial_streams(monkeypatch):
+    """The eight-events-per-step path (AVX2, int32 timestamps, full blocks) and the scalar loop must return the same code and
+    the same bytes for anything: timestamps at the ends of the int32 range, negative differences, bad polarities, pixels
+    outside the sensor, escapes of every size."""
+    import ctypes
+    from event_representation_study_b200 import _lib
+    lib = _lib.lib
+    rng = np.random.default_rng(2024)
+    H, W = 480, 640
+
+    def run(x, y, t, p, offs, scalar):
+        if scalar:
+            monkeypatch.setenv("EVREP_PACK_SCALAR", "1")
+        else:
+            monkeypatch.delenv("EVREP_PACK_SCALAR", raising=False)
+        B = len(offs) - 1
+        nb = int(lib.evrep_pack_delta_host_blocks(offs.ctypes.data, B))
+        rec3, tbase, ep, ed = np.full(192 * nb + 8, 0xAB, np.uint8), np.zeros(nb, np.int32), np.zeros(nb + 1, np.uint32), np.zeros(len(x) + 1, np.uint32)
+        need = ctypes.c_int64(-1)
+        rc = lib.evrep_pack_events_delta_host(x.ctypes.data, y.ctypes.data, t.ctypes.data, 4, p.ctypes.data, offs.ctypes.data, B, H, W, rec3.ctypes.data,
+                                              tbase.ctypes.data, ep.ctypes.data, ed.ctypes.data, len(ed), ctypes.byref(need), 1)
+        return rc, (rec3, tbase, ep, ed[:max(need.value, 0)]) if rc == 0 else None
+
+    kinds = ["clean", "gaps", "unsorted", "polarity", "pixel", "low-end", "high-end", "wrap"]
+    seen_ok = seen_bad = 0
+    for trial in range(64):
+        kind = kinds[trial % len(kinds)]
+        n = int(rng.integers(64, 400))
+        offs = np.array([0, n], np.int64)
+        x = rng.integers(0, W, n).astype(np.uint16)
+        y = rng.integers(0, H, n).astype(np.uint16)
+        p = rng.choice(np.array([-1, 1], np.int8), n)
+        t = np.cumsum(rng.integers(0, 4, n)).astype(np.int64)
+        if kind == "gaps":
+            t = np.cumsum(rng.choice([0, 1, 2, 3, 1000, 2**20], n)).astype(np.int64)
+        if kind == "low-end":
+            t = t - 2**31
+        if kind == "high-end":
+            t = t + (2**31 - 1 - int(t[-1]))
+        if kind == "wrap":  # spans more than 2^31: must be refused by both
+            t = t - 2**31
+            t[n // 2:] += 2**31 + 5
+        t = np.clip(t, -2**31, 2**31 - 1).astype(np.int32)
+        k = int(rng.integers(1, n))
+        if kind == "unsorted":
+            t[k] = t[k - 1] - int(rng.integers(1, 50)) if t[k - 1] > -2**31 + 60 else t[k]
+        if kind == "polarity":
+            p[k] = rng.choice(np.array([0, 2, -2, 127], np.int8))
+        if kind == "pixel":
+            (x if trial % 2 else y)[k] = (W if trial % 2 else H) + int(rng.integers(0, 3))
+        a, b = run(x, y, t, p, offs, scalar=False), run(x, y, t, p, offs, scalar=True)
+        assert a[0] == b[0], (kind, trial, a[0], b[0])
+        if a[0] == 0:
+            seen_ok += 1
+            for u, v in zip(a[1], b[1]):
+                assert np.array_equal(u, v), (kind, trial)
+            assert (a[1][0][-8:] == 0xAB).all()  # nothing written past the last block
+        else:
+            seen_bad += 1
+    assert seen_ok >= 16 and seen_bad >= 16
