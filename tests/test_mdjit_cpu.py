@@ -13,6 +13,17 @@ from event_representation_study_b200 import _lib
 lib = _lib.lib
 
 
+def _nvrtc_available():
+    w = np.zeros(4, np.int8)
+    f = np.full(4, 2, np.int8)
+    nb = ctypes.c_size_t(0)
+    rc = lib.evrep_mixed_density_specialize_compile_only(w.ctypes.data, f.ctypes.data, w.ctypes.data, 4, 0, 1000, ctypes.byref(nb))
+    return not (rc == _lib.EUNSUPPORTED and b"unavailable" in lib.evrep_last_error())
+
+
+pytestmark = pytest.mark.skipif(not _nvrtc_available(), reason="libnvrtc.so.12 (CUDA toolkit runtime compiler) is not installed on this machine")
+
+
 def codes(wi, fu, ag):
     return (np.array(wi, np.int8), np.array([_lib.FUNCS[f] for f in fu], np.int8), np.array([_lib.AGGS[a] for a in ag], np.int8))
 
