@@ -45,6 +45,7 @@ struct Job {
   int32_t* tbase;
   uint32_t* esc_count;  // per block (pass 1), then exclusive prefix in place -> esc_prefix
   uint32_t* esc_dt;
+  bool zero_neg = false;       // p == 0 is accepted and written like p == -1 (the caller's consumers treat both as "negative")
   bool avx2 = false;           // full blocks of int32 timestamps take the eight-events-per-step path
   std::atomic<int> status{0};  // bit 0 unsorted, bit 1 polarity not -1 / +1, bit 2 pixel outside the sensor, bit 3 time range
 };
@@ -54,12 +55,13 @@ struct Job {
 // t >= t_first is a signed compare, t - t_first < 2^31 is "the wrapped difference is not negative", and once both neighbours
 // pass those two, their difference cannot wrap.  Returns the `bad` bits; *n_esc_out = escapes of the block.
 __attribute__((target("avx2"))) int block64_avx2(const uint16_t* x, const uint16_t* y, const int32_t* t, const int8_t* p, int32_t t_first, uint32_t Wd,
-                                                  uint32_t Hd, int xb, uint32_t sh_p, uint32_t sh_c, uint8_t* out, uint32_t* n_esc_out) {
+                                                  uint32_t Hd, int xb, uint32_t sh_p, uint32_t sh_c, bool zero_neg, uint8_t* out, uint32_t* n_esc_out) {
   const __m256i v_first = _mm256_set1_epi32(t_first), v_three = _mm256_set1_epi32(3), v_two = _mm256_set1_epi32(2), v_one = _mm256_set1_epi32(1),
                 v_m1 = _mm256_set1_epi32(-1), v_zero = _mm256_setzero_si256(), v_w = _mm256_set1_epi32((int)Wd - 1), v_h = _mm256_set1_epi32((int)Hd - 1);
   const __m128i c_xb = _mm_cvtsi32_si128(xb), c_p = _mm_cvtsi32_si128((int)sh_p), c_c = _mm_cvtsi32_si128((int)sh_c);
   const __m256i pick = _mm256_setr_epi8(0, 1, 2, 4, 5, 6, 8, 9, 10, 12, 13, 14, -1, -1, -1, -1, 0, 1, 2, 4, 5, 6, 8, 9, 10, 12, 13, 14, -1, -1, -1, -1);
   const __m256i shift_in = _mm256_setr_epi32(0, 0, 1, 2, 3, 4, 5, 6);
+  const __m256i v_neg_alt = _mm256_set1_epi32(zero_neg ? 0 : -1);  // the second value accepted as "negative"
   __m256i f_sort = v_zero, f_pol = v_zero, f_pix = v_zero, f_rng = v_zero;
   uint32_t n_esc = 0;
   for (int g = 0; g < 8; ++g) {
@@ -74,7 +76,7 @@ __attribute__((target("avx2"))) int block64_avx2(const uint16_t* x, const uint16
     const __m256i d = _mm256_sub_epi32(tv, tprev);
     f_sort = _mm256_or_si256(f_sort, _mm256_cmpgt_epi32(v_zero, d));
     const __m256i pos = _mm256_cmpeq_epi32(pv, v_one);
-    f_pol = _mm256_or_si256(f_pol, _mm256_andnot_si256(_mm256_or_si256(pos, _mm256_cmpeq_epi32(pv, v_m1)), v_m1));
+    f_pol = _mm256_or_si256(f_pol, _mm256_andnot_si256(_mm256_or_si256(_mm256_or_si256(pos, _mm256_cmpeq_epi32(pv, v_m1)), _mm256_cmpeq_epi32(pv, v_neg_alt)), v_m1));
     f_pix = _mm256_or_si256(f_pix, _mm256_or_si256(_mm256_cmpgt_epi32(xv, v_w), _mm256_cmpgt_epi32(yv, v_h)));
     const __m256i esc = _mm256_cmpgt_epi32(d, v_two);
     n_esc += (uint32_t)__builtin_popcount((unsigned)_mm256_movemask_ps(_mm256_castsi256_ps(esc)));
@@ -99,14 +101,14 @@ __attribute__((target("avx2"))) int block64_avx2(const uint16_t* x, const uint16
   return bad;
 }
 template <typename TT>
-inline bool try_block64(const uint16_t*, const uint16_t*, const TT*, const int8_t*, int64_t, uint32_t, uint32_t, int, uint32_t, uint32_t, uint8_t*, uint32_t*, int*, bool) {
+inline bool try_block64(const uint16_t*, const uint16_t*, const TT*, const int8_t*, int64_t, uint32_t, uint32_t, int, uint32_t, uint32_t, bool, uint8_t*, uint32_t*, int*, bool) {
   return false;  // 64-bit timestamps: the scalar loop
 }
 template <>
 inline bool try_block64<int32_t>(const uint16_t* x, const uint16_t* y, const int32_t* t, const int8_t* p, int64_t t_first, uint32_t Wd, uint32_t Hd, int xb,
-                                 uint32_t sh_p, uint32_t sh_c, uint8_t* out, uint32_t* n_esc, int* bad, bool have_avx2) {
+                                 uint32_t sh_p, uint32_t sh_c, bool zero_neg, uint8_t* out, uint32_t* n_esc, int* bad, bool have_avx2) {
   if (!have_avx2) return false;
-  *bad |= block64_avx2(x, y, t, p, (int32_t)t_first, Wd, Hd, xb, sh_p, sh_c, out, n_esc);
+  *bad |= block64_avx2(x, y, t, p, (int32_t)t_first, Wd, Hd, xb, sh_p, sh_c, zero_neg, out, n_esc);
   return true;
 }
 #endif
@@ -125,6 +127,7 @@ void run_blocks_t(Job& j, int64_t b0, int64_t b1, bool fill) {
   uint8_t* __restrict__ rec3 = j.rec3;
   const uint32_t Wd = (uint32_t)j.W, Hd = (uint32_t)j.H;
   const int xb = j.xb;
+  const bool zero_neg = j.zero_neg;
   const uint32_t sh_p = (uint32_t)(j.xb + j.yb), sh_c = sh_p + 1u;
   int w = (int)(std::upper_bound(blk_prefix, blk_prefix + j.B + 1, b0) - blk_prefix) - 1;  // window of block b0
   int bad = 0;
@@ -148,7 +151,7 @@ void run_blocks_t(Job& j, int64_t b0, int64_t b1, bool fill) {
     j.tbase[b] = (int32_t)rel0;
     uint32_t n_esc = 0;
 #ifdef EVREP_PACK_AVX2
-    if (e1 - e0 == 64 && try_block64<TT>(x + e0, y + e0, t + e0, p + e0, t_first, Wd, Hd, xb, sh_p, sh_c, out, &n_esc, &bad, j.avx2)) {
+    if (e1 - e0 == 64 && try_block64<TT>(x + e0, y + e0, t + e0, p + e0, t_first, Wd, Hd, xb, sh_p, sh_c, zero_neg, out, &n_esc, &bad, j.avx2)) {
       j.esc_count[b] = n_esc;
       continue;
     }
@@ -159,7 +162,7 @@ void run_blocks_t(Job& j, int64_t b0, int64_t b1, bool fill) {
       const int64_t d = ti - (int64_t)t[i > e0 ? i - 1 : i];
       const uint32_t xi = x[i], yi = y[i];
       const int pi = p[i];
-      bad |= (d < 0) | ((pi != 1 && pi != -1) << 1) | ((xi >= Wd || yi >= Hd) << 2) | ((d >= ((int64_t)1 << 32) || ti - t_first >= ((int64_t)1 << 31)) << 3);
+      bad |= (d < 0) | ((pi != 1 && pi != -1 && !(zero_neg && pi == 0)) << 1) | ((xi >= Wd || yi >= Hd) << 2) | ((d >= ((int64_t)1 << 32) || ti - t_first >= ((int64_t)1 << 31)) << 3);
       n_esc += d > 2;
       return xi | (yi << xb) | ((pi > 0 ? 1u : 0u) << sh_p) | ((d > 2 ? 3u : (uint32_t)d) << sh_c);
     };
@@ -219,7 +222,7 @@ extern "C" int64_t evrep_pack_delta_host_blocks(const int64_t* win_offsets, int 
 
 extern "C" int evrep_pack_events_delta_host(const uint16_t* x, const uint16_t* y, const void* t, int t_bytes, const int8_t* p, const int64_t* win_offsets,
                                             int B, int H, int W, uint8_t* rec3, int32_t* tbase, uint32_t* esc_prefix, uint32_t* esc_dt,
-                                            int64_t esc_capacity, int64_t* n_escapes, int n_threads) {
+                                            int64_t esc_capacity, int64_t* n_escapes, int zero_is_negative, int n_threads) {
   using evrep::set_error;
   if (B < 0 || !win_offsets || (t_bytes != 4 && t_bytes != 8) || H < 1 || W < 1 || !esc_prefix || !n_escapes) { set_error("bad argument"); return EVREP_EINVAL; }
   const int xb = bits_for(W), yb = bits_for(H);
@@ -239,6 +242,7 @@ extern "C" int evrep_pack_events_delta_host(const uint16_t* x, const uint16_t* y
   j.B = B; j.H = H; j.W = W; j.xb = xb; j.yb = yb;
   j.blk_prefix = blk_prefix.data();
   j.rec3 = rec3; j.tbase = tbase; j.esc_count = esc_prefix; j.esc_dt = esc_dt;
+  j.zero_neg = zero_is_negative != 0;
 #ifdef EVREP_PACK_AVX2
   j.avx2 = __builtin_cpu_supports("avx2") && !getenv("EVREP_PACK_SCALAR");
 #endif

@@ -113,7 +113,7 @@ def _pack3(x, y, p8, rel, offsets, xb, yb, pin):
     return PackedEvents(None, None, tens[1], offsets, 3, xb, yb, 6, rec3=tens[0], esc_prefix=tens[2], esc_dt=tens[3])
 
 
-def _pack3_native(x, y, t, p, offsets, H, W, pin, threads):
+def _pack3_native(x, y, t, p, offsets, H, W, pin, threads, zero_as_negative=False):
     """Format 3 through the library's host encoder (evrep_pack_events_delta_host: one fused pass on a few threads, byte-identical
     to _pack3) -> PackedEvents, None when the stream does not fit the format, or NotImplemented when the arrays are not in the
     layout the encoder reads (it takes them as they are: no copies)."""
@@ -136,7 +136,7 @@ def _pack3_native(x, y, t, p, offsets, H, W, pin, threads):
         esc_dt = mk(cap, torch.int32)
         rc = lib.evrep_pack_events_delta_host(x.ctypes.data, y.ctypes.data, t.ctypes.data, t.dtype.itemsize, p.ctypes.data, offsets.ctypes.data, B, H, W,
                                               rec3.data_ptr(), tbase.data_ptr(), esc_prefix.data_ptr(), esc_dt.data_ptr(), cap, ctypes.byref(need),
-                                              int(threads))
+                                              int(bool(zero_as_negative)), int(threads))
         if rc == _EWORKSPACE:
             cap = int(need.value)
             continue
@@ -153,17 +153,19 @@ def _pack3_native(x, y, t, p, offsets, H, W, pin, threads):
                         esc_prefix=esc_prefix[:n_blocks + 1], esc_dt=esc_dt[:max(n_esc, 1)])
 
 
-def pack_host(x, y, t, p, offsets, H, W, fmt=None, pin=False, native=True, threads=0):
+def pack_host(x, y, t, p, offsets, H, W, fmt=None, pin=False, native=True, threads=0, zero_as_negative=False):
     """SoA numpy events of a CSR batch -> PackedEvents, or None when the stream fits none of the formats (sparse or unsorted
     streams: upload the SoA arrays instead).  fmt: 3, 4, 6 or None (= the smallest that fits).  Format 3 is written by the
     library's host encoder when the arrays are uint16 / int16 x, y, int32 / int64 t and int8 p (native=False: the numpy
     passes, ~30 x slower, kept as the restatement the tests hold the encoder to); threads: host threads of that encoder
-    (0 = as many as the machine has, at most 16)."""
+    (0 = as many as the machine has, at most 16).  zero_as_negative: format 3 has one polarity bit; with this flag a {0, 1} stream
+    fits it too - p == 0 travels as "negative" and comes back as -1, which every representation here treats like 0 when the window
+    holds no -1 (operations.py:59-61) - instead of falling back to the 4-byte format (formats 4 / 6 keep the 0: they are lossless)."""
     offsets = np.ascontiguousarray(offsets, np.int64)
     total = int(offsets[-1])
     if native and fmt in (None, 3):
         try:
-            pk3 = _pack3_native(x, y, t, p, offsets, H, W, pin, threads)
+            pk3 = _pack3_native(x, y, t, p, offsets, H, W, pin, threads, zero_as_negative)
         except (IndexError, ValueError):
             raise
         except Exception as e:  # e.g. pinned memory unavailable: the numpy passes below write the same bytes
@@ -192,7 +194,7 @@ def pack_host(x, y, t, p, offsets, H, W, fmt=None, pin=False, native=True, threa
     rel = t64 - first
     for f in ((fmt,) if fmt else (fmt_rest or (3, 4, 6))):
         if f == 3:
-            pk3 = _pack3(x, y, p8, rel, offsets, xb, yb, pin)
+            pk3 = _pack3(x, y, np.where(p8 == 0, np.int8(-1), p8) if zero_as_negative else p8, rel, offsets, xb, yb, pin)
             if pk3 is not None:
                 return pk3
             continue

@@ -429,11 +429,15 @@ int evrep_est_backward_batched(const uint16_t* x, const uint16_t* y, const float
  * EVREP_EWORKSPACE when it does not fit, call again with a larger table).  One fused pass over the events on n_threads host
  * threads (< 1: as many as the machine has, at most 16); byte-identical to packed.py's numpy packer.  EVREP_EUNSUPPORTED when
  * the stream does not fit the format (a window not time sorted inside a block, a polarity other than -1 / +1, x and y needing
- * more than 21 bits, a window spanning 2^31 us): ship formats 4 / 6 or the SoA arrays instead. */
+ * more than 21 bits, a window spanning 2^31 us): ship formats 4 / 6 or the SoA arrays instead.  zero_is_negative != 0 also
+ * accepts p == 0 and writes it like p == -1 (the decoder then returns -1): for {0, 1} streams whose consumers treat 0 and -1
+ * alike - every representation of this library does when a window holds no -1 (operations.py:59-61, the p > 0 tests of
+ * event_stack.py / time_surface.py) - at the price of not being able to tell them apart afterwards. */
 int64_t evrep_pack_delta_host_blocks(const int64_t* win_offsets, int B);
 int evrep_pack_events_delta_host(const uint16_t* x, const uint16_t* y, const void* t, int t_bytes, const int8_t* p,
                                  const int64_t* win_offsets, int B, int H, int W, uint8_t* rec3, int32_t* tbase,
-                                 uint32_t* esc_prefix, uint32_t* esc_dt, int64_t esc_capacity, int64_t* n_escapes, int n_threads);
+                                 uint32_t* esc_prefix, uint32_t* esc_dt, int64_t esc_capacity, int64_t* n_escapes, int zero_is_negative,
+                                 int n_threads);
 
 #ifdef __cplusplus
 }

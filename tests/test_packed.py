@@ -177,7 +177,7 @@ def test_simd_and_scalar_host_encoders_agree_on_adversarial_streams(monkeypatch)
     rng = np.random.default_rng(2024)
     H, W = 480, 640
 
-    def run(x, y, t, p, offs, scalar):
+    def run(x, y, t, p, offs, scalar, zero_neg=False):
         if scalar:
             monkeypatch.setenv("EVREP_PACK_SCALAR", "1")
         else:
@@ -187,7 +187,7 @@ def test_simd_and_scalar_host_encoders_agree_on_adversarial_streams(monkeypatch)
         rec3, tbase, ep, ed = np.full(192 * nb + 8, 0xAB, np.uint8), np.zeros(nb, np.int32), np.zeros(nb + 1, np.uint32), np.zeros(len(x) + 1, np.uint32)
         need = ctypes.c_int64(-1)
         rc = lib.evrep_pack_events_delta_host(x.ctypes.data, y.ctypes.data, t.ctypes.data, 4, p.ctypes.data, offs.ctypes.data, B, H, W, rec3.ctypes.data,
-                                              tbase.ctypes.data, ep.ctypes.data, ed.ctypes.data, len(ed), ctypes.byref(need), 1)
+                                              tbase.ctypes.data, ep.ctypes.data, ed.ctypes.data, len(ed), ctypes.byref(need), int(zero_neg), 1)
         return rc, (rec3, tbase, ep, ed[:max(need.value, 0)]) if rc == 0 else None
 
     kinds = ["clean", "gaps", "unsorted", "polarity", "pixel", "low-end", "high-end", "wrap"]
@@ -217,7 +217,10 @@ def test_simd_and_scalar_host_encoders_agree_on_adversarial_streams(monkeypatch)
             p[k] = rng.choice(np.array([0, 2, -2, 127], np.int8))
         if kind == "pixel":
             (x if trial % 2 else y)[k] = (W if trial % 2 else H) + int(rng.integers(0, 3))
-        a, b = run(x, y, t, p, offs, scalar=False), run(x, y, t, p, offs, scalar=True)
+        zn = trial % 3 == 0  # every third trial also accepts p == 0 as "negative"
+        if zn and kind == "clean":
+            p[rng.integers(0, n, 5)] = 0
+        a, b = run(x, y, t, p, offs, scalar=False, zero_neg=zn), run(x, y, t, p, offs, scalar=True, zero_neg=zn)
         assert a[0] == b[0], (kind, trial, a[0], b[0])
         if a[0] == 0:
             seen_ok += 1
@@ -227,3 +230,22 @@ def test_simd_and_scalar_host_encoders_agree_on_adversarial_streams(monkeypatch)
         else:
             seen_bad += 1
     assert seen_ok >= 16 and seen_bad >= 16
+
+
+def test_zero_as_negative_lets_01_streams_use_the_three_byte_format():
+    """pack_host(zero_as_negative=True): p == 0 travels in format 3 as "negative" and decodes as -1 - native encoder and numpy
+    restatement write the same bytes, equal to packing the stream with its zeros replaced by -1."""
+    from event_representation_study_b200 import packed
+    H, W = 240, 304
+    wins, b = _batch([5000, 64, 70], H, W, 31, polarity="01", duration_us=20_000)
+    assert (b["p"] == 0).any() and (b["p"] == 1).any()
+    args = (b["x"], b["y"], b["t"])
+    plain = packed.pack_host(*args, b["p"], b["offsets"], H, W)
+    assert plain is not None and plain.fmt in (4, 6)                 # lossless by default: the zeros need the 2-bit polarity code
+    mapped = np.where(b["p"] == 0, -1, b["p"]).astype(np.int8)
+    want = packed.pack_host(*args, mapped, b["offsets"], H, W, fmt=3, native=False)
+    for native in (True, False):
+        got = packed.pack_host(*args, b["p"], b["offsets"], H, W, native=native, zero_as_negative=True)
+        _same(want, got)
+    x, y, t, p = packed.unpack_numpy(got)
+    assert np.array_equal(p, mapped) and np.array_equal(x, b["x"]) and np.array_equal(y, b["y"])
