@@ -153,6 +153,53 @@ def _pack3_native(x, y, t, p, offsets, H, W, pin, threads, zero_as_negative=Fals
                         esc_prefix=esc_prefix[:n_blocks + 1], esc_dt=esc_dt[:max(n_esc, 1)])
 
 
+class HostPacker:
+    """Format-3 encoder with its output buffers allocated ONCE (pinned, if asked): what a loader thread calls per batch.
+    `pack_host(pin=True)` pins fresh buffers on every call, and cudaHostAlloc costs milliseconds; this object keeps `slots`
+    sets of buffers sized for `max_events` / `max_windows` and hands them out round robin, so batch k + 1 can be packed while
+    the copy of batch k is still in flight.  pack() returns a PackedEvents whose tensors are views into the current slot
+    (valid until that slot comes round again), or None when the stream does not fit format 3 (see evrep_pack_events_delta_host).
+    Arrays must be in the encoder's layout: x, y uint16 / int16, t int32 / int64, p int8, C-contiguous."""
+
+    def __init__(self, max_events, max_windows, H, W, pin=True, slots=2, threads=0, zero_as_negative=False, escape_fraction=1 / 64):
+        self.H, self.W, self.threads, self.zero_as_negative = int(H), int(W), int(threads), bool(zero_as_negative)
+        self.max_events, self.max_windows = int(max_events), int(max_windows)
+        self.max_blocks = (self.max_events + 63) // 64 + self.max_windows  # every window may end in a partial block
+        self.esc_capacity = max(1024, int(self.max_events * escape_fraction))
+        mk = (lambda n, dt: torch.empty(n, dtype=dt).pin_memory()) if pin else (lambda n, dt: torch.empty(n, dtype=dt))
+        self._slots = [{"rec3": mk(192 * self.max_blocks, torch.uint8), "tbase": mk(self.max_blocks, torch.int32),
+                        "esc_prefix": mk(self.max_blocks + 1, torch.int32), "esc_dt": mk(self.esc_capacity, torch.int32)} for _ in range(max(1, int(slots)))]
+        self._next = 0
+
+    def pack(self, x, y, t, p, offsets):
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        total, B = int(offsets[-1]), len(offsets) - 1
+        if total > self.max_events or B > self.max_windows:
+            raise ValueError(f"batch of {total} events in {B} windows exceeds the packer's capacity ({self.max_events}, {self.max_windows})")
+        for v, kinds in ((x, (np.uint16, np.int16)), (y, (np.uint16, np.int16)), (t, (np.int32, np.int64)), (p, (np.int8,))):
+            if not isinstance(v, np.ndarray) or v.dtype.type not in kinds or not v.flags.c_contiguous or len(v) < total:
+                raise TypeError("HostPacker takes C-contiguous numpy arrays: x, y uint16 / int16, t int32 / int64, p int8")
+        n_blocks = int(lib.evrep_pack_delta_host_blocks(offsets.ctypes.data, B))
+        buf = self._slots[self._next]
+        self._next = (self._next + 1) % len(self._slots)
+        need = ctypes.c_int64(0)
+        rc = lib.evrep_pack_events_delta_host(x.ctypes.data, y.ctypes.data, t.ctypes.data, t.dtype.itemsize, p.ctypes.data, offsets.ctypes.data, B, self.H, self.W,
+                                              buf["rec3"].data_ptr(), buf["tbase"].data_ptr(), buf["esc_prefix"].data_ptr(), buf["esc_dt"].data_ptr(),
+                                              self.esc_capacity, ctypes.byref(need), int(self.zero_as_negative), self.threads)
+        if rc == _EUNSUPPORTED:
+            return None
+        if rc == _EWORKSPACE:
+            raise ValueError(f"{int(need.value)} timestamp escapes exceed the packer's table of {self.esc_capacity} (raise escape_fraction: the stream is sparse)")
+        if rc == _EINVAL and b"outside the sensor" in lib.evrep_last_error():
+            raise IndexError("event outside the sensor")
+        check(rc)
+        n_esc = int(need.value)
+        if n_esc == 0:
+            buf["esc_dt"][:1] = 0
+        return PackedEvents(None, None, buf["tbase"][:n_blocks], offsets, 3, _bits(self.W), _bits(self.H), 6, rec3=buf["rec3"][:192 * n_blocks],
+                            esc_prefix=buf["esc_prefix"][:n_blocks + 1], esc_dt=buf["esc_dt"][:max(n_esc, 1)])
+
+
 def pack_host(x, y, t, p, offsets, H, W, fmt=None, pin=False, native=True, threads=0, zero_as_negative=False):
     """SoA numpy events of a CSR batch -> PackedEvents, or None when the stream fits none of the formats (sparse or unsorted
     streams: upload the SoA arrays instead).  fmt: 3, 4, 6 or None (= the smallest that fits).  Format 3 is written by the

@@ -249,3 +249,31 @@ def test_zero_as_negative_lets_01_streams_use_the_three_byte_format():
         _same(want, got)
     x, y, t, p = packed.unpack_numpy(got)
     assert np.array_equal(p, mapped) and np.array_equal(x, b["x"]) and np.array_equal(y, b["y"])
+
+
+def test_host_packer_reuses_its_buffers():
+    """packed.HostPacker: buffers allocated once, handed out round robin; every batch equals pack_host's bytes."""
+    from event_representation_study_b200 import packed
+    H, W = 240, 304
+    hp = packed.HostPacker(max_events=20_000, max_windows=4, H=H, W=W, pin=False, slots=2, threads=1, escape_fraction=1.0)  # sparse test streams
+    seen = []
+    for k, sizes in enumerate(([5000, 0, 70], [64], [9000, 9000], [1, 2, 3, 4])):
+        wins, b = _batch(sizes, H, W, 40 + k, duration_us=20_000)
+        pk = hp.pack(b["x"], b["y"], b["t"], b["p"], b["offsets"])
+        _same(packed.pack_host(b["x"], b["y"], b["t"], b["p"], b["offsets"], H, W, fmt=3, native=False), pk)
+        seen.append(pk.rec3.data_ptr())
+    assert seen[0] == seen[2] and seen[1] == seen[3] and seen[0] != seen[1]  # two slots, alternating
+    wins, b = _batch([30_000], H, W, 50)
+    with pytest.raises(ValueError):
+        hp.pack(b["x"], b["y"], b["t"], b["p"], b["offsets"])               # beyond the capacity it was built for
+    wins, b = _batch([300], H, W, 51, polarity="01")
+    with pytest.raises(TypeError):
+        hp.pack(b["x"].astype(np.int64), b["y"], b["t"], b["p"], b["offsets"])
+    assert hp.pack(b["x"], b["y"], b["t"], b["p"], b["offsets"]) is None    # zeros do not fit one polarity bit ...
+    hz = packed.HostPacker(1000, 1, H, W, pin=False, zero_as_negative=True, escape_fraction=1.0)
+    assert hz.pack(b["x"], b["y"], b["t"], b["p"], b["offsets"]).fmt == 3    # ... unless the caller says they are the negatives
+    sparse = packed.HostPacker(1000, 1, H, W, pin=False, escape_fraction=0.0)
+    wins, b = _batch([900], H, W, 52, duration_us=3_000_000_000)
+    if (np.diff(b["t"].astype(np.int64)) > 2).sum() > 1024:
+        with pytest.raises(ValueError):
+            sparse.pack(b["x"], b["y"], b["t"], b["p"], b["offsets"])
