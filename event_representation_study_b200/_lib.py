@@ -64,6 +64,8 @@ SIGNATURES = {
     "evrep_unpack_events": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "evrep_unpack_delta_workspace_bytes": (_sz, [_i]),
     "evrep_pack_delta_host_blocks": (_i64, [_vp, _i]),
+    "evrep_pack_host_blocks": (_i64, [_vp, _i, _i]),
+    "evrep_pack_events_host": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i]),
     "evrep_pack_events_delta_host": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i64, _vp, _i, _i]),
     "evrep_unpack_events_delta": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "evrep_transport_plan_host": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),

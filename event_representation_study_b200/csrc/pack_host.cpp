@@ -270,3 +270,125 @@ extern "C" int evrep_pack_events_delta_host(const uint16_t* x, const uint16_t* y
   if (run > 0) parallel_blocks(j, n_blocks, n_threads, true);
   return EVREP_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// formats 4 and 6 (the loader's half of evrep_unpack_events): one 32-bit word per event - x, y, a 2-bit polarity code and, in
+// format 4, the offset to the smallest timestamp of the event's block of 64 - or that word plus a 16-bit offset (format 6,
+// blocks of 256).  Any event order, any polarity in {-1, 0, 1}.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct WordJob {
+  const uint16_t* x;
+  const uint16_t* y;
+  const void* t;
+  int t_bytes;
+  const int8_t* p;
+  const int64_t* offs;
+  const int64_t* blk_prefix;
+  int B, H, W, xb, yb, fmt, bs;
+  uint32_t* word;
+  uint16_t* dt16;
+  int32_t* tbase;
+  std::atomic<int> status{0};  // bit 0 offset too large for the format, bit 1 polarity outside {-1, 0, 1}, bit 2 pixel outside, bit 3 base outside int32
+};
+
+template <typename TT>
+void word_blocks_t(WordJob& j, int64_t b0, int64_t b1) {
+  const uint16_t* __restrict__ x = j.x;
+  const uint16_t* __restrict__ y = j.y;
+  const TT* __restrict__ t = (const TT*)j.t;
+  const int8_t* __restrict__ p = j.p;
+  const int64_t* __restrict__ offs = j.offs;
+  const int64_t* __restrict__ blk_prefix = j.blk_prefix;
+  uint32_t* __restrict__ word = j.word;
+  uint16_t* __restrict__ dt16 = j.dt16;
+  const uint32_t Wd = (uint32_t)j.W, Hd = (uint32_t)j.H;
+  const int xb = j.xb, bs = j.bs, fmt = j.fmt;
+  const uint32_t sh_p = (uint32_t)(j.xb + j.yb), sh_t = sh_p + 2u;
+  const int64_t limit = fmt == 4 ? ((int64_t)1 << (30 - j.xb - j.yb)) : 65536;
+  int w = (int)(std::upper_bound(blk_prefix, blk_prefix + j.B + 1, b0) - blk_prefix) - 1;
+  int bad = 0;
+  for (int64_t b = b0; b < b1; ++b) {
+    while (b >= blk_prefix[w + 1]) ++w;
+    const int64_t ws = offs[w], we = offs[w + 1];
+    const int64_t e0 = ws + ((b - blk_prefix[w]) << bs), e1 = std::min(e0 + ((int64_t)1 << bs), we);
+    const int64_t t_first = (int64_t)t[ws];
+    int64_t lo = (int64_t)t[e0];
+    for (int64_t i = e0 + 1; i < e1; ++i) lo = std::min(lo, (int64_t)t[i]);
+    const int64_t base = lo - t_first;
+    if (base < -((int64_t)1 << 31) || base >= ((int64_t)1 << 31)) bad |= 8;
+    j.tbase[b] = (int32_t)base;
+    for (int64_t i = e0; i < e1; ++i) {
+      const int64_t d = (int64_t)t[i] - lo;
+      const uint32_t xi = x[i], yi = y[i];
+      const int pi = p[i];
+      bad |= (d >= limit) | ((pi < -1 || pi > 1) << 1) | ((xi >= Wd || yi >= Hd) << 2);
+      uint32_t v = xi | (yi << xb) | (((uint32_t)pi & 3u) << sh_p);
+      if (fmt == 4) v |= (uint32_t)d << sh_t;
+      else dt16[i] = (uint16_t)d;
+      word[i] = v;
+    }
+  }
+  if (bad) j.status.fetch_or(bad);
+}
+
+}  // namespace
+
+extern "C" int64_t evrep_pack_host_blocks(const int64_t* win_offsets, int B, int fmt) {
+  if (!win_offsets || B < 0 || (fmt != 3 && fmt != 4 && fmt != 6)) return -1;
+  const int bs = fmt == 6 ? 8 : 6;
+  int64_t nb = 0;
+  for (int b = 0; b < B; ++b) {
+    const int64_t n = win_offsets[b + 1] - win_offsets[b];
+    if (n < 0) return -1;
+    nb += (n + ((int64_t)1 << bs) - 1) >> bs;
+  }
+  return nb;
+}
+
+extern "C" int evrep_pack_events_host(const uint16_t* x, const uint16_t* y, const void* t, int t_bytes, const int8_t* p, const int64_t* win_offsets, int B,
+                                      int H, int W, int fmt, uint32_t* word, uint16_t* dt16, int32_t* tbase, int n_threads) {
+  using evrep::set_error;
+  if (B < 0 || !win_offsets || (t_bytes != 4 && t_bytes != 8) || H < 1 || W < 1 || (fmt != 4 && fmt != 6)) { set_error("bad argument"); return EVREP_EINVAL; }
+  const int xb = bits_for(W), yb = bits_for(H);
+  if (fmt == 4 && xb + yb > 29) { set_error("wire format 4 holds x, y, the polarity code and a time offset in 32 bits; %d x %d leaves no room", W, H); return EVREP_EUNSUPPORTED; }
+  if (xb + yb > 30) { set_error("sensor %d x %d does not fit a 32-bit event word", W, H); return EVREP_EUNSUPPORTED; }
+  const int bs = fmt == 6 ? 8 : 6;
+  std::vector<int64_t> blk_prefix((size_t)B + 1, 0);
+  for (int b = 0; b < B; ++b) {
+    const int64_t n = win_offsets[b + 1] - win_offsets[b];
+    if (n < 0 || win_offsets[b] < 0) { set_error("win_offsets must be non-decreasing and non-negative"); return EVREP_EINVAL; }
+    blk_prefix[(size_t)b + 1] = blk_prefix[(size_t)b] + ((n + ((int64_t)1 << bs) - 1) >> bs);
+  }
+  const int64_t n_blocks = blk_prefix[(size_t)B];
+  const int64_t total = B ? win_offsets[B] : 0;
+  if (total > 0 && (!x || !y || !t || !p || !word || !tbase || (fmt == 6 && !dt16))) { set_error("null event / output array"); return EVREP_EINVAL; }
+  WordJob j;
+  j.x = x; j.y = y; j.t = t; j.t_bytes = t_bytes; j.p = p; j.offs = win_offsets; j.blk_prefix = blk_prefix.data();
+  j.B = B; j.H = H; j.W = W; j.xb = xb; j.yb = yb; j.fmt = fmt; j.bs = bs;
+  j.word = word; j.dt16 = dt16; j.tbase = tbase;
+  if (n_threads < 1) n_threads = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+  auto run = [&j](int64_t b0, int64_t b1) {
+    if (j.t_bytes == 4) word_blocks_t<int32_t>(j, b0, b1);
+    else word_blocks_t<int64_t>(j, b0, b1);
+  };
+  if (n_threads <= 1 || n_blocks < 4096) {
+    run(0, n_blocks);
+  } else {
+    std::vector<std::thread> th;
+    const int64_t per = (n_blocks + n_threads - 1) / n_threads;
+    for (int k = 0; k < n_threads; ++k) {
+      const int64_t b0 = k * per, b1 = std::min(n_blocks, b0 + per);
+      if (b0 >= b1) break;
+      th.emplace_back([&run, b0, b1] { run(b0, b1); });
+    }
+    for (auto& t_ : th) t_.join();
+  }
+  const int bad = j.status.load();
+  if (bad & 4) { set_error("event outside the sensor"); return EVREP_EINVAL; }
+  if (bad & 2) { set_error("polarities must be in {-1, 0, 1}"); return EVREP_EINVAL; }
+  if (bad & 1) { set_error("a block spans more time than wire format %d holds", fmt); return EVREP_EUNSUPPORTED; }
+  if (bad & 8) { set_error("a block starts 2^31 us or more from its window's first event"); return EVREP_EUNSUPPORTED; }
+  return EVREP_OK;
+}

@@ -153,6 +153,45 @@ def _pack3_native(x, y, t, p, offsets, H, W, pin, threads, zero_as_negative=Fals
                         esc_prefix=esc_prefix[:n_blocks + 1], esc_dt=esc_dt[:max(n_esc, 1)])
 
 
+def _native_arrays(x, y, t, p, total):
+    """The arrays as the library's host encoders read them (no copies), or None when they are in another layout"""
+    out = []
+    for v, kinds in ((x, (np.uint16, np.int16)), (y, (np.uint16, np.int16)), (t, (np.int32, np.int64)), (p, (np.int8,))):
+        v = np.asarray(v)
+        if v.dtype.type not in kinds or not v.flags.c_contiguous or len(v) < total:
+            return None
+        out.append(v)
+    return out
+
+
+def _pack_words_native(x, y, t, p, offsets, H, W, f, pin, threads):
+    """Formats 4 / 6 through evrep_pack_events_host (byte-identical to the numpy passes of pack_host) -> PackedEvents, None when
+    the stream does not fit the format, NotImplemented when the arrays are in another layout."""
+    total, B = int(offsets[-1]), len(offsets) - 1
+    arrs = _native_arrays(x, y, t, p, total)
+    if arrs is None:
+        return NotImplemented
+    x, y, t, p = arrs
+    n_blocks = int(lib.evrep_pack_host_blocks(offsets.ctypes.data, B, f))
+    if n_blocks < 0:
+        return NotImplemented
+    mk = (lambda n, dt: torch.empty(max(n, 1), dtype=dt).pin_memory()) if pin else (lambda n, dt: torch.empty(max(n, 1), dtype=dt))
+    word, tbase = mk(total, torch.int32), mk(n_blocks, torch.int32)
+    dt16 = mk(total, torch.int16) if f == 6 else None
+    rc = lib.evrep_pack_events_host(x.ctypes.data, y.ctypes.data, t.ctypes.data, t.dtype.itemsize, p.ctypes.data, offsets.ctypes.data, B, H, W, f,
+                                    word.data_ptr(), dt16.data_ptr() if dt16 is not None else None, tbase.data_ptr(), int(threads))
+    if rc == _EUNSUPPORTED:
+        return None
+    if rc == _EINVAL:
+        msg = lib.evrep_last_error()
+        if b"outside the sensor" in msg:
+            raise IndexError("event outside the sensor")
+        if b"polarities" in msg:
+            raise ValueError("polarities must be in {-1, 0, 1}")
+    check(rc)
+    return PackedEvents(word[:total], dt16[:total] if dt16 is not None else None, tbase[:n_blocks], offsets, f, _bits(W), _bits(H), BLOCK_SHIFT[f])
+
+
 class HostPacker:
     """Format-3 encoder with its output buffers allocated ONCE (pinned, if asked): what a loader thread calls per batch.
     `pack_host(pin=True)` pins fresh buffers on every call, and cudaHostAlloc costs milliseconds; this object keeps `slots`
@@ -202,31 +241,35 @@ class HostPacker:
 
 def pack_host(x, y, t, p, offsets, H, W, fmt=None, pin=False, native=True, threads=0, zero_as_negative=False):
     """SoA numpy events of a CSR batch -> PackedEvents, or None when the stream fits none of the formats (sparse or unsorted
-    streams: upload the SoA arrays instead).  fmt: 3, 4, 6 or None (= the smallest that fits).  Format 3 is written by the
-    library's host encoder when the arrays are uint16 / int16 x, y, int32 / int64 t and int8 p (native=False: the numpy
-    passes, ~30 x slower, kept as the restatement the tests hold the encoder to); threads: host threads of that encoder
+    streams: upload the SoA arrays instead).  fmt: 3, 4, 6 or None (= the smallest that fits).  The library's host encoders
+    write every format when the arrays are uint16 / int16 x, y, int32 / int64 t and int8 p (native=False: the numpy
+    passes, ~30 x slower, kept as the restatement the tests hold the encoders to); threads: host threads of that encoder
     (0 = as many as the machine has, at most 16).  zero_as_negative: format 3 has one polarity bit; with this flag a {0, 1} stream
     fits it too - p == 0 travels as "negative" and comes back as -1, which every representation here treats like 0 when the window
     holds no -1 (operations.py:59-61) - instead of falling back to the 4-byte format (formats 4 / 6 keep the 0: they are lossless)."""
     offsets = np.ascontiguousarray(offsets, np.int64)
     total = int(offsets[-1])
-    if native and fmt in (None, 3):
+    arrs = _native_arrays(x, y, t, p, total) if native else None
+    if arrs is not None:  # the library's host encoders, smallest format first; they read the arrays as they are
         try:
-            pk3 = _pack3_native(x, y, t, p, offsets, H, W, pin, threads, zero_as_negative)
+            if total and (arrs[3][:total].min() < -1 or arrs[3][:total].max() > 1):
+                raise ValueError("polarities must be in {-1, 0, 1}")
+            for f in ((fmt,) if fmt else (3, 4, 6)):
+                if f == 3:
+                    pk = _pack3_native(*arrs, offsets, H, W, pin, threads, zero_as_negative)
+                else:
+                    pk = _pack_words_native(*arrs, offsets, H, W, f, pin, threads)
+                if pk is NotImplemented:
+                    break
+                if pk is not None:
+                    return pk
+            else:
+                return None
         except (IndexError, ValueError):
             raise
         except Exception as e:  # e.g. pinned memory unavailable: the numpy passes below write the same bytes
             import warnings
             warnings.warn(f"native event packer unavailable ({type(e).__name__}: {e}); packing with numpy")
-            pk3 = NotImplemented
-        if pk3 is not NotImplemented:
-            if pk3 is not None or fmt == 3:
-                return pk3
-            fmt_rest = (4, 6)
-        else:
-            fmt_rest = None
-    else:
-        fmt_rest = None
     x = np.asarray(x)[:total].astype(np.uint32)
     y = np.asarray(y)[:total].astype(np.uint32)
     if total and (x.max() >= W or y.max() >= H):
@@ -239,13 +282,13 @@ def pack_host(x, y, t, p, offsets, H, W, fmt=None, pin=False, native=True, threa
     t64 = np.asarray(t)[:total].astype(np.int64)
     first = np.repeat(t64[offsets[:-1][n > 0]], n[n > 0]) if total else np.zeros(0, np.int64)
     rel = t64 - first
-    for f in ((fmt,) if fmt else (fmt_rest or (3, 4, 6))):
+    for f in ((fmt,) if fmt else (3, 4, 6)):
         if f == 3:
             pk3 = _pack3(x, y, np.where(p8 == 0, np.int8(-1), p8) if zero_as_negative else p8, rel, offsets, xb, yb, pin)
             if pk3 is not None:
                 return pk3
             continue
-        if f == 4 and xb + yb > 29:
+        if (f == 4 and xb + yb > 29) or xb + yb > 30:  # no room for the time offset / for the polarity code in a 32-bit word
             continue
         bs = BLOCK_SHIFT[f]
         nb = (n + (1 << bs) - 1) >> bs

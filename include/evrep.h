@@ -434,6 +434,14 @@ int evrep_est_backward_batched(const uint16_t* x, const uint16_t* y, const float
  * alike - every representation of this library does when a window holds no -1 (operations.py:59-61, the p > 0 tests of
  * event_stack.py / time_surface.py) - at the price of not being able to tell them apart afterwards. */
 int64_t evrep_pack_delta_host_blocks(const int64_t* win_offsets, int B);
+/* The same for wire formats 4 and 6 (the loader's half of evrep_unpack_events): word (one uint32 per event), dt16 (one uint16 per
+ * event, format 6 only) and tbase (one int32 per block of 64 / 256 events; evrep_pack_host_blocks gives the count).  Any event
+ * order, polarities in {-1, 0, 1}; EVREP_EUNSUPPORTED when a block spans more time than the format holds
+ * (2^(30 - bits(W) - bits(H)) us in format 4, 65536 us in format 6). */
+int64_t evrep_pack_host_blocks(const int64_t* win_offsets, int B, int fmt);
+int evrep_pack_events_host(const uint16_t* x, const uint16_t* y, const void* t, int t_bytes, const int8_t* p,
+                           const int64_t* win_offsets, int B, int H, int W, int fmt, uint32_t* word, uint16_t* dt16,
+                           int32_t* tbase, int n_threads);
 int evrep_pack_events_delta_host(const uint16_t* x, const uint16_t* y, const void* t, int t_bytes, const int8_t* p,
                                  const int64_t* win_offsets, int B, int H, int W, uint8_t* rec3, int32_t* tbase,
                                  uint32_t* esc_prefix, uint32_t* esc_dt, int64_t esc_capacity, int64_t* n_escapes, int zero_is_negative,

@@ -277,3 +277,58 @@ def test_host_packer_reuses_its_buffers():
     if (np.diff(b["t"].astype(np.int64)) > 2).sum() > 1024:
         with pytest.raises(ValueError):
             sparse.pack(b["x"], b["y"], b["t"], b["p"], b["offsets"])
+
+
+@pytest.mark.parametrize("fmt,sizes,dur,polarity,t_dtype,threads,shuffle", [
+    (4, [5000, 0, 64, 65, 1, 12345], 2_000, "pm1", np.int32, 1, False),
+    (4, [30000, 7], 30_000, "01", np.int64, 1, True),          # any order, zeros kept
+    (6, [5000, 0, 256, 257, 1, 12345], 50_000, "01", np.int32, 1, True),
+    (6, [300_000, 300_001, 0, 5], 300_000, "pm1", np.int32, 4, False),  # > 4096 blocks: the threaded path
+    (4, [], 1000, "pm1", np.int32, 1, False),
+])
+def test_native_word_encoders_equal_the_numpy_packer(fmt, sizes, dur, polarity, t_dtype, threads, shuffle):
+    """evrep_pack_events_host (formats 4 / 6) against the numpy passes of pack_host: same words, offsets and block bases"""
+    import torch
+    from event_representation_study_b200 import packed
+    from event_representation_study_b200.synth import pack_batch
+    H, W = 240, 304
+    wins, b = _batch(sizes, H, W, 61, polarity=polarity, duration_us=dur)
+    if not sizes:
+        b = pack_batch([])
+    t = b["t"].astype(t_dtype) if len(b["t"]) else np.zeros(0, t_dtype)
+    if shuffle and len(t) > 10:  # events out of order inside a block: these formats do not care
+        t[3], t[9] = t[9], t[3]
+    ref = packed.pack_host(b["x"], b["y"], t, b["p"], b["offsets"], H, W, fmt=fmt, native=False)
+    nat = packed.pack_host(b["x"], b["y"], t, b["p"], b["offsets"], H, W, fmt=fmt, native=True, threads=threads)
+    assert (ref is None) == (nat is None)
+    if ref is None:
+        return
+    assert ref.fmt == nat.fmt == fmt and ref.block_shift == nat.block_shift and ref.x_bits == nat.x_bits
+    assert torch.equal(ref.word, nat.word) and torch.equal(ref.tbase, nat.tbase)
+    assert (ref.dt16 is None) == (nat.dt16 is None) and (ref.dt16 is None or torch.equal(ref.dt16, nat.dt16))
+    if int(b["offsets"][-1]):
+        x, y, tt, p = packed.unpack_numpy(nat)
+        assert np.array_equal(x, b["x"]) and np.array_equal(p, b["p"])
+
+
+def test_native_word_encoders_refuse_like_the_numpy_packer():
+    from event_representation_study_b200 import packed
+    H, W = 240, 304
+    wins, b = _batch([4000], H, W, 62, duration_us=300_000_000)  # 75 ms between events
+    for native in (True, False):
+        assert packed.pack_host(b["x"], b["y"], b["t"], b["p"], b["offsets"], H, W, fmt=4, native=native) is None
+        assert packed.pack_host(b["x"], b["y"], b["t"], b["p"], b["offsets"], H, W, fmt=6, native=native) is None
+    bad_p = b["p"].copy()
+    bad_p[3] = 2
+    for native in (True, False):
+        with pytest.raises(ValueError):
+            packed.pack_host(b["x"], b["y"], b["t"], bad_p, b["offsets"], H, W, native=native)
+    bad_y = b["y"].copy()
+    bad_y[0] = H
+    for native in (True, False):
+        with pytest.raises(IndexError):
+            packed.pack_host(b["x"], bad_y, b["t"], b["p"], b["offsets"], H, W, fmt=4, native=native)
+    # a sensor too large for format 4: the chain moves on to format 6 in both paths
+    big_n = packed.pack_host(np.array([4000], np.uint16), np.array([3000], np.uint16), np.array([5], np.int32), np.array([0], np.int8), np.array([0, 1]), 40000, 50000)
+    big_r = packed.pack_host(np.array([4000], np.uint16), np.array([3000], np.uint16), np.array([5], np.int32), np.array([0], np.int8), np.array([0, 1]), 40000, 50000, native=False)
+    assert (big_n is None) == (big_r is None) and (big_n is None or big_n.fmt == big_r.fmt)
