@@ -332,3 +332,27 @@ def test_native_word_encoders_refuse_like_the_numpy_packer():
     big_n = packed.pack_host(np.array([4000], np.uint16), np.array([3000], np.uint16), np.array([5], np.int32), np.array([0], np.int8), np.array([0, 1]), 40000, 50000)
     big_r = packed.pack_host(np.array([4000], np.uint16), np.array([3000], np.uint16), np.array([5], np.int32), np.array([0], np.int8), np.array([0, 1]), 40000, 50000, native=False)
     assert (big_n is None) == (big_r is None) and (big_n is None or big_n.fmt == big_r.fmt)
+
+
+def test_pinned_branches_of_the_packers(monkeypatch):
+    """pin=True takes its own allocation branch in every packer (buffers pinned first, filled through their pointers); with
+    pin_memory replaced by a copy - there is no CUDA here - the results must equal the pageable ones."""
+    import torch
+    from event_representation_study_b200 import packed
+    calls = []
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: calls.append(self.numel()) or self.clone())
+    H, W = 240, 304
+    wins, b = _batch([5000, 0, 300], H, W, 71, duration_us=20_000)
+    for fmt in (3, 4, 6):
+        for native in (True, False):
+            a = packed.pack_host(b["x"], b["y"], b["t"], b["p"], b["offsets"], H, W, fmt=fmt, native=native, pin=True)
+            c = packed.pack_host(b["x"], b["y"], b["t"], b["p"], b["offsets"], H, W, fmt=fmt, native=native, pin=False)
+            assert a is not None and c is not None and a.fmt == c.fmt == fmt
+            for k in ("word", "dt16", "tbase", "rec3", "esc_prefix", "esc_dt"):
+                u, v = getattr(a, k), getattr(c, k)
+                assert (u is None) == (v is None) and (u is None or torch.equal(u, v)), (fmt, native, k)
+            parts = a.host_parts(0, 3)
+            assert all(v.numel() > 0 for v in parts.values())
+    hp = packed.HostPacker(10_000, 3, H, W, pin=True, escape_fraction=1.0)
+    _same(hp.pack(b["x"], b["y"], b["t"], b["p"], b["offsets"]), packed.pack_host(b["x"], b["y"], b["t"], b["p"], b["offsets"], H, W, fmt=3, native=False))
+    assert len(calls) > 10
